@@ -1,0 +1,124 @@
+/* groove_b200.h — C ABI of the B200-native Transformer Groove Infilling hot path.
+ *
+ * The reference (pelinski/TransformerGrooveInfilling) has no FFI: its hot path is pure PyTorch
+ * eager code.  Each entry point below therefore cites the reference *Python* interface whose
+ * arithmetic it replaces (paths relative to the reference root; BGT = BaseGrooveTransformers).
+ * The reference-side binding a maintainer would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the caller (PyTorch) owns all buffers; the library borrows them for the duration of the
+ *     enqueue and keeps no reference;
+ *   - every call enqueues asynchronously on the cudaStream_t passed as `stream` (void* here);
+ *   - return value 0 = success; non-zero = error, message via gt_last_error() (thread-local);
+ *     no C++ exception crosses this boundary; shape / alignment violations are rejected before
+ *     any launch;
+ *   - all tensors are float32, row-major, batch-first: src [n_seq,32,e_src], y/hvo [n_seq,32,27].
+ */
+#ifndef GROOVE_B200_H
+#define GROOVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GT_ABI_VERSION 1
+#define GT_T_STEPS 32          /* train.py:128 `max_len: 32`; BGT/models/utils.py:49 requires T == max_len */
+
+/* precision modes */
+#define GT_PREC_FP32 0         /* fp32 SIMT arithmetic everywhere (the 1e-4 "fp32/TF32" parity mode) */
+#define GT_PREC_BF16 1         /* bf16 operands / fp32 accumulate on tcgen05 tensor cores (2e-3 mode) */
+
+/* Mirrors the constructor arguments of GrooveTransformerEncoder / GrooveTransformer
+ * (BGT/models/transformer.py:10-11, :87-88) and params["model"] of train.py:115-143. */
+typedef struct gt_config {
+  int32_t d_model;
+  int32_t nhead;
+  int32_t dim_ff;
+  int32_t n_enc;       /* num_encoder_layers */
+  int32_t n_dec;       /* num_decoder_layers; 0 = encoder-only model */
+  int32_t e_src;       /* embedding_size_src (16 MSO / 27 symbolic) */
+  int32_t e_tgt;       /* embedding_size_tgt (27 = 9 voices x h,v,o) */
+  int32_t precision;   /* GT_PREC_* */
+  float   dropout;     /* p of every nn.Dropout on the path */
+  int32_t reserved;
+} gt_config;
+
+int         gt_version(void);
+const char *gt_last_error(void);
+
+/* Flat fp32 parameter vector.  Tensors appear in the reference's state_dict order with the `pe`
+ * buffers skipped (enumerated in SURVEY.md §8b); each tensor starts on a 16-byte boundary.
+ * gt_param_layout writes up to `max_entries` (offset,size) pairs in floats and returns the number
+ * of tensors (or a negative error). */
+int64_t gt_param_count(const gt_config *cfg);
+int     gt_param_layout(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int max_entries);
+
+/* Scratch the caller must provide.  mode 0 = inference (ping-pong buffers only),
+ * 1 = training (activations saved for backward). */
+int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode);
+
+/* Forward pass: BGT/models/transformer.py:108-115 (encoder-only: InputLayer -> Encoder -> OutputLayer)
+ * and :35-46 (encoder-decoder; tgt_in is the already right-shifted target, BGT/models/train.py:130-131).
+ * hvo[n,32,27] receives channels 0-8 raw hit logits, 9-17 sigmoid, 18-26 0.5*tanh
+ * (BGT/models/io_layers.py:36-48).  train!=0 applies dropout (counter-based masks keyed by
+ * seed/step/global sequence index seq0+n) and saves activations in `ws` for gt_backward. */
+int gt_forward(const gt_config *cfg, const float *params, const float *pe,
+               const float *src, const float *tgt_in, int64_t n_seq,
+               float *hvo, void *ws, int64_t ws_bytes,
+               int train, uint64_t seed, uint64_t step, int64_t seq0, void *stream);
+
+/* Backward of gt_forward(train=1) — what `loss.backward()` does at BGT/models/train.py:138.
+ * hvo is the output gt_forward produced; d_hvo[n,32,27] is the gradient w.r.t. those ACTIVATED
+ * outputs; gradients are ACCUMULATED (+=)
+ * into the flat `grads` vector (same layout as params).  d_src / d_tgt_in are not produced. */
+int gt_backward(const gt_config *cfg, const float *params, const float *pe,
+                const float *src, const float *tgt_in, int64_t n_seq,
+                const float *hvo, const float *d_hvo, float *grads, void *ws, int64_t ws_bytes,
+                uint64_t seed, uint64_t step, int64_t seq0, void *stream);
+
+/* calculate_loss, BGT/models/train.py:9-40.  metrics6 = {total, hit_accuracy, hit_perplexity,
+ * bce_hits, mse_velocities, mse_offsets}.  If d_hvo != NULL it receives grad_scale * dLoss/d(hvo).
+ * `partials` is scratch of gt_loss_scratch_floats(n_seq) floats (two-stage deterministic sum). */
+int64_t gt_loss_scratch_floats(int64_t n_seq);
+int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty,
+            float *metrics6, float *d_hvo, float grad_scale, float *partials, void *stream);
+
+/* One fused training step body (BGT/models/train.py:126-138 without the optimizer): forward with
+ * dropout, loss + metrics, backward.  `grads` is ZEROED first, then holds dLoss/dparams.
+ * For n_dec>0 the shifted target is built internally from y (train.py:130-131). */
+int gt_train_step(const gt_config *cfg, const float *params, const float *pe,
+                  const float *src, const float *y, int64_t n_seq, float hit_loss_penalty,
+                  float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,
+                  uint64_t seed, uint64_t step, int64_t seq0, void *stream);
+
+/* predict(): BGT/models/transformer.py:117-125 (encoder-only: forward + threshold) and :48-83
+ * (encoder-decoder: 32-step autoregressive loop feeding back thresholded hits and raw v,o).
+ * hvo_out[n,32,27] channels 0-8 are 0.0/1.0 hits (BGT/models/utils.py:59-69, threshold path only). */
+int gt_predict(const gt_config *cfg, const float *params, const float *pe,
+               const float *src, int64_t n_seq, float thres,
+               float *hvo_out, void *ws, int64_t ws_bytes, void *stream);
+
+/* torch.optim.SGD(lr).step() / torch.optim.Adam(lr).step() as called at BGT/models/train.py:141,
+ * over the flat vectors.  g is multiplied by grad_scale first (1/world after an all-reduce SUM).
+ * `step` for Adam is 1-based. */
+int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale, void *stream);
+int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
+                 float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
+
+/* Test hook: fills keep[i] = 1/0 for element indices idx0..idx0+n-1 of dropout site `site`
+ * (the generator restated in oracle/groove_oracle.py:dropout_keep). */
+int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p,
+                          int64_t idx0, int64_t n, uint8_t *keep, void *stream);
+
+/* Stand-alone tcgen05 tile GEMM used by the unit tests of the tensor-core engine:
+ * D[M,N] = A[M,K] (bf16 bits) * B[N,K]^T (bf16 bits), fp32 out; M multiple of 128. */
+int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k,
+                     int variant, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROOVE_B200_H */

@@ -20,27 +20,17 @@ import torch
 sys.dont_write_bytecode = True
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-sys.path.insert(0, "/root/reference")
+sys.path.insert(0, "/root/reference")          # the UNMODIFIED reference; must shadow the repo's alias package
 warnings.filterwarnings("ignore")
 
 import groove_oracle as G  # noqa: E402
+from golden_cases import CASES, digest  # noqa: E402
 from BaseGrooveTransformers.models.transformer import GrooveTransformerEncoder, GrooveTransformer  # noqa: E402
 from BaseGrooveTransformers.models.train import calculate_loss  # noqa: E402
+import BaseGrooveTransformers as _ref  # noqa: E402
+assert _ref.__file__.startswith("/root/reference/"), "make_golden must run against the real reference"
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
-
-# name -> (cfg, batch, hit_loss_penalty, lr).  Hyper-parameters follow the yamls named in
-# BASELINE.json (C1..C5); layer counts are reduced for the d=256 cases to keep the
-# fixtures small — the per-layer arithmetic is identical.
-CASES = {
-    "c1_closedhh_testing": (G.GrooveCfg(32, 4, 16, 6, 0, 16, 27), 5, 0.47, 0.094),
-    "c2_closedhh":         (G.GrooveCfg(32, 16, 512, 6, 0, 16, 27), 4, 0.38, 0.07),
-    "c3_kicksnares_l2":    (G.GrooveCfg(256, 2, 512, 2, 0, 16, 27), 3, 0.73, 0.089),
-    "c4_random_large_l2":  (G.GrooveCfg(256, 16, 64, 2, 0, 16, 27), 3, 1.0, 0.04),
-    "c5_symbolic_encdec":  (G.GrooveCfg(32, 16, 512, 2, 2, 27, 27), 4, 0.38, 0.07),
-    "odd_small_encdec":    (G.GrooveCfg(24, 3, 40, 1, 1, 16, 27), 2, 0.5, 0.05),
-}
-
 
 def build_ref(cfg):
     if cfg.n_dec > 0:
@@ -56,13 +46,6 @@ def build_ref(cfg):
         sd[k] = v.clone()
     m.load_state_dict(sd, strict=True)
     return m, P
-
-
-def digest(t: torch.Tensor, tag: int):
-    """(dot with a fixed pseudo-random vector, L2 norm) — compact and discriminating."""
-    r = torch.from_numpy(G.det_uniform(900 + tag, t.numel(), -1, 1)).double()
-    td = t.detach().double().reshape(-1)
-    return np.array([float(td @ r), float(td.norm())])
 
 
 def run_case(name, cfg, n, penalty, lr):

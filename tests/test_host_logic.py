@@ -1,0 +1,129 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, parameter layout and
+state_dict compatibility, optimizer state layout, the drop-in import paths, error behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import groove_oracle as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "groove_b200.h")).read()
+    declared = set(re.findall(r"\b(gt_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        getattr(lib, name)
+    assert lib.gt_version() == 1
+
+
+def test_param_layout_matches_reference_state_dict_order():
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    for cfg in (G.GrooveCfg(32, 16, 512, 6, 0, 16, 27), G.GrooveCfg(24, 3, 40, 2, 3, 27, 27)):
+        c = _lib.GtConfig(cfg.d_model, cfg.nhead, cfg.dim_ff, cfg.n_enc, cfg.n_dec, cfg.e_src, cfg.e_tgt, 0, 0.0, 0)
+        shapes = G.param_shapes(cfg)
+        offs, sizes = (C.c_int64 * len(shapes))(), (C.c_int64 * len(shapes))()
+        assert lib.gt_param_layout(C.byref(c), offs, sizes, len(shapes)) == len(shapes)
+        assert [int(s) for s in sizes] == [int(np.prod(s)) for _, s in shapes]
+        assert all(int(o) % 4 == 0 for o in offs) and list(offs) == sorted(offs)
+        assert lib.gt_param_count(C.byref(c)) >= sum(int(s) for s in sizes)
+
+
+def test_invalid_configs_are_rejected_with_messages():
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    bad = _lib.GtConfig(30, 4, 16, 1, 0, 16, 27, 0, 0.0, 0)
+    assert lib.gt_param_count(C.byref(bad)) < 0 and b"divisible" in lib.gt_last_error()
+    bad = _lib.GtConfig(32, 4, 16, 1, 0, 16, 26, 0, 0.0, 0)
+    assert lib.gt_workspace_bytes(C.byref(bad), 4, 1) < 0 and b"27" in lib.gt_last_error()
+    ok = _lib.GtConfig(32, 4, 16, 1, 0, 16, 27, 0, 0.0, 0)
+    assert lib.gt_workspace_bytes(C.byref(ok), 0, 1) < 0
+    assert lib.gt_workspace_bytes(C.byref(ok), 8, 1) > lib.gt_workspace_bytes(C.byref(ok), 8, 0) > 0
+    assert lib.gt_sgd_step(None, None, 4, 0.1, 1.0, None) != 0        # null pointers are refused before any launch
+
+
+def test_state_dict_keys_match_reference_demo_checkpoint():
+    from BaseGrooveTransformers.models.transformer import GrooveTransformerEncoder
+    want = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "demo_checkpoint_keys.txt")) if not l.startswith("#")]
+    m = GrooveTransformerEncoder(32, 16, 27, 4, 16, 0.18, 6, 32, "cpu")
+    sd = m.state_dict()
+    assert list(sd) == [w[0] for w in want]
+    for w in want:
+        assert list(sd[w[0]].shape) == [int(v) for v in w[1:]], w[0]
+    np.testing.assert_allclose(sd["InputLayerEncoder.PositionalEncoding.pe"].numpy(), G.positional_table(32).numpy(), atol=1e-7)
+
+
+def test_encdec_state_dict_and_flat_views():
+    from BaseGrooveTransformers.models.transformer import GrooveTransformer
+    cfg = G.GrooveCfg(24, 3, 40, 2, 3, 27, 27)
+    m = GrooveTransformer(24, 27, 27, 3, 40, 0.1, 2, 3, 32, "cpu")
+    names = [k for k, _ in G.param_shapes(cfg)]
+    assert [k for k in m.state_dict() if not k.endswith(".pe")] == names
+    assert [n for n, _ in m.named_parameters()] == names
+    # parameters are views of ONE flat vector: writing through a parameter changes the flat vector
+    with torch.no_grad():
+        m.OutputLayer.Linear.bias.fill_(3.0)
+    assert float(m.flat_parameters().detach()[-28:-1].sum()) == 81.0
+    P = G.det_params(cfg)
+    sd = m.state_dict(); sd.update(P); m.load_state_dict(sd, strict=True)
+    o, s = m._offsets[5]
+    assert torch.equal(m.flat_parameters()[o:o + s].detach().view(P[names[5]].shape), P[names[5]])
+    # reference init: all layers of a stack start identical; in/out layers U(-0.1,0.1) with zero bias
+    m2 = GrooveTransformer(32, 27, 27, 4, 64, 0.1, 3, 2, 32, "cpu")
+    assert torch.equal(m2.Encoder.Encoder.layers[0].linear1.weight, m2.Encoder.Encoder.layers[2].linear1.weight)
+    assert float(m2.OutputLayer.Linear.weight.abs().max()) <= 0.1 and float(m2.OutputLayer.Linear.bias.abs().max()) == 0
+    assert float(m2.Decoder.Decoder.layers[1].norm3.weight.mean()) == 1.0
+
+
+def test_dropin_imports_and_signatures():
+    import inspect
+    from BaseGrooveTransformers import calculate_loss, initialize_model, train_loop
+    assert list(inspect.signature(train_loop).parameters) == [
+        "dataloader", "groove_transformer", "loss_fn", "bce_fn", "mse_fn", "opt", "epoch", "save", "device",
+        "encoder_only", "hit_loss_penalty", "test_inputs", "test_gt", "validation_inputs", "validation_gt"]
+    assert list(inspect.signature(calculate_loss).parameters) == ["prediction", "y", "bce_fn", "mse_fn", "hit_loss_penalty"]
+    params = {"model": dict(encoder_only=1, optimizer="sgd", d_model=32, n_heads=4, dim_feedforward=16, dropout=0.1,
+                            num_encoder_layers=2, num_decoder_layers=0, max_len=32, embedding_size_src=16,
+                            embedding_size_tgt=27, device="cpu"),
+              "training": dict(learning_rate=0.05, batch_size=4), "load_model": None}
+    model, opt, epoch = initialize_model(params)
+    assert epoch == 0 and type(model).__name__ == "GrooveTransformerEncoder"
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["lr"] == 0.05 and sd["param_groups"][0]["params"] == list(range(len(list(model.parameters()))))
+    # the SGD state-dict has the key set of the reference's demo checkpoint optimizer
+    line = [l for l in open(os.path.join(ROOT, "tests", "golden", "demo_checkpoint_keys.txt")) if l.startswith("#")][0]
+    for key in ("dampening", "lr", "momentum", "nesterov", "params", "weight_decay"):
+        assert key in sd["param_groups"][0] and key in line
+    params["model"]["optimizer"] = "adam"; params["model"]["encoder_only"] = 0; params["model"]["num_decoder_layers"] = 1
+    model, opt, _ = initialize_model(params)
+    assert type(model).__name__ == "GrooveTransformer" and type(opt).__name__ == "FusedAdam"
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 32, 16), torch.zeros(1, 32, 27))     # CPU tensors: the product has no CPU path
+
+
+def test_checkpoint_resume_roundtrip(tmp_path):
+    from BaseGrooveTransformers import initialize_model
+    params = {"model": dict(encoder_only=1, optimizer="adam", d_model=16, n_heads=2, dim_feedforward=8, dropout=0.0,
+                            num_encoder_layers=1, num_decoder_layers=0, max_len=32, embedding_size_src=16,
+                            embedding_size_tgt=27, device="cpu"),
+              "training": dict(learning_rate=0.01, batch_size=4), "load_model": None}
+    model, opt, _ = initialize_model(params)
+    opt._t = 3; opt._m.fill_(0.5)
+    torch.save({"epoch": 7, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt.state_dict(), "loss": 1.0},
+               tmp_path / "transformer_run_abc_Epoch_7.Model")
+    params["load_model"] = {"location": "local", "dir": str(tmp_path), "file_pattern": "transformer_run_{}_Epoch_{}.Model"}
+    m2, o2, ep = initialize_model(params)
+    assert ep == 7 and o2._t == 3 and float(o2._m[:64].mean()) == 0.5
+    assert torch.equal(m2.flat_parameters().detach(), model.flat_parameters().detach())
+    params["load_model"]["dir"] = str(tmp_path / "nothing")
+    with pytest.raises(FileNotFoundError):
+        initialize_model(params)

@@ -1,0 +1,7 @@
+"""groove_b200 — B200-native (sm_100a) implementation of the Transformer Groove Infilling training
+and inference step, behind the reference's ``BaseGrooveTransformers`` module API."""
+from .modules import GrooveTransformer, GrooveTransformerEncoder
+from .training import FusedAdam, FusedSGD, calculate_loss, initialize_model, train_loop
+
+__all__ = ["GrooveTransformer", "GrooveTransformerEncoder", "calculate_loss", "initialize_model", "train_loop",
+           "FusedSGD", "FusedAdam"]

@@ -1,0 +1,92 @@
+"""ctypes binding of libgroove_b200.so (C ABI declared in include/groove_b200.h).
+
+The library is the ONLY compute path: there is no CPU / eager fallback.  If it cannot be built or
+loaded, importing the compute entry points raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+PREC_FP32, PREC_BF16 = 0, 1
+T_STEPS = 32
+
+
+class GtConfig(C.Structure):
+    _fields_ = [
+        ("d_model", C.c_int32), ("nhead", C.c_int32), ("dim_ff", C.c_int32), ("n_enc", C.c_int32),
+        ("n_dec", C.c_int32), ("e_src", C.c_int32), ("e_tgt", C.c_int32), ("precision", C.c_int32),
+        ("dropout", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_u64 = C.c_uint64
+_f = C.c_float
+_cfgp = C.POINTER(GtConfig)
+
+# name -> (restype, argtypes); must list every symbol include/groove_b200.h declares
+SIGNATURES = {
+    "gt_version": (C.c_int, []),
+    "gt_last_error": (C.c_char_p, []),
+    "gt_param_count": (_i64, [_cfgp]),
+    "gt_param_layout": (C.c_int, [_cfgp, C.POINTER(_i64), C.POINTER(_i64), C.c_int]),
+    "gt_workspace_bytes": (_i64, [_cfgp, _i64, C.c_int]),
+    "gt_forward": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _p, _p, _i64, C.c_int, _u64, _u64, _i64, _p]),
+    "gt_backward": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
+    "gt_loss_scratch_floats": (_i64, [_i64]),
+    "gt_loss": (C.c_int, [_p, _p, _i64, _f, _p, _p, _f, _p, _p]),
+    "gt_train_step": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
+    "gt_predict": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, _p]),
+    "gt_sgd_step": (C.c_int, [_p, _p, _i64, _f, _f, _p]),
+    "gt_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
+    "gt_debug_dropout_mask": (C.c_int, [_u64, _u64, C.c_int32, _f, _i64, _i64, _p, _p]),
+    "gt_debug_tc_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) the CUDA library.  Raises RuntimeError on any failure."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if build_if_missing:
+            path = _build.build()
+        if not os.path.exists(path):
+            raise RuntimeError(f"groove_b200: CUDA library {path} is missing and no CPU fallback exists")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.gt_version() != 1:
+            raise RuntimeError("groove_b200: ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().gt_last_error()
+        raise RuntimeError(f"groove_b200 {what} failed: {msg.decode() if msg else 'unknown error'}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,157 @@
+// common.cuh — shared declarations for the groove_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/groove_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "groove_b200 targets sm_100a (B200) only"
+#endif
+
+namespace gt {
+
+constexpr int T = GT_T_STEPS;     // steps per groove
+constexpr float LN_EPS = 1e-5f;   // torch.nn.LayerNorm default
+
+// ---- error plumbing (no exceptions across the C ABI) ---------------------------------------
+void set_error(const std::string &msg);
+#define GT_FAIL(msg)                                                     \
+  do {                                                                   \
+    gt::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+    return 1;                                                            \
+  } while (0)
+#define GT_CHECK(cond, msg) \
+  do {                      \
+    if (!(cond)) GT_FAIL(msg); \
+  } while (0)
+#define GT_CUDA(expr)                                                     \
+  do {                                                                    \
+    cudaError_t _e = (expr);                                              \
+    if (_e != cudaSuccess) GT_FAIL(std::string(#expr) + " -> " + cudaGetErrorString(_e)); \
+  } while (0)
+#define GT_TRY(expr)        \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != 0) return _r; \
+  } while (0)
+
+// ---- counter-based dropout generator (restated bit-exactly in oracle/groove_oracle.py) -----
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+inline uint32_t site_key(uint64_t seed, uint64_t step, int32_t site) {
+  uint32_t k = mix32((uint32_t)seed ^ 0x9E3779B9u);
+  k = mix32(k ^ (uint32_t)(seed >> 32));
+  k = mix32(k + (uint32_t)step * 0x85EBCA6Bu);
+  k = mix32(k ^ ((uint32_t)site * 0xC2B2AE35u));
+  return k;
+}
+inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 65536.0;
+  long r = lrint(t);            // round-half-even like Python's round()
+  if (r < 0) r = 0;
+  if (r > 65535) r = 65535;
+  return (uint32_t)r;
+}
+inline float drop_scale(uint32_t thr) { return thr == 0 ? 1.0f : (float)(65536.0 / (65536.0 - (double)thr)); }
+
+struct Drop {           // one dropout site; thr == 0 means "inactive"
+  uint32_t key = 0, thr = 0;
+  float scale = 1.f;
+};
+__device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t thr, uint64_t idx) {
+  uint64_t w = idx >> 1;
+  uint32_t x = (uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu);
+  uint32_t h = mix32((x * 0x9E3779B1u) ^ key);
+  uint32_t half = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return half >= thr;
+}
+
+// site numbering (oracle: site_id / SITE_IN_*)
+constexpr int SITE_IN_ENC = 1, SITE_IN_DEC = 2;
+inline int site_id(int stack, int layer, int k) { return 16 + (stack * 64 + layer) * 8 + k; }
+
+// ---- parameter layout -----------------------------------------------------------------------
+struct AttnP { int64_t w_in, b_in, w_out, b_out; };
+struct LayerP {
+  AttnP sa, ca;                       // self-attention, cross-attention (decoder only)
+  int64_t w1, b1, w2, b2;             // linear1 [F,d], linear2 [d,F]
+  int64_t g1, be1, g2, be2, g3, be3;  // norm1..3 (norm3 decoder only)
+};
+struct Layout {
+  int64_t in_enc_w, in_enc_b, in_dec_w, in_dec_b;
+  LayerP enc[64], dec[64];
+  int64_t enc_norm_g, enc_norm_b, dec_norm_g, dec_norm_b;
+  int64_t out_w, out_b;
+  int64_t total;
+  int n_tensors;
+  int64_t offs[2048], sizes[2048];
+};
+int build_layout(const gt_config &c, Layout &L);
+int validate_config(const gt_config *cfg);
+
+// ---- fp32 SIMT kernels (kernels_simt.cu) ----------------------------------------------------
+struct GemmEpi {
+  const float *bias = nullptr;       // + bias[n]
+  int relu = 0;                      // max(.,0)
+  const float *pe = nullptr;         // + pe[(m % 32) * N + n]
+  Drop drop;                         // dropout on element ((row0 + m) * N + n)
+  int64_t drop_row0 = 0;
+  const float *mask_pos = nullptr;   // v = mask_pos[m*ld_mask+n] > 0 ? v * mask_scale : 0
+  int64_t ld_mask = 0;
+  float mask_scale = 1.f;
+  const float *residual = nullptr;   // + residual[m*ld_res+n]
+  int64_t ld_res = 0;
+  int accumulate = 0;                // C += v
+  int atomic = 0;                    // atomicAdd(C, v)   (split-K)
+};
+// C[m,n] = epi( sum_k A(m,k) * B(n,k) ), A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]
+int gemm_f32(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk,
+             float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &epi,
+             int64_t split_k_chunk, cudaStream_t st);
+// out[n] += sum_m X[m*ld + n]
+int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStream_t st);
+
+struct AttnArgs {
+  const float *q, *k, *v;  int64_t ldq, ldk, ldv;
+  float *o;                int64_t ldo;
+  const float *d_o;        int64_t ld_do;     // backward only
+  float *dq, *dk, *dv;     int64_t ld_dq, ld_dk, ld_dv;
+  int64_t n_seq; int H, dh, causal;
+  Drop drop; int64_t seq0;
+};
+int attention_fwd(const AttnArgs &a, cudaStream_t st);
+int attention_bwd(const AttnArgs &a, cudaStream_t st);
+
+// y = LN(res + dropout(a)) ; u = res + dropout(a) saved when u != nullptr
+int ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, float *u, float *y,
+           float *mean, float *rstd, int64_t M, int d, const Drop &drop, int64_t row0, cudaStream_t st);
+// du = dLN/du ; da = du * dropmask (only written when da != nullptr) ; dgamma/dbeta accumulated
+int ln_bwd(const float *dy, const float *u, const float *mean, const float *rstd, const float *gamma,
+           float *du, float *da, float *dgamma, float *dbeta, int64_t M, int d, const Drop &drop,
+           int64_t row0, cudaStream_t st);
+// x0 = dropout(r + pe)
+int pe_dropout_fwd(const float *r, const float *pe, float *x0, int64_t M, int d, const Drop &drop,
+                   int64_t row0, cudaStream_t st);
+// g = dx0 * dropmask * (r > 0)
+int pe_dropout_bwd(const float *dx0, const float *r, float *g, int64_t M, int d, const Drop &drop,
+                   int64_t row0, cudaStream_t st);
+// in place on logits [M,27]: ch 9..17 sigmoid, 18..26 0.5*tanh ; thres >= 0: ch 0..8 -> (sigmoid > thres)
+int head_activation(float *hvo, int64_t M, int e_tgt, float thres, cudaStream_t st);
+// dlogits = d_hvo * activation'(hvo)
+int head_activation_bwd(const float *d_hvo, const float *hvo, float *dlogits, int64_t M, int e_tgt, cudaStream_t st);
+int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
+                 float grad_scale, float *partials, cudaStream_t st);
+int64_t loss_scratch_floats(int64_t n_seq);
+int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st);
+int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st);
+int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,
+              int64_t step, float gs, cudaStream_t st);
+int debug_dropout_mask(uint32_t key, uint32_t thr, int64_t idx0, int64_t n, uint8_t *keep, cudaStream_t st);
+int predict_feedback(const float *hvo, float *tgt, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st);
+
+}  // namespace gt

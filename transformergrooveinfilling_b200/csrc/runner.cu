@@ -1,0 +1,569 @@
+// runner.cu — parameter layout, workspace planning and the fp32 pass orchestration behind the
+// C ABI (include/groove_b200.h).  One C call = one whole pass (all layers), so Python pays one
+// ctypes call per forward / backward / fused train step.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "tc_path.cuh"
+
+namespace gt {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+int validate_config(const gt_config *c) {
+  GT_CHECK(c != nullptr, "null config");
+  GT_CHECK(c->d_model >= 1 && c->d_model <= 512, "d_model must be in [1,512]");
+  GT_CHECK(c->nhead >= 1 && c->d_model % c->nhead == 0, "d_model must be divisible by nhead");
+  GT_CHECK(c->dim_ff >= 1 && c->dim_ff <= 8192, "dim_feedforward must be in [1,8192]");
+  GT_CHECK(c->n_enc >= 1 && c->n_enc <= 64, "num_encoder_layers must be in [1,64]");
+  GT_CHECK(c->n_dec >= 0 && c->n_dec <= 64, "num_decoder_layers must be in [0,64]");
+  GT_CHECK(c->e_src >= 1 && c->e_src <= 512, "embedding_size_src out of range");
+  GT_CHECK(c->e_tgt == 27, "embedding_size_tgt must be 27 (9 voices x hit/velocity/offset)");
+  GT_CHECK(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
+  GT_CHECK(c->precision == GT_PREC_FP32 || c->precision == GT_PREC_BF16, "unknown precision mode");
+  return 0;
+}
+
+int build_layout(const gt_config &c, Layout &L) {
+  memset(&L, 0, sizeof(L));
+  int64_t off = 0;
+  int nt = 0;
+  auto take = [&](int64_t n) {
+    int64_t o = off;
+    L.offs[nt] = o; L.sizes[nt] = n; ++nt;
+    off += (n + 3) / 4 * 4;              // 16-byte alignment of every tensor
+    return o;
+  };
+  const int64_t d = c.d_model, F = c.dim_ff;
+  auto attn = [&](AttnP &a) { a.w_in = take(3 * d * d); a.b_in = take(3 * d); a.w_out = take(d * d); a.b_out = take(d); };
+  L.in_enc_w = take(d * c.e_src); L.in_enc_b = take(d);
+  for (int l = 0; l < c.n_enc; ++l) {
+    LayerP &p = L.enc[l];
+    attn(p.sa);
+    p.w1 = take(F * d); p.b1 = take(F); p.w2 = take(d * F); p.b2 = take(d);
+    p.g1 = take(d); p.be1 = take(d); p.g2 = take(d); p.be2 = take(d);
+  }
+  L.enc_norm_g = take(d); L.enc_norm_b = take(d);
+  if (c.n_dec > 0) {
+    L.in_dec_w = take(d * c.e_tgt); L.in_dec_b = take(d);
+    for (int l = 0; l < c.n_dec; ++l) {
+      LayerP &p = L.dec[l];
+      attn(p.sa); attn(p.ca);
+      p.w1 = take(F * d); p.b1 = take(F); p.w2 = take(d * F); p.b2 = take(d);
+      p.g1 = take(d); p.be1 = take(d); p.g2 = take(d); p.be2 = take(d); p.g3 = take(d); p.be3 = take(d);
+    }
+    L.dec_norm_g = take(d); L.dec_norm_b = take(d);
+  }
+  L.out_w = take(c.e_tgt * d); L.out_b = take(c.e_tgt);
+  L.total = off;
+  L.n_tensors = nt;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------------------------
+struct LayerBuf {
+  float *qkv, *ctx, *u1, *m1, *r1, *x1, *hd, *u2, *m2, *r2, *x2;
+  float *qc, *kvc, *ctx2, *u3, *m3, *r3, *x3;   // decoder only (x2 = after cross-attn, x3 = layer output)
+};
+struct Plan {
+  float *r0e, *x0e, *r0d, *y0d;
+  LayerBuf enc[64], dec[64];
+  float *mf_e, *rf_e, *mem;          // encoder final LN
+  float *mf_d, *rf_d, *zdec;         // decoder final LN
+  float *a;                          // GEMM output feeding an LN  [M,d]
+  float *tgt_in;                     // shifted target (fused train step / predict)
+  float *full;                       // [M,27] full-pass outputs of one predict() iteration
+  float *d_hvo, *loss_partials;      // fused train step
+  // backward temporaries
+  float *dxa, *dxb, *du, *da, *dh, *dqkv, *dctx, *dlog, *dmem, *dqc, *dkvc, *g0;
+  int64_t bytes;
+};
+
+static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, Plan &P) {
+  memset(&P, 0, sizeof(P));
+  const int64_t M = n_seq * T, d = c.d_model, F = c.dim_ff;
+  int64_t off = 0;
+  auto take = [&](int64_t n) -> float * {
+    int64_t o = off;
+    off += (n * 4 + 255) / 256 * 256;
+    return base ? reinterpret_cast<float *>(base + o) : nullptr;
+  };
+  const bool train = mode == 1;
+  auto layer = [&](LayerBuf &b, bool dec) {
+    b.qkv = take(M * 3 * d); b.ctx = take(M * d);
+    b.u1 = train ? take(M * d) : nullptr; b.m1 = train ? take(M) : nullptr; b.r1 = train ? take(M) : nullptr;
+    b.x1 = take(M * d); b.hd = take(M * F);
+    b.u2 = train ? take(M * d) : nullptr; b.m2 = train ? take(M) : nullptr; b.r2 = train ? take(M) : nullptr;
+    b.x2 = take(M * d);
+    if (dec) {
+      b.qc = take(M * d); b.kvc = take(M * 2 * d); b.ctx2 = take(M * d);
+      b.u3 = train ? take(M * d) : nullptr; b.m3 = train ? take(M) : nullptr; b.r3 = train ? take(M) : nullptr;
+      b.x3 = take(M * d);
+    }
+  };
+  P.r0e = take(M * d); P.x0e = take(M * d);
+  if (train) {
+    for (int l = 0; l < c.n_enc; ++l) layer(P.enc[l], false);
+  } else {
+    layer(P.enc[0], false);
+    for (int l = 1; l < c.n_enc; ++l) P.enc[l] = P.enc[0];
+  }
+  P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
+  if (c.n_dec > 0) {
+    P.r0d = take(M * d); P.y0d = take(M * d);
+    if (train) {
+      for (int l = 0; l < c.n_dec; ++l) layer(P.dec[l], true);
+    } else {
+      layer(P.dec[0], true);
+      for (int l = 1; l < c.n_dec; ++l) P.dec[l] = P.dec[0];
+    }
+    P.mf_d = train ? take(M) : nullptr; P.rf_d = train ? take(M) : nullptr; P.zdec = take(M * d);
+    P.tgt_in = take(M * c.e_tgt);
+    if (!train) P.full = take(M * c.e_tgt);
+  }
+  P.a = take(M * d);
+  if (train) {
+    P.d_hvo = take(M * c.e_tgt);
+    P.loss_partials = take(loss_scratch_floats(n_seq));
+    P.dxa = take(M * d); P.dxb = take(M * d); P.du = take(M * d); P.da = take(M * d);
+    P.dh = take(M * F); P.dqkv = take(M * 3 * d); P.dctx = take(M * d); P.dlog = take(M * c.e_tgt);
+    P.g0 = take(M * d);
+    if (c.n_dec > 0) { P.dmem = take(M * d); P.dqc = take(M * d); P.dkvc = take(M * 2 * d); }
+  }
+  P.bytes = off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass context + small helpers
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  gt_config c;
+  Layout L;
+  const float *P;
+  float *G;
+  const float *pe;
+  int64_t n_seq, M;
+  bool train;
+  uint64_t seed, step;
+  int64_t seq0;
+  cudaStream_t st;
+  Drop drop(int site) const {
+    Drop d;
+    uint32_t thr = drop_threshold(c.dropout);
+    if (!train || thr == 0) return d;
+    d.thr = thr; d.key = site_key(seed, step, site); d.scale = drop_scale(thr);
+    return d;
+  }
+  int64_t row0() const { return seq0 * T; }
+};
+
+static const int64_t WGRAD_CHUNK = 2048;
+
+// out[M,N] = epi(X[M,K] W[N,K]^T)
+static int linear(const Ctx &x, const float *X, int64_t K, const float *W, float *out, int64_t N, GemmEpi e) {
+  return gemm_f32(X, K, 1, W, K, 1, out, N, x.M, N, K, e, 0, x.st);
+}
+// dX[M,K] = epi(dY[M,N] W[N,K])
+static int linear_dgrad(const Ctx &x, const float *dY, int64_t N, const float *W, int64_t K, float *dX, GemmEpi e) {
+  return gemm_f32(dY, N, 1, W, 1, K, dX, K, x.M, K, N, e, 0, x.st);
+}
+// dW[N,K] += dY[M,N]^T X[M,K] ; db[N] += colsum(dY)
+static int linear_wgrad(const Ctx &x, const float *dY, int64_t ldy, int64_t N, const float *X, int64_t ldx, int64_t K,
+                        float *dW, float *db) {
+  GemmEpi e; e.atomic = 1;
+  GT_TRY(gemm_f32(dY, 1, ldy, X, 1, ldx, dW, K, N, K, x.M, e, WGRAD_CHUNK, x.st));
+  if (db) GT_TRY(colsum_f32(dY, ldy, x.M, (int)N, db, x.st));
+  return 0;
+}
+
+static AttnArgs attn_args(const Ctx &x, const float *q, int64_t ldq, const float *k, const float *v, int64_t ldkv,
+                          float *o, int causal, int site) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv;
+  a.o = o; a.ldo = x.c.d_model;
+  a.n_seq = x.n_seq; a.H = x.c.nhead; a.dh = x.c.d_model / x.c.nhead; a.causal = causal;
+  a.drop = x.drop(site); a.seq0 = x.seq0;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+static int input_layer_fwd(const Ctx &x, const float *src, int E, int64_t w, int64_t b, float *r0, float *x0, int site) {
+  GemmEpi e; e.bias = x.P + b; e.relu = 1;
+  GT_TRY(linear(x, src, E, x.P + w, r0, x.c.d_model, e));
+  return pe_dropout_fwd(r0, x.pe, x0, x.M, x.c.d_model, x.drop(site), x.row0(), x.st);
+}
+
+static int ffn_fwd(const Ctx &x, const LayerP &p, const float *xin, float *hd, float *a, int stack, int li) {
+  const int d = x.c.d_model, F = x.c.dim_ff;
+  GemmEpi e1; e1.bias = x.P + p.b1; e1.relu = 1; e1.drop = x.drop(site_id(stack, li, 2)); e1.drop_row0 = x.row0();
+  GT_TRY(linear(x, xin, d, x.P + p.w1, hd, F, e1));
+  GemmEpi e2; e2.bias = x.P + p.b2;
+  return linear(x, hd, F, x.P + p.w2, a, d, e2);
+}
+
+static int enc_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *xin) {
+  const LayerP &p = x.L.enc[li];
+  const LayerBuf &b = pl.enc[li];
+  const int d = x.c.d_model;
+  GemmEpi e; e.bias = x.P + p.sa.b_in;
+  GT_TRY(linear(x, xin, d, x.P + p.sa.w_in, b.qkv, 3 * d, e));
+  GT_TRY(attention_fwd(attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 0, site_id(0, li, 0)), x.st));
+  GemmEpi eo; eo.bias = x.P + p.sa.b_out;
+  GT_TRY(linear(x, b.ctx, d, x.P + p.sa.w_out, pl.a, d, eo));
+  GT_TRY(ln_fwd(pl.a, xin, x.P + p.g1, x.P + p.be1, b.u1, b.x1, b.m1, b.r1, x.M, d, x.drop(site_id(0, li, 1)), x.row0(), x.st));
+  GT_TRY(ffn_fwd(x, p, b.x1, b.hd, pl.a, 0, li));
+  return ln_fwd(pl.a, b.x1, x.P + p.g2, x.P + p.be2, b.u2, b.x2, b.m2, b.r2, x.M, d, x.drop(site_id(0, li, 3)), x.row0(), x.st);
+}
+
+static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin) {
+  const LayerP &p = x.L.dec[li];
+  const LayerBuf &b = pl.dec[li];
+  const int d = x.c.d_model;
+  GemmEpi e; e.bias = x.P + p.sa.b_in;
+  GT_TRY(linear(x, yin, d, x.P + p.sa.w_in, b.qkv, 3 * d, e));
+  GT_TRY(attention_fwd(attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 1, site_id(1, li, 0)), x.st));
+  GemmEpi eo; eo.bias = x.P + p.sa.b_out;
+  GT_TRY(linear(x, b.ctx, d, x.P + p.sa.w_out, pl.a, d, eo));
+  GT_TRY(ln_fwd(pl.a, yin, x.P + p.g1, x.P + p.be1, b.u1, b.x1, b.m1, b.r1, x.M, d, x.drop(site_id(1, li, 1)), x.row0(), x.st));
+  // cross attention: q from the target stream, k/v from the encoder memory
+  GemmEpi eq; eq.bias = x.P + p.ca.b_in;
+  GT_TRY(linear(x, b.x1, d, x.P + p.ca.w_in, b.qc, d, eq));
+  GemmEpi ekv; ekv.bias = x.P + p.ca.b_in + d;
+  GT_TRY(linear(x, pl.mem, d, x.P + p.ca.w_in + (int64_t)d * d, b.kvc, 2 * d, ekv));
+  GT_TRY(attention_fwd(attn_args(x, b.qc, d, b.kvc, b.kvc + d, 2 * d, b.ctx2, 0, site_id(1, li, 4)), x.st));
+  GemmEpi eco; eco.bias = x.P + p.ca.b_out;
+  GT_TRY(linear(x, b.ctx2, d, x.P + p.ca.w_out, pl.a, d, eco));
+  GT_TRY(ln_fwd(pl.a, b.x1, x.P + p.g2, x.P + p.be2, b.u2, b.x2, b.m2, b.r2, x.M, d, x.drop(site_id(1, li, 5)), x.row0(), x.st));
+  GT_TRY(ffn_fwd(x, p, b.x2, b.hd, pl.a, 1, li));
+  return ln_fwd(pl.a, b.x2, x.P + p.g3, x.P + p.be3, b.u3, b.x3, b.m3, b.r3, x.M, d, x.drop(site_id(1, li, 3)), x.row0(), x.st);
+}
+
+static int encoder_fwd(const Ctx &x, const Plan &pl, const float *src) {
+  GT_TRY(input_layer_fwd(x, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, pl.r0e, pl.x0e, SITE_IN_ENC));
+  const float *cur = pl.x0e;
+  for (int l = 0; l < x.c.n_enc; ++l) {
+    GT_TRY(enc_layer_fwd(x, pl, l, cur));
+    cur = pl.enc[l].x2;
+  }
+  Drop none;
+  return ln_fwd(cur, nullptr, x.P + x.L.enc_norm_g, x.P + x.L.enc_norm_b, nullptr, pl.mem, pl.mf_e, pl.rf_e, x.M,
+                x.c.d_model, none, 0, x.st);
+}
+
+static int decoder_fwd(const Ctx &x, const Plan &pl, const float *tgt_in) {
+  GT_TRY(input_layer_fwd(x, tgt_in, x.c.e_tgt, x.L.in_dec_w, x.L.in_dec_b, pl.r0d, pl.y0d, SITE_IN_DEC));
+  const float *cur = pl.y0d;
+  for (int l = 0; l < x.c.n_dec; ++l) {
+    GT_TRY(dec_layer_fwd(x, pl, l, cur));
+    cur = pl.dec[l].x3;
+  }
+  Drop none;
+  return ln_fwd(cur, nullptr, x.P + x.L.dec_norm_g, x.P + x.L.dec_norm_b, nullptr, pl.zdec, pl.mf_d, pl.rf_d, x.M,
+                x.c.d_model, none, 0, x.st);
+}
+
+static int head_fwd(const Ctx &x, const float *z, float *hvo, float thres) {
+  GemmEpi e; e.bias = x.P + x.L.out_b;
+  GT_TRY(linear(x, z, x.c.d_model, x.P + x.L.out_w, hvo, x.c.e_tgt, e));
+  return head_activation(hvo, x.M, x.c.e_tgt, thres, x.st);
+}
+
+static int forward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, float *hvo) {
+  GT_TRY(encoder_fwd(x, pl, src));
+  if (x.c.n_dec > 0) {
+    GT_CHECK(tgt_in != nullptr, "encoder-decoder forward needs the shifted target");
+    GT_TRY(decoder_fwd(x, pl, tgt_in));
+    return head_fwd(x, pl.zdec, hvo, -1.f);
+  }
+  return head_fwd(x, pl.mem, hvo, -1.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// Given du2-like gradient `dout` w.r.t. the FFN block output (post-LN), produce gradient w.r.t. the
+// block input in `dx_out`.  xin = block input (saved), u/m/r = saved LN input + stats.
+static int ffn_bwd(const Ctx &x, const Plan &pl, const LayerP &p, const float *dout, const float *xin, const float *hd,
+                   const float *u, const float *m, const float *r, int64_t g, int64_t be, float *dx_out, int stack, int li) {
+  const int d = x.c.d_model, F = x.c.dim_ff;
+  GT_TRY(ln_bwd(dout, u, m, r, x.P + g, pl.du, pl.da, x.G + g, x.G + be, x.M, d, x.drop(site_id(stack, li, 3)), x.row0(), x.st));
+  // dhd = da W2 ; dh = dhd * (hd>0) * scale
+  GemmEpi e; e.mask_pos = hd; e.ld_mask = F; e.mask_scale = x.drop(site_id(stack, li, 2)).scale;
+  GT_TRY(linear_dgrad(x, pl.da, d, x.P + p.w2, F, pl.dh, e));
+  GT_TRY(linear_wgrad(x, pl.da, d, d, hd, F, F, x.G + p.w2, x.G + p.b2));
+  GemmEpi e2; e2.residual = pl.du; e2.ld_res = d;
+  GT_TRY(linear_dgrad(x, pl.dh, F, x.P + p.w1, d, dx_out, e2));
+  return linear_wgrad(x, pl.dh, F, F, xin, d, d, x.G + p.w1, x.G + p.b1);
+}
+
+static int enc_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *xin, const float *dout, float *dx_tmp, float *dx_in) {
+  const LayerP &p = x.L.enc[li];
+  const LayerBuf &b = pl.enc[li];
+  const int d = x.c.d_model;
+  GT_TRY(ffn_bwd(x, pl, p, dout, b.x1, b.hd, b.u2, b.m2, b.r2, p.g2, p.be2, dx_tmp, 0, li));
+  GT_TRY(ln_bwd(dx_tmp, b.u1, b.m1, b.r1, x.P + p.g1, pl.du, pl.da, x.G + p.g1, x.G + p.be1, x.M, d,
+                x.drop(site_id(0, li, 1)), x.row0(), x.st));
+  GemmEpi e0;
+  GT_TRY(linear_dgrad(x, pl.da, d, x.P + p.sa.w_out, d, pl.dctx, e0));
+  GT_TRY(linear_wgrad(x, pl.da, d, d, b.ctx, d, d, x.G + p.sa.w_out, x.G + p.sa.b_out));
+  AttnArgs a = attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, nullptr, 0, site_id(0, li, 0));
+  a.d_o = pl.dctx; a.ld_do = d;
+  a.dq = pl.dqkv; a.dk = pl.dqkv + d; a.dv = pl.dqkv + 2 * d; a.ld_dq = a.ld_dk = a.ld_dv = 3 * d;
+  GT_TRY(attention_bwd(a, x.st));
+  GemmEpi e1; e1.residual = pl.du; e1.ld_res = d;
+  GT_TRY(linear_dgrad(x, pl.dqkv, 3 * d, x.P + p.sa.w_in, d, dx_in, e1));
+  return linear_wgrad(x, pl.dqkv, 3 * d, 3 * d, xin, d, d, x.G + p.sa.w_in, x.G + p.sa.b_in);
+}
+
+static int dec_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *yin, const float *dout, float *dx_tmp, float *dx_in) {
+  const LayerP &p = x.L.dec[li];
+  const LayerBuf &b = pl.dec[li];
+  const int d = x.c.d_model;
+  GT_TRY(ffn_bwd(x, pl, p, dout, b.x2, b.hd, b.u3, b.m3, b.r3, p.g3, p.be3, dx_tmp, 1, li));
+  // cross-attention block
+  GT_TRY(ln_bwd(dx_tmp, b.u2, b.m2, b.r2, x.P + p.g2, pl.du, pl.da, x.G + p.g2, x.G + p.be2, x.M, d,
+                x.drop(site_id(1, li, 5)), x.row0(), x.st));
+  GemmEpi e0;
+  GT_TRY(linear_dgrad(x, pl.da, d, x.P + p.ca.w_out, d, pl.dctx, e0));
+  GT_TRY(linear_wgrad(x, pl.da, d, d, b.ctx2, d, d, x.G + p.ca.w_out, x.G + p.ca.b_out));
+  AttnArgs c = attn_args(x, b.qc, d, b.kvc, b.kvc + d, 2 * d, nullptr, 0, site_id(1, li, 4));
+  c.d_o = pl.dctx; c.ld_do = d;
+  c.dq = pl.dqc; c.ld_dq = d; c.dk = pl.dkvc; c.dv = pl.dkvc + d; c.ld_dk = c.ld_dv = 2 * d;
+  GT_TRY(attention_bwd(c, x.st));
+  // d(x1) = du (residual) + dqc Wq ; dmem += dkvc Wkv
+  GemmEpi e1; e1.residual = pl.du; e1.ld_res = d;
+  GT_TRY(linear_dgrad(x, pl.dqc, d, x.P + p.ca.w_in, d, dx_in, e1));          // dx_in used as scratch for d(x1)
+  GT_TRY(linear_wgrad(x, pl.dqc, d, d, b.x1, d, d, x.G + p.ca.w_in, x.G + p.ca.b_in));
+  GemmEpi e2; e2.accumulate = 1;
+  GT_TRY(linear_dgrad(x, pl.dkvc, 2 * d, x.P + p.ca.w_in + (int64_t)d * d, d, pl.dmem, e2));
+  GT_TRY(linear_wgrad(x, pl.dkvc, 2 * d, 2 * d, pl.mem, d, d, x.G + p.ca.w_in + (int64_t)d * d, x.G + p.ca.b_in + d));
+  // causal self-attention block
+  GT_TRY(ln_bwd(dx_in, b.u1, b.m1, b.r1, x.P + p.g1, pl.du, pl.da, x.G + p.g1, x.G + p.be1, x.M, d,
+                x.drop(site_id(1, li, 1)), x.row0(), x.st));
+  GT_TRY(linear_dgrad(x, pl.da, d, x.P + p.sa.w_out, d, pl.dctx, e0));
+  GT_TRY(linear_wgrad(x, pl.da, d, d, b.ctx, d, d, x.G + p.sa.w_out, x.G + p.sa.b_out));
+  AttnArgs a = attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, nullptr, 1, site_id(1, li, 0));
+  a.d_o = pl.dctx; a.ld_do = d;
+  a.dq = pl.dqkv; a.dk = pl.dqkv + d; a.dv = pl.dqkv + 2 * d; a.ld_dq = a.ld_dk = a.ld_dv = 3 * d;
+  GT_TRY(attention_bwd(a, x.st));
+  GemmEpi e3; e3.residual = pl.du; e3.ld_res = d;
+  GT_TRY(linear_dgrad(x, pl.dqkv, 3 * d, x.P + p.sa.w_in, d, dx_tmp, e3));
+  GT_TRY(linear_wgrad(x, pl.dqkv, 3 * d, 3 * d, yin, d, d, x.G + p.sa.w_in, x.G + p.sa.b_in));
+  return 0;   // result in dx_tmp
+}
+
+static int input_layer_bwd(const Ctx &x, const Plan &pl, const float *dx0, const float *r0, const float *src, int E,
+                           int64_t w, int64_t b, int site) {
+  GT_TRY(pe_dropout_bwd(dx0, r0, pl.g0, x.M, x.c.d_model, x.drop(site), x.row0(), x.st));
+  return linear_wgrad(x, pl.g0, x.c.d_model, x.c.d_model, src, E, E, x.G + w, x.G + b);
+}
+
+static int backward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, const float *hvo,
+                        const float *d_hvo) {
+  const int d = x.c.d_model, E = x.c.e_tgt;
+  Drop none;
+  // head
+  GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
+  const float *z = x.c.n_dec > 0 ? pl.zdec : pl.mem;
+  GT_TRY(linear_wgrad(x, pl.dlog, E, E, z, d, d, x.G + x.L.out_w, x.G + x.L.out_b));
+  GemmEpi e0;
+  GT_TRY(linear_dgrad(x, pl.dlog, E, x.P + x.L.out_w, d, pl.dxa, e0));
+  float *cur = pl.dxa, *oth = pl.dxb;
+  if (x.c.n_dec > 0) {
+    GT_CUDA(cudaMemsetAsync(pl.dmem, 0, (size_t)x.M * d * sizeof(float), x.st));
+    const float *last = pl.dec[x.c.n_dec - 1].x3;
+    GT_TRY(ln_bwd(cur, last, pl.mf_d, pl.rf_d, x.P + x.L.dec_norm_g, oth, nullptr, x.G + x.L.dec_norm_g,
+                  x.G + x.L.dec_norm_b, x.M, d, none, 0, x.st));
+    std::swap(cur, oth);
+    for (int l = x.c.n_dec - 1; l >= 0; --l) {
+      const float *yin = l == 0 ? pl.y0d : pl.dec[l - 1].x3;
+      // reads `cur`; `oth` and pl.g0 are temporaries; the result lands in `oth`
+      GT_TRY(dec_layer_bwd(x, pl, l, yin, cur, oth, pl.g0));
+      std::swap(cur, oth);
+    }
+    GT_TRY(input_layer_bwd(x, pl, cur, pl.r0d, tgt_in, E, x.L.in_dec_w, x.L.in_dec_b, SITE_IN_DEC));
+    // encoder gradient starts from dmem
+    GT_CUDA(cudaMemcpyAsync(pl.dxa, pl.dmem, (size_t)x.M * d * sizeof(float), cudaMemcpyDeviceToDevice, x.st));
+    cur = pl.dxa; oth = pl.dxb;
+  }
+  const float *last = pl.enc[x.c.n_enc - 1].x2;
+  GT_TRY(ln_bwd(cur, last, pl.mf_e, pl.rf_e, x.P + x.L.enc_norm_g, oth, nullptr, x.G + x.L.enc_norm_g,
+                x.G + x.L.enc_norm_b, x.M, d, none, 0, x.st));
+  std::swap(cur, oth);
+  for (int l = x.c.n_enc - 1; l >= 0; --l) {
+    const float *xin = l == 0 ? pl.x0e : pl.enc[l - 1].x2;
+    GT_TRY(enc_layer_bwd(x, pl, l, xin, cur, pl.g0, oth));
+    std::swap(cur, oth);
+  }
+  return input_layer_bwd(x, pl, cur, pl.r0e, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, SITE_IN_ENC);
+}
+
+static int make_ctx(Ctx &x, const gt_config *cfg, const float *params, float *grads, const float *pe, int64_t n_seq,
+                    bool train, uint64_t seed, uint64_t step, int64_t seq0, void *stream) {
+  GT_TRY(validate_config(cfg));
+  GT_CHECK(n_seq >= 1, "n_seq must be >= 1");
+  GT_CHECK(n_seq <= (int64_t)1 << 24, "n_seq too large for one call");
+  GT_CHECK(params != nullptr && pe != nullptr, "null params / pe");
+  GT_CHECK(((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0, "params / grads must be 16-byte aligned");
+  x.c = *cfg;
+  GT_TRY(build_layout(*cfg, x.L));
+  x.P = params; x.G = grads; x.pe = pe; x.n_seq = n_seq; x.M = n_seq * T; x.train = train;
+  x.seed = seed; x.step = step; x.seq0 = seq0; x.st = (cudaStream_t)stream;
+  return 0;
+}
+
+static int check_ws(const gt_config *cfg, int64_t n_seq, int mode, void *ws, int64_t ws_bytes, Plan &pl) {
+  GT_CHECK(ws != nullptr, "null workspace");
+  GT_CHECK(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  make_plan(*cfg, n_seq, mode, (char *)ws, pl);
+  GT_CHECK(ws_bytes >= pl.bytes, "workspace too small: need " + std::to_string(pl.bytes) + " bytes, got " + std::to_string(ws_bytes));
+  return 0;
+}
+
+}  // namespace gt
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace gt;
+
+extern "C" {
+
+int gt_version(void) { return GT_ABI_VERSION; }
+const char *gt_last_error(void) { return g_err.c_str(); }
+
+int64_t gt_param_count(const gt_config *cfg) {
+  if (validate_config(cfg)) return -1;
+  static thread_local Layout L;
+  build_layout(*cfg, L);
+  return L.total;
+}
+
+int gt_param_layout(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int max_entries) {
+  if (validate_config(cfg)) return -1;
+  static thread_local Layout L;
+  build_layout(*cfg, L);
+  if (max_entries < L.n_tensors) { set_error("gt_param_layout: max_entries too small"); return -1; }
+  for (int i = 0; i < L.n_tensors; ++i) { offsets[i] = L.offs[i]; sizes[i] = L.sizes[i]; }
+  return L.n_tensors;
+}
+
+int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode) {
+  if (validate_config(cfg)) return -1;
+  if (n_seq < 1 || (mode != 0 && mode != 1)) { set_error("gt_workspace_bytes: bad n_seq / mode"); return -1; }
+  if (cfg->precision == GT_PREC_BF16) return tc_workspace_bytes(*cfg, n_seq, mode);
+  static thread_local Plan pl;
+  make_plan(*cfg, n_seq, mode, nullptr, pl);
+  return pl.bytes;
+}
+
+int gt_forward(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *tgt_in,
+               int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, int train, uint64_t seed, uint64_t step,
+               int64_t seq0, void *stream) {
+  static thread_local Ctx x;
+  GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, train != 0, seed, step, seq0, stream));
+  GT_CHECK(src != nullptr && hvo != nullptr, "null src / hvo");
+  if (cfg->precision == GT_PREC_BF16)
+    return tc_forward(*cfg, x.L, params, pe, src, tgt_in, n_seq, hvo, ws, ws_bytes, train != 0, seed, step, seq0, x.st);
+  static thread_local Plan pl;
+  GT_TRY(check_ws(cfg, n_seq, train ? 1 : 0, ws, ws_bytes, pl));
+  return forward_all(x, pl, src, tgt_in, hvo);
+}
+
+int gt_backward(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *tgt_in,
+                int64_t n_seq, const float *hvo, const float *d_hvo, float *grads, void *ws, int64_t ws_bytes, uint64_t seed,
+                uint64_t step, int64_t seq0, void *stream) {
+  static thread_local Ctx x;
+  GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
+  GT_CHECK(src != nullptr && hvo != nullptr && d_hvo != nullptr && grads != nullptr, "null src / hvo / d_hvo / grads");
+  if (cfg->precision == GT_PREC_BF16)
+    return tc_backward(*cfg, x.L, params, pe, src, tgt_in, n_seq, hvo, d_hvo, grads, ws, ws_bytes, seed, step, seq0, x.st);
+  static thread_local Plan pl;
+  GT_TRY(check_ws(cfg, n_seq, 1, ws, ws_bytes, pl));
+  return backward_all(x, pl, src, tgt_in, hvo, d_hvo);
+}
+
+int64_t gt_loss_scratch_floats(int64_t n_seq) { return loss_scratch_floats(n_seq); }
+
+int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty, float *metrics6, float *d_hvo,
+            float grad_scale, float *partials, void *stream) {
+  GT_CHECK(hvo && y && metrics6 && partials, "gt_loss: null pointer");
+  GT_CHECK(n_seq >= 1, "gt_loss: empty batch");
+  return loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, d_hvo, grad_scale, partials, (cudaStream_t)stream);
+}
+
+int gt_train_step(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *y,
+                  int64_t n_seq, float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws,
+                  int64_t ws_bytes, uint64_t seed, uint64_t step, int64_t seq0, void *stream) {
+  static thread_local Ctx x;
+  GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
+  GT_CHECK(src && y && grads && metrics6 && hvo, "gt_train_step: null pointer");
+  if (cfg->precision == GT_PREC_BF16)
+    return tc_train_step(*cfg, x.L, params, pe, src, y, n_seq, hit_loss_penalty, grads, metrics6, hvo, ws, ws_bytes, seed,
+                         step, seq0, x.st);
+  static thread_local Plan pl;
+  GT_TRY(check_ws(cfg, n_seq, 1, ws, ws_bytes, pl));
+  GT_CUDA(cudaMemsetAsync(grads, 0, (size_t)x.L.total * sizeof(float), x.st));
+  const float *tgt_in = nullptr;
+  if (cfg->n_dec > 0) {
+    GT_TRY(shift_right(y, pl.tgt_in, n_seq, cfg->e_tgt, x.st));
+    tgt_in = pl.tgt_in;
+  }
+  GT_TRY(forward_all(x, pl, src, tgt_in, hvo));
+  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, x.st));
+  return backward_all(x, pl, src, tgt_in, hvo, pl.d_hvo);
+}
+
+int gt_predict(const gt_config *cfg, const float *params, const float *pe, const float *src, int64_t n_seq, float thres,
+               float *hvo_out, void *ws, int64_t ws_bytes, void *stream) {
+  static thread_local Ctx x;
+  GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, false, 0, 0, 0, stream));
+  GT_CHECK(src && hvo_out, "gt_predict: null pointer");
+  GT_CHECK(thres >= 0.f && thres <= 1.f, "gt_predict: threshold must be in [0,1]");
+  if (cfg->precision == GT_PREC_BF16)
+    return tc_predict(*cfg, x.L, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, x.st);
+  static thread_local Plan pl;
+  GT_TRY(check_ws(cfg, n_seq, 0, ws, ws_bytes, pl));
+  GT_TRY(encoder_fwd(x, pl, src));
+  if (cfg->n_dec == 0) return head_fwd(x, pl.mem, hvo_out, thres);
+  // BGT/models/transformer.py:48-83: 32 decoder passes; step i feeds (thresholded h, raw v, raw o) to i+1.
+  GT_CUDA(cudaMemsetAsync(pl.tgt_in, 0, (size_t)x.M * cfg->e_tgt * sizeof(float), x.st));
+  float *full = pl.full;
+  for (int i = 0; i < T; ++i) {
+    GT_TRY(decoder_fwd(x, pl, pl.tgt_in));
+    GT_TRY(head_fwd(x, pl.zdec, full, -1.f));
+    GT_TRY(predict_feedback(full, pl.tgt_in, hvo_out, n_seq, cfg->e_tgt, i, thres, x.st));
+  }
+  return 0;
+}
+
+int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale, void *stream) {
+  GT_CHECK(p && g && n >= 0, "gt_sgd_step: bad arguments");
+  return sgd_step(p, g, n, lr, grad_scale, (cudaStream_t)stream);
+}
+int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int64_t step, float grad_scale, void *stream) {
+  GT_CHECK(p && g && m && v && n >= 0, "gt_adam_step: bad arguments");
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
+int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p, int64_t idx0, int64_t n, uint8_t *keep,
+                          void *stream) {
+  GT_CHECK(keep && n >= 0, "gt_debug_dropout_mask: bad arguments");
+  return debug_dropout_mask(site_key(seed, step, site), drop_threshold(p), idx0, n, keep, (cudaStream_t)stream);
+}
+
+int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k, int variant, void *stream) {
+  return tc_debug_gemm(a, b, d, m, n, k, variant, (cudaStream_t)stream);
+}
+
+}  // extern "C"
