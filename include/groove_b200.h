@@ -108,6 +108,15 @@ int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale,
 int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Launch accounting for bench.py.  gt_launch_count(-1) = kernels launched by this library so far
+ * (all classes); gt_profile_enable(class, max_records) brackets every launch of one kernel class with
+ * CUDA events on its stream (0 disables); gt_profile_collect sums their elapsed times and resets.
+ * Kernel classes: 1 gemm_f32, 2 attention fwd, 3 attention bwd, 4 layernorm, 5 element-wise, 6 loss,
+ * 7 optimizer, 16 tc weight prep, 17 tc layer fwd, 18 tc layer bwd, 19 tc head, 20 tc wgrad, 21 tc input. */
+int64_t gt_launch_count(int kernel_class);
+int     gt_profile_enable(int kernel_class, int max_records);
+int     gt_profile_collect(double *total_ms, int64_t *launches);
+
 /* Test hook: fills keep[i] = 1/0 for element indices idx0..idx0+n-1 of dropout site `site`
  * (the generator restated in oracle/groove_oracle.py:dropout_keep). */
 int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p,

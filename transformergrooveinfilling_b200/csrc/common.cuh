@@ -38,6 +38,18 @@ void set_error(const std::string &msg);
     if (_r != 0) return _r; \
   } while (0)
 
+// ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py roofline) --------
+enum KernelClass {
+  KC_NONE = 0, KC_GEMM_F32 = 1, KC_ATTN_FWD = 2, KC_ATTN_BWD = 3, KC_LN = 4, KC_ELEMWISE = 5, KC_LOSS = 6, KC_OPT = 7,
+  KC_TC_PREP = 16, KC_TC_LAYER_FWD = 17, KC_TC_LAYER_BWD = 18, KC_TC_HEAD = 19, KC_TC_WGRAD = 20, KC_TC_INPUT = 21,
+  KC_MAX = 32
+};
+struct LaunchScope {     // RAII: counts the launch; records start/stop events when its class is being profiled
+  int cls; cudaStream_t st; int slot;
+  LaunchScope(int cls, cudaStream_t st);
+  ~LaunchScope();
+};
+
 // ---- counter-based dropout generator (restated bit-exactly in oracle/groove_oracle.py) -----
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;

@@ -112,7 +112,8 @@ int gemm_f32(const float *A, int64_t sam, int64_t sak, const float *B, int64_t s
   }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
   GT_CHECK(grid.y <= 65535, "GEMM N too large");
-  gemm_f32_kernel<<<grid, 256, 0, st>>>(g);
+  { LaunchScope _ls(KC_GEMM_F32, st);
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(g); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -132,7 +133,8 @@ int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStr
   int rows = 256;
   int64_t blocks = (M + rows - 1) / rows;
   int threads = N >= 256 ? 256 : ((N + 31) / 32 * 32);
-  colsum_kernel<<<(unsigned)blocks, threads, 0, st>>>(X, ld, M, N, out, rows);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  colsum_kernel<<<(unsigned)blocks, threads, 0, st>>>(X, ld, M, N, out, rows); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -292,10 +294,12 @@ static int attn_launch(const AttnArgs &a, bool bwd, cudaStream_t st) {
   int64_t blocks = (pairs + warps - 1) / warps;
   if (bwd) {
     GT_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attention_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, warps);
+    { LaunchScope _ls(KC_ATTN_BWD, st);
+    attention_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, warps); }
   } else {
     GT_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attention_fwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, warps);
+    { LaunchScope _ls(KC_ATTN_FWD, st);
+    attention_fwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, warps); }
   }
   GT_CUDA(cudaGetLastError());
   return 0;
@@ -357,7 +361,8 @@ int ln_fwd(const float *a, const float *res, const float *gamma, const float *be
   if (M == 0) return 0;
   GT_CHECK(d <= 512, "d_model > 512 not supported");
   const int wpb = 8;
-  ln_fwd_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, d, drop, row0);
+  { LaunchScope _ls(KC_LN, st);
+  ln_fwd_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, d, drop, row0); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -426,8 +431,9 @@ int ln_bwd(const float *dy, const float *u, const float *mean, const float *rstd
   GT_CHECK(d <= 512, "d_model > 512 not supported");
   const int wpb = 8, rpw = 16;
   int64_t blocks = (M + wpb * rpw - 1) / (wpb * rpw);
+  { LaunchScope _ls(KC_LN, st);
   ln_bwd_kernel<<<(unsigned)blocks, wpb * 32, 2 * d * sizeof(float), st>>>(dy, u, mean, rstd, gamma, du, da, dgamma, dbeta,
-                                                                           M, d, drop, row0, rpw);
+                                                                           M, d, drop, row0, rpw); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -446,7 +452,8 @@ __global__ void pe_dropout_fwd_kernel(const float *__restrict__ r, const float *
 int pe_dropout_fwd(const float *r, const float *pe, float *x0, int64_t M, int d, const Drop &drop, int64_t row0, cudaStream_t st) {
   int64_t n = M * d;
   if (n == 0) return 0;
-  pe_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r, pe, x0, n, d, drop, row0 * d);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  pe_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r, pe, x0, n, d, drop, row0 * d); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -461,7 +468,8 @@ __global__ void pe_dropout_bwd_kernel(const float *__restrict__ dx0, const float
 int pe_dropout_bwd(const float *dx0, const float *r, float *g, int64_t M, int d, const Drop &drop, int64_t row0, cudaStream_t st) {
   int64_t n = M * d;
   if (n == 0) return 0;
-  pe_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dx0, r, g, n, drop, row0 * d);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  pe_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dx0, r, g, n, drop, row0 * d); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -478,7 +486,8 @@ __global__ void head_activation_kernel(float *hvo, int64_t n, int e_tgt, float t
 int head_activation(float *hvo, int64_t M, int e_tgt, float thres, cudaStream_t st) {
   int64_t n = M * e_tgt;
   if (n == 0) return 0;
-  head_activation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvo, n, e_tgt, thres);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  head_activation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvo, n, e_tgt, thres); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -495,7 +504,8 @@ __global__ void head_activation_bwd_kernel(const float *__restrict__ d_hvo, cons
 int head_activation_bwd(const float *d_hvo, const float *hvo, float *dlogits, int64_t M, int e_tgt, cudaStream_t st) {
   int64_t n = M * e_tgt;
   if (n == 0) return 0;
-  head_activation_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_hvo, hvo, dlogits, n, e_tgt);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  head_activation_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_hvo, hvo, dlogits, n, e_tgt); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -575,9 +585,11 @@ int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty,
   int64_t M = n_seq * T;
   GT_CHECK(M > 0, "empty batch");
   int64_t blocks = (M + LOSS_ROWS_PER_BLOCK - 1) / LOSS_ROWS_PER_BLOCK;
-  loss_partial_kernel<<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, penalty, d_hvo, grad_scale / (float)M, partials);
+  { LaunchScope _ls(KC_LOSS, st);
+  loss_partial_kernel<<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, penalty, d_hvo, grad_scale / (float)M, partials); }
   GT_CUDA(cudaGetLastError());
-  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, metrics6);
+  { LaunchScope _ls(KC_LOSS, st);
+  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, metrics6); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -591,7 +603,8 @@ __global__ void shift_right_kernel(const float *__restrict__ y, float *out, int6
 int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st) {
   int64_t n = n_seq * T * e;
   if (n == 0) return 0;
-  shift_right_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, out, n, e);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  shift_right_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, out, n, e); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -611,7 +624,8 @@ __global__ void predict_feedback_kernel(const float *__restrict__ hvo, float *tg
 int predict_feedback(const float *hvo, float *tgt, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st) {
   int64_t n = n_seq * e;
   if (n == 0) return 0;
-  predict_feedback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvo, tgt, out, n_seq, e, step_i, thres);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  predict_feedback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvo, tgt, out, n_seq, e, step_i, thres); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -623,7 +637,8 @@ __global__ void sgd_kernel(float *p, const float *__restrict__ g, int64_t n, flo
 }
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st) {
   if (n == 0) return 0;
-  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, lr, gs);
+  { LaunchScope _ls(KC_OPT, st);
+  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, lr, gs); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -645,7 +660,8 @@ int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
   if (n == 0) return 0;
   GT_CHECK(step >= 1, "Adam step is 1-based");
   double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs);
+  { LaunchScope _ls(KC_OPT, st);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -656,7 +672,8 @@ __global__ void debug_mask_kernel(uint32_t key, uint32_t thr, int64_t idx0, int6
 }
 int debug_dropout_mask(uint32_t key, uint32_t thr, int64_t idx0, int64_t n, uint8_t *keep, cudaStream_t st) {
   if (n == 0) return 0;
-  debug_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, thr, idx0, n, keep);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  debug_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, thr, idx0, n, keep); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }

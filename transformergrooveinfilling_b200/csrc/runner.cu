@@ -14,6 +14,23 @@ namespace gt {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 
+// ---- launch accounting ------------------------------------------------------------------------
+static int64_t g_launches[KC_MAX] = {0};
+static int g_prof_class = KC_NONE;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+
+LaunchScope::LaunchScope(int c, cudaStream_t s) : cls(c), st(s), slot(-1) {
+  ++g_launches[c];
+  if (c == g_prof_class && g_prof_used < g_prof_events.size()) {
+    slot = (int)g_prof_used++;
+    cudaEventRecord(g_prof_events[slot].first, st);
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (slot >= 0) cudaEventRecord(g_prof_events[slot].second, st);
+}
+
 int validate_config(const gt_config *c) {
   GT_CHECK(c != nullptr, "null config");
   GT_CHECK(c->d_model >= 1 && c->d_model <= 512, "d_model must be in [1,512]");
@@ -560,6 +577,38 @@ int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p, i
                           void *stream) {
   GT_CHECK(keep && n >= 0, "gt_debug_dropout_mask: bad arguments");
   return debug_dropout_mask(site_key(seed, step, site), drop_threshold(p), idx0, n, keep, (cudaStream_t)stream);
+}
+
+int64_t gt_launch_count(int kernel_class) {
+  if (kernel_class < 0) { int64_t t = 0; for (int i = 0; i < KC_MAX; ++i) t += g_launches[i]; return t; }
+  return kernel_class < KC_MAX ? g_launches[kernel_class] : 0;
+}
+
+int gt_profile_enable(int kernel_class, int max_records) {
+  for (auto &e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_prof_events.clear();
+  g_prof_used = 0;
+  g_prof_class = KC_NONE;
+  if (kernel_class <= 0 || kernel_class >= KC_MAX || max_records <= 0) return 0;
+  g_prof_events.resize((size_t)max_records);
+  for (auto &e : g_prof_events) { GT_CUDA(cudaEventCreate(&e.first)); GT_CUDA(cudaEventCreate(&e.second)); }
+  g_prof_class = kernel_class;
+  return 0;
+}
+
+int gt_profile_collect(double *total_ms, int64_t *launches) {
+  GT_CHECK(total_ms && launches, "gt_profile_collect: null pointer");
+  double tot = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    GT_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+    float ms = 0.f;
+    GT_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = (int64_t)g_prof_used;
+  g_prof_used = 0;
+  return 0;
 }
 
 int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k, int variant, void *stream) {
