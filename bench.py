@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the groove_b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one full training step (forward with dropout, calculate_loss, backward, optimizer update)
+over one synthetic batch of 2-bar grooves (32 steps x 27 hvo channels) of the workload's shape.
+Rank 0 prints ONE JSON line (see DESIGN.md §Measurement for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# hyper-parameters verbatim from the reference yamls (C1..C5); `batch` is the per-GPU
+# synthetic batch used for throughput
+WORKLOADS = {
+    "c1": dict(yaml="InfillingClosedHH_testing_training.yaml", d=32, H=4, F=16, L=6, Ld=0, E=16, p=0.18, lr=0.094, pen=0.47, batch=65536),
+    "c2": dict(yaml="InfillingClosedHH_training.yaml", d=32, H=16, F=512, L=6, Ld=0, E=16, p=0.24, lr=0.07, pen=0.38, batch=32768),
+    "c3": dict(yaml="InfillingKicksAndSnares_training.yaml", d=256, H=2, F=512, L=6, Ld=0, E=16, p=0.30, lr=0.089, pen=0.73, batch=8192),
+    "c4": dict(yaml="InfillingRandom_test_large.yaml", d=256, H=16, F=64, L=11, Ld=0, E=16, p=0.15, lr=0.04, pen=1.0, batch=8192),
+    "c5": dict(yaml="InfillingClosedHH_Symbolic_training.yaml(encoder_only=0)", d=32, H=16, F=512, L=6, Ld=6, E=27, p=0.24, lr=0.07, pen=0.38, batch=16384),
+}
+
+
+def train_flops_per_seq(w):
+    """Algorithmic FLOPs per sequence: 2 FLOP/MAC, backward = 2x forward, recompute
+    not counted, element-wise / softmax / LN not counted."""
+    d, F, L, Ld, E = w["d"], w["F"], w["L"], w["Ld"], w["E"]
+    mac = 32 * E * d + L * (32 * (4 * d * d + 2 * d * F) + 2 * 32 * 32 * d) + 32 * d * 27
+    if Ld:
+        mac += 32 * 27 * d + Ld * (32 * (8 * d * d + 2 * d * F) + 4 * 32 * 32 * d)
+    return 3 * 2 * mac
+
+
+def synth_batch(w, n, seed):
+    """SURVEY.md §8d synthetic inputs, generated on the CPU with a seeded generator."""
+    g = torch.Generator().manual_seed(seed)
+    hits = (torch.rand(n, 32, 9, generator=g) < 0.15).float()
+    y = torch.cat((hits, torch.rand(n, 32, 9, generator=g) * hits, (torch.rand(n, 32, 9, generator=g) - 0.5) * hits), 2)
+    if w["E"] == 27:
+        h2 = (torch.rand(n, 32, 9, generator=g) < 0.15).float()
+        x = torch.cat((h2, torch.rand(n, 32, 9, generator=g) * h2, (torch.rand(n, 32, 9, generator=g) - 0.5) * h2), 2)
+    else:
+        m = (torch.rand(n, 32, 8, generator=g) < 0.5).float()
+        x = torch.cat((torch.rand(n, 32, 8, generator=g) * m, (torch.rand(n, 32, 8, generator=g) - 0.5) * m), 2)
+    return x.contiguous(), y.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 100 ms through NVML while running."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_baseline(w, steps, warmup, batch, dropout):
+    """The oracle port (oracle/groove_oracle.py: the reference's arithmetic as plain torch-CPU tensor
+    ops + autograd, torch-native dropout like the reference's nn.Dropout) timed on this box's host
+    cores: forward + calculate_loss + backward + SGD update per step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import groove_oracle as G
+    torch.set_num_threads(os.cpu_count())
+    G.FAST_BASELINE = True
+    cfg = G.GrooveCfg(w["d"], w["H"], w["F"], w["L"], w["Ld"], w["E"], 27, dropout)
+    P = G.det_params(cfg)
+    x, y = synth_batch(w, batch, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, grads, _ = G.train_step_oracle(P, cfg, x, y, w["pen"], G.DropCtx(dropout, train=True, native=True))
+        P = {k: G.sgd_step(v, grads[k], w["lr"]) for k, v in P.items()}
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    return batch * len(times) / tot, tot / len(times)
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 512 if args.steps + args.warmup <= 30 else 256
+    v, sec = cpu_baseline(w, args.steps, args.warmup, batch, w["p"])
+    line = {
+        "impl": "reference", "metric": "train_seq_per_s", "value": v, "unit": "seq/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, args, batch, 1, "f32-cpu"),
+        "cpu_baseline": {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps of batch {batch} ({w['yaml']}, dropout {w['p']}, SGD), oracle port on host CPU"},
+        "e2e": {"value": v, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, per_gpu_batch, world, precision):
+    return {"workload": f"{w['yaml']} full train step (fwd+loss+bwd+{args.optimizer})", "d_model": w["d"], "nhead": w["H"],
+            "dim_feedforward": w["F"], "num_encoder_layers": w["L"], "num_decoder_layers": w["Ld"], "dropout": w["p"],
+            "hit_loss_penalty": w["pen"], "optimizer": args.optimizer, "per_gpu_batch": per_gpu_batch,
+            "global_batch": per_gpu_batch * world, "seq_len": 32, "channels": 27, "precision": precision,
+            "parallelism": f"dp{world}",
+            "l2_policy": "per-step working set (inputs + saved activations) is far larger than the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: workload table)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import ctypes as C
+    import torch.distributed as dist
+    from transformergrooveinfilling_b200 import FusedAdam, FusedSGD, GrooveTransformer, GrooveTransformerEncoder, _lib
+    from transformergrooveinfilling_b200.dp import DataParallelStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the groove_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n = args.batch or w["batch"]
+
+    def make(precision):
+        if w["Ld"]:
+            m = GrooveTransformer(w["d"], w["E"], 27, w["H"], w["F"], w["p"], w["L"], w["Ld"], 32, dev)
+        else:
+            m = GrooveTransformerEncoder(w["d"], w["E"], 27, w["H"], w["F"], w["p"], w["L"], 32, dev)
+        m.set_precision(precision).set_seed(1234).train()
+        return m
+
+    torch.manual_seed(0)
+    precision = args.precision
+    model = None
+    if precision in ("auto", "bf16"):
+        try:
+            model = make("bf16")
+            model._workspace(4, 1, dev)          # raises if the tensor-core path does not cover this shape
+            precision = "bf16"
+        except RuntimeError:
+            if args.precision == "bf16":
+                raise
+            model = None
+    if model is None:
+        torch.manual_seed(0)
+        model, precision = make("fp32"), "fp32"
+    if world > 1:                                   # identical replicas
+        dist.broadcast(model.flat_parameters().detach(), 0)
+    opt = FusedAdam(model, 1e-3) if args.optimizer == "adam" else FusedSGD(model, w["lr"])
+    dp = DataParallelStep(model, opt, w["pen"])
+
+    xh, yh = synth_batch(w, n, 1234 + rank)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    x, y = xh.to(dev), yh.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident():
+        dp.step(x, y)
+
+    metrics_host = torch.empty(6, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        x.copy_(xh, non_blocking=True)
+        y.copy_(yh, non_blocking=True)
+        m = dp.step(x, y)
+        metrics_host.copy_(m, non_blocking=False)      # the step's result (loss + 5 metrics) read back every step
+
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- timed region: kernel-resident throughput, dominant kernel class bracketed by CUDA events ----
+    dom = {"bf16": 18, "fp32": 1}[precision]
+    lib.gt_profile_enable(dom, 4096)
+    l0 = lib.gt_launch_count(-1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.finish()
+    launches = lib.gt_launch_count(-1) - l0
+    tot_ms, cnt = C.c_double(0), C.c_int64(0)
+    lib.gt_profile_collect(C.byref(tot_ms), C.byref(cnt))
+    dom_launches_per_step = lib.gt_launch_count(dom)
+    lib.gt_profile_enable(0, 0)
+    # ---- end-to-end: pinned host inputs copied in, metrics copied out, every step ----
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    final_loss = float(metrics_host[0])
+
+    value = n * world * args.steps / (ms / 1e3)
+    e2e = n * world * args.steps / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fl_step = train_flops_per_seq(w) * n
+    roof = None
+    if cnt.value > 0:
+        # the dominant kernel class and the share of the step's algorithmic FLOPs its launches carry
+        if precision == "bf16":
+            L_all = w["L"] + w["Ld"]
+            layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
+            fl_launch = 2 * 2 * layer_mac * n           # one encoder layer backward = 2x its forward FLOPs
+            kname = "tc_layer_bwd"
+        else:
+            fl_launch = fl_step * args.steps / max(cnt.value, 1)   # every contraction except attention runs in gemm_f32
+            kname = "gemm_f32 (fp32 FMA; tensor peak shown for reference only)"
+        avg_ms = tot_ms.value / cnt.value
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = fl_launch / (avg_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
+                "kernel_share_of_step": tot_ms.value / ms}
+    line = {
+        "metric": "train_seq_per_s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(w, args, n, world, precision),
+        "step_tflops": fl_step * world * args.steps / (ms / 1e3) / 1e12,
+        "roofline": roof,
+        "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4, "d2h_bytes_per_step": 24,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = 512
+        v, sec = cpu_baseline(w, 4, 1, cb, w["p"])
+        v0, _ = cpu_baseline(w, 6, 1, cb, 0.0)
+        line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"4 steps of batch {cb}, same workload (dropout {w['p']}, torch-native masks), SGD; oracle port on host CPU",
+                                "value_dropout0": v0, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,11 @@ import torch
 T_STEPS = 32          # BGT max_len; train.py:128 hard-wires 32
 N_VOICES = 9
 
+# When the port is TIMED as the CPU baseline (bench.py) it uses the same fused ATen CPU ops the
+# reference's nn modules dispatch to (F.linear, F.layer_norm, F.scaled_dot_product_attention,
+# F.dropout), so the baseline is not handicapped by the spelled-out arithmetic used for parity.
+FAST_BASELINE = False
+
 # ----------------------------------------------------------------------------------------------
 # deterministic integer hashing (shared definition with csrc/rng.cuh)
 # ----------------------------------------------------------------------------------------------
@@ -124,8 +129,11 @@ def site_id(stack: int, layer: int, k: int) -> int:
 class DropCtx:
     """Carries (p, seed, step, first global sequence index) and applies the shared masks."""
 
-    def __init__(self, p=0.0, seed=0, step=0, seq0=0, train=True):
+    def __init__(self, p=0.0, seed=0, step=0, seq0=0, train=True, native=False):
         self.p, self.seed, self.step, self.seq0, self.train = p, seed, step, seq0, train
+        # native=True: torch's own dropout (what the reference's nn.Dropout does) — used only when the
+        # oracle is TIMED as the CPU baseline, never for parity
+        self.native = native
 
     def active(self):
         return self.train and dropout_threshold(self.p) > 0
@@ -134,6 +142,8 @@ class DropCtx:
         """x: [N, 32, W]; element index = ((seq0+n)*32 + t)*W + c."""
         if not self.active():
             return x
+        if self.native:
+            return torch.nn.functional.dropout(x, self.p, True)
         n, t, w = x.shape
         idx = (np.arange(n * t * w, dtype=np.uint64) + np.uint64(self.seq0 * t * w))
         keep = dropout_keep(self.seed, self.step, site, idx, self.p).reshape(n, t, w)
@@ -143,6 +153,8 @@ class DropCtx:
         """pr: [N, H, 32, 32]; element index = (((seq0+n)*H + h)*32 + i)*32 + j."""
         if not self.active():
             return pr
+        if self.native:
+            return torch.nn.functional.dropout(pr, self.p, True)
         n, h, a, b = pr.shape
         idx = (np.arange(n * h * a * b, dtype=np.uint64) + np.uint64(self.seq0 * h * a * b))
         keep = dropout_keep(self.seed, self.step, site, idx, self.p).reshape(n, h, a, b)
@@ -163,8 +175,17 @@ def positional_table(d_model: int, max_len: int = T_STEPS) -> torch.Tensor:
     return tab[None]
 
 
+def lin(x, w, b):
+    """y = x W^T + b (torch.nn.Linear)."""
+    if FAST_BASELINE:
+        return torch.nn.functional.linear(x, w, b)
+    return x @ w.T + b
+
+
 def layer_norm(x, g, b, eps=1e-5):
     """torch.nn.LayerNorm over the last dim, biased variance (torch/nn/functional.py layer_norm)."""
+    if FAST_BASELINE:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * g + b
@@ -172,7 +193,7 @@ def layer_norm(x, g, b, eps=1e-5):
 
 def input_layer(P, pre, x, pe, drop: DropCtx, site):
     """BGT/models/io_layers.py:17-22 — dropout(relu(x W^T + b) + pe)."""
-    r = torch.relu(x @ P[pre + ".Linear.weight"].T + P[pre + ".Linear.bias"])
+    r = torch.relu(lin(x, P[pre + ".Linear.weight"], P[pre + ".Linear.bias"]))
     return drop.rows(r + pe.to(r.dtype), site)
 
 
@@ -183,25 +204,33 @@ def mha(P, pre, xq, xkv, nhead, drop: DropCtx, site, causal=False):
     n, t, d = xq.shape
     dh = d // nhead
     w, b = P[pre + ".in_proj_weight"], P[pre + ".in_proj_bias"]
-    q = xq @ w[:d].T + b[:d]
-    k = xkv @ w[d:2 * d].T + b[d:2 * d]
-    v = xkv @ w[2 * d:].T + b[2 * d:]
+    if FAST_BASELINE and xq is xkv:
+        q, k, v = torch.nn.functional.linear(xq, w, b).chunk(3, dim=-1)
+    else:
+        q = xq @ w[:d].T + b[:d]
+        k = xkv @ w[d:2 * d].T + b[d:2 * d]
+        v = xkv @ w[2 * d:].T + b[2 * d:]
     split = lambda z: z.reshape(n, -1, nhead, dh).permute(0, 2, 1, 3)      # [N,H,T,dh]
     q, k, v = split(q), split(k), split(v)
+    if FAST_BASELINE:
+        ctx = torch.nn.functional.scaled_dot_product_attention(q, k, v, dropout_p=drop.p if drop.active() else 0.0,
+                                                               is_causal=causal)
+        ctx = ctx.permute(0, 2, 1, 3).reshape(n, t, d)
+        return torch.nn.functional.linear(ctx, P[pre + ".out_proj.weight"], P[pre + ".out_proj.bias"])
     s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
     if causal:   # BGT/models/utils.py:53-56 — 0 on/below the diagonal, -inf above
         s = s + torch.triu(torch.full((t, t), float("-inf"), dtype=s.dtype), diagonal=1)
     pr = drop.probs(torch.softmax(s, dim=-1), site)
     ctx = (pr @ v).permute(0, 2, 1, 3).reshape(n, t, d)
-    return ctx @ P[pre + ".out_proj.weight"].T + P[pre + ".out_proj.bias"]
+    return lin(ctx, P[pre + ".out_proj.weight"], P[pre + ".out_proj.bias"])
 
 
 def encoder_layer(P, pre, x, nhead, drop: DropCtx, li):
     """torch/nn/modules/transformer.py:951-956 (post-norm), _sa_block :961-977, _ff_block :980-982."""
     a = mha(P, pre + ".self_attn", x, x, nhead, drop, site_id(0, li, 0))
     x = layer_norm(x + drop.rows(a, site_id(0, li, 1)), P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
-    h = drop.rows(torch.relu(x @ P[pre + ".linear1.weight"].T + P[pre + ".linear1.bias"]), site_id(0, li, 2))
-    f = h @ P[pre + ".linear2.weight"].T + P[pre + ".linear2.bias"]
+    h = drop.rows(torch.relu(lin(x, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"])), site_id(0, li, 2))
+    f = lin(h, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"])
     return layer_norm(x + drop.rows(f, site_id(0, li, 3)), P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
 
 
@@ -211,14 +240,14 @@ def decoder_layer(P, pre, y, mem, nhead, drop: DropCtx, li):
     y = layer_norm(y + drop.rows(a, site_id(1, li, 1)), P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
     c = mha(P, pre + ".multihead_attn", y, mem, nhead, drop, site_id(1, li, 4))
     y = layer_norm(y + drop.rows(c, site_id(1, li, 5)), P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
-    h = drop.rows(torch.relu(y @ P[pre + ".linear1.weight"].T + P[pre + ".linear1.bias"]), site_id(1, li, 2))
-    f = h @ P[pre + ".linear2.weight"].T + P[pre + ".linear2.bias"]
+    h = drop.rows(torch.relu(lin(y, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"])), site_id(1, li, 2))
+    f = lin(h, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"])
     return layer_norm(y + drop.rows(f, site_id(1, li, 3)), P[pre + ".norm3.weight"], P[pre + ".norm3.bias"])
 
 
 def output_layer(P, z):
     """BGT/models/io_layers.py:36-48 — channels 0-8 raw hit logits, 9-17 sigmoid, 18-26 0.5*tanh."""
-    y = z @ P["OutputLayer.Linear.weight"].T + P["OutputLayer.Linear.bias"]
+    y = lin(z, P["OutputLayer.Linear.weight"], P["OutputLayer.Linear.bias"])
     v9 = y.shape[-1] // 3
     return y[..., :v9], torch.sigmoid(y[..., v9:2 * v9]), 0.5 * torch.tanh(y[..., 2 * v9:])
 

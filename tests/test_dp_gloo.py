@@ -1,0 +1,77 @@
+"""World-size-2 gloo test (CPU) of the data-parallel step logic: shard -> local gradient ->
+all-reduce(SUM) -> 1/world -> update equals the single-process step on the full batch.  The local
+gradient is produced by the oracle (test infrastructure) because there is no GPU here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import groove_oracle as G
+
+CFG = G.GrooveCfg(16, 2, 8, 1, 0, 16, 27)
+PEN, LR, N = 0.5, 0.1, 8
+
+
+class _FlatSGD:
+    def __init__(self, flat, lr):
+        self.flat, self.lr, self.grad_scale, self.grad = flat, lr, 1.0, None
+
+    def step(self):
+        self.flat -= self.lr * self.grad_scale * self.grad
+
+
+def _names():
+    return [k for k, _ in G.param_shapes(CFG)]
+
+
+def _flatten(d):
+    return torch.cat([d[k].reshape(-1) for k in _names()])
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from transformergrooveinfilling_b200.dp import DataParallelStep, shard_bounds
+    P = G.det_params(CFG)
+    flat = _flatten(P).clone()
+    x, y = G.det_batch(CFG, N)
+    lo, hi = shard_bounds(N, rank, world)
+    opt = _FlatSGD(flat, LR)
+
+    def compute(xl, yl):
+        loss6, grads, _ = G.train_step_oracle(P, CFG, xl, yl, PEN, G.DropCtx(0.0))
+        opt.grad = _flatten(grads)
+        return torch.tensor(loss6, dtype=torch.float32), opt.grad
+
+    dp = DataParallelStep(None, opt, PEN, compute=compute)
+    metrics = dp.step(x[lo:hi], y[lo:hi], reduce_metrics=True)
+    if rank == 0:
+        torch.save({"flat": flat, "metrics": metrics, "scale": opt.grad_scale}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_step_equals_single_process(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    P = G.det_params(CFG)
+    x, y = G.det_batch(CFG, N)
+    loss6, grads, _ = G.train_step_oracle(P, CFG, x, y, PEN, G.DropCtx(0.0))
+    want = _flatten(P) - LR * _flatten(grads)
+    assert got["scale"] == 0.5
+    np.testing.assert_allclose(got["flat"].numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got["metrics"].numpy(), np.array(loss6), rtol=2e-5)
+
+
+def test_shard_bounds():
+    from transformergrooveinfilling_b200.dp import shard_bounds
+    assert [shard_bounds(8, r, 4) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    with pytest.raises(ValueError):
+        shard_bounds(10, 0, 4)
