@@ -27,16 +27,34 @@ __global__ void __launch_bounds__(128) tc_debug_gemm_kernel(const uint16_t *__re
   if (warp == 0) tmem_alloc(&tmem_slot, ncols);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 
-  // stage operands: thread = row, 16-byte chunks along K
-  for (int kb = 0; kb < K / 8; ++kb) {
-    uint4 v = *reinterpret_cast<const uint4 *>(A + (size_t)(m0 + tid) * K + kb * 8);
-    *reinterpret_cast<uint4 *>(sA + kmajor_off(tid, kb * 8, 128)) = v;
-  }
-  for (int r = tid; r < N; r += 128)
+  // stage operands: 16-byte chunks.  bit2 / bit3: the operand is given TRANSPOSED in global memory
+  // ([K, M] / [K, N] row-major) and staged with k as the row index -> consumed as an MN-major operand.
+  const bool a_t = variant & 4, b_t = variant & 8;
+  if (!a_t) {
     for (int kb = 0; kb < K / 8; ++kb) {
-      uint4 v = *reinterpret_cast<const uint4 *>(B + (size_t)r * K + kb * 8);
-      *reinterpret_cast<uint4 *>(sB + kmajor_off(r, kb * 8, N)) = v;
+      uint4 v = *reinterpret_cast<const uint4 *>(A + (size_t)(m0 + tid) * K + kb * 8);
+      *reinterpret_cast<uint4 *>(sA + kmajor_off(tid, kb * 8, 128)) = v;
     }
+  } else {
+    for (int k = tid; k < K; k += 128)
+      for (int mb = 0; mb < 16; ++mb) {
+        uint4 v = *reinterpret_cast<const uint4 *>(A + (size_t)k * M + m0 + mb * 8);
+        *reinterpret_cast<uint4 *>(sA + kmajor_off(k, mb * 8, K)) = v;
+      }
+  }
+  if (!b_t) {
+    for (int r = tid; r < N; r += 128)
+      for (int kb = 0; kb < K / 8; ++kb) {
+        uint4 v = *reinterpret_cast<const uint4 *>(B + (size_t)r * K + kb * 8);
+        *reinterpret_cast<uint4 *>(sB + kmajor_off(r, kb * 8, N)) = v;
+      }
+  } else {
+    for (int k = tid; k < K; k += 128)
+      for (int nb = 0; nb < N / 8; ++nb) {
+        uint4 v = *reinterpret_cast<const uint4 *>(B + (size_t)k * N + nb * 8);
+        *reinterpret_cast<uint4 *>(sB + kmajor_off(k, nb * 8, K)) = v;
+      }
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -44,12 +62,17 @@ __global__ void __launch_bounds__(128) tc_debug_gemm_kernel(const uint16_t *__re
   const uint32_t tmem = tmem_slot;
 
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N);
-    uint32_t a_lbo = (128 / 8) * 128, a_sbo = 128, b_lbo = (uint32_t)(N / 8) * 128, b_sbo = 128;
+    const uint32_t idesc = make_idesc_bf16(128, N, a_t ? 1 : 0, b_t ? 1 : 0);
+    // K-major image [R rows x K]: K-adjacent core matrices (R/8)*128 B apart (LBO), row-adjacent 128 B (SBO).
+    // MN-major use of an image [K rows x R]: k-adjacent cores 128 B apart (LBO), mn-adjacent (K/8)*128 B (SBO).
+    uint32_t a_lbo = a_t ? 128u : (128 / 8) * 128u, a_sbo = a_t ? (uint32_t)(K / 8) * 128u : 128u;
+    uint32_t b_lbo = b_t ? 128u : (uint32_t)(N / 8) * 128u, b_sbo = b_t ? (uint32_t)(K / 8) * 128u : 128u;
     if (variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
     for (int k16 = 0; k16 < K / 16; ++k16) {
-      uint64_t ad = make_desc(smem_u32(sA) + (uint32_t)(k16 * 2) * (128 / 8) * 128, a_lbo, a_sbo);
-      uint64_t bd = make_desc(smem_u32(sB) + (uint32_t)(k16 * 2) * (N / 8) * 128, b_lbo, b_sbo);
+      uint32_t a_off = a_t ? (uint32_t)(k16 * 2) * 128u : (uint32_t)(k16 * 2) * (128 / 8) * 128u;
+      uint32_t b_off = b_t ? (uint32_t)(k16 * 2) * 128u : (uint32_t)(k16 * 2) * (uint32_t)(N / 8) * 128u;
+      uint64_t ad = make_desc(smem_u32(sA) + a_off, a_lbo, a_sbo);
+      uint64_t bd = make_desc(smem_u32(sB) + b_off, b_lbo, b_sbo);
       mma_bf16_ss(tmem, ad, bd, idesc, k16 > 0 ? 1u : 0u);
     }
     mma_commit(&bar);
