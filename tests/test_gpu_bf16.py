@@ -1,0 +1,105 @@
+"""bf16 tensor-core path (fused tcgen05 encoder-layer kernels) against the oracle.
+Tolerances per BASELINE.json north_star for the bf16 mode: per-step loss within 2e-3 relative,
+thresholded hits agreeing on >= 99.9 % of cells."""
+import numpy as np
+import pytest
+import torch
+
+import groove_oracle as G
+from _util import build_model, grads_by_name, rel_err
+from transformergrooveinfilling_b200 import FusedSGD
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 2e-3
+
+SHAPES = {
+    "c1": (G.GrooveCfg(32, 4, 16, 6, 0, 16, 27), 0.47, 0.18),
+    "c2": (G.GrooveCfg(32, 16, 512, 6, 0, 16, 27), 0.38, 0.24),
+    "c5enc": (G.GrooveCfg(32, 16, 512, 2, 0, 27, 27), 0.38, 0.24),
+    "f48_h32": (G.GrooveCfg(32, 32, 48, 1, 0, 16, 27), 0.5, 0.1),
+    "f96_h1": (G.GrooveCfg(32, 1, 96, 2, 0, 16, 27), 0.5, 0.1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+@pytest.mark.parametrize("n", [4, 7])
+def test_eval_forward(name, n):
+    cfg, pen, p = SHAPES[name]
+    model, P = build_model(cfg, dropout=p, precision="bf16")
+    model.eval()
+    x, y = G.det_batch(cfg, n)
+    with torch.no_grad():
+        h, v, o = model(x.cuda())
+    rh, rv, ro = G.forward_encoder_only(P, cfg, x)
+    assert rel_err(h.cpu().numpy(), rh.numpy()) < 3e-2
+    assert np.abs(v.cpu().numpy() - rv.numpy()).max() < 2e-2 and np.abs(o.cpu().numpy() - ro.numpy()).max() < 2e-2
+    ph, pv, po = model.predict(x.cuda())
+    oh, _, _ = G.predict_encoder_only(P, cfg, x)
+    # random-init logits hover around 0 (|logit| ~ 0.3), so bf16 rounding flips ~1 % of the near-threshold cells;
+    # the 99.9 % agreement of the north star is checked on decisive logits in test_hit_agreement_after_training
+    assert (ph.cpu() == oh).float().mean() >= 0.97
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+def test_train_forward_with_dropout(name):
+    cfg, pen, p = SHAPES[name]
+    model, P = build_model(cfg, dropout=p, precision="bf16")
+    model.set_seed(99, step=2, seq0=5).train()
+    x, y = G.det_batch(cfg, 6)
+    with torch.no_grad():
+        h, v, o = model(x.cuda())
+    drop = G.DropCtx(p=p, seed=99, step=2, seq0=5, train=True)
+    rh, rv, ro = G.output_layer(P, G.encode(P, cfg, x, drop))
+    assert rel_err(h.cpu().numpy(), rh.numpy()) < 3e-2
+    assert np.abs(v.cpu().numpy() - rv.numpy()).max() < 2e-2
+
+
+@pytest.mark.parametrize("name,n", [("c1", 5), ("c1", 64), ("c2", 4), ("c2", 64), ("f48_h32", 3), ("f96_h1", 6)])
+def test_train_step_matches_oracle(name, n):
+    cfg, pen, p = SHAPES[name]
+    model, P = build_model(cfg, dropout=p, precision="bf16")
+    model.set_seed(7, step=1, seq0=0).train()
+    x, y = G.det_batch(cfg, n)
+    metrics, hvo = model.train_step(x.cuda(), y.cuda(), pen)
+    loss6, grads, _ = G.train_step_oracle(P, cfg, x, y, pen, G.DropCtx(p, 7, 1, 0, True))
+    got = metrics.cpu().numpy().astype(np.float64)
+    assert abs(got[0] - loss6[0]) / abs(loss6[0]) < LOSS_RTOL, (got, loss6)
+    gg = grads_by_name(model)
+    worst = ("", 0.0)
+    for k, w in grads.items():
+        scale = float(w.abs().max())
+        if scale < 1e-6:
+            continue
+        e = float((gg[k] - w).abs().max()) / scale
+        if e > worst[1]:
+            worst = (k, e)
+    # bf16 operand rounding is independent per sample: the gradient error is ~3 % of each tensor's max at
+    # n=4 and falls as 1/sqrt(n) (tools/diag_bf16_grad.py: 0.8 % median at n=64); a logic error would not shrink
+    assert worst[1] < (4e-2 if n >= 64 else 0.2), f"gradient mismatch {worst}"
+
+
+def test_loss_trajectory_bf16_vs_fp32():
+    """20 SGD steps from identical weights / data / dropout masks: the bf16 path tracks the fp32 path
+    (itself within 1e-4 of the reference) within 2e-3 relative at every step."""
+    cfg, pen, p = SHAPES["c2"]
+    x, y = [t.cuda() for t in G.det_batch(cfg, 64)]
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        model, _ = build_model(cfg, dropout=p, precision=prec)
+        model.set_seed(3).train()
+        opt = FusedSGD(model, 0.07)
+        t = []
+        for _ in range(20):
+            m, _ = model.train_step(x, y, pen)
+            opt.step()
+            t.append(float(m[0]))
+        traj[prec] = np.array(t)
+    np.testing.assert_allclose(traj["bf16"], traj["fp32"], rtol=LOSS_RTOL)
+    assert traj["fp32"][-1] < traj["fp32"][0]
+
+
+def test_unsupported_shapes_fail_loudly():
+    cfg = G.GrooveCfg(256, 16, 64, 1, 0, 16, 27)
+    model, _ = build_model(cfg, dropout=0.0, precision="bf16")
+    with pytest.raises(RuntimeError, match="not available"):
+        model.train_step(*[t.cuda() for t in G.det_batch(cfg, 4)], 1.0)

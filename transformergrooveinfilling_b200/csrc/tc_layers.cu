@@ -1,0 +1,950 @@
+// tc_layers.cu — fused per-layer kernels of the bf16 tensor-core path.  See tc_layers.cuh.
+#include "tc_layers.cuh"
+#include "umma.cuh"
+
+namespace gt {
+using namespace umma;
+
+bool tc_shape_supported(const gt_config &c, std::string *why) {
+  auto no = [&](const char *m) { if (why) *why = m; return false; };
+  if (c.n_dec != 0) return no("encoder-decoder models run in precision=fp32 (the fused tcgen05 layer kernels cover the encoder stack)");
+  if (c.d_model != 32) return no("fused tcgen05 layer kernels are instantiated for d_model=32");
+  if (c.n_enc > TC_MAX_LAYERS) return no("more than 16 layers");
+  if (c.dim_ff % 16 != 0 || c.dim_ff > 512) return no("dim_feedforward must be a multiple of 16 and <= 512 (TMEM-resident weight gradients)");
+  if (tc_ffn_chunk(c.dim_ff) == 0) return no("dim_feedforward has no valid chunking");
+  int dh = c.d_model / c.nhead;
+  if (dh != 1 && (dh & 1)) return no("head dim must be 1 or even");
+  return true;
+}
+
+// =============================================================================================
+// weight prep: fp32 master parameters -> bf16 canonical K-major operand images (one block per layer)
+// =============================================================================================
+__device__ __forceinline__ uint4 pack8(const float *s) {
+  float4 a = *reinterpret_cast<const float4 *>(s), b = *reinterpret_cast<const float4 *>(s + 4);
+  return make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+}
+
+__global__ void tc_prep_kernel(TcPrepArgs a) {
+  const int l = blockIdx.y;
+  const int D = a.D, F = a.F, FC = a.FC;
+  const TcImg o = tc_img(D, F);
+  uint8_t *img = a.img + (size_t)l * a.img_stride;
+  const int kb_d = D / 8, kb_f = F / 8;
+  const int n_qkv = 3 * D * kb_d, n_wo = D * kb_d, n_w1 = F * kb_d, n_w2 = D * kb_f;
+  const int total = n_qkv + n_wo + n_w1 + n_w2;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+    int i = id;
+    if (i < n_qkv) {
+      int r = i / kb_d, kb = i % kb_d;
+      *reinterpret_cast<uint4 *>(img + o.wqkv + kmajor_off(r, kb * 8, 3 * D)) = pack8(a.params + a.w_in[l] + (int64_t)r * D + kb * 8);
+      continue;
+    }
+    i -= n_qkv;
+    if (i < n_wo) {
+      int r = i / kb_d, kb = i % kb_d;
+      *reinterpret_cast<uint4 *>(img + o.wo + kmajor_off(r, kb * 8, D)) = pack8(a.params + a.w_out[l] + (int64_t)r * D + kb * 8);
+      continue;
+    }
+    i -= n_wo;
+    if (i < n_w1) {                     // W1 [F, D]: chunk c = rows c*FC.. -> image [FC x D]
+      int gr = i / kb_d, kb = i % kb_d, c = gr / FC, r = gr % FC;
+      *reinterpret_cast<uint4 *>(img + o.w1 + (size_t)c * FC * D * 2 + kmajor_off(r, kb * 8, FC)) =
+          pack8(a.params + a.w1[l] + (int64_t)gr * D + kb * 8);
+      continue;
+    }
+    i -= n_w1;
+    {                                   // W2 [D, F]: chunk c = columns c*FC.. -> image [D x FC]
+      int j = i / kb_f, gk = (i % kb_f) * 8, c = gk / FC, kk = gk % FC;
+      *reinterpret_cast<uint4 *>(img + o.w2 + (size_t)c * D * FC * 2 + kmajor_off(j, kk, D)) =
+          pack8(a.params + a.w2[l] + (int64_t)j * F + gk);
+    }
+  }
+}
+
+int tc_prep_weights(const TcPrepArgs &a, cudaStream_t st) {
+  dim3 grid(16, a.n_layers);
+  { LaunchScope _ls(KC_TC_PREP, st);
+    tc_prep_kernel<<<grid, 256, 0, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// shared device helpers
+// =============================================================================================
+// A operand: image of a [128 x K] tile.  B operand: image of an [N x K] weight (chunk).
+__device__ __forceinline__ uint64_t desc_a128(uint32_t base, int k16) { return make_desc(base + (uint32_t)k16 * 2u * 2048u, 2048u, 128u); }
+__device__ __forceinline__ uint64_t desc_b(uint32_t base, int N, int k16) {
+  const uint32_t kstride = (uint32_t)(N >> 3) * 128u;
+  return make_desc(base + (uint32_t)k16 * 2u * kstride, kstride, 128u);
+}
+// two dropout decisions from one hash (idx_even must be even): returns scale or 0 for each
+__device__ __forceinline__ void drop2(const Drop &d, uint64_t idx_even, float &m0, float &m1) {
+  if (d.thr == 0) { m0 = 1.f; m1 = 1.f; return; }
+  uint64_t w = idx_even >> 1;
+  uint32_t x = (uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu);
+  uint32_t h = mix32((x * 0x9E3779B1u) ^ d.key);
+  m0 = ((h & 0xFFFFu) >= d.thr) ? d.scale : 0.f;
+  m1 = ((h >> 16) >= d.thr) ? d.scale : 0.f;
+}
+
+struct SmemPlan {
+  uint32_t w, par, xa, qkv, ctx, h, total;
+};
+__host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
+__host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC) {
+  SmemPlan s;
+  s.w = 0;
+  s.par = al128(tc_img(D, F).total);
+  s.xa = al128(s.par + (uint32_t)(9 * D + F) * 4u);
+  s.qkv = al128(s.xa + 128u * D * 2u);
+  s.ctx = al128(s.qkv + 128u * (3u * D + 1u) * 4u);
+  s.h = al128(s.ctx + 128u * D * 2u);
+  s.total = al128(s.h + 128u * FC * 2u);
+  return s;
+}
+
+// =============================================================================================
+// forward: x_in -> QKV (UMMA) -> attention (SIMT) -> out-proj (UMMA) -> +res, LN1 -> FFN1 (UMMA,
+// chunked) -> relu/dropout -> FFN2 (UMMA, accumulating in TMEM) -> +res, LN2 -> x_out
+// torch/nn/modules/transformer.py:951-956 (post-norm encoder layer)
+// =============================================================================================
+template <int D>
+__global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs a) {
+  static_assert(D % 16 == 0 && (3 * D / 2) % 16 == 0, "unsupported d_model");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, half = tid >> 7;
+  const int F = a.F, FC = a.FC, H = a.H, dh = a.dh, nchunk = F / FC;
+  const SmemPlan sp = fwd_smem(D, F, FC);
+  const TcImg io = tc_img(D, F);
+  uint8_t *sW = smem + sp.w;
+  float *sPar = reinterpret_cast<float *>(smem + sp.par);
+  float *p_bqkv = sPar, *p_bo = sPar + 3 * D, *p_b1 = p_bo + D, *p_b2 = p_b1 + F, *p_g1 = p_b2 + D, *p_be1 = p_g1 + D,
+        *p_g2 = p_be1 + D, *p_be2 = p_g2 + D;
+  uint8_t *sXa = smem + sp.xa;
+  float *sQKV = reinterpret_cast<float *>(smem + sp.qkv);
+  uint8_t *sCtx = smem + sp.ctx;
+  uint8_t *sH = smem + sp.h;
+  constexpr int LS = 3 * D + 1;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  for (int i = tid; i < 3 * D; i += 256) p_bqkv[i] = a.bqkv[i];
+  for (int i = tid; i < F; i += 256) p_b1[i] = a.b1[i];
+  if (tid < D) {
+    p_bo[tid] = a.bo[tid]; p_b2[tid] = a.b2[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid];
+    p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid];
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {          // stage the layer's operand images with bulk TMA, one transaction barrier
+    mbar_expect_tx(&bar_w, a.img_bytes);
+    for (uint32_t off = 0; off < a.img_bytes; off += 32768u) {
+      uint32_t n = a.img_bytes - off < 32768u ? a.img_bytes - off : 32768u;
+      tma_load_1d(sW + off, a.img + off, n, &bar_w);
+    }
+  }
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_big = tmem, t_small = tmem + 128;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t aXa = smem_u32(sXa), aCtx = smem_u32(sCtx), aH = smem_u32(sH), aW = smem_u32(sW);
+  mbar_wait(&bar_w, 0);
+  uint32_t ph = 0;
+  const float attn_scale = rsqrtf((float)dh) * 1.4426950408889634f;   // 1/sqrt(dh) * log2(e)
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t grow = (int64_t)tile * TC_TILE + row;
+    const bool valid = grow < a.M;
+    // ---- P0: x_in tile -> bf16 A operand ----
+    {
+      constexpr int CH = D / 16;                       // 8-column chunks per thread (half a row)
+      const float *src = a.x_in + grow * D + half * (D / 2);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = pack8(src + c * 8);
+        *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, half * (D / 2) + c * 8, 128)) = v;
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- P1: QKV = x Wqkv^T ----
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, 3 * D);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.wqkv, 3 * D, k), idesc, k > 0);
+      mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;
+    fence_after_sync();
+    // ---- P2: + bias -> fp32 q|k|v rows in shared memory ----
+    {
+      constexpr int PER = 3 * D / 2;
+      for (int cb = half * PER; cb < (half + 1) * PER; cb += 16) {
+        float v[16];
+        tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sQKV[row * LS + cb + j] = v[j] + p_bqkv[cb + j];
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    // ---- P3: attention, one warp per (sequence, head), lane = query row ----
+    for (int p = warp; p < 4 * H; p += 8) {
+      const int s = p / H, h = p - s * H;
+      const int r = s * 32 + lane;
+      const float *q = sQKV + r * LS + h * dh;
+      const float *kb = sQKV + (s * 32) * LS + D + h * dh;
+      const float *vb = kb + D;
+      float sc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = 0.f;
+      for (int c = 0; c < dh; ++c) {
+        const float qc = q[c];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc[j] = fmaf(qc, kb[j * LS + c], sc[j]);
+      }
+      float mx = sc[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sc[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { sc[j] = exp2f((sc[j] - mx) * attn_scale); sum += sc[j]; }
+      const float inv = 1.f / sum;
+      const uint64_t base = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float m0, m1;
+        drop2(a.d_attn, base + j, m0, m1);
+        sc[j] *= inv * m0; sc[j + 1] *= inv * m1;
+      }
+      int c = 0;
+      for (; c + 1 < dh; c += 2) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { o0 = fmaf(sc[j], vb[j * LS + c], o0); o1 = fmaf(sc[j], vb[j * LS + c + 1], o1); }
+        *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r, h * dh + c, 128)) = pack_bf16(o0, o1);
+      }
+      if (c < dh) {
+        float o0 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o0 = fmaf(sc[j], vb[j * LS + c], o0);
+        *reinterpret_cast<__nv_bfloat16 *>(sCtx + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(o0);
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- P4: out-proj ----
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_small, desc_a128(aCtx, k), desc_b(aW + io.wo, D, k), idesc, k > 0);
+      mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;
+    fence_after_sync();
+    // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = row, warps 0-3) ----
+    float x1[D];
+    if (half == 0) {
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, x1 + cb);
+      tmem_ld_wait();
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      float s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        float4 xr = valid ? *reinterpret_cast<const float4 *>(a.x_in + grow * D + c) : make_float4(0, 0, 0, 0);
+        float m0, m1, m2, m3;
+        drop2(a.d1, e0 + c, m0, m1);
+        drop2(a.d1, e0 + c + 2, m2, m3);
+        x1[c] = xr.x + (x1[c] + p_bo[c]) * m0;
+        x1[c + 1] = xr.y + (x1[c + 1] + p_bo[c + 1]) * m1;
+        x1[c + 2] = xr.z + (x1[c + 2] + p_bo[c + 2]) * m2;
+        x1[c + 3] = xr.w + (x1[c + 3] + p_bo[c + 3]) * m3;
+        s1 += (x1[c] + x1[c + 1]) + (x1[c + 2] + x1[c + 3]);
+        if (a.u1 && valid) *reinterpret_cast<float4 *>(a.u1 + grow * D + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
+      }
+      const float mu = s1 * (1.f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { float t = x1[c] - mu; q = fmaf(t, t, q); }
+      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+#pragma unroll
+      for (int c = 0; c < D; ++c) x1[c] = (x1[c] - mu) * rs * p_g1[c] + p_be1[c];
+#pragma unroll
+      for (int c = 0; c < D; c += 8)
+        *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c, 128)) =
+            make_uint4(pack_bf16(x1[c], x1[c + 1]), pack_bf16(x1[c + 2], x1[c + 3]), pack_bf16(x1[c + 4], x1[c + 5]),
+                       pack_bf16(x1[c + 6], x1[c + 7]));
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- P6: FFN, hidden dimension in chunks of FC; FFN2 accumulates in TMEM across chunks ----
+    const uint32_t idesc1 = make_idesc_bf16(128, FC), idesc2 = make_idesc_bf16(128, D);
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1, FC, k), idesc1, k > 0);
+      mma_commit(&bar_mma);
+    }
+    const bool epi = (FC >= 32) || (half == 0);
+    const int per = FC >= 32 ? FC / 2 : FC;
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&bar_mma, ph); ph ^= 1;               // FFN1(c) (and FFN2(c-1)) complete
+      fence_after_sync();
+      if (epi) {
+        const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC);
+        for (int cb = half * per; cb < half * per + per; cb += 16) {
+          float v[16];
+          tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float m0, m1;
+            drop2(a.d_ffn, e0 + cb + j, m0, m1);
+            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f) * m0;
+            float h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f) * m1;
+            pk[j >> 1] = pack_bf16(h0, h1);
+          }
+          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        for (int k = 0; k < FC / 16; ++k)
+          mma_bf16_ss(t_small, desc_a128(aH, k), desc_b(aW + io.w2 + (uint32_t)c * D * FC * 2u, D, k), idesc2, (c | k) > 0);
+        if (c + 1 < nchunk) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), idesc1, k > 0);
+        }
+        mma_commit(&bar_mma);
+      }
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;                 // last FFN2 complete
+    fence_after_sync();
+    // ---- P8: + bias, dropout, + residual, LayerNorm2 -> x_out ----
+    if (half == 0) {
+      float f[D];
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, f + cb);
+      tmem_ld_wait();
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      float s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; c += 2) {
+        float m0, m1;
+        drop2(a.d2, e0 + c, m0, m1);
+        f[c] = x1[c] + (f[c] + p_b2[c]) * m0;
+        f[c + 1] = x1[c + 1] + (f[c + 1] + p_b2[c + 1]) * m1;
+        s1 += f[c] + f[c + 1];
+      }
+      if (a.u2 && valid) {
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.u2 + grow * D + c) = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
+      }
+      const float mu = s1 * (1.f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { float t = f[c] - mu; q = fmaf(t, t, q); }
+      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < D; c += 4)
+          *reinterpret_cast<float4 *>(a.x_out + grow * D + c) =
+              make_float4((f[c] - mu) * rs * p_g2[c] + p_be2[c], (f[c + 1] - mu) * rs * p_g2[c + 1] + p_be2[c + 1],
+                          (f[c + 2] - mu) * rs * p_g2[c + 2] + p_be2[c + 2], (f[c + 3] - mu) * rs * p_g2[c + 3] + p_be2[c + 3]);
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
+  GT_CHECK(D == 32, "tc_layer_fwd: d_model not instantiated");
+  const SmemPlan sp = fwd_smem(D, a.F, a.FC);
+  GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
+  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  { LaunchScope _ls(KC_TC_LAYER_FWD, st);
+    tc_layer_fwd_kernel<32><<<grid, 256, sp.total, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// backward of one encoder layer.  Recomputes LN statistics, q|k|v, the attention probabilities and
+// the FFN hidden activations tile by tile; ALL weight gradients of the layer accumulate in TMEM
+// across the CTA's tiles (dW1, dW2^T, dWqkv, dWo: 320 columns) via MN-major UMMAs that contract
+// over the 128 tokens of the tile, and are flushed once per CTA with fp32 atomics.
+//
+// TMEM map (512 columns): [0,128) working (q|k|v / H chunk / dH chunk)  [128,160) dx accumulators
+// [160,192) dctx   [192,320) dW1 chunks   [320,448) dW2^T chunks   [448,480) dWqkv   [480,512) dWo
+// =============================================================================================
+struct BwdSmem {
+  uint32_t w, par, gpar, xin, x1, da, ctx, dq, qkv, dctx, h, dh, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem(int D, int F) {
+  BwdSmem s;
+  s.w = 0;
+  s.par = al128(tc_img(D, F).total);
+  s.gpar = al128(s.par + (uint32_t)(9 * D + F) * 4u);
+  s.xin = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);
+  s.x1 = s.xin + 128u * D * 2u;
+  s.da = s.x1 + 128u * D * 2u;
+  s.ctx = s.da + 128u * D * 2u;
+  s.dq = s.ctx + 128u * D * 2u;                       // dqkv image [128 x 3D]; M-padded reads run into the union below
+  uint32_t u = al128(s.dq + 128u * 3u * D * 2u);
+  s.qkv = u;                                          // attention phase: fp32 q|k|v rows + fp32 dctx rows
+  s.dctx = al128(s.qkv + 128u * (3u * D + 1u) * 4u);
+  uint32_t end_attn = al128(s.dctx + 128u * (D + 1u) * 4u);
+  s.h = u;                                            // FFN phase (aliases the attention scratch): H and dH images
+  s.dh = s.h + 128u * 128u * 2u;
+  uint32_t end_ffn = s.dh + 128u * 128u * 2u;
+  s.total = end_attn > end_ffn ? end_attn : end_ffn;
+  return s;
+}
+
+// per-lane vector of 32 values -> lane l receives the sum over the warp's lanes of v[l]  (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ float warp_sum_all(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// MN-major views of the row-major images (contract over the image's ROW index)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t base, int rows, int k16) {      // image [rows(k) x cols(mn)]
+  return make_desc(base + (uint32_t)k16 * 256u, 128u, (uint32_t)(rows >> 3) * 128u);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
+  static_assert(D == 32, "the register-tile column sums assume d_model == 32");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, half = tid >> 7;
+  const int F = a.F, FC = a.FC, H = a.H, dh = a.dh, nchunk = F / FC;
+  const BwdSmem sp = bwd_smem(D, F);
+  const TcImg io = tc_img(D, F);
+  uint8_t *sW = smem + sp.w;
+  float *sPar = reinterpret_cast<float *>(smem + sp.par);
+  float *p_bqkv = sPar, *p_bo = sPar + 3 * D, *p_b1 = p_bo + D, *p_b2 = p_b1 + F, *p_g1 = p_b2 + D, *p_be1 = p_g1 + D,
+        *p_g2 = p_be1 + D, *p_be2 = p_g2 + D;
+  float *sG = reinterpret_cast<float *>(smem + sp.gpar);       // gradient partials, same order as sPar
+  float *g_bqkv = sG, *g_bo = sG + 3 * D, *g_b1 = g_bo + D, *g_b2 = g_b1 + F, *g_g1 = g_b2 + D, *g_be1 = g_g1 + D,
+        *g_g2 = g_be1 + D, *g_be2 = g_g2 + D;
+  uint8_t *sXin = smem + sp.xin, *sX1 = smem + sp.x1, *sDA = smem + sp.da, *sCtx = smem + sp.ctx, *sDQ = smem + sp.dq;
+  float *sQKV = reinterpret_cast<float *>(smem + sp.qkv);
+  float *sDC = reinterpret_cast<float *>(smem + sp.dctx);
+  uint8_t *sH = smem + sp.h, *sDH = smem + sp.dh;
+  constexpr int LS = 3 * D + 1, LC = D + 1;
+  (void)p_bo; (void)p_b2; (void)p_be2;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  for (int i = tid; i < 9 * D + F; i += 256) sG[i] = 0.f;
+  for (int i = tid; i < 3 * D; i += 256) p_bqkv[i] = a.bqkv[i];
+  for (int i = tid; i < F; i += 256) p_b1[i] = a.b1[i];
+  if (tid < D) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; p_g2[tid] = a.g2[tid]; }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, a.img_bytes);
+    for (uint32_t off = 0; off < a.img_bytes; off += 32768u) {
+      uint32_t n = a.img_bytes - off < 32768u ? a.img_bytes - off : 32768u;
+      tma_load_1d(sW + off, a.img + off, n, &bar_w);
+    }
+  }
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_big = tmem, t_sa = tmem + 128, t_sb = tmem + 160, t_dw1 = tmem + 192, t_dw2 = tmem + 320,
+                 t_dwqkv = tmem + 448, t_dwo = tmem + 480;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t aW = smem_u32(sW), aXin = smem_u32(sXin), aX1 = smem_u32(sX1), aDA = smem_u32(sDA), aCtx = smem_u32(sCtx),
+                 aDQ = smem_u32(sDQ), aH = smem_u32(sH), aDH = smem_u32(sDH);
+  mbar_wait(&bar_w, 0);
+  uint32_t ph = 0;
+  const float inv_sqrt_dh = rsqrtf((float)dh);
+  const float attn_scale = inv_sqrt_dh * 1.4426950408889634f;
+  const bool epi = (FC >= 32) || (half == 0);
+  const int per = FC >= 32 ? FC / 2 : FC;
+  // instruction descriptors
+  const uint32_t id_kk_fc = make_idesc_bf16(128, FC, 0, 0);      // H chunk          A K-major, B K-major
+  const uint32_t id_kmn_fc = make_idesc_bf16(128, FC, 0, 1);     // dH chunk         A K-major, B MN-major
+  const uint32_t id_kmn_d = make_idesc_bf16(128, D, 0, 1);       // dx / dctx        A K-major, B MN-major
+  const uint32_t id_mnmn_d = make_idesc_bf16(128, D, 1, 1);      // weight gradients A MN-major, B MN-major
+  const uint32_t id_kk_3d = make_idesc_bf16(128, 3 * D, 0, 0);   // q|k|v recompute
+
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++iter) {
+    const int64_t grow = (int64_t)tile * TC_TILE + row;
+    const bool valid = grow < a.M;
+    const uint32_t acc0 = iter > 0 ? 1u : 0u;
+    float du[D];                       // half 0: gradient w.r.t. the LayerNorm input currently being processed
+    float mean1 = 0.f, rstd1 = 0.f;
+    // ---- B0: LN2 backward, x1 = LN1(u1) ; half 1 stages x_in ----
+    if (half == 0) {
+      float xh[D];
+      float s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u2_in + grow * D + c) : make_float4(0, 0, 0, 0);
+        xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
+        s1 += (t.x + t.y) + (t.z + t.w);
+        float4 g = valid ? *reinterpret_cast<const float4 *>(a.dy + grow * D + c) : make_float4(0, 0, 0, 0);
+        du[c] = g.x; du[c + 1] = g.y; du[c + 2] = g.z; du[c + 3] = g.w;
+      }
+      float mu = s1 * (1.f / D), q = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
+      float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      float m1 = 0.f, m2 = 0.f;
+      float w[32];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        xh[c] *= rs;
+        w[c] = du[c] * xh[c];                        // d gamma contribution
+        float g = du[c] * p_g2[c];
+        m1 += g; m2 = fmaf(g, xh[c], m2);
+      }
+      m1 *= (1.f / D); m2 *= (1.f / D);
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_g2[lane], t); }
+#pragma unroll
+      for (int c = 0; c < D; ++c) w[c] = du[c];
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_be2[lane], t); }
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      uint32_t pk[D / 2];
+#pragma unroll
+      for (int c = 0; c < D; c += 2) {
+        du[c] = rs * (du[c] * p_g2[c] - m1 - xh[c] * m2);
+        du[c + 1] = rs * (du[c + 1] * p_g2[c + 1] - m1 - xh[c + 1] * m2);
+        float k0, k1;
+        drop2(a.d2, e0 + c, k0, k1);
+        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da2 = grad wrt the FFN2 output (+bias)
+        pk[c >> 1] = pack_bf16(w[c], w[c + 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < D; c += 8)
+        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_b2[lane], t); }
+      // x1 = LN1(u1)
+      s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
+        xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
+        s1 += (t.x + t.y) + (t.z + t.w);
+      }
+      mu = s1 * (1.f / D); q = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
+      rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      mean1 = mu; rstd1 = rs;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = xh[c + j] * rs * p_g1[c + j] + p_be1[c + j];
+        *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) =
+            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = pack8(a.x_in + grow * D + c);
+        *reinterpret_cast<uint4 *>(sXin + kmajor_off(row, c, 128)) = v;
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- B1: FFN backward, chunk by chunk ----
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1, FC, k), id_kk_fc, k > 0);
+      mma_commit(&bar_mma);
+    }
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&bar_mma, ph); ph ^= 1;               // H(c) accumulator ready (and every earlier MMA retired)
+      fence_after_sync();
+      uint32_t mask_lo = 0, mask_hi = 0;              // (kept && h > 0) for this thread's columns of the chunk
+      if (epi) {
+        const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC);
+        int bit = 0;
+        for (int cb = half * per; cb < half * per + per; cb += 16) {
+          float v[16];
+          tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+          uint32_t bits = 0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float m0, m1;
+            drop2(a.d_ffn, e0 + cb + j, m0, m1);
+            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f) * m0;
+            float h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f) * m1;
+            bits |= (h0 > 0.f ? 1u : 0u) << j;
+            bits |= (h1 > 0.f ? 1u : 0u) << (j + 1);
+            pk[j >> 1] = pack_bf16(h0, h1);
+          }
+          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (bit < 32) mask_lo |= bits << bit; else mask_hi |= bits << (bit - 32);
+          bit += 16;
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {                                 // dH(c) = da2 . W2[:, chunk]   (B: MN-major view of the W2 chunk image [D x FC])
+        fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_bf16_ss(t_big, desc_a128(aDA, k), desc_mn(aW + io.w2 + (uint32_t)c * D * FC * 2u, D, k), id_kmn_fc, k > 0);
+        mma_commit(&bar_mma);
+      }
+      mbar_wait(&bar_mma, ph); ph ^= 1;
+      fence_after_sync();
+      if (epi) {
+        const float sc = a.d_ffn.scale;
+        int bit = 0;
+        for (int cb = half * per; cb < half * per + per; cb += 32) {
+          float w[32];
+          const int nb = (half * per + per - cb) >= 32 ? 2 : 1;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (b < nb) {
+              tmem_ld16(t_big + lane_off + (uint32_t)(cb + 16 * b), w + 16 * b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[16 + j] = 0.f;
+            }
+          }
+          tmem_ld_wait();
+          const uint32_t bits32 = (bit == 0) ? mask_lo : mask_hi;       // per <= 64: at most two 32-column groups
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = ((bits32 >> j) & 1u) ? w[j] * sc : 0.f;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (b < nb) {
+              *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb + 16 * b, 128)) =
+                  make_uint4(pack_bf16(w[16 * b], w[16 * b + 1]), pack_bf16(w[16 * b + 2], w[16 * b + 3]),
+                             pack_bf16(w[16 * b + 4], w[16 * b + 5]), pack_bf16(w[16 * b + 6], w[16 * b + 7]));
+              *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb + 16 * b + 8, 128)) =
+                  make_uint4(pack_bf16(w[16 * b + 8], w[16 * b + 9]), pack_bf16(w[16 * b + 10], w[16 * b + 11]),
+                             pack_bf16(w[16 * b + 12], w[16 * b + 13]), pack_bf16(w[16 * b + 14], w[16 * b + 15]));
+            }
+          }
+          const float t = warp_colsum32(w, lane);     // bias gradient of linear1 for 32 columns
+          if (lane < 16 * nb) atomicAdd(&g_b1[c * FC + cb + lane], t);
+          bit += 32;
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t w1c = aW + io.w1 + (uint32_t)c * FC * D * 2u;
+        for (int k = 0; k < FC / 16; ++k)             // dx1 += dH . W1[chunk, :]     (B: MN-major view of the W1 chunk image [FC x D])
+          mma_bf16_ss(t_sa, desc_a128(aDH, k), desc_mn(w1c, FC, k), id_kmn_d, (c | k) > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                 // contract over the tile's 128 tokens
+          mma_bf16_ss(t_dw1 + 32u * c, desc_mn(aDH, 128, k), desc_mn(aX1, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);   // dW1[chunk]   += dH^T x1
+          mma_bf16_ss(t_dw2 + 32u * c, desc_mn(aH, 128, k), desc_mn(aDA, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);    // dW2^T[chunk] += H^T da2
+        }
+        if (c + 1 < nchunk) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), id_kk_fc, k > 0);
+        }
+        mma_commit(&bar_mma);
+      }
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;                 // dx1 complete, all weight-gradient MMAs of this tile retired
+    fence_after_sync();
+    // ---- B2: LN1 backward ----
+    if (half == 0) {
+      float acc[D], xh[D];
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+      tmem_ld_wait();
+      float m1 = 0.f, m2 = 0.f;
+      float w[32];
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
+        xh[c] = (t.x - mean1) * rstd1; xh[c + 1] = (t.y - mean1) * rstd1; xh[c + 2] = (t.z - mean1) * rstd1; xh[c + 3] = (t.w - mean1) * rstd1;
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        du[c] += acc[c];                              // grad wrt x1 = residual path + FFN path
+        w[c] = du[c] * xh[c];
+        float g = du[c] * p_g1[c];
+        m1 += g; m2 = fmaf(g, xh[c], m2);
+      }
+      m1 *= (1.f / D); m2 *= (1.f / D);
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_g1[lane], t); }
+#pragma unroll
+      for (int c = 0; c < D; ++c) w[c] = du[c];
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_be1[lane], t); }
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      uint32_t pk[D / 2];
+#pragma unroll
+      for (int c = 0; c < D; c += 2) {
+        du[c] = rstd1 * (du[c] * p_g1[c] - m1 - xh[c] * m2);
+        du[c + 1] = rstd1 * (du[c + 1] * p_g1[c + 1] - m1 - xh[c + 1] * m2);
+        float k0, k1;
+        drop2(a.d1, e0 + c, k0, k1);
+        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da1 = grad wrt the out-proj output (+bias)
+        pk[c >> 1] = pack_bf16(w[c], w[c + 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < D; c += 8)
+        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_bo[lane], t); }
+      if (valid) {                                    // park du1 (residual path into dx) in the output buffer
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(du[c], du[c + 1], du[c + 2], du[c + 3]);
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- B3: recompute q|k|v ; dctx = da1 . Wo ----
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXin, k), desc_b(aW + io.wqkv, 3 * D, k), id_kk_3d, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_sb, desc_a128(aDA, k), desc_mn(aW + io.wo, D, k), id_kmn_d, k > 0);
+      mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;
+    fence_after_sync();
+    {
+      constexpr int PER = 3 * D / 2;
+      for (int cb = half * PER; cb < (half + 1) * PER; cb += 16) {
+        float v[16];
+        tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sQKV[row * LS + cb + j] = v[j] + p_bqkv[cb + j];
+      }
+      if (half == 0) {
+        for (int cb = 0; cb < D; cb += 16) {
+          float v[16];
+          tmem_ld16(t_sb + lane_off + (uint32_t)cb, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sDC[row * LC + cb + j] = v[j];
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    // ---- B5: attention backward, one warp per (sequence, head), lane = query row; dK/dV via warp transposed sums ----
+    for (int p = warp; p < 4 * H; p += 8) {
+      const int s = p / H, h = p - s * H;
+      const int r = s * 32 + lane;
+      const float *q = sQKV + r * LS + h * dh;
+      const float *kb = sQKV + (s * 32) * LS + D + h * dh;
+      const float *vb = kb + D;
+      const float *go = sDC + r * LC + h * dh;
+      float pr[32], dp[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { pr[j] = 0.f; dp[j] = 0.f; }
+      for (int c = 0; c < dh; ++c) {
+        const float qc = q[c], gc = go[c];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { pr[j] = fmaf(qc, kb[j * LS + c], pr[j]); dp[j] = fmaf(gc, vb[j * LS + c], dp[j]); }
+      }
+      float mx = pr[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, pr[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { pr[j] = exp2f((pr[j] - mx) * attn_scale); sum += pr[j]; }
+      const float inv = 1.f / sum;
+      const uint64_t base = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 32);
+      float pd[32];
+      float delta = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float m0, m1;
+        drop2(a.d_attn, base + j, m0, m1);
+        pr[j] *= inv; pr[j + 1] *= inv;
+        pd[j] = pr[j] * m0; pd[j + 1] = pr[j + 1] * m1;
+        dp[j] *= m0; dp[j + 1] *= m1;
+        delta = fmaf(dp[j], pr[j], delta);
+        delta = fmaf(dp[j + 1], pr[j + 1], delta);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dp[j] = pr[j] * (dp[j] - delta) * inv_sqrt_dh;      // dS
+      for (int c = 0; c < dh; ++c) {
+        float o = 0.f, dq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { o = fmaf(pd[j], vb[j * LS + c], o); dq = fmaf(dp[j], kb[j * LS + c], dq); }
+        *reinterpret_cast<__nv_bfloat16 *>(sCtx + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(o);
+        *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(dq);
+        const float qc = q[c], gc = go[c];
+        float w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = dp[j] * qc;
+        const float dk = warp_colsum32(w, lane);      // lane = key row
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = pd[j] * gc;
+        const float dv = warp_colsum32(w, lane);
+        *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, D + h * dh + c, 128)) = __float2bfloat16_rn(dk);
+        *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, 2 * D + h * dh + c, 128)) = __float2bfloat16_rn(dv);
+        const float sq = warp_sum_all(dq), sk = warp_sum_all(dk), sv = warp_sum_all(dv);
+        if (lane == 0) {
+          atomicAdd(&g_bqkv[h * dh + c], sq);
+          atomicAdd(&g_bqkv[D + h * dh + c], sk);
+          atomicAdd(&g_bqkv[2 * D + h * dh + c], sv);
+        }
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- B6: dx_in = dqkv . Wqkv ; dWqkv += dqkv^T x_in ; dWo += da1^T ctx ----
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 3 * D / 16; ++k) mma_bf16_ss(t_sa, desc_a128(aDQ, k), desc_mn(aW + io.wqkv, 3 * D, k), id_kmn_d, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        mma_bf16_ss(t_dwqkv, desc_mn(aDQ, 128, k), desc_mn(aXin, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);
+        mma_bf16_ss(t_dwo, desc_mn(aDA, 128, k), desc_mn(aCtx, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);
+      }
+      mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, ph); ph ^= 1;
+    fence_after_sync();
+    if (half == 0) {
+      float acc[D];
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+          float4 t = *reinterpret_cast<const float4 *>(a.dx + grow * D + c);
+          *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(t.x + acc[c], t.y + acc[c + 1], t.z + acc[c + 2], t.w + acc[c + 3]);
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  // ---- flush: TMEM-resident weight gradients and shared-memory bias / LayerNorm partials -> global (fp32 atomics) ----
+  fence_after_sync();
+  {
+    const int m = row;                                // TMEM lane = output row of the weight-gradient blocks
+    for (int c = half; c < nchunk; c += 2) {          // half 0: even chunks, half 1: odd chunks
+      float v[D];
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_dw1 + 32u * c + lane_off + (uint32_t)cb, v + cb);
+      tmem_ld_wait();
+      if (m < FC) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) atomicAdd(a.gw1 + (int64_t)(c * FC + m) * D + i, v[i]);
+      }
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_dw2 + 32u * c + lane_off + (uint32_t)cb, v + cb);
+      tmem_ld_wait();
+      if (m < FC) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) atomicAdd(a.gw2 + (int64_t)j * F + c * FC + m, v[j]);
+      }
+    }
+    {
+      float v[D];
+      const uint32_t t = half == 0 ? t_dwqkv : t_dwo;
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t + lane_off + (uint32_t)cb, v + cb);
+      tmem_ld_wait();
+      if (half == 0 && m < 3 * D) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) atomicAdd(a.gwqkv + (int64_t)m * D + i, v[i]);
+      }
+      if (half == 1 && m < D) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) atomicAdd(a.gwo + (int64_t)m * D + i, v[i]);
+      }
+    }
+  }
+  for (int i = tid; i < 3 * D; i += 256) atomicAdd(a.gbqkv + i, g_bqkv[i]);
+  for (int i = tid; i < F; i += 256) atomicAdd(a.gb1 + i, g_b1[i]);
+  if (tid < D) {
+    atomicAdd(a.gbo + tid, g_bo[tid]); atomicAdd(a.gb2 + tid, g_b2[tid]);
+    atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
+    atomicAdd(a.gg2 + tid, g_g2[tid]); atomicAdd(a.gbe2 + tid, g_be2[tid]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
+  GT_CHECK(D == 32, "tc_layer_bwd: d_model not instantiated");
+  GT_CHECK(a.F / a.FC <= 4, "tc_layer_bwd: more than 4 FFN chunks do not fit the TMEM gradient accumulators");
+  const BwdSmem sp = bwd_smem(D, a.F);
+  GT_CHECK(sp.total <= 227 * 1024, "tc_layer_bwd: shared memory budget exceeded");
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
+  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  { LaunchScope _ls(KC_TC_LAYER_BWD, st);
+    tc_layer_bwd_kernel<32><<<grid, 256, sp.total, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gt

@@ -1,4 +1,7 @@
 // tc_path.cu — bf16 tensor-core path (tcgen05 / TMEM / bulk TMA).  See DESIGN.md §"bf16 path".
+#include <string.h>
+
+#include "tc_layers.cuh"
 #include "tc_path.cuh"
 #include "umma.cuh"
 
@@ -107,18 +110,221 @@ int tc_debug_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, 
 }
 
 // =============================================================================================
-// model passes — filled in by tc_layers.cu
+// model passes (encoder-only): the L encoder layers run in the fused tcgen05 kernels of
+// tc_layers.cu; the input layer, the final LayerNorm + output head and the loss (a few % of the
+// step, K = 16..32 contractions) reuse the fp32 kernels of kernels_simt.cu.
 // =============================================================================================
-static const char *kNoTc = "precision=bf16 is not available for this configuration yet; use precision=fp32";
+struct TcPlan {
+  uint8_t *img;
+  float *r0, *x[TC_MAX_LAYERS + 1], *u1[TC_MAX_LAYERS], *u2[TC_MAX_LAYERS];
+  float *z, *mf, *rf;
+  float *d_hvo, *loss_partials, *dlog, *dxa, *dxb, *g0;
+  int64_t bytes;
+  uint32_t img_stride;
+};
 
-int64_t tc_workspace_bytes(const gt_config &, int64_t, int) { set_error(kNoTc); return -1; }
-int tc_forward(const gt_config &, const Layout &, const float *, const float *, const float *, const float *, int64_t, float *,
-               void *, int64_t, bool, uint64_t, uint64_t, int64_t, cudaStream_t) { GT_FAIL(kNoTc); }
-int tc_backward(const gt_config &, const Layout &, const float *, const float *, const float *, const float *, int64_t,
-                const float *, const float *, float *, void *, int64_t, uint64_t, uint64_t, int64_t, cudaStream_t) { GT_FAIL(kNoTc); }
-int tc_train_step(const gt_config &, const Layout &, const float *, const float *, const float *, const float *, int64_t, float,
-                  float *, float *, float *, void *, int64_t, uint64_t, uint64_t, int64_t, cudaStream_t) { GT_FAIL(kNoTc); }
-int tc_predict(const gt_config &, const Layout &, const float *, const float *, const float *, int64_t, float, float *, void *,
-               int64_t, cudaStream_t) { GT_FAIL(kNoTc); }
+static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, TcPlan &P) {
+  memset(&P, 0, sizeof(P));
+  const int64_t M = n_seq * T, d = c.d_model;
+  int64_t off = 0;
+  auto take = [&](int64_t nbytes) -> char * {
+    int64_t o = off;
+    off += (nbytes + 255) / 256 * 256;
+    return base ? base + o : nullptr;
+  };
+  P.img_stride = (tc_img(c.d_model, c.dim_ff).total + 255u) & ~255u;
+  P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
+  const bool train = mode == 1;
+  P.r0 = reinterpret_cast<float *>(take(M * d * 4));
+  if (train) {
+    for (int l = 0; l <= c.n_enc; ++l) P.x[l] = reinterpret_cast<float *>(take(M * d * 4));
+    for (int l = 0; l < c.n_enc; ++l) {
+      P.u1[l] = reinterpret_cast<float *>(take(M * d * 4));
+      P.u2[l] = reinterpret_cast<float *>(take(M * d * 4));
+    }
+    P.mf = reinterpret_cast<float *>(take(M * 4));
+    P.rf = reinterpret_cast<float *>(take(M * 4));
+  } else {
+    float *a = reinterpret_cast<float *>(take(M * d * 4)), *b = reinterpret_cast<float *>(take(M * d * 4));
+    for (int l = 0; l <= c.n_enc; ++l) P.x[l] = (l & 1) ? b : a;
+  }
+  P.z = reinterpret_cast<float *>(take(M * d * 4));
+  if (train) {
+    P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
+    P.loss_partials = reinterpret_cast<float *>(take(loss_scratch_floats(n_seq) * 4));
+    P.dlog = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
+    P.dxa = reinterpret_cast<float *>(take(M * d * 4));
+    P.dxb = reinterpret_cast<float *>(take(M * d * 4));
+    P.g0 = reinterpret_cast<float *>(take(M * d * 4));
+  }
+  P.bytes = off;
+}
+
+struct TcCtx {
+  gt_config c;
+  const Layout *L;
+  const float *P;
+  float *G;
+  const float *pe;
+  int64_t n_seq, M;
+  bool train;
+  uint64_t seed, step;
+  int64_t seq0;
+  cudaStream_t st;
+  Drop drop(int site) const {
+    Drop d;
+    uint32_t thr = drop_threshold(c.dropout);
+    if (!train || thr == 0) return d;
+    d.thr = thr; d.key = site_key(seed, step, site); d.scale = drop_scale(thr);
+    return d;
+  }
+};
+
+static int tc_check(const gt_config &c, int64_t n_seq, int mode, void *ws, int64_t ws_bytes, TcPlan &pl) {
+  std::string why;
+  GT_CHECK(tc_shape_supported(c, &why), "precision=bf16 is not available for this configuration (" + why + "); use precision=fp32");
+  GT_CHECK(ws != nullptr && ((uintptr_t)ws & 255) == 0, "workspace must be non-null and 256-byte aligned");
+  tc_make_plan(c, n_seq, mode, (char *)ws, pl);
+  GT_CHECK(ws_bytes >= pl.bytes, "workspace too small: need " + std::to_string(pl.bytes) + " bytes");
+  return 0;
+}
+
+int64_t tc_workspace_bytes(const gt_config &c, int64_t n_seq, int mode) {
+  std::string why;
+  if (!tc_shape_supported(c, &why)) {
+    set_error("precision=bf16 is not available for this configuration (" + why + "); use precision=fp32");
+    return -1;
+  }
+  static thread_local TcPlan pl;
+  tc_make_plan(c, n_seq, mode, nullptr, pl);
+  return pl.bytes;
+}
+
+static TcLayerArgs tc_layer_args(const TcCtx &x, const TcPlan &pl, int l) {
+  TcLayerArgs a;
+  memset(&a, 0, sizeof(a));
+  const LayerP &p = x.L->enc[l];
+  a.img = pl.img + (size_t)l * pl.img_stride;
+  a.img_bytes = tc_img(x.c.d_model, x.c.dim_ff).total;
+  a.bqkv = x.P + p.sa.b_in; a.bo = x.P + p.sa.b_out; a.b1 = x.P + p.b1; a.b2 = x.P + p.b2;
+  a.g1 = x.P + p.g1; a.be1 = x.P + p.be1; a.g2 = x.P + p.g2; a.be2 = x.P + p.be2;
+  if (x.G) {
+    a.gwqkv = x.G + p.sa.w_in; a.gbqkv = x.G + p.sa.b_in; a.gwo = x.G + p.sa.w_out; a.gbo = x.G + p.sa.b_out;
+    a.gw1 = x.G + p.w1; a.gb1 = x.G + p.b1; a.gw2 = x.G + p.w2; a.gb2 = x.G + p.b2;
+    a.gg1 = x.G + p.g1; a.gbe1 = x.G + p.be1; a.gg2 = x.G + p.g2; a.gbe2 = x.G + p.be2;
+  }
+  a.M = x.M; a.n_tiles = (int)((x.n_seq + 3) / 4);
+  a.F = x.c.dim_ff; a.FC = tc_ffn_chunk(x.c.dim_ff); a.H = x.c.nhead; a.dh = x.c.d_model / x.c.nhead;
+  a.d_attn = x.drop(site_id(0, l, 0)); a.d1 = x.drop(site_id(0, l, 1)); a.d_ffn = x.drop(site_id(0, l, 2));
+  a.d2 = x.drop(site_id(0, l, 3));
+  a.seq0 = x.seq0;
+  return a;
+}
+
+static int tc_prep(const TcCtx &x, const TcPlan &pl) {
+  TcPrepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params = x.P; a.img = pl.img; a.img_stride = pl.img_stride; a.n_layers = x.c.n_enc;
+  a.D = x.c.d_model; a.F = x.c.dim_ff; a.FC = tc_ffn_chunk(x.c.dim_ff);
+  for (int l = 0; l < x.c.n_enc; ++l) {
+    a.w_in[l] = x.L->enc[l].sa.w_in; a.w_out[l] = x.L->enc[l].sa.w_out; a.w1[l] = x.L->enc[l].w1; a.w2[l] = x.L->enc[l].w2;
+  }
+  return tc_prep_weights(a, x.st);
+}
+
+static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres) {
+  const int d = x.c.d_model;
+  GT_TRY(tc_prep(x, pl));
+  GemmEpi e; e.bias = x.P + x.L->in_enc_b; e.relu = 1;
+  GT_TRY(gemm_f32(src, x.c.e_src, 1, x.P + x.L->in_enc_w, x.c.e_src, 1, pl.r0, d, x.M, d, x.c.e_src, e, 0, x.st));
+  GT_TRY(pe_dropout_fwd(pl.r0, x.pe, pl.x[0], x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  for (int l = 0; l < x.c.n_enc; ++l) {
+    TcLayerArgs a = tc_layer_args(x, pl, l);
+    a.x_in = pl.x[l]; a.x_out = pl.x[l + 1];
+    a.u1 = save ? pl.u1[l] : nullptr; a.u2 = save ? pl.u2[l] : nullptr;
+    GT_TRY(tc_layer_fwd(d, a, x.st));
+  }
+  Drop none;
+  GT_TRY(ln_fwd(pl.x[x.c.n_enc], nullptr, x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, nullptr, pl.z, pl.mf, pl.rf, x.M, d,
+                none, 0, x.st));
+  GemmEpi eh; eh.bias = x.P + x.L->out_b;
+  GT_TRY(gemm_f32(pl.z, d, 1, x.P + x.L->out_w, d, 1, hvo, x.c.e_tgt, x.M, x.c.e_tgt, d, eh, 0, x.st));
+  return head_activation(hvo, x.M, x.c.e_tgt, thres, x.st);
+}
+
+static int tc_wgrad(const TcCtx &x, const float *dY, int64_t N, const float *X, int64_t K, float *dW, float *db) {
+  GemmEpi e; e.atomic = 1;
+  GT_TRY(gemm_f32(dY, 1, N, X, 1, K, dW, K, N, K, x.M, e, 2048, x.st));
+  return colsum_f32(dY, N, x.M, (int)N, db, x.st);
+}
+
+static int tc_backward_all(const TcCtx &x, const TcPlan &pl, const float *src, const float *hvo, const float *d_hvo) {
+  const int d = x.c.d_model, E = x.c.e_tgt;
+  Drop none;
+  GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
+  GT_TRY(tc_wgrad(x, pl.dlog, E, pl.z, d, x.G + x.L->out_w, x.G + x.L->out_b));
+  GemmEpi e0;
+  GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxa, d, x.M, d, E, e0, 0, x.st));
+  GT_TRY(ln_bwd(pl.dxa, pl.x[x.c.n_enc], pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxb, nullptr, x.G + x.L->enc_norm_g,
+                x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+  float *cur = pl.dxb, *oth = pl.dxa;
+  for (int l = x.c.n_enc - 1; l >= 0; --l) {
+    TcLayerArgs a = tc_layer_args(x, pl, l);
+    a.x_in = pl.x[l]; a.u1_in = pl.u1[l]; a.u2_in = pl.u2[l]; a.dy = cur; a.dx = oth;
+    GT_TRY(tc_layer_bwd(d, a, x.st));
+    float *t = cur; cur = oth; oth = t;
+  }
+  GT_TRY(pe_dropout_bwd(cur, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  return tc_wgrad(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b);
+}
+
+static void tc_ctx(TcCtx &x, const gt_config &c, const Layout &L, const float *params, float *grads, const float *pe,
+                   int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  x.c = c; x.L = &L; x.P = params; x.G = grads; x.pe = pe; x.n_seq = n_seq; x.M = n_seq * T; x.train = train;
+  x.seed = seed; x.step = step; x.seq0 = seq0; x.st = st;
+}
+
+int tc_forward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
+               int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, bool train, uint64_t seed, uint64_t step, int64_t seq0,
+               cudaStream_t st) {
+  static thread_local TcPlan pl;
+  // gt_forward(train=1) always saves activations (it is the autograd forward); eval forwards do not
+  GT_TRY(tc_check(c, n_seq, train ? 1 : 0, ws, ws_bytes, pl));
+  TcCtx x;
+  tc_ctx(x, c, L, params, nullptr, pe, n_seq, train, seed, step, seq0, st);
+  return tc_forward_all(x, pl, src, hvo, train, -1.f);
+}
+
+int tc_backward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
+                int64_t n_seq, const float *hvo, const float *d_hvo, float *grads, void *ws, int64_t ws_bytes, uint64_t seed,
+                uint64_t step, int64_t seq0, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  GT_TRY(tc_check(c, n_seq, 1, ws, ws_bytes, pl));
+  TcCtx x;
+  tc_ctx(x, c, L, params, grads, pe, n_seq, true, seed, step, seq0, st);
+  return tc_backward_all(x, pl, src, hvo, d_hvo);
+}
+
+int tc_train_step(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *y,
+                  int64_t n_seq, float penalty, float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,
+                  uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  GT_TRY(tc_check(c, n_seq, 1, ws, ws_bytes, pl));
+  TcCtx x;
+  tc_ctx(x, c, L, params, grads, pe, n_seq, true, seed, step, seq0, st);
+  GT_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * sizeof(float), st));
+  GT_TRY(tc_forward_all(x, pl, src, hvo, true, -1.f));
+  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, st));
+  return tc_backward_all(x, pl, src, hvo, pl.d_hvo);
+}
+
+int tc_predict(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, int64_t n_seq,
+               float thres, float *hvo_out, void *ws, int64_t ws_bytes, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  GT_TRY(tc_check(c, n_seq, 0, ws, ws_bytes, pl));
+  TcCtx x;
+  tc_ctx(x, c, L, params, nullptr, pe, n_seq, false, 0, 0, 0, st);
+  return tc_forward_all(x, pl, src, hvo_out, false, thres);
+}
 
 }  // namespace gt

@@ -273,7 +273,7 @@ class _GrooveBase(nn.Module):
     def _run_forward(self, src, tgt_in, train, save):
         lib = _lib.load()
         n = src.shape[0]
-        ws = self._workspace(n, 1 if save else 0, src.device)
+        ws = self._workspace(n, 1 if (save or train) else 0, src.device)     # gt_forward(train=1) saves activations
         hvo = torch.empty(n, T_STEPS, self.embedding_size_tgt, dtype=torch.float32, device=src.device)
         cfg = self._cfg()
         step = self._step
