@@ -90,7 +90,7 @@ __device__ __forceinline__ void drop2(const Drop &d, uint64_t idx_even, float &m
 }
 
 struct SmemPlan {
-  uint32_t w, par, xa, qkv, ctx, h, total;
+  uint32_t w, par, xa, q, k, v, ctx, h, total;
 };
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC) {
@@ -98,27 +98,133 @@ __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC) {
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
   s.xa = al128(s.par + (uint32_t)(9 * D + F) * 4u);
-  s.qkv = al128(s.xa + 128u * D * 2u);
-  s.ctx = al128(s.qkv + 128u * (3u * D + 1u) * 4u);
+  s.q = al128(s.xa + 128u * D * 2u);                 // fp32 q rows, stride D+4 (16-byte aligned, conflict-free)
+  s.k = al128(s.q + 128u * (D + 4u) * 4u);           // fp32 k, compact per (sequence, head): [4][H][32][dh]
+  s.v = s.k + 128u * D * 4u;
+  s.ctx = al128(s.v + 128u * D * 4u);
   s.h = al128(s.ctx + 128u * D * 2u);
   s.total = al128(s.h + 128u * FC * 2u);
   return s;
+}
+
+// ---- attention score / context inner products for one (sequence, head) pair; lane = query row --------------
+// K and V of the pair are 32 x DH fp32, contiguous and 16-byte aligned (read as warp-wide broadcasts).
+template <int DH>
+__device__ __forceinline__ void attn_scores(const float *q, const float *kh, int dh, float qs, float (&sc)[32]) {
+  if constexpr (DH == 2) {
+    const float2 q2 = *reinterpret_cast<const float2 *>(q);
+    const float q0 = q2.x * qs, q1 = q2.y * qs;
+    const float4 *k4 = reinterpret_cast<const float4 *>(kh);
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const float4 kk = k4[jj];
+      sc[2 * jj] = fmaf(q1, kk.y, q0 * kk.x);
+      sc[2 * jj + 1] = fmaf(q1, kk.w, q0 * kk.z);
+    }
+  } else if constexpr (DH > 0 && DH % 4 == 0) {
+    float qv[DH];
+#pragma unroll
+    for (int c = 0; c < DH; c += 4) {
+      const float4 t = *reinterpret_cast<const float4 *>(q + c);
+      qv[c] = t.x * qs; qv[c + 1] = t.y * qs; qv[c + 2] = t.z * qs; qv[c + 3] = t.w * qs;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; c += 4) {
+        const float4 kk = *reinterpret_cast<const float4 *>(kh + j * DH + c);
+        acc = fmaf(qv[c], kk.x, acc); acc = fmaf(qv[c + 1], kk.y, acc); acc = fmaf(qv[c + 2], kk.z, acc); acc = fmaf(qv[c + 3], kk.w, acc);
+      }
+      sc[j] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sc[j] = 0.f;
+    for (int c = 0; c < dh; ++c) {
+      const float qc = q[c] * qs;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = fmaf(qc, kh[j * dh + c], sc[j]);
+    }
+  }
+}
+// out[c] = sum_j p[j] * vh[j][c]; written as bf16 into the K-major image `img` at (row, col0 + c)
+template <int DH>
+__device__ __forceinline__ void attn_context(const float (&p)[32], const float *vh, int dh, uint8_t *img, int row, int col0) {
+  if constexpr (DH == 2) {
+    const float4 *v4 = reinterpret_cast<const float4 *>(vh);
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const float4 vv = v4[jj];
+      o0 = fmaf(p[2 * jj], vv.x, o0); o1 = fmaf(p[2 * jj], vv.y, o1);
+      o0 = fmaf(p[2 * jj + 1], vv.z, o0); o1 = fmaf(p[2 * jj + 1], vv.w, o1);
+    }
+    *reinterpret_cast<uint32_t *>(img + kmajor_off(row, col0, 128)) = pack_bf16(o0, o1);
+  } else if constexpr (DH > 0 && DH % 4 == 0) {
+    float o[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+      for (int c = 0; c < DH; c += 4) {
+        const float4 vv = *reinterpret_cast<const float4 *>(vh + j * DH + c);
+        o[c] = fmaf(p[j], vv.x, o[c]); o[c + 1] = fmaf(p[j], vv.y, o[c + 1]); o[c + 2] = fmaf(p[j], vv.z, o[c + 2]); o[c + 3] = fmaf(p[j], vv.w, o[c + 3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < DH; c += 2) *reinterpret_cast<uint32_t *>(img + kmajor_off(row, col0 + c, 128)) = pack_bf16(o[c], o[c + 1]);
+  } else {
+    for (int c = 0; c < dh; ++c) {
+      float o = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o = fmaf(p[j], vh[j * dh + c], o);
+      *reinterpret_cast<__nv_bfloat16 *>(img + kmajor_off(row, col0 + c, 128)) = __float2bfloat16_rn(o);
+    }
+  }
+}
+// write one token row's 32 k (or v) values (all heads) into the compact per-(sequence, head) layout
+template <int D, int DH>
+__device__ __forceinline__ void store_kv_row(float *dst, const float (&v)[D], int row, int H, int dh) {
+  const int s = row >> 5, j = row & 31;
+  float *base = dst + s * 32 * D;                    // [H][32][dh] of this sequence
+  if constexpr (DH == 2) {
+#pragma unroll
+    for (int h = 0; h < D / 2; ++h) *reinterpret_cast<float2 *>(base + h * 64 + j * 2) = make_float2(v[2 * h], v[2 * h + 1]);
+  } else if constexpr (DH > 0 && DH % 4 == 0) {
+#pragma unroll
+    for (int h = 0; h < D / DH; ++h)
+#pragma unroll
+      for (int c = 0; c < DH; c += 4)
+        *reinterpret_cast<float4 *>(base + h * 32 * DH + j * DH + c) = make_float4(v[h * DH + c], v[h * DH + c + 1], v[h * DH + c + 2], v[h * DH + c + 3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const int h = c / dh, cc = c - h * dh;
+      base[h * 32 * dh + j * dh + cc] = v[c];
+    }
+  }
+  (void)H;
 }
 
 // =============================================================================================
 // forward: x_in -> QKV (UMMA) -> attention (SIMT) -> out-proj (UMMA) -> +res, LN1 -> FFN1 (UMMA,
 // chunked) -> relu/dropout -> FFN2 (UMMA, accumulating in TMEM) -> +res, LN2 -> x_out
 // torch/nn/modules/transformer.py:951-956 (post-norm encoder layer)
+// 512 threads: thread = (token row = tid & 127, column part = tid >> 7).
 // =============================================================================================
-template <int D>
-__global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs a) {
-  static_assert(D % 16 == 0 && (3 * D / 2) % 16 == 0, "unsupported d_model");
+constexpr int FWD_THREADS = 512;
+
+template <int D, int DH>
+__global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLayerArgs a) {
+  static_assert(D == 32, "q|k|v epilogue assigns one 32-column projection per thread part");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & 127, half = tid >> 7;
-  const int F = a.F, FC = a.FC, H = a.H, dh = a.dh, nchunk = F / FC;
+  const int row = tid & 127, part = tid >> 7;
+  const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   const SmemPlan sp = fwd_smem(D, F, FC);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
@@ -126,15 +232,17 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
   float *p_bqkv = sPar, *p_bo = sPar + 3 * D, *p_b1 = p_bo + D, *p_b2 = p_b1 + F, *p_g1 = p_b2 + D, *p_be1 = p_g1 + D,
         *p_g2 = p_be1 + D, *p_be2 = p_g2 + D;
   uint8_t *sXa = smem + sp.xa;
-  float *sQKV = reinterpret_cast<float *>(smem + sp.qkv);
+  float *sQ = reinterpret_cast<float *>(smem + sp.q);
+  float *sK = reinterpret_cast<float *>(smem + sp.k);
+  float *sV = reinterpret_cast<float *>(smem + sp.v);
   uint8_t *sCtx = smem + sp.ctx;
   uint8_t *sH = smem + sp.h;
-  constexpr int LS = 3 * D + 1;
+  constexpr int LQ = D + 4;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
-  for (int i = tid; i < 3 * D; i += 256) p_bqkv[i] = a.bqkv[i];
-  for (int i = tid; i < F; i += 256) p_b1[i] = a.b1[i];
+  for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
+  for (int i = tid; i < F; i += FWD_THREADS) p_b1[i] = a.b1[i];
   if (tid < D) {
     p_bo[tid] = a.bo[tid]; p_b2[tid] = a.b2[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid];
     p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid];
@@ -155,21 +263,17 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
   const uint32_t aXa = smem_u32(sXa), aCtx = smem_u32(sCtx), aH = smem_u32(sH), aW = smem_u32(sW);
   mbar_wait(&bar_w, 0);
   uint32_t ph = 0;
-  const float attn_scale = rsqrtf((float)dh) * 1.4426950408889634f;   // 1/sqrt(dh) * log2(e)
+  const float attn_scale = rsqrtf((float)dh) * 1.4426950408889634f;   // 1/sqrt(dh) * log2(e), folded into q
+  const float keep_scale = a.d_attn.scale;
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t grow = (int64_t)tile * TC_TILE + row;
     const bool valid = grow < a.M;
-    // ---- P0: x_in tile -> bf16 A operand ----
+    // ---- P0: x_in tile -> bf16 A operand (8 columns per thread) ----
     {
-      constexpr int CH = D / 16;                       // 8-column chunks per thread (half a row)
-      const float *src = a.x_in + grow * D + half * (D / 2);
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (valid) v = pack8(src + c * 8);
-        *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, half * (D / 2) + c * 8, 128)) = v;
-      }
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (valid) v = pack8(a.x_in + grow * D + part * 8);
+      *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, part * 8, 128)) = v;
     }
     fence_async_smem();
     fence_before_sync();
@@ -184,61 +288,55 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
-    // ---- P2: + bias -> fp32 q|k|v rows in shared memory ----
-    {
-      constexpr int PER = 3 * D / 2;
-      for (int cb = half * PER; cb < (half + 1) * PER; cb += 16) {
-        float v[16];
-        tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
-        tmem_ld_wait();
+    // ---- P2: + bias; part 0 -> q rows, part 1 -> k, part 2 -> v (compact per head) ----
+    if (part < 3) {
+      float v[D];
+      tmem_ld16(t_big + lane_off + (uint32_t)(part * D), v);
+      tmem_ld16(t_big + lane_off + (uint32_t)(part * D + 16), v + 16);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sQKV[row * LS + cb + j] = v[j] + p_bqkv[cb + j];
+      for (int c = 0; c < D; c += 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(p_bqkv + part * D + c);
+        v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+      }
+      if (part == 0) {
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(sQ + row * LQ + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      } else {
+        store_kv_row<D, DH>(part == 1 ? sK : sV, v, row, H, dh);
       }
     }
     fence_before_sync();
     __syncthreads();
     // ---- P3: attention, one warp per (sequence, head), lane = query row ----
-    for (int p = warp; p < 4 * H; p += 8) {
+    for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {
       const int s = p / H, h = p - s * H;
       const int r = s * 32 + lane;
-      const float *q = sQKV + r * LS + h * dh;
-      const float *kb = sQKV + (s * 32) * LS + D + h * dh;
-      const float *vb = kb + D;
+      const float *kh = sK + s * 32 * D + h * 32 * dh;
+      const float *vh = sV + s * 32 * D + h * 32 * dh;
       float sc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sc[j] = 0.f;
-      for (int c = 0; c < dh; ++c) {
-        const float qc = q[c];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sc[j] = fmaf(qc, kb[j * LS + c], sc[j]);
-      }
+      attn_scores<DH>(sQ + r * LQ + h * dh, kh, dh, attn_scale, sc);
       float mx = sc[0];
 #pragma unroll
       for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sc[j]);
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { sc[j] = exp2f((sc[j] - mx) * attn_scale); sum += sc[j]; }
-      const float inv = 1.f / sum;
-      const uint64_t base = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 32);
+      for (int j = 0; j < 32; ++j) { sc[j] = exp2f(sc[j] - mx); sum += sc[j]; }
+      const float inv = keep_scale / sum;
+      if (a.d_attn.thr) {
+        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 16);    // idx >> 1 of column 0
+        const uint32_t xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)w0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float m0, m1;
-        drop2(a.d_attn, base + j, m0, m1);
-        sc[j] *= inv * m0; sc[j + 1] *= inv * m1;
-      }
-      int c = 0;
-      for (; c + 1 < dh; c += 2) {
-        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_attn.key);
+          sc[j] = ((hsh & 0xFFFFu) >= a.d_attn.thr) ? sc[j] * inv : 0.f;
+          sc[j + 1] = ((hsh >> 16) >= a.d_attn.thr) ? sc[j + 1] * inv : 0.f;
+        }
+      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { o0 = fmaf(sc[j], vb[j * LS + c], o0); o1 = fmaf(sc[j], vb[j * LS + c + 1], o1); }
-        *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r, h * dh + c, 128)) = pack_bf16(o0, o1);
+        for (int j = 0; j < 32; ++j) sc[j] *= inv;
       }
-      if (c < dh) {
-        float o0 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o0 = fmaf(sc[j], vb[j * LS + c], o0);
-        *reinterpret_cast<__nv_bfloat16 *>(sCtx + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(o0);
-      }
+      attn_context<DH>(sc, vh, dh, sCtx, r, h * dh);
     }
     fence_async_smem();
     fence_before_sync();
@@ -253,9 +351,9 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
-    // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = row, warps 0-3) ----
+    // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = row, part 0) ----
     float x1[D];
-    if (half == 0) {
+    if (part == 0) {
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, x1 + cb);
       tmem_ld_wait();
@@ -298,24 +396,28 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
       for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1, FC, k), idesc1, k > 0);
       mma_commit(&bar_mma);
     }
-    const bool epi = (FC >= 32) || (half == 0);
-    const int per = FC >= 32 ? FC / 2 : FC;
+    const int nblk = FC / 16;                          // 16-column blocks of the chunk, dealt round-robin to the 4 parts
     for (int c = 0; c < nchunk; ++c) {
       mbar_wait(&bar_mma, ph); ph ^= 1;               // FFN1(c) (and FFN2(c-1)) complete
       fence_after_sync();
-      if (epi) {
-        const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC);
-        for (int cb = half * per; cb < half * per + per; cb += 16) {
+      {
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 1;        // multiple of 8 (F, FC multiples of 16)
+        for (int b = part; b < nblk; b += 4) {
+          const int cb = b * 16;
+          const uint64_t wb = w0 + (uint64_t)(cb >> 1);                                 // + (0..7) below never carries
+          const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
           float v[16];
           tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float m0, m1;
-            drop2(a.d_ffn, e0 + cb + j, m0, m1);
-            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f) * m0;
-            float h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f) * m1;
+            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
+            if (a.d_ffn.thr) {
+              const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_ffn.key);
+              h0 = ((hsh & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
+              h1 = ((hsh >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+            }
             pk[j >> 1] = pack_bf16(h0, h1);
           }
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -340,7 +442,7 @@ __global__ void __launch_bounds__(256, 1) tc_layer_fwd_kernel(const TcLayerArgs 
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // last FFN2 complete
     fence_after_sync();
     // ---- P8: + bias, dropout, + residual, LayerNorm2 -> x_out ----
-    if (half == 0) {
+    if (part == 0) {
       float f[D];
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, f + cb);
@@ -391,16 +493,25 @@ static int num_sms() {
   return n;
 }
 
+template <int DH>
+static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { LaunchScope _ls(KC_TC_LAYER_FWD, st);
+    tc_layer_fwd_kernel<32, DH><<<grid, FWD_THREADS, smem, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(D == 32, "tc_layer_fwd: d_model not instantiated");
   const SmemPlan sp = fwd_smem(D, a.F, a.FC);
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
-  GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
-  { LaunchScope _ls(KC_TC_LAYER_FWD, st);
-    tc_layer_fwd_kernel<32><<<grid, 256, sp.total, st>>>(a); }
-  GT_CUDA(cudaGetLastError());
-  return 0;
+  switch (a.dh) {
+    case 2: return launch_fwd<2>(a, sp.total, grid, st);
+    case 8: return launch_fwd<8>(a, sp.total, grid, st);
+    default: return launch_fwd<0>(a, sp.total, grid, st);
+  }
 }
 
 // =============================================================================================
