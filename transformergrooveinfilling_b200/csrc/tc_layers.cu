@@ -524,22 +524,25 @@ int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
 // [160,192) dctx   [192,320) dW1 chunks   [320,448) dW2^T chunks   [448,480) dWqkv   [480,512) dWo
 // =============================================================================================
 struct BwdSmem {
-  uint32_t w, par, gpar, xin, x1, da, ctx, dq, qkv, dctx, h, dh, total;
+  uint32_t w, par, gpar, stat, xin, x1, da, ctx, dq, q, k, v, dctx, h, dh, total;
 };
 __host__ __device__ inline BwdSmem bwd_smem(int D, int F) {
   BwdSmem s;
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
   s.gpar = al128(s.par + (uint32_t)(9 * D + F) * 4u);
-  s.xin = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);
+  s.stat = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);   // per-row (mean1, rstd1)
+  s.xin = al128(s.stat + 128u * 2u * 4u);
   s.x1 = s.xin + 128u * D * 2u;
   s.da = s.x1 + 128u * D * 2u;
   s.ctx = s.da + 128u * D * 2u;
   s.dq = s.ctx + 128u * D * 2u;                       // dqkv image [128 x 3D]; M-padded reads run into the union below
   uint32_t u = al128(s.dq + 128u * 3u * D * 2u);
-  s.qkv = u;                                          // attention phase: fp32 q|k|v rows + fp32 dctx rows
-  s.dctx = al128(s.qkv + 128u * (3u * D + 1u) * 4u);
-  uint32_t end_attn = al128(s.dctx + 128u * (D + 1u) * 4u);
+  s.q = u;                                            // attention phase: fp32 q rows, compact k / v, fp32 dctx rows
+  s.k = al128(s.q + 128u * (D + 4u) * 4u);
+  s.v = s.k + 128u * D * 4u;
+  s.dctx = al128(s.v + 128u * D * 4u);
+  uint32_t end_attn = al128(s.dctx + 128u * (D + 4u) * 4u);
   s.h = u;                                            // FFN phase (aliases the attention scratch): H and dH images
   s.dh = s.h + 128u * 128u * 2u;
   uint32_t end_ffn = s.dh + 128u * 128u * 2u;
@@ -571,36 +574,41 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t base, int rows, int k16) { 
   return make_desc(base + (uint32_t)k16 * 256u, 128u, (uint32_t)(rows >> 3) * 128u);
 }
 
-template <int D>
-__global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
+constexpr int BWD_THREADS = 512;
+constexpr int BWD_PARTS = BWD_THREADS / 128;
+
+template <int D, int DH>
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
   static_assert(D == 32, "the register-tile column sums assume d_model == 32");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & 127, half = tid >> 7;
-  const int F = a.F, FC = a.FC, H = a.H, dh = a.dh, nchunk = F / FC;
+  const int row = tid & 127, part = tid >> 7;
+  const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   const BwdSmem sp = bwd_smem(D, F);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
   float *sPar = reinterpret_cast<float *>(smem + sp.par);
   float *p_bqkv = sPar, *p_bo = sPar + 3 * D, *p_b1 = p_bo + D, *p_b2 = p_b1 + F, *p_g1 = p_b2 + D, *p_be1 = p_g1 + D,
-        *p_g2 = p_be1 + D, *p_be2 = p_g2 + D;
+        *p_g2 = p_be1 + D;
   float *sG = reinterpret_cast<float *>(smem + sp.gpar);       // gradient partials, same order as sPar
   float *g_bqkv = sG, *g_bo = sG + 3 * D, *g_b1 = g_bo + D, *g_b2 = g_b1 + F, *g_g1 = g_b2 + D, *g_be1 = g_g1 + D,
         *g_g2 = g_be1 + D, *g_be2 = g_g2 + D;
+  float *sStat = reinterpret_cast<float *>(smem + sp.stat);
   uint8_t *sXin = smem + sp.xin, *sX1 = smem + sp.x1, *sDA = smem + sp.da, *sCtx = smem + sp.ctx, *sDQ = smem + sp.dq;
-  float *sQKV = reinterpret_cast<float *>(smem + sp.qkv);
+  float *sQ = reinterpret_cast<float *>(smem + sp.q);
+  float *sK = reinterpret_cast<float *>(smem + sp.k);
+  float *sV = reinterpret_cast<float *>(smem + sp.v);
   float *sDC = reinterpret_cast<float *>(smem + sp.dctx);
   uint8_t *sH = smem + sp.h, *sDH = smem + sp.dh;
-  constexpr int LS = 3 * D + 1, LC = D + 1;
-  (void)p_bo; (void)p_b2; (void)p_be2;
+  constexpr int LQ = D + 4;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
-  for (int i = tid; i < 9 * D + F; i += 256) sG[i] = 0.f;
-  for (int i = tid; i < 3 * D; i += 256) p_bqkv[i] = a.bqkv[i];
-  for (int i = tid; i < F; i += 256) p_b1[i] = a.b1[i];
+  for (int i = tid; i < 9 * D + F; i += BWD_THREADS) sG[i] = 0.f;
+  for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
+  for (int i = tid; i < F; i += BWD_THREADS) p_b1[i] = a.b1[i];
   if (tid < D) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; p_g2[tid] = a.g2[tid]; }
   fence_before_sync();
   __syncthreads();
@@ -622,8 +630,7 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
   uint32_t ph = 0;
   const float inv_sqrt_dh = rsqrtf((float)dh);
   const float attn_scale = inv_sqrt_dh * 1.4426950408889634f;
-  const bool epi = (FC >= 32) || (half == 0);
-  const int per = FC >= 32 ? FC / 2 : FC;
+  const int nblk = FC / 16;
   // instruction descriptors
   const uint32_t id_kk_fc = make_idesc_bf16(128, FC, 0, 0);      // H chunk          A K-major, B K-major
   const uint32_t id_kmn_fc = make_idesc_bf16(128, FC, 0, 1);     // dH chunk         A K-major, B MN-major
@@ -636,10 +643,9 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
     const int64_t grow = (int64_t)tile * TC_TILE + row;
     const bool valid = grow < a.M;
     const uint32_t acc0 = iter > 0 ? 1u : 0u;
-    float du[D];                       // half 0: gradient w.r.t. the LayerNorm input currently being processed
-    float mean1 = 0.f, rstd1 = 0.f;
-    // ---- B0: LN2 backward, x1 = LN1(u1) ; half 1 stages x_in ----
-    if (half == 0) {
+    float du[D];                       // part 0: gradient w.r.t. the LayerNorm input currently being processed
+    // ---- B0: part 0: LN2 backward ; part 1: x1 = LN1(u1) ; part 2: stage x_in ----
+    if (part == 0) {
       float xh[D];
       float s1 = 0.f;
 #pragma unroll
@@ -650,10 +656,11 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
         float4 g = valid ? *reinterpret_cast<const float4 *>(a.dy + grow * D + c) : make_float4(0, 0, 0, 0);
         du[c] = g.x; du[c + 1] = g.y; du[c + 2] = g.z; du[c + 3] = g.w;
       }
-      float mu = s1 * (1.f / D), q = 0.f;
+      const float mu = s1 * (1.f / D);
+      float q = 0.f;
 #pragma unroll
       for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
-      float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
       float m1 = 0.f, m2 = 0.f;
       float w[32];
 #pragma unroll
@@ -669,7 +676,6 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
       for (int c = 0; c < D; ++c) w[c] = du[c];
       { float t = warp_colsum32(w, lane); atomicAdd(&g_be2[lane], t); }
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
-      uint32_t pk[D / 2];
 #pragma unroll
       for (int c = 0; c < D; c += 2) {
         du[c] = rs * (du[c] * p_g2[c] - m1 - xh[c] * m2);
@@ -677,25 +683,27 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
         float k0, k1;
         drop2(a.d2, e0 + c, k0, k1);
         w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da2 = grad wrt the FFN2 output (+bias)
-        pk[c >> 1] = pack_bf16(w[c], w[c + 1]);
       }
 #pragma unroll
       for (int c = 0; c < D; c += 8)
-        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
+        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
+            make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
       { float t = warp_colsum32(w, lane); atomicAdd(&g_b2[lane], t); }
-      // x1 = LN1(u1)
-      s1 = 0.f;
+    } else if (part == 1) {
+      float xh[D];
+      float s1 = 0.f;
 #pragma unroll
       for (int c = 0; c < D; c += 4) {
         float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
         xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
         s1 += (t.x + t.y) + (t.z + t.w);
       }
-      mu = s1 * (1.f / D); q = 0.f;
+      const float mu = s1 * (1.f / D);
+      float q = 0.f;
 #pragma unroll
       for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
-      rs = rsqrtf(q * (1.f / D) + LN_EPS);
-      mean1 = mu; rstd1 = rs;
+      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      sStat[row * 2] = mu; sStat[row * 2 + 1] = rs;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         float y[8];
@@ -704,7 +712,7 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
         *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) =
             make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
       }
-    } else {
+    } else if (part == 2) {
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -725,11 +733,14 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
     for (int c = 0; c < nchunk; ++c) {
       mbar_wait(&bar_mma, ph); ph ^= 1;               // H(c) accumulator ready (and every earlier MMA retired)
       fence_after_sync();
-      uint32_t mask_lo = 0, mask_hi = 0;              // (kept && h > 0) for this thread's columns of the chunk
-      if (epi) {
-        const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC);
-        int bit = 0;
-        for (int cb = half * per; cb < half * per + per; cb += 16) {
+      uint32_t mask = 0;                              // (kept && h > 0) bits of this thread's (<= 2) 16-column blocks
+      {
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 1;
+        int t = 0;
+        for (int b = part; b < nblk; b += BWD_PARTS, ++t) {
+          const int cb = b * 16;
+          const uint64_t wb = w0 + (uint64_t)(cb >> 1);
+          const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
           float v[16];
           tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
           tmem_ld_wait();
@@ -737,18 +748,19 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
           uint32_t bits = 0;
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float m0, m1;
-            drop2(a.d_ffn, e0 + cb + j, m0, m1);
-            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f) * m0;
-            float h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f) * m1;
+            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
+            if (a.d_ffn.thr) {
+              const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_ffn.key);
+              h0 = ((hsh & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
+              h1 = ((hsh >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+            }
             bits |= (h0 > 0.f ? 1u : 0u) << j;
             bits |= (h1 > 0.f ? 1u : 0u) << (j + 1);
             pk[j >> 1] = pack_bf16(h0, h1);
           }
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          if (bit < 32) mask_lo |= bits << bit; else mask_hi |= bits << (bit - 32);
-          bit += 16;
+          mask |= bits << (16 * t);
         }
       }
       fence_async_smem();
@@ -763,40 +775,34 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
       }
       mbar_wait(&bar_mma, ph); ph ^= 1;
       fence_after_sync();
-      if (epi) {
+      if (part < nblk) {                              // this thread owns blocks b0 = part and (if present) b1 = part + PARTS
         const float sc = a.d_ffn.scale;
-        int bit = 0;
-        for (int cb = half * per; cb < half * per + per; cb += 32) {
-          float w[32];
-          const int nb = (half * per + per - cb) >= 32 ? 2 : 1;
+        const int b0 = part, b1 = part + BWD_PARTS;
+        const bool two = b1 < nblk;
+        float w[32];
+        tmem_ld16(t_big + lane_off + (uint32_t)(b0 * 16), w);
+        if (two) {
+          tmem_ld16(t_big + lane_off + (uint32_t)(b1 * 16), w + 16);
+        } else {
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            if (b < nb) {
-              tmem_ld16(t_big + lane_off + (uint32_t)(cb + 16 * b), w + 16 * b);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[16 + j] = 0.f;
-            }
-          }
-          tmem_ld_wait();
-          const uint32_t bits32 = (bit == 0) ? mask_lo : mask_hi;       // per <= 64: at most two 32-column groups
-#pragma unroll
-          for (int j = 0; j < 32; ++j) w[j] = ((bits32 >> j) & 1u) ? w[j] * sc : 0.f;
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            if (b < nb) {
-              *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb + 16 * b, 128)) =
-                  make_uint4(pack_bf16(w[16 * b], w[16 * b + 1]), pack_bf16(w[16 * b + 2], w[16 * b + 3]),
-                             pack_bf16(w[16 * b + 4], w[16 * b + 5]), pack_bf16(w[16 * b + 6], w[16 * b + 7]));
-              *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb + 16 * b + 8, 128)) =
-                  make_uint4(pack_bf16(w[16 * b + 8], w[16 * b + 9]), pack_bf16(w[16 * b + 10], w[16 * b + 11]),
-                             pack_bf16(w[16 * b + 12], w[16 * b + 13]), pack_bf16(w[16 * b + 14], w[16 * b + 15]));
-            }
-          }
-          const float t = warp_colsum32(w, lane);     // bias gradient of linear1 for 32 columns
-          if (lane < 16 * nb) atomicAdd(&g_b1[c * FC + cb + lane], t);
-          bit += 32;
+          for (int j = 0; j < 16; ++j) w[16 + j] = 0.f;
         }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = ((mask >> j) & 1u) ? w[j] * sc : 0.f;
+        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b0 * 16, 128)) =
+            make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b0 * 16 + 8, 128)) =
+            make_uint4(pack_bf16(w[8], w[9]), pack_bf16(w[10], w[11]), pack_bf16(w[12], w[13]), pack_bf16(w[14], w[15]));
+        if (two) {
+          *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b1 * 16, 128)) =
+              make_uint4(pack_bf16(w[16], w[17]), pack_bf16(w[18], w[19]), pack_bf16(w[20], w[21]), pack_bf16(w[22], w[23]));
+          *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b1 * 16 + 8, 128)) =
+              make_uint4(pack_bf16(w[24], w[25]), pack_bf16(w[26], w[27]), pack_bf16(w[28], w[29]), pack_bf16(w[30], w[31]));
+        }
+        const float t = warp_colsum32(w, lane);       // bias gradient of linear1: lane l <-> column (l<16 ? b0 : b1)*16 + l%16
+        if (lane < 16) atomicAdd(&g_b1[c * FC + b0 * 16 + lane], t);
+        else if (two) atomicAdd(&g_b1[c * FC + b1 * 16 + lane - 16], t);
       }
       fence_async_smem();
       fence_before_sync();
@@ -821,12 +827,13 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // dx1 complete, all weight-gradient MMAs of this tile retired
     fence_after_sync();
-    // ---- B2: LN1 backward ----
-    if (half == 0) {
+    // ---- B2: LN1 backward (part 0) ----
+    if (part == 0) {
       float acc[D], xh[D];
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
       tmem_ld_wait();
+      const float mean1 = sStat[row * 2], rstd1 = sStat[row * 2 + 1];
       float m1 = 0.f, m2 = 0.f;
       float w[32];
 #pragma unroll
@@ -847,7 +854,6 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
       for (int c = 0; c < D; ++c) w[c] = du[c];
       { float t = warp_colsum32(w, lane); atomicAdd(&g_be1[lane], t); }
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
-      uint32_t pk[D / 2];
 #pragma unroll
       for (int c = 0; c < D; c += 2) {
         du[c] = rstd1 * (du[c] * p_g1[c] - m1 - xh[c] * m2);
@@ -855,16 +861,16 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
         float k0, k1;
         drop2(a.d1, e0 + c, k0, k1);
         w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da1 = grad wrt the out-proj output (+bias)
-        pk[c >> 1] = pack_bf16(w[c], w[c + 1]);
       }
 #pragma unroll
       for (int c = 0; c < D; c += 8)
-        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_bo[lane], t); }
+        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
+            make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
       if (valid) {                                    // park du1 (residual path into dx) in the output buffer
 #pragma unroll
         for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(du[c], du[c + 1], du[c + 2], du[c + 3]);
       }
+      { float t = warp_colsum32(w, lane); atomicAdd(&g_bo[lane], t); }
     }
     fence_async_smem();
     fence_before_sync();
@@ -880,79 +886,86 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
-    {
-      constexpr int PER = 3 * D / 2;
-      for (int cb = half * PER; cb < (half + 1) * PER; cb += 16) {
-        float v[16];
-        tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
-        tmem_ld_wait();
+    {                                                 // part 0 -> q, 1 -> k, 2 -> v, 3 -> dctx
+      float v[D];
+      const uint32_t src = part < 3 ? t_big + (uint32_t)(part * D) : t_sb;
+      tmem_ld16(src + lane_off, v);
+      tmem_ld16(src + lane_off + 16u, v + 16);
+      tmem_ld_wait();
+      if (part < 3) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sQKV[row * LS + cb + j] = v[j] + p_bqkv[cb + j];
-      }
-      if (half == 0) {
-        for (int cb = 0; cb < D; cb += 16) {
-          float v[16];
-          tmem_ld16(t_sb + lane_off + (uint32_t)cb, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sDC[row * LC + cb + j] = v[j];
+        for (int c = 0; c < D; c += 4) {
+          const float4 b = *reinterpret_cast<const float4 *>(p_bqkv + part * D + c);
+          v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
         }
+      }
+      if (part == 0 || part == 3) {
+        float *dst = (part == 0 ? sQ : sDC) + row * LQ;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      } else {
+        store_kv_row<D, DH>(part == 1 ? sK : sV, v, row, H, dh);
       }
     }
     fence_before_sync();
     __syncthreads();
     // ---- B5: attention backward, one warp per (sequence, head), lane = query row; dK/dV via warp transposed sums ----
-    for (int p = warp; p < 4 * H; p += 8) {
+    for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {
       const int s = p / H, h = p - s * H;
       const int r = s * 32 + lane;
-      const float *q = sQKV + r * LS + h * dh;
-      const float *kb = sQKV + (s * 32) * LS + D + h * dh;
-      const float *vb = kb + D;
-      const float *go = sDC + r * LC + h * dh;
+      const float *q = sQ + r * LQ + h * dh;
+      const float *go = sDC + r * LQ + h * dh;
+      const float *kh = sK + s * 32 * D + h * 32 * dh;
+      const float *vh = sV + s * 32 * D + h * 32 * dh;
       float pr[32], dp[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { pr[j] = 0.f; dp[j] = 0.f; }
-      for (int c = 0; c < dh; ++c) {
-        const float qc = q[c], gc = go[c];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { pr[j] = fmaf(qc, kb[j * LS + c], pr[j]); dp[j] = fmaf(gc, vb[j * LS + c], dp[j]); }
-      }
+      attn_scores<DH>(q, kh, dh, attn_scale, pr);
+      attn_scores<DH>(go, vh, dh, 1.f, dp);           // dP[i][j] = dO_i . v_j
       float mx = pr[0];
 #pragma unroll
       for (int j = 1; j < 32; ++j) mx = fmaxf(mx, pr[j]);
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { pr[j] = exp2f((pr[j] - mx) * attn_scale); sum += pr[j]; }
+      for (int j = 0; j < 32; ++j) { pr[j] = exp2f(pr[j] - mx); sum += pr[j]; }
       const float inv = 1.f / sum;
-      const uint64_t base = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 32);
-      float pd[32];
+      uint32_t keep = 0xFFFFFFFFu;
+      if (a.d_attn.thr) {
+        keep = 0;
+        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 16);
+        const uint32_t xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)w0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_attn.key);
+          keep |= ((hsh & 0xFFFFu) >= a.d_attn.thr ? 1u : 0u) << j;
+          keep |= ((hsh >> 16) >= a.d_attn.thr ? 1u : 0u) << (j + 1);
+        }
+      }
+      const float ks = a.d_attn.scale;
       float delta = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float m0, m1;
-        drop2(a.d_attn, base + j, m0, m1);
-        pr[j] *= inv; pr[j + 1] *= inv;
-        pd[j] = pr[j] * m0; pd[j + 1] = pr[j + 1] * m1;
-        dp[j] *= m0; dp[j + 1] *= m1;
+      for (int j = 0; j < 32; ++j) {
+        pr[j] *= inv;                                                  // P
+        dp[j] = ((keep >> j) & 1u) ? dp[j] * ks : 0.f;                 // dL/dP
         delta = fmaf(dp[j], pr[j], delta);
-        delta = fmaf(dp[j + 1], pr[j + 1], delta);
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dp[j] = pr[j] * (dp[j] - delta) * inv_sqrt_dh;      // dS
+      for (int j = 0; j < 32; ++j) dp[j] = pr[j] * (dp[j] - delta) * inv_sqrt_dh;      // dS (1/sqrt(dh) folded in)
       for (int c = 0; c < dh; ++c) {
-        float o = 0.f, dq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { o = fmaf(pd[j], vb[j * LS + c], o); dq = fmaf(dp[j], kb[j * LS + c], dq); }
-        *reinterpret_cast<__nv_bfloat16 *>(sCtx + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(o);
-        *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(dq);
         const float qc = q[c], gc = go[c];
+        float o = 0.f, dq = 0.f;
         float w[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) w[j] = dp[j] * qc;
-        const float dk = warp_colsum32(w, lane);      // lane = key row
+        for (int j = 0; j < 32; ++j) {
+          const float pd = ((keep >> j) & 1u) ? pr[j] * ks : 0.f;      // dropped probabilities
+          o = fmaf(pd, vh[j * dh + c], o);
+          dq = fmaf(dp[j], kh[j * dh + c], dq);
+          w[j] = pd * gc;
+        }
+        const float dv = warp_colsum32(w, lane);      // lane = key row
 #pragma unroll
-        for (int j = 0; j < 32; ++j) w[j] = pd[j] * gc;
-        const float dv = warp_colsum32(w, lane);
+        for (int j = 0; j < 32; ++j) w[j] = dp[j] * qc;
+        const float dk = warp_colsum32(w, lane);
+        *reinterpret_cast<__nv_bfloat16 *>(sCtx + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(o);
+        *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, h * dh + c, 128)) = __float2bfloat16_rn(dq);
         *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, D + h * dh + c, 128)) = __float2bfloat16_rn(dk);
         *reinterpret_cast<__nv_bfloat16 *>(sDQ + kmajor_off(r, 2 * D + h * dh + c, 128)) = __float2bfloat16_rn(dv);
         const float sq = warp_sum_all(dq), sk = warp_sum_all(dk), sv = warp_sum_all(dv);
@@ -980,7 +993,7 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
-    if (half == 0) {
+    if (part == 0) {
       float acc[D];
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
@@ -1000,41 +1013,39 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
   fence_after_sync();
   {
     const int m = row;                                // TMEM lane = output row of the weight-gradient blocks
-    for (int c = half; c < nchunk; c += 2) {          // half 0: even chunks, half 1: odd chunks
+    // jobs: 0..nchunk-1 dW1 chunks, nchunk..2nchunk-1 dW2^T chunks, then dWqkv, dWo — dealt round-robin to the parts
+    for (int job = part; job < 2 * nchunk + 2; job += BWD_PARTS) {
       float v[D];
-#pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_dw1 + 32u * c + lane_off + (uint32_t)cb, v + cb);
-      tmem_ld_wait();
-      if (m < FC) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) atomicAdd(a.gw1 + (int64_t)(c * FC + m) * D + i, v[i]);
-      }
-#pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_dw2 + 32u * c + lane_off + (uint32_t)cb, v + cb);
-      tmem_ld_wait();
-      if (m < FC) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) atomicAdd(a.gw2 + (int64_t)j * F + c * FC + m, v[j]);
-      }
-    }
-    {
-      float v[D];
-      const uint32_t t = half == 0 ? t_dwqkv : t_dwo;
+      uint32_t t;
+      if (job < nchunk) t = t_dw1 + 32u * job;
+      else if (job < 2 * nchunk) t = t_dw2 + 32u * (job - nchunk);
+      else t = job == 2 * nchunk ? t_dwqkv : t_dwo;
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t + lane_off + (uint32_t)cb, v + cb);
       tmem_ld_wait();
-      if (half == 0 && m < 3 * D) {
+      if (job < nchunk) {
+        if (m < FC) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) atomicAdd(a.gwqkv + (int64_t)m * D + i, v[i]);
-      }
-      if (half == 1 && m < D) {
+          for (int i = 0; i < D; ++i) atomicAdd(a.gw1 + (int64_t)(job * FC + m) * D + i, v[i]);
+        }
+      } else if (job < 2 * nchunk) {
+        if (m < FC) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) atomicAdd(a.gw2 + (int64_t)j * F + (job - nchunk) * FC + m, v[j]);
+        }
+      } else if (job == 2 * nchunk) {
+        if (m < 3 * D) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) atomicAdd(a.gwqkv + (int64_t)m * D + i, v[i]);
+        }
+      } else if (m < D) {
 #pragma unroll
         for (int i = 0; i < D; ++i) atomicAdd(a.gwo + (int64_t)m * D + i, v[i]);
       }
     }
   }
-  for (int i = tid; i < 3 * D; i += 256) atomicAdd(a.gbqkv + i, g_bqkv[i]);
-  for (int i = tid; i < F; i += 256) atomicAdd(a.gb1 + i, g_b1[i]);
+  for (int i = tid; i < 3 * D; i += BWD_THREADS) atomicAdd(a.gbqkv + i, g_bqkv[i]);
+  for (int i = tid; i < F; i += BWD_THREADS) atomicAdd(a.gb1 + i, g_b1[i]);
   if (tid < D) {
     atomicAdd(a.gbo + tid, g_bo[tid]); atomicAdd(a.gb2 + tid, g_b2[tid]);
     atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
@@ -1045,17 +1056,26 @@ __global__ void __launch_bounds__(256, 1) tc_layer_bwd_kernel(const TcLayerArgs 
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+template <int DH>
+static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { LaunchScope _ls(KC_TC_LAYER_BWD, st);
+    tc_layer_bwd_kernel<32, DH><<<grid, BWD_THREADS, smem, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(D == 32, "tc_layer_bwd: d_model not instantiated");
   GT_CHECK(a.F / a.FC <= 4, "tc_layer_bwd: more than 4 FFN chunks do not fit the TMEM gradient accumulators");
   const BwdSmem sp = bwd_smem(D, a.F);
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_bwd: shared memory budget exceeded");
-  GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
-  { LaunchScope _ls(KC_TC_LAYER_BWD, st);
-    tc_layer_bwd_kernel<32><<<grid, 256, sp.total, st>>>(a); }
-  GT_CUDA(cudaGetLastError());
-  return 0;
+  switch (a.dh) {
+    case 2: return launch_bwd<2>(a, sp.total, grid, st);
+    case 8: return launch_bwd<8>(a, sp.total, grid, st);
+    default: return launch_bwd<0>(a, sp.total, grid, st);
+  }
 }
 
 }  // namespace gt
