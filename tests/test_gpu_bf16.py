@@ -99,7 +99,7 @@ def test_loss_trajectory_bf16_vs_fp32():
 
 
 def test_unsupported_shapes_fail_loudly():
-    cfg = G.GrooveCfg(256, 16, 64, 1, 0, 16, 27)
+    cfg = G.GrooveCfg(64, 4, 64, 1, 0, 16, 27)
     model, _ = build_model(cfg, dropout=0.0, precision="bf16")
     with pytest.raises(RuntimeError, match="not available"):
         model.train_step(*[t.cuda() for t in G.det_batch(cfg, 4)], 1.0)

@@ -1,5 +1,6 @@
 // tc_layers.cu — fused per-layer kernels of the bf16 tensor-core path.  See tc_layers.cuh.
 #include "tc_layers.cuh"
+#include "tc256.cuh"
 #include "umma.cuh"
 
 namespace gt {
@@ -7,8 +8,9 @@ using namespace umma;
 
 bool tc_shape_supported(const gt_config &c, std::string *why) {
   auto no = [&](const char *m) { if (why) *why = m; return false; };
+  if (c.d_model == 256) return t256_shape_supported(c, why);
   if (c.n_dec != 0) return no("encoder-decoder models run in precision=fp32 (the fused tcgen05 layer kernels cover the encoder stack)");
-  if (c.d_model != 32) return no("fused tcgen05 layer kernels are instantiated for d_model=32");
+  if (c.d_model != 32) return no("fused tcgen05 layer kernels are instantiated for d_model=32 and d_model=256");
   if (c.n_enc > TC_MAX_LAYERS) return no("more than 16 layers");
   if (c.dim_ff % 16 != 0 || c.dim_ff > 512) return no("dim_feedforward must be a multiple of 16 and <= 512 (TMEM-resident weight gradients)");
   if (tc_ffn_chunk(c.dim_ff) == 0) return no("dim_feedforward has no valid chunking");
@@ -503,6 +505,7 @@ static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 }
 
 int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
+  if (D == 256) return t256_layer_fwd(a, st);
   GT_CHECK(D == 32, "tc_layer_fwd: d_model not instantiated");
   const SmemPlan sp = fwd_smem(D, a.F, a.FC);
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
@@ -1066,6 +1069,7 @@ static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 }
 
 int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
+  if (D == 256) return t256_layer_bwd(a, st);
   GT_CHECK(D == 32, "tc_layer_bwd: d_model not instantiated");
   GT_CHECK(a.F / a.FC <= 4, "tc_layer_bwd: more than 4 FFN chunks do not fit the TMEM gradient accumulators");
   const BwdSmem sp = bwd_smem(D, a.F);

@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include "tc_layers.cuh"
+#include "tc256.cuh"
 #include "tc_path.cuh"
 #include "umma.cuh"
 
@@ -132,7 +133,7 @@ static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base
     off += (nbytes + 255) / 256 * 256;
     return base ? base + o : nullptr;
   };
-  P.img_stride = (tc_img(c.d_model, c.dim_ff).total + 255u) & ~255u;
+  P.img_stride = ((c.d_model == 256 ? t256_img_bytes(c.dim_ff) : tc_img(c.d_model, c.dim_ff).total) + 255u) & ~255u;
   P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
   const bool train = mode == 1;
   P.r0 = reinterpret_cast<float *>(take(M * d * 4));
@@ -205,7 +206,7 @@ static TcLayerArgs tc_layer_args(const TcCtx &x, const TcPlan &pl, int l) {
   memset(&a, 0, sizeof(a));
   const LayerP &p = x.L->enc[l];
   a.img = pl.img + (size_t)l * pl.img_stride;
-  a.img_bytes = tc_img(x.c.d_model, x.c.dim_ff).total;
+  a.img_bytes = x.c.d_model == 256 ? t256_img_bytes(x.c.dim_ff) : tc_img(x.c.d_model, x.c.dim_ff).total;
   a.bqkv = x.P + p.sa.b_in; a.bo = x.P + p.sa.b_out; a.b1 = x.P + p.b1; a.b2 = x.P + p.b2;
   a.g1 = x.P + p.g1; a.be1 = x.P + p.be1; a.g2 = x.P + p.g2; a.be2 = x.P + p.be2;
   if (x.G) {
@@ -229,7 +230,7 @@ static int tc_prep(const TcCtx &x, const TcPlan &pl) {
   for (int l = 0; l < x.c.n_enc; ++l) {
     a.w_in[l] = x.L->enc[l].sa.w_in; a.w_out[l] = x.L->enc[l].sa.w_out; a.w1[l] = x.L->enc[l].w1; a.w2[l] = x.L->enc[l].w2;
   }
-  return tc_prep_weights(a, x.st);
+  return x.c.d_model == 256 ? t256_prep_weights(a, x.st) : tc_prep_weights(a, x.st);
 }
 
 static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres) {
