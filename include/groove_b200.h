@@ -127,6 +127,10 @@ int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p,
 int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k,
                      int variant, void *stream);
 
+/* Micro-benchmark of the tensor pipe: n_mma back-to-back 128 x n x 16 bf16 UMMAs per SM from shared-memory
+ * operands; out[0] (device float) = clocks per UMMA.  Used by tools/umma_rate.py. */
+int gt_debug_umma_rate(int n, int n_mma, int ksteps, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "tc_path.cuh"
+#include "tc256.cuh"
 
 namespace gt {
 
@@ -611,6 +612,9 @@ int gt_profile_collect(double *total_ms, int64_t *launches) {
   return 0;
 }
 
+int gt_debug_umma_rate(int n, int n_mma, int ksteps, float *out, void *stream) {
+  return t256_debug_umma_rate(n, n_mma, ksteps, out, (cudaStream_t)stream);
+}
 int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k, int variant, void *stream) {
   return tc_debug_gemm(a, b, d, m, n, k, variant, (cudaStream_t)stream);
 }

@@ -505,7 +505,6 @@ static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 }
 
 int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
-  if (D == 256) return t256_layer_fwd(a, st);
   GT_CHECK(D == 32, "tc_layer_fwd: d_model not instantiated");
   const SmemPlan sp = fwd_smem(D, a.F, a.FC);
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
@@ -1069,7 +1068,6 @@ static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 }
 
 int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
-  if (D == 256) return t256_layer_bwd(a, st);
   GT_CHECK(D == 32, "tc_layer_bwd: d_model not instantiated");
   GT_CHECK(a.F / a.FC <= 4, "tc_layer_bwd: more than 4 FFN chunks do not fit the TMEM gradient accumulators");
   const BwdSmem sp = bwd_smem(D, a.F);

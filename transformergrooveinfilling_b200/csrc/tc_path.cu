@@ -133,7 +133,7 @@ static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base
     off += (nbytes + 255) / 256 * 256;
     return base ? base + o : nullptr;
   };
-  P.img_stride = ((c.d_model == 256 ? t256_img_bytes(c.dim_ff) : tc_img(c.d_model, c.dim_ff).total) + 255u) & ~255u;
+  P.img_stride = (tc_img(c.d_model, c.dim_ff).total + 255u) & ~255u;
   P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
   const bool train = mode == 1;
   P.r0 = reinterpret_cast<float *>(take(M * d * 4));
@@ -191,6 +191,7 @@ static int tc_check(const gt_config &c, int64_t n_seq, int mode, void *ws, int64
 }
 
 int64_t tc_workspace_bytes(const gt_config &c, int64_t n_seq, int mode) {
+  if (c.d_model == 256) return t256_workspace_bytes(c, n_seq, mode);
   std::string why;
   if (!tc_shape_supported(c, &why)) {
     set_error("precision=bf16 is not available for this configuration (" + why + "); use precision=fp32");
@@ -206,7 +207,7 @@ static TcLayerArgs tc_layer_args(const TcCtx &x, const TcPlan &pl, int l) {
   memset(&a, 0, sizeof(a));
   const LayerP &p = x.L->enc[l];
   a.img = pl.img + (size_t)l * pl.img_stride;
-  a.img_bytes = x.c.d_model == 256 ? t256_img_bytes(x.c.dim_ff) : tc_img(x.c.d_model, x.c.dim_ff).total;
+  a.img_bytes = tc_img(x.c.d_model, x.c.dim_ff).total;
   a.bqkv = x.P + p.sa.b_in; a.bo = x.P + p.sa.b_out; a.b1 = x.P + p.b1; a.b2 = x.P + p.b2;
   a.g1 = x.P + p.g1; a.be1 = x.P + p.be1; a.g2 = x.P + p.g2; a.be2 = x.P + p.be2;
   if (x.G) {
@@ -230,7 +231,7 @@ static int tc_prep(const TcCtx &x, const TcPlan &pl) {
   for (int l = 0; l < x.c.n_enc; ++l) {
     a.w_in[l] = x.L->enc[l].sa.w_in; a.w_out[l] = x.L->enc[l].sa.w_out; a.w1[l] = x.L->enc[l].w1; a.w2[l] = x.L->enc[l].w2;
   }
-  return x.c.d_model == 256 ? t256_prep_weights(a, x.st) : tc_prep_weights(a, x.st);
+  return tc_prep_weights(a, x.st);
 }
 
 static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres) {
@@ -288,6 +289,7 @@ static void tc_ctx(TcCtx &x, const gt_config &c, const Layout &L, const float *p
 int tc_forward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
                int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, bool train, uint64_t seed, uint64_t step, int64_t seq0,
                cudaStream_t st) {
+  if (c.d_model == 256) return t256_forward(c, L, params, pe, src, n_seq, hvo, ws, ws_bytes, train, seed, step, seq0, st);
   static thread_local TcPlan pl;
   // gt_forward(train=1) always saves activations (it is the autograd forward); eval forwards do not
   GT_TRY(tc_check(c, n_seq, train ? 1 : 0, ws, ws_bytes, pl));
@@ -299,6 +301,7 @@ int tc_forward(const gt_config &c, const Layout &L, const float *params, const f
 int tc_backward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
                 int64_t n_seq, const float *hvo, const float *d_hvo, float *grads, void *ws, int64_t ws_bytes, uint64_t seed,
                 uint64_t step, int64_t seq0, cudaStream_t st) {
+  if (c.d_model == 256) return t256_backward(c, L, params, pe, src, n_seq, hvo, d_hvo, grads, ws, ws_bytes, seed, step, seq0, st);
   static thread_local TcPlan pl;
   GT_TRY(tc_check(c, n_seq, 1, ws, ws_bytes, pl));
   TcCtx x;
@@ -309,6 +312,8 @@ int tc_backward(const gt_config &c, const Layout &L, const float *params, const 
 int tc_train_step(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *y,
                   int64_t n_seq, float penalty, float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,
                   uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  if (c.d_model == 256)
+    return t256_train_step(c, L, params, pe, src, y, n_seq, penalty, grads, metrics6, hvo, ws, ws_bytes, seed, step, seq0, st);
   static thread_local TcPlan pl;
   GT_TRY(tc_check(c, n_seq, 1, ws, ws_bytes, pl));
   TcCtx x;
@@ -321,6 +326,7 @@ int tc_train_step(const gt_config &c, const Layout &L, const float *params, cons
 
 int tc_predict(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, int64_t n_seq,
                float thres, float *hvo_out, void *ws, int64_t ws_bytes, cudaStream_t st) {
+  if (c.d_model == 256) return t256_predict(c, L, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, st);
   static thread_local TcPlan pl;
   GT_TRY(tc_check(c, n_seq, 0, ws, ws_bytes, pl));
   TcCtx x;

@@ -127,11 +127,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // bounded wait: a lost arrival becomes a trap (reported as a CUDA error) instead of a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
 
+// warp-converged election of one issuing lane (the same lane every time for a full warp)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
