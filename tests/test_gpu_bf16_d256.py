@@ -55,3 +55,68 @@ def test_many_tiles_persistent_loop():
         h, v, o = model(x.cuda())
     rh, rv, ro = G.forward_encoder_only(P, cfg, x)
     assert rel_err(h.cpu().numpy(), rh.numpy()) < 3e-2
+
+
+def _worst_grad_err(model, grads):
+    gg = grads_by_name(model)
+    worst = ("", 0.0)
+    for k, w in grads.items():
+        scale = float(w.abs().max())
+        if scale < 1e-6:
+            continue
+        e = float((gg[k] - w).abs().max()) / scale
+        if e > worst[1]:
+            worst = (k, e)
+    return worst
+
+
+@pytest.mark.parametrize("name,n", [("c4_l2", 4), ("c4_l2", 64), ("h8_f128", 5), ("h8_f128", 64), ("h16_f192_sym", 7)])
+def test_train_step_matches_oracle(name, n):
+    cfg, pen, p = SHAPES[name]
+    model, P = build_model(cfg, dropout=p, precision="bf16")
+    model.set_seed(7, step=1, seq0=0).train()
+    x, y = G.det_batch(cfg, n)
+    metrics, hvo = model.train_step(x.cuda(), y.cuda(), pen)
+    loss6, grads, _ = G.train_step_oracle(P, cfg, x, y, pen, G.DropCtx(p, 7, 1, 0, True))
+    got = metrics.cpu().numpy().astype(np.float64)
+    assert abs(got[0] - loss6[0]) / abs(loss6[0]) < LOSS_RTOL, (got, loss6)
+    worst = _worst_grad_err(model, grads)
+    # bf16 operand rounding is independent per sample: the error is a few % of each tensor's max at n=4 and falls as
+    # 1/sqrt(n); a logic error would not shrink
+    assert worst[1] < (4e-2 if n >= 64 else 0.2), f"gradient mismatch {worst}"
+
+
+def test_train_step_no_dropout_many_tiles():
+    cfg, pen, p = SHAPES["c4_l2"]
+    model, P = build_model(cfg, dropout=0.0, precision="bf16")
+    model.set_seed(1).train()
+    n = 4 * 148 + 6                     # more tiles than SMs plus a ragged tail tile
+    x, y = G.det_batch(cfg, n)
+    metrics, hvo = model.train_step(x.cuda(), y.cuda(), pen)
+    loss6, grads, _ = G.train_step_oracle(P, cfg, x, y, pen, G.DropCtx(0.0, 1, 0, 0, True))
+    got = metrics.cpu().numpy().astype(np.float64)
+    assert abs(got[0] - loss6[0]) / abs(loss6[0]) < LOSS_RTOL, (got, loss6)
+    worst = _worst_grad_err(model, grads)
+    assert worst[1] < 4e-2, f"gradient mismatch {worst}"
+
+
+def test_loss_trajectory_bf16_vs_fp32():
+    """20 SGD steps from identical weights / data / dropout masks.  Each step's loss is within 2e-3 of the fp32 path's at
+    the same weights (test_train_step_matches_oracle); along a 20-step trajectory the weight differences compound, so
+    the trajectories are compared at twice that."""
+    from transformergrooveinfilling_b200 import FusedSGD
+    cfg, pen, p = SHAPES["c4_l2"]
+    x, y = [t.cuda() for t in G.det_batch(cfg, 64)]
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        model, _ = build_model(cfg, dropout=p, precision=prec)
+        model.set_seed(3).train()
+        opt = FusedSGD(model, 0.04)
+        t = []
+        for _ in range(20):
+            m, _ = model.train_step(x, y, pen)
+            opt.step()
+            t.append(float(m[0]))
+        traj[prec] = np.array(t)
+    np.testing.assert_allclose(traj["bf16"], traj["fp32"], rtol=2 * LOSS_RTOL)
+    assert traj["fp32"][-1] < traj["fp32"][0]

@@ -1,10 +1,9 @@
 // tc256.cu — fused encoder-layer kernels for d_model = 256.  See tc256.cuh for the design.
-#include "tc256.cuh"
-#include "umma.cuh"
 #include <stdlib.h>
 
+#include "tc256_dev.cuh"
+
 namespace gt {
-using namespace umma;
 
 bool t256_shape_supported(const gt_config &c, std::string *why) {
   auto no = [&](const char *m) { if (why) *why = m; return false; };
@@ -159,19 +158,6 @@ int t256_from_tiled(const float *tiled, float *rowmajor, int64_t M, cudaStream_t
   return 0;
 }
 
-// =============================================================================================
-// device helpers
-// =============================================================================================
-// 64-bit UMMA descriptors are built once per operand and advanced by adding (bytes >> 4) to the address field
-__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
-__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
-__device__ __forceinline__ uint64_t descA128(uint32_t base) { return make_desc(base, 2048u, 128u); }                 // A image with 128 rows: k16 step = 4096 B
-__device__ __forceinline__ uint64_t descB(uint32_t base, int N) { return make_desc(base, (uint32_t)(N >> 3) * 128u, 128u); }   // k16 step = N * 32 B
-// dropout hash of two consecutive elements (idx even): w = idx >> 1 given as (wlo + j, xhi)
-__device__ __forceinline__ uint32_t drop_hash(uint32_t wlo_j, uint32_t xhi, uint32_t key) { return mix32(((wlo_j ^ xhi) * 0x9E3779B1u) ^ key); }
-
-#define T256_STAMP() do { if (dbg_on && ndbg < 60) a.dbg[ndbg++] = clock64(); } while (0)
 
 struct T256FwdSmem {
   static constexpr uint32_t x = 0, ring = 65536, qkv = 131072, ctx = 180224, par = 212992, stat = 224256, total = 228352;
@@ -770,7 +756,7 @@ int t256_debug_umma_rate(int N, int n_mma, int ksteps, float *out, cudaStream_t 
   return 0;
 }
 
-static int t256_num_sms() {
+int t256_num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -780,32 +766,6 @@ static int t256_num_sms() {
   }
   return n;
 }
-
-// optional clock64 timeline of CTA 0 (GT_T256_DBG=<number of launches to trace>)
-struct T256Dbg {
-  unsigned long long *buf = nullptr;
-  int left = getenv("GT_T256_DBG") ? atoi(getenv("GT_T256_DBG")) : 0;
-  bool arm(T256Args &a, cudaStream_t st) {
-    if (left <= 0) return false;
-    if (!buf) cudaMalloc(&buf, 512 * sizeof(unsigned long long));
-    cudaMemsetAsync(buf, 0, 512 * sizeof(unsigned long long), st);
-    a.dbg = buf;
-    return true;
-  }
-  void report(const char *what, cudaStream_t st) {
-    --left;
-    unsigned long long h[512];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "%s timeline (clk since tile start):", what);
-    for (int i = 1; i < 60 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
-    fprintf(stderr, "\n  mma stage-available:");
-    for (int i = 64; i < 184 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
-    fprintf(stderr, "\n  producer slot-free:");
-    for (int i = 192; i < 312 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
-    fprintf(stderr, "\n");
-  }
-};
 
 template <int DH>
 static int t256_launch_fwd(const T256Args &a_in, int grid, cudaStream_t st) {
@@ -830,7 +790,5 @@ int t256_layer_fwd(const T256Args &a, cudaStream_t st) {
   }
 }
 
-int t256_layer_bwd(const T256Args &, cudaStream_t) { GT_FAIL("t256_layer_bwd: not built yet"); }
-int t256_wgrad(const T256WgradArgs &, cudaStream_t) { GT_FAIL("t256_wgrad: not built yet"); }
 
 }  // namespace gt

@@ -137,7 +137,8 @@ bool t256_shape_supported(const gt_config &c, std::string *why);
 int t256_prep_weights(const TcPrepArgs &a, cudaStream_t st);
 int t256_layer_fwd(const T256Args &a, cudaStream_t st);
 int t256_layer_bwd(const T256Args &a, cudaStream_t st);
-int t256_wgrad(const T256WgradArgs &a, cudaStream_t st);
+constexpr int64_t T256_WG_JOBBUF = 16384;   // device bytes for the weight-gradient job list
+int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st);
 int t256_debug_umma_rate(int N, int n_mma, int ksteps, float *out, cudaStream_t st);
 // layout conversion at the stack boundaries
 int t256_to_image(const float *rowmajor, uint8_t *img, int64_t M, int n_tiles, cudaStream_t st);

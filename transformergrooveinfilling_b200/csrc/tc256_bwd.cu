@@ -1,0 +1,862 @@
+// tc256_bwd.cu — backward of the d_model = 256 fused encoder layer: a data-gradient kernel (same
+// weight-streaming structure as the forward: producer lane, MMA-issuer lane, 16 compute warps) and a
+// weight-gradient kernel that contracts the saved bf16 operand images over all tokens.
+//
+// data-gradient kernel, per tile of 128 tokens (torch/nn/modules/transformer.py:951-956 backwards):
+//   B0  LayerNorm2 backward (dy, u2)            -> du2 (parked in dx), da2 = du2 * mask2 (bf16 image)
+//   B1  dH(c)  = da2 W2[:, chunk c]             UMMA 128x64x256      B2  relu/dropout mask from the saved H image
+//   B3  dx1   += dH(c) W1[chunk c, :]           UMMA 128x256x64
+//   B4  LayerNorm1 backward (du2 + dx1, u1)     -> du1 (parked in dx), da1 = du1 * mask1 (bf16 image)
+//   B5  dctx   = da1 Wo                         UMMA 128x256x256  -> bf16 -> per-CTA scratch (L2)
+//   B6  per head group: recompute q|k|v (UMMA 128x192x256), attention backward on mma.sync fragments,
+//       dx_in += dqkv_g Wqkv[group rows, :]     UMMA 128x256x192
+//   B7  dx = du1 + dx_in
+// Every bf16 image a weight gradient needs (da2, dH, da1, dqkv here; x, x1, ctx, H from the forward) is
+// left in HBM in the canonical UMMA layout, so the weight-gradient kernel stages them with plain bulk
+// copies and feeds them to the tensor core as MN-major operands (contraction over the token rows).
+#include <stdlib.h>
+
+#include "tc256_dev.cuh"
+
+namespace gt {
+
+struct T256BwdSmem {
+  // r1: da2 image -> da1 image -> attention scratch [128 x 256] = q | k | v | dO(group)
+  // r2: FFN phase: H chunk image (+0) and dH chunk image (+16384) ; attention phase: x image
+  static constexpr uint32_t r1 = 0, r2 = 65536, ring = 131072, par = 196608, gpar = par + 1280 * 4, stat = gpar + 2816 * 4,
+                            total = stat + 4096;
+};
+static_assert(T256BwdSmem::total <= 227 * 1024 - 1024, "backward shared memory budget");
+
+// ---- attention backward for one (sequence s, head hl of the group) pair; one warp ---------------------------------
+// sS: scratch image [128 x 256]: cols [0,64) q (scaled by log2e/sqrt(dh)), [64,128) k, [128,192) v, [192,256) dO.
+// dq / dk / dv overwrite q / k / v in place (this warp is the only reader of those rows x columns).
+// g_b: shared-memory partial sums of the in-projection bias gradient for this group: [3][64].
+template <int DH>
+__device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
+  const int g = lane >> 2, t = lane & 3;
+  const int qc = hl * DH, kc = 64 + hl * DH, vc = 128 + hl * DH, oc = 192 + hl * DH;
+  const float inv_sqrt_dh = rsqrtf((float)DH), ln2 = 0.6931471805599453f, ks = dr.scale;
+  const int mi = lane >> 3, rr = lane & 7;
+  float dk[2][DH / 8][4], dv[2][DH / 8][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < DH / 8; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { dk[a][b][c] = 0.f; dv[a][b][c] = 0.f; }
+  float sq[DH / 8][2];                               // column sums of dq over this lane's rows
+#pragma unroll
+  for (int b = 0; b < DH / 8; ++b) { sq[b][0] = 0.f; sq[b][1] = 0.f; }
+
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = s * 32 + 16 * mt + g;             // query rows r0, r0 + 8
+    float p[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { p[i][c] = 0.f; dp[i][c] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < DH / 16; ++kt) {
+      const int c0 = 16 * kt + 2 * t;
+      const uint32_t a0 = lds32(sS + kmajor_off(r0, qc + c0, 128)), a1 = lds32(sS + kmajor_off(r0 + 8, qc + c0, 128));
+      const uint32_t a2 = lds32(sS + kmajor_off(r0, qc + c0 + 8, 128)), a3 = lds32(sS + kmajor_off(r0 + 8, qc + c0 + 8, 128));
+      const uint32_t o0 = lds32(sS + kmajor_off(r0, oc + c0, 128)), o1 = lds32(sS + kmajor_off(r0 + 8, oc + c0, 128));
+      const uint32_t o2 = lds32(sS + kmajor_off(r0, oc + c0 + 8, 128)), o3 = lds32(sS + kmajor_off(r0 + 8, oc + c0 + 8, 128));
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int key = s * 32 + 8 * nt + g;
+        mma16816(p[nt], a0, a1, a2, a3, lds32(sS + kmajor_off(key, kc + c0, 128)), lds32(sS + kmajor_off(key, kc + c0 + 8, 128)));
+        mma16816(dp[nt], o0, o1, o2, o3, lds32(sS + kmajor_off(key, vc + c0, 128)), lds32(sS + kmajor_off(key, vc + c0 + 8, 128)));
+      }
+    }
+    // softmax (rows r0: c0,c1 ; r0+8: c2,c3)
+    float m0 = p[0][0], m1 = p[0][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { m0 = fmaxf(m0, fmaxf(p[nt][0], p[nt][1])); m1 = fmaxf(m1, fmaxf(p[nt][2], p[nt][3])); }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      p[nt][0] = exp2f(p[nt][0] - m0); p[nt][1] = exp2f(p[nt][1] - m0);
+      p[nt][2] = exp2f(p[nt][2] - m1); p[nt][3] = exp2f(p[nt][3] - m1);
+      s0 += p[nt][0] + p[nt][1]; s1 += p[nt][2] + p[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+    // dropout keep bits of this lane's 16 probabilities: bit (4 nt + c)
+    uint32_t keep = 0xFFFFu;
+    if (dr.thr) {
+      keep = 0;
+      const int q0 = 16 * mt + g;
+      const uint64_t wa = w_pair + (uint64_t)q0 * 16u, wb = wa + 128u;
+      const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
+      const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t ha = drop_hash(alo + (uint32_t)(4 * nt + t), ahi, dr.key);
+        const uint32_t hb = drop_hash(blo + (uint32_t)(4 * nt + t), bhi, dr.key);
+        keep |= ((ha & 0xFFFFu) >= dr.thr ? 1u : 0u) << (4 * nt);
+        keep |= ((ha >> 16) >= dr.thr ? 1u : 0u) << (4 * nt + 1);
+        keep |= ((hb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (4 * nt + 2);
+        keep |= ((hb >> 16) >= dr.thr ? 1u : 0u) << (4 * nt + 3);
+      }
+    }
+    // P, dropped P (pd), dL/dP through the dropout, delta = rowsum(dPd * P), dS = P (dPd - delta)
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        p[nt][c] *= (c < 2 ? i0 : i1);
+        dp[nt][c] = ((keep >> (4 * nt + c)) & 1u) ? dp[nt][c] * ks : 0.f;
+      }
+      d0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
+      d1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    // packed bf16 fragments: pdp = dropped probabilities, dsq = dS / sqrt(dh) (for dq), dsk = dS * ln2 (for dk; q is stored scaled)
+    uint32_t pdp[4][2], dsq[4][2], dsk[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float ds[4], pd[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ds[c] = p[nt][c] * (dp[nt][c] - (c < 2 ? d0 : d1));
+        pd[c] = ((keep >> (4 * nt + c)) & 1u) ? p[nt][c] * ks : 0.f;
+      }
+      pdp[nt][0] = pack_bf16(pd[0], pd[1]); pdp[nt][1] = pack_bf16(pd[2], pd[3]);
+      dsq[nt][0] = pack_bf16(ds[0] * inv_sqrt_dh, ds[1] * inv_sqrt_dh); dsq[nt][1] = pack_bf16(ds[2] * inv_sqrt_dh, ds[3] * inv_sqrt_dh);
+      dsk[nt][0] = pack_bf16(ds[0] * ln2, ds[1] * ln2); dsk[nt][1] = pack_bf16(ds[2] * ln2, ds[3] * ln2);
+    }
+    // dk += dS^T Q ; dv += Pd^T dO   (contraction over this m-tile's 16 queries; A = transposed fragments)
+#pragma unroll
+    for (int np = 0; np < DH / 16; ++np) {
+      const int qrow = s * 32 + 16 * mt + (mi & 1) * 8 + rr;
+      uint32_t bq[4], bo[4];
+      ldmatrix_x4_trans(bq, sS + kmajor_off(qrow, qc + 16 * np + (mi >> 1) * 8, 128));
+      ldmatrix_x4_trans(bo, sS + kmajor_off(qrow, oc + 16 * np + (mi >> 1) * 8, 128));
+#pragma unroll
+      for (int kmt = 0; kmt < 2; ++kmt) {
+        const uint32_t s0t = movmatrix_trans(dsk[2 * kmt][0]), s1t = movmatrix_trans(dsk[2 * kmt + 1][0]);
+        const uint32_t s2t = movmatrix_trans(dsk[2 * kmt][1]), s3t = movmatrix_trans(dsk[2 * kmt + 1][1]);
+        mma16816(dk[kmt][2 * np], s0t, s1t, s2t, s3t, bq[0], bq[1]);
+        mma16816(dk[kmt][2 * np + 1], s0t, s1t, s2t, s3t, bq[2], bq[3]);
+        const uint32_t p0t = movmatrix_trans(pdp[2 * kmt][0]), p1t = movmatrix_trans(pdp[2 * kmt + 1][0]);
+        const uint32_t p2t = movmatrix_trans(pdp[2 * kmt][1]), p3t = movmatrix_trans(pdp[2 * kmt + 1][1]);
+        mma16816(dv[kmt][2 * np], p0t, p1t, p2t, p3t, bo[0], bo[1]);
+        mma16816(dv[kmt][2 * np + 1], p0t, p1t, p2t, p3t, bo[2], bo[3]);
+      }
+    }
+    // dq = (dS / sqrt(dh)) K
+    float dq[DH / 8][4];
+#pragma unroll
+    for (int b = 0; b < DH / 8; ++b) { dq[b][0] = 0.f; dq[b][1] = 0.f; dq[b][2] = 0.f; dq[b][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {                  // keys 16 kt .. 16 kt + 15
+#pragma unroll
+      for (int np = 0; np < DH / 16; ++np) {
+        const int key = s * 32 + 16 * kt + (mi & 1) * 8 + rr;
+        uint32_t bk[4];
+        ldmatrix_x4_trans(bk, sS + kmajor_off(key, kc + 16 * np + (mi >> 1) * 8, 128));
+        mma16816(dq[2 * np], dsq[2 * kt][0], dsq[2 * kt][1], dsq[2 * kt + 1][0], dsq[2 * kt + 1][1], bk[0], bk[1]);
+        mma16816(dq[2 * np + 1], dsq[2 * kt][0], dsq[2 * kt][1], dsq[2 * kt + 1][0], dsq[2 * kt + 1][1], bk[2], bk[3]);
+      }
+    }
+    __syncwarp();                                     // every lane has finished reading this m-tile's q rows
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(r0, qc + 8 * nt + 2 * t, 128)) = pack_bf16(dq[nt][0], dq[nt][1]);
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(r0 + 8, qc + 8 * nt + 2 * t, 128)) = pack_bf16(dq[nt][2], dq[nt][3]);
+      sq[nt][0] += dq[nt][0] + dq[nt][2]; sq[nt][1] += dq[nt][1] + dq[nt][3];
+    }
+  }
+  __syncwarp();                                       // all reads of k / v / dO by every lane are done
+#pragma unroll
+  for (int kmt = 0; kmt < 2; ++kmt)
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      const int kr = s * 32 + 16 * kmt + g;
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr, kc + 8 * nt + 2 * t, 128)) = pack_bf16(dk[kmt][nt][0], dk[kmt][nt][1]);
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr + 8, kc + 8 * nt + 2 * t, 128)) = pack_bf16(dk[kmt][nt][2], dk[kmt][nt][3]);
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr, vc + 8 * nt + 2 * t, 128)) = pack_bf16(dv[kmt][nt][0], dv[kmt][nt][1]);
+      *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr + 8, vc + 8 * nt + 2 * t, 128)) = pack_bf16(dv[kmt][nt][2], dv[kmt][nt][3]);
+    }
+  // in-projection bias gradient: column sums over the pair's 32 rows
+#pragma unroll
+  for (int nt = 0; nt < DH / 8; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float a = sq[nt][j];
+      float b = dk[0][nt][j] + dk[0][nt][j + 2] + dk[1][nt][j] + dk[1][nt][j + 2];
+      float c = dv[0][nt][j] + dv[0][nt][j + 2] + dv[1][nt][j] + dv[1][nt][j + 2];
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+      }
+      if (g == 0) {
+        const int col = hl * DH + 8 * nt + 2 * t + j;
+        atomicAdd(g_b + col, a); atomicAdd(g_b + 64 + col, b); atomicAdd(g_b + 128 + col, c);
+      }
+    }
+  }
+}
+
+// ---- LayerNorm backward over a [128 x 256] tile; thread = (row, 64-column part) ----------------------------------
+// dyv(cb, out16): loads 16 values of the incoming gradient for columns part*64 + cb..  (re-readable)
+// Writes du (tiled fp32 -> park) and da = du * dropmask (bf16 -> sImg and gImg); accumulates dgamma / dbeta / dbias partials.
+template <class DyLoad>
+__device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*global tile image*/, const float *gamma, float *park /*tiled fp32 tile*/,
+                                            uint8_t *sImg, uint8_t *gImg, const Drop &dr, uint64_t e_row /* element index of (row, col 0) */,
+                                            float *g_gamma, float *g_beta, float *g_bias, float *sStatA, float *sStatB, int row, int part, int lane) {
+  // pass A: statistics of u
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 8) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + c, 128));
+    const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+  }
+  sStatA[row * 4 + part] = s1; sStatB[row * 4 + part] = s2;
+  named_bar_sync(1, T256_CTHREADS);
+  float mu, rs;
+  {
+    const float4 sa = *reinterpret_cast<const float4 *>(sStatA + row * 4), sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
+    mu = ((sa.x + sa.y) + (sa.z + sa.w)) * (1.f / 256);
+    const float var = fmaxf(((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256) - mu * mu, 0.f);
+    rs = rsqrtf(var + LN_EPS);
+  }
+  named_bar_sync(1, T256_CTHREADS);                  // everyone has read the statistics before they are overwritten below
+  // pass B: m1 = mean(dy g), m2 = mean(dy g xhat) ; dgamma / dbeta column sums
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < 64; cb += 16) {
+    float dy[16], w[32];
+    dyv(cb, dy);
+    const uint4 v0 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb, 128));
+    const uint4 v1 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 8, 128));
+    const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
+                          bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float xh = (uu[j] - mu) * rs, gd = dy[j] * gamma[part * 64 + cb + j];
+      m1 += gd; m2 = fmaf(gd, xh, m2);
+      w[j] = dy[j] * xh; w[16 + j] = dy[j];
+    }
+    const float tsum = t256_colsum32(w, lane);
+    if (lane < 16) atomicAdd(g_gamma + part * 64 + cb + lane, tsum);
+    else atomicAdd(g_beta + part * 64 + cb + lane - 16, tsum);
+  }
+  sStatA[row * 4 + part] = m1; sStatB[row * 4 + part] = m2;
+  named_bar_sync(1, T256_CTHREADS);
+  {
+    const float4 sa = *reinterpret_cast<const float4 *>(sStatA + row * 4), sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
+    m1 = ((sa.x + sa.y) + (sa.z + sa.w)) * (1.f / 256);
+    m2 = ((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256);
+  }
+  // pass C: du = rstd (dy g - m1 - xhat m2) ; da = du * dropmask
+  const uint64_t w0 = (e_row + (uint64_t)(part * 64)) >> 1;
+  const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
+#pragma unroll 1
+  for (int cb = 0; cb < 64; cb += 32) {
+    float w[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float dy[16];
+      dyv(cb + 16 * h, dy);
+      const uint4 v0 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 16 * h, 128));
+      const uint4 v1 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 16 * h + 8, 128));
+      const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
+                            bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float xh = (uu[j] - mu) * rs;
+        w[16 * h + j] = rs * (dy[j] * gamma[part * 64 + cb + 16 * h + j] - m1 - xh * m2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4 *>(park + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+    if (dr.thr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const uint32_t hs = drop_hash(wlo + (uint32_t)((cb + j) >> 1), xhi, dr.key);
+        w[j] = ((hs & 0xFFFFu) >= dr.thr) ? w[j] * dr.scale : 0.f;
+        w[j + 1] = ((hs >> 16) >= dr.thr) ? w[j + 1] * dr.scale : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 pk = make_uint4(pack_bf16(w[j], w[j + 1]), pack_bf16(w[j + 2], w[j + 3]), pack_bf16(w[j + 4], w[j + 5]), pack_bf16(w[j + 6], w[j + 7]));
+      const uint32_t off = kmajor_off(row, part * 64 + cb + j, 128);
+      *reinterpret_cast<uint4 *>(sImg + off) = pk;
+      *reinterpret_cast<uint4 *>(gImg + off) = pk;
+    }
+    const float tsum = t256_colsum32(w, lane);
+    atomicAdd(g_bias + part * 64 + cb + lane, tsum);
+  }
+}
+
+// =============================================================================================
+// data-gradient kernel
+// =============================================================================================
+template <int DH>
+__global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T256Args a) {
+  constexpr int G = T256_G, GH = 64 / DH, NS = T256_NS;
+  using S = T256BwdSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_da2ready, bar_hready, bar_hfree, bar_dhfull, bar_dhimgready, bar_r2a,
+      bar_r2b, bar_dx1full, bar_da1ready, bar_dctxfull, bar_xready, bar_qkvfree, bar_qkvfull, bar_dqkvready, bar_dqkvfree, bar_dxinfull;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int F = a.F, NCH = F / 64, H = a.H;
+  uint8_t *sR1 = smem + S::r1, *sR2 = smem + S::r2, *sRing = smem + S::ring;
+  float *sPar = reinterpret_cast<float *>(smem + S::par);
+  float *p_bqkv = sPar, *p_g1 = sPar + 768, *p_g2 = p_g1 + 256;
+  float *sG = reinterpret_cast<float *>(smem + S::gpar);
+  float *g_bqkv = sG, *g_bo = sG + 768, *g_b2 = g_bo + 256, *g_g1 = g_b2 + 256, *g_be1 = g_g1 + 256, *g_g2 = g_be1 + 256, *g_be2 = g_g2 + 256,
+        *g_b1 = g_be2 + 256;
+  float *sStatA = reinterpret_cast<float *>(smem + S::stat), *sStatB = sStatA + 512;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    uint64_t *bars[] = {&bar_da2ready, &bar_hready, &bar_hfree, &bar_dhfull, &bar_dhimgready, &bar_r2a, &bar_r2b, &bar_dx1full, &bar_da1ready,
+                        &bar_dctxfull, &bar_xready, &bar_qkvfree, &bar_qkvfull, &bar_dqkvready, &bar_dqkvfree, &bar_dxinfull};
+    for (uint64_t *b : bars) mbar_init(b, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 768; i += T256_THREADS) p_bqkv[i] = a.bqkv[i];
+  if (tid < 256) { p_g1[tid] = a.g1[tid]; p_g2[tid] = a.g2[tid]; }
+  for (int i = tid; i < 2816; i += T256_THREADS) sG[i] = 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_dx = tmem, t_b = tmem + 256;
+  const uint32_t aR1 = smem_u32(sR1), aR2 = smem_u32(sR2), aRing = smem_u32(sRing);
+  const int nfs = 4 * NCH;                          // FFN stages per tile
+  const uint32_t uses_per_tile = (uint32_t)(16 + NCH);   // (64 + 4 NCH) / NS
+  const uint8_t *wimg = a.img + (size_t)(blockIdx.x % T256_REP) * a.img_rep_stride + (size_t)t256_fwd_stages(F) * T256_STAGE;
+
+  if (warp == 16) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t use0 = it * uses_per_tile;
+        auto stage = [&](int st, uint32_t bytes) {
+          const int slot = st % NS;
+          mbar_wait(&bar_empty[slot], ((use0 + (uint32_t)(st / NS)) & 1u) ^ 1u);
+          mbar_expect_tx(&bar_full[slot], bytes);
+          tma_load_1d(sRing + slot * T256_STAGE, wimg + (size_t)st * T256_STAGE, bytes, &bar_full[slot]);
+        };
+        mbar_wait(&bar_r2b, (it & 1u) ^ 1u);                   // the previous tile's q|k|v recompute no longer reads the x image in r2
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
+          mbar_wait(&bar_hfree, (n & 1u) ^ 1u);
+          mbar_expect_tx(&bar_hready, 16384u);
+          tma_load_1d(sR2, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready);
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) stage(4 * c + j, 16384u);
+        }
+        mbar_wait(&bar_r2a, it & 1u);                          // dx1 of the last FFN chunk retired: r2 is free for the x image
+        mbar_expect_tx(&bar_xready, 65536u);
+        tma_load_1d(sR2, a.x_img_in + (size_t)tile * T256_TILE_IMG, 32768u, &bar_xready);
+        tma_load_1d(sR2 + 32768, a.x_img_in + (size_t)tile * T256_TILE_IMG + 32768, 32768u, &bar_xready);
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) stage(nfs + j, 16384u);
+#pragma unroll 1
+        for (int j = 0; j < 56; ++j) {
+          // QKV(0) x8 ; g = 1..3: QKV(g) x8, WqkvT(g-1) x6 ; WqkvT(3) x6
+          const bool is_qkv = j < 8 || (j < 50 && ((j - 8) % 14) < 8);
+          stage(nfs + 8 + j, is_qkv ? 12288u : 16384u);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ======================= MMA issuer =======================
+    if (elect_one()) {
+      const uint32_t id_192 = make_idesc_bf16(128, 192), id_256 = make_idesc_bf16(128, 256), id_64 = make_idesc_bf16(128, 64);
+      const uint64_t dR1 = descA128(aR1), dR2 = descA128(aR2), dDH = descA128(aR2 + 16384u);
+      const uint64_t dB192 = descB(aRing, 192), dB256 = descB(aRing, 256), dB64 = descB(aRing, 64);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t use0 = it * uses_per_tile;
+        auto full_wait = [&](int st) {
+          mbar_wait(&bar_full[st % NS], (use0 + (uint32_t)(st / NS)) & 1u);
+          fence_after_sync();
+        };
+        // ---- FFN backward ----
+        mbar_wait(&bar_da2ready, it & 1u);
+        fence_after_sync();
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {              // dH(c) = da2 W2[:, chunk]
+            const int st = 4 * c + hf;
+            full_wait(st);
+            const uint64_t db = desc_adv(dB64, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              mma_bf16_ss(t_b, desc_adv(dR1, (uint32_t)(hf * 8 + k) * 4096u), desc_adv(db, (uint32_t)k * 2048u), id_64, (hf | k) > 0);
+            mma_commit(&bar_empty[st % NS]);
+          }
+          mma_commit(&bar_dhfull);
+          mbar_wait(&bar_dhimgready, n & 1u);
+          fence_after_sync();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {              // dx1 += dH(c) W1[chunk, :]
+            const int st = 4 * c + 2 + hf;
+            full_wait(st);
+            const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              mma_bf16_ss(t_dx, desc_adv(dDH, (uint32_t)(hf * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (c | hf | k) > 0);
+            mma_commit(&bar_empty[st % NS]);
+          }
+        }
+        mma_commit(&bar_dx1full);
+        mma_commit(&bar_r2a);
+        // ---- dctx = da1 Wo ----
+        mbar_wait(&bar_da1ready, it & 1u);
+        fence_after_sync();
+#pragma unroll 2
+        for (int b = 0; b < 8; ++b) {
+          const int st = nfs + b;
+          full_wait(st);
+          const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            mma_bf16_ss(t_b, desc_adv(dR1, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (b | k) > 0);
+          mma_commit(&bar_empty[st % NS]);
+        }
+        mma_commit(&bar_dctxfull);
+        // ---- attention backward, per head group ----
+        mbar_wait(&bar_xready, it & 1u);
+        fence_after_sync();
+        const int A0 = nfs + 8;
+        auto dxin = [&](int gg, int st0) {              // dx_in += dqkv[:, group gg] Wqkv[group gg rows, :]   (K = 192: six stages)
+          const uint32_t n = it * G + (uint32_t)gg;
+          mbar_wait(&bar_dqkvready, n & 1u);
+          fence_after_sync();
+#pragma unroll 2
+          for (int b = 0; b < 6; ++b) {
+            const int st = st0 + b;
+            full_wait(st);
+            const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              mma_bf16_ss(t_dx, desc_adv(dR1, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (gg | b | k) > 0);
+            mma_commit(&bar_empty[st % NS]);
+          }
+          mma_commit(&bar_dqkvfree);
+        };
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+          const int st0 = g == 0 ? A0 : A0 + 8 + (g - 1) * 14;
+          const uint32_t n = it * G + (uint32_t)g;
+          mbar_wait(&bar_qkvfree, n & 1u);
+          fence_after_sync();
+#pragma unroll 2
+          for (int kc = 0; kc < 8; ++kc) {
+            const int st = st0 + kc;
+            full_wait(st);
+            const uint64_t db = desc_adv(dB192, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              mma_bf16_ss(t_b, desc_adv(dR2, (uint32_t)(kc * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 6144u), id_192, (kc | k) > 0);
+            mma_commit(&bar_empty[st % NS]);
+          }
+          mma_commit(&bar_qkvfull);
+          if (g == G - 1) mma_commit(&bar_r2b);
+          if (g >= 1) dxin(g - 1, st0 + 8);
+        }
+        dxin(G - 1, A0 + 50);
+        mma_commit(&bar_dxinfull);
+      }
+    }
+  } else {
+    // ======================= compute warps =======================
+    const int q4 = warp & 3, part = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float attn_scale = rsqrtf((float)DH) * 1.4426950408889634f;
+    uint8_t *scratch = a.dctx_scratch + (size_t)blockIdx.x * T256_TILE_IMG;
+    uint32_t it = 0;
+    int ndbg = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it == 1;
+      T256_STAMP();
+      const int64_t grow = (int64_t)tile * TC_TILE + row;
+      const float *dy_t = a.dy + (size_t)tile * T256_TILE_F32;
+      float *dx_t = a.dx + (size_t)tile * T256_TILE_F32;
+      const uint64_t e_row = (uint64_t)((a.seq0 * 32 + grow) * 256);
+      // ---- B0: LayerNorm2 backward ----
+      {
+        auto dyload = [&](int cb, float (&o)[16]) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(dy_t + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4));
+            o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
+          }
+        };
+        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, p_g2, dx_t, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
+                    g_g2, g_be2, g_b2, sStatA, sStatB, row, part, lane);
+      }
+      fence_async_smem();
+      named_bar_sync(1, T256_CTHREADS);
+      if (tid == 0) mbar_arrive(&bar_da2ready);
+      T256_STAMP();
+      // ---- B2: hidden-activation gradient per FFN chunk ----
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
+        mbar_wait(&bar_hready, n & 1u);
+        mbar_wait(&bar_dhfull, n & 1u);
+        fence_after_sync();
+        float w[32];
+        tmem_ld16(t_b + lane_off + (uint32_t)(part * 16), w);
+        tmem_ld_wait();
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(sR2 + kmajor_off(row, part * 16, 128));
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(sR2 + kmajor_off(row, part * 16 + 8, 128));
+        const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float sc = a.d_ffn.scale;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          w[2 * j] = (hh[j] & 0x7FFFu) != 0u && !(hh[j] & 0x8000u) ? w[2 * j] * sc : 0.f;                  // H > 0  (bf16 low half)
+          w[2 * j + 1] = (hh[j] & 0x7FFF0000u) != 0u && !(hh[j] & 0x80000000u) ? w[2 * j + 1] * sc : 0.f;  // bf16 high half
+        }
+#pragma unroll
+        for (int j = 16; j < 32; ++j) w[j] = 0.f;
+        const uint4 pk0 = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        const uint4 pk1 = make_uint4(pack_bf16(w[8], w[9]), pack_bf16(w[10], w[11]), pack_bf16(w[12], w[13]), pack_bf16(w[14], w[15]));
+        uint8_t *dhg = a.dh_img + ((size_t)tile * NCH + c) * 16384;
+        const uint32_t o0 = kmajor_off(row, part * 16, 128), o1 = kmajor_off(row, part * 16 + 8, 128);
+        *reinterpret_cast<uint4 *>(sR2 + 16384 + o0) = pk0; *reinterpret_cast<uint4 *>(sR2 + 16384 + o1) = pk1;
+        *reinterpret_cast<uint4 *>(dhg + o0) = pk0; *reinterpret_cast<uint4 *>(dhg + o1) = pk1;
+        const float tsum = t256_colsum32(w, lane);
+        if (lane < 16) atomicAdd(g_b1 + c * 64 + part * 16 + lane, tsum);
+        fence_async_smem();
+        fence_before_sync();
+        named_bar_sync(1, T256_CTHREADS);
+        if (tid == 0) { mbar_arrive(&bar_dhimgready); mbar_arrive(&bar_hfree); }
+      }
+      T256_STAMP();
+      // ---- B4: LayerNorm1 backward on du2 (parked) + dx1 (TMEM) ----
+      mbar_wait(&bar_dx1full, it & 1u);
+      fence_after_sync();
+      T256_STAMP();
+      {
+        auto dyload = [&](int cb, float (&o)[16]) {
+          float f[16];
+          tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(dx_t + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4));
+            o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] += f[j];
+        };
+        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, p_g1, dx_t, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
+                    g_g1, g_be1, g_bo, sStatA, sStatB, row, part, lane);
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(1, T256_CTHREADS);
+      if (tid == 0) mbar_arrive(&bar_da1ready);
+      T256_STAMP();
+      // ---- B5: dctx (TMEM) -> bf16 -> this CTA's scratch image ----
+      mbar_wait(&bar_dctxfull, it & 1u);
+      fence_after_sync();
+      T256_STAMP();
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 16) {
+        float f[16];
+        tmem_ld16(t_b + lane_off + (uint32_t)(part * 64 + cb), f);
+        tmem_ld_wait();
+        *reinterpret_cast<uint4 *>(scratch + kmajor_off(row, part * 64 + cb, 128)) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        *reinterpret_cast<uint4 *>(scratch + kmajor_off(row, part * 64 + cb + 8, 128)) =
+            make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+      }
+      __threadfence_block();
+      fence_before_sync();
+      named_bar_sync(1, T256_CTHREADS);
+      if (tid == 0) mbar_arrive(&bar_qkvfree);
+      T256_STAMP();
+      // ---- B6: head groups ----
+      for (int g = 0; g < G; ++g) {
+        const uint32_t n = it * G + (uint32_t)g;
+        mbar_wait(&bar_qkvfull, n & 1u);
+        fence_after_sync();
+        T256_STAMP();
+        float v[48];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tmem_ld16(t_b + lane_off + (uint32_t)(part * 48 + i * 16), v + i * 16);
+        const uint4 dc0 = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)g * 16384 + (size_t)tid * 16));
+        const uint4 dc1 = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)g * 16384 + 8192 + (size_t)tid * 16));
+        tmem_ld_wait();
+        if (g >= 1) mbar_wait(&bar_dqkvfree, (n - 1u) & 1u);     // dx_in of the previous group no longer reads the dqkv image in r1
+        if (tid == 0) tma_store_wait_read();                       // ... nor do the bulk stores of its dq | dk | dv slices
+        fence_before_sync();
+        named_bar_sync(1, T256_CTHREADS);
+        if (tid == 0 && g + 1 < G) mbar_arrive(&bar_qkvfree);     // the TMEM chunk is drained: the next group's q|k|v may overwrite it
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int n0 = part * 48 + i * 8, pq = n0 >> 6;
+          const float *bias = p_bqkv + pq * 256 + g * 64 + (n0 & 63);
+          const float sc = pq == 0 ? attn_scale : 1.f;
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = (v[i * 8 + j] + bias[j]) * sc;
+          *reinterpret_cast<uint4 *>(sR1 + kmajor_off(row, n0, 128)) =
+              make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        }
+        *reinterpret_cast<uint4 *>(sR1 + 49152 + (size_t)tid * 16) = dc0;
+        *reinterpret_cast<uint4 *>(sR1 + 49152 + 8192 + (size_t)tid * 16) = dc1;
+        named_bar_sync(1, T256_CTHREADS);
+        T256_STAMP();
+        if (warp < 4 * GH) {
+          const int s = warp / GH, hl = warp % GH;
+          const int64_t seq = a.seq0 + (int64_t)tile * 4 + s;
+          const uint64_t w_pair = (uint64_t)((seq * H + (g * GH + hl)) * 32) * 16u;
+          t256_attn_bwd<DH>(sR1, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
+        }
+        fence_async_smem();
+        named_bar_sync(1, T256_CTHREADS);
+        if (tid == 0) {
+          mbar_arrive(&bar_dqkvready);
+          uint8_t *dq_g = a.dqkv_img + (size_t)tile * (3 * T256_TILE_IMG) + (size_t)g * 16384;
+          tma_store_1d(dq_g, sR1, 16384u);
+          tma_store_1d(dq_g + T256_TILE_IMG, sR1 + 16384, 16384u);
+          tma_store_1d(dq_g + 2 * T256_TILE_IMG, sR1 + 32768, 16384u);
+          tma_store_commit();
+        }
+        T256_STAMP();
+      }
+      // ---- B7: dx = du1 (parked) + dx_in ----
+      mbar_wait(&bar_dxinfull, it & 1u);
+      fence_after_sync();
+      T256_STAMP();
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 16) {
+        float f[16];
+        tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
+        float4 pv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pv[j] = __ldcg(reinterpret_cast<const float4 *>(dx_t + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4 *>(dx_t + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4) =
+              make_float4(pv[j].x + f[4 * j], pv[j].y + f[4 * j + 1], pv[j].z + f[4 * j + 2], pv[j].w + f[4 * j + 3]);
+      }
+      if (tid == 0) tma_store_wait_read();
+      fence_before_sync();
+      named_bar_sync(1, T256_CTHREADS);
+      T256_STAMP();
+    }
+    if (tid == 0) tma_store_wait_all();
+    // ---- flush bias / LayerNorm gradient partials ----
+    named_bar_sync(1, T256_CTHREADS);
+    for (int i = tid; i < 768; i += T256_CTHREADS) {
+      // g_bqkv is stored per group: [g][3][64] -> in_proj_bias index part*256 + g*64 + col
+      const int g = i / 192, r = i % 192, pq = r / 64, col = r % 64;
+      atomicAdd(a.gbqkv + pq * 256 + g * 64 + col, g_bqkv[i]);
+    }
+    for (int i = tid; i < F; i += T256_CTHREADS) atomicAdd(a.gb1 + i, g_b1[i]);
+    if (tid < 256) {
+      atomicAdd(a.gbo + tid, g_bo[tid]); atomicAdd(a.gb2 + tid, g_b2[tid]);
+      atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
+      atomicAdd(a.gg2 + tid, g_g2[tid]); atomicAdd(a.gbe2 + tid, g_be2[tid]);
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int DH>
+static int t256_launch_bwd(const T256Args &a_in, int grid, cudaStream_t st) {
+  static T256Dbg dbg;
+  T256Args a = a_in;
+  const bool d = dbg.arm(a, st);
+  GT_CUDA(cudaFuncSetAttribute(t256_layer_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256BwdSmem::total));
+  { LaunchScope _ls(KC_TC_LAYER_BWD, st);
+    t256_layer_bwd_kernel<DH><<<grid, T256_THREADS, T256BwdSmem::total, st>>>(a); }
+  GT_CUDA(cudaGetLastError());
+  if (d) dbg.report("t256 bwd", st);
+  return 0;
+}
+
+int t256_layer_bwd(const T256Args &a, cudaStream_t st) {
+  GT_CHECK(a.F % 64 == 0 && a.F >= 64 && a.F <= 512, "t256_layer_bwd: dim_feedforward not supported");
+  int grid = a.n_tiles < t256_num_sms() ? a.n_tiles : t256_num_sms();
+  if (grid > 160) grid = 160;                        // dctx scratch is sized for 160 CTAs
+  switch (a.dh) {
+    case 16: return t256_launch_bwd<16>(a, grid, st);
+    case 32: return t256_launch_bwd<32>(a, grid, st);
+    default: GT_FAIL("t256_layer_bwd: head dim not instantiated");
+  }
+}
+
+// =============================================================================================
+// weight-gradient kernel: dW = sum over tiles of  A_tile^T B_tile  with both operands taken as MN-major views
+// of the saved [128 tokens x C] images.  CTA = (job, split): job = one [128 x N] block of one weight gradient,
+// split = a contiguous range of tiles.  Two 96 KB stages (A block 32 KB + B up to 64 KB) double-buffer the
+// bulk-TMA loads against the 8 UMMAs of a tile; the accumulator lives in TMEM for the whole CTA and is added
+// to the fp32 gradient with vector atomics at the end.
+// =============================================================================================
+struct T256WJob {
+  const uint8_t *a_img, *b_img;       // per-tile images
+  uint32_t a_tile_stride, a_off;      // bytes: tile stride of the A image, offset of this job's 128-column block
+  uint32_t b_tile_stride, b_bytes;    // B: whole image of the tile ([128 x N])
+  int N;                              // 64..256
+  float *out;                         // out[(m) * ld_m + n * ld_n]
+  int ld_m, ld_n;
+  int tile0, tile1;
+};
+constexpr int T256_WG_MAXJOBS = 160;
+struct T256WgradLaunch {
+  T256WJob jobs[T256_WG_MAXJOBS];
+};
+
+__device__ __forceinline__ uint64_t t256_desc_mn(uint32_t base, uint32_t bytes) {      // image [128 rows (k) x cols (mn)]; k16 step = 256 B
+  return make_desc(base + bytes, 128u, 2048u);
+}
+
+__global__ void __launch_bounds__(192, 1) t256_wgrad_kernel(const T256WJob *__restrict__ jobs) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const T256WJob job = jobs[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t STG = 98304;
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1); mbar_init(&bar_done, 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int ntl = job.tile1 - job.tile0;
+  if (warp == 4) {
+    if (elect_one()) {
+      for (int i = 0; i < ntl; ++i) {
+        const int slot = i & 1;
+        mbar_wait(&bar_empty[slot], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&bar_full[slot], 32768u + job.b_bytes);
+        const size_t tile = (size_t)(job.tile0 + i);
+        tma_load_1d(smem + slot * STG, job.a_img + tile * job.a_tile_stride + job.a_off, 32768u, &bar_full[slot]);
+        for (uint32_t off = 0; off < job.b_bytes; off += 32768u) {
+          const uint32_t nb = job.b_bytes - off < 32768u ? job.b_bytes - off : 32768u;
+          tma_load_1d(smem + slot * STG + 32768 + off, job.b_img + tile * job.b_tile_stride + off, nb, &bar_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, job.N, 1, 1);
+      for (int i = 0; i < ntl; ++i) {
+        const int slot = i & 1;
+        mbar_wait(&bar_full[slot], ((uint32_t)i >> 1) & 1u);
+        fence_after_sync();
+        const uint32_t base = smem_u32(smem) + slot * STG;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mma_bf16_ss(tmem, t256_desc_mn(base, (uint32_t)k * 256u), t256_desc_mn(base + 32768u, (uint32_t)k * 256u), idesc, (i | k) > 0);
+        mma_commit(&bar_empty[slot]);
+      }
+      mma_commit(&bar_done);
+    }
+  }
+  if (warp < 4) {
+    if (ntl > 0) {
+      mbar_wait(&bar_done, 0);
+      fence_after_sync();
+      const int m = warp * 32 + lane;
+      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+      for (int cb = 0; cb < job.N; cb += 16) {
+        float f[16];
+        tmem_ld16(tmem + lane_off + (uint32_t)cb, f);
+        tmem_ld_wait();
+        if (job.ld_n == 1) {
+          float *o = job.out + (size_t)m * job.ld_m + cb;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4 *>(o + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(job.out + (size_t)m * job.ld_m + (size_t)(cb + j) * job.ld_n, f[j]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st) {
+  // job list: dWqkv 6 blocks (A = dqkv cols, B = x), dWo 2 (A = da1, B = ctx), dW1^T 2 (A = x1, B = dH), dW2 2 (A = da2, B = H)
+  static thread_local T256WgradLaunch L;
+  const int F = a.F, nt = a.n_tiles;
+  const uint32_t hbytes = (uint32_t)(128 * F * 2);
+  struct Base { const uint8_t *ai; uint32_t as, ao; const uint8_t *bi; uint32_t bs, bb; int N; float *out; int ldm, ldn; int weight; };
+  Base base[16];
+  int nb = 0;
+  for (int mb = 0; mb < 6; ++mb)
+    base[nb++] = {a.dqkv_img, (uint32_t)(3 * T256_TILE_IMG), (uint32_t)mb * 32768u, a.x_img, (uint32_t)T256_TILE_IMG, 65536u, 256,
+                  a.gwqkv + (size_t)mb * 128 * 256, 256, 1, 4};
+  for (int mb = 0; mb < 2; ++mb)
+    base[nb++] = {a.da1_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.ctx_img, (uint32_t)T256_TILE_IMG, 65536u, 256,
+                  a.gwo + (size_t)mb * 128 * 256, 256, 1, 4};
+  const int nfb = (F + 255) / 256;                   // N blocks of at most 256 hidden units
+  for (int fb = 0; fb < nfb; ++fb) {
+    const int Nf = F - fb * 256 < 256 ? F - fb * 256 : 256;
+    const int wgt = Nf > 128 ? 4 : (Nf > 64 ? 2 : 1);
+    for (int mb = 0; mb < 2; ++mb) {
+      // dW1[f][j] = sum_t dH[t][f] x1[t][j]  computed transposed: acc[m = j][n = f]
+      base[nb++] = {a.x1_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.dh_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
+                    a.gw1 + (size_t)fb * 256 * 256 + (size_t)mb * 128, 1, 256, wgt};
+      // dW2[j][f] = sum_t da2[t][j] H[t][f]
+      base[nb++] = {a.da2_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.h_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
+                    a.gw2 + (size_t)mb * 128 * F + (size_t)fb * 256, F, 1, wgt};
+    }
+  }
+  int wsum = 0;
+  for (int i = 0; i < nb; ++i) wsum += base[i].weight;
+  const int sms = t256_num_sms();
+  int nj = 0;
+  for (int i = 0; i < nb; ++i) {
+    int splits = (int)((int64_t)sms * base[i].weight / wsum);
+    if (splits < 1) splits = 1;
+    if (splits > nt) splits = nt;
+    for (int s = 0; s < splits && nj < T256_WG_MAXJOBS; ++s) {
+      T256WJob &j = L.jobs[nj++];
+      j.a_img = base[i].ai; j.a_tile_stride = base[i].as; j.a_off = base[i].ao;
+      j.b_img = base[i].bi; j.b_tile_stride = base[i].bs; j.b_bytes = base[i].bb; j.N = base[i].N;
+      j.out = base[i].out; j.ld_m = base[i].ldm; j.ld_n = base[i].ldn;
+      j.tile0 = (int)((int64_t)nt * s / splits); j.tile1 = (int)((int64_t)nt * (s + 1) / splits);
+    }
+  }
+  GT_CUDA(cudaMemcpyAsync(job_buf, L.jobs, sizeof(T256WJob) * nj, cudaMemcpyHostToDevice, st));
+  GT_CUDA(cudaFuncSetAttribute(t256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 98304));
+  { LaunchScope _ls(KC_TC_WGRAD, st);
+    t256_wgrad_kernel<<<nj, 192, 2 * 98304, st>>>(reinterpret_cast<const T256WJob *>(job_buf)); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gt

@@ -17,7 +17,7 @@ struct T256Plan {
   uint8_t *u1img[TC_MAX_LAYERS], *u2img[TC_MAX_LAYERS];
   uint8_t *x1img[TC_MAX_LAYERS], *ctximg[TC_MAX_LAYERS], *himg[TC_MAX_LAYERS];
   float *d_hvo, *loss_partials, *dlog, *dxrm, *dxrm2, *g0, *dxa, *dxb;
-  uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch;
+  uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch, *wg_jobs;
   int64_t bytes;
   int n_tiles;
 };
@@ -66,6 +66,7 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
     P.dhimg = reinterpret_cast<uint8_t *>(take(th));
     P.dqkvimg = reinterpret_cast<uint8_t *>(take(3 * ti));
     P.dctx_scratch = reinterpret_cast<uint8_t *>(take((int64_t)160 * T256_TILE_IMG));
+    P.wg_jobs = reinterpret_cast<uint8_t *>(take(T256_WG_JOBBUF));
   } else {
     uint8_t *ia = reinterpret_cast<uint8_t *>(take(ti)), *ib = reinterpret_cast<uint8_t *>(take(ti));
     for (int l = 0; l <= c.n_enc; ++l) P.ximg[l] = (l & 1) ? ib : ia;
@@ -195,7 +196,7 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
     w.x1_img = pl.x1img[l]; w.da2_img = pl.da2img; w.h_img = pl.himg[l];
     w.gwqkv = x.G + p.sa.w_in; w.gwo = x.G + p.sa.w_out; w.gw1 = x.G + p.w1; w.gw2 = x.G + p.w2;
     w.n_tiles = pl.n_tiles; w.F = x.c.dim_ff;
-    GT_TRY(t256_wgrad(w, x.st));
+    GT_TRY(t256_wgrad(w, pl.wg_jobs, x.st));
     float *t = cur; cur = oth; oth = t;
   }
   GT_TRY(t256_from_tiled(cur, pl.dxrm, x.M, x.st));
