@@ -108,6 +108,19 @@ int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale,
 int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Data-parallel overlap (BASELINE.json north_star: "bucketed NCCL gradient allreduce ... overlapped with backward").
+ * The reference has no distributed code; the flat gradient of gt_backward / gt_train_step is partitioned into
+ * contiguous buckets listed in the order backward FINISHES them (output head first, one bucket per decoder / encoder
+ * layer in reverse layer order, encoder input layer last) — a descending partition of the flat vector, so consecutive
+ * buckets can be merged into one range.  gt_grad_buckets returns their number and (offset,size) in floats.
+ * After gt_grad_events_enable(n >= bucket count), every gt_backward / gt_train_step records one library-owned CUDA
+ * event per bucket on its stream as soon as the bucket is final; gt_grad_bucket_wait(b, s) makes stream `s` (the
+ * caller's communication stream) wait for bucket b of the most recent call, so the caller can launch that bucket's
+ * all-reduce while the layers below are still in backward.  gt_grad_events_enable(0) frees the events. */
+int gt_grad_buckets(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int max_entries);
+int gt_grad_events_enable(int max_buckets);
+int gt_grad_bucket_wait(int bucket, void *stream);
+
 /* Launch accounting for bench.py.  gt_launch_count(-1) = kernels launched by this library so far
  * (all classes); gt_profile_enable(class, max_records) brackets every launch of one kernel class with
  * CUDA events on its stream (0 disables); gt_profile_collect sums their elapsed times and resets.

@@ -32,7 +32,7 @@ def _flatten(d):
     return torch.cat([d[k].reshape(-1) for k in _names()])
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bucketed=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
@@ -48,18 +48,32 @@ def _worker(rank, world, port, out):
         opt.grad = _flatten(grads)
         return torch.tensor(loss6, dtype=torch.float32), opt.grad
 
-    dp = DataParallelStep(None, opt, PEN, compute=compute)
+    if bucketed:
+        # descending partition of the flat gradient in "completion order", like gt_grad_buckets; the wait hook
+        # records the order in which groups were released
+        n = flat.numel()
+        cuts = [n, n - 40, n // 2, 7, 0]
+        ranges = [(cuts[i + 1], cuts[i] - cuts[i + 1]) for i in range(len(cuts) - 1)]
+        waited = []
+        dp = DataParallelStep(None, opt, PEN, compute=compute, bucket_ranges=ranges, bucket_bytes=4 * 64,
+                              wait_bucket=waited.append)
+        assert dp.groups is not None and sum(g[1] for g in dp.groups) == n
+    else:
+        dp = DataParallelStep(None, opt, PEN, compute=compute)
     metrics = dp.step(x[lo:hi], y[lo:hi], reduce_metrics=True)
+    if bucketed:
+        assert waited == [g[2] for g in dp.groups] and waited[-1] == len(ranges) - 1
     if rank == 0:
         torch.save({"flat": flat, "metrics": metrics, "scale": opt.grad_scale}, out)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_dp_step_equals_single_process(tmp_path):
+@pytest.mark.parametrize("bucketed", [False, True])
+def test_dp_step_equals_single_process(tmp_path, bucketed):
     out = str(tmp_path / "r0.pt")
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if bucketed else 0)
+    mp.spawn(_worker, args=(2, port, out, bucketed), nprocs=2, join=True)
     got = torch.load(out)
     P = G.det_params(CFG)
     x, y = G.det_batch(CFG, N)
@@ -75,3 +89,13 @@ def test_shard_bounds():
     assert [shard_bounds(8, r, 4) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
     with pytest.raises(ValueError):
         shard_bounds(10, 0, 4)
+
+
+def test_merge_buckets():
+    from transformergrooveinfilling_b200.dp import merge_buckets
+    r = [(90, 10), (60, 30), (30, 30), (5, 25), (0, 5)]
+    assert merge_buckets(r, 1) == [(90, 10, 0), (60, 30, 1), (30, 30, 2), (5, 25, 3), (0, 5, 4)]
+    assert merge_buckets(r, 40) == [(60, 40, 1), (0, 60, 4)]
+    assert merge_buckets(r, 1000) == [(0, 100, 4)]
+    with pytest.raises(ValueError):
+        merge_buckets([(90, 10), (50, 30)], 1)

@@ -127,3 +127,30 @@ def test_checkpoint_resume_roundtrip(tmp_path):
     params["load_model"]["dir"] = str(tmp_path / "nothing")
     with pytest.raises(FileNotFoundError):
         initialize_model(params)
+
+
+def test_grad_buckets_partition_the_flat_vector_in_backward_order():
+    """gt_grad_buckets: contiguous ranges in completion order (head first, encoder input layer last) that tile the
+    flat gradient exactly; layer buckets start at that layer's first tensor."""
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    for cfg in (G.GrooveCfg(32, 16, 512, 6, 0, 16, 27), G.GrooveCfg(24, 3, 40, 2, 3, 27, 27)):
+        c = _lib.GtConfig(cfg.d_model, cfg.nhead, cfg.dim_ff, cfg.n_enc, cfg.n_dec, cfg.e_src, cfg.e_tgt, 0, 0.0, 0)
+        total = lib.gt_param_count(C.byref(c))
+        offs, sizes = (C.c_int64 * 160)(), (C.c_int64 * 160)()
+        n = lib.gt_grad_buckets(C.byref(c), offs, sizes, 160)
+        assert n == (cfg.n_enc + cfg.n_dec + 3 if cfg.n_dec else cfg.n_enc + 2)
+        end = total
+        for i in range(n):
+            assert offs[i] + sizes[i] == end and sizes[i] > 0
+            end = offs[i]
+        assert end == 0
+        names = [k for k, _ in G.param_shapes(cfg)]
+        po, ps = (C.c_int64 * len(names))(), (C.c_int64 * len(names))()
+        lib.gt_param_layout(C.byref(c), po, ps, len(names))
+        start = {names[i]: int(po[i]) for i in range(len(names))}
+        first_enc_bucket = cfg.n_dec + 2 if cfg.n_dec else 1
+        assert offs[first_enc_bucket] == start[f"Encoder.Encoder.layers.{cfg.n_enc - 1}.self_attn.in_proj_weight"]
+        assert offs[n - 1] == 0 and offs[n - 2] == start["Encoder.Encoder.layers.0.self_attn.in_proj_weight"]
+        assert lib.gt_grad_buckets(C.byref(c), offs, sizes, 1) < 0
+    assert lib.gt_grad_bucket_wait(0, None) != 0 and b"not enabled" in lib.gt_last_error()

@@ -43,6 +43,9 @@ SIGNATURES = {
     "gt_predict": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, _p]),
     "gt_sgd_step": (C.c_int, [_p, _p, _i64, _f, _f, _p]),
     "gt_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
+    "gt_grad_buckets": (C.c_int, [_cfgp, C.POINTER(_i64), C.POINTER(_i64), C.c_int]),
+    "gt_grad_events_enable": (C.c_int, [C.c_int]),
+    "gt_grad_bucket_wait": (C.c_int, [C.c_int, _p]),
     "gt_launch_count": (_i64, [C.c_int]),
     "gt_profile_enable": (C.c_int, [C.c_int, C.c_int]),
     "gt_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),

@@ -106,6 +106,16 @@ struct Layout {
 int build_layout(const gt_config &c, Layout &L);
 int validate_config(const gt_config *cfg);
 
+// ---- gradient buckets (data-parallel overlap) -------------------------------------------------
+// The flat gradient is partitioned into contiguous ranges listed in the order in which backward FINISHES them
+// (head first, input layer last).  Backward drivers call grad_bucket_ready(idx) right after enqueueing the last
+// kernel that writes into bucket idx; when events are enabled (gt_grad_events_enable) that records a CUDA event a
+// communication stream can wait on, so the all-reduce of a bucket overlaps the backward of the layers below it.
+enum BucketKind { BK_HEAD = 0, BK_DEC_LAYER = 1, BK_MID = 2, BK_ENC_LAYER = 3, BK_IN_ENC = 4 };
+int grad_bucket_index(const gt_config &c, int kind, int layer);
+int grad_bucket_count(const gt_config &c);
+void grad_bucket_ready(const gt_config &c, int kind, int layer, cudaStream_t st);
+
 // ---- fp32 SIMT kernels (kernels_simt.cu) ----------------------------------------------------
 struct GemmEpi {
   const float *bias = nullptr;       // + bias[n]

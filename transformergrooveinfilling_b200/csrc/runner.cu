@@ -32,6 +32,46 @@ LaunchScope::~LaunchScope() {
   if (slot >= 0) cudaEventRecord(g_prof_events[slot].second, st);
 }
 
+// ---- gradient buckets ---------------------------------------------------------------------------
+static std::vector<cudaEvent_t> g_bucket_events;
+static bool g_bucket_events_on = false;
+
+int grad_bucket_count(const gt_config &c) { return c.n_dec > 0 ? c.n_enc + c.n_dec + 3 : c.n_enc + 2; }
+
+int grad_bucket_index(const gt_config &c, int kind, int layer) {
+  const int after_dec = c.n_dec > 0 ? c.n_dec + 2 : 1;     // index of the last encoder layer's bucket
+  switch (kind) {
+    case BK_HEAD: return 0;
+    case BK_DEC_LAYER: return 1 + (c.n_dec - 1 - layer);
+    case BK_MID: return c.n_dec + 1;
+    case BK_ENC_LAYER: return after_dec + (c.n_enc - 1 - layer);
+    default: return after_dec + c.n_enc;
+  }
+}
+
+void grad_bucket_ready(const gt_config &c, int kind, int layer, cudaStream_t st) {
+  if (!g_bucket_events_on) return;
+  const int i = grad_bucket_index(c, kind, layer);
+  if (i >= 0 && i < (int)g_bucket_events.size()) cudaEventRecord(g_bucket_events[i], st);
+}
+
+// [offset, offset+size) of every bucket in completion order: a descending partition of the flat vector
+static int bucket_ranges(const gt_config &c, const Layout &L, int64_t *offs, int64_t *sizes) {
+  std::vector<int64_t> starts;
+  if (c.n_dec > 0) {
+    starts.push_back(L.dec_norm_g);
+    for (int l = c.n_dec - 1; l >= 0; --l) starts.push_back(L.dec[l].sa.w_in);
+    starts.push_back(L.enc_norm_g);
+  } else {
+    starts.push_back(L.enc_norm_g);
+  }
+  for (int l = c.n_enc - 1; l >= 0; --l) starts.push_back(L.enc[l].sa.w_in);
+  starts.push_back(L.in_enc_w);
+  int64_t end = L.total;
+  for (size_t i = 0; i < starts.size(); ++i) { offs[i] = starts[i]; sizes[i] = end - starts[i]; end = starts[i]; }
+  return (int)starts.size();
+}
+
 int validate_config(const gt_config *c) {
   GT_CHECK(c != nullptr, "null config");
   GT_CHECK(c->d_model >= 1 && c->d_model <= 512, "d_model must be in [1,512]");
@@ -401,11 +441,13 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
     const float *last = pl.dec[x.c.n_dec - 1].x3;
     GT_TRY(ln_bwd(cur, last, pl.mf_d, pl.rf_d, x.P + x.L.dec_norm_g, oth, nullptr, x.G + x.L.dec_norm_g,
                   x.G + x.L.dec_norm_b, x.M, d, none, 0, x.st));
+    grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
     std::swap(cur, oth);
     for (int l = x.c.n_dec - 1; l >= 0; --l) {
       const float *yin = l == 0 ? pl.y0d : pl.dec[l - 1].x3;
       // reads `cur`; `oth` and pl.g0 are temporaries; the result lands in `oth`
       GT_TRY(dec_layer_bwd(x, pl, l, yin, cur, oth, pl.g0));
+      grad_bucket_ready(x.c, BK_DEC_LAYER, l, x.st);
       std::swap(cur, oth);
     }
     GT_TRY(input_layer_bwd(x, pl, cur, pl.r0d, tgt_in, E, x.L.in_dec_w, x.L.in_dec_b, SITE_IN_DEC));
@@ -416,13 +458,17 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
   const float *last = pl.enc[x.c.n_enc - 1].x2;
   GT_TRY(ln_bwd(cur, last, pl.mf_e, pl.rf_e, x.P + x.L.enc_norm_g, oth, nullptr, x.G + x.L.enc_norm_g,
                 x.G + x.L.enc_norm_b, x.M, d, none, 0, x.st));
+  grad_bucket_ready(x.c, x.c.n_dec > 0 ? BK_MID : BK_HEAD, 0, x.st);
   std::swap(cur, oth);
   for (int l = x.c.n_enc - 1; l >= 0; --l) {
     const float *xin = l == 0 ? pl.x0e : pl.enc[l - 1].x2;
     GT_TRY(enc_layer_bwd(x, pl, l, xin, cur, pl.g0, oth));
+    grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     std::swap(cur, oth);
   }
-  return input_layer_bwd(x, pl, cur, pl.r0e, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, SITE_IN_ENC);
+  GT_TRY(input_layer_bwd(x, pl, cur, pl.r0e, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, SITE_IN_ENC));
+  grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
+  return 0;
 }
 
 static int make_ctx(Ctx &x, const gt_config *cfg, const float *params, float *grads, const float *pe, int64_t n_seq,
@@ -578,6 +624,31 @@ int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p, i
                           void *stream) {
   GT_CHECK(keep && n >= 0, "gt_debug_dropout_mask: bad arguments");
   return debug_dropout_mask(site_key(seed, step, site), drop_threshold(p), idx0, n, keep, (cudaStream_t)stream);
+}
+
+int gt_grad_buckets(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int max_entries) {
+  if (validate_config(cfg)) return -1;
+  static thread_local Layout L;
+  build_layout(*cfg, L);
+  if (!offsets || !sizes || max_entries < grad_bucket_count(*cfg)) { set_error("gt_grad_buckets: max_entries too small"); return -1; }
+  return bucket_ranges(*cfg, L, offsets, sizes);
+}
+
+int gt_grad_events_enable(int max_buckets) {
+  for (auto &e : g_bucket_events) cudaEventDestroy(e);
+  g_bucket_events.clear();
+  g_bucket_events_on = false;
+  if (max_buckets <= 0) return 0;
+  g_bucket_events.resize((size_t)max_buckets);
+  for (auto &e : g_bucket_events) GT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g_bucket_events_on = true;
+  return 0;
+}
+
+int gt_grad_bucket_wait(int bucket, void *stream) {
+  GT_CHECK(g_bucket_events_on && bucket >= 0 && bucket < (int)g_bucket_events.size(), "gt_grad_bucket_wait: bucket events are not enabled / bad index");
+  GT_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g_bucket_events[bucket], 0));
+  return 0;
 }
 
 int64_t gt_launch_count(int kernel_class) {

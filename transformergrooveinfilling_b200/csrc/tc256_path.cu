@@ -181,6 +181,7 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
   GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxrm, d, x.M, d, E, e0, 0, x.st));
   GT_TRY(ln_bwd(pl.dxrm, pl.xLrm, pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxrm2, nullptr, x.G + x.L->enc_norm_g,
                 x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+  grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
   GT_TRY(t256_to_tiled(pl.dxrm2, pl.dxa, x.M, pl.n_tiles, x.st));
   float *cur = pl.dxa, *oth = pl.dxb;
   for (int l = L - 1; l >= 0; --l) {
@@ -197,11 +198,14 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
     w.gwqkv = x.G + p.sa.w_in; w.gwo = x.G + p.sa.w_out; w.gw1 = x.G + p.w1; w.gw2 = x.G + p.w2;
     w.n_tiles = pl.n_tiles; w.F = x.c.dim_ff;
     GT_TRY(t256_wgrad(w, pl.wg_jobs, x.st));
+    grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     float *t = cur; cur = oth; oth = t;
   }
   GT_TRY(t256_from_tiled(cur, pl.dxrm, x.M, x.st));
   GT_TRY(pe_dropout_bwd(pl.dxrm, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
-  return t256_wgrad_f32(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b);
+  GT_TRY(t256_wgrad_f32(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
+  return 0;
 }
 
 static void t256_ctx(T256Ctx &x, const gt_config &c, const Layout &L, const float *params, float *grads, const float *pe,

@@ -269,15 +269,19 @@ static int tc_backward_all(const TcCtx &x, const TcPlan &pl, const float *src, c
   GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxa, d, x.M, d, E, e0, 0, x.st));
   GT_TRY(ln_bwd(pl.dxa, pl.x[x.c.n_enc], pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxb, nullptr, x.G + x.L->enc_norm_g,
                 x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+  grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
   float *cur = pl.dxb, *oth = pl.dxa;
   for (int l = x.c.n_enc - 1; l >= 0; --l) {
     TcLayerArgs a = tc_layer_args(x, pl, l);
     a.x_in = pl.x[l]; a.u1_in = pl.u1[l]; a.u2_in = pl.u2[l]; a.dy = cur; a.dx = oth;
     GT_TRY(tc_layer_bwd(d, a, x.st));
+    grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     float *t = cur; cur = oth; oth = t;
   }
   GT_TRY(pe_dropout_bwd(cur, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
-  return tc_wgrad(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b);
+  GT_TRY(tc_wgrad(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
+  return 0;
 }
 
 static void tc_ctx(TcCtx &x, const gt_config &c, const Layout &L, const float *params, float *grads, const float *pe,

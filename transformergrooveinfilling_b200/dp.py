@@ -10,7 +10,7 @@ keyed by the GLOBAL sequence index (seq0 = rank * n_local), so a DP run draws th
 single-GPU run of the concatenated batch."""
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -35,20 +35,94 @@ def combine_metrics(metrics: torch.Tensor, group=None) -> torch.Tensor:
     return m
 
 
+def merge_buckets(ranges: Sequence[Tuple[int, int]], min_floats: int) -> List[Tuple[int, int, int]]:
+    """``ranges`` = (offset, size) of the library's gradient buckets in completion order — a descending
+    partition of the flat vector (gt_grad_buckets).  Consecutive buckets are merged until a group
+    holds at least ``min_floats`` floats (an all-reduce below ~0.5 MB is pure launch latency); a
+    short tail joins the previous group.  Returns (offset, size, index of the LAST bucket of the
+    group) — the group may be reduced once that bucket's event has fired."""
+    end = None
+    for o, sz in ranges:
+        if end is not None and o + sz != end:
+            raise ValueError("gradient buckets must form a descending contiguous partition")
+        end = o
+    groups: List[List[int]] = []
+    cur = None
+    for i, (o, sz) in enumerate(ranges):
+        cur = [o, sz, i] if cur is None else [o, cur[1] + sz, i]
+        if cur[1] >= min_floats:
+            groups.append(cur)
+            cur = None
+    if cur is not None:                       # short tail: join the previous group
+        if groups:
+            groups[-1] = [cur[0], groups[-1][1] + cur[1], cur[2]]
+        else:
+            groups.append(cur)
+    return [tuple(g) for g in groups]
+
+
 class DataParallelStep:
-    """step(x_local, y_local) = local fused fwd+loss+bwd -> all-reduce(SUM) flat grad -> optimizer
-    step with grad_scale = 1/world.  ``compute`` defaults to ``model.train_step``; tests inject a CPU
-    stand-in to exercise the collective logic over gloo."""
+    """step(x_local, y_local) = local fused fwd+loss+bwd -> all-reduce(SUM) of the flat gradient ->
+    optimizer step with grad_scale = 1/world.
+
+    With ``overlap=True`` (default on CUDA, world > 1) the gradient is reduced in BUCKETS while
+    backward is still running: the library records one CUDA event per bucket as backward finishes
+    it (include/groove_b200.h: gt_grad_buckets / gt_grad_bucket_wait), and each group's NCCL
+    all-reduce is issued on a communication stream that waits only for that event.  ``compute`` /
+    ``bucket_ranges`` / ``wait_bucket`` are injection points for the CPU (gloo) tests."""
 
     def __init__(self, model, optimizer, hit_loss_penalty: float, group=None,
-                 compute: Optional[Callable] = None, comm_stream: Optional["torch.cuda.Stream"] = None):
+                 compute: Optional[Callable] = None, comm_stream: Optional["torch.cuda.Stream"] = None,
+                 overlap: Optional[bool] = None, bucket_bytes: int = 512 * 1024,
+                 bucket_ranges: Optional[Sequence[Tuple[int, int]]] = None,
+                 wait_bucket: Optional[Callable[[int], None]] = None):
         self.model, self.opt, self.penalty, self.group = model, optimizer, hit_loss_penalty, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.compute = compute
         self.comm_stream = comm_stream
+        self.wait_bucket = wait_bucket
+        self.groups: Optional[List[Tuple[int, int, int]]] = None
         if hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = 1.0 / self.world
+        if overlap is None:
+            overlap = self.world > 1 and (compute is None or bucket_ranges is not None)
+        if overlap and self.world > 1:
+            if bucket_ranges is None:
+                bucket_ranges = self._library_buckets()
+            self.groups = merge_buckets(bucket_ranges, max(1, bucket_bytes // 4))
+
+    def _library_buckets(self):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        cfg = self.model._cfg()
+        cap = 160
+        offs, sizes = (C.c_int64 * cap)(), (C.c_int64 * cap)()
+        n = lib.gt_grad_buckets(C.byref(cfg), offs, sizes, cap)
+        if n < 0:
+            raise RuntimeError(lib.gt_last_error().decode())
+        _lib.check(lib.gt_grad_events_enable(n), "gt_grad_events_enable")
+        dev = self.model.flat_parameters().device
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(dev)
+        stream = self.comm_stream
+        self.wait_bucket = lambda b: _lib.check(lib.gt_grad_bucket_wait(b, stream.cuda_stream), "gt_grad_bucket_wait")
+        return [(int(offs[i]), int(sizes[i])) for i in range(n)]
+
+    def _reduce_overlapped(self, grad):
+        works = []
+        for off, size, last in self.groups:
+            if self.comm_stream is not None:
+                with torch.cuda.stream(self.comm_stream):
+                    self.wait_bucket(last)            # comm stream waits for this bucket's backward only
+                    works.append(dist.all_reduce(grad[off:off + size], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                if self.wait_bucket is not None:
+                    self.wait_bucket(last)
+                works.append(dist.all_reduce(grad[off:off + size], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()                                  # the compute stream waits for every bucket before the optimizer
 
     def step(self, x_local, y_local, reduce_metrics: bool = False):
         n_local = x_local.shape[0]
@@ -60,7 +134,10 @@ class DataParallelStep:
             metrics, _ = self.model.train_step(x_local, y_local, self.penalty)
             grad = self.model.flat_grad()
         if self.world > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
+            if self.groups is not None:
+                self._reduce_overlapped(grad)
+            else:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
             if not hasattr(self.opt, "grad_scale"):
                 grad /= self.world
         self.opt.step()
