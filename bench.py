@@ -18,6 +18,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the ONE JSON line (NCCL prints its version banner there)
 
 import torch  # noqa: E402
 
@@ -150,6 +152,66 @@ def workload_config(w, args, per_gpu_batch, world, precision):
             "l2_policy": "per-step working set (inputs + saved activations) is far larger than the 126 MB L2; no flush needed"}
 
 
+def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, precision):
+    """predict() throughput (BGT/models/transformer.py:117-125 / :48-83): sequences/s through model.predict."""
+    import ctypes as C
+    out_h = torch.empty(n, 32, 27, dtype=torch.float32).pin_memory()
+    model.eval()
+
+    def step_resident():
+        with torch.no_grad():
+            model._predict_hvo(x, 0.5)
+
+    def step_e2e():
+        x.copy_(xh, non_blocking=True)
+        h, v, o = model.predict(x)
+        out_h.copy_(torch.cat((h.float(), v, o), 2), non_blocking=False)
+
+    for _ in range(args.warmup):
+        step_resident()
+    lib.gt_profile_enable(17 if precision == "bf16" else 1, 4096)
+    l0 = lib.gt_launch_count(-1)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.finish()
+    launches = lib.gt_launch_count(-1) - l0
+    tot_ms, cnt = C.c_double(0), C.c_int64(0)
+    lib.gt_profile_collect(C.byref(tot_ms), C.byref(cnt))
+    lib.gt_profile_enable(0, 0)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fl_step = train_flops_per_seq(w) / 3 * n
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roof = None
+    if cnt.value and precision == "bf16":
+        layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
+        avg_ms = tot_ms.value / cnt.value
+        ach = 2 * layer_mac * n / (avg_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc_layer_fwd (eval)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": cnt.value, "kernel_share_of_step": tot_ms.value / ms}
+    cfg = workload_config(w, args, n, world, precision)
+    cfg["workload"] = f"{w['yaml']} predict() (eval forward + hit threshold" + (", autoregressive decoder)" if w["Ld"] else ")")
+    line = {"metric": "infer_seq_per_s", "value": n * world * args.steps / (ms / 1e3), "unit": "seq/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic", "config": cfg,
+            "step_tflops": fl_step * world * args.steps / (ms / 1e3) / 1e12, "roofline": roof,
+            "e2e": {"value": n * world * args.steps / (ms_e2e / 1e3), "unit": "seq/s", "h2d_bytes_per_step": xh.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,7 +222,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: workload table)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train step (headline) or predict()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-bucket-mb", type=float, default=4.0, help="gradient bucket size of the overlapped all-reduce (N > 1)")
+    ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of per-bucket overlap")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -210,7 +275,8 @@ def main():
     if world > 1:                                   # identical replicas
         dist.broadcast(model.flat_parameters().detach(), 0)
     opt = FusedAdam(model, 1e-3) if args.optimizer == "adam" else FusedSGD(model, w["lr"])
-    dp = DataParallelStep(model, opt, w["pen"])
+    dp = DataParallelStep(model, opt, w["pen"], overlap=False if args.no_overlap else None,
+                          bucket_bytes=int(args.dp_bucket_mb * (1 << 20)))
 
     xh, yh = synth_batch(w, n, 1234 + rank)
     xh, yh = xh.pin_memory(), yh.pin_memory()
@@ -233,6 +299,9 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
+
+    if args.mode == "infer":
+        return run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, precision)
 
     def step_resident():
         dp.step(x, y)
@@ -278,10 +347,15 @@ def main():
     if cnt.value > 0:
         # the dominant kernel class and the share of the step's algorithmic FLOPs its launches carry
         if precision == "bf16":
-            L_all = w["L"] + w["Ld"]
             layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
-            fl_launch = 2 * 2 * layer_mac * n           # one encoder layer backward = 2x its forward FLOPs
-            kname = "tc_layer_bwd"
+            if w["d"] == 256:
+                # d_model = 256: the layer-backward kernel computes the data gradients (1x the layer's forward FLOPs);
+                # the weight gradients run in t256_wgrad_kernel (class 20, listed under "kernels")
+                fl_launch = 2 * layer_mac * n
+                kname = "t256_layer_bwd (data gradients + attention backward; recomputed q|k|v and probabilities not counted)"
+            else:
+                fl_launch = 2 * 2 * layer_mac * n       # one encoder layer backward = 2x its forward FLOPs
+                kname = "tc_layer_bwd (data + weight gradients)"
         else:
             fl_launch = fl_step * args.steps / max(cnt.value, 1)   # every contraction except attention runs in gemm_f32
             kname = "gemm_f32 (fp32 FMA; tensor peak shown for reference only)"
@@ -292,6 +366,31 @@ def main():
                 "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
                 "kernel_share_of_step": tot_ms.value / ms}
+    # ---- per-kernel-class breakdown: 3 extra steps with every class bracketed by events (outside the timed regions) ----
+    kernels = {}
+    names = {1: "gemm_f32", 2: "attention_fwd_f32", 3: "attention_bwd_f32", 4: "layernorm", 5: "elementwise", 6: "loss", 7: "optimizer",
+             16: "tc_weight_prep", 17: "tc_layer_fwd", 18: "tc_layer_bwd", 20: "tc_wgrad"}
+    lib.gt_profile_enable(-1, 8192)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    ms3 = e0.elapsed_time(e1)
+    layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
+    lin_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"])
+    fl_cls = {17: 2 * layer_mac * n, 18: (2 if w["d"] == 256 else 4) * layer_mac * n, 20: 2 * lin_mac * n}
+    for cls, nm in names.items():
+        t, c = C.c_double(0), C.c_int64(0)
+        lib.gt_profile_collect_class(cls, C.byref(t), C.byref(c))
+        if c.value:
+            kernels[nm] = {"launches_per_step": c.value / 3, "ms_per_step": t.value / 3, "share": t.value / ms3}
+            if precision == "bf16" and cls in fl_cls:
+                kernels[nm]["tflops"] = fl_cls[cls] / (t.value / c.value / 1e3) / 1e12
+    lib.gt_profile_collect(C.byref(tot_ms), C.byref(cnt))
+    lib.gt_profile_enable(0, 0)
     line = {
         "metric": "train_seq_per_s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -301,7 +400,7 @@ def main():
         "roofline": roof,
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4, "d2h_bytes_per_step": 24,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss,
+        "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss, "kernels": kernels,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = 512

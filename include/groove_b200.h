@@ -56,8 +56,9 @@ const char *gt_last_error(void);
 int64_t gt_param_count(const gt_config *cfg);
 int     gt_param_layout(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int max_entries);
 
-/* Scratch the caller must provide.  mode 0 = inference (ping-pong buffers only),
- * 1 = training (activations saved for backward). */
+/* Scratch the caller must provide.  mode 0 = inference forward (ping-pong buffers only),
+ * 1 = training (activations saved for backward), 2 = gt_predict (for encoder-decoder models: per-layer key/value
+ * caches of the incremental decode; same as 0 for encoder-only models). */
 int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode);
 
 /* Forward pass: BGT/models/transformer.py:108-115 (encoder-only: InputLayer -> Encoder -> OutputLayer)
@@ -100,6 +101,13 @@ int gt_train_step(const gt_config *cfg, const float *params, const float *pe,
 int gt_predict(const gt_config *cfg, const float *params, const float *pe,
                const float *src, int64_t n_seq, float thres,
                float *hvo_out, void *ws, int64_t ws_bytes, void *stream);
+/* Encoder-decoder gt_predict runs an incremental decode: the target mask is causal (BGT/models/utils.py:53-56), so
+ * caching each decoder layer's self-attention keys/values (and the cross-attention keys/values of the encoder
+ * memory) reproduces the reference's 32 full decoder passes with 1/32 of the decoder work.  variant 0 = that decode
+ * (workspace mode 2); variant 1 = the reference's literal 32-pass loop (workspace mode 0), kept as its cross-check. */
+int gt_predict_variant(const gt_config *cfg, const float *params, const float *pe,
+                       const float *src, int64_t n_seq, float thres,
+                       float *hvo_out, void *ws, int64_t ws_bytes, int variant, void *stream);
 
 /* torch.optim.SGD(lr).step() / torch.optim.Adam(lr).step() as called at BGT/models/train.py:141,
  * over the flat vectors.  g is multiplied by grad_scale first (1/world after an all-reduce SUM).
@@ -129,6 +137,9 @@ int gt_grad_bucket_wait(int bucket, void *stream);
 int64_t gt_launch_count(int kernel_class);
 int     gt_profile_enable(int kernel_class, int max_records);
 int     gt_profile_collect(double *total_ms, int64_t *launches);
+/* gt_profile_enable(-1, n) brackets EVERY class; gt_profile_collect_class reads one class's total without resetting
+ * (call it before gt_profile_collect, which resets). */
+int     gt_profile_collect_class(int kernel_class, double *total_ms, int64_t *launches);
 
 /* Test hook: fills keep[i] = 1/0 for element indices idx0..idx0+n-1 of dropout site `site`
  * (the generator restated in oracle/groove_oracle.py:dropout_keep). */

@@ -158,6 +158,24 @@ def test_predict_matches_reference(name):
         model.predict(x.cuda(), use_pd=True)
 
 
+@pytest.mark.parametrize("name", ["c5_symbolic_encdec", "odd_small_encdec"])
+@pytest.mark.parametrize("n", [1, 37])
+def test_kv_cached_decode_equals_literal_32_pass_loop(name, n):
+    """gt_predict (incremental decode with per-layer key/value caches) against the reference's literal loop of 32 full
+    decoder passes (BGT/models/transformer.py:62-72) run by the same library: same hits, v/o to fp32 reorder."""
+    cfg, _, _, _ = CASES[name]
+    model, _ = build_model(cfg, dropout=0.1)
+    model.eval()
+    x, _ = G.det_batch(cfg, n)
+    with torch.no_grad():
+        fast = model._predict_hvo(x.cuda(), 0.5).cpu().numpy()
+        slow = model._predict_hvo(x.cuda(), 0.5, literal=True).cpu().numpy()
+    assert (fast[..., :9] == slow[..., :9]).mean() >= 0.999
+    agree = (fast[..., :9] == slow[..., :9]).all(axis=(1, 2))       # a flipped hit legitimately changes later steps
+    np.testing.assert_allclose(fast[agree][..., 9:], slow[agree][..., 9:], rtol=1e-4, atol=3e-5)
+    assert agree.mean() >= 0.97
+
+
 @pytest.mark.parametrize("n", [1, 3, 33, 130])
 def test_ragged_batch_sizes_and_batch_independence(n):
     """Sequences are independent: the outputs for a batch equal the outputs of its rows run alone,

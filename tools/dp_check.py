@@ -20,8 +20,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for prec, tol in (("fp32", 2e-5), ("bf16", 2e-5)):
-        cfg = G.GrooveCfg(32, 16, 512, 3, 0, 16, 27)
+    cases = [("fp32", 2e-5, G.GrooveCfg(32, 16, 512, 3, 0, 16, 27), True), ("bf16", 2e-5, G.GrooveCfg(32, 16, 512, 3, 0, 16, 27), True),
+             ("bf16", 2e-5, G.GrooveCfg(32, 16, 512, 3, 0, 16, 27), False), ("bf16", 2e-5, G.GrooveCfg(256, 16, 64, 2, 0, 16, 27), True),
+             ("fp32", 2e-5, G.GrooveCfg(32, 4, 64, 2, 2, 27, 27), True)]
+    for prec, tol, cfg, overlap in cases:
         n = 16 * world
         x, y = [t.cuda() for t in G.det_batch(cfg, n)]
         ref, _ = build_model(cfg, device=f"cuda:{local}", dropout=0.24, precision=prec)
@@ -31,13 +33,15 @@ def main():
         ropt.step()
         mod, _ = build_model(cfg, device=f"cuda:{local}", dropout=0.24, precision=prec)
         mod.set_seed(5, 0, 0).train()
-        dp = DataParallelStep(mod, FusedSGD(mod, 0.07), 0.38)
+        dp = DataParallelStep(mod, FusedSGD(mod, 0.07), 0.38, overlap=overlap, bucket_bytes=64 * 1024)
+        assert (dp.groups is not None and len(dp.groups) >= 2) == overlap
         lo, hi = shard_bounds(n, rank, world)
         m = dp.step(x[lo:hi].contiguous(), y[lo:hi].contiguous(), reduce_metrics=True)
         dl = abs(float(m[0]) - float(m_ref[0])) / abs(float(m_ref[0]))
         dpar = float((mod.flat_parameters() - ref.flat_parameters()).abs().max() / ref.flat_parameters().abs().max())
         if rank == 0:
-            print(f"DP_CHECK {prec} world={world} loss_rel_diff={dl:.2e} param_rel_diff={dpar:.2e}")
+            print(f"DP_CHECK {prec} d={cfg.d_model} dec={cfg.n_dec} overlap={overlap} groups={len(dp.groups or [])} world={world} "
+                  f"loss_rel_diff={dl:.2e} param_rel_diff={dpar:.2e}")
         ok = ok and dl < tol * 10 and dpar < 1e-4
     dist.barrier()
     dist.destroy_process_group()

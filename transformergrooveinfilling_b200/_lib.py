@@ -41,6 +41,7 @@ SIGNATURES = {
     "gt_loss": (C.c_int, [_p, _p, _i64, _f, _p, _p, _f, _p, _p]),
     "gt_train_step": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
     "gt_predict": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, _p]),
+    "gt_predict_variant": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, C.c_int, _p]),
     "gt_sgd_step": (C.c_int, [_p, _p, _i64, _f, _f, _p]),
     "gt_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
     "gt_grad_buckets": (C.c_int, [_cfgp, C.POINTER(_i64), C.POINTER(_i64), C.c_int]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "gt_launch_count": (_i64, [C.c_int]),
     "gt_profile_enable": (C.c_int, [C.c_int, C.c_int]),
     "gt_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "gt_profile_collect_class": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gt_debug_dropout_mask": (C.c_int, [_u64, _u64, C.c_int32, _f, _i64, _i64, _p, _p]),
     "gt_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, _p]),
     "gt_debug_tc_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

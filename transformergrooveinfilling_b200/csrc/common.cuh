@@ -174,6 +174,10 @@ int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,
               int64_t step, float gs, cudaStream_t st);
 int debug_dropout_mask(uint32_t key, uint32_t thr, int64_t idx0, int64_t n, uint8_t *keep, cudaStream_t st);
+int attention_decode(const float *q, int64_t ldq, const float *k, const float *v, int64_t ld_key, int64_t ld_seq, int nkeys,
+                     float *o, int64_t ldo, int64_t n_seq, int H, int dh, cudaStream_t st);
+int add_pe_row(float *x, const float *pe_row, int64_t n_rows, int d, cudaStream_t st);
+int decode_feedback(const float *hvo_step, float *tok, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st);
 int predict_feedback(const float *hvo, float *tgt, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st);
 
 }  // namespace gt

@@ -630,6 +630,83 @@ int predict_feedback(const float *hvo, float *tgt, float *out, int64_t n_seq, in
   return 0;
 }
 
+// ---- KV-cached autoregressive decode (gt_predict, encoder-decoder) -----------------------------------------------
+// One warp per (sequence, head); lane = key position.  q: one row per sequence; K/V: `nkeys` cached rows per sequence.
+__global__ void attn_decode_kernel(const float *__restrict__ q, int64_t ldq, const float *__restrict__ k, const float *__restrict__ v,
+                                   int64_t ld_key, int64_t ld_seq, int nkeys, float *__restrict__ o, int64_t ldo, int64_t n_seq,
+                                   int H, int dh) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t pair = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
+  if (pair >= n_seq * H) return;
+  const int64_t seq = pair / H;
+  const int head = (int)(pair % H);
+  const float *qr = q + seq * ldq + head * dh;
+  const float *kr = k + seq * ld_seq + (int64_t)lane * ld_key + head * dh;
+  const float *vr = v + seq * ld_seq + (int64_t)lane * ld_key + head * dh;
+  const bool live = lane < nkeys;
+  float sc = 0.f;
+  if (live)
+    for (int c = 0; c < dh; ++c) sc = fmaf(qr[c], kr[c], sc);
+  sc = live ? sc * rsqrtf((float)dh) : -INFINITY;
+  float mx = sc;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float p = live ? expf(sc - mx) : 0.f;
+  float sum = p;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  p /= sum;
+  for (int c = 0; c < dh; ++c) {
+    float t = live ? p * vr[c] : 0.f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) o[seq * ldo + head * dh + c] = t;
+  }
+}
+int attention_decode(const float *q, int64_t ldq, const float *k, const float *v, int64_t ld_key, int64_t ld_seq, int nkeys,
+                     float *o, int64_t ldo, int64_t n_seq, int H, int dh, cudaStream_t st) {
+  GT_CHECK(nkeys >= 1 && nkeys <= T, "attention_decode: nkeys out of range");
+  const int64_t pairs = n_seq * H;
+  { LaunchScope _ls(KC_ATTN_FWD, st);
+  attn_decode_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, st>>>(q, ldq, k, v, ld_key, ld_seq, nkeys, o, ldo, n_seq, H, dh); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// x[n, d] += pe[pos, :]   (InputLayer: relu(linear) + positional row of decode position `pos`)
+__global__ void add_pe_row_kernel(float *x, const float *__restrict__ pe_row, int64_t n, int d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] += pe_row[i % d];
+}
+int add_pe_row(float *x, const float *pe_row, int64_t n_rows, int d, cudaStream_t st) {
+  const int64_t n = n_rows * d;
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  add_pe_row_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, pe_row, n, d); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// decode step i: hvo_step[n, e] (hits = raw logits, v/o activated) -> out[n, i, :] with thresholded hits; the same row is
+// the decoder's input token of step i+1 (BGT/models/transformer.py:66-72)
+__global__ void decode_feedback_kernel(const float *__restrict__ hvo_step, float *tok, float *out, int64_t n_seq, int e, int step_i,
+                                       float thres) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seq * e) return;
+  int64_t s = i / e;
+  int c = (int)(i % e);
+  float v = hvo_step[i];
+  if (c < e / 3) v = (1.f / (1.f + expf(-v)) > thres) ? 1.f : 0.f;
+  out[(s * T + step_i) * e + c] = v;
+  tok[i] = v;
+}
+int decode_feedback(const float *hvo_step, float *tok, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st) {
+  const int64_t n = n_seq * e;
+  { LaunchScope _ls(KC_ELEMWISE, st);
+  decode_feedback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvo_step, tok, out, n_seq, e, step_i, thres); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---- optimizers over the flat vectors ---------------------------------------------------------
 __global__ void sgd_kernel(float *p, const float *__restrict__ g, int64_t n, float lr, float gs) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

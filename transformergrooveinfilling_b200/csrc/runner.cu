@@ -19,12 +19,14 @@ void set_error(const std::string &msg) { g_err = msg; }
 static int64_t g_launches[KC_MAX] = {0};
 static int g_prof_class = KC_NONE;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<int> g_prof_cls;
 static size_t g_prof_used = 0;
 
 LaunchScope::LaunchScope(int c, cudaStream_t s) : cls(c), st(s), slot(-1) {
   ++g_launches[c];
-  if (c == g_prof_class && g_prof_used < g_prof_events.size()) {
+  if ((c == g_prof_class || g_prof_class == -1) && g_prof_used < g_prof_events.size()) {
     slot = (int)g_prof_used++;
+    g_prof_cls[slot] = c;
     cudaEventRecord(g_prof_events[slot].first, st);
   }
 }
@@ -140,6 +142,9 @@ struct Plan {
   float *d_hvo, *loss_partials;      // fused train step
   // backward temporaries
   float *dxa, *dxb, *du, *da, *dh, *dqkv, *dctx, *dlog, *dmem, *dqc, *dkvc, *g0;
+  // KV-cached decode (mode 2): per-layer key/value caches + one-token-per-sequence step buffers
+  float *kv_self[64], *kv_cross[64];
+  float *s_tok, *s_ya, *s_yb, *s_x1, *s_x2, *s_q, *s_ctx, *s_a, *s_hd, *s_z, *s_hvo;
   int64_t bytes;
 };
 
@@ -153,6 +158,7 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     return base ? reinterpret_cast<float *>(base + o) : nullptr;
   };
   const bool train = mode == 1;
+  const bool decode = mode == 2 && c.n_dec > 0;
   auto layer = [&](LayerBuf &b, bool dec) {
     b.qkv = take(M * 3 * d); b.ctx = take(M * d);
     b.u1 = train ? take(M * d) : nullptr; b.m1 = train ? take(M) : nullptr; b.r1 = train ? take(M) : nullptr;
@@ -173,7 +179,13 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     for (int l = 1; l < c.n_enc; ++l) P.enc[l] = P.enc[0];
   }
   P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
-  if (c.n_dec > 0) {
+  if (decode) {
+    const int64_t n = n_seq;
+    for (int l = 0; l < c.n_dec; ++l) { P.kv_self[l] = take(M * 2 * d); P.kv_cross[l] = take(M * 2 * d); }
+    P.s_tok = take(n * c.e_tgt); P.s_ya = take(n * d); P.s_yb = take(n * d); P.s_x1 = take(n * d); P.s_x2 = take(n * d);
+    P.s_q = take(n * d); P.s_ctx = take(n * d); P.s_a = take(n * d); P.s_hd = take(n * F); P.s_z = take(n * d);
+    P.s_hvo = take(n * c.e_tgt);
+  } else if (c.n_dec > 0) {
     P.r0d = take(M * d); P.y0d = take(M * d);
     if (train) {
       for (int l = 0; l < c.n_dec; ++l) layer(P.dec[l], true);
@@ -471,6 +483,64 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// KV-cached autoregressive predict (encoder-decoder).  BGT/models/transformer.py:48-83 runs 32 FULL decoder passes; the
+// target mask is causal (BGT/models/utils.py:53-56), so position i of pass i depends only on tokens <= i and an incremental
+// decode that caches each layer's self-attention keys/values (and the cross-attention keys/values of the encoder
+// memory, which never change) produces the same outputs with 1/32 of the decoder work.
+// ---------------------------------------------------------------------------------------------
+static int linear_rows(const Ctx &x, const float *X, int64_t K, const float *W, float *out, int64_t ldc, int64_t N, int64_t rows,
+                       GemmEpi e) {
+  return gemm_f32(X, K, 1, W, K, 1, out, ldc, rows, N, K, e, 0, x.st);
+}
+
+static int predict_decode(const Ctx &x, const Plan &pl, float thres, float *hvo_out) {
+  const int d = x.c.d_model, F = x.c.dim_ff, E = x.c.e_tgt, H = x.c.nhead, dh = d / H;
+  const int64_t n = x.n_seq;
+  Drop none;
+  for (int l = 0; l < x.c.n_dec; ++l) {        // cross-attention keys / values of the memory, once per layer
+    const LayerP &p = x.L.dec[l];
+    GemmEpi e; e.bias = x.P + p.ca.b_in + d;
+    GT_TRY(linear(x, pl.mem, d, x.P + p.ca.w_in + (int64_t)d * d, pl.kv_cross[l], 2 * d, e));
+  }
+  GT_CUDA(cudaMemsetAsync(pl.s_tok, 0, (size_t)n * E * sizeof(float), x.st));
+  for (int i = 0; i < T; ++i) {
+    GemmEpi ein; ein.bias = x.P + x.L.in_dec_b; ein.relu = 1;
+    GT_TRY(linear_rows(x, pl.s_tok, E, x.P + x.L.in_dec_w, pl.s_ya, d, d, n, ein));
+    GT_TRY(add_pe_row(pl.s_ya, x.pe + (int64_t)i * d, n, d, x.st));
+    float *cur = pl.s_ya, *nxt = pl.s_yb;
+    for (int l = 0; l < x.c.n_dec; ++l) {
+      const LayerP &p = x.L.dec[l];
+      GemmEpi eq; eq.bias = x.P + p.sa.b_in;
+      GT_TRY(linear_rows(x, cur, d, x.P + p.sa.w_in, pl.s_q, d, d, n, eq));
+      GemmEpi ekv; ekv.bias = x.P + p.sa.b_in + d;        // this token's key | value -> row i of the layer's cache
+      GT_TRY(linear_rows(x, cur, d, x.P + p.sa.w_in + (int64_t)d * d, pl.kv_self[l] + (int64_t)i * 2 * d, (int64_t)T * 2 * d, 2 * d, n, ekv));
+      GT_TRY(attention_decode(pl.s_q, d, pl.kv_self[l], pl.kv_self[l] + d, 2 * d, (int64_t)T * 2 * d, i + 1, pl.s_ctx, d, n, H, dh, x.st));
+      GemmEpi eo; eo.bias = x.P + p.sa.b_out;
+      GT_TRY(linear_rows(x, pl.s_ctx, d, x.P + p.sa.w_out, pl.s_a, d, d, n, eo));
+      GT_TRY(ln_fwd(pl.s_a, cur, x.P + p.g1, x.P + p.be1, nullptr, pl.s_x1, nullptr, nullptr, n, d, none, 0, x.st));
+      GemmEpi ecq; ecq.bias = x.P + p.ca.b_in;
+      GT_TRY(linear_rows(x, pl.s_x1, d, x.P + p.ca.w_in, pl.s_q, d, d, n, ecq));
+      GT_TRY(attention_decode(pl.s_q, d, pl.kv_cross[l], pl.kv_cross[l] + d, 2 * d, (int64_t)T * 2 * d, T, pl.s_ctx, d, n, H, dh, x.st));
+      GemmEpi eco; eco.bias = x.P + p.ca.b_out;
+      GT_TRY(linear_rows(x, pl.s_ctx, d, x.P + p.ca.w_out, pl.s_a, d, d, n, eco));
+      GT_TRY(ln_fwd(pl.s_a, pl.s_x1, x.P + p.g2, x.P + p.be2, nullptr, pl.s_x2, nullptr, nullptr, n, d, none, 0, x.st));
+      GemmEpi e1; e1.bias = x.P + p.b1; e1.relu = 1;
+      GT_TRY(linear_rows(x, pl.s_x2, d, x.P + p.w1, pl.s_hd, F, F, n, e1));
+      GemmEpi e2; e2.bias = x.P + p.b2;
+      GT_TRY(linear_rows(x, pl.s_hd, F, x.P + p.w2, pl.s_a, d, d, n, e2));
+      GT_TRY(ln_fwd(pl.s_a, pl.s_x2, x.P + p.g3, x.P + p.be3, nullptr, nxt, nullptr, nullptr, n, d, none, 0, x.st));
+      std::swap(cur, nxt);
+    }
+    GT_TRY(ln_fwd(cur, nullptr, x.P + x.L.dec_norm_g, x.P + x.L.dec_norm_b, nullptr, pl.s_z, nullptr, nullptr, n, d, none, 0, x.st));
+    GemmEpi eh; eh.bias = x.P + x.L.out_b;
+    GT_TRY(linear_rows(x, pl.s_z, d, x.P + x.L.out_w, pl.s_hvo, E, E, n, eh));
+    GT_TRY(head_activation(pl.s_hvo, n, E, -1.f, x.st));
+    GT_TRY(decode_feedback(pl.s_hvo, pl.s_tok, hvo_out, n, E, i, thres, x.st));
+  }
+  return 0;
+}
+
 static int make_ctx(Ctx &x, const gt_config *cfg, const float *params, float *grads, const float *pe, int64_t n_seq,
                     bool train, uint64_t seed, uint64_t step, int64_t seq0, void *stream) {
   GT_TRY(validate_config(cfg));
@@ -523,8 +593,8 @@ int gt_param_layout(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int 
 
 int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode) {
   if (validate_config(cfg)) return -1;
-  if (n_seq < 1 || (mode != 0 && mode != 1)) { set_error("gt_workspace_bytes: bad n_seq / mode"); return -1; }
-  if (cfg->precision == GT_PREC_BF16) return tc_workspace_bytes(*cfg, n_seq, mode);
+  if (n_seq < 1 || mode < 0 || mode > 2) { set_error("gt_workspace_bytes: bad n_seq / mode"); return -1; }
+  if (cfg->precision == GT_PREC_BF16) return tc_workspace_bytes(*cfg, n_seq, mode == 2 ? 0 : mode);
   static thread_local Plan pl;
   make_plan(*cfg, n_seq, mode, nullptr, pl);
   return pl.bytes;
@@ -589,6 +659,11 @@ int gt_train_step(const gt_config *cfg, const float *params, const float *pe, co
 
 int gt_predict(const gt_config *cfg, const float *params, const float *pe, const float *src, int64_t n_seq, float thres,
                float *hvo_out, void *ws, int64_t ws_bytes, void *stream) {
+  return gt_predict_variant(cfg, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, 0, stream);
+}
+
+int gt_predict_variant(const gt_config *cfg, const float *params, const float *pe, const float *src, int64_t n_seq, float thres,
+                       float *hvo_out, void *ws, int64_t ws_bytes, int variant, void *stream) {
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, false, 0, 0, 0, stream));
   GT_CHECK(src && hvo_out, "gt_predict: null pointer");
@@ -596,10 +671,12 @@ int gt_predict(const gt_config *cfg, const float *params, const float *pe, const
   if (cfg->precision == GT_PREC_BF16)
     return tc_predict(*cfg, x.L, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, x.st);
   static thread_local Plan pl;
-  GT_TRY(check_ws(cfg, n_seq, 0, ws, ws_bytes, pl));
+  GT_TRY(check_ws(cfg, n_seq, variant == 1 ? 0 : 2, ws, ws_bytes, pl));
   GT_TRY(encoder_fwd(x, pl, src));
   if (cfg->n_dec == 0) return head_fwd(x, pl.mem, hvo_out, thres);
-  // BGT/models/transformer.py:48-83: 32 decoder passes; step i feeds (thresholded h, raw v, raw o) to i+1.
+  if (variant != 1) return predict_decode(x, pl, thres, hvo_out);
+  // variant 1 — the reference's literal loop, BGT/models/transformer.py:48-83: 32 full decoder passes; step i feeds
+  // (thresholded h, raw v, raw o) to i+1.  Kept as the cross-check of the KV-cached decode.
   GT_CUDA(cudaMemsetAsync(pl.tgt_in, 0, (size_t)x.M * cfg->e_tgt * sizeof(float), x.st));
   float *full = pl.full;
   for (int i = 0; i < T; ++i) {
@@ -661,8 +738,9 @@ int gt_profile_enable(int kernel_class, int max_records) {
   g_prof_events.clear();
   g_prof_used = 0;
   g_prof_class = KC_NONE;
-  if (kernel_class <= 0 || kernel_class >= KC_MAX || max_records <= 0) return 0;
+  if (kernel_class == 0 || kernel_class < -1 || kernel_class >= KC_MAX || max_records <= 0) return 0;
   g_prof_events.resize((size_t)max_records);
+  g_prof_cls.assign((size_t)max_records, 0);
   for (auto &e : g_prof_events) { GT_CUDA(cudaEventCreate(&e.first)); GT_CUDA(cudaEventCreate(&e.second)); }
   g_prof_class = kernel_class;
   return 0;
@@ -680,6 +758,23 @@ int gt_profile_collect(double *total_ms, int64_t *launches) {
   *total_ms = tot;
   *launches = (int64_t)g_prof_used;
   g_prof_used = 0;
+  return 0;
+}
+
+int gt_profile_collect_class(int kernel_class, double *total_ms, int64_t *launches) {
+  GT_CHECK(total_ms && launches, "gt_profile_collect_class: null pointer");
+  double tot = 0;
+  int64_t n = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (g_prof_cls[i] != kernel_class) continue;
+    GT_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+    float ms = 0.f;
+    GT_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *launches = n;
   return 0;
 }
 

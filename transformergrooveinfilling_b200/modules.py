@@ -324,16 +324,18 @@ class _GrooveBase(nn.Module):
                                      ws.numel(), self._seed, step, self._seq0, _lib.stream_ptr(x.device)), "gt_train_step")
         return metrics, hvo
 
-    def _predict_hvo(self, src, thres):
+    def _predict_hvo(self, src, thres, literal: bool = False):
+        """gt_predict; ``literal=True`` runs the reference's 32 full decoder passes instead of the KV-cached decode
+        (encoder-decoder models; used by the tests to cross-check the two)."""
         lib = _lib.load()
         src = self._check_input(src, self.embedding_size_src, "src")
         n = src.shape[0]
-        ws = self._workspace(n, 0, src.device)
+        ws = self._workspace(n, 0 if literal else 2, src.device)
         out = torch.empty(n, T_STEPS, 27, dtype=torch.float32, device=src.device)
         cfg = self._cfg()
-        _lib.check(lib.gt_predict(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._pe_flat()), _lib.ptr(src), n,
-                                  float(thres), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(src.device)),
-                   "gt_predict")
+        _lib.check(lib.gt_predict_variant(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._pe_flat()), _lib.ptr(src), n,
+                                          float(thres), _lib.ptr(out), _lib.ptr(ws), ws.numel(), 1 if literal else 0,
+                                          _lib.stream_ptr(src.device)), "gt_predict")
         return out
 
     @staticmethod
