@@ -71,15 +71,37 @@ def dropout_threshold(p: float) -> int:
     return int(min(65535, max(0, round(p * 65536.0))))
 
 
+def hash_quad(v, key):
+    """64 random bits (lo, hi uint32 pairs held in uint64 arrays) per quad value ``v`` — csrc/common.cuh:hash_quad."""
+    x = _u32(_u32(v) * np.uint64(0x9E3779B1)) ^ np.uint64(key)
+    x ^= x >> np.uint64(16)
+    p = x * np.uint64(0x7FEB352D)
+    plo, phi = _u32(p), p >> np.uint64(32)
+    y = plo ^ phi
+    q = y * np.uint64(0x846CA68B)
+    lo = _u32(q) ^ phi
+    hi = (q >> np.uint64(32)) ^ _u32((y << np.uint64(16)) | (y >> np.uint64(16)))
+    return lo, hi
+
+
 def dropout_keep(seed: int, step: int, site: int, idx: np.ndarray, p: float) -> np.ndarray:
-    """Keep-mask for element indices ``idx`` (uint64).  One 32-bit hash serves two elements."""
-    key = np.uint64(site_key(seed, step, site))
+    """Keep-mask for element indices ``idx`` (uint64).  One 64-bit hash serves the quad of elements
+    4w..4w+3: element k of the quad reads 16-bit field k of (lo, hi) — csrc/common.cuh:drop_keep."""
+    key = site_key(seed, step, site)
     idx = np.asarray(idx, dtype=np.uint64)
-    w = idx >> np.uint64(1)
-    x = _u32(w) ^ _u32((w >> np.uint64(32)) * np.uint64(0x85EBCA6B))
-    h = mix32(_u32(x * np.uint64(0x9E3779B1)) ^ key)
-    half = np.where((idx & np.uint64(1)) == 1, h >> np.uint64(16), h & np.uint64(0xFFFF))
+    w = idx >> np.uint64(2)
+    v = _u32(w) ^ _u32((w >> np.uint64(32)) * np.uint64(0x85EBCA6B))
+    lo, hi = hash_quad(v, key)
+    k = idx & np.uint64(3)
+    word = np.where(k >= 2, hi, lo)
+    half = np.where((k & np.uint64(1)) == 1, word >> np.uint64(16), word & np.uint64(0xFFFF))
     return half >= np.uint64(dropout_threshold(p))
+
+
+def key_perm(k):
+    """Position of key k inside a query row at the attention-probability sites (csrc/common.cuh:key_perm)."""
+    k = np.asarray(k)
+    return (k & 16) | (((k >> 1) & 3) << 2) | (((k >> 3) & 1) << 1) | (k & 1)
 
 
 def dropout_scale(p: float) -> float:
@@ -150,13 +172,14 @@ class DropCtx:
         return x * torch.from_numpy(keep).to(x.dtype) * dropout_scale(self.p)
 
     def probs(self, pr: torch.Tensor, site: int) -> torch.Tensor:
-        """pr: [N, H, 32, 32]; element index = (((seq0+n)*H + h)*32 + i)*32 + j."""
+        """pr: [N, H, 32, 32]; element index = (((seq0+n)*H + h)*32 + i)*32 + key_perm(j)."""
         if not self.active():
             return pr
         if self.native:
             return torch.nn.functional.dropout(pr, self.p, True)
         n, h, a, b = pr.shape
-        idx = (np.arange(n * h * a * b, dtype=np.uint64) + np.uint64(self.seq0 * h * a * b))
+        rows = (np.arange(n * h * a, dtype=np.uint64) + np.uint64(self.seq0 * h * a)) * np.uint64(b)
+        idx = rows[:, None] + key_perm(np.arange(b)).astype(np.uint64)[None, :]
         keep = dropout_keep(self.seed, self.step, site, idx, self.p).reshape(n, h, a, b)
         return pr * torch.from_numpy(keep).to(pr.dtype) * dropout_scale(self.p)
 

@@ -75,12 +75,37 @@ struct Drop {           // one dropout site; thr == 0 means "inactive"
   uint32_t key = 0, thr = 0;
   float scale = 1.f;
 };
+// 64 random bits = four 16-bit dropout decisions for the QUAD of elements 4w .. 4w+3 of one site.  v = (uint32)w ^
+// ((uint32)(w >> 32) * 0x85EBCA6B).  One xorshift-multiply round, then two 32x32 -> 64 multiplies (IMAD.WIDE) whose
+// halves are cross-mixed: 12 instructions per four decisions.
+__host__ __device__ __forceinline__ void hash_quad(uint32_t v, uint32_t key, uint32_t &lo, uint32_t &hi) {
+  uint32_t x = (v * 0x9E3779B1u) ^ key;
+  x ^= x >> 16;
+  const uint64_t p = (uint64_t)x * 0x7FEB352Du;
+  const uint32_t plo = (uint32_t)p, phi = (uint32_t)(p >> 32);
+  const uint32_t y = plo ^ phi;
+  const uint64_t q = (uint64_t)y * 0x846CA68Bu;
+  lo = (uint32_t)q ^ phi;
+  hi = (uint32_t)(q >> 32) ^ ((y << 16) | (y >> 16));
+}
+// decision k (0..3) of a quad: 16-bit field k of (lo, hi) >= thr  <=> keep
+__host__ __device__ __forceinline__ bool quad_keep(uint32_t lo, uint32_t hi, int k, uint32_t thr) {
+  const uint32_t word = (k & 2) ? hi : lo;
+  return ((k & 1) ? (word >> 16) : (word & 0xFFFFu)) >= thr;
+}
 __device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t thr, uint64_t idx) {
-  uint64_t w = idx >> 1;
-  uint32_t x = (uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu);
-  uint32_t h = mix32((x * 0x9E3779B1u) ^ key);
-  uint32_t half = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
-  return half >= thr;
+  const uint64_t w = idx >> 2;
+  uint32_t lo, hi;
+  hash_quad((uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu), key, lo, hi);
+  return quad_keep(lo, hi, (int)(idx & 3), thr);
+}
+// Attention-probability sites index key j of a query row at position key_perm(j): the four probabilities an mma.sync
+// accumulator thread owns for one row (keys 8 nt + 2 t + b, nt in {0,1} or {2,3}) then form ONE quad.
+__host__ __device__ __forceinline__ int key_perm(int k) { return (k & 16) | (((k >> 1) & 3) << 2) | (((k >> 3) & 1) << 1) | (k & 1); }
+__device__ __forceinline__ float ex2_ftz(float x) {      // 2^x, one MUFU (exp2f adds a denormal-range fix-up: 3 more instructions)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // site numbering (oracle: site_id / SITE_IN_*)

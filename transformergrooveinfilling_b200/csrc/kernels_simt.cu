@@ -183,7 +183,7 @@ __global__ void attention_fwd_kernel(AttnArgs a, int warps) {
 #pragma unroll
   for (int j = 0; j < T; ++j) {
     float p = s[j] * inv;
-    if (a.drop.thr) p = drop_keep(a.drop.key, a.drop.thr, base + j) ? p * a.drop.scale : 0.f;
+    if (a.drop.thr) p = drop_keep(a.drop.key, a.drop.thr, base + key_perm(j)) ? p * a.drop.scale : 0.f;
     s[j] = p;
   }
   __syncwarp();
@@ -249,7 +249,7 @@ __global__ void attention_bwd_kernel(AttnArgs a, int warps) {
   for (int j = 0; j < T; ++j) {
     float p = s[j] * inv;
     float keep = 1.f;
-    if (a.drop.thr) keep = drop_keep(a.drop.key, a.drop.thr, base + j) ? a.drop.scale : 0.f;
+    if (a.drop.thr) keep = drop_keep(a.drop.key, a.drop.thr, base + key_perm(j)) ? a.drop.scale : 0.f;
     Ps[lane * (T + 1) + j] = p * keep;   // dropped probabilities (feed dV)
     dp[j] *= keep;                       // gradient w.r.t. the un-dropped probability
     delta = fmaf(dp[j], p, delta);

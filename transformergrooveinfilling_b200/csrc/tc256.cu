@@ -220,8 +220,8 @@ __device__ __forceinline__ void t256_attn_fwd(const uint8_t *sQKV, uint8_t *sCtx
     s0[u] = 0.f; s1[u] = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      sacc[u][nt][0] = exp2f(sacc[u][nt][0] - m0[u]); sacc[u][nt][1] = exp2f(sacc[u][nt][1] - m0[u]);
-      sacc[u][nt][2] = exp2f(sacc[u][nt][2] - m1[u]); sacc[u][nt][3] = exp2f(sacc[u][nt][3] - m1[u]);
+      sacc[u][nt][0] = ex2_ftz(sacc[u][nt][0] - m0[u]); sacc[u][nt][1] = ex2_ftz(sacc[u][nt][1] - m0[u]);
+      sacc[u][nt][2] = ex2_ftz(sacc[u][nt][2] - m1[u]); sacc[u][nt][3] = ex2_ftz(sacc[u][nt][3] - m1[u]);
       s0[u] += sacc[u][nt][0] + sacc[u][nt][1]; s1[u] += sacc[u][nt][2] + sacc[u][nt][3];
     }
   }
@@ -237,18 +237,24 @@ __device__ __forceinline__ void t256_attn_fwd(const uint8_t *sQKV, uint8_t *sCtx
   for (int u = 0; u < NHP; ++u) {
     const float i0 = dr.scale / s0[u], i1 = dr.scale / s1[u];
     if (dr.thr) {
+      // quads of one query row (common.cuh: key_perm): quad t = this lane's keys of nt 0,1 ; quad 4 + t = those of nt 2,3
       const int q0 = half[u] * 16 + g;
-      const uint64_t wa = w_pair[u] + (uint64_t)q0 * 16u, wb = wa + 128u;           // rows q0 and q0 + 8
+      const uint64_t wa = w_pair[u] + (uint64_t)q0 * 8u, wb = wa + 64u;            // rows q0 and q0 + 8
       const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
       const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const uint32_t ha = drop_hash(alo + (uint32_t)(4 * nt + t), ahi, dr.key);
-        const uint32_t hb = drop_hash(blo + (uint32_t)(4 * nt + t), bhi, dr.key);
-        sacc[u][nt][0] = ((ha & 0xFFFFu) >= dr.thr) ? sacc[u][nt][0] * i0 : 0.f;
-        sacc[u][nt][1] = ((ha >> 16) >= dr.thr) ? sacc[u][nt][1] * i0 : 0.f;
-        sacc[u][nt][2] = ((hb & 0xFFFFu) >= dr.thr) ? sacc[u][nt][2] * i1 : 0.f;
-        sacc[u][nt][3] = ((hb >> 16) >= dr.thr) ? sacc[u][nt][3] * i1 : 0.f;
+      for (int np = 0; np < 2; ++np) {
+        uint32_t la, ha, lb, hb;
+        hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
+        hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
+        sacc[u][2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np][0] * i0 : 0.f;
+        sacc[u][2 * np][1] = ((la >> 16) >= dr.thr) ? sacc[u][2 * np][1] * i0 : 0.f;
+        sacc[u][2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np + 1][0] * i0 : 0.f;
+        sacc[u][2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? sacc[u][2 * np + 1][1] * i0 : 0.f;
+        sacc[u][2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np][2] * i1 : 0.f;
+        sacc[u][2 * np][3] = ((lb >> 16) >= dr.thr) ? sacc[u][2 * np][3] * i1 : 0.f;
+        sacc[u][2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np + 1][2] * i1 : 0.f;
+        sacc[u][2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? sacc[u][2 * np + 1][3] * i1 : 0.f;
       }
     } else {
 #pragma unroll
@@ -507,7 +513,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
             const int hp = warp + 16 * u, pair = hp >> 1;
             half[u] = hp & 1; s[u] = pair / GH; hl[u] = pair % GH;
             const int64_t seq = a.seq0 + (int64_t)tile * 4 + s[u];
-            w_pair[u] = (uint64_t)((seq * H + (g * GH + hl[u])) * 32) * 16u;
+            w_pair[u] = (uint64_t)((seq * H + (g * GH + hl[u])) * 32) * 8u;      // quad index of (row 0, position 0) of this (sequence, head)
           }
           t256_attn_fwd<DH, NHP>(sQKV, sCtx + b * 16384, s, hl, half, lane, a.d_attn, w_pair);
         }
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         u[c + 4] = bf16lo(xv.z); u[c + 5] = bf16hi(xv.z); u[c + 6] = bf16lo(xv.w); u[c + 7] = bf16hi(xv.w);
       }
       {
-        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * 256 + part * 64) >> 1;
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * 256 + part * 64) >> 2;
         const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
         const float *bo = p_bo + part * 64;
         uint8_t *u1g = a.u1_img ? a.u1_img + (size_t)tile * T256_TILE_IMG : nullptr;
@@ -545,15 +551,19 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
           tmem_ld16(t_out + lane_off + (uint32_t)(part * 64 + cb), f);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float m0 = 1.f, m1 = 1.f;
+          for (int j = 0; j < 16; j += 4) {
+            float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
             if (a.d1.thr) {
-              const uint32_t hs = drop_hash(wlo + (uint32_t)((cb + j) >> 1), xhi, a.d1.key);
-              m0 = ((hs & 0xFFFFu) >= a.d1.thr) ? a.d1.scale : 0.f; m1 = ((hs >> 16) >= a.d1.thr) ? a.d1.scale : 0.f;
+              uint32_t lo, hi;
+              hash_quad((wlo + (uint32_t)((cb + j) >> 2)) ^ xhi, a.d1.key, lo, hi);
+              m0 = ((lo & 0xFFFFu) >= a.d1.thr) ? a.d1.scale : 0.f; m1 = ((lo >> 16) >= a.d1.thr) ? a.d1.scale : 0.f;
+              m2 = ((hi & 0xFFFFu) >= a.d1.thr) ? a.d1.scale : 0.f; m3 = ((hi >> 16) >= a.d1.thr) ? a.d1.scale : 0.f;
             }
             u[cb + j] += (f[j] + bo[cb + j]) * m0;
             u[cb + j + 1] += (f[j + 1] + bo[cb + j + 1]) * m1;
-            s1 += u[cb + j] + u[cb + j + 1];
+            u[cb + j + 2] += (f[j + 2] + bo[cb + j + 2]) * m2;
+            u[cb + j + 3] += (f[j + 3] + bo[cb + j + 3]) * m3;
+            s1 += (u[cb + j] + u[cb + j + 1]) + (u[cb + j + 2] + u[cb + j + 3]);
           }
           if (u1g) {
 #pragma unroll
@@ -601,19 +611,24 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         float v[16];
         tmem_ld16(t_h + lane_off + (uint32_t)(part * 16), v);
         tmem_ld_wait();
-        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * 64 + part * 16) >> 1;
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * 64 + part * 16) >> 2;
         const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
         const float *b1 = p_b1 + c * 64 + part * 16;
         uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
+        for (int j = 0; j < 16; j += 4) {
           float h0 = fmaxf(v[j] + b1[j], 0.f), h1 = fmaxf(v[j + 1] + b1[j + 1], 0.f);
+          float h2 = fmaxf(v[j + 2] + b1[j + 2], 0.f), h3 = fmaxf(v[j + 3] + b1[j + 3], 0.f);
           if (a.d_ffn.thr) {
-            const uint32_t hs = drop_hash(wlo + (uint32_t)(j >> 1), xhi, a.d_ffn.key);
-            h0 = ((hs & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-            h1 = ((hs >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+            uint32_t lo, hi;
+            hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
+            h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
+            h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+            h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
+            h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
           }
           pk[j >> 1] = pack_bf16(h0, h1);
+          pk[(j >> 1) + 1] = pack_bf16(h2, h3);
         }
         if (c > 0) {                                   // the bulk store of the previous chunk's H image must have finished reading sH
           if (tid == 0) tma_store_wait_read();
@@ -638,7 +653,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
       fence_after_sync();
       T256_STAMP();
       {
-        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * 256 + part * 64) >> 1;
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * 256 + part * 64) >> 2;
         const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
         const float *b2 = p_b2 + part * 64;
         uint8_t *u2g = a.u2_img ? a.u2_img + (size_t)tile * T256_TILE_IMG : nullptr;
@@ -649,15 +664,19 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
           tmem_ld16(t_out + lane_off + (uint32_t)(part * 64 + cb), f);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float m0 = 1.f, m1 = 1.f;
+          for (int j = 0; j < 16; j += 4) {
+            float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
             if (a.d2.thr) {
-              const uint32_t hs = drop_hash(wlo + (uint32_t)((cb + j) >> 1), xhi, a.d2.key);
-              m0 = ((hs & 0xFFFFu) >= a.d2.thr) ? a.d2.scale : 0.f; m1 = ((hs >> 16) >= a.d2.thr) ? a.d2.scale : 0.f;
+              uint32_t lo, hi;
+              hash_quad((wlo + (uint32_t)((cb + j) >> 2)) ^ xhi, a.d2.key, lo, hi);
+              m0 = ((lo & 0xFFFFu) >= a.d2.thr) ? a.d2.scale : 0.f; m1 = ((lo >> 16) >= a.d2.thr) ? a.d2.scale : 0.f;
+              m2 = ((hi & 0xFFFFu) >= a.d2.thr) ? a.d2.scale : 0.f; m3 = ((hi >> 16) >= a.d2.thr) ? a.d2.scale : 0.f;
             }
             u[cb + j] += (f[j] + b2[cb + j]) * m0;
             u[cb + j + 1] += (f[j + 1] + b2[cb + j + 1]) * m1;
-            s1 += u[cb + j] + u[cb + j + 1];
+            u[cb + j + 2] += (f[j + 2] + b2[cb + j + 2]) * m2;
+            u[cb + j + 3] += (f[j + 3] + b2[cb + j + 3]) * m3;
+            s1 += (u[cb + j] + u[cb + j + 1]) + (u[cb + j + 2] + u[cb + j + 3]);
           }
           if (u2g) {
 #pragma unroll

@@ -80,8 +80,8 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      p[nt][0] = exp2f(p[nt][0] - m0); p[nt][1] = exp2f(p[nt][1] - m0);
-      p[nt][2] = exp2f(p[nt][2] - m1); p[nt][3] = exp2f(p[nt][3] - m1);
+      p[nt][0] = ex2_ftz(p[nt][0] - m0); p[nt][1] = ex2_ftz(p[nt][1] - m0);
+      p[nt][2] = ex2_ftz(p[nt][2] - m1); p[nt][3] = ex2_ftz(p[nt][3] - m1);
       s0 += p[nt][0] + p[nt][1]; s1 += p[nt][2] + p[nt][3];
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
@@ -92,17 +92,22 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
     if (dr.thr) {
       keep = 0;
       const int q0 = 16 * mt + g;
-      const uint64_t wa = w_pair + (uint64_t)q0 * 16u, wb = wa + 128u;
+      const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;      // quad index of position 0 of rows q0 and q0 + 8
       const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
       const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const uint32_t ha = drop_hash(alo + (uint32_t)(4 * nt + t), ahi, dr.key);
-        const uint32_t hb = drop_hash(blo + (uint32_t)(4 * nt + t), bhi, dr.key);
-        keep |= ((ha & 0xFFFFu) >= dr.thr ? 1u : 0u) << (4 * nt);
-        keep |= ((ha >> 16) >= dr.thr ? 1u : 0u) << (4 * nt + 1);
-        keep |= ((hb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (4 * nt + 2);
-        keep |= ((hb >> 16) >= dr.thr ? 1u : 0u) << (4 * nt + 3);
+      for (int np = 0; np < 2; ++np) {            // quad 4 np + t = this lane's keys of nt = 2 np, 2 np + 1 (common.cuh: key_perm)
+        uint32_t la, ha, lb, hb;
+        hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
+        hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
+        keep |= ((la & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np);
+        keep |= ((la >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 1);
+        keep |= ((lb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 2);
+        keep |= ((lb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 3);
+        keep |= ((ha & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 4);
+        keep |= ((ha >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 5);
+        keep |= ((hb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 6);
+        keep |= ((hb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 7);
       }
     }
     // P, dropped P (pd), dL/dP through the dropout, delta = rowsum(dPd * P), dS = P (dPd - delta)
@@ -262,7 +267,7 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
     m2 = ((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256);
   }
   // pass C: du = rstd (dy g - m1 - xhat m2) ; da = du * dropmask
-  const uint64_t w0 = (e_row + (uint64_t)(part * 64)) >> 1;
+  const uint64_t w0 = (e_row + (uint64_t)(part * 64)) >> 2;
   const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
 #pragma unroll 1
   for (int cb = 0; cb < 64; cb += 32) {
@@ -286,10 +291,13 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
       *reinterpret_cast<float4 *>(park + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
     if (dr.thr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const uint32_t hs = drop_hash(wlo + (uint32_t)((cb + j) >> 1), xhi, dr.key);
-        w[j] = ((hs & 0xFFFFu) >= dr.thr) ? w[j] * dr.scale : 0.f;
-        w[j + 1] = ((hs >> 16) >= dr.thr) ? w[j + 1] * dr.scale : 0.f;
+      for (int j = 0; j < 32; j += 4) {
+        uint32_t lo, hi;
+        hash_quad((wlo + (uint32_t)((cb + j) >> 2)) ^ xhi, dr.key, lo, hi);
+        w[j] = ((lo & 0xFFFFu) >= dr.thr) ? w[j] * dr.scale : 0.f;
+        w[j + 1] = ((lo >> 16) >= dr.thr) ? w[j + 1] * dr.scale : 0.f;
+        w[j + 2] = ((hi & 0xFFFFu) >= dr.thr) ? w[j + 2] * dr.scale : 0.f;
+        w[j + 3] = ((hi >> 16) >= dr.thr) ? w[j + 3] * dr.scale : 0.f;
       }
     }
 #pragma unroll
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         if (warp < 4 * GH) {
           const int s = warp / GH, hl = warp % GH;
           const int64_t seq = a.seq0 + (int64_t)tile * 4 + s;
-          const uint64_t w_pair = (uint64_t)((seq * H + (g * GH + hl)) * 32) * 16u;
+          const uint64_t w_pair = (uint64_t)((seq * H + (g * GH + hl)) * 32) * 8u;     // quad index of (row 0, position 0)
           t256_attn_bwd<DH>(sR1, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
         }
         fence_async_smem();

@@ -12,8 +12,6 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 __device__ __forceinline__ uint64_t descA128(uint32_t base) { return make_desc(base, 2048u, 128u); }                 // A image with 128 rows: k16 step = 4096 B
 __device__ __forceinline__ uint64_t descB(uint32_t base, int N) { return make_desc(base, (uint32_t)(N >> 3) * 128u, 128u); }   // k16 step = N * 32 B
-// dropout hash of two consecutive elements (idx even): w = idx >> 1 given as (wlo + j, xhi)
-__device__ __forceinline__ uint32_t drop_hash(uint32_t wlo_j, uint32_t xhi, uint32_t key) { return mix32(((wlo_j ^ xhi) * 0x9E3779B1u) ^ key); }
 
 
 // per-lane vector of 32 values -> lane l receives the sum over the warp's lanes of v[l]  (31 shuffles)

@@ -81,14 +81,16 @@ __device__ __forceinline__ uint64_t desc_b(uint32_t base, int N, int k16) {
   const uint32_t kstride = (uint32_t)(N >> 3) * 128u;
   return make_desc(base + (uint32_t)k16 * 2u * kstride, kstride, 128u);
 }
-// two dropout decisions from one hash (idx_even must be even): returns scale or 0 for each
-__device__ __forceinline__ void drop2(const Drop &d, uint64_t idx_even, float &m0, float &m1) {
-  if (d.thr == 0) { m0 = 1.f; m1 = 1.f; return; }
-  uint64_t w = idx_even >> 1;
-  uint32_t x = (uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu);
-  uint32_t h = mix32((x * 0x9E3779B1u) ^ d.key);
-  m0 = ((h & 0xFFFFu) >= d.thr) ? d.scale : 0.f;
-  m1 = ((h >> 16) >= d.thr) ? d.scale : 0.f;
+// four dropout decisions from one 64-bit hash (idx4 must be a multiple of 4): returns scale or 0 for each
+__device__ __forceinline__ void drop4(const Drop &d, uint64_t idx4, float &m0, float &m1, float &m2, float &m3) {
+  if (d.thr == 0) { m0 = 1.f; m1 = 1.f; m2 = 1.f; m3 = 1.f; return; }
+  const uint64_t w = idx4 >> 2;
+  uint32_t lo, hi;
+  hash_quad((uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu), d.key, lo, hi);
+  m0 = ((lo & 0xFFFFu) >= d.thr) ? d.scale : 0.f;
+  m1 = ((lo >> 16) >= d.thr) ? d.scale : 0.f;
+  m2 = ((hi & 0xFFFFu) >= d.thr) ? d.scale : 0.f;
+  m3 = ((hi >> 16) >= d.thr) ? d.scale : 0.f;
 }
 
 struct SmemPlan {
@@ -323,16 +325,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sc[j]);
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { sc[j] = exp2f(sc[j] - mx); sum += sc[j]; }
+      for (int j = 0; j < 32; ++j) { sc[j] = ex2_ftz(sc[j] - mx); sum += sc[j]; }
       const float inv = keep_scale / sum;
       if (a.d_attn.thr) {
-        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 16);    // idx >> 1 of column 0
+        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 8);    // quad index (idx >> 2) of position 0
         const uint32_t xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)w0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_attn.key);
-          sc[j] = ((hsh & 0xFFFFu) >= a.d_attn.thr) ? sc[j] * inv : 0.f;
-          sc[j + 1] = ((hsh >> 16) >= a.d_attn.thr) ? sc[j + 1] * inv : 0.f;
+        for (int m = 0; m < 8; ++m) {                 // quad m = positions 4m..4m+3 = keys k0, k0+1, k0+8, k0+9 (common.cuh: key_perm)
+          const int k0 = (m >> 2) * 16 + (m & 3) * 2;
+          uint32_t lo, hi;
+          hash_quad((wlo + (uint32_t)m) ^ xhi, a.d_attn.key, lo, hi);
+          sc[k0] = ((lo & 0xFFFFu) >= a.d_attn.thr) ? sc[k0] * inv : 0.f;
+          sc[k0 + 1] = ((lo >> 16) >= a.d_attn.thr) ? sc[k0 + 1] * inv : 0.f;
+          sc[k0 + 8] = ((hi & 0xFFFFu) >= a.d_attn.thr) ? sc[k0 + 8] * inv : 0.f;
+          sc[k0 + 9] = ((hi >> 16) >= a.d_attn.thr) ? sc[k0 + 9] * inv : 0.f;
         }
       } else {
 #pragma unroll
@@ -365,8 +371,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       for (int c = 0; c < D; c += 4) {
         float4 xr = valid ? *reinterpret_cast<const float4 *>(a.x_in + grow * D + c) : make_float4(0, 0, 0, 0);
         float m0, m1, m2, m3;
-        drop2(a.d1, e0 + c, m0, m1);
-        drop2(a.d1, e0 + c + 2, m2, m3);
+        drop4(a.d1, e0 + c, m0, m1, m2, m3);
         x1[c] = xr.x + (x1[c] + p_bo[c]) * m0;
         x1[c + 1] = xr.y + (x1[c + 1] + p_bo[c + 1]) * m1;
         x1[c + 2] = xr.z + (x1[c + 2] + p_bo[c + 2]) * m2;
@@ -403,24 +408,29 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       mbar_wait(&bar_mma, ph); ph ^= 1;               // FFN1(c) (and FFN2(c-1)) complete
       fence_after_sync();
       {
-        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 1;        // multiple of 8 (F, FC multiples of 16)
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 2;        // multiple of 4 (F, FC multiples of 16)
         for (int b = part; b < nblk; b += 4) {
           const int cb = b * 16;
-          const uint64_t wb = w0 + (uint64_t)(cb >> 1);                                 // + (0..7) below never carries
+          const uint64_t wb = w0 + (uint64_t)(cb >> 2);                                 // + (0..3) below never carries
           const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
           float v[16];
           tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
+          for (int j = 0; j < 16; j += 4) {
             float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
+            float h2 = fmaxf(v[j + 2] + p_b1[c * FC + cb + j + 2], 0.f), h3 = fmaxf(v[j + 3] + p_b1[c * FC + cb + j + 3], 0.f);
             if (a.d_ffn.thr) {
-              const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_ffn.key);
-              h0 = ((hsh & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-              h1 = ((hsh >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+              uint32_t lo, hi;
+              hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
+              h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
+              h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+              h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
+              h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
             }
             pk[j >> 1] = pack_bf16(h0, h1);
+            pk[(j >> 1) + 1] = pack_bf16(h2, h3);
           }
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -452,12 +462,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
       float s1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; c += 2) {
-        float m0, m1;
-        drop2(a.d2, e0 + c, m0, m1);
+      for (int c = 0; c < D; c += 4) {
+        float m0, m1, m2, m3;
+        drop4(a.d2, e0 + c, m0, m1, m2, m3);
         f[c] = x1[c] + (f[c] + p_b2[c]) * m0;
         f[c + 1] = x1[c + 1] + (f[c + 1] + p_b2[c + 1]) * m1;
-        s1 += f[c] + f[c + 1];
+        f[c + 2] = x1[c + 2] + (f[c + 2] + p_b2[c + 2]) * m2;
+        f[c + 3] = x1[c + 3] + (f[c + 3] + p_b2[c + 3]) * m3;
+        s1 += (f[c] + f[c + 1]) + (f[c + 2] + f[c + 3]);
       }
       if (a.u2 && valid) {
 #pragma unroll
@@ -679,12 +691,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       { float t = warp_colsum32(w, lane); atomicAdd(&g_be2[lane], t); }
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
 #pragma unroll
-      for (int c = 0; c < D; c += 2) {
-        du[c] = rs * (du[c] * p_g2[c] - m1 - xh[c] * m2);
-        du[c + 1] = rs * (du[c + 1] * p_g2[c + 1] - m1 - xh[c + 1] * m2);
-        float k0, k1;
-        drop2(a.d2, e0 + c, k0, k1);
-        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da2 = grad wrt the FFN2 output (+bias)
+      for (int c = 0; c < D; c += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) du[c + j] = rs * (du[c + j] * p_g2[c + j] - m1 - xh[c + j] * m2);
+        float k0, k1, k2, k3;
+        drop4(a.d2, e0 + c, k0, k1, k2, k3);
+        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1; w[c + 2] = du[c + 2] * k2; w[c + 3] = du[c + 3] * k3;   // da2 = grad wrt the FFN2 output (+bias)
       }
 #pragma unroll
       for (int c = 0; c < D; c += 8)
@@ -737,11 +749,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       fence_after_sync();
       uint32_t mask = 0;                              // (kept && h > 0) bits of this thread's (<= 2) 16-column blocks
       {
-        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 1;
+        const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 2;
         int t = 0;
         for (int b = part; b < nblk; b += BWD_PARTS, ++t) {
           const int cb = b * 16;
-          const uint64_t wb = w0 + (uint64_t)(cb >> 1);
+          const uint64_t wb = w0 + (uint64_t)(cb >> 2);
           const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
           float v[16];
           tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
@@ -749,16 +761,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
           uint32_t pk[8];
           uint32_t bits = 0;
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
+          for (int j = 0; j < 16; j += 4) {
             float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
+            float h2 = fmaxf(v[j + 2] + p_b1[c * FC + cb + j + 2], 0.f), h3 = fmaxf(v[j + 3] + p_b1[c * FC + cb + j + 3], 0.f);
             if (a.d_ffn.thr) {
-              const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_ffn.key);
-              h0 = ((hsh & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-              h1 = ((hsh >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+              uint32_t lo, hi;
+              hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
+              h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
+              h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
+              h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
+              h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
             }
             bits |= (h0 > 0.f ? 1u : 0u) << j;
             bits |= (h1 > 0.f ? 1u : 0u) << (j + 1);
+            bits |= (h2 > 0.f ? 1u : 0u) << (j + 2);
+            bits |= (h3 > 0.f ? 1u : 0u) << (j + 3);
             pk[j >> 1] = pack_bf16(h0, h1);
+            pk[(j >> 1) + 1] = pack_bf16(h2, h3);
           }
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -857,12 +876,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       { float t = warp_colsum32(w, lane); atomicAdd(&g_be1[lane], t); }
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
 #pragma unroll
-      for (int c = 0; c < D; c += 2) {
-        du[c] = rstd1 * (du[c] * p_g1[c] - m1 - xh[c] * m2);
-        du[c + 1] = rstd1 * (du[c + 1] * p_g1[c + 1] - m1 - xh[c + 1] * m2);
-        float k0, k1;
-        drop2(a.d1, e0 + c, k0, k1);
-        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1;              // da1 = grad wrt the out-proj output (+bias)
+      for (int c = 0; c < D; c += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) du[c + j] = rstd1 * (du[c + j] * p_g1[c + j] - m1 - xh[c + j] * m2);
+        float k0, k1, k2, k3;
+        drop4(a.d1, e0 + c, k0, k1, k2, k3);
+        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1; w[c + 2] = du[c + 2] * k2; w[c + 3] = du[c + 3] * k3;   // da1 = grad wrt the out-proj output (+bias)
       }
 #pragma unroll
       for (int c = 0; c < D; c += 8)
@@ -927,18 +946,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       for (int j = 1; j < 32; ++j) mx = fmaxf(mx, pr[j]);
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { pr[j] = exp2f(pr[j] - mx); sum += pr[j]; }
+      for (int j = 0; j < 32; ++j) { pr[j] = ex2_ftz(pr[j] - mx); sum += pr[j]; }
       const float inv = 1.f / sum;
       uint32_t keep = 0xFFFFFFFFu;
       if (a.d_attn.thr) {
         keep = 0;
-        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 16);
+        const uint64_t w0 = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32 + lane) * 8);
         const uint32_t xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)w0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const uint32_t hsh = mix32((((wlo + (uint32_t)(j >> 1)) ^ xhi) * 0x9E3779B1u) ^ a.d_attn.key);
-          keep |= ((hsh & 0xFFFFu) >= a.d_attn.thr ? 1u : 0u) << j;
-          keep |= ((hsh >> 16) >= a.d_attn.thr ? 1u : 0u) << (j + 1);
+        for (int m = 0; m < 8; ++m) {                 // quad m = keys k0, k0+1, k0+8, k0+9 (common.cuh: key_perm)
+          const int k0 = (m >> 2) * 16 + (m & 3) * 2;
+          uint32_t lo, hi;
+          hash_quad((wlo + (uint32_t)m) ^ xhi, a.d_attn.key, lo, hi);
+          keep |= ((lo & 0xFFFFu) >= a.d_attn.thr ? 1u : 0u) << k0;
+          keep |= ((lo >> 16) >= a.d_attn.thr ? 1u : 0u) << (k0 + 1);
+          keep |= ((hi & 0xFFFFu) >= a.d_attn.thr ? 1u : 0u) << (k0 + 8);
+          keep |= ((hi >> 16) >= a.d_attn.thr ? 1u : 0u) << (k0 + 9);
         }
       }
       const float ks = a.d_attn.scale;
