@@ -154,3 +154,11 @@ def test_grad_buckets_partition_the_flat_vector_in_backward_order():
         assert offs[n - 1] == 0 and offs[n - 2] == start["Encoder.Encoder.layers.0.self_attn.in_proj_weight"]
         assert lib.gt_grad_buckets(C.byref(c), offs, sizes, 1) < 0
     assert lib.gt_grad_bucket_wait(0, None) != 0 and b"not enabled" in lib.gt_last_error()
+
+
+def test_input_pipelines_refuse_a_cpu_device():
+    from transformergrooveinfilling_b200.pipeline import DeviceResidentLoader, HostBatchPrefetcher
+    with pytest.raises(RuntimeError):
+        HostBatchPrefetcher("cpu", (4, 32, 16), (4, 32, 27))
+    with pytest.raises(RuntimeError):
+        DeviceResidentLoader(torch.zeros(4, 32, 16), torch.zeros(4, 32, 27), 2, "cpu")

@@ -1,6 +1,7 @@
 // tc_layers.cu — fused per-layer kernels of the bf16 tensor-core path.  See tc_layers.cuh.
 #include "tc_layers.cuh"
 #include "tc256.cuh"
+#include "tc_attn32.cuh"
 #include "umma.cuh"
 
 namespace gt {
@@ -97,15 +98,23 @@ struct SmemPlan {
   uint32_t w, par, xa, q, k, v, ctx, h, total;
 };
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
-__host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC) {
+// mma = attention on mma.sync (tc_attn32.cuh): q | k | v are bf16 row-major token images instead of fp32 rows / compact heads
+__host__ __device__ inline constexpr bool attn_mma(int DH) { return DH == 2 || DH == 4 || DH == 8; }
+__host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC, bool mma) {
   SmemPlan s;
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
   s.xa = al128(s.par + (uint32_t)(9 * D + F) * 4u);
   s.q = al128(s.xa + 128u * D * 2u);                 // fp32 q rows, stride D+4 (16-byte aligned, conflict-free)
-  s.k = al128(s.q + 128u * (D + 4u) * 4u);           // fp32 k, compact per (sequence, head): [4][H][32][dh]
-  s.v = s.k + 128u * D * 4u;
-  s.ctx = al128(s.v + 128u * D * 4u);
+  if (mma) {
+    s.k = s.q + A32_IMG;
+    s.v = s.k + A32_IMG;
+    s.ctx = al128(s.v + A32_IMG);
+  } else {
+    s.k = al128(s.q + 128u * (D + 4u) * 4u);         // fp32 k, compact per (sequence, head): [4][H][32][dh]
+    s.v = s.k + 128u * D * 4u;
+    s.ctx = al128(s.v + 128u * D * 4u);
+  }
   s.h = al128(s.ctx + 128u * D * 2u);
   s.total = al128(s.h + 128u * FC * 2u);
   return s;
@@ -229,7 +238,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
   const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
-  const SmemPlan sp = fwd_smem(D, F, FC);
+  constexpr bool MMA = attn_mma(DH);
+  const SmemPlan sp = fwd_smem(D, F, FC, MMA);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
   float *sPar = reinterpret_cast<float *>(smem + sp.par);
@@ -303,7 +313,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
         const float4 b = *reinterpret_cast<const float4 *>(p_bqkv + part * D + c);
         v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
       }
-      if (part == 0) {
+      if constexpr (MMA) {
+        a32_store_row(smem + (part == 0 ? sp.q : part == 1 ? sp.k : sp.v), row, v, part == 0 ? attn_scale : 1.f);
+      } else if (part == 0) {
 #pragma unroll
         for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(sQ + row * LQ + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       } else {
@@ -312,8 +324,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     }
     fence_before_sync();
     __syncthreads();
-    // ---- P3: attention, one warp per (sequence, head), lane = query row ----
-    for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {
+    // ---- P3: attention, one warp per (sequence, head) ----
+    if constexpr (MMA) {
+      for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {
+        const int s = p / H, h = p - s * H;
+        const uint64_t w_pair = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32) * 8);
+        a32_attn_fwd<DH>(smem + sp.q, smem + sp.k, smem + sp.v, sCtx, s, h, lane, a.d_attn, w_pair);
+      }
+    } else
+    for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {      // lane = query row
       const int s = p / H, h = p - s * H;
       const int r = s * 32 + lane;
       const float *kh = sK + s * 32 * D + h * 32 * dh;
@@ -518,11 +537,12 @@ static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 
 int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(D == 32, "tc_layer_fwd: d_model not instantiated");
-  const SmemPlan sp = fwd_smem(D, a.F, a.FC);
+  const SmemPlan sp = fwd_smem(D, a.F, a.FC, attn_mma(a.dh));
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
   switch (a.dh) {
     case 2: return launch_fwd<2>(a, sp.total, grid, st);
+    case 4: return launch_fwd<4>(a, sp.total, grid, st);
     case 8: return launch_fwd<8>(a, sp.total, grid, st);
     default: return launch_fwd<0>(a, sp.total, grid, st);
   }
@@ -540,7 +560,7 @@ int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
 struct BwdSmem {
   uint32_t w, par, gpar, stat, xin, x1, da, ctx, dq, q, k, v, dctx, h, dh, total;
 };
-__host__ __device__ inline BwdSmem bwd_smem(int D, int F) {
+__host__ __device__ inline BwdSmem bwd_smem(int D, int F, bool mma) {
   BwdSmem s;
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
@@ -553,10 +573,18 @@ __host__ __device__ inline BwdSmem bwd_smem(int D, int F) {
   s.dq = s.ctx + 128u * D * 2u;                       // dqkv image [128 x 3D]; M-padded reads run into the union below
   uint32_t u = al128(s.dq + 128u * 3u * D * 2u);
   s.q = u;                                            // attention phase: fp32 q rows, compact k / v, fp32 dctx rows
-  s.k = al128(s.q + 128u * (D + 4u) * 4u);
-  s.v = s.k + 128u * D * 4u;
-  s.dctx = al128(s.v + 128u * D * 4u);
-  uint32_t end_attn = al128(s.dctx + 128u * (D + 4u) * 4u);
+  uint32_t end_attn;
+  if (mma) {                                          // ... or four bf16 row-major token images (tc_attn32.cuh)
+    s.k = s.q + A32_IMG;
+    s.v = s.k + A32_IMG;
+    s.dctx = s.v + A32_IMG;
+    end_attn = al128(s.dctx + A32_IMG);
+  } else {
+    s.k = al128(s.q + 128u * (D + 4u) * 4u);
+    s.v = s.k + 128u * D * 4u;
+    s.dctx = al128(s.v + 128u * D * 4u);
+    end_attn = al128(s.dctx + 128u * (D + 4u) * 4u);
+  }
   s.h = u;                                            // FFN phase (aliases the attention scratch): H and dH images
   s.dh = s.h + 128u * 128u * 2u;
   uint32_t end_ffn = s.dh + 128u * 128u * 2u;
@@ -600,7 +628,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
   const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
-  const BwdSmem sp = bwd_smem(D, F);
+  constexpr bool MMA = attn_mma(DH);
+  const BwdSmem sp = bwd_smem(D, F, MMA);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
   float *sPar = reinterpret_cast<float *>(smem + sp.par);
@@ -920,7 +949,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
           v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
         }
       }
-      if (part == 0 || part == 3) {
+      if constexpr (MMA) {
+        a32_store_row(smem + (part == 0 ? sp.q : part == 1 ? sp.k : part == 2 ? sp.v : sp.dctx), row, v, part == 0 ? attn_scale : 1.f);
+      } else if (part == 0 || part == 3) {
         float *dst = (part == 0 ? sQ : sDC) + row * LQ;
 #pragma unroll
         for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -930,8 +961,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     }
     fence_before_sync();
     __syncthreads();
-    // ---- B5: attention backward, one warp per (sequence, head), lane = query row; dK/dV via warp transposed sums ----
-    for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {
+    // ---- B5: attention backward, one warp per (sequence, head) ----
+    if constexpr (MMA) {
+      for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {
+        const int s = p / H, h = p - s * H;
+        const uint64_t w_pair = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32) * 8);
+        a32_attn_bwd<DH>(smem + sp.q, smem + sp.k, smem + sp.v, smem + sp.dctx, sCtx, sDQ, s, h, lane, a.d_attn, w_pair, g_bqkv);
+      }
+    } else
+    for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {      // lane = query row; dK/dV via warp transposed sums
       const int s = p / H, h = p - s * H;
       const int r = s * 32 + lane;
       const float *q = sQ + r * LQ + h * dh;
@@ -1093,11 +1131,12 @@ static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
 int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(D == 32, "tc_layer_bwd: d_model not instantiated");
   GT_CHECK(a.F / a.FC <= 4, "tc_layer_bwd: more than 4 FFN chunks do not fit the TMEM gradient accumulators");
-  const BwdSmem sp = bwd_smem(D, a.F);
+  const BwdSmem sp = bwd_smem(D, a.F, attn_mma(a.dh));
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_bwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
   switch (a.dh) {
     case 2: return launch_bwd<2>(a, sp.total, grid, st);
+    case 4: return launch_bwd<4>(a, sp.total, grid, st);
     case 8: return launch_bwd<8>(a, sp.total, grid, st);
     default: return launch_bwd<0>(a, sp.total, grid, st);
   }
