@@ -180,7 +180,10 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
 
     for _ in range(args.warmup):
         step_resident()
-    lib.gt_profile_enable(17 if precision == "bf16" else 1, 4096)
+    from transformergrooveinfilling_b200 import _lib
+    path_kind = lib.gt_path_kind(C.byref(model._cfg()))
+    fused = path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256)
+    lib.gt_profile_enable({0: 1, 1: 17, 2: 17, 3: 22}[path_kind], 16384)
     l0 = lib.gt_launch_count(-1)
     sampler = ClockSampler(dev.index)
     sampler.start()
@@ -201,7 +204,7 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
     fl_step = train_flops_per_seq(w) / 3 * n
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     roof = None
-    if cnt.value and precision == "bf16":
+    if cnt.value and fused:
         layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
         avg_ms = tot_ms.value / cnt.value
         ach = 2 * layer_mac * n / (avg_ms / 1e3) / 1e12
@@ -215,7 +218,11 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
             "step_tflops": fl_step * world * args.steps / (ms / 1e3) / 1e12, "roofline": roof,
             "e2e": {"value": n * world * args.steps / (ms_e2e / 1e3), "unit": "seq/s", "h2d_bytes_per_step": xh.numel() * 4,
                     "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(launches), "clocks": clocks,
+            "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[path_kind]}
+    if cnt.value and not fused:
+        line["dominant_gemm"] = {"class": "gemm_tc" if path_kind == 3 else "gemm_f32", "launches_timed": cnt.value,
+                                 "share_of_step": tot_ms.value / ms}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -349,7 +356,9 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     # ---- timed region: kernel-resident throughput, dominant kernel class bracketed by CUDA events ----
-    dom = {"bf16": 18, "fp32": 1}[precision]
+    # fp32 SIMT GEMM / fused layer backward kernel / generic tcgen05 GEMM (shapes without fused layer kernels)
+    path_kind = lib.gt_path_kind(C.byref(model._cfg()))
+    dom = {_lib.PATH_FP32_SIMT: 1, _lib.PATH_FUSED_D32: 18, _lib.PATH_FUSED_D256: 18, _lib.PATH_GEMM_TC: 22}[path_kind]
     lib.gt_profile_enable(dom, 4096)
     l0 = lib.gt_launch_count(-1)
     sampler = ClockSampler(local)
@@ -379,7 +388,14 @@ def main():
     roof = None
     if cnt.value > 0:
         # the dominant kernel class and the share of the step's algorithmic FLOPs its launches carry
-        if precision == "bf16":
+        if path_kind == _lib.PATH_GEMM_TC:
+            # every Linear contraction of the step (forward, data gradient, weight gradient) except the K = 16 / 27 input
+            # layers and the 27-wide head runs in gemm_tc; attention runs in the SIMT attention kernels
+            d, F, L, Ld = w["d"], w["F"], w["L"], w["Ld"]
+            lin = L * 32 * (4 * d * d + 2 * d * F) + Ld * 32 * (8 * d * d + 2 * d * F)
+            fl_launch = 3 * 2 * lin * n * args.steps / max(cnt.value, 1)
+            kname = "gemm_tc (generic tcgen05 GEMM: fp32 operands rounded to bf16 while staged, fp32 accumulate; average over all Linear fwd / dgrad / wgrad launches)"
+        elif precision == "bf16":
             layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
             if w["d"] == 256:
                 # d_model = 256: the layer-backward kernel computes the data gradients (1x the layer's forward FLOPs);
@@ -402,7 +418,7 @@ def main():
     # ---- per-kernel-class breakdown: 3 extra steps with every class bracketed by events (outside the timed regions) ----
     kernels = {}
     names = {1: "gemm_f32", 2: "attention_fwd_f32", 3: "attention_bwd_f32", 4: "layernorm", 5: "elementwise", 6: "loss", 7: "optimizer",
-             16: "tc_weight_prep", 17: "tc_layer_fwd", 18: "tc_layer_bwd", 20: "tc_wgrad"}
+             16: "tc_weight_prep", 17: "tc_layer_fwd", 18: "tc_layer_bwd", 20: "tc_wgrad", 22: "gemm_tc"}
     lib.gt_profile_enable(-1, 8192)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -420,7 +436,7 @@ def main():
         lib.gt_profile_collect_class(cls, C.byref(t), C.byref(c))
         if c.value:
             kernels[nm] = {"launches_per_step": c.value / 3, "ms_per_step": t.value / 3, "share": t.value / ms3}
-            if precision == "bf16" and cls in fl_cls:
+            if path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256) and cls in fl_cls:
                 kernels[nm]["tflops"] = fl_cls[cls] / (t.value / c.value / 1e3) / 1e12
     lib.gt_profile_collect(C.byref(tot_ms), C.byref(cnt))
     lib.gt_profile_enable(0, 0)
@@ -434,6 +450,7 @@ def main():
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4, "d2h_bytes_per_step": 24,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss, "kernels": kernels,
+        "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[path_kind],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = 512

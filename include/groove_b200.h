@@ -31,6 +31,12 @@ extern "C" {
 #define GT_PREC_FP32 0         /* fp32 SIMT arithmetic everywhere (the 1e-4 "fp32/TF32" parity mode) */
 #define GT_PREC_BF16 1         /* bf16 operands / fp32 accumulate on tcgen05 tensor cores (2e-3 mode) */
 
+/* which implementation a configuration runs on (gt_path_kind) */
+#define GT_PATH_FP32_SIMT   0  /* precision fp32: fp32 FMA kernels */
+#define GT_PATH_FUSED_D32   1  /* precision bf16, d_model = 32 encoder-only: fused tcgen05 layer kernels */
+#define GT_PATH_FUSED_D256  2  /* precision bf16, d_model = 256, head_dim 16 / 32, encoder-only: weight-streaming fused kernels */
+#define GT_PATH_GEMM_TC     3  /* precision bf16, every other shape incl. encoder-decoder: per-op kernels, contractions on gemm_tc */
+
 /* Mirrors the constructor arguments of GrooveTransformerEncoder / GrooveTransformer
  * (BGT/models/transformer.py:10-11, :87-88) and params["model"] of train.py:115-143. */
 typedef struct gt_config {
@@ -48,6 +54,8 @@ typedef struct gt_config {
 
 int         gt_version(void);
 const char *gt_last_error(void);
+/* GT_PATH_* for this configuration, or a negative value for an invalid configuration. */
+int         gt_path_kind(const gt_config *cfg);
 
 /* Flat fp32 parameter vector.  Tensors appear in the reference's state_dict order with the `pe`
  * buffers skipped (enumerated in SURVEY.md §8b); each tensor starts on a 16-byte boundary.
@@ -86,6 +94,16 @@ int gt_backward(const gt_config *cfg, const float *params, const float *pe,
 int64_t gt_loss_scratch_floats(int64_t n_seq);
 int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty,
             float *metrics6, float *d_hvo, float grad_scale, float *partials, void *stream);
+
+/* Evaluator metrics — the step right after predict() in the reference's per-epoch evaluation
+ * (GrooveEvaluator/GrooveEvaluator/evaluator.py:189-251 get_hits_accuracies / get_velocity_errors /
+ * get_micro_timing_errors, fed by evaluator.py:171-186 with np.concatenate(model.predict(...), axis=2)).
+ * pred_hvo / gt_hvo are [n_seq,32,3*n_voices] (hits | velocities | offsets).  out receives 3*(n_voices+1) floats:
+ * {hit accuracy, velocity MSE, micro-timing MSE} x {voice 0 .. n_voices-1, Overall}.  partials is scratch of
+ * gt_eval_scratch_floats(n_seq, n_voices) floats (two-stage deterministic sum). */
+int64_t gt_eval_scratch_floats(int64_t n_seq, int n_voices);
+int gt_eval_metrics(const float *pred_hvo, const float *gt_hvo, int64_t n_seq, int n_voices,
+                    float *out, float *partials, void *stream);
 
 /* One fused training step body (BGT/models/train.py:126-138 without the optimizer): forward with
  * dropout, loss + metrics, backward.  `grads` is ZEROED first, then holds dLoss/dparams.
@@ -133,7 +151,8 @@ int gt_grad_bucket_wait(int bucket, void *stream);
  * (all classes); gt_profile_enable(class, max_records) brackets every launch of one kernel class with
  * CUDA events on its stream (0 disables); gt_profile_collect sums their elapsed times and resets.
  * Kernel classes: 1 gemm_f32, 2 attention fwd, 3 attention bwd, 4 layernorm, 5 element-wise, 6 loss,
- * 7 optimizer, 16 tc weight prep, 17 tc layer fwd, 18 tc layer bwd, 19 tc head, 20 tc wgrad, 21 tc input. */
+ * 7 optimizer, 16 tc weight prep, 17 tc layer fwd, 18 tc layer bwd, 19 tc head, 20 tc wgrad, 21 tc input,
+ * 22 gemm_tc (generic tcgen05 GEMM). */
 int64_t gt_launch_count(int kernel_class);
 int     gt_profile_enable(int kernel_class, int max_records);
 int     gt_profile_collect(double *total_ms, int64_t *launches);
@@ -150,6 +169,17 @@ int gt_debug_dropout_mask(uint64_t seed, uint64_t step, int32_t site, float p,
  * D[M,N] = A[M,K] (bf16 bits) * B[N,K]^T (bf16 bits), fp32 out; M multiple of 128. */
 int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k,
                      int variant, void *stream);
+
+/* Test hook for the generic GEMMs: C[m,n] = epi(sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]) on fp32 device buffers.
+ * tc != 0 runs the tcgen05 kernel (operands rounded to bf16, fp32 accumulate), tc == 0 the fp32 SIMT kernel.
+ * flags: bit0 relu, bit1 accumulate (C += v), bit2 atomic (required when split_k_chunk splits K).  bias[N], residual
+ * (ld_res) and mask_pos (ld_mask, mask_scale) may be NULL; drop_p > 0 applies the counter-based dropout of site
+ * `site` at (seed, step) to element (row0 + m) * N + n. */
+int gt_debug_gemm(int tc, const float *a, int64_t sam, int64_t sak, const float *b, int64_t sbn, int64_t sbk,
+                  float *c, int64_t ldc, int64_t m, int64_t n, int64_t k, int flags, const float *bias,
+                  const float *residual, int64_t ld_res, const float *mask_pos, int64_t ld_mask, float mask_scale,
+                  float drop_p, uint64_t seed, uint64_t step, int32_t site, int64_t row0, int64_t split_k_chunk,
+                  void *stream);
 
 /* Micro-benchmark of the tensor pipe: n_mma back-to-back 128 x n x 16 bf16 UMMAs per SM from shared-memory
  * operands; out[0] (device float) = clocks per UMMA.  Used by tools/umma_rate.py. */

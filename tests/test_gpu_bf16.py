@@ -98,8 +98,18 @@ def test_loss_trajectory_bf16_vs_fp32():
     assert traj["fp32"][-1] < traj["fp32"][0]
 
 
-def test_unsupported_shapes_fail_loudly():
+def test_shapes_without_fused_kernels_run_on_gemm_tc():
+    """precision='bf16' is available for every configuration: shapes the fused layer kernels are not instantiated for run the
+    per-op path with their contractions on the generic tcgen05 GEMM (tests/test_gpu_gemm_tc.py), never an fp32 fallback."""
+    import ctypes as C
+    from transformergrooveinfilling_b200 import _lib
     cfg = G.GrooveCfg(64, 4, 64, 1, 0, 16, 27)
-    model, _ = build_model(cfg, dropout=0.0, precision="bf16")
-    with pytest.raises(RuntimeError, match="not available"):
-        model.train_step(*[t.cuda() for t in G.det_batch(cfg, 4)], 1.0)
+    model, P = build_model(cfg, dropout=0.0, precision="bf16")
+    lib = _lib.load()
+    assert lib.gt_path_kind(C.byref(model._cfg())) == _lib.PATH_GEMM_TC
+    n0 = lib.gt_launch_count(22)
+    x, y = G.det_batch(cfg, 4)
+    metrics, _ = model.train_step(x.cuda(), y.cuda(), 1.0)
+    assert lib.gt_launch_count(22) > n0
+    loss6, _, _ = G.train_step_oracle(P, cfg, x, y, 1.0, G.DropCtx(0.0, 0, 0, 0, True))
+    assert abs(float(metrics[0]) - loss6[0]) / abs(loss6[0]) < LOSS_RTOL

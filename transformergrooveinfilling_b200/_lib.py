@@ -11,6 +11,7 @@ import threading
 from . import build as _build
 
 PREC_FP32, PREC_BF16 = 0, 1
+PATH_FP32_SIMT, PATH_FUSED_D32, PATH_FUSED_D256, PATH_GEMM_TC = 0, 1, 2, 3
 T_STEPS = 32
 
 
@@ -32,6 +33,7 @@ _cfgp = C.POINTER(GtConfig)
 SIGNATURES = {
     "gt_version": (C.c_int, []),
     "gt_last_error": (C.c_char_p, []),
+    "gt_path_kind": (C.c_int, [_cfgp]),
     "gt_param_count": (_i64, [_cfgp]),
     "gt_param_layout": (C.c_int, [_cfgp, C.POINTER(_i64), C.POINTER(_i64), C.c_int]),
     "gt_workspace_bytes": (_i64, [_cfgp, _i64, C.c_int]),
@@ -39,6 +41,8 @@ SIGNATURES = {
     "gt_backward": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
     "gt_loss_scratch_floats": (_i64, [_i64]),
     "gt_loss": (C.c_int, [_p, _p, _i64, _f, _p, _p, _f, _p, _p]),
+    "gt_eval_scratch_floats": (_i64, [_i64, C.c_int]),
+    "gt_eval_metrics": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gt_train_step": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
     "gt_predict": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, _p]),
     "gt_predict_variant": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, C.c_int, _p]),
@@ -52,6 +56,8 @@ SIGNATURES = {
     "gt_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gt_profile_collect_class": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gt_debug_dropout_mask": (C.c_int, [_u64, _u64, C.c_int32, _f, _i64, _i64, _p, _p]),
+    "gt_debug_gemm": (C.c_int, [C.c_int, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _i64, _p, _i64,
+                                _f, _f, _u64, _u64, C.c_int32, _i64, _i64, _p]),
     "gt_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, _p]),
     "gt_debug_tc_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
 }

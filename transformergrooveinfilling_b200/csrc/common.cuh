@@ -41,7 +41,7 @@ void set_error(const std::string &msg);
 // ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py roofline) --------
 enum KernelClass {
   KC_NONE = 0, KC_GEMM_F32 = 1, KC_ATTN_FWD = 2, KC_ATTN_BWD = 3, KC_LN = 4, KC_ELEMWISE = 5, KC_LOSS = 6, KC_OPT = 7,
-  KC_TC_PREP = 16, KC_TC_LAYER_FWD = 17, KC_TC_LAYER_BWD = 18, KC_TC_HEAD = 19, KC_TC_WGRAD = 20, KC_TC_INPUT = 21,
+  KC_TC_PREP = 16, KC_TC_LAYER_FWD = 17, KC_TC_LAYER_BWD = 18, KC_TC_HEAD = 19, KC_TC_WGRAD = 20, KC_TC_INPUT = 21, KC_GEMM_TC = 22,
   KC_MAX = 32
 };
 struct LaunchScope {     // RAII: counts the launch; records start/stop events when its class is being profiled
@@ -160,6 +160,12 @@ struct GemmEpi {
 int gemm_f32(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk,
              float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &epi,
              int64_t split_k_chunk, cudaStream_t st);
+// Same contract on the tensor cores (gemm_tc.cu): operands rounded to bf16 while they are staged, fp32 accumulation in
+// TMEM, fp32 result.  gemm_tc_supported: each operand has a contiguous index and M, N, K >= 32.
+bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t M, int64_t N, int64_t K);
+int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk,
+            float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &epi,
+            int64_t split_k_chunk, cudaStream_t st);
 // out[n] += sum_m X[m*ld + n]
 int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStream_t st);
 
@@ -194,6 +200,9 @@ int head_activation_bwd(const float *d_hvo, const float *hvo, float *dlogits, in
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
                  float grad_scale, float *partials, cudaStream_t st);
 int64_t loss_scratch_floats(int64_t n_seq);
+// per-voice hit accuracy / velocity MSE / micro-timing MSE (+ Overall) of predictions against ground truth [n_seq,32,3V]
+int64_t eval_scratch_floats(int64_t n_seq, int n_voices);
+int eval_metrics(const float *pred, const float *gt, int64_t n_seq, int n_voices, float *out, float *partials, cudaStream_t st);
 int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st);
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st);
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,

@@ -1,0 +1,306 @@
+// gemm_tc.cu — generic mixed-precision GEMM on tcgen05 for every shape the fused layer kernels do not cover
+// (d_model other than 32 / 256, head_dim 64 / 128 at d_model = 256, and the whole encoder-decoder model).
+//
+//   C[m,n] = epi( sum_k A(m,k) * B(n,k) )      A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
+//
+// Same contract as gemm_f32 (kernels_simt.cu): fp32 operands and fp32 results in HBM, the same fused epilogue
+// (bias / ReLU / positional encoding / dropout / ReLU-mask / residual / accumulate / split-K atomics).  The
+// operands are rounded to bf16 on their way into shared memory and contracted by UMMA with an fp32 accumulator
+// in TMEM, i.e. exactly the arithmetic of the fused bf16 layer kernels.
+//
+// One CTA = one 128 x BN tile of C and one K range.  Per 64-deep K block all 256 threads load fp32 from global
+// (32-byte chunks, 8 rows x 4 chunks per warp so that the 16-byte st.shared of the packed chunk is conflict-free),
+// convert, and write the canonical no-swizzle core-matrix image; one thread issues the 4 UMMAs of the block and
+// commits them to the stage's mbarrier; two stages, so the loads of block i+1 overlap the MMAs of block i, and two
+// CTAs per SM overlap one CTA's epilogue with the other's main loop.  An operand whose contraction index is NOT the
+// contiguous one in memory (the data-gradient and weight-gradient forms) is staged as the image of its transpose
+// and consumed as an MN-major operand — no transposition in registers or shared memory.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace gt {
+using namespace umma;
+
+namespace {
+
+constexpr int GBM = 128, GBK = 64, GSTG = 2, GTHREADS = 256;
+
+struct GemmTcArgs {
+  const float *A, *B;
+  float *C;
+  int64_t sam, sak, sbn, sbk, ldc, M, N, K, kchunk;
+  int n_tiles;
+  int a_vec, b_vec, c_vec;          // 16-byte accesses are legal on A / B / (C, residual, mask)
+  GemmEpi e;
+};
+
+// image rows r0 + 8-row blocks, CH = 1 << LCH chunks of 8 columns; item i of the tile:
+__device__ __forceinline__ void item_rc(int i, int lch, int &r, int &c) {
+  const int b = i >> 3;
+  c = b & ((1 << lch) - 1);
+  r = (i & 7) | ((b >> lch) << 3);
+}
+
+// fp32 tile -> registers.  Image row i = src row (row0 + i), image column j = src column (col0 + j); columns are the
+// contiguous index in memory, `ld` floats between rows.  Out-of-range elements read as zero.
+template <int ITEMS>
+__device__ __forceinline__ void tile_load(float4 (&v)[ITEMS][2], const float *__restrict__ src, int64_t ld, int rows, int lch,
+                                          int64_t row0, int64_t rows_end, int64_t col0, int64_t cols_end, bool vec, int tid) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int i = tid + it * GTHREADS;
+    v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= (rows << lch)) continue;
+    int r, c;
+    item_rc(i, lch, r, c);
+    const int64_t gr = row0 + r, gc = col0 + (int64_t)c * 8;
+    if (gr >= rows_end || gc >= cols_end) continue;
+    const float *p = src + gr * ld + gc;
+    if (vec && gc + 8 <= cols_end) {
+      v[it][0] = __ldg(reinterpret_cast<const float4 *>(p));
+      v[it][1] = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    } else {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (gc + j < cols_end) ? __ldg(p + j) : 0.f;
+      v[it][0] = make_float4(t[0], t[1], t[2], t[3]);
+      v[it][1] = make_float4(t[4], t[5], t[6], t[7]);
+    }
+  }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void tile_store(const float4 (&v)[ITEMS][2], uint8_t *img, int rows, int lch, int tid) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int i = tid + it * GTHREADS;
+    if (i >= (rows << lch)) continue;
+    int r, c;
+    item_rc(i, lch, r, c);
+    *reinterpret_cast<uint4 *>(img + kmajor_off(r, c * 8, rows)) =
+        make_uint4(pack_bf16(v[it][0].x, v[it][0].y), pack_bf16(v[it][0].z, v[it][0].w), pack_bf16(v[it][1].x, v[it][1].y),
+                   pack_bf16(v[it][1].z, v[it][1].w));
+  }
+}
+
+__device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }
+
+template <int BN>
+__global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g) {
+  constexpr uint32_t A_BYTES = GBM * GBK * 2, B_BYTES = BN * GBK * 2, STG = A_BYTES + B_BYTES;
+  constexpr int AI = GBM * GBK / 8 / GTHREADS, BI = (BN * GBK / 8 + GTHREADS - 1) / GTHREADS;
+  constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_free[GSTG], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)(blockIdx.x / g.n_tiles) * GBM;
+  const int64_t n0 = (int64_t)(blockIdx.x % g.n_tiles) * BN;
+  const int64_t k_begin = (int64_t)blockIdx.y * g.kchunk;
+  const int64_t k_end = min(g.K, k_begin + g.kchunk);
+  const bool a_mn = g.sak != 1, b_mn = g.sbk != 1;
+  const int nrem = (int)min((int64_t)BN, g.N - n0);
+  const int nn = (nrem + 15) & ~15;                       // UMMA N of this tile
+
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  if (tid == 0) {
+    for (int i = 0; i < GSTG; ++i) mbar_init(&bar_free[i], 1);
+    mbar_init(&bar_done, 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_bf16(GBM, nn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+  // image geometry: K-major source -> image [rows = M/N extent] x [64 k columns]; MN-major source -> image [64 k rows] x [extent]
+  const int a_rows = a_mn ? GBK : GBM, a_lch = a_mn ? 4 : 3;
+  const int b_rows = b_mn ? GBK : BN, b_lch = b_mn ? ilog2(BN / 8) : 3;
+  const int64_t a_ld = a_mn ? g.sak : g.sam, b_ld = b_mn ? g.sbk : g.sbn;
+  const uint32_t a_lbo = a_mn ? 128u : (GBM / 8) * 128u, a_sbo = a_mn ? (GBK / 8) * 128u : 128u;
+  const uint32_t b_lbo = b_mn ? 128u : (BN / 8) * 128u, b_sbo = b_mn ? (GBK / 8) * 128u : 128u;
+  const uint32_t a_kstep = a_mn ? 256u : 2u * (GBM / 8) * 128u, b_kstep = b_mn ? 256u : 2u * (BN / 8) * 128u;   // bytes per k16
+
+  const int nkb = (int)((k_end - k_begin + GBK - 1) / GBK);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % GSTG;
+    const int64_t k0 = k_begin + (int64_t)kb * GBK;
+    float4 ra[AI][2], rb[BI][2];
+    if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, k_end, m0, g.M, g.a_vec != 0, tid);
+    else tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, m0, g.M, k0, k_end, g.a_vec != 0, tid);
+    if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, k_end, n0, g.N, g.b_vec != 0, tid);
+    else tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, n0, g.N, k0, k_end, g.b_vec != 0, tid);
+    if (kb >= GSTG) mbar_wait(&bar_free[s], (uint32_t)((kb / GSTG) - 1) & 1u);    // the MMAs that read this stage have retired
+    uint8_t *sA = smem + (uint32_t)s * STG, *sB = sA + A_BYTES;
+    tile_store<AI>(ra, sA, a_rows, a_lch, tid);
+    tile_store<BI>(rb, sB, b_rows, b_lch, tid);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const int64_t krem = k_end - k0;
+      const int nk16 = krem >= GBK ? GBK / 16 : (int)((krem + 15) / 16);
+      const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+      for (int k = 0; k < nk16; ++k)
+        mma_bf16_ss(tmem, make_desc(aA + (uint32_t)k * a_kstep, a_lbo, a_sbo), make_desc(aB + (uint32_t)k * b_kstep, b_lbo, b_sbo), idesc,
+                    (kb | k) > 0 ? 1u : 0u);
+      mma_commit(&bar_free[s]);
+      if (kb + 1 == nkb) mma_commit(&bar_done);
+    }
+  }
+  mbar_wait(&bar_done, 0);
+  fence_after_sync();
+
+  // ---- epilogue: warp w drains TMEM lanes 32 (w & 3) .., 16-column chunks (w >> 2), (w >> 2) + 2, ... ----
+  const GemmEpi &e = g.e;
+  const int q = warp & 3;
+  const int64_t m = m0 + q * 32 + lane;
+  const bool m_ok = m < g.M;
+  const bool first_split = blockIdx.y == 0;
+  for (int cb = (warp >> 2) * 16; cb < nn; cb += 32) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+    tmem_ld_wait();
+    if (!m_ok) continue;
+    const int64_t nb = n0 + cb;
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const int64_t n = nb + j4;
+      if (n >= g.N) break;
+      const bool full = n + 4 <= g.N;
+      float w[4] = {v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]};
+      if (e.bias && first_split) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(e.bias + n + j);
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = fmaxf(w[j], 0.f);
+      }
+      if (e.pe) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(e.pe + (m % T) * g.N + n + j);
+      }
+      if (e.drop.thr) {
+        const uint64_t idx = (uint64_t)((e.drop_row0 + m) * g.N + n);
+        if (full && (idx & 3) == 0) {                     // the four elements are one quad of the site: one hash
+          const uint64_t wq = idx >> 2;
+          uint32_t lo, hi;
+          hash_quad((uint32_t)wq ^ ((uint32_t)(wq >> 32) * 0x85EBCA6Bu), e.drop.key, lo, hi);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = quad_keep(lo, hi, j, e.drop.thr) ? w[j] * e.drop.scale : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] = drop_keep(e.drop.key, e.drop.thr, idx + j) ? w[j] * e.drop.scale : 0.f;
+        }
+      }
+      if (e.mask_pos) {
+        const float *mp = e.mask_pos + m * e.ld_mask + n;
+        if (full && g.c_vec) {
+          const float4 t = __ldg(reinterpret_cast<const float4 *>(mp));
+          w[0] = t.x > 0.f ? w[0] * e.mask_scale : 0.f; w[1] = t.y > 0.f ? w[1] * e.mask_scale : 0.f;
+          w[2] = t.z > 0.f ? w[2] * e.mask_scale : 0.f; w[3] = t.w > 0.f ? w[3] * e.mask_scale : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] = __ldg(mp + j) > 0.f ? w[j] * e.mask_scale : 0.f;
+        }
+      }
+      if (e.residual) {
+        const float *rp = e.residual + m * e.ld_res + n;
+        if (full && g.c_vec) {
+          const float4 t = __ldg(reinterpret_cast<const float4 *>(rp));
+          w[0] += t.x; w[1] += t.y; w[2] += t.z; w[3] += t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(rp + j);
+        }
+      }
+      float *c = g.C + m * g.ldc + n;
+      if (e.atomic) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < g.N) atomicAdd(c + j, w[j]);
+      } else if (full && g.c_vec) {
+        float4 o = make_float4(w[0], w[1], w[2], w[3]);
+        if (e.accumulate) { const float4 t = *reinterpret_cast<const float4 *>(c); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+        *reinterpret_cast<float4 *>(c) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < g.N) c[j] = e.accumulate ? c[j] + w[j] : w[j];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int BN>
+int launch(const GemmTcArgs &g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
+  constexpr size_t smem = (size_t)GSTG * (GBM * GBK * 2 + BN * GBK * 2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    GT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(m_tiles * g.n_tiles), (unsigned)splits);
+  { LaunchScope _ls(KC_GEMM_TC, st);
+    gemm_tc_kernel<BN><<<grid, GTHREADS, smem, st>>>(g); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t M, int64_t N, int64_t K) {
+  // one of the two indices of each operand must be contiguous; tiny contractions / outputs stay on the SIMT kernel
+  if (!((sak == 1) || (sam == 1)) || !((sbk == 1) || (sbn == 1))) return false;
+  return M >= 32 && N >= 32 && K >= 32;
+}
+
+int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk, float *C, int64_t ldc, int64_t M,
+            int64_t N, int64_t K, const GemmEpi &epi, int64_t split_k_chunk, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  GT_CHECK(gemm_tc_supported(sam, sak, sbn, sbk, M, N, K), "gemm_tc: unsupported operand layout / shape");
+  GemmTcArgs g;
+  g.A = A; g.B = B; g.C = C; g.sam = sam; g.sak = sak; g.sbn = sbn; g.sbk = sbk; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.e = epi;
+  int64_t splits = 1;
+  if (split_k_chunk > 0 && K > split_k_chunk) {
+    split_k_chunk = (split_k_chunk + GBK - 1) / GBK * GBK;
+    splits = (K + split_k_chunk - 1) / split_k_chunk;
+    while (splits > 65535) { split_k_chunk *= 2; splits = (K + split_k_chunk - 1) / split_k_chunk; }
+    g.kchunk = split_k_chunk;
+    GT_CHECK(epi.atomic, "split-K GEMM needs an atomic epilogue");
+  } else {
+    g.kchunk = (K + GBK - 1) / GBK * GBK;
+  }
+  const int64_t a_ld = sak != 1 ? sak : sam, b_ld = sbk != 1 ? sbk : sbn;
+  g.a_vec = aligned16(A) && (a_ld % 4 == 0) && (sak != 1 || true);
+  g.b_vec = aligned16(B) && (b_ld % 4 == 0);
+  // a K-major source starts its chunks at k0 (multiple of 64) and an MN-major one at m0 / n0 (multiples of 128 / BN): always 16-byte
+  // aligned relative to the base; K-split offsets are multiples of 64 as well.
+  g.c_vec = aligned16(C) && (ldc % 4 == 0) && (!epi.residual || (aligned16(epi.residual) && epi.ld_res % 4 == 0)) &&
+            (!epi.mask_pos || (aligned16(epi.mask_pos) && epi.ld_mask % 4 == 0));
+  const int64_t m_tiles = (M + GBM - 1) / GBM;
+  GT_CHECK(m_tiles * ((N + 31) / 32) < (int64_t)1 << 31, "gemm_tc: too many tiles");
+  // tile width: the narrowest of {32, 64, 128, 256} that covers N, 256-wide tiles beyond that (a 384 / 768-wide output uses 128 / 256)
+  int bn;
+  if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else if (N <= 256) bn = 256;
+  else bn = (N % 256 == 0 || N % 256 > 128) ? 256 : ((N % 128 == 0 || N % 128 > 64) ? 128 : 256);
+  g.n_tiles = (int)((N + bn - 1) / bn);
+  switch (bn) {
+    case 32: return launch<32>(g, m_tiles, splits, st);
+    case 64: return launch<64>(g, m_tiles, splits, st);
+    case 128: return launch<128>(g, m_tiles, splits, st);
+    default: return launch<256>(g, m_tiles, splits, st);
+  }
+}
+
+}  // namespace gt

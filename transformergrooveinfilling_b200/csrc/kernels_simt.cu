@@ -594,6 +594,68 @@ int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty,
   return 0;
 }
 
+// ---- evaluator metrics: GrooveEvaluator/GrooveEvaluator/evaluator.py:189-251 ----------------------
+// get_hits_accuracies / get_velocity_errors / get_micro_timing_errors over prediction and ground-truth arrays
+// [n_seq, 32, 3 V]: per voice i the mean over examples of (pred == gt).sum(steps) / 32 and of ((gt - pred)^2).mean(steps);
+// "Overall" = the same over the flattened [steps x voices] axis.  Every example has the same 32 steps, so each of these is a
+// plain mean over (example, step) [and voice]; the kernel produces the 3 V channel sums, HBM-bound at 2 x 32 x 3 V x 4 bytes
+// per sequence.  Thread t of a block owns channel t % 3V of row t / 3V: a block reads 9 consecutive rows (243 consecutive
+// floats at V = 9) per pass; partial sums per block, fixed-order double accumulation in the final kernel (deterministic).
+constexpr int EVAL_BLOCK = 256, EVAL_MAX_BLOCKS = 148 * 8;
+static int64_t eval_blocks(int64_t M, int C3) {
+  const int rows_per_pass = EVAL_BLOCK / C3;
+  int64_t b = (M + (int64_t)rows_per_pass * 8 - 1) / ((int64_t)rows_per_pass * 8);
+  return b < 1 ? 1 : (b > EVAL_MAX_BLOCKS ? EVAL_MAX_BLOCKS : b);
+}
+int64_t eval_scratch_floats(int64_t n_seq, int n_voices) { return eval_blocks(n_seq * T, 3 * n_voices) * 3 * n_voices; }
+__global__ void eval_partial_kernel(const float *__restrict__ pred, const float *__restrict__ gt, int64_t M, int V, float *partials) {
+  __shared__ float red[EVAL_BLOCK];
+  const int C3 = 3 * V, rows_per_pass = EVAL_BLOCK / C3, t = threadIdx.x;
+  const int c = t % C3, rl = t / C3;
+  float acc = 0.f;
+  if (rl < rows_per_pass) {
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + rl; r < M; r += (int64_t)gridDim.x * rows_per_pass) {
+      const float p = __ldg(pred + r * C3 + c), g = __ldg(gt + r * C3 + c);
+      acc += c < V ? (p == g ? 1.f : 0.f) : (g - p) * (g - p);
+    }
+  }
+  red[t] = acc;
+  __syncthreads();
+  if (t < C3) {
+    float s = 0.f;
+    for (int j = 0; j < rows_per_pass; ++j) s += red[t + j * C3];
+    partials[(int64_t)blockIdx.x * C3 + t] = s;
+  }
+}
+__global__ void eval_final_kernel(const float *__restrict__ partials, int64_t blocks, int64_t M, int V, float *out) {
+  __shared__ double ch[96];
+  const int C3 = 3 * V, t = threadIdx.x;
+  if (t < C3) {
+    double s = 0.0;
+    for (int64_t b = 0; b < blocks; ++b) s += (double)partials[b * C3 + t];
+    ch[t] = s / (double)M;
+  }
+  __syncthreads();
+  if (t < 3) {                                       // out: [hits | velocity | micro-timing] x (V per-voice values, then Overall)
+    double o = 0.0;
+    for (int i = 0; i < V; ++i) { out[t * (V + 1) + i] = (float)ch[t * V + i]; o += ch[t * V + i]; }
+    out[t * (V + 1) + V] = (float)(o / V);
+  }
+}
+int eval_metrics(const float *pred, const float *gt, int64_t n_seq, int n_voices, float *out, float *partials, cudaStream_t st) {
+  const int64_t M = n_seq * T;
+  GT_CHECK(M > 0, "eval_metrics: empty batch");
+  GT_CHECK(n_voices >= 1 && n_voices <= 32, "eval_metrics: n_voices must be in [1, 32]");
+  const int64_t blocks = eval_blocks(M, 3 * n_voices);
+  { LaunchScope _ls(KC_LOSS, st);
+  eval_partial_kernel<<<(unsigned)blocks, EVAL_BLOCK, 0, st>>>(pred, gt, M, n_voices, partials); }
+  GT_CUDA(cudaGetLastError());
+  { LaunchScope _ls(KC_LOSS, st);
+  eval_final_kernel<<<1, 96, 0, st>>>(partials, blocks, M, n_voices, out); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void shift_right_kernel(const float *__restrict__ y, float *out, int64_t n, int e) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

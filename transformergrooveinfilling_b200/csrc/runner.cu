@@ -220,6 +220,7 @@ struct Ctx {
   const float *pe;
   int64_t n_seq, M;
   bool train;
+  bool tc;                    // precision = bf16 on a shape without fused layer kernels: contractions run on gemm_tc
   uint64_t seed, step;
   int64_t seq0;
   cudaStream_t st;
@@ -235,19 +236,27 @@ struct Ctx {
 
 static const int64_t WGRAD_CHUNK = 2048;
 
+// every contraction of the generic path goes through here: the tcgen05 GEMM when the pass runs in bf16 mode and the shape
+// qualifies (gemm_tc_supported), the fp32 SIMT GEMM otherwise (fp32 mode; K = 16 / 27 input layers and the 27-wide head)
+static int gemm(const Ctx &x, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk, float *C,
+                int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &e, int64_t split_k_chunk) {
+  if (x.tc && gemm_tc_supported(sam, sak, sbn, sbk, M, N, K)) return gemm_tc(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, e, split_k_chunk, x.st);
+  return gemm_f32(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, e, split_k_chunk, x.st);
+}
+
 // out[M,N] = epi(X[M,K] W[N,K]^T)
 static int linear(const Ctx &x, const float *X, int64_t K, const float *W, float *out, int64_t N, GemmEpi e) {
-  return gemm_f32(X, K, 1, W, K, 1, out, N, x.M, N, K, e, 0, x.st);
+  return gemm(x, X, K, 1, W, K, 1, out, N, x.M, N, K, e, 0);
 }
 // dX[M,K] = epi(dY[M,N] W[N,K])
 static int linear_dgrad(const Ctx &x, const float *dY, int64_t N, const float *W, int64_t K, float *dX, GemmEpi e) {
-  return gemm_f32(dY, N, 1, W, 1, K, dX, K, x.M, K, N, e, 0, x.st);
+  return gemm(x, dY, N, 1, W, 1, K, dX, K, x.M, K, N, e, 0);
 }
 // dW[N,K] += dY[M,N]^T X[M,K] ; db[N] += colsum(dY)
 static int linear_wgrad(const Ctx &x, const float *dY, int64_t ldy, int64_t N, const float *X, int64_t ldx, int64_t K,
                         float *dW, float *db) {
   GemmEpi e; e.atomic = 1;
-  GT_TRY(gemm_f32(dY, 1, ldy, X, 1, ldx, dW, K, N, K, x.M, e, WGRAD_CHUNK, x.st));
+  GT_TRY(gemm(x, dY, 1, ldy, X, 1, ldx, dW, K, N, K, x.M, e, WGRAD_CHUNK));
   if (db) GT_TRY(colsum_f32(dY, ldy, x.M, (int)N, db, x.st));
   return 0;
 }
@@ -491,7 +500,7 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
 // ---------------------------------------------------------------------------------------------
 static int linear_rows(const Ctx &x, const float *X, int64_t K, const float *W, float *out, int64_t ldc, int64_t N, int64_t rows,
                        GemmEpi e) {
-  return gemm_f32(X, K, 1, W, K, 1, out, ldc, rows, N, K, e, 0, x.st);
+  return gemm(x, X, K, 1, W, K, 1, out, ldc, rows, N, K, e, 0);
 }
 
 static int predict_decode(const Ctx &x, const Plan &pl, float thres, float *hvo_out) {
@@ -552,8 +561,13 @@ static int make_ctx(Ctx &x, const gt_config *cfg, const float *params, float *gr
   GT_TRY(build_layout(*cfg, x.L));
   x.P = params; x.G = grads; x.pe = pe; x.n_seq = n_seq; x.M = n_seq * T; x.train = train;
   x.seed = seed; x.step = step; x.seq0 = seq0; x.st = (cudaStream_t)stream;
+  x.tc = cfg->precision == GT_PREC_BF16;
   return 0;
 }
+
+// precision = bf16 has two implementations: the fused tcgen05 layer kernels (tc_layers.cu / tc256*.cu) for the shapes they are
+// instantiated for, and the generic path of this file with its contractions on gemm_tc for every other shape.
+static bool fused_layers(const gt_config &c) { return c.precision == GT_PREC_BF16 && tc_shape_supported(c, nullptr); }
 
 static int check_ws(const gt_config *cfg, int64_t n_seq, int mode, void *ws, int64_t ws_bytes, Plan &pl) {
   GT_CHECK(ws != nullptr, "null workspace");
@@ -575,6 +589,13 @@ extern "C" {
 int gt_version(void) { return GT_ABI_VERSION; }
 const char *gt_last_error(void) { return g_err.c_str(); }
 
+int gt_path_kind(const gt_config *cfg) {
+  if (validate_config(cfg)) return -1;
+  if (cfg->precision != GT_PREC_BF16) return GT_PATH_FP32_SIMT;
+  if (!tc_shape_supported(*cfg, nullptr)) return GT_PATH_GEMM_TC;
+  return cfg->d_model == 256 ? GT_PATH_FUSED_D256 : GT_PATH_FUSED_D32;
+}
+
 int64_t gt_param_count(const gt_config *cfg) {
   if (validate_config(cfg)) return -1;
   static thread_local Layout L;
@@ -594,7 +615,7 @@ int gt_param_layout(const gt_config *cfg, int64_t *offsets, int64_t *sizes, int 
 int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode) {
   if (validate_config(cfg)) return -1;
   if (n_seq < 1 || mode < 0 || mode > 2) { set_error("gt_workspace_bytes: bad n_seq / mode"); return -1; }
-  if (cfg->precision == GT_PREC_BF16) return tc_workspace_bytes(*cfg, n_seq, mode == 2 ? 0 : mode);
+  if (fused_layers(*cfg)) return tc_workspace_bytes(*cfg, n_seq, mode == 2 ? 0 : mode);
   static thread_local Plan pl;
   make_plan(*cfg, n_seq, mode, nullptr, pl);
   return pl.bytes;
@@ -606,7 +627,7 @@ int gt_forward(const gt_config *cfg, const float *params, const float *pe, const
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, train != 0, seed, step, seq0, stream));
   GT_CHECK(src != nullptr && hvo != nullptr, "null src / hvo");
-  if (cfg->precision == GT_PREC_BF16)
+  if (fused_layers(*cfg))
     return tc_forward(*cfg, x.L, params, pe, src, tgt_in, n_seq, hvo, ws, ws_bytes, train != 0, seed, step, seq0, x.st);
   static thread_local Plan pl;
   GT_TRY(check_ws(cfg, n_seq, train ? 1 : 0, ws, ws_bytes, pl));
@@ -619,7 +640,7 @@ int gt_backward(const gt_config *cfg, const float *params, const float *pe, cons
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
   GT_CHECK(src != nullptr && hvo != nullptr && d_hvo != nullptr && grads != nullptr, "null src / hvo / d_hvo / grads");
-  if (cfg->precision == GT_PREC_BF16)
+  if (fused_layers(*cfg))
     return tc_backward(*cfg, x.L, params, pe, src, tgt_in, n_seq, hvo, d_hvo, grads, ws, ws_bytes, seed, step, seq0, x.st);
   static thread_local Plan pl;
   GT_TRY(check_ws(cfg, n_seq, 1, ws, ws_bytes, pl));
@@ -635,13 +656,25 @@ int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_pena
   return loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, d_hvo, grad_scale, partials, (cudaStream_t)stream);
 }
 
+int64_t gt_eval_scratch_floats(int64_t n_seq, int n_voices) {
+  if (n_seq < 1 || n_voices < 1 || n_voices > 32) { set_error("gt_eval_scratch_floats: bad n_seq / n_voices"); return -1; }
+  return eval_scratch_floats(n_seq, n_voices);
+}
+
+int gt_eval_metrics(const float *pred_hvo, const float *gt_hvo, int64_t n_seq, int n_voices, float *out, float *partials,
+                    void *stream) {
+  GT_CHECK(pred_hvo && gt_hvo && out && partials, "gt_eval_metrics: null pointer");
+  GT_CHECK(n_seq >= 1, "gt_eval_metrics: empty batch");
+  return eval_metrics(pred_hvo, gt_hvo, n_seq, n_voices, out, partials, (cudaStream_t)stream);
+}
+
 int gt_train_step(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *y,
                   int64_t n_seq, float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws,
                   int64_t ws_bytes, uint64_t seed, uint64_t step, int64_t seq0, void *stream) {
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
   GT_CHECK(src && y && grads && metrics6 && hvo, "gt_train_step: null pointer");
-  if (cfg->precision == GT_PREC_BF16)
+  if (fused_layers(*cfg))
     return tc_train_step(*cfg, x.L, params, pe, src, y, n_seq, hit_loss_penalty, grads, metrics6, hvo, ws, ws_bytes, seed,
                          step, seq0, x.st);
   static thread_local Plan pl;
@@ -668,7 +701,7 @@ int gt_predict_variant(const gt_config *cfg, const float *params, const float *p
   GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, false, 0, 0, 0, stream));
   GT_CHECK(src && hvo_out, "gt_predict: null pointer");
   GT_CHECK(thres >= 0.f && thres <= 1.f, "gt_predict: threshold must be in [0,1]");
-  if (cfg->precision == GT_PREC_BF16)
+  if (fused_layers(*cfg))
     return tc_predict(*cfg, x.L, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, x.st);
   static thread_local Plan pl;
   GT_TRY(check_ws(cfg, n_seq, variant == 1 ? 0 : 2, ws, ws_bytes, pl));
@@ -776,6 +809,20 @@ int gt_profile_collect_class(int kernel_class, double *total_ms, int64_t *launch
   *total_ms = tot;
   *launches = n;
   return 0;
+}
+
+int gt_debug_gemm(int tc, const float *a, int64_t sam, int64_t sak, const float *b, int64_t sbn, int64_t sbk, float *c, int64_t ldc,
+                  int64_t m, int64_t n, int64_t k, int flags, const float *bias, const float *residual, int64_t ld_res,
+                  const float *mask_pos, int64_t ld_mask, float mask_scale, float drop_p, uint64_t seed, uint64_t step, int32_t site,
+                  int64_t row0, int64_t split_k_chunk, void *stream) {
+  GT_CHECK(a && b && c && m >= 0 && n >= 0 && k >= 1, "gt_debug_gemm: bad arguments");
+  GemmEpi e;
+  e.bias = bias; e.relu = flags & 1; e.accumulate = (flags >> 1) & 1; e.atomic = (flags >> 2) & 1;
+  e.residual = residual; e.ld_res = ld_res; e.mask_pos = mask_pos; e.ld_mask = ld_mask; e.mask_scale = mask_scale;
+  const uint32_t thr = drop_threshold(drop_p);
+  if (thr) { e.drop.thr = thr; e.drop.key = site_key(seed, step, site); e.drop.scale = drop_scale(thr); e.drop_row0 = row0; }
+  if (tc) return gemm_tc(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
+  return gemm_f32(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
 }
 
 int gt_debug_umma_rate(int n, int n_mma, int ksteps, float *out, void *stream) {
