@@ -1,7 +1,8 @@
 """groove_b200 — B200-native (sm_100a) implementation of the Transformer Groove Infilling training
 and inference step, behind the reference's ``BaseGrooveTransformers`` module API."""
 from .modules import GrooveTransformer, GrooveTransformerEncoder
+from .evaluator import HVOMetrics, hvo_metrics_vector
 from .training import FusedAdam, FusedSGD, calculate_loss, initialize_model, train_loop
 
 __all__ = ["GrooveTransformer", "GrooveTransformerEncoder", "calculate_loss", "initialize_model", "train_loop",
-           "FusedSGD", "FusedAdam"]
+           "FusedSGD", "FusedAdam", "HVOMetrics", "hvo_metrics_vector"]

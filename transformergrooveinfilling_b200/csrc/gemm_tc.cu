@@ -30,7 +30,7 @@ struct GemmTcArgs {
   float *C;
   int64_t sam, sak, sbn, sbk, ldc, M, N, K, kchunk;
   int n_tiles;
-  int a_vec, b_vec, c_vec;          // 16-byte accesses are legal on A / B / (C, residual, mask)
+  int a_vec, b_vec;                 // 16-byte loads are legal on A / B
   GemmEpi e;
 };
 
@@ -153,81 +153,71 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   mbar_wait(&bar_done, 0);
   fence_after_sync();
 
-  // ---- epilogue: warp w drains TMEM lanes 32 (w & 3) .., 16-column chunks (w >> 2), (w >> 2) + 2, ... ----
+  // ---- epilogue ----
+  // Warp w drains TMEM lanes 32 (w & 3) .. in 32-column chunks (w >> 2), (w >> 2) + 2, ...  Phase 1 (lane = row, the TMEM
+  // mapping): bias, ReLU, dropout with one hash per quad.  The chunk then goes through a padded per-warp shared-memory
+  // buffer (the operand stages are free: every MMA has retired) so that phase 2 runs with lane = column: every access to
+  // C, the residual and the ReLU mask is a 128-byte row segment per warp instruction instead of 32 scattered 16-byte ones.
   const GemmEpi &e = g.e;
   const int q = warp & 3;
-  const int64_t m = m0 + q * 32 + lane;
-  const bool m_ok = m < g.M;
+  const int64_t mw0 = m0 + q * 32;                        // first row of this warp
   const bool first_split = blockIdx.y == 0;
-  for (int cb = (warp >> 2) * 16; cb < nn; cb += 32) {
-    float v[16];
-    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+  float *buf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
+  for (int cb = (warp >> 2) * 32; cb < nn; cb += 64) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
     tmem_ld_wait();
-    if (!m_ok) continue;
     const int64_t nb = n0 + cb;
-#pragma unroll
-    for (int j4 = 0; j4 < 16; j4 += 4) {
-      const int64_t n = nb + j4;
-      if (n >= g.N) break;
-      const bool full = n + 4 <= g.N;
-      float w[4] = {v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]};
+    {
+      const int64_t m = mw0 + lane;
       if (e.bias && first_split) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(e.bias + n + j);
+        for (int j = 0; j < 32; ++j) if (nb + j < g.N) v[j] += __ldg(e.bias + nb + j);
       }
       if (e.relu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = fmaxf(w[j], 0.f);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (e.pe) {
+      if (e.drop.thr && !e.pe && m < g.M) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(e.pe + (m % T) * g.N + n + j);
-      }
-      if (e.drop.thr) {
-        const uint64_t idx = (uint64_t)((e.drop_row0 + m) * g.N + n);
-        if (full && (idx & 3) == 0) {                     // the four elements are one quad of the site: one hash
-          const uint64_t wq = idx >> 2;
-          uint32_t lo, hi;
-          hash_quad((uint32_t)wq ^ ((uint32_t)(wq >> 32) * 0x85EBCA6Bu), e.drop.key, lo, hi);
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int64_t n = nb + j4;
+          if (n >= g.N) break;
+          const uint64_t idx = (uint64_t)((e.drop_row0 + m) * g.N + n);
+          if (n + 4 <= g.N && (idx & 3) == 0) {             // the four elements are one quad of the site: one hash
+            const uint64_t wq = idx >> 2;
+            uint32_t lo, hi;
+            hash_quad((uint32_t)wq ^ ((uint32_t)(wq >> 32) * 0x85EBCA6Bu), e.drop.key, lo, hi);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] = quad_keep(lo, hi, j, e.drop.thr) ? w[j] * e.drop.scale : 0.f;
-        } else {
+            for (int j = 0; j < 4; ++j) v[j4 + j] = quad_keep(lo, hi, j, e.drop.thr) ? v[j4 + j] * e.drop.scale : 0.f;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] = drop_keep(e.drop.key, e.drop.thr, idx + j) ? w[j] * e.drop.scale : 0.f;
+            for (int j = 0; j < 4; ++j)
+              if (n + j < g.N) v[j4 + j] = drop_keep(e.drop.key, e.drop.thr, idx + j) ? v[j4 + j] * e.drop.scale : 0.f;
+          }
         }
       }
-      if (e.mask_pos) {
-        const float *mp = e.mask_pos + m * e.ld_mask + n;
-        if (full && g.c_vec) {
-          const float4 t = __ldg(reinterpret_cast<const float4 *>(mp));
-          w[0] = t.x > 0.f ? w[0] * e.mask_scale : 0.f; w[1] = t.y > 0.f ? w[1] * e.mask_scale : 0.f;
-          w[2] = t.z > 0.f ? w[2] * e.mask_scale : 0.f; w[3] = t.w > 0.f ? w[3] * e.mask_scale : 0.f;
-        } else {
+    }
+    __syncwarp();                                           // the previous chunk's phase 2 has finished reading buf
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] = __ldg(mp + j) > 0.f ? w[j] * e.mask_scale : 0.f;
+    for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int64_t n = nb + lane;
+    if (n < g.N) {
+      const int rows = (int)min((int64_t)32, g.M - mw0);
+      for (int i = 0; i < rows; ++i) {
+        const int64_t m = mw0 + i;
+        float w = buf[i * 33 + lane];
+        if (e.pe) {
+          w += __ldg(e.pe + (m % T) * g.N + n);
+          if (e.drop.thr) w = drop_keep(e.drop.key, e.drop.thr, (uint64_t)((e.drop_row0 + m) * g.N + n)) ? w * e.drop.scale : 0.f;
         }
-      }
-      if (e.residual) {
-        const float *rp = e.residual + m * e.ld_res + n;
-        if (full && g.c_vec) {
-          const float4 t = __ldg(reinterpret_cast<const float4 *>(rp));
-          w[0] += t.x; w[1] += t.y; w[2] += t.z; w[3] += t.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (n + j < g.N) w[j] += __ldg(rp + j);
-        }
-      }
-      float *c = g.C + m * g.ldc + n;
-      if (e.atomic) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (n + j < g.N) atomicAdd(c + j, w[j]);
-      } else if (full && g.c_vec) {
-        float4 o = make_float4(w[0], w[1], w[2], w[3]);
-        if (e.accumulate) { const float4 t = *reinterpret_cast<const float4 *>(c); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-        *reinterpret_cast<float4 *>(c) = o;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (n + j < g.N) c[j] = e.accumulate ? c[j] + w[j] : w[j];
+        if (e.mask_pos) w = __ldg(e.mask_pos + m * e.ld_mask + n) > 0.f ? w * e.mask_scale : 0.f;
+        if (e.residual) w += __ldg(e.residual + m * e.ld_res + n);
+        float *c = g.C + m * g.ldc + n;
+        if (e.atomic) atomicAdd(c, w);
+        else if (e.accumulate) *c += w;
+        else *c = w;
       }
     }
   }
@@ -279,12 +269,10 @@ int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sb
     g.kchunk = (K + GBK - 1) / GBK * GBK;
   }
   const int64_t a_ld = sak != 1 ? sak : sam, b_ld = sbk != 1 ? sbk : sbn;
-  g.a_vec = aligned16(A) && (a_ld % 4 == 0) && (sak != 1 || true);
+  g.a_vec = aligned16(A) && (a_ld % 4 == 0);
   g.b_vec = aligned16(B) && (b_ld % 4 == 0);
   // a K-major source starts its chunks at k0 (multiple of 64) and an MN-major one at m0 / n0 (multiples of 128 / BN): always 16-byte
   // aligned relative to the base; K-split offsets are multiples of 64 as well.
-  g.c_vec = aligned16(C) && (ldc % 4 == 0) && (!epi.residual || (aligned16(epi.residual) && epi.ld_res % 4 == 0)) &&
-            (!epi.mask_pos || (aligned16(epi.mask_pos) && epi.ld_mask % 4 == 0));
   const int64_t m_tiles = (M + GBM - 1) / GBM;
   GT_CHECK(m_tiles * ((N + 31) / 32) < (int64_t)1 << 31, "gemm_tc: too many tiles");
   // tile width: the narrowest of {32, 64, 128, 256} that covers N, 256-wide tiles beyond that (a 384 / 768-wide output uses 128 / 256)
