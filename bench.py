@@ -418,7 +418,8 @@ def main():
     # ---- per-kernel-class breakdown: 3 extra steps with every class bracketed by events (outside the timed regions) ----
     kernels = {}
     names = {1: "gemm_f32", 2: "attention_fwd_f32", 3: "attention_bwd_f32", 4: "layernorm", 5: "elementwise", 6: "loss", 7: "optimizer",
-             16: "tc_weight_prep", 17: "tc_layer_fwd", 18: "tc_layer_bwd", 20: "tc_wgrad", 22: "gemm_tc"}
+             16: "tc_weight_prep", 17: "tc_layer_fwd", 18: "tc_layer_bwd", 19: "fused_tail (final LN + head + loss)", 20: "tc_wgrad",
+             21: "fused_stem (input layer + pe)", 22: "gemm_tc"}
     lib.gt_profile_enable(-1, 8192)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

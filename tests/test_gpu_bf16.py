@@ -54,7 +54,7 @@ def test_train_forward_with_dropout(name):
     assert np.abs(v.cpu().numpy() - rv.numpy()).max() < 2e-2
 
 
-@pytest.mark.parametrize("name,n", [("c1", 5), ("c1", 64), ("c2", 4), ("c2", 64), ("f48_h32", 3), ("f96_h1", 6)])
+@pytest.mark.parametrize("name,n", [("c1", 5), ("c1", 64), ("c2", 4), ("c2", 64), ("c5enc", 9), ("f48_h32", 3), ("f96_h1", 6)])
 def test_train_step_matches_oracle(name, n):
     cfg, pen, p = SHAPES[name]
     model, P = build_model(cfg, dropout=p, precision="bf16")
@@ -76,6 +76,50 @@ def test_train_step_matches_oracle(name, n):
     # bf16 operand rounding is independent per sample: the gradient error is ~3 % of each tensor's max at
     # n=4 and falls as 1/sqrt(n) (tools/diag_bf16_grad.py: 0.8 % median at n=64); a logic error would not shrink
     assert worst[1] < (4e-2 if n >= 64 else 0.2), f"gradient mismatch {worst}"
+
+
+@pytest.mark.parametrize("name,n", [("c1", 5), ("c5enc", 9)])
+def test_autograd_path_equals_fused_step_bf16(name, n):
+    """The reference's call sequence model(x) -> calculate_loss -> loss.backward() and the single-call fused step run the
+    same layer kernels but different tail kernels (edge32.cu: the fused step folds calculate_loss into the tail forward
+    and hands dL/dlogits to the tail backward; the autograd path applies the activation derivative from (d_hvo, hvo)):
+    with the same dropout masks they must agree to fp32 re-ordering noise."""
+    from transformergrooveinfilling_b200 import calculate_loss
+    cfg, pen, p = SHAPES[name]
+    x, y = [t.cuda() for t in G.det_batch(cfg, n)]
+    m1, _ = build_model(cfg, dropout=p, precision="bf16")
+    m2, _ = build_model(cfg, dropout=p, precision="bf16")
+    m1.set_seed(5, step=3, seq0=0).train(); m2.set_seed(5, step=3, seq0=0).train()
+    metrics, hvo = m1.train_step(x, y, pen)
+    pred = m2(x)
+    out = calculate_loss(pred, y, None, None, pen)
+    out[0].backward()
+    np.testing.assert_allclose(torch.cat(pred, 2).detach().cpu().numpy(), hvo.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.array([out[0].item(), *out[1:]]), metrics.cpu().numpy(), rtol=2e-6)
+    g1, g2 = grads_by_name(m1), grads_by_name(m2)
+    for k in g1:
+        scale = float(g1[k].abs().max()) + 1e-12
+        assert float((g2[k] - g1[k]).abs().max()) / scale < 1e-4, k
+
+
+def test_edge_gradients_against_oracle():
+    """The ends of the path (input layer + positional encoding, final LayerNorm + head + loss and their gradients) are fp32
+    kernels (edge32.cu); with one layer in between, the head / final-norm gradients only see the bf16 rounding of that
+    layer's output and are compared with the oracle at a tighter tolerance than the layer gradients."""
+    cfg = G.GrooveCfg(32, 4, 16, 1, 0, 27, 27)
+    model, P = build_model(cfg, dropout=0.0, precision="bf16")
+    model.train()
+    x, y = G.det_batch(cfg, 33)
+    metrics, _ = model.train_step(x.cuda(), y.cuda(), 0.6)
+    loss6, grads, _ = G.train_step_oracle(P, cfg, x, y, 0.6, G.DropCtx(0.0, 0, 0, 0, True))
+    assert abs(float(metrics[0]) - loss6[0]) / abs(loss6[0]) < LOSS_RTOL
+    gg = grads_by_name(model)
+    for k in ("OutputLayer.Linear.bias", "OutputLayer.Linear.weight", "Encoder.Encoder.norm.weight", "Encoder.Encoder.norm.bias"):
+        scale = float(grads[k].abs().max())
+        assert float((gg[k] - grads[k]).abs().max()) / scale < 5e-2, k
+    for k in ("InputLayerEncoder.Linear.weight", "InputLayerEncoder.Linear.bias"):
+        scale = float(grads[k].abs().max())
+        assert float((gg[k] - grads[k]).abs().max()) / scale < 0.1, k
 
 
 def test_loss_trajectory_bf16_vs_fp32():

@@ -200,6 +200,22 @@ int head_activation_bwd(const float *d_hvo, const float *hvo, float *dlogits, in
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
                  float grad_scale, float *partials, cudaStream_t st);
 int64_t loss_scratch_floats(int64_t n_seq);
+int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metrics6, cudaStream_t st);
+// fused ends of the d_model = 32 path (edge32.cu): input layer + positional encoding + dropout ; final LayerNorm + output
+// head + activations (+ calculate_loss) ; and their backward passes, one HBM-bound kernel each
+int64_t edge32_loss_partials(int64_t n_seq);
+int edge32_stem_fwd(const float *src, int E, const float *W, const float *b, const float *pe, float *x0, int64_t M, const Drop &drop,
+                    int64_t row0, cudaStream_t st);
+int edge32_stem_bwd(const float *dx0, const float *src, int E, const float *W, const float *b, float *gW, float *gb, int64_t M,
+                    const Drop &drop, int64_t row0, cudaStream_t st);
+int edge32_tail_fwd(const float *x, const float *gamma, const float *beta, const float *Wout, const float *bout, float *hvo,
+                    float *mean, float *rstd, int64_t M, float thres, cudaStream_t st);
+int edge32_tail_fwd_loss(const float *x, const float *gamma, const float *beta, const float *Wout, const float *bout, float *hvo,
+                         float *mean, float *rstd, int64_t M, const float *y, float penalty, float *dlog, float *partials,
+                         float *metrics6, cudaStream_t st);
+int edge32_tail_bwd(const float *d_in, const float *hvo, const float *x, const float *mean, const float *rstd, const float *gamma,
+                    const float *beta, const float *Wout, float *dx, float *gW, float *gb, float *gg, float *gbe, int64_t M,
+                    cudaStream_t st);
 // per-voice hit accuracy / velocity MSE / micro-timing MSE (+ Overall) of predictions against ground truth [n_seq,32,3V]
 int64_t eval_scratch_floats(int64_t n_seq, int n_voices);
 int eval_metrics(const float *pred, const float *gt, int64_t n_seq, int n_voices, float *out, float *partials, cudaStream_t st);

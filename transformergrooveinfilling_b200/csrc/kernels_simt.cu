@@ -580,6 +580,12 @@ __global__ void loss_final_kernel(const float *__restrict__ partials, int64_t bl
     metrics6[5] = (float)mo;
   }
 }
+int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metrics6, cudaStream_t st) {
+  { LaunchScope _ls(KC_LOSS, st);
+  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, metrics6); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
                  float grad_scale, float *partials, cudaStream_t st) {
   int64_t M = n_seq * T;

@@ -124,6 +124,9 @@ struct TcPlan {
   uint32_t img_stride;
 };
 
+// the fused stem / tail kernels of edge32.cu cover the reference's two source widths (16 MSO features, 27 hvo channels)
+static bool tc_fused_edges(const gt_config &c) { return c.d_model == 32 && (c.e_src == 16 || c.e_src == 27) && c.e_tgt == 27; }
+
 static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, TcPlan &P) {
   memset(&P, 0, sizeof(P));
   const int64_t M = n_seq * T, d = c.d_model;
@@ -136,7 +139,8 @@ static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base
   P.img_stride = (tc_img(c.d_model, c.dim_ff).total + 255u) & ~255u;
   P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
   const bool train = mode == 1;
-  P.r0 = reinterpret_cast<float *>(take(M * d * 4));
+  const bool fused = tc_fused_edges(c);        // edge32.cu: no r0 / z / g0 / d_hvo intermediates
+  if (!fused) P.r0 = reinterpret_cast<float *>(take(M * d * 4));
   if (train) {
     for (int l = 0; l <= c.n_enc; ++l) P.x[l] = reinterpret_cast<float *>(take(M * d * 4));
     for (int l = 0; l < c.n_enc; ++l) {
@@ -149,14 +153,14 @@ static void tc_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base
     float *a = reinterpret_cast<float *>(take(M * d * 4)), *b = reinterpret_cast<float *>(take(M * d * 4));
     for (int l = 0; l <= c.n_enc; ++l) P.x[l] = (l & 1) ? b : a;
   }
-  P.z = reinterpret_cast<float *>(take(M * d * 4));
+  if (!fused) P.z = reinterpret_cast<float *>(take(M * d * 4));
   if (train) {
-    P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
-    P.loss_partials = reinterpret_cast<float *>(take(loss_scratch_floats(n_seq) * 4));
+    if (!fused) P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
+    P.loss_partials = reinterpret_cast<float *>(take((fused ? edge32_loss_partials(n_seq) : loss_scratch_floats(n_seq)) * 4));
     P.dlog = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
     P.dxa = reinterpret_cast<float *>(take(M * d * 4));
     P.dxb = reinterpret_cast<float *>(take(M * d * 4));
-    P.g0 = reinterpret_cast<float *>(take(M * d * 4));
+    if (!fused) P.g0 = reinterpret_cast<float *>(take(M * d * 4));
   }
   P.bytes = off;
 }
@@ -234,18 +238,33 @@ static int tc_prep(const TcCtx &x, const TcPlan &pl) {
   return tc_prep_weights(a, x.st);
 }
 
-static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres) {
+// y != nullptr: the tail also evaluates calculate_loss (metrics6) and leaves dL/dlogits in pl.dlog (fused edges only)
+static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres,
+                          const float *y = nullptr, float penalty = 0.f, float *metrics6 = nullptr) {
   const int d = x.c.d_model;
+  const bool fused = tc_fused_edges(x.c);
   GT_TRY(tc_prep(x, pl));
-  GemmEpi e; e.bias = x.P + x.L->in_enc_b; e.relu = 1;
-  GT_TRY(gemm_f32(src, x.c.e_src, 1, x.P + x.L->in_enc_w, x.c.e_src, 1, pl.r0, d, x.M, d, x.c.e_src, e, 0, x.st));
-  GT_TRY(pe_dropout_fwd(pl.r0, x.pe, pl.x[0], x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  if (fused) {
+    GT_TRY(edge32_stem_fwd(src, x.c.e_src, x.P + x.L->in_enc_w, x.P + x.L->in_enc_b, x.pe, pl.x[0], x.M, x.drop(SITE_IN_ENC),
+                           x.seq0 * T, x.st));
+  } else {
+    GemmEpi e; e.bias = x.P + x.L->in_enc_b; e.relu = 1;
+    GT_TRY(gemm_f32(src, x.c.e_src, 1, x.P + x.L->in_enc_w, x.c.e_src, 1, pl.r0, d, x.M, d, x.c.e_src, e, 0, x.st));
+    GT_TRY(pe_dropout_fwd(pl.r0, x.pe, pl.x[0], x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  }
   for (int l = 0; l < x.c.n_enc; ++l) {
     TcLayerArgs a = tc_layer_args(x, pl, l);
     a.x_in = pl.x[l]; a.x_out = pl.x[l + 1];
     a.u1 = save ? pl.u1[l] : nullptr; a.u2 = save ? pl.u2[l] : nullptr;
     GT_TRY(tc_layer_fwd(d, a, x.st));
   }
+  if (fused) {
+    const float *xl = pl.x[x.c.n_enc], *g = x.P + x.L->enc_norm_g, *b = x.P + x.L->enc_norm_b, *w = x.P + x.L->out_w, *bo = x.P + x.L->out_b;
+    if (y != nullptr)
+      return edge32_tail_fwd_loss(xl, g, b, w, bo, hvo, pl.mf, pl.rf, x.M, y, penalty, pl.dlog, pl.loss_partials, metrics6, x.st);
+    return edge32_tail_fwd(xl, g, b, w, bo, hvo, pl.mf, pl.rf, x.M, thres, x.st);
+  }
+  GT_CHECK(y == nullptr, "tc_forward_all: fused loss needs the fused edge kernels");
   Drop none;
   GT_TRY(ln_fwd(pl.x[x.c.n_enc], nullptr, x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, nullptr, pl.z, pl.mf, pl.rf, x.M, d,
                 none, 0, x.st));
@@ -260,15 +279,22 @@ static int tc_wgrad(const TcCtx &x, const float *dY, int64_t N, const float *X, 
   return colsum_f32(dY, N, x.M, (int)N, db, x.st);
 }
 
+// hvo == nullptr: d_hvo already holds dL/dlogits (left by the fused tail + loss forward)
 static int tc_backward_all(const TcCtx &x, const TcPlan &pl, const float *src, const float *hvo, const float *d_hvo) {
   const int d = x.c.d_model, E = x.c.e_tgt;
+  const bool fused = tc_fused_edges(x.c);
   Drop none;
-  GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
-  GT_TRY(tc_wgrad(x, pl.dlog, E, pl.z, d, x.G + x.L->out_w, x.G + x.L->out_b));
-  GemmEpi e0;
-  GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxa, d, x.M, d, E, e0, 0, x.st));
-  GT_TRY(ln_bwd(pl.dxa, pl.x[x.c.n_enc], pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxb, nullptr, x.G + x.L->enc_norm_g,
-                x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+  if (fused) {
+    GT_TRY(edge32_tail_bwd(d_hvo, hvo, pl.x[x.c.n_enc], pl.mf, pl.rf, x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, x.P + x.L->out_w,
+                           pl.dxb, x.G + x.L->out_w, x.G + x.L->out_b, x.G + x.L->enc_norm_g, x.G + x.L->enc_norm_b, x.M, x.st));
+  } else {
+    GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
+    GT_TRY(tc_wgrad(x, pl.dlog, E, pl.z, d, x.G + x.L->out_w, x.G + x.L->out_b));
+    GemmEpi e0;
+    GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxa, d, x.M, d, E, e0, 0, x.st));
+    GT_TRY(ln_bwd(pl.dxa, pl.x[x.c.n_enc], pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxb, nullptr, x.G + x.L->enc_norm_g,
+                  x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+  }
   grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
   float *cur = pl.dxb, *oth = pl.dxa;
   for (int l = x.c.n_enc - 1; l >= 0; --l) {
@@ -278,8 +304,13 @@ static int tc_backward_all(const TcCtx &x, const TcPlan &pl, const float *src, c
     grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     float *t = cur; cur = oth; oth = t;
   }
-  GT_TRY(pe_dropout_bwd(cur, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
-  GT_TRY(tc_wgrad(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  if (fused) {
+    GT_TRY(edge32_stem_bwd(cur, src, x.c.e_src, x.P + x.L->in_enc_w, x.P + x.L->in_enc_b, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b,
+                           x.M, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  } else {
+    GT_TRY(pe_dropout_bwd(cur, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+    GT_TRY(tc_wgrad(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  }
   grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
   return 0;
 }
@@ -323,6 +354,10 @@ int tc_train_step(const gt_config &c, const Layout &L, const float *params, cons
   TcCtx x;
   tc_ctx(x, c, L, params, grads, pe, n_seq, true, seed, step, seq0, st);
   GT_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * sizeof(float), st));
+  if (tc_fused_edges(c)) {
+    GT_TRY(tc_forward_all(x, pl, src, hvo, true, -1.f, y, penalty, metrics6));
+    return tc_backward_all(x, pl, src, nullptr, pl.dlog);
+  }
   GT_TRY(tc_forward_all(x, pl, src, hvo, true, -1.f));
   GT_TRY(loss_fwd_bwd(hvo, y, n_seq, penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, st));
   return tc_backward_all(x, pl, src, hvo, pl.d_hvo);
