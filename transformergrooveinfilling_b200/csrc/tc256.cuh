@@ -116,6 +116,7 @@ struct T256Args {
   float *dx;
   uint8_t *da2_img, *da1_img, *dh_img, *dqkv_img;   // bf16 images written for the weight-gradient kernel
   uint8_t *dctx_scratch;                 // per-CTA 64 KB scratch (L2 resident)
+  float *park_scratch;                   // per-CTA fp32 tile (128 KB, L2 resident): LayerNorm-input gradients du2 / du1
   const uint8_t *img;                    // this layer's stage streams (forward, then backward), T256_REP replicas
   uint32_t img_rep_stride;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;

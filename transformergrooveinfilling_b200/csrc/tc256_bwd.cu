@@ -3,10 +3,10 @@
 // weight-gradient kernel that contracts the saved bf16 operand images over all tokens.
 //
 // data-gradient kernel, per tile of 128 tokens (torch/nn/modules/transformer.py:951-956 backwards):
-//   B0  LayerNorm2 backward (dy, u2)            -> du2 (parked in dx), da2 = du2 * mask2 (bf16 image)
+//   B0  LayerNorm2 backward (dy, u2)            -> du2 (parked, per-CTA scratch), da2 = du2 * mask2 (bf16 image)
 //   B1  dH(c)  = da2 W2[:, chunk c]             UMMA 128x64x256      B2  relu/dropout mask from the saved H image
 //   B3  dx1   += dH(c) W1[chunk c, :]           UMMA 128x256x64
-//   B4  LayerNorm1 backward (du2 + dx1, u1)     -> du1 (parked in dx), da1 = du1 * mask1 (bf16 image)
+//   B4  LayerNorm1 backward (du2 + dx1, u1)     -> du1 (parked), da1 = du1 * mask1 (bf16 image)
 //   B5  dctx   = da1 Wo                         UMMA 128x256x256  -> bf16 -> per-CTA scratch (L2)
 //   B6  per head group: recompute q|k|v (UMMA 128x192x256), attention backward on mma.sync fragments,
 //       dx_in += dqkv_g Wqkv[group rows, :]     UMMA 128x256x192
@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float attn_scale = rsqrtf((float)DH) * 1.4426950408889634f;
     uint8_t *scratch = a.dctx_scratch + (size_t)blockIdx.x * T256_TILE_IMG;
+    // du2 / du1 are parked in a per-CTA fp32 tile that is rewritten every tile, so it stays L2-resident and its lines are
+    // (mostly) never written back to HBM; parking them in the tile's own dx rows cost two extra HBM round trips per tile
+    float *park = a.park_scratch + (size_t)blockIdx.x * T256_TILE_F32;
     uint32_t it = 0;
     int ndbg = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
           }
         };
-        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, p_g2, dx_t, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
+        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, p_g2, park, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
                     g_g2, g_be2, g_b2, sStatA, sStatB, row, part, lane);
       }
       fence_async_smem();
@@ -567,14 +570,14 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(dx_t + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4));
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(park + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4));
             o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
           }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] += f[j];
         };
-        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, p_g1, dx_t, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
+        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, p_g1, park, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
                     g_g1, g_be1, g_bo, sStatA, sStatB, row, part, lane);
       }
       fence_async_smem();
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
         float4 pv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pv[j] = __ldcg(reinterpret_cast<const float4 *>(dx_t + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4));
+        for (int j = 0; j < 4; ++j) pv[j] = __ldcg(reinterpret_cast<const float4 *>(park + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4));
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j)

@@ -18,6 +18,7 @@ struct T256Plan {
   uint8_t *x1img[TC_MAX_LAYERS], *ctximg[TC_MAX_LAYERS], *himg[TC_MAX_LAYERS];
   float *d_hvo, *loss_partials, *dlog, *dxrm, *dxrm2, *g0, *dxa, *dxb;
   uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch, *wg_jobs;
+  float *park_scratch;
   int64_t bytes;
   int n_tiles;
 };
@@ -66,6 +67,7 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
     P.dhimg = reinterpret_cast<uint8_t *>(take(th));
     P.dqkvimg = reinterpret_cast<uint8_t *>(take(3 * ti));
     P.dctx_scratch = reinterpret_cast<uint8_t *>(take((int64_t)160 * T256_TILE_IMG));
+    P.park_scratch = reinterpret_cast<float *>(take((int64_t)160 * T256_TILE_F32 * 4));
     P.wg_jobs = reinterpret_cast<uint8_t *>(take(T256_WG_JOBBUF));
   } else {
     uint8_t *ia = reinterpret_cast<uint8_t *>(take(ti)), *ib = reinterpret_cast<uint8_t *>(take(ti));
@@ -189,7 +191,7 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
     T256Args a = t256_layer_args(x, pl, l);
     a.x_img_in = pl.ximg[l]; a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.dy = cur; a.dx = oth;
     a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l];
-    a.da2_img = pl.da2img; a.da1_img = pl.da1img; a.dh_img = pl.dhimg; a.dqkv_img = pl.dqkvimg; a.dctx_scratch = pl.dctx_scratch;
+    a.da2_img = pl.da2img; a.da1_img = pl.da1img; a.dh_img = pl.dhimg; a.dqkv_img = pl.dqkvimg; a.dctx_scratch = pl.dctx_scratch; a.park_scratch = pl.park_scratch;
     GT_TRY(t256_layer_bwd(a, x.st));
     T256WgradArgs w;
     memset(&w, 0, sizeof(w));

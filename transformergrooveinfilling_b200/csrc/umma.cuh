@@ -181,6 +181,11 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                : "memory");
 }
 
+// asynchronous L2 prefetch of a contiguous global range (bytes: multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
