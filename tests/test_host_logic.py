@@ -162,3 +162,27 @@ def test_input_pipelines_refuse_a_cpu_device():
         HostBatchPrefetcher("cpu", (4, 32, 16), (4, 32, 27))
     with pytest.raises(RuntimeError):
         DeviceResidentLoader(torch.zeros(4, 32, 16), torch.zeros(4, 32, 27), 2, "cpu")
+
+
+def test_sample_sweep_and_params_from_config():
+    """sweep.py host logic: draws follow the wandb spec of configs/InfillingClosedHH_sweep.yaml and map to train.py's params."""
+    from transformergrooveinfilling_b200.sweep import params_from_config, sample_sweep
+    spec = {"method": "random", "parameters": {
+        "batch_size": {"values": [16, 32, 64]}, "d_model": {"values": [16, 32, 64, 128]}, "dim_feedforward": {"values": [16, 512]},
+        "dropout": {"distribution": "uniform", "min": 0.1, "max": 0.3}, "optimizer_algorithm": {"value": "sgd"},
+        "learning_rate": {"distribution": "uniform", "min": 0, "max": 0.1}, "n_heads": {"values": [1, 2, 4, 8, 16, 32]},
+        "num_encoder_decoder_layers": {"distribution": "int_uniform", "min": 6, "max": 12}, "epochs": {"value": 100},
+        "encoder_only": {"value": 1}, "experiment": {"value": "InfillingClosedHH"},
+        "hit_loss_penalty": {"distribution": "uniform", "min": 0, "max": 1}}}
+    a, b = sample_sweep(spec, 20, seed=3), sample_sweep(spec, 20, seed=3)
+    assert a == b and len(a) == 20
+    for c in a:
+        assert c["d_model"] % c["n_heads"] == 0 and 6 <= c["num_encoder_decoder_layers"] <= 12
+        assert 0.1 <= c["dropout"] <= 0.3 and c["optimizer_algorithm"] == "sgd"
+        p = params_from_config(c, "cuda", "bf16")
+        assert p["model"]["num_encoder_layers"] == c["num_encoder_decoder_layers"] and p["model"]["num_decoder_layers"] == 0
+        assert p["model"]["embedding_size_src"] == 16 and p["model"]["embedding_size_tgt"] == 27 and p["model"]["max_len"] == 32
+        assert p["training"]["batch_size"] == c["batch_size"] and p["load_model"] is None
+    sym = dict(a[0], experiment="InfillingClosedHH_Symbolic", encoder_only=0)
+    p = params_from_config(sym)
+    assert p["model"]["embedding_size_src"] == 27 and p["model"]["num_decoder_layers"] == sym["num_encoder_decoder_layers"]

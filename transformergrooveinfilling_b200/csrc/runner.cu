@@ -23,7 +23,7 @@ static std::vector<int> g_prof_cls;
 static size_t g_prof_used = 0;
 
 LaunchScope::LaunchScope(int c, cudaStream_t s) : cls(c), st(s), slot(-1) {
-  ++g_launches[c];
+  __atomic_fetch_add(&g_launches[c], 1, __ATOMIC_RELAXED);     // members of a sweep launch from several host threads
   if ((c == g_prof_class || g_prof_class == -1) && g_prof_used < g_prof_events.size()) {
     slot = (int)g_prof_used++;
     g_prof_cls[slot] = c;

@@ -1,0 +1,185 @@
+"""Sweep packing: train several hyper-parameter variants of one wandb sweep concurrently on ONE GPU.
+
+The reference is used through ``wandb agent`` random sweeps (``configs/InfillingClosedHH_sweep.yaml:1-37``,
+``configs/InfillingKicksAndSnares_sweep_2.yaml``): every agent run is one ``train.py`` process with one small model and a
+batch of 16..512 grooves.  At those batch sizes a step of the fused path is a chain of ~40 short kernels that occupies a
+handful of the 148 SMs (a tile is 4 sequences: batch 16 = 4 CTAs), so one run leaves the GPU > 90 % idle.  ``SweepPacker``
+gives every member of the sweep its own model, fused optimizer, device-resident loader and CUDA stream and drives each
+member from its own host thread: the library calls release the GIL (ctypes), so the members' kernel chains are enqueued
+concurrently and the hardware scheduler runs them side by side.  No member sees another member's state: results are those
+of running each configuration alone (checked in ``tests/test_gpu_sweep.py``).
+
+``sample_sweep`` draws configurations from a wandb sweep specification the way the agent's ``method: random`` does
+(``values`` / ``value`` / ``distribution: uniform | int_uniform``), and ``params_from_config`` builds the ``params`` dict of
+``train.py:114-143`` from one drawn configuration, so ``initialize_model`` is used unchanged.
+"""
+from __future__ import annotations
+
+import random
+import threading
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from .pipeline import DeviceResidentLoader
+from .training import initialize_model
+
+
+def sample_sweep(sweep: Dict, n: int, seed: int = 0) -> List[Dict]:
+    """``n`` random draws from a wandb sweep spec (the ``parameters`` block of configs/*_sweep*.yaml).  Draws whose
+    ``d_model`` is not divisible by ``n_heads`` are rejected, as ``torch.nn.MultiheadAttention`` rejects them in the
+    reference (the agent would record a crashed run)."""
+    rng = random.Random(seed)
+    spec = sweep.get("parameters", sweep)
+    out: List[Dict] = []
+    guard = 0
+    while len(out) < n:
+        guard += 1
+        if guard > 1000 * max(n, 1):
+            raise ValueError("sweep specification admits no valid configuration")
+        cfg = {}
+        for name, p in spec.items():
+            if "value" in p:
+                cfg[name] = p["value"]
+            elif "values" in p:
+                cfg[name] = rng.choice(list(p["values"]))
+            elif p.get("distribution") == "uniform":
+                cfg[name] = rng.uniform(float(p["min"]), float(p["max"]))
+            elif p.get("distribution") == "int_uniform":
+                cfg[name] = rng.randint(int(p["min"]), int(p["max"]))
+            else:
+                raise ValueError(f"sweep parameter '{name}': unsupported specification {p}")
+        if "d_model" in cfg and "n_heads" in cfg and cfg["d_model"] % cfg["n_heads"] != 0:
+            continue
+        out.append(cfg)
+    return out
+
+
+def params_from_config(cfg: Dict, device="cuda", precision: Optional[str] = None) -> Dict:
+    """The ``params`` dict train.py:114-143 builds from ``wandb.config`` (same keys, same derivations)."""
+    encoder_only = cfg.get("encoder_only", 1)
+    layers = cfg["num_encoder_decoder_layers"]
+    model = {
+        "experiment": cfg.get("experiment", "InfillingClosedHH"),
+        "encoder_only": encoder_only,
+        "optimizer": cfg.get("optimizer_algorithm", "sgd"),
+        "d_model": cfg["d_model"],
+        "n_heads": cfg["n_heads"],
+        "dim_feedforward": cfg["dim_feedforward"],
+        "dropout": cfg["dropout"],
+        "num_encoder_layers": layers,
+        "num_decoder_layers": 0 if encoder_only else layers,
+        "max_len": 32,
+        "embedding_size_src": 16 if cfg.get("experiment", "InfillingClosedHH") != "InfillingClosedHH_Symbolic" else 27,
+        "embedding_size_tgt": 27,
+        "device": device,
+    }
+    if precision is not None:
+        model["precision"] = precision
+    return {"model": model,
+            "training": {"learning_rate": cfg["learning_rate"], "batch_size": cfg["batch_size"],
+                         "hit_loss_penalty": cfg["hit_loss_penalty"]},
+            "load_model": cfg.get("load_model")}
+
+
+class SweepMember:
+    """One configuration of the sweep: model + optimizer + loader + stream + the metrics it has produced."""
+
+    def __init__(self, params: Dict, inputs, outputs, device, seed: int):
+        self.params = params
+        self.model, self.optimizer, self.epoch = initialize_model(params)
+        self.model.set_seed(seed).train()
+        self.penalty = float(params["training"]["hit_loss_penalty"])
+        self.encoder_only = bool(params["model"]["encoder_only"])
+        self.loader = DeviceResidentLoader(inputs, outputs, params["training"]["batch_size"], device, shuffle=True, seed=seed)
+        self.stream = torch.cuda.Stream(device=device)
+        self.metrics: List[torch.Tensor] = []       # one [6] device tensor per step: loss, acc, ppl, bce, mse_v, mse_o
+        self.steps = 0
+        self.sequences = 0
+
+    def run_steps(self, n_steps: int) -> None:
+        """Enqueue ``n_steps`` optimizer steps on this member's stream (wrapping around epochs of its loader)."""
+        if not self.encoder_only:
+            raise NotImplementedError("SweepPacker drives encoder-only members (every shipped sweep sets encoder_only: 1)")
+        with torch.cuda.stream(self.stream):
+            done = 0
+            while done < n_steps:
+                for x, y, _idx in self.loader:
+                    m, _ = self.model.train_step(x, y, self.penalty)
+                    self.optimizer.step()
+                    self.metrics.append(m)
+                    self.sequences += x.shape[0]
+                    done += 1
+                    if done == n_steps:
+                        break
+                else:
+                    self.epoch += 1
+            self.steps += n_steps
+
+    def history(self) -> torch.Tensor:
+        """[steps, 6] host tensor of the per-step metrics (synchronises this member's stream)."""
+        self.stream.synchronize()
+        return torch.stack(self.metrics).cpu() if self.metrics else torch.empty(0, 6)
+
+
+class SweepPacker:
+    """Runs the members of a sweep concurrently on one device.
+
+    ``configs``: drawn sweep configurations (``sample_sweep``) or ready ``params`` dicts; ``inputs`` / ``outputs``: the
+    processed dataset (``[S, 32, E_src]`` / ``[S, 32, 27]``), copied to the device once and shared read-only by all members.
+    ``concurrent=False`` runs the members one after the other on the same streams (the baseline the packing is measured
+    against: what separate agent runs sharing the GPU in turn would get)."""
+
+    def __init__(self, configs: Sequence[Dict], inputs, outputs, device="cuda", precision: Optional[str] = None, seed: int = 0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("SweepPacker runs on a CUDA device — the groove_b200 path has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        x = torch.as_tensor(inputs, dtype=torch.float32).to(self.device).contiguous()
+        y = torch.as_tensor(outputs, dtype=torch.float32).to(self.device).contiguous()
+        self.members: List[SweepMember] = []
+        for i, cfg in enumerate(configs):
+            params = cfg if "model" in cfg and "training" in cfg else params_from_config(cfg, str(self.device), precision)
+            self.members.append(SweepMember(params, x, y, self.device, seed + i))
+        torch.cuda.synchronize(self.device)          # dataset copy and parameter initialisation ran on the default stream
+
+    def run(self, n_steps: int, concurrent: bool = True, on_error: Optional[Callable] = None) -> None:
+        """Every member takes ``n_steps`` optimizer steps.  Returns once all steps are ENQUEUED; ``synchronize()`` or
+        ``history()`` waits for the device."""
+        if not concurrent:
+            for m in self.members:
+                m.run_steps(n_steps)
+                m.stream.synchronize()           # one member at a time on the device, not just on the host
+            return
+        errors: List[BaseException] = []
+
+        def work(m: SweepMember):
+            try:
+                torch.cuda.set_device(self.device)
+                m.run_steps(n_steps)
+            except BaseException as e:      # surfaced on the caller's thread below
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(m,), daemon=True) for m in self.members]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            if on_error is not None:
+                on_error(errors)
+            else:
+                raise errors[0]
+
+    def synchronize(self) -> None:
+        for m in self.members:
+            m.stream.synchronize()
+
+    def history(self) -> List[torch.Tensor]:
+        return [m.history() for m in self.members]
+
+    def best(self) -> int:
+        """Index of the member with the lowest last loss (the sweep's ``metric: {goal: minimize, name: loss}``)."""
+        last = [float(h[-1, 0]) if h.numel() else float("inf") for h in self.history()]
+        return min(range(len(last)), key=last.__getitem__)
