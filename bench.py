@@ -438,7 +438,9 @@ def main():
         if c.value:
             kernels[nm] = {"launches_per_step": c.value / 3, "ms_per_step": t.value / 3, "share": t.value / ms3}
             if path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256) and cls in fl_cls:
-                kernels[nm]["tflops"] = fl_cls[cls] / (t.value / c.value / 1e3) / 1e12
+                # one launch per encoder layer carries fl_cls[cls] (the weight-gradient class also holds the two small
+                # input-layer / head launches of edge256.cu: their time is included, their FLOPs are not)
+                kernels[nm]["tflops"] = fl_cls[cls] * w["L"] / (t.value / 3 / 1e3) / 1e12
     lib.gt_profile_collect(C.byref(tot_ms), C.byref(cnt))
     lib.gt_profile_enable(0, 0)
     line = {

@@ -120,3 +120,37 @@ def test_loss_trajectory_bf16_vs_fp32():
         traj[prec] = np.array(t)
     np.testing.assert_allclose(traj["bf16"], traj["fp32"], rtol=2 * LOSS_RTOL)
     assert traj["fp32"][-1] < traj["fp32"][0]
+
+
+@pytest.mark.parametrize("name,n", [("c4_l2", 6), ("h16_f192_sym", 9)])
+def test_autograd_path_equals_fused_step(name, n):
+    """model(x) -> calculate_loss -> loss.backward() against the single-call fused step: same layer kernels, different tail
+    kernels (edge256.cu: the fused step folds calculate_loss into the tail forward and hands dL/dlogits to the tail backward,
+    the autograd path applies the activation derivative from (d_hvo, hvo)); same dropout masks -> fp32 re-ordering noise only."""
+    from transformergrooveinfilling_b200 import calculate_loss
+    cfg, pen, p = SHAPES[name]
+    x, y = [t.cuda() for t in G.det_batch(cfg, n)]
+    m1, _ = build_model(cfg, dropout=p, precision="bf16")
+    m2, _ = build_model(cfg, dropout=p, precision="bf16")
+    m1.set_seed(5, step=3, seq0=0).train(); m2.set_seed(5, step=3, seq0=0).train()
+    metrics, hvo = m1.train_step(x, y, pen)
+    pred = m2(x)
+    out = calculate_loss(pred, y, None, None, pen)
+    out[0].backward()
+    np.testing.assert_allclose(torch.cat(pred, 2).detach().cpu().numpy(), hvo.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.array([out[0].item(), *out[1:]]), metrics.cpu().numpy(), rtol=2e-6)
+    g1, g2 = grads_by_name(m1), grads_by_name(m2)
+    for k in g1:
+        scale = float(g1[k].abs().max()) + 1e-12
+        assert float((g2[k] - g1[k]).abs().max()) / scale < 2e-4, k
+
+
+def test_predict_threshold_d256():
+    cfg, pen, p = SHAPES["c4_l2"]
+    model, P = build_model(cfg, dropout=p, precision="bf16")
+    x, y = G.det_batch(cfg, 10)
+    h, v, o = model.predict(x.cuda())
+    assert h.dtype == torch.int64 and set(h.unique().tolist()) <= {0, 1} and not model.training
+    oh, ov, oo = G.predict_encoder_only(P, cfg, x)
+    assert (h.cpu() == oh).float().mean() >= 0.97
+    assert np.abs(v.cpu().numpy() - ov.numpy()).max() < 2e-2

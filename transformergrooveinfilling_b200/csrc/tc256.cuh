@@ -140,6 +140,20 @@ int t256_layer_fwd(const T256Args &a, cudaStream_t st);
 int t256_layer_bwd(const T256Args &a, cudaStream_t st);
 constexpr int64_t T256_WG_JOBBUF = 16384;   // device bytes for the weight-gradient job list
 int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st);
+int t256_wgrad_pair(const uint8_t *a_img, const uint8_t *b_img, int N, float *out, int n_tiles, void *job_buf, cudaStream_t st);
+// fused ends of the stack on the tile-native layouts (edge256.cu)
+int64_t edge256_loss_partials();
+int edge256_stem_fwd(const float *src, int E, const float *W, const float *b, const float *pe, uint8_t *x_img, int64_t M, int n_tiles,
+                     const Drop &drop, int64_t row0, cudaStream_t st);
+int edge256_stem_bwd(const float *dx_tiled, const float *src, int E, const float *W, const float *b, uint8_t *g_img, uint8_t *src_img,
+                     float *scratch, void *job_buf, float *gW, float *gb, int64_t M, int n_tiles, const Drop &drop, int64_t row0,
+                     cudaStream_t st);
+int edge256_tail_fwd(const uint8_t *x_img, const float *gamma, const float *beta, const float *Wout, const float *bout, float *hvo, float *mean,
+                     float *rstd, int64_t M, int n_tiles, float thres, const float *y, float penalty, float *dlog, float *partials,
+                     float *metrics6, cudaStream_t st);
+int edge256_tail_bwd(const float *d_in, const float *hvo, const uint8_t *x_img, const float *mean, const float *rstd, const float *gamma,
+                     const float *beta, const float *Wout, float *dx_tiled, uint8_t *dl_img, float *scratch, void *job_buf, float *gW,
+                     float *gb, float *gg, float *gbe, int64_t M, int n_tiles, cudaStream_t st);
 int t256_debug_umma_rate(int N, int n_mma, int ksteps, float *out, cudaStream_t st);
 // layout conversion at the stack boundaries
 int t256_to_image(const float *rowmajor, uint8_t *img, int64_t M, int n_tiles, cudaStream_t st);

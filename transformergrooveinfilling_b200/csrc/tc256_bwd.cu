@@ -870,4 +870,31 @@ int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st) {
   return 0;
 }
 
+// out[256][N] (row stride N) += sum over tiles of A_tile^T B_tile: A = [128 x 256] images (tile stride 64 KB), B = [128 x N] images
+// (tile stride 128 * N * 2 bytes), N in {16, 32, ..., 256}.  Used by edge256.cu for the parameter gradients of the input layer and
+// of the final LayerNorm + head.
+int t256_wgrad_pair(const uint8_t *a_img, const uint8_t *b_img, int N, float *out, int n_tiles, void *job_buf, cudaStream_t st) {
+  static thread_local T256WgradLaunch L;
+  GT_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "t256_wgrad_pair: N must be a multiple of 16 in [16, 256]");
+  const int sms = t256_num_sms();
+  int splits = sms / 2;
+  if (splits > n_tiles) splits = n_tiles;
+  if (splits < 1) splits = 1;
+  int nj = 0;
+  for (int mb = 0; mb < 2; ++mb)
+    for (int s = 0; s < splits; ++s) {
+      T256WJob &j = L.jobs[nj++];
+      j.a_img = a_img; j.a_tile_stride = (uint32_t)T256_TILE_IMG; j.a_off = (uint32_t)mb * 32768u;
+      j.b_img = b_img; j.b_tile_stride = (uint32_t)(128 * N * 2); j.b_bytes = (uint32_t)(128 * N * 2); j.N = N;
+      j.out = out + (size_t)mb * 128 * N; j.ld_m = N; j.ld_n = 1;
+      j.tile0 = (int)((int64_t)n_tiles * s / splits); j.tile1 = (int)((int64_t)n_tiles * (s + 1) / splits);
+    }
+  GT_CUDA(cudaMemcpyAsync(job_buf, L.jobs, sizeof(T256WJob) * nj, cudaMemcpyHostToDevice, st));
+  GT_CUDA(cudaFuncSetAttribute(t256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 98304));
+  { LaunchScope _ls(KC_TC_WGRAD, st);
+    t256_wgrad_kernel<<<nj, 192, 2 * 98304, st>>>(reinterpret_cast<const T256WJob *>(job_buf)); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace gt

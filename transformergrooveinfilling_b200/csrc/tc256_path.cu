@@ -19,9 +19,14 @@ struct T256Plan {
   float *d_hvo, *loss_partials, *dlog, *dxrm, *dxrm2, *g0, *dxa, *dxb;
   uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch, *wg_jobs;
   float *park_scratch;
+  uint8_t *dlimg, *srcimg;                        // fused edges: [128 x 32] bf16 images per tile
+  float *edge_scratch;                            // fused edges: T [256][32] + sums [64] (tail), Tin [256][32] (stem)
   int64_t bytes;
   int n_tiles;
 };
+
+// the fused stem / tail kernels of edge256.cu cover the reference's two source widths (16 MSO features, 27 hvo channels)
+static bool t256_fused_edges(const gt_config &c) { return (c.e_src == 16 || c.e_src == 27) && c.e_tgt == 27; }
 
 static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, T256Plan &P) {
   memset(&P, 0, sizeof(P));
@@ -39,10 +44,13 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
   P.img_stride = ((t256_img_bytes(c.dim_ff) + 255u) & ~255u) * T256_REP;
   P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
   const bool train = mode == 1;
-  P.r0 = reinterpret_cast<float *>(take(M * d * 4));
-  P.x0rm = reinterpret_cast<float *>(take(M * d * 4));
-  P.xLrm = reinterpret_cast<float *>(take(M * d * 4));
-  P.z = reinterpret_cast<float *>(take(M * d * 4));
+  const bool fused = t256_fused_edges(c);
+  if (!fused) {
+    P.r0 = reinterpret_cast<float *>(take(M * d * 4));
+    P.x0rm = reinterpret_cast<float *>(take(M * d * 4));
+    P.xLrm = reinterpret_cast<float *>(take(M * d * 4));
+    P.z = reinterpret_cast<float *>(take(M * d * 4));
+  }
   P.mf = reinterpret_cast<float *>(take(M * 4));
   P.rf = reinterpret_cast<float *>(take(M * 4));
   if (train) {
@@ -54,12 +62,18 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
       P.ctximg[l] = reinterpret_cast<uint8_t *>(take(ti));
       P.himg[l] = reinterpret_cast<uint8_t *>(take(th));
     }
-    P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
-    P.loss_partials = reinterpret_cast<float *>(take(loss_scratch_floats(n_seq) * 4));
+    if (!fused) P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
+    P.loss_partials = reinterpret_cast<float *>(take((loss_scratch_floats(n_seq) + edge256_loss_partials()) * 4));
     P.dlog = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
-    P.dxrm = reinterpret_cast<float *>(take(M * d * 4));
-    P.dxrm2 = reinterpret_cast<float *>(take(M * d * 4));
-    P.g0 = reinterpret_cast<float *>(take(M * d * 4));
+    if (!fused) {
+      P.dxrm = reinterpret_cast<float *>(take(M * d * 4));
+      P.dxrm2 = reinterpret_cast<float *>(take(M * d * 4));
+      P.g0 = reinterpret_cast<float *>(take(M * d * 4));
+    } else {
+      P.dlimg = reinterpret_cast<uint8_t *>(take((int64_t)n_tiles * 8192));
+      P.srcimg = reinterpret_cast<uint8_t *>(take((int64_t)n_tiles * 8192));
+      P.edge_scratch = reinterpret_cast<float *>(take((int64_t)(2 * 256 * 32 + 64) * 4));
+    }
     P.dxa = reinterpret_cast<float *>(take(tf));
     P.dxb = reinterpret_cast<float *>(take(tf));
     P.da2img = reinterpret_cast<uint8_t *>(take(ti));
@@ -147,19 +161,31 @@ static int t256_prep(const T256Ctx &x, const T256Plan &pl) {
   return t256_prep_weights(a, x.st);
 }
 
-static int t256_forward_all(const T256Ctx &x, const T256Plan &pl, const float *src, float *hvo, bool save, float thres) {
+// y != nullptr: the tail also evaluates calculate_loss (metrics6) and leaves dL/dlogits in pl.dlog (fused edges only)
+static int t256_forward_all(const T256Ctx &x, const T256Plan &pl, const float *src, float *hvo, bool save, float thres,
+                            const float *y = nullptr, float penalty = 0.f, float *metrics6 = nullptr) {
   const int d = x.c.d_model, L = x.c.n_enc;
+  const bool fused = t256_fused_edges(x.c);
   GT_TRY(t256_prep(x, pl));
-  GemmEpi e; e.bias = x.P + x.L->in_enc_b; e.relu = 1;
-  GT_TRY(gemm_f32(src, x.c.e_src, 1, x.P + x.L->in_enc_w, x.c.e_src, 1, pl.r0, d, x.M, d, x.c.e_src, e, 0, x.st));
-  GT_TRY(pe_dropout_fwd(pl.r0, x.pe, pl.x0rm, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
-  GT_TRY(t256_to_image(pl.x0rm, pl.ximg[0], x.M, pl.n_tiles, x.st));
+  if (fused) {
+    GT_TRY(edge256_stem_fwd(src, x.c.e_src, x.P + x.L->in_enc_w, x.P + x.L->in_enc_b, x.pe, pl.ximg[0], x.M, pl.n_tiles,
+                            x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  } else {
+    GemmEpi e; e.bias = x.P + x.L->in_enc_b; e.relu = 1;
+    GT_TRY(gemm_f32(src, x.c.e_src, 1, x.P + x.L->in_enc_w, x.c.e_src, 1, pl.r0, d, x.M, d, x.c.e_src, e, 0, x.st));
+    GT_TRY(pe_dropout_fwd(pl.r0, x.pe, pl.x0rm, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+    GT_TRY(t256_to_image(pl.x0rm, pl.ximg[0], x.M, pl.n_tiles, x.st));
+  }
   for (int l = 0; l < L; ++l) {
     T256Args a = t256_layer_args(x, pl, l);
     a.x_img_in = pl.ximg[l]; a.x_img_out = pl.ximg[l + 1];
     if (save) { a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; }
     GT_TRY(t256_layer_fwd(a, x.st));
   }
+  if (fused)
+    return edge256_tail_fwd(pl.ximg[L], x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, x.P + x.L->out_w, x.P + x.L->out_b, hvo, pl.mf, pl.rf,
+                            x.M, pl.n_tiles, thres, y, penalty, pl.dlog, pl.loss_partials, metrics6, x.st);
+  GT_CHECK(y == nullptr, "t256_forward_all: fused loss needs the fused edge kernels");
   GT_TRY(t256_from_image(pl.ximg[L], pl.xLrm, x.M, x.st));
   Drop none;
   GT_TRY(ln_fwd(pl.xLrm, nullptr, x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, nullptr, pl.z, pl.mf, pl.rf, x.M, d, none, 0, x.st));
@@ -176,15 +202,24 @@ static int t256_wgrad_f32(const T256Ctx &x, const float *dY, int64_t N, const fl
 
 static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *src, const float *hvo, const float *d_hvo) {
   const int d = x.c.d_model, E = x.c.e_tgt, L = x.c.n_enc;
+  const bool fused = t256_fused_edges(x.c);
   Drop none;
-  GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
-  GT_TRY(t256_wgrad_f32(x, pl.dlog, E, pl.z, d, x.G + x.L->out_w, x.G + x.L->out_b));
-  GemmEpi e0;
-  GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxrm, d, x.M, d, E, e0, 0, x.st));
-  GT_TRY(ln_bwd(pl.dxrm, pl.xLrm, pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxrm2, nullptr, x.G + x.L->enc_norm_g,
-                x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
-  grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
-  GT_TRY(t256_to_tiled(pl.dxrm2, pl.dxa, x.M, pl.n_tiles, x.st));
+  if (fused) {
+    // hvo == nullptr: d_hvo already holds dL/dlogits (left by the fused tail + loss forward)
+    GT_TRY(edge256_tail_bwd(d_hvo, hvo, pl.ximg[L], pl.mf, pl.rf, x.P + x.L->enc_norm_g, x.P + x.L->enc_norm_b, x.P + x.L->out_w, pl.dxa,
+                            pl.dlimg, pl.edge_scratch, pl.wg_jobs, x.G + x.L->out_w, x.G + x.L->out_b, x.G + x.L->enc_norm_g,
+                            x.G + x.L->enc_norm_b, x.M, pl.n_tiles, x.st));
+    grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
+  } else {
+    GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
+    GT_TRY(t256_wgrad_f32(x, pl.dlog, E, pl.z, d, x.G + x.L->out_w, x.G + x.L->out_b));
+    GemmEpi e0;
+    GT_TRY(gemm_f32(pl.dlog, E, 1, x.P + x.L->out_w, 1, d, pl.dxrm, d, x.M, d, E, e0, 0, x.st));
+    GT_TRY(ln_bwd(pl.dxrm, pl.xLrm, pl.mf, pl.rf, x.P + x.L->enc_norm_g, pl.dxrm2, nullptr, x.G + x.L->enc_norm_g,
+                  x.G + x.L->enc_norm_b, x.M, d, none, 0, x.st));
+    grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
+    GT_TRY(t256_to_tiled(pl.dxrm2, pl.dxa, x.M, pl.n_tiles, x.st));
+  }
   float *cur = pl.dxa, *oth = pl.dxb;
   for (int l = L - 1; l >= 0; --l) {
     const LayerP &p = x.L->enc[l];
@@ -203,9 +238,16 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
     grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     float *t = cur; cur = oth; oth = t;
   }
-  GT_TRY(t256_from_tiled(cur, pl.dxrm, x.M, x.st));
-  GT_TRY(pe_dropout_bwd(pl.dxrm, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
-  GT_TRY(t256_wgrad_f32(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  if (fused) {
+    // the g image reuses the da2 image buffer: the last layer-backward / weight-gradient launches that read it are done (stream order)
+    GT_TRY(edge256_stem_bwd(cur, src, x.c.e_src, x.P + x.L->in_enc_w, x.P + x.L->in_enc_b, pl.da2img, pl.srcimg,
+                            pl.edge_scratch + 256 * 32 + 64, pl.wg_jobs, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b, x.M, pl.n_tiles,
+                            x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+  } else {
+    GT_TRY(t256_from_tiled(cur, pl.dxrm, x.M, x.st));
+    GT_TRY(pe_dropout_bwd(pl.dxrm, pl.r0, pl.g0, x.M, d, x.drop(SITE_IN_ENC), x.seq0 * T, x.st));
+    GT_TRY(t256_wgrad_f32(x, pl.g0, d, src, x.c.e_src, x.G + x.L->in_enc_w, x.G + x.L->in_enc_b));
+  }
   grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
   return 0;
 }
@@ -243,6 +285,10 @@ int t256_train_step(const gt_config &c, const Layout &L, const float *params, co
   T256Ctx x;
   t256_ctx(x, c, L, params, grads, pe, n_seq, true, seed, step, seq0, st);
   GT_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * sizeof(float), st));
+  if (t256_fused_edges(c)) {
+    GT_TRY(t256_forward_all(x, pl, src, hvo, true, -1.f, y, penalty, metrics6));
+    return t256_backward_all(x, pl, src, nullptr, pl.dlog);
+  }
   GT_TRY(t256_forward_all(x, pl, src, hvo, true, -1.f));
   GT_TRY(loss_fwd_bwd(hvo, y, n_seq, penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, st));
   return t256_backward_all(x, pl, src, hvo, pl.d_hvo);
