@@ -144,6 +144,7 @@ struct Plan {
   float *dxa, *dxb, *du, *da, *dh, *dqkv, *dctx, *dlog, *dmem, *dqc, *dkvc, *g0;
   // KV-cached decode (mode 2): per-layer key/value caches + one-token-per-sequence step buffers
   float *kv_self[64], *kv_cross[64];
+  uint8_t *enc_img;                  // hybrid encoder (fused d_model = 32 layer kernels inside an encoder-decoder model): weight images
   float *s_tok, *s_ya, *s_yb, *s_x1, *s_x2, *s_q, *s_ctx, *s_a, *s_hd, *s_z, *s_hvo;
   int64_t bytes;
 };
@@ -159,7 +160,12 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
   };
   const bool train = mode == 1;
   const bool decode = mode == 2 && c.n_dec > 0;
+  const bool hybrid = c.n_dec > 0 && tc_encoder_supported(c);
+  auto layer_slim = [&](LayerBuf &b) {                // hybrid encoder layer: the fused kernels keep only u1 / u2 and the output
+    b.u1 = train ? take(M * d) : nullptr; b.u2 = train ? take(M * d) : nullptr; b.x2 = take(M * d);
+  };
   auto layer = [&](LayerBuf &b, bool dec) {
+    if (!dec && hybrid) return layer_slim(b);
     b.qkv = take(M * 3 * d); b.ctx = take(M * d);
     b.u1 = train ? take(M * d) : nullptr; b.m1 = train ? take(M) : nullptr; b.r1 = train ? take(M) : nullptr;
     b.x1 = take(M * d); b.hd = take(M * F);
@@ -177,8 +183,13 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
   } else {
     layer(P.enc[0], false);
     for (int l = 1; l < c.n_enc; ++l) P.enc[l] = P.enc[0];
+    if (hybrid && c.n_enc > 1) {                      // the fused layer kernels ping-pong between two output buffers
+      float *b2 = take(M * d);
+      for (int l = 1; l < c.n_enc; l += 2) P.enc[l].x2 = b2;
+    }
   }
   P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
+  if (hybrid) P.enc_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_enc + 3) / 4));
   if (decode) {
     const int64_t n = n_seq;
     for (int l = 0; l < c.n_dec; ++l) { P.kv_self[l] = take(M * 2 * d); P.kv_cross[l] = take(M * 2 * d); }
@@ -327,11 +338,23 @@ static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin)
 }
 
 static int encoder_fwd(const Ctx &x, const Plan &pl, const float *src) {
-  GT_TRY(input_layer_fwd(x, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, pl.r0e, pl.x0e, SITE_IN_ENC));
   const float *cur = pl.x0e;
-  for (int l = 0; l < x.c.n_enc; ++l) {
-    GT_TRY(enc_layer_fwd(x, pl, l, cur));
-    cur = pl.enc[l].x2;
+  if (pl.enc_img != nullptr) {
+    // hybrid: the encoder stack of an encoder-decoder model on the fused stem + fused tcgen05 layer kernels
+    GT_TRY(tc_enc_prep(x.c, x.L, x.P, pl.enc_img, x.st));
+    GT_TRY(edge32_stem_fwd(src, x.c.e_src, x.P + x.L.in_enc_w, x.P + x.L.in_enc_b, x.pe, pl.x0e, x.M, x.drop(SITE_IN_ENC), x.row0(),
+                           x.st));
+    for (int l = 0; l < x.c.n_enc; ++l) {
+      GT_TRY(tc_enc_layer_fwd(x.c, x.L, x.P, pl.enc_img, l, cur, pl.enc[l].x2, pl.enc[l].u1, pl.enc[l].u2, x.n_seq, x.train, x.seed,
+                              x.step, x.seq0, x.st));
+      cur = pl.enc[l].x2;
+    }
+  } else {
+    GT_TRY(input_layer_fwd(x, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, pl.r0e, pl.x0e, SITE_IN_ENC));
+    for (int l = 0; l < x.c.n_enc; ++l) {
+      GT_TRY(enc_layer_fwd(x, pl, l, cur));
+      cur = pl.enc[l].x2;
+    }
   }
   Drop none;
   return ln_fwd(cur, nullptr, x.P + x.L.enc_norm_g, x.P + x.L.enc_norm_b, nullptr, pl.mem, pl.mf_e, pl.rf_e, x.M,
@@ -483,11 +506,19 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
   std::swap(cur, oth);
   for (int l = x.c.n_enc - 1; l >= 0; --l) {
     const float *xin = l == 0 ? pl.x0e : pl.enc[l - 1].x2;
-    GT_TRY(enc_layer_bwd(x, pl, l, xin, cur, pl.g0, oth));
+    if (pl.enc_img != nullptr)
+      GT_TRY(tc_enc_layer_bwd(x.c, x.L, x.P, x.G, pl.enc_img, l, xin, pl.enc[l].u1, pl.enc[l].u2, cur, oth, x.n_seq, x.seed, x.step,
+                              x.seq0, x.st));
+    else
+      GT_TRY(enc_layer_bwd(x, pl, l, xin, cur, pl.g0, oth));
     grad_bucket_ready(x.c, BK_ENC_LAYER, l, x.st);
     std::swap(cur, oth);
   }
-  GT_TRY(input_layer_bwd(x, pl, cur, pl.r0e, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, SITE_IN_ENC));
+  if (pl.enc_img != nullptr)
+    GT_TRY(edge32_stem_bwd(cur, src, x.c.e_src, x.P + x.L.in_enc_w, x.P + x.L.in_enc_b, x.G + x.L.in_enc_w, x.G + x.L.in_enc_b, x.M,
+                           x.drop(SITE_IN_ENC), x.row0(), x.st));
+  else
+    GT_TRY(input_layer_bwd(x, pl, cur, pl.r0e, src, x.c.e_src, x.L.in_enc_w, x.L.in_enc_b, SITE_IN_ENC));
   grad_bucket_ready(x.c, BK_IN_ENC, 0, x.st);
   return 0;
 }

@@ -321,6 +321,48 @@ static void tc_ctx(TcCtx &x, const gt_config &c, const Layout &L, const float *p
   x.seed = seed; x.step = step; x.seq0 = seq0; x.st = st;
 }
 
+// ---- encoder stack of an encoder-DECODER model (runner.cu hybrid path) ------------------------------------------------
+// The encoder of GrooveTransformer is the encoder-only stack (BGT/models/transformer.py:25-29 vs :101-104), so in bf16
+// mode with d_model = 32 its layers run in the fused kernels while the decoder runs per-op on gemm_tc.  The caller owns the
+// activation buffers (row-major fp32 [tokens, 32]) and the image block (n_enc * tc_enc_img_stride bytes).
+static gt_config enc_only(const gt_config &c) { gt_config e = c; e.n_dec = 0; return e; }
+bool tc_encoder_supported(const gt_config &c) {
+  return c.precision == GT_PREC_BF16 && c.d_model == 32 && tc_shape_supported(enc_only(c), nullptr) && tc_fused_edges(c);
+}
+uint32_t tc_enc_img_stride(const gt_config &c) { return (tc_img(c.d_model, c.dim_ff).total + 255u) & ~255u; }
+
+static void tc_ext_ctx(TcCtx &x, TcPlan &pl, const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *img,
+                       int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  tc_ctx(x, c, L, params, grads, nullptr, n_seq, train, seed, step, seq0, st);
+  memset(&pl, 0, sizeof(pl));
+  pl.img = img; pl.img_stride = tc_enc_img_stride(c);
+}
+int tc_enc_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *img, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  TcCtx x;
+  tc_ext_ctx(x, pl, c, L, params, nullptr, img, 1, false, 0, 0, 0, st);
+  return tc_prep(x, pl);
+}
+int tc_enc_layer_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *img, int l, const float *x_in, float *x_out,
+                     float *u1, float *u2, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  TcCtx x;
+  tc_ext_ctx(x, pl, c, L, params, nullptr, img, n_seq, train, seed, step, seq0, st);
+  TcLayerArgs a = tc_layer_args(x, pl, l);
+  a.x_in = x_in; a.x_out = x_out; a.u1 = u1; a.u2 = u2;
+  return tc_layer_fwd(c.d_model, a, st);
+}
+int tc_enc_layer_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *img, int l, const float *x_in,
+                     const float *u1, const float *u2, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step,
+                     int64_t seq0, cudaStream_t st) {
+  static thread_local TcPlan pl;
+  TcCtx x;
+  tc_ext_ctx(x, pl, c, L, params, grads, img, n_seq, true, seed, step, seq0, st);
+  TcLayerArgs a = tc_layer_args(x, pl, l);
+  a.x_in = x_in; a.u1_in = u1; a.u2_in = u2; a.dy = dy; a.dx = dx;
+  return tc_layer_bwd(c.d_model, a, st);
+}
+
 int tc_forward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
                int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, bool train, uint64_t seed, uint64_t step, int64_t seq0,
                cudaStream_t st) {

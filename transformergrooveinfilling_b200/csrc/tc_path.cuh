@@ -16,6 +16,15 @@ int tc_train_step(const gt_config &c, const Layout &L, const float *params, cons
                   int64_t ws_bytes, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st);
 int tc_predict(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, int64_t n_seq,
                float thres, float *hvo_out, void *ws, int64_t ws_bytes, cudaStream_t st);
+// encoder stack of an encoder-decoder model on the fused d_model = 32 kernels (runner.cu hybrid path)
+bool tc_encoder_supported(const gt_config &c);
+uint32_t tc_enc_img_stride(const gt_config &c);
+int tc_enc_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *img, cudaStream_t st);
+int tc_enc_layer_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *img, int l, const float *x_in, float *x_out,
+                     float *u1, float *u2, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st);
+int tc_enc_layer_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *img, int l, const float *x_in,
+                     const float *u1, const float *u2, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step,
+                     int64_t seq0, cudaStream_t st);
 int tc_debug_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int n, int k, int variant, cudaStream_t st);
 
 }  // namespace gt
