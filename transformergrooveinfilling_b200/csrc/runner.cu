@@ -145,6 +145,7 @@ struct Plan {
   // KV-cached decode (mode 2): per-layer key/value caches + one-token-per-sequence step buffers
   float *kv_self[64], *kv_cross[64];
   uint8_t *enc_img;                  // hybrid encoder (fused d_model = 32 layer kernels inside an encoder-decoder model): weight images
+  uint8_t *dec_img;                  // hybrid decoder: W1 / W2 images of the fused feed-forward blocks
   float *s_tok, *s_ya, *s_yb, *s_x1, *s_x2, *s_q, *s_ctx, *s_a, *s_hd, *s_z, *s_hvo;
   int64_t bytes;
 };
@@ -168,7 +169,7 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     if (!dec && hybrid) return layer_slim(b);
     b.qkv = take(M * 3 * d); b.ctx = take(M * d);
     b.u1 = train ? take(M * d) : nullptr; b.m1 = train ? take(M) : nullptr; b.r1 = train ? take(M) : nullptr;
-    b.x1 = take(M * d); b.hd = take(M * F);
+    b.x1 = take(M * d); b.hd = (dec && hybrid) ? nullptr : take(M * F);      // hybrid decoder: the hidden activations never leave the SM
     b.u2 = train ? take(M * d) : nullptr; b.m2 = train ? take(M) : nullptr; b.r2 = train ? take(M) : nullptr;
     b.x2 = take(M * d);
     if (dec) {
@@ -189,7 +190,10 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     }
   }
   P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
-  if (hybrid) P.enc_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_enc + 3) / 4));
+  if (hybrid) {
+    P.enc_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_enc + 3) / 4));
+    if (!decode) P.dec_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_dec + 3) / 4));
+  }
   if (decode) {
     const int64_t n = n_seq;
     for (int l = 0; l < c.n_dec; ++l) { P.kv_self[l] = take(M * 2 * d); P.kv_cross[l] = take(M * 2 * d); }
@@ -333,6 +337,8 @@ static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin)
   GemmEpi eco; eco.bias = x.P + p.ca.b_out;
   GT_TRY(linear(x, b.ctx2, d, x.P + p.ca.w_out, pl.a, d, eco));
   GT_TRY(ln_fwd(pl.a, b.x1, x.P + p.g2, x.P + p.be2, b.u2, b.x2, b.m2, b.r2, x.M, d, x.drop(site_id(1, li, 5)), x.row0(), x.st));
+  if (pl.dec_img != nullptr)       // hybrid: FFN + residual + LayerNorm3 in one fused kernel (TC_MODE_FFN)
+    return tc_dec_ffn_fwd(x.c, x.L, x.P, pl.dec_img, li, b.x2, b.x3, b.u3, x.n_seq, x.train, x.seed, x.step, x.seq0, x.st);
   GT_TRY(ffn_fwd(x, p, b.x2, b.hd, pl.a, 1, li));
   return ln_fwd(pl.a, b.x2, x.P + p.g3, x.P + p.be3, b.u3, b.x3, b.m3, b.r3, x.M, d, x.drop(site_id(1, li, 3)), x.row0(), x.st);
 }
@@ -362,6 +368,7 @@ static int encoder_fwd(const Ctx &x, const Plan &pl, const float *src) {
 }
 
 static int decoder_fwd(const Ctx &x, const Plan &pl, const float *tgt_in) {
+  if (pl.dec_img != nullptr) GT_TRY(tc_dec_prep(x.c, x.L, x.P, pl.dec_img, x.st));
   GT_TRY(input_layer_fwd(x, tgt_in, x.c.e_tgt, x.L.in_dec_w, x.L.in_dec_b, pl.r0d, pl.y0d, SITE_IN_DEC));
   const float *cur = pl.y0d;
   for (int l = 0; l < x.c.n_dec; ++l) {
@@ -430,7 +437,10 @@ static int dec_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *yin,
   const LayerP &p = x.L.dec[li];
   const LayerBuf &b = pl.dec[li];
   const int d = x.c.d_model;
-  GT_TRY(ffn_bwd(x, pl, p, dout, b.x2, b.hd, b.u3, b.m3, b.r3, p.g3, p.be3, dx_tmp, 1, li));
+  if (pl.dec_img != nullptr)
+    GT_TRY(tc_dec_ffn_bwd(x.c, x.L, x.P, x.G, pl.dec_img, li, b.x2, b.u3, dout, dx_tmp, x.n_seq, x.seed, x.step, x.seq0, x.st));
+  else
+    GT_TRY(ffn_bwd(x, pl, p, dout, b.x2, b.hd, b.u3, b.m3, b.r3, p.g3, p.be3, dx_tmp, 1, li));
   // cross-attention block
   GT_TRY(ln_bwd(dx_tmp, b.u2, b.m2, b.r2, x.P + p.g2, pl.du, pl.da, x.G + p.g2, x.G + p.be2, x.M, d,
                 x.drop(site_id(1, li, 5)), x.row0(), x.st));

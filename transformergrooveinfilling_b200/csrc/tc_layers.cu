@@ -229,7 +229,9 @@ __device__ __forceinline__ void store_kv_row(float *dst, const float (&v)[D], in
 // =============================================================================================
 constexpr int FWD_THREADS = 512;
 
-template <int D, int DH>
+// MODE 0: whole encoder layer.  MODE 1 (TC_MODE_FFN): the feed-forward block alone — x_out = LN(x_in + drop(FFN(x_in))) with
+// the block's LayerNorm in g2 / be2 — used for the third block of a decoder layer (torch/nn/modules/transformer.py:1143-1153).
+template <int D, int DH, int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLayerArgs a) {
   static_assert(D == 32, "q|k|v epilogue assigns one 32-column projection per thread part");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -255,11 +257,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
-  for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
+  if constexpr (MODE == 0)
+    for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
   for (int i = tid; i < F; i += FWD_THREADS) p_b1[i] = a.b1[i];
   if (tid < D) {
-    p_bo[tid] = a.bo[tid]; p_b2[tid] = a.b2[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid];
-    p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid];
+    if constexpr (MODE == 0) { p_bo[tid] = a.bo[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
+    p_b2[tid] = a.b2[tid]; p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid];
   }
   fence_before_sync();
   __syncthreads();
@@ -292,6 +295,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    float x1[D];                                       // part 0: the FFN block's input row (= its residual)
+    if constexpr (MODE != 0) {
+      if (part == 0) {
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+          const float4 t = valid ? *reinterpret_cast<const float4 *>(a.x_in + grow * D + c) : make_float4(0, 0, 0, 0);
+          x1[c] = t.x; x1[c + 1] = t.y; x1[c + 2] = t.z; x1[c + 3] = t.w;
+        }
+      }
+    }
+    if constexpr (MODE == 0) {
     // ---- P1: QKV = x Wqkv^T ----
     if (tid == 0) {
       fence_after_sync();
@@ -379,7 +393,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
     // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = row, part 0) ----
-    float x1[D];
     if (part == 0) {
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, x1 + cb);
@@ -414,6 +427,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    }  // MODE == 0
     // ---- P6: FFN, hidden dimension in chunks of FC; FFN2 accumulates in TMEM across chunks ----
     const uint32_t idesc1 = make_idesc_bf16(128, FC), idesc2 = make_idesc_bf16(128, D);
     if (tid == 0) {
@@ -526,11 +540,11 @@ static int num_sms() {
   return n;
 }
 
-template <int DH>
+template <int DH, int MODE = 0>
 static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
-  GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_FWD, st);
-    tc_layer_fwd_kernel<32, DH><<<grid, FWD_THREADS, smem, st>>>(a); }
+    tc_layer_fwd_kernel<32, DH, MODE><<<grid, FWD_THREADS, smem, st>>>(a); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -540,6 +554,7 @@ int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   const SmemPlan sp = fwd_smem(D, a.F, a.FC, attn_mma(a.dh));
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  if (a.mode == TC_MODE_FFN) return launch_fwd<2, TC_MODE_FFN>(a, fwd_smem(D, a.F, a.FC, true).total, grid, st);
   switch (a.dh) {
     case 2: return launch_fwd<2>(a, sp.total, grid, st);
     case 4: return launch_fwd<4>(a, sp.total, grid, st);
@@ -619,7 +634,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t base, int rows, int k16) { 
 constexpr int BWD_THREADS = 512;
 constexpr int BWD_PARTS = BWD_THREADS / 128;
 
-template <int D, int DH>
+template <int D, int DH, int MODE>
 __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
   static_assert(D == 32, "the register-tile column sums assume d_model == 32");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -650,9 +665,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
   for (int i = tid; i < 9 * D + F; i += BWD_THREADS) sG[i] = 0.f;
-  for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
+  if constexpr (MODE == 0)
+    for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
   for (int i = tid; i < F; i += BWD_THREADS) p_b1[i] = a.b1[i];
-  if (tid < D) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; p_g2[tid] = a.g2[tid]; }
+  if (tid < D) {
+    if constexpr (MODE == 0) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
+    p_g2[tid] = a.g2[tid];
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -732,6 +751,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
             make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
       { float t = warp_colsum32(w, lane); atomicAdd(&g_b2[lane], t); }
+    } else if (part == 1 && MODE != 0) {
+      // FFN block alone: its input x_in IS x1 (no LayerNorm to recompute)
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = pack8(a.x_in + grow * D + c);
+        *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) = v;
+      }
     } else if (part == 1) {
       float xh[D];
       float s1 = 0.f;
@@ -755,7 +782,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) =
             make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
       }
-    } else if (part == 2) {
+    } else if (part == 2 && MODE == 0) {
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -877,6 +904,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // dx1 complete, all weight-gradient MMAs of this tile retired
     fence_after_sync();
+    if constexpr (MODE != 0) {
+      // FFN block alone: dx = du2 (residual path) + dx1 (FFN path); nothing else to do for this tile
+      if (part == 0) {
+        float acc[D];
+#pragma unroll
+        for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < D; c += 4)
+            *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(du[c] + acc[c], du[c + 1] + acc[c + 1], du[c + 2] + acc[c + 2], du[c + 3] + acc[c + 3]);
+        }
+      }
+      fence_before_sync();
+      __syncthreads();
+      continue;
+    }
     // ---- B2: LN1 backward (part 0) ----
     if (part == 0) {
       float acc[D], xh[D];
@@ -1077,7 +1121,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   {
     const int m = row;                                // TMEM lane = output row of the weight-gradient blocks
     // jobs: 0..nchunk-1 dW1 chunks, nchunk..2nchunk-1 dW2^T chunks, then dWqkv, dWo — dealt round-robin to the parts
-    for (int job = part; job < 2 * nchunk + 2; job += BWD_PARTS) {
+    for (int job = part; job < 2 * nchunk + (MODE == 0 ? 2 : 0); job += BWD_PARTS) {
       float v[D];
       uint32_t t;
       if (job < nchunk) t = t_dw1 + 32u * job;
@@ -1107,11 +1151,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       }
     }
   }
-  for (int i = tid; i < 3 * D; i += BWD_THREADS) atomicAdd(a.gbqkv + i, g_bqkv[i]);
+  if constexpr (MODE == 0)
+    for (int i = tid; i < 3 * D; i += BWD_THREADS) atomicAdd(a.gbqkv + i, g_bqkv[i]);
   for (int i = tid; i < F; i += BWD_THREADS) atomicAdd(a.gb1 + i, g_b1[i]);
   if (tid < D) {
-    atomicAdd(a.gbo + tid, g_bo[tid]); atomicAdd(a.gb2 + tid, g_b2[tid]);
-    atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
+    if constexpr (MODE == 0) {
+      atomicAdd(a.gbo + tid, g_bo[tid]);
+      atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
+    }
+    atomicAdd(a.gb2 + tid, g_b2[tid]);
     atomicAdd(a.gg2 + tid, g_g2[tid]); atomicAdd(a.gbe2 + tid, g_be2[tid]);
   }
   fence_before_sync();
@@ -1119,11 +1167,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int DH>
+template <int DH, int MODE = 0>
 static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
-  GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_BWD, st);
-    tc_layer_bwd_kernel<32, DH><<<grid, BWD_THREADS, smem, st>>>(a); }
+    tc_layer_bwd_kernel<32, DH, MODE><<<grid, BWD_THREADS, smem, st>>>(a); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1134,6 +1182,7 @@ int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   const BwdSmem sp = bwd_smem(D, a.F, attn_mma(a.dh));
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_bwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  if (a.mode == TC_MODE_FFN) return launch_bwd<2, TC_MODE_FFN>(a, bwd_smem(D, a.F, true).total, grid, st);
   switch (a.dh) {
     case 2: return launch_bwd<2>(a, sp.total, grid, st);
     case 4: return launch_bwd<4>(a, sp.total, grid, st);

@@ -11,6 +11,7 @@ namespace gt {
 
 constexpr int TC_TILE = 128;
 constexpr int TC_MAX_LAYERS = 16;
+constexpr int TC_MODE_LAYER = 0, TC_MODE_FFN = 1;   // whole encoder layer / feed-forward block alone (third block of a decoder layer)
 
 struct TcImg {               // byte offsets of the bf16 operand images of one layer
   uint32_t wqkv, wo, w1, w2, total;
@@ -51,6 +52,7 @@ struct TcLayerArgs {
   int n_tiles, F, FC, H, dh;
   Drop d_attn, d1, d_ffn, d2;
   int64_t seq0;
+  int mode;                            // TC_MODE_LAYER / TC_MODE_FFN (FFN block: x_in, u2, b1, b2, g2, be2, d_ffn, d2 only)
 };
 
 bool tc_shape_supported(const gt_config &c, std::string *why);

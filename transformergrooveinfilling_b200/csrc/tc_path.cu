@@ -363,6 +363,51 @@ int tc_enc_layer_bwd(const gt_config &c, const Layout &L, const float *params, f
   return tc_layer_bwd(c.d_model, a, st);
 }
 
+// ---- feed-forward block of a DECODER layer (third block: x3 = LN3(x2 + drop(FFN(x2)))) on the fused kernels, TC_MODE_FFN ----
+// dec_img: n_dec * tc_enc_img_stride bytes (only the W1 / W2 images of each block are used)
+int tc_dec_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, cudaStream_t st) {
+  TcPrepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params = params; a.img = dec_img; a.img_stride = tc_enc_img_stride(c); a.n_layers = c.n_dec;
+  a.D = c.d_model; a.F = c.dim_ff; a.FC = tc_ffn_chunk(c.dim_ff);
+  for (int l = 0; l < c.n_dec; ++l) {
+    a.w_in[l] = L.dec[l].sa.w_in; a.w_out[l] = L.dec[l].sa.w_out; a.w1[l] = L.dec[l].w1; a.w2[l] = L.dec[l].w2;
+  }
+  return tc_prep_weights(a, st);
+}
+static TcLayerArgs tc_dec_ffn_args(const TcCtx &x, uint8_t *dec_img, int l) {
+  TcLayerArgs a;
+  memset(&a, 0, sizeof(a));
+  const LayerP &p = x.L->dec[l];
+  a.mode = TC_MODE_FFN;
+  a.img = dec_img + (size_t)l * tc_enc_img_stride(x.c);
+  a.img_bytes = tc_img(x.c.d_model, x.c.dim_ff).total;
+  a.b1 = x.P + p.b1; a.b2 = x.P + p.b2; a.g2 = x.P + p.g3; a.be2 = x.P + p.be3;
+  if (x.G) { a.gw1 = x.G + p.w1; a.gb1 = x.G + p.b1; a.gw2 = x.G + p.w2; a.gb2 = x.G + p.b2; a.gg2 = x.G + p.g3; a.gbe2 = x.G + p.be3; }
+  a.M = x.M; a.n_tiles = (int)((x.n_seq + 3) / 4);
+  a.F = x.c.dim_ff; a.FC = tc_ffn_chunk(x.c.dim_ff); a.H = x.c.nhead; a.dh = x.c.d_model / x.c.nhead;
+  a.d_ffn = x.drop(site_id(1, l, 2)); a.d2 = x.drop(site_id(1, l, 3));
+  a.seq0 = x.seq0;
+  return a;
+}
+int tc_dec_ffn_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, const float *x_in, float *x_out,
+                   float *u, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  TcCtx x;
+  tc_ctx(x, c, L, params, nullptr, nullptr, n_seq, train, seed, step, seq0, st);
+  TcLayerArgs a = tc_dec_ffn_args(x, dec_img, l);
+  a.x_in = x_in; a.x_out = x_out; a.u2 = u;
+  return tc_layer_fwd(c.d_model, a, st);
+}
+int tc_dec_ffn_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *dec_img, int l, const float *x_in,
+                   const float *u, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step, int64_t seq0,
+                   cudaStream_t st) {
+  TcCtx x;
+  tc_ctx(x, c, L, params, grads, nullptr, n_seq, true, seed, step, seq0, st);
+  TcLayerArgs a = tc_dec_ffn_args(x, dec_img, l);
+  a.x_in = x_in; a.u2_in = u; a.dy = dy; a.dx = dx;
+  return tc_layer_bwd(c.d_model, a, st);
+}
+
 int tc_forward(const gt_config &c, const Layout &L, const float *params, const float *pe, const float *src, const float *,
                int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, bool train, uint64_t seed, uint64_t step, int64_t seq0,
                cudaStream_t st) {
