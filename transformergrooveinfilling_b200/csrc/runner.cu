@@ -192,7 +192,7 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
   P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
   if (hybrid) {
     P.enc_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_enc + 3) / 4));
-    if (!decode) P.dec_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_dec + 3) / 4));
+    if (!decode) P.dec_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * 2 * c.n_dec + 3) / 4));
   }
   if (decode) {
     const int64_t n = n_seq;
@@ -322,6 +322,12 @@ static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin)
   const LayerP &p = x.L.dec[li];
   const LayerBuf &b = pl.dec[li];
   const int d = x.c.d_model;
+  if (pl.dec_img != nullptr && tc_dec_attn_supported(x.c)) {
+    // hybrid decoder layer = three fused blocks: causal self-attention + LN1, cross-attention + LN2, FFN + LN3
+    GT_TRY(tc_dec_attn_fwd(x.c, x.L, x.P, pl.dec_img, li, 0, yin, nullptr, b.x1, b.u1, x.n_seq, x.train, x.seed, x.step, x.seq0, x.st));
+    GT_TRY(tc_dec_attn_fwd(x.c, x.L, x.P, pl.dec_img, li, 1, b.x1, pl.mem, b.x2, b.u2, x.n_seq, x.train, x.seed, x.step, x.seq0, x.st));
+    return tc_dec_ffn_fwd(x.c, x.L, x.P, pl.dec_img, li, b.x2, b.x3, b.u3, x.n_seq, x.train, x.seed, x.step, x.seq0, x.st);
+  }
   GemmEpi e; e.bias = x.P + p.sa.b_in;
   GT_TRY(linear(x, yin, d, x.P + p.sa.w_in, b.qkv, 3 * d, e));
   GT_TRY(attention_fwd(attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 1, site_id(1, li, 0)), x.st));
@@ -441,6 +447,13 @@ static int dec_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *yin,
     GT_TRY(tc_dec_ffn_bwd(x.c, x.L, x.P, x.G, pl.dec_img, li, b.x2, b.u3, dout, dx_tmp, x.n_seq, x.seed, x.step, x.seq0, x.st));
   else
     GT_TRY(ffn_bwd(x, pl, p, dout, b.x2, b.hd, b.u3, b.m3, b.r3, p.g3, p.be3, dx_tmp, 1, li));
+  if (pl.dec_img != nullptr && tc_dec_attn_supported(x.c)) {
+    // fused cross-attention block: dx_tmp (grad wrt x2) -> dx_in (grad wrt x1), dmem += ; then the causal self-attention block
+    GT_TRY(tc_dec_attn_bwd(x.c, x.L, x.P, x.G, pl.dec_img, li, 1, b.x1, pl.mem, b.u2, dx_tmp, dx_in, pl.dmem, x.n_seq, x.seed, x.step,
+                           x.seq0, x.st));
+    return tc_dec_attn_bwd(x.c, x.L, x.P, x.G, pl.dec_img, li, 0, yin, nullptr, b.u1, dx_in, dx_tmp, nullptr, x.n_seq, x.seed, x.step,
+                           x.seq0, x.st);
+  }
   // cross-attention block
   GT_TRY(ln_bwd(dx_tmp, b.u2, b.m2, b.r2, x.P + p.g2, pl.du, pl.da, x.G + p.g2, x.G + p.be2, x.M, d,
                 x.drop(site_id(1, li, 5)), x.row0(), x.st));

@@ -87,7 +87,8 @@ __device__ __forceinline__ void a32_softmax(float (&sacc)[2][4][4], float (&inv)
 
 // ---- forward: ctx rows of one (sequence s, head h) pair -> bf16 K-major A image sCtx --------------------------
 // w_pair = quad index (element index >> 2) of (query row 0, position 0) of this pair at the attention dropout site
-template <int DH>
+// CAUSAL: key j of query i is masked for j > i (BGT/models/utils.py:53-56 get_tgt_mask; decoder self-attention)
+template <int DH, bool CAUSAL = false>
 __device__ __forceinline__ void a32_attn_fwd(const uint8_t *sQ, const uint8_t *sK, const uint8_t *sV, uint8_t *sCtx, int s, int h, int lane,
                                              const Drop &dr, uint64_t w_pair) {
   static_assert(DH == 2 || DH == 4 || DH == 8, "mma attention path: head dim 2, 4 or 8");
@@ -107,6 +108,11 @@ __device__ __forceinline__ void a32_attn_fwd(const uint8_t *sQ, const uint8_t *s
     for (int nt = 0; nt < 4; ++nt) {
       sacc[u][nt][0] = 0.f; sacc[u][nt][1] = 0.f; sacc[u][nt][2] = 0.f; sacc[u][nt][3] = 0.f;
       mma1688(sacc[u][nt], a0, a1, bk[nt]);
+      if constexpr (CAUSAL) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (8 * nt + 2 * t + (c & 1) > 16 * u + g + (c >> 1) * 8) sacc[u][nt][c] = -1e30f;
+      }
     }
   }
   float inv[2][2];
@@ -159,7 +165,7 @@ __device__ __forceinline__ void a32_attn_fwd(const uint8_t *sQ, const uint8_t *s
 // sDO: dL/dctx rows.  Writes the recomputed ctx rows to sCtx (for dWo) and dq | dk | dv to the K-major image sDQ
 // [128 x 96] (columns [0,32) dq wrt the UNscaled q, [32,64) dk, [64,96) dv); adds the in-projection bias gradient
 // (column sums over the pair's 32 rows) to g_b[0..96).
-template <int DH>
+template <int DH, bool CAUSAL = false>
 __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *sK, const uint8_t *sV, const uint8_t *sDO, uint8_t *sCtx, uint8_t *sDQ,
                                              int s, int h, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
   static_assert(DH == 2 || DH == 4 || DH == 8, "mma attention path: head dim 2, 4 or 8");
@@ -195,6 +201,11 @@ __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *s
       for (int c = 0; c < 4; ++c) { p[nt][c] = 0.f; dp[nt][c] = 0.f; }
       mma1688(p[nt], a0, a1, bk[nt]);
       mma1688(dp[nt], o0, o1, bv[nt]);
+      if constexpr (CAUSAL) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (8 * nt + 2 * t + (c & 1) > 16 * mt + g + (c >> 1) * 8) p[nt][c] = -1e30f;
+      }
     }
     float m0 = p[0][0], m1 = p[0][2];
 #pragma unroll

@@ -82,6 +82,11 @@ __device__ __forceinline__ uint64_t desc_b(uint32_t base, int N, int k16) {
   const uint32_t kstride = (uint32_t)(N >> 3) * 128u;
   return make_desc(base + (uint32_t)k16 * 2u * kstride, kstride, 128u);
 }
+// rows [n0, n0 + N') of an [N x K] weight image as a B operand (N' goes into the instruction descriptor)
+__device__ __forceinline__ uint64_t desc_b_rows(uint32_t base, int N, int n0, int k16) {
+  const uint32_t kstride = (uint32_t)(N >> 3) * 128u;
+  return make_desc(base + (uint32_t)(n0 >> 3) * 128u + (uint32_t)k16 * 2u * kstride, kstride, 128u);
+}
 // four dropout decisions from one 64-bit hash (idx4 must be a multiple of 4): returns scale or 0 for each
 __device__ __forceinline__ void drop4(const Drop &d, uint64_t idx4, float &m0, float &m1, float &m2, float &m3) {
   if (d.thr == 0) { m0 = 1.f; m1 = 1.f; m2 = 1.f; m3 = 1.f; return; }
@@ -116,7 +121,7 @@ __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC, bool mma) {
     s.ctx = al128(s.v + 128u * D * 4u);
   }
   s.h = al128(s.ctx + 128u * D * 2u);
-  s.total = al128(s.h + 128u * FC * 2u);
+  s.total = al128(s.h + 128u * (uint32_t)(FC < 32 ? 32 : FC) * 2u);     // >= 8 KB: the cross-attention memory tile is staged here
   return s;
 }
 
@@ -241,6 +246,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   const int row = tid & 127, part = tid >> 7;
   const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   constexpr bool MMA = attn_mma(DH);
+  constexpr bool ATTN_ONLY = MODE >= TC_MODE_ATTN_CAUSAL, CAUSAL = MODE == TC_MODE_ATTN_CAUSAL, CROSS = MODE == TC_MODE_ATTN_CROSS;
+  static_assert(!ATTN_ONLY || MMA, "attention-only blocks use the mma.sync attention path");
   const SmemPlan sp = fwd_smem(D, F, FC, MMA);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
@@ -257,12 +264,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
-  if constexpr (MODE == 0)
+  if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
-  for (int i = tid; i < F; i += FWD_THREADS) p_b1[i] = a.b1[i];
+  if constexpr (!ATTN_ONLY)
+    for (int i = tid; i < F; i += FWD_THREADS) p_b1[i] = a.b1[i];
   if (tid < D) {
-    if constexpr (MODE == 0) { p_bo[tid] = a.bo[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
-    p_b2[tid] = a.b2[tid]; p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid];
+    if constexpr (MODE != TC_MODE_FFN) { p_bo[tid] = a.bo[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
+    if constexpr (!ATTN_ONLY) { p_b2[tid] = a.b2[tid]; p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid]; }
   }
   fence_before_sync();
   __syncthreads();
@@ -291,6 +299,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       uint4 v = make_uint4(0, 0, 0, 0);
       if (valid) v = pack8(a.x_in + grow * D + part * 8);
       *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, part * 8, 128)) = v;
+      if constexpr (CROSS) {                           // cross-attention: keys / values come from the encoder memory tile
+        uint4 m = make_uint4(0, 0, 0, 0);
+        if (valid) m = pack8(a.mem + grow * D + part * 8);
+        *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 8, 128)) = m;
+      }
     }
     fence_async_smem();
     fence_before_sync();
@@ -305,13 +318,21 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
         }
       }
     }
-    if constexpr (MODE == 0) {
-    // ---- P1: QKV = x Wqkv^T ----
+    if constexpr (MODE != TC_MODE_FFN) {
+    // ---- P1: QKV = x Wqkv^T  (cross: q = x Wq^T, k | v = mem Wkv^T: rows [D, 3D) of the packed in-projection) ----
     if (tid == 0) {
       fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, 3 * D);
+      if constexpr (CROSS) {
+        const uint32_t idq = make_idesc_bf16(128, D), idkv = make_idesc_bf16(128, 2 * D);
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.wqkv, 3 * D, k), idesc, k > 0);
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b_rows(aW + io.wqkv, 3 * D, 0, k), idq, k > 0);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big + (uint32_t)D, desc_a128(aH, k), desc_b_rows(aW + io.wqkv, 3 * D, D, k), idkv, k > 0);
+      } else {
+        const uint32_t idesc = make_idesc_bf16(128, 3 * D);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.wqkv, 3 * D, k), idesc, k > 0);
+      }
       mma_commit(&bar_mma);
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
@@ -343,7 +364,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {
         const int s = p / H, h = p - s * H;
         const uint64_t w_pair = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32) * 8);
-        a32_attn_fwd<DH>(smem + sp.q, smem + sp.k, smem + sp.v, sCtx, s, h, lane, a.d_attn, w_pair);
+        a32_attn_fwd<DH, CAUSAL>(smem + sp.q, smem + sp.k, smem + sp.v, sCtx, s, h, lane, a.d_attn, w_pair);
       }
     } else
     for (int p = warp; p < 4 * H; p += FWD_THREADS / 32) {      // lane = query row
@@ -418,16 +439,24 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
 #pragma unroll
       for (int c = 0; c < D; ++c) x1[c] = (x1[c] - mu) * rs * p_g1[c] + p_be1[c];
+      if constexpr (ATTN_ONLY) {                       // attention block alone: its LayerNorm output is the block output
+        if (valid) {
 #pragma unroll
-      for (int c = 0; c < D; c += 8)
-        *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c, 128)) =
-            make_uint4(pack_bf16(x1[c], x1[c + 1]), pack_bf16(x1[c + 2], x1[c + 3]), pack_bf16(x1[c + 4], x1[c + 5]),
-                       pack_bf16(x1[c + 6], x1[c + 7]));
+          for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.x_out + grow * D + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < D; c += 8)
+          *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c, 128)) =
+              make_uint4(pack_bf16(x1[c], x1[c + 1]), pack_bf16(x1[c + 2], x1[c + 3]), pack_bf16(x1[c + 4], x1[c + 5]),
+                         pack_bf16(x1[c + 6], x1[c + 7]));
+      }
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    }  // MODE == 0
+    }  // MODE != TC_MODE_FFN
+    if constexpr (ATTN_ONLY) continue;
     // ---- P6: FFN, hidden dimension in chunks of FC; FFN2 accumulates in TMEM across chunks ----
     const uint32_t idesc1 = make_idesc_bf16(128, FC), idesc2 = make_idesc_bf16(128, D);
     if (tid == 0) {
@@ -555,6 +584,15 @@ int tc_layer_fwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_fwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
   if (a.mode == TC_MODE_FFN) return launch_fwd<2, TC_MODE_FFN>(a, fwd_smem(D, a.F, a.FC, true).total, grid, st);
+  if (a.mode == TC_MODE_ATTN_CAUSAL || a.mode == TC_MODE_ATTN_CROSS) {
+    const bool causal = a.mode == TC_MODE_ATTN_CAUSAL;
+    switch (a.dh) {
+      case 2: return causal ? launch_fwd<2, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_fwd<2, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      case 4: return causal ? launch_fwd<4, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_fwd<4, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      case 8: return causal ? launch_fwd<8, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_fwd<8, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      default: GT_FAIL("tc_layer_fwd: attention-only blocks need head dim 2, 4 or 8");
+    }
+  }
   switch (a.dh) {
     case 2: return launch_fwd<2>(a, sp.total, grid, st);
     case 4: return launch_fwd<4>(a, sp.total, grid, st);
@@ -644,6 +682,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   const int row = tid & 127, part = tid >> 7;
   const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   constexpr bool MMA = attn_mma(DH);
+  constexpr bool ATTN_ONLY = MODE >= TC_MODE_ATTN_CAUSAL, CAUSAL = MODE == TC_MODE_ATTN_CAUSAL, CROSS = MODE == TC_MODE_ATTN_CROSS;
+  static_assert(!ATTN_ONLY || MMA, "attention-only blocks use the mma.sync attention path");
   const BwdSmem sp = bwd_smem(D, F, MMA);
   const TcImg io = tc_img(D, F);
   uint8_t *sW = smem + sp.w;
@@ -665,12 +705,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
   for (int i = tid; i < 9 * D + F; i += BWD_THREADS) sG[i] = 0.f;
-  if constexpr (MODE == 0)
+  if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
-  for (int i = tid; i < F; i += BWD_THREADS) p_b1[i] = a.b1[i];
+  if constexpr (!ATTN_ONLY)
+    for (int i = tid; i < F; i += BWD_THREADS) p_b1[i] = a.b1[i];
   if (tid < D) {
-    if constexpr (MODE == 0) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
-    p_g2[tid] = a.g2[tid];
+    if constexpr (MODE != TC_MODE_FFN) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
+    if constexpr (!ATTN_ONLY) p_g2[tid] = a.g2[tid];
   }
   fence_before_sync();
   __syncthreads();
@@ -707,7 +748,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     const uint32_t acc0 = iter > 0 ? 1u : 0u;
     float du[D];                       // part 0: gradient w.r.t. the LayerNorm input currently being processed
     // ---- B0: part 0: LN2 backward ; part 1: x1 = LN1(u1) ; part 2: stage x_in ----
-    if (part == 0) {
+    if (part == 0 && ATTN_ONLY) {
+      // attention block alone: the incoming gradient is already dL/d(LayerNorm1 output)
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        float4 g = valid ? *reinterpret_cast<const float4 *>(a.dy + grow * D + c) : make_float4(0, 0, 0, 0);
+        du[c] = g.x; du[c + 1] = g.y; du[c + 2] = g.z; du[c + 3] = g.w;
+      }
+    } else if (part == 0) {
       float xh[D];
       float s1 = 0.f;
 #pragma unroll
@@ -751,13 +799,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
             make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
       { float t = warp_colsum32(w, lane); atomicAdd(&g_b2[lane], t); }
-    } else if (part == 1 && MODE != 0) {
+    } else if (part == 1 && MODE == TC_MODE_FFN) {
       // FFN block alone: its input x_in IS x1 (no LayerNorm to recompute)
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (valid) v = pack8(a.x_in + grow * D + c);
         *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) = v;
+      }
+    } else if (part == 1 && ATTN_ONLY) {
+      if constexpr (CROSS) {                           // encoder memory tile (keys / values) -> the (otherwise unused) x1 image
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) v = pack8(a.mem + grow * D + c);
+          *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) = v;
+        }
       }
     } else if (part == 1) {
       float xh[D];
@@ -782,7 +839,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) =
             make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
       }
-    } else if (part == 2 && MODE == 0) {
+    } else if (part == 2 && MODE != TC_MODE_FFN) {
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -793,6 +850,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    if constexpr (!ATTN_ONLY) {
     // ---- B1: FFN backward, chunk by chunk ----
     if (tid == 0) {
       fence_after_sync();
@@ -921,13 +979,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       __syncthreads();
       continue;
     }
+    }  // !ATTN_ONLY
     // ---- B2: LN1 backward (part 0) ----
     if (part == 0) {
       float acc[D], xh[D];
+      float mean1, rstd1;
+      if constexpr (ATTN_ONLY) {
 #pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
-      tmem_ld_wait();
-      const float mean1 = sStat[row * 2], rstd1 = sStat[row * 2 + 1];
+        for (int c = 0; c < D; ++c) acc[c] = 0.f;
+        float s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+          float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
+          xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
+          s1 += (t.x + t.y) + (t.z + t.w);
+        }
+        mean1 = s1 * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { const float t = xh[c] - mean1; q = fmaf(t, t, q); }
+        rstd1 = rsqrtf(q * (1.f / D) + LN_EPS);
+      } else {
+#pragma unroll
+        for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+        tmem_ld_wait();
+        mean1 = sStat[row * 2]; rstd1 = sStat[row * 2 + 1];
+      }
       float m1 = 0.f, m2 = 0.f;
       float w[32];
 #pragma unroll
@@ -972,8 +1049,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     // ---- B3: recompute q|k|v ; dctx = da1 . Wo ----
     if (tid == 0) {
       fence_after_sync();
+      if constexpr (CROSS) {                          // q = x Wq^T ; k | v = mem Wkv^T
+        const uint32_t idq = make_idesc_bf16(128, D), idkv = make_idesc_bf16(128, 2 * D);
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXin, k), desc_b(aW + io.wqkv, 3 * D, k), id_kk_3d, k > 0);
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXin, k), desc_b_rows(aW + io.wqkv, 3 * D, 0, k), idq, k > 0);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big + (uint32_t)D, desc_a128(aX1, k), desc_b_rows(aW + io.wqkv, 3 * D, D, k), idkv, k > 0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXin, k), desc_b(aW + io.wqkv, 3 * D, k), id_kk_3d, k > 0);
+      }
 #pragma unroll
       for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_sb, desc_a128(aDA, k), desc_mn(aW + io.wo, D, k), id_kmn_d, k > 0);
       mma_commit(&bar_mma);
@@ -1010,7 +1095,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {
         const int s = p / H, h = p - s * H;
         const uint64_t w_pair = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32) * 8);
-        a32_attn_bwd<DH>(smem + sp.q, smem + sp.k, smem + sp.v, smem + sp.dctx, sCtx, sDQ, s, h, lane, a.d_attn, w_pair, g_bqkv);
+        a32_attn_bwd<DH, CAUSAL>(smem + sp.q, smem + sp.k, smem + sp.v, smem + sp.dctx, sCtx, sDQ, s, h, lane, a.d_attn, w_pair, g_bqkv);
       }
     } else
     for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {      // lane = query row; dK/dV via warp transposed sums
@@ -1089,17 +1174,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     // ---- B6: dx_in = dqkv . Wqkv ; dWqkv += dqkv^T x_in ; dWo += da1^T ctx ----
     if (tid == 0) {
       fence_after_sync();
+      if constexpr (CROSS) {
+        // dx = dq Wq (dqkv columns [0, D)) ; dmem = dk|dv Wkv (columns [D, 3D)) -> t_sb (dctx is consumed)
 #pragma unroll
-      for (int k = 0; k < 3 * D / 16; ++k) mma_bf16_ss(t_sa, desc_a128(aDQ, k), desc_mn(aW + io.wqkv, 3 * D, k), id_kmn_d, k > 0);
+        for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_sa, desc_a128(aDQ, k), desc_mn(aW + io.wqkv, 3 * D, k), id_kmn_d, k > 0);
+#pragma unroll
+        for (int k = D / 16; k < 3 * D / 16; ++k) mma_bf16_ss(t_sb, desc_a128(aDQ, k), desc_mn(aW + io.wqkv, 3 * D, k), id_kmn_d, k > D / 16);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3 * D / 16; ++k) mma_bf16_ss(t_sa, desc_a128(aDQ, k), desc_mn(aW + io.wqkv, 3 * D, k), id_kmn_d, k > 0);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         mma_bf16_ss(t_dwqkv, desc_mn(aDQ, 128, k), desc_mn(aXin, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);
+        // cross: rows [D, 3D) of dWqkv contract dk | dv with the MEMORY tile: a second accumulator (the unused dW1 columns)
+        if constexpr (CROSS) mma_bf16_ss(t_dw1, desc_mn(aDQ, 128, k), desc_mn(aX1, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);
         mma_bf16_ss(t_dwo, desc_mn(aDA, 128, k), desc_mn(aCtx, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);
       }
       mma_commit(&bar_mma);
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
+    if constexpr (CROSS) {
+      if (part == 1) {                                // dmem += dk|dv Wkv (this CTA owns the tile's rows; decoder layers run in stream order)
+        float acc[D];
+#pragma unroll
+        for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sb + lane_off + (uint32_t)cb, acc + cb);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < D; c += 4) {
+            float4 t = *reinterpret_cast<const float4 *>(a.dmem + grow * D + c);
+            *reinterpret_cast<float4 *>(a.dmem + grow * D + c) = make_float4(t.x + acc[c], t.y + acc[c + 1], t.z + acc[c + 2], t.w + acc[c + 3]);
+          }
+        }
+      }
+    }
     if (part == 0) {
       float acc[D];
 #pragma unroll
@@ -1121,12 +1231,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   {
     const int m = row;                                // TMEM lane = output row of the weight-gradient blocks
     // jobs: 0..nchunk-1 dW1 chunks, nchunk..2nchunk-1 dW2^T chunks, then dWqkv, dWo — dealt round-robin to the parts
-    for (int job = part; job < 2 * nchunk + (MODE == 0 ? 2 : 0); job += BWD_PARTS) {
+    for (int job = ATTN_ONLY ? 2 * nchunk + part : part; job < 2 * nchunk + (MODE == TC_MODE_FFN ? 0 : 2); job += BWD_PARTS) {
       float v[D];
       uint32_t t;
       if (job < nchunk) t = t_dw1 + 32u * job;
       else if (job < 2 * nchunk) t = t_dw2 + 32u * (job - nchunk);
-      else t = job == 2 * nchunk ? t_dwqkv : t_dwo;
+      else t = job == 2 * nchunk ? ((CROSS && m >= D) ? t_dw1 : t_dwqkv) : t_dwo;
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t + lane_off + (uint32_t)cb, v + cb);
       tmem_ld_wait();
@@ -1151,16 +1261,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       }
     }
   }
-  if constexpr (MODE == 0)
+  if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += BWD_THREADS) atomicAdd(a.gbqkv + i, g_bqkv[i]);
-  for (int i = tid; i < F; i += BWD_THREADS) atomicAdd(a.gb1 + i, g_b1[i]);
+  if constexpr (!ATTN_ONLY)
+    for (int i = tid; i < F; i += BWD_THREADS) atomicAdd(a.gb1 + i, g_b1[i]);
   if (tid < D) {
-    if constexpr (MODE == 0) {
+    if constexpr (MODE != TC_MODE_FFN) {
       atomicAdd(a.gbo + tid, g_bo[tid]);
       atomicAdd(a.gg1 + tid, g_g1[tid]); atomicAdd(a.gbe1 + tid, g_be1[tid]);
     }
-    atomicAdd(a.gb2 + tid, g_b2[tid]);
-    atomicAdd(a.gg2 + tid, g_g2[tid]); atomicAdd(a.gbe2 + tid, g_be2[tid]);
+    if constexpr (!ATTN_ONLY) {
+      atomicAdd(a.gb2 + tid, g_b2[tid]);
+      atomicAdd(a.gg2 + tid, g_g2[tid]); atomicAdd(a.gbe2 + tid, g_be2[tid]);
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -1183,6 +1296,15 @@ int tc_layer_bwd(int D, const TcLayerArgs &a, cudaStream_t st) {
   GT_CHECK(sp.total <= 227 * 1024, "tc_layer_bwd: shared memory budget exceeded");
   int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
   if (a.mode == TC_MODE_FFN) return launch_bwd<2, TC_MODE_FFN>(a, bwd_smem(D, a.F, true).total, grid, st);
+  if (a.mode == TC_MODE_ATTN_CAUSAL || a.mode == TC_MODE_ATTN_CROSS) {
+    const bool causal = a.mode == TC_MODE_ATTN_CAUSAL;
+    switch (a.dh) {
+      case 2: return causal ? launch_bwd<2, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_bwd<2, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      case 4: return causal ? launch_bwd<4, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_bwd<4, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      case 8: return causal ? launch_bwd<8, TC_MODE_ATTN_CAUSAL>(a, sp.total, grid, st) : launch_bwd<8, TC_MODE_ATTN_CROSS>(a, sp.total, grid, st);
+      default: GT_FAIL("tc_layer_bwd: attention-only blocks need head dim 2, 4 or 8");
+    }
+  }
   switch (a.dh) {
     case 2: return launch_bwd<2>(a, sp.total, grid, st);
     case 4: return launch_bwd<4>(a, sp.total, grid, st);

@@ -11,7 +11,9 @@ namespace gt {
 
 constexpr int TC_TILE = 128;
 constexpr int TC_MAX_LAYERS = 16;
-constexpr int TC_MODE_LAYER = 0, TC_MODE_FFN = 1;   // whole encoder layer / feed-forward block alone (third block of a decoder layer)
+// whole encoder layer / feed-forward block alone / attention block alone (attention + out-proj + residual + LayerNorm), causal
+// self-attention or cross-attention over an encoder-memory tile: the three blocks of a decoder layer
+constexpr int TC_MODE_LAYER = 0, TC_MODE_FFN = 1, TC_MODE_ATTN_CAUSAL = 2, TC_MODE_ATTN_CROSS = 3;
 
 struct TcImg {               // byte offsets of the bf16 operand images of one layer
   uint32_t wqkv, wo, w1, w2, total;
@@ -44,6 +46,8 @@ struct TcLayerArgs {
   // forward: x_in -> (u1, u2 saved when non-null) -> x_out.   backward: + dy (grad wrt x_out) -> dx
   const float *x_in, *u1_in, *u2_in, *dy;
   float *u1, *u2, *x_out, *dx;
+  const float *mem;                    // TC_MODE_ATTN_CROSS: encoder memory [tokens, D] (keys / values)
+  float *dmem;                         // ... and its gradient (accumulated: every decoder layer adds to it)
   const uint8_t *img;
   uint32_t img_bytes;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;

@@ -364,16 +364,61 @@ int tc_enc_layer_bwd(const gt_config &c, const Layout &L, const float *params, f
 }
 
 // ---- feed-forward block of a DECODER layer (third block: x3 = LN3(x2 + drop(FFN(x2)))) on the fused kernels, TC_MODE_FFN ----
-// dec_img: n_dec * tc_enc_img_stride bytes (only the W1 / W2 images of each block are used)
+// dec_img: 2 * n_dec * tc_enc_img_stride bytes: block l = (self-attention in/out projections, W1, W2) of decoder layer l,
+// block n_dec + l = (cross-attention in/out projections, ...) of decoder layer l
 int tc_dec_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, cudaStream_t st) {
-  TcPrepArgs a;
-  memset(&a, 0, sizeof(a));
-  a.params = params; a.img = dec_img; a.img_stride = tc_enc_img_stride(c); a.n_layers = c.n_dec;
-  a.D = c.d_model; a.F = c.dim_ff; a.FC = tc_ffn_chunk(c.dim_ff);
-  for (int l = 0; l < c.n_dec; ++l) {
-    a.w_in[l] = L.dec[l].sa.w_in; a.w_out[l] = L.dec[l].sa.w_out; a.w1[l] = L.dec[l].w1; a.w2[l] = L.dec[l].w2;
+  for (int pass = 0; pass < 2; ++pass) {
+    TcPrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.params = params; a.img = dec_img + (size_t)pass * c.n_dec * tc_enc_img_stride(c); a.img_stride = tc_enc_img_stride(c);
+    a.n_layers = c.n_dec; a.D = c.d_model; a.F = c.dim_ff; a.FC = tc_ffn_chunk(c.dim_ff);
+    for (int l = 0; l < c.n_dec; ++l) {
+      const AttnP &ap = pass == 0 ? L.dec[l].sa : L.dec[l].ca;
+      a.w_in[l] = ap.w_in; a.w_out[l] = ap.w_out; a.w1[l] = L.dec[l].w1; a.w2[l] = L.dec[l].w2;
+    }
+    GT_TRY(tc_prep_weights(a, st));
   }
-  return tc_prep_weights(a, st);
+  return 0;
+}
+bool tc_dec_attn_supported(const gt_config &c) { const int dh = c.d_model / c.nhead; return dh == 2 || dh == 4 || dh == 8; }
+// attention block of a decoder layer: cross = 0: causal self-attention + LayerNorm1 ; cross = 1: cross-attention over `mem` + LayerNorm2
+static TcLayerArgs tc_dec_attn_args(const TcCtx &x, uint8_t *dec_img, int l, int cross) {
+  TcLayerArgs a;
+  memset(&a, 0, sizeof(a));
+  const LayerP &p = x.L->dec[l];
+  const AttnP &ap = cross ? p.ca : p.sa;
+  a.mode = cross ? TC_MODE_ATTN_CROSS : TC_MODE_ATTN_CAUSAL;
+  a.img = dec_img + (size_t)(cross ? x.c.n_dec + l : l) * tc_enc_img_stride(x.c);
+  a.img_bytes = tc_img(x.c.d_model, x.c.dim_ff).w1;            // in-projection + out-projection images only
+  a.bqkv = x.P + ap.b_in; a.bo = x.P + ap.b_out;
+  a.g1 = x.P + (cross ? p.g2 : p.g1); a.be1 = x.P + (cross ? p.be2 : p.be1);
+  if (x.G) {
+    a.gwqkv = x.G + ap.w_in; a.gbqkv = x.G + ap.b_in; a.gwo = x.G + ap.w_out; a.gbo = x.G + ap.b_out;
+    a.gg1 = x.G + (cross ? p.g2 : p.g1); a.gbe1 = x.G + (cross ? p.be2 : p.be1);
+  }
+  a.M = x.M; a.n_tiles = (int)((x.n_seq + 3) / 4);
+  a.F = x.c.dim_ff; a.FC = tc_ffn_chunk(x.c.dim_ff); a.H = x.c.nhead; a.dh = x.c.d_model / x.c.nhead;
+  a.d_attn = x.drop(site_id(1, l, cross ? 4 : 0)); a.d1 = x.drop(site_id(1, l, cross ? 5 : 1));
+  a.seq0 = x.seq0;
+  return a;
+}
+int tc_dec_attn_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, int cross, const float *x_in,
+                    const float *mem, float *x_out, float *u, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0,
+                    cudaStream_t st) {
+  TcCtx x;
+  tc_ctx(x, c, L, params, nullptr, nullptr, n_seq, train, seed, step, seq0, st);
+  TcLayerArgs a = tc_dec_attn_args(x, dec_img, l, cross);
+  a.x_in = x_in; a.mem = mem; a.x_out = x_out; a.u1 = u;
+  return tc_layer_fwd(c.d_model, a, st);
+}
+int tc_dec_attn_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *dec_img, int l, int cross,
+                    const float *x_in, const float *mem, const float *u, const float *dy, float *dx, float *dmem, int64_t n_seq,
+                    uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st) {
+  TcCtx x;
+  tc_ctx(x, c, L, params, grads, nullptr, n_seq, true, seed, step, seq0, st);
+  TcLayerArgs a = tc_dec_attn_args(x, dec_img, l, cross);
+  a.x_in = x_in; a.mem = mem; a.u1_in = u; a.dy = dy; a.dx = dx; a.dmem = dmem;
+  return tc_layer_bwd(c.d_model, a, st);
 }
 static TcLayerArgs tc_dec_ffn_args(const TcCtx &x, uint8_t *dec_img, int l) {
   TcLayerArgs a;

@@ -25,7 +25,15 @@ int tc_enc_layer_fwd(const gt_config &c, const Layout &L, const float *params, u
 int tc_enc_layer_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *img, int l, const float *x_in,
                      const float *u1, const float *u2, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step,
                      int64_t seq0, cudaStream_t st);
-// feed-forward block of a decoder layer on the fused kernels (TC_MODE_FFN); dec_img: n_dec * tc_enc_img_stride bytes
+// the three blocks of a decoder layer on the fused kernels (TC_MODE_ATTN_CAUSAL / TC_MODE_ATTN_CROSS / TC_MODE_FFN);
+// dec_img: 2 * n_dec * tc_enc_img_stride bytes
+bool tc_dec_attn_supported(const gt_config &c);
+int tc_dec_attn_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, int cross, const float *x_in,
+                    const float *mem, float *x_out, float *u, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0,
+                    cudaStream_t st);
+int tc_dec_attn_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *dec_img, int l, int cross,
+                    const float *x_in, const float *mem, const float *u, const float *dy, float *dx, float *dmem, int64_t n_seq,
+                    uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st);
 int tc_dec_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, cudaStream_t st);
 int tc_dec_ffn_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, const float *x_in, float *x_out,
                    float *u, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st);
