@@ -204,7 +204,7 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
     fl_step = train_flops_per_seq(w) / 3 * n
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     roof = None
-    if cnt.value and fused:
+    if cnt.value and fused and not w["Ld"]:
         layer_mac = 32 * (4 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 2 * 32 * 32 * w["d"]
         avg_ms = tot_ms.value / cnt.value
         ach = 2 * layer_mac * n / (avg_ms / 1e3) / 1e12
@@ -402,6 +402,11 @@ def main():
                 # the weight gradients run in t256_wgrad_kernel (class 20, listed under "kernels")
                 fl_launch = 2 * layer_mac * n
                 kname = "t256_layer_bwd (data gradients + attention backward; recomputed q|k|v and probabilities not counted)"
+            elif w["Ld"]:
+                # encoder-decoder: 6 whole-layer launches + 3 block launches per decoder layer; average over the launches
+                dec_mac = 32 * (8 * w["d"] ** 2 + 2 * w["d"] * w["F"]) + 4 * 32 * 32 * w["d"]
+                fl_launch = 2 * 2 * (w["L"] * layer_mac + w["Ld"] * dec_mac) * n * args.steps / max(cnt.value, 1)
+                kname = "tc_layer_bwd (encoder layers + decoder self-attention / cross-attention / FFN blocks; average launch)"
             else:
                 fl_launch = 2 * 2 * layer_mac * n       # one encoder layer backward = 2x its forward FLOPs
                 kname = "tc_layer_bwd (data + weight gradients)"
@@ -437,7 +442,7 @@ def main():
         lib.gt_profile_collect_class(cls, C.byref(t), C.byref(c))
         if c.value:
             kernels[nm] = {"launches_per_step": c.value / 3, "ms_per_step": t.value / 3, "share": t.value / ms3}
-            if path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256) and cls in fl_cls:
+            if path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256) and cls in fl_cls and not w["Ld"]:
                 # one launch per encoder layer carries fl_cls[cls] (the weight-gradient class also holds the two small
                 # input-layer / head launches of edge256.cu: their time is included, their FLOPs are not)
                 kernels[nm]["tflops"] = fl_cls[cls] * w["L"] / (t.value / 3 / 1e3) / 1e12

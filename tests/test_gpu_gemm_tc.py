@@ -116,7 +116,13 @@ SHAPES = {
     # InfillingClosedHH_Symbolic_training.yaml with encoder_only = 0 (C5 encoder-decoder), 2 + 2 of its 6 + 6 layers
     "c5_encdec_l2": (G.GrooveCfg(32, 16, 512, 2, 2, 27, 27), 0.38, 0.24),
     "d64_encdec": (G.GrooveCfg(64, 2, 64, 1, 1, 16, 27), 1.0, 0.1),
+    # fused encoder-decoder blocks at the other mma.sync head dims: head dim 4 with a single 16-wide FFN chunk, head dim 8
+    "d32_h8_f16_encdec": (G.GrooveCfg(32, 8, 16, 1, 2, 16, 27), 0.6, 0.2),
+    "d32_h4_f96_encdec": (G.GrooveCfg(32, 4, 96, 2, 1, 27, 27), 0.9, 0.15),
+    # head dim 16: the encoder stack and the decoder FFN blocks are fused, the decoder attention blocks run per-op
+    "d32_h2_encdec": (G.GrooveCfg(32, 2, 64, 1, 1, 16, 27), 0.5, 0.1),
 }
+FUSED_ENCDEC = ("c5_encdec_l2", "d32_h8_f16_encdec", "d32_h4_f96_encdec")
 
 
 def test_path_kind():
@@ -125,6 +131,10 @@ def test_path_kind():
     for name, (cfg, _, _) in SHAPES.items():
         model, _ = build_model(cfg, precision="bf16")
         kinds[name] = lib.gt_path_kind(C.byref(model._cfg()))
+    # the C5 encoder-decoder (d_model 32, head dim 2) runs every block of every layer in the fused kernels (hybrid path of
+    # runner.cu: fused encoder stack + three fused blocks per decoder layer); the other shapes run per-op on gemm_tc
+    for k in FUSED_ENCDEC:
+        assert kinds.pop(k) == _lib.PATH_FUSED_D32
     assert set(kinds.values()) == {_lib.PATH_GEMM_TC}, kinds
     m32, _ = build_model(G.GrooveCfg(32, 4, 16, 1, 0, 16, 27), precision="bf16")
     assert lib.gt_path_kind(C.byref(m32._cfg())) == _lib.PATH_FUSED_D32
@@ -171,7 +181,9 @@ def _worst_grad_err(model, grads):
 
 
 @pytest.mark.parametrize("name,n", [("c3_l2", 4), ("c3_l2", 64), ("d64_h4", 5), ("d64_h4", 67), ("d128_h8_sym", 64),
-                                    ("c5_encdec_l2", 6), ("c5_encdec_l2", 64), ("d64_encdec", 64)])
+                                    ("c5_encdec_l2", 6), ("c5_encdec_l2", 64), ("d64_encdec", 64), ("d32_h8_f16_encdec", 64),
+                                    ("d32_h8_f16_encdec", 7), ("d32_h4_f96_encdec", 64), ("d32_h2_encdec", 64),
+                                    ("c5_encdec_l2", 4 * 148 + 3)])
 def test_train_step_matches_oracle(name, n):
     cfg, pen, p = SHAPES[name]
     model, P = build_model(cfg, dropout=p, precision="bf16")
@@ -234,3 +246,26 @@ def test_predict_encdec_bf16_agrees_with_fp32():
     assert (res["bf16"][0][:, 0] == res["fp32"][0][:, 0]).mean() >= 0.995
     assert (res["bf16"][0] == res["fp32"][0]).mean() > 0.97
     assert np.abs(res["bf16"][1][:, 0] - res["fp32"][1][:, 0]).max() < 2e-2
+
+
+@pytest.mark.parametrize("name,n", [("c5_encdec_l2", 9), ("d32_h4_f96_encdec", 6)])
+def test_autograd_path_equals_fused_step_encdec(name, n):
+    """model(x, y_shifted) -> calculate_loss -> loss.backward() against the single-call fused step on the fused encoder-decoder
+    path: same layer / block kernels, different tail kernels (the fused step folds calculate_loss into the decoder tail)."""
+    from transformergrooveinfilling_b200 import calculate_loss
+    cfg, pen, p = SHAPES[name]
+    x, y = [t.cuda() for t in G.det_batch(cfg, n)]
+    m1, _ = build_model(cfg, dropout=p, precision="bf16")
+    m2, _ = build_model(cfg, dropout=p, precision="bf16")
+    m1.set_seed(5, step=3, seq0=0).train(); m2.set_seed(5, step=3, seq0=0).train()
+    metrics, hvo = m1.train_step(x, y, pen)
+    pred = m2(x, G.shift_right(y.cpu()).cuda())
+    out = calculate_loss(pred, y, None, None, pen)
+    out[0].backward()
+    np.testing.assert_allclose(torch.cat(pred, 2).detach().cpu().numpy(), hvo.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.array([out[0].item(), *out[1:]]), metrics.cpu().numpy(), rtol=2e-6)
+    from _util import grads_by_name as _g
+    g1, g2 = _g(m1), _g(m2)
+    for k in g1:
+        scale = float(g1[k].abs().max()) + 1e-12
+        assert float((g2[k] - g1[k]).abs().max()) / scale < 2e-4, k

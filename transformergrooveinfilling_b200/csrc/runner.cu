@@ -215,7 +215,7 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
   P.a = take(M * d);
   if (train) {
     P.d_hvo = take(M * c.e_tgt);
-    P.loss_partials = take(loss_scratch_floats(n_seq));
+    P.loss_partials = take(loss_scratch_floats(n_seq) + edge32_loss_partials(n_seq));
     P.dxa = take(M * d); P.dxb = take(M * d); P.du = take(M * d); P.da = take(M * d);
     P.dh = take(M * F); P.dqkv = take(M * 3 * d); P.dctx = take(M * d); P.dlog = take(M * c.e_tgt);
     P.g0 = take(M * d);
@@ -373,14 +373,21 @@ static int encoder_fwd(const Ctx &x, const Plan &pl, const float *src) {
                 x.c.d_model, none, 0, x.st);
 }
 
-static int decoder_fwd(const Ctx &x, const Plan &pl, const float *tgt_in) {
+// fused ends of the hybrid decoder (edge32.cu): the target input layer and the final LayerNorm + head (+ loss)
+static bool dec_fused_edges(const Ctx &x, const Plan &pl) { return pl.dec_img != nullptr && x.c.e_tgt == 27; }
+
+static int decoder_fwd(const Ctx &x, const Plan &pl, const float *tgt_in, bool final_ln = true) {
   if (pl.dec_img != nullptr) GT_TRY(tc_dec_prep(x.c, x.L, x.P, pl.dec_img, x.st));
-  GT_TRY(input_layer_fwd(x, tgt_in, x.c.e_tgt, x.L.in_dec_w, x.L.in_dec_b, pl.r0d, pl.y0d, SITE_IN_DEC));
+  if (dec_fused_edges(x, pl))
+    GT_TRY(edge32_stem_fwd(tgt_in, x.c.e_tgt, x.P + x.L.in_dec_w, x.P + x.L.in_dec_b, x.pe, pl.y0d, x.M, x.drop(SITE_IN_DEC), x.row0(), x.st));
+  else
+    GT_TRY(input_layer_fwd(x, tgt_in, x.c.e_tgt, x.L.in_dec_w, x.L.in_dec_b, pl.r0d, pl.y0d, SITE_IN_DEC));
   const float *cur = pl.y0d;
   for (int l = 0; l < x.c.n_dec; ++l) {
     GT_TRY(dec_layer_fwd(x, pl, l, cur));
     cur = pl.dec[l].x3;
   }
+  if (!final_ln) return 0;
   Drop none;
   return ln_fwd(cur, nullptr, x.P + x.L.dec_norm_g, x.P + x.L.dec_norm_b, nullptr, pl.zdec, pl.mf_d, pl.rf_d, x.M,
                 x.c.d_model, none, 0, x.st);
@@ -392,13 +399,24 @@ static int head_fwd(const Ctx &x, const float *z, float *hvo, float thres) {
   return head_activation(hvo, x.M, x.c.e_tgt, thres, x.st);
 }
 
-static int forward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, float *hvo) {
+// y != nullptr (hybrid decoder with fused ends only): the tail also evaluates calculate_loss and leaves dL/dlogits in pl.dlog
+static int forward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, float *hvo, const float *y = nullptr,
+                       float penalty = 0.f, float *metrics6 = nullptr) {
   GT_TRY(encoder_fwd(x, pl, src));
   if (x.c.n_dec > 0) {
     GT_CHECK(tgt_in != nullptr, "encoder-decoder forward needs the shifted target");
+    if (dec_fused_edges(x, pl)) {
+      GT_TRY(decoder_fwd(x, pl, tgt_in, false));
+      const float *last = pl.dec[x.c.n_dec - 1].x3, *g = x.P + x.L.dec_norm_g, *b = x.P + x.L.dec_norm_b, *w = x.P + x.L.out_w, *bo = x.P + x.L.out_b;
+      if (y != nullptr)
+        return edge32_tail_fwd_loss(last, g, b, w, bo, hvo, pl.mf_d, pl.rf_d, x.M, y, penalty, pl.dlog, pl.loss_partials, metrics6, x.st);
+      return edge32_tail_fwd(last, g, b, w, bo, hvo, pl.mf_d, pl.rf_d, x.M, -1.f, x.st);
+    }
+    GT_CHECK(y == nullptr, "forward_all: fused loss needs the fused decoder ends");
     GT_TRY(decoder_fwd(x, pl, tgt_in));
     return head_fwd(x, pl.zdec, hvo, -1.f);
   }
+  GT_CHECK(y == nullptr, "forward_all: fused loss needs the fused decoder ends");
   return head_fwd(x, pl.mem, hvo, -1.f);
 }
 
@@ -496,18 +514,28 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
                         const float *d_hvo) {
   const int d = x.c.d_model, E = x.c.e_tgt;
   Drop none;
-  // head
-  GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
-  const float *z = x.c.n_dec > 0 ? pl.zdec : pl.mem;
-  GT_TRY(linear_wgrad(x, pl.dlog, E, E, z, d, d, x.G + x.L.out_w, x.G + x.L.out_b));
-  GemmEpi e0;
-  GT_TRY(linear_dgrad(x, pl.dlog, E, x.P + x.L.out_w, d, pl.dxa, e0));
+  const bool fused_dec_ends = x.c.n_dec > 0 && dec_fused_edges(x, pl);
   float *cur = pl.dxa, *oth = pl.dxb;
+  if (!fused_dec_ends) {
+    // head
+    GT_CHECK(hvo != nullptr, "backward_all: hvo is required on this path");
+    GT_TRY(head_activation_bwd(d_hvo, hvo, pl.dlog, x.M, E, x.st));
+    const float *z = x.c.n_dec > 0 ? pl.zdec : pl.mem;
+    GT_TRY(linear_wgrad(x, pl.dlog, E, E, z, d, d, x.G + x.L.out_w, x.G + x.L.out_b));
+    GemmEpi e0;
+    GT_TRY(linear_dgrad(x, pl.dlog, E, x.P + x.L.out_w, d, pl.dxa, e0));
+  }
   if (x.c.n_dec > 0) {
     GT_CUDA(cudaMemsetAsync(pl.dmem, 0, (size_t)x.M * d * sizeof(float), x.st));
     const float *last = pl.dec[x.c.n_dec - 1].x3;
-    GT_TRY(ln_bwd(cur, last, pl.mf_d, pl.rf_d, x.P + x.L.dec_norm_g, oth, nullptr, x.G + x.L.dec_norm_g,
-                  x.G + x.L.dec_norm_b, x.M, d, none, 0, x.st));
+    if (fused_dec_ends) {
+      // hvo == nullptr: d_hvo already holds dL/dlogits (left by the fused tail + loss forward)
+      GT_TRY(edge32_tail_bwd(d_hvo, hvo, last, pl.mf_d, pl.rf_d, x.P + x.L.dec_norm_g, x.P + x.L.dec_norm_b, x.P + x.L.out_w, oth,
+                             x.G + x.L.out_w, x.G + x.L.out_b, x.G + x.L.dec_norm_g, x.G + x.L.dec_norm_b, x.M, x.st));
+    } else {
+      GT_TRY(ln_bwd(cur, last, pl.mf_d, pl.rf_d, x.P + x.L.dec_norm_g, oth, nullptr, x.G + x.L.dec_norm_g,
+                    x.G + x.L.dec_norm_b, x.M, d, none, 0, x.st));
+    }
     grad_bucket_ready(x.c, BK_HEAD, 0, x.st);
     std::swap(cur, oth);
     for (int l = x.c.n_dec - 1; l >= 0; --l) {
@@ -517,7 +545,11 @@ static int backward_all(const Ctx &x, const Plan &pl, const float *src, const fl
       grad_bucket_ready(x.c, BK_DEC_LAYER, l, x.st);
       std::swap(cur, oth);
     }
-    GT_TRY(input_layer_bwd(x, pl, cur, pl.r0d, tgt_in, E, x.L.in_dec_w, x.L.in_dec_b, SITE_IN_DEC));
+    if (fused_dec_ends)
+      GT_TRY(edge32_stem_bwd(cur, tgt_in, E, x.P + x.L.in_dec_w, x.P + x.L.in_dec_b, x.G + x.L.in_dec_w, x.G + x.L.in_dec_b, x.M,
+                             x.drop(SITE_IN_DEC), x.row0(), x.st));
+    else
+      GT_TRY(input_layer_bwd(x, pl, cur, pl.r0d, tgt_in, E, x.L.in_dec_w, x.L.in_dec_b, SITE_IN_DEC));
     // encoder gradient starts from dmem
     GT_CUDA(cudaMemcpyAsync(pl.dxa, pl.dmem, (size_t)x.M * d * sizeof(float), cudaMemcpyDeviceToDevice, x.st));
     cur = pl.dxa; oth = pl.dxb;
@@ -646,6 +678,8 @@ const char *gt_last_error(void) { return g_err.c_str(); }
 int gt_path_kind(const gt_config *cfg) {
   if (validate_config(cfg)) return -1;
   if (cfg->precision != GT_PREC_BF16) return GT_PATH_FP32_SIMT;
+  // encoder-decoder, d_model = 32, head dim 2 / 4 / 8: every block of every layer runs in the fused tcgen05 kernels
+  if (cfg->n_dec > 0 && tc_encoder_supported(*cfg) && tc_dec_attn_supported(*cfg) && cfg->e_tgt == 27) return GT_PATH_FUSED_D32;
   if (!tc_shape_supported(*cfg, nullptr)) return GT_PATH_GEMM_TC;
   return cfg->d_model == 256 ? GT_PATH_FUSED_D256 : GT_PATH_FUSED_D32;
 }
@@ -738,6 +772,10 @@ int gt_train_step(const gt_config *cfg, const float *params, const float *pe, co
   if (cfg->n_dec > 0) {
     GT_TRY(shift_right(y, pl.tgt_in, n_seq, cfg->e_tgt, x.st));
     tgt_in = pl.tgt_in;
+  }
+  if (cfg->n_dec > 0 && dec_fused_edges(x, pl)) {
+    GT_TRY(forward_all(x, pl, src, tgt_in, hvo, y, hit_loss_penalty, metrics6));
+    return backward_all(x, pl, src, tgt_in, nullptr, pl.dlog);
   }
   GT_TRY(forward_all(x, pl, src, tgt_in, hvo));
   GT_TRY(loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, x.st));
