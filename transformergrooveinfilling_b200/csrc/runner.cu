@@ -606,6 +606,11 @@ static int predict_decode(const Ctx &x, const Plan &pl, float thres, float *hvo_
     float *cur = pl.s_ya, *nxt = pl.s_yb;
     for (int l = 0; l < x.c.n_dec; ++l) {
       const LayerP &p = x.L.dec[l];
+      if (dec32_supported(x.c)) {               // d_model = 32: the whole layer for this token in one kernel (decode32.cu)
+        GT_TRY(dec32_layer_step(x.c, p, x.P, cur, nxt, pl.kv_self[l], pl.kv_cross[l], n, i, x.st));
+        std::swap(cur, nxt);
+        continue;
+      }
       GemmEpi eq; eq.bias = x.P + p.sa.b_in;
       GT_TRY(linear_rows(x, cur, d, x.P + p.sa.w_in, pl.s_q, d, d, n, eq));
       GemmEpi ekv; ekv.bias = x.P + p.sa.b_in + d;        // this token's key | value -> row i of the layer's cache
