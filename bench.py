@@ -416,8 +416,18 @@ def main():
         avg_ms = tot_ms.value / cnt.value
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = fl_launch / (avg_ms / 1e3) / 1e12
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if tr and precision == "bf16":
+                traffic = tr["dram_bytes_per_launch"] * n / tr["per_gpu_batch"]
+                traffic_note = (f"ncu dram bytes of one {tr['kernel']} launch at batch {tr['per_gpu_batch']}"
+                                + ("" if n == tr["per_gpu_batch"] else f", scaled per sequence to batch {n}"))
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
+                "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_note,
+                "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
                 "kernel_share_of_step": tot_ms.value / ms}
     # ---- per-kernel-class breakdown: 3 extra steps with every class bracketed by events (outside the timed regions) ----
