@@ -425,7 +425,9 @@ def main():
                                 + ("" if n == tr["per_gpu_batch"] else f", scaled per sequence to batch {n}"))
         except Exception:
             pass
+        hbm_peak = peaks.get("hbm_gbs", peaks.get("hbm_gb_s", 6550.4))
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "hbm_achieved_gbs": (traffic / (avg_ms / 1e3) / 1e9) if traffic else None, "hbm_peak_gbs": hbm_peak,
                 "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_note,
                 "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
