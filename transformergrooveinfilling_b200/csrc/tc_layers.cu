@@ -676,7 +676,7 @@ template <int D, int DH, int MODE>
 __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
   static_assert(D == 32, "the register-tile column sums assume d_model == 32");
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_h;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   constexpr int LQ = D + 4;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); mbar_init(&bar_h, 1); fence_mbar_init(); }
   for (int i = tid; i < 9 * D + F; i += BWD_THREADS) sG[i] = 0.f;
   if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   const uint32_t aW = smem_u32(sW), aXin = smem_u32(sXin), aX1 = smem_u32(sX1), aDA = smem_u32(sDA), aCtx = smem_u32(sCtx),
                  aDQ = smem_u32(sDQ), aH = smem_u32(sH), aDH = smem_u32(sDH);
   mbar_wait(&bar_w, 0);
-  uint32_t ph = 0;
+  uint32_t ph = 0, phh = 0;                          // parities of bar_mma / bar_h
   const float inv_sqrt_dh = rsqrtf((float)dh);
   const float attn_scale = inv_sqrt_dh * 1.4426950408889634f;
   const int nblk = FC / 16;
@@ -856,10 +856,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       fence_after_sync();
 #pragma unroll
       for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1, FC, k), id_kk_fc, k > 0);
-      mma_commit(&bar_mma);
+      mma_commit(&bar_h);
     }
+    // The H recompute of chunk c + 1 is issued BEFORE the dx1 / dW1 / dW2 MMAs of chunk c and signals its own barrier, so the
+    // H epilogue of chunk c + 1 runs on the CUDA cores while those MMAs are still in the tensor pipe.  The H image is double
+    // buffered for that (odd chunks use the ctx | dqkv image region, which is dead until the attention phase); every other
+    // buffer is protected by the in-order completion the dH commit of the next chunk waits for.
     for (int c = 0; c < nchunk; ++c) {
-      mbar_wait(&bar_mma, ph); ph ^= 1;               // H(c) accumulator ready (and every earlier MMA retired)
+      uint8_t *sHc = (c & 1) ? sCtx : sH;
+      const uint32_t aHc = (c & 1) ? aCtx : aH;
+      mbar_wait(&bar_h, phh); phh ^= 1;               // H(c) accumulator ready
       fence_after_sync();
       uint32_t mask = 0;                              // (kept && h > 0) bits of this thread's (<= 2) 16-column blocks
       {
@@ -893,8 +899,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
             pk[j >> 1] = pack_bf16(h0, h1);
             pk[(j >> 1) + 1] = pack_bf16(h2, h3);
           }
-          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4 *>(sHc + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(sHc + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           mask |= bits << (16 * t);
         }
       }
@@ -944,20 +950,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
+        if (c + 1 < nchunk) {                         // H(c + 1) first, with its own barrier (t_big: the dH(c) accumulator is drained)
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), id_kk_fc, k > 0);
+          mma_commit(&bar_h);
+        }
         const uint32_t w1c = aW + io.w1 + (uint32_t)c * FC * D * 2u;
         for (int k = 0; k < FC / 16; ++k)             // dx1 += dH . W1[chunk, :]     (B: MN-major view of the W1 chunk image [FC x D])
           mma_bf16_ss(t_sa, desc_a128(aDH, k), desc_mn(w1c, FC, k), id_kmn_d, (c | k) > 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                 // contract over the tile's 128 tokens
           mma_bf16_ss(t_dw1 + 32u * c, desc_mn(aDH, 128, k), desc_mn(aX1, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);   // dW1[chunk]   += dH^T x1
-          mma_bf16_ss(t_dw2 + 32u * c, desc_mn(aH, 128, k), desc_mn(aDA, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);    // dW2^T[chunk] += H^T da2
+          mma_bf16_ss(t_dw2 + 32u * c, desc_mn(aHc, 128, k), desc_mn(aDA, 128, k), id_mnmn_d, k > 0 ? 1u : acc0);   // dW2^T[chunk] += H^T da2
         }
-        if (c + 1 < nchunk) {
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k)
-            mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), id_kk_fc, k > 0);
-        }
-        mma_commit(&bar_mma);
+        if (c + 1 == nchunk) mma_commit(&bar_mma);    // earlier chunks: covered by the dH commit of the next chunk
       }
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // dx1 complete, all weight-gradient MMAs of this tile retired
