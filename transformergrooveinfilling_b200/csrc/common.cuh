@@ -179,6 +179,10 @@ struct AttnArgs {
 };
 int attention_fwd(const AttnArgs &a, cudaStream_t st);
 int attention_bwd(const AttnArgs &a, cudaStream_t st);
+// the same contract on mma.sync with bf16 operands (attn_mma.cu): head dims 16 / 32 / 64 / 128, even leading dimensions
+bool attention_tc_supported(const AttnArgs &a);
+int attention_fwd_tc(const AttnArgs &a, cudaStream_t st);
+int attention_bwd_tc(const AttnArgs &a, cudaStream_t st);
 
 // y = LN(res + dropout(a)) ; u = res + dropout(a) saved when u != nullptr
 int ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, float *u, float *y,

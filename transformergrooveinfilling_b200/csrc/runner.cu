@@ -287,6 +287,14 @@ static AttnArgs attn_args(const Ctx &x, const float *q, int64_t ldq, const float
   return a;
 }
 
+// bf16 mode: attention on mma.sync (attn_mma.cu) for head dims 16 / 32 / 64 / 128; fp32 mode and other head dims: the fp32 kernels
+static int attn_fwd(const Ctx &x, const AttnArgs &a) {
+  return (x.tc && attention_tc_supported(a)) ? attention_fwd_tc(a, x.st) : attention_fwd(a, x.st);
+}
+static int attn_bwd(const Ctx &x, const AttnArgs &a) {
+  return (x.tc && attention_tc_supported(a)) ? attention_bwd_tc(a, x.st) : attention_bwd(a, x.st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -310,7 +318,7 @@ static int enc_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *xin)
   const int d = x.c.d_model;
   GemmEpi e; e.bias = x.P + p.sa.b_in;
   GT_TRY(linear(x, xin, d, x.P + p.sa.w_in, b.qkv, 3 * d, e));
-  GT_TRY(attention_fwd(attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 0, site_id(0, li, 0)), x.st));
+  GT_TRY(attn_fwd(x, attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 0, site_id(0, li, 0))));
   GemmEpi eo; eo.bias = x.P + p.sa.b_out;
   GT_TRY(linear(x, b.ctx, d, x.P + p.sa.w_out, pl.a, d, eo));
   GT_TRY(ln_fwd(pl.a, xin, x.P + p.g1, x.P + p.be1, b.u1, b.x1, b.m1, b.r1, x.M, d, x.drop(site_id(0, li, 1)), x.row0(), x.st));
@@ -330,7 +338,7 @@ static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin)
   }
   GemmEpi e; e.bias = x.P + p.sa.b_in;
   GT_TRY(linear(x, yin, d, x.P + p.sa.w_in, b.qkv, 3 * d, e));
-  GT_TRY(attention_fwd(attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 1, site_id(1, li, 0)), x.st));
+  GT_TRY(attn_fwd(x, attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, b.ctx, 1, site_id(1, li, 0))));
   GemmEpi eo; eo.bias = x.P + p.sa.b_out;
   GT_TRY(linear(x, b.ctx, d, x.P + p.sa.w_out, pl.a, d, eo));
   GT_TRY(ln_fwd(pl.a, yin, x.P + p.g1, x.P + p.be1, b.u1, b.x1, b.m1, b.r1, x.M, d, x.drop(site_id(1, li, 1)), x.row0(), x.st));
@@ -339,7 +347,7 @@ static int dec_layer_fwd(const Ctx &x, const Plan &pl, int li, const float *yin)
   GT_TRY(linear(x, b.x1, d, x.P + p.ca.w_in, b.qc, d, eq));
   GemmEpi ekv; ekv.bias = x.P + p.ca.b_in + d;
   GT_TRY(linear(x, pl.mem, d, x.P + p.ca.w_in + (int64_t)d * d, b.kvc, 2 * d, ekv));
-  GT_TRY(attention_fwd(attn_args(x, b.qc, d, b.kvc, b.kvc + d, 2 * d, b.ctx2, 0, site_id(1, li, 4)), x.st));
+  GT_TRY(attn_fwd(x, attn_args(x, b.qc, d, b.kvc, b.kvc + d, 2 * d, b.ctx2, 0, site_id(1, li, 4))));
   GemmEpi eco; eco.bias = x.P + p.ca.b_out;
   GT_TRY(linear(x, b.ctx2, d, x.P + p.ca.w_out, pl.a, d, eco));
   GT_TRY(ln_fwd(pl.a, b.x1, x.P + p.g2, x.P + p.be2, b.u2, b.x2, b.m2, b.r2, x.M, d, x.drop(site_id(1, li, 5)), x.row0(), x.st));
@@ -451,7 +459,7 @@ static int enc_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *xin,
   AttnArgs a = attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, nullptr, 0, site_id(0, li, 0));
   a.d_o = pl.dctx; a.ld_do = d;
   a.dq = pl.dqkv; a.dk = pl.dqkv + d; a.dv = pl.dqkv + 2 * d; a.ld_dq = a.ld_dk = a.ld_dv = 3 * d;
-  GT_TRY(attention_bwd(a, x.st));
+  GT_TRY(attn_bwd(x, a));
   GemmEpi e1; e1.residual = pl.du; e1.ld_res = d;
   GT_TRY(linear_dgrad(x, pl.dqkv, 3 * d, x.P + p.sa.w_in, d, dx_in, e1));
   return linear_wgrad(x, pl.dqkv, 3 * d, 3 * d, xin, d, d, x.G + p.sa.w_in, x.G + p.sa.b_in);
@@ -481,7 +489,7 @@ static int dec_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *yin,
   AttnArgs c = attn_args(x, b.qc, d, b.kvc, b.kvc + d, 2 * d, nullptr, 0, site_id(1, li, 4));
   c.d_o = pl.dctx; c.ld_do = d;
   c.dq = pl.dqc; c.ld_dq = d; c.dk = pl.dkvc; c.dv = pl.dkvc + d; c.ld_dk = c.ld_dv = 2 * d;
-  GT_TRY(attention_bwd(c, x.st));
+  GT_TRY(attn_bwd(x, c));
   // d(x1) = du (residual) + dqc Wq ; dmem += dkvc Wkv
   GemmEpi e1; e1.residual = pl.du; e1.ld_res = d;
   GT_TRY(linear_dgrad(x, pl.dqc, d, x.P + p.ca.w_in, d, dx_in, e1));          // dx_in used as scratch for d(x1)
@@ -497,7 +505,7 @@ static int dec_layer_bwd(const Ctx &x, const Plan &pl, int li, const float *yin,
   AttnArgs a = attn_args(x, b.qkv, 3 * d, b.qkv + d, b.qkv + 2 * d, 3 * d, nullptr, 1, site_id(1, li, 0));
   a.d_o = pl.dctx; a.ld_do = d;
   a.dq = pl.dqkv; a.dk = pl.dqkv + d; a.dv = pl.dqkv + 2 * d; a.ld_dq = a.ld_dk = a.ld_dv = 3 * d;
-  GT_TRY(attention_bwd(a, x.st));
+  GT_TRY(attn_bwd(x, a));
   GemmEpi e3; e3.residual = pl.du; e3.ld_res = d;
   GT_TRY(linear_dgrad(x, pl.dqkv, 3 * d, x.P + p.sa.w_in, d, dx_tmp, e3));
   GT_TRY(linear_wgrad(x, pl.dqkv, 3 * d, 3 * d, yin, d, d, x.G + p.sa.w_in, x.G + p.sa.b_in));
