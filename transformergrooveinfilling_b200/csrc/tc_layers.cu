@@ -291,19 +291,26 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   const float attn_scale = rsqrtf((float)dh) * 1.4426950408889634f;   // 1/sqrt(dh) * log2(e), folded into q
   const float keep_scale = a.d_attn.scale;
 
+  // this thread's 8-column chunk of the NEXT tile's input row (and memory row), fetched a whole tile time ahead: the tile
+  // would otherwise start with a load of rows nobody has touched yet
+  uint4 xnext = make_uint4(0, 0, 0, 0), mnext = make_uint4(0, 0, 0, 0);
+  auto fetch_tile = [&](int t) {
+    const int64_t r = (int64_t)t * TC_TILE + row;
+    xnext = make_uint4(0, 0, 0, 0); mnext = make_uint4(0, 0, 0, 0);
+    if (t < a.n_tiles && r < a.M) {
+      xnext = pack8(a.x_in + r * D + part * 8);
+      if constexpr (CROSS) mnext = pack8(a.mem + r * D + part * 8);
+    }
+  };
+  fetch_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t grow = (int64_t)tile * TC_TILE + row;
     const bool valid = grow < a.M;
     // ---- P0: x_in tile -> bf16 A operand (8 columns per thread) ----
     {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (valid) v = pack8(a.x_in + grow * D + part * 8);
-      *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, part * 8, 128)) = v;
-      if constexpr (CROSS) {                           // cross-attention: keys / values come from the encoder memory tile
-        uint4 m = make_uint4(0, 0, 0, 0);
-        if (valid) m = pack8(a.mem + grow * D + part * 8);
-        *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 8, 128)) = m;
-      }
+      *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, part * 8, 128)) = xnext;
+      if constexpr (CROSS) *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 8, 128)) = mnext;   // keys / values come from the encoder memory tile
+      fetch_tile(tile + (int)gridDim.x);
     }
     fence_async_smem();
     fence_before_sync();
@@ -619,7 +626,7 @@ __host__ __device__ inline BwdSmem bwd_smem(int D, int F, bool mma) {
   s.par = al128(tc_img(D, F).total);
   s.gpar = al128(s.par + (uint32_t)(9 * D + F) * 4u);
   s.stat = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);   // per-row (mean1, rstd1)
-  s.xin = al128(s.stat + 128u * 2u * 4u);
+  s.xin = al128(s.stat + 2u * 128u * 4u * 16u);         // two ping-pong buffers of [128 rows][4 parts] float4
   s.x1 = s.xin + 128u * D * 2u;
   s.da = s.x1 + 128u * D * 2u;
   s.ctx = s.da + 128u * D * 2u;
@@ -693,7 +700,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   float *sG = reinterpret_cast<float *>(smem + sp.gpar);       // gradient partials, same order as sPar
   float *g_bqkv = sG, *g_bo = sG + 3 * D, *g_b1 = g_bo + D, *g_b2 = g_b1 + F, *g_g1 = g_b2 + D, *g_be1 = g_g1 + D,
         *g_g2 = g_be1 + D, *g_be2 = g_g2 + D;
-  float *sStat = reinterpret_cast<float *>(smem + sp.stat);
+  float4 *sEx = reinterpret_cast<float4 *>(smem + sp.stat);     // [2][128 rows][4 parts]: row-statistics exchange (ping-pong)
+  int xphase = 0;
+  // sum of a float4 over the four column parts of this token row
+  auto xsum = [&](const float4 v) -> float4 {
+    float4 *buf = sEx + xphase * 512;
+    xphase ^= 1;
+    buf[row * 4 + part] = v;
+    __syncthreads();
+    const float4 p0 = buf[row * 4], p1 = buf[row * 4 + 1], p2 = buf[row * 4 + 2], p3 = buf[row * 4 + 3];
+    return make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w));
+  };
   uint8_t *sXin = smem + sp.xin, *sX1 = smem + sp.x1, *sDA = smem + sp.da, *sCtx = smem + sp.ctx, *sDQ = smem + sp.dq;
   float *sQ = reinterpret_cast<float *>(smem + sp.q);
   float *sK = reinterpret_cast<float *>(smem + sp.k);
@@ -746,105 +763,94 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     const int64_t grow = (int64_t)tile * TC_TILE + row;
     const bool valid = grow < a.M;
     const uint32_t acc0 = iter > 0 ? 1u : 0u;
-    float du[D];                       // part 0: gradient w.r.t. the LayerNorm input currently being processed
-    // ---- B0: part 0: LN2 backward ; part 1: x1 = LN1(u1) ; part 2: stage x_in ----
-    if (part == 0 && ATTN_ONLY) {
-      // attention block alone: the incoming gradient is already dL/d(LayerNorm1 output)
-#pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float4 g = valid ? *reinterpret_cast<const float4 *>(a.dy + grow * D + c) : make_float4(0, 0, 0, 0);
-        du[c] = g.x; du[c + 1] = g.y; du[c + 2] = g.z; du[c + 3] = g.w;
-      }
-    } else if (part == 0) {
-      float xh[D];
-      float s1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u2_in + grow * D + c) : make_float4(0, 0, 0, 0);
-        xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
-        s1 += (t.x + t.y) + (t.z + t.w);
-        float4 g = valid ? *reinterpret_cast<const float4 *>(a.dy + grow * D + c) : make_float4(0, 0, 0, 0);
-        du[c] = g.x; du[c + 1] = g.y; du[c + 2] = g.z; du[c + 3] = g.w;
-      }
-      const float mu = s1 * (1.f / D);
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
-      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
-      float m1 = 0.f, m2 = 0.f;
-      float w[32];
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        xh[c] *= rs;
-        w[c] = du[c] * xh[c];                        // d gamma contribution
-        float g = du[c] * p_g2[c];
-        m1 += g; m2 = fmaf(g, xh[c], m2);
-      }
-      m1 *= (1.f / D); m2 *= (1.f / D);
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_g2[lane], t); }
-#pragma unroll
-      for (int c = 0; c < D; ++c) w[c] = du[c];
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_be2[lane], t); }
-      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
-#pragma unroll
-      for (int c = 0; c < D; c += 4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) du[c + j] = rs * (du[c + j] * p_g2[c + j] - m1 - xh[c + j] * m2);
-        float k0, k1, k2, k3;
-        drop4(a.d2, e0 + c, k0, k1, k2, k3);
-        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1; w[c + 2] = du[c + 2] * k2; w[c + 3] = du[c + 3] * k3;   // da2 = grad wrt the FFN2 output (+bias)
-      }
-#pragma unroll
-      for (int c = 0; c < D; c += 8)
-        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
-            make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_b2[lane], t); }
-    } else if (part == 1 && MODE == TC_MODE_FFN) {
-      // FFN block alone: its input x_in IS x1 (no LayerNorm to recompute)
-#pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (valid) v = pack8(a.x_in + grow * D + c);
-        *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) = v;
-      }
-    } else if (part == 1 && ATTN_ONLY) {
-      if constexpr (CROSS) {                           // encoder memory tile (keys / values) -> the (otherwise unused) x1 image
-#pragma unroll
-        for (int c = 0; c < D; c += 8) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) v = pack8(a.mem + grow * D + c);
-          *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) = v;
+    // Every row-wise phase is split four ways: thread (row, part) owns columns [8 part, 8 part + 8) of its token row; row
+    // statistics are combined through xsum() (one __syncthreads per exchange).  All 16 warps work in the LayerNorm phases
+    // instead of the 4 warps of part 0, and the three column sums of a phase share ONE 31-shuffle transpose.
+    const int c0 = part * 8;
+    float du[8];                       // gradient w.r.t. the LayerNorm input currently being processed (this thread's 8 columns)
+    float mean1 = 0.f, rstd1 = 1.f;    // LayerNorm1 statistics of this row
+    // ---- B0: LN2 backward ; x1 = LN1(u1) ; stage x_in (and the memory tile / the FFN input) ----
+    {
+      float dyv[8], u2v[8], u1v[8];
+      auto load8 = [&](const float *src, float (&o)[8]) {
+        const float4 t0 = valid ? *reinterpret_cast<const float4 *>(src + grow * D + c0) : make_float4(0, 0, 0, 0);
+        const float4 t1 = valid ? *reinterpret_cast<const float4 *>(src + grow * D + c0 + 4) : make_float4(0, 0, 0, 0);
+        o[0] = t0.x; o[1] = t0.y; o[2] = t0.z; o[3] = t0.w; o[4] = t1.x; o[5] = t1.y; o[6] = t1.z; o[7] = t1.w;
+      };
+      load8(a.dy, dyv);
+      {
+        // the row-wise phases start with plain loads of rows nobody has touched yet: pull the NEXT tile's rows into L2 now,
+        // a whole tile time ahead (part p fetches array p: one 128-byte line per row)
+        const int64_t nrow = grow + (int64_t)gridDim.x * TC_TILE;
+        if (nrow < a.M) {
+          const float *pf = part == 0 ? a.dy : part == 1 ? (ATTN_ONLY ? a.u1_in : a.u2_in) : part == 2 ? a.x_in : (MODE == TC_MODE_LAYER ? a.u1_in : (CROSS ? a.mem : a.dy));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + nrow * D));
         }
       }
-    } else if (part == 1) {
-      float xh[D];
-      float s1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
-        xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
-        s1 += (t.x + t.y) + (t.z + t.w);
-      }
-      const float mu = s1 * (1.f / D);
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; ++c) { xh[c] -= mu; q = fmaf(xh[c], xh[c], q); }
-      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
-      sStat[row * 2] = mu; sStat[row * 2 + 1] = rs;
-#pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = xh[c + j] * rs * p_g1[c + j] + p_be1[c + j];
-        *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c, 128)) =
-            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-      }
-    } else if (part == 2 && MODE != TC_MODE_FFN) {
-#pragma unroll
-      for (int c = 0; c < D; c += 8) {
+      if constexpr (MODE != TC_MODE_FFN) {           // x_in tile -> bf16 A operand of the q|k|v recompute
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (valid) v = pack8(a.x_in + grow * D + c);
-        *reinterpret_cast<uint4 *>(sXin + kmajor_off(row, c, 128)) = v;
+        if (valid) v = pack8(a.x_in + grow * D + c0);
+        *reinterpret_cast<uint4 *>(sXin + kmajor_off(row, c0, 128)) = v;
+      }
+      if constexpr (MODE == TC_MODE_FFN || CROSS) {   // FFN block: its input IS x1 ; cross-attention: the encoder-memory tile
+        const float *src = MODE == TC_MODE_FFN ? a.x_in : a.mem;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = pack8(src + grow * D + c0);
+        *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c0, 128)) = v;
+      }
+      if constexpr (ATTN_ONLY) {
+        // attention block alone: the incoming gradient is already dL/d(LayerNorm1 output)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) du[j] = dyv[j];
+      } else {
+        load8(a.u2_in, u2v);
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { e.x += u2v[j]; e.y = fmaf(u2v[j], u2v[j], e.y); }
+        if constexpr (MODE == TC_MODE_LAYER) {
+          load8(a.u1_in, u1v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { e.z += u1v[j]; e.w = fmaf(u1v[j], u1v[j], e.w); }
+        }
+        e = xsum(e);
+        const float mean2 = e.x * (1.f / D), rstd2 = rsqrtf(fmaxf(e.y * (1.f / D) - mean2 * mean2, 0.f) + LN_EPS);
+        if constexpr (MODE == TC_MODE_LAYER) {
+          mean1 = e.z * (1.f / D);
+          rstd1 = rsqrtf(fmaxf(e.w * (1.f / D) - mean1 * mean1, 0.f) + LN_EPS);
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = (u1v[j] - mean1) * rstd1 * p_g1[c0 + j] + p_be1[c0 + j];
+          *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c0, 128)) =
+              make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+        }
+        float w[32];
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          u2v[j] = (u2v[j] - mean2) * rstd2;           // x-hat
+          w[j] = dyv[j] * u2v[j];                      // d gamma contribution
+          w[8 + j] = dyv[j];                           // d beta contribution
+          const float g = dyv[j] * p_g2[c0 + j];
+          m.x += g; m.y = fmaf(g, u2v[j], m.y);
+        }
+        m = xsum(m);
+        const float m1 = m.x * (1.f / D), m2 = m.y * (1.f / D);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) du[j] = rstd2 * (dyv[j] * p_g2[c0 + j] - m1 - u2v[j] * m2);
+        const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D + c0);
+        float k0, k1, k2, k3;
+        drop4(a.d2, e0, k0, k1, k2, k3);
+        w[16] = du[0] * k0; w[17] = du[1] * k1; w[18] = du[2] * k2; w[19] = du[3] * k3;     // da2 = grad wrt the FFN2 output (+bias)
+        drop4(a.d2, e0 + 4, k0, k1, k2, k3);
+        w[20] = du[4] * k0; w[21] = du[5] * k1; w[22] = du[6] * k2; w[23] = du[7] * k3;
+#pragma unroll
+        for (int j = 24; j < 32; ++j) w[j] = 0.f;
+        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c0, 128)) =
+            make_uint4(pack_bf16(w[16], w[17]), pack_bf16(w[18], w[19]), pack_bf16(w[20], w[21]), pack_bf16(w[22], w[23]));
+        const float t = warp_colsum32(w, lane);
+        if (lane < 8) atomicAdd(&g_g2[c0 + lane], t);
+        else if (lane < 16) atomicAdd(&g_be2[c0 + lane - 8], t);
+        else if (lane < 24) atomicAdd(&g_b2[c0 + lane - 16], t);
       }
     }
     fence_async_smem();
@@ -971,15 +977,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     fence_after_sync();
     if constexpr (MODE != 0) {
       // FFN block alone: dx = du2 (residual path) + dx1 (FFN path); nothing else to do for this tile
-      if (part == 0) {
-        float acc[D];
-#pragma unroll
-        for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+      {
+        float acc[8];
+        tmem_ld8(t_sa + lane_off + (uint32_t)c0, acc);
         tmem_ld_wait();
         if (valid) {
-#pragma unroll
-          for (int c = 0; c < D; c += 4)
-            *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(du[c] + acc[c], du[c + 1] + acc[c + 1], du[c + 2] + acc[c + 2], du[c + 3] + acc[c + 3]);
+          *reinterpret_cast<float4 *>(a.dx + grow * D + c0) = make_float4(du[0] + acc[0], du[1] + acc[1], du[2] + acc[2], du[3] + acc[3]);
+          *reinterpret_cast<float4 *>(a.dx + grow * D + c0 + 4) = make_float4(du[4] + acc[4], du[5] + acc[5], du[6] + acc[6], du[7] + acc[7]);
         }
       }
       fence_before_sync();
@@ -987,68 +991,60 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       continue;
     }
     }  // !ATTN_ONLY
-    // ---- B2: LN1 backward (part 0) ----
-    if (part == 0) {
-      float acc[D], xh[D];
-      float mean1, rstd1;
-      if constexpr (ATTN_ONLY) {
+    // ---- B2: LN1 backward (all parts, 8 columns each) ----
+    {
+      float u1v[8], xh[8];
+      {
+        const float4 t0 = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c0) : make_float4(0, 0, 0, 0);
+        const float4 t1 = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c0 + 4) : make_float4(0, 0, 0, 0);
+        u1v[0] = t0.x; u1v[1] = t0.y; u1v[2] = t0.z; u1v[3] = t0.w; u1v[4] = t1.x; u1v[5] = t1.y; u1v[6] = t1.z; u1v[7] = t1.w;
+      }
+      if constexpr (ATTN_ONLY) {                     // no forward recompute ran in B0: LayerNorm1 statistics from u1 here
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = 0.f;
-        float s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-          float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
-          xh[c] = t.x; xh[c + 1] = t.y; xh[c + 2] = t.z; xh[c + 3] = t.w;
-          s1 += (t.x + t.y) + (t.z + t.w);
-        }
-        mean1 = s1 * (1.f / D);
-        float q = 0.f;
-#pragma unroll
-        for (int c = 0; c < D; ++c) { const float t = xh[c] - mean1; q = fmaf(t, t, q); }
-        rstd1 = rsqrtf(q * (1.f / D) + LN_EPS);
+        for (int j = 0; j < 8; ++j) { e.x += u1v[j]; e.y = fmaf(u1v[j], u1v[j], e.y); }
+        e = xsum(e);
+        mean1 = e.x * (1.f / D);
+        rstd1 = rsqrtf(fmaxf(e.y * (1.f / D) - mean1 * mean1, 0.f) + LN_EPS);
       } else {
-#pragma unroll
-        for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+        float acc[8];
+        tmem_ld8(t_sa + lane_off + (uint32_t)c0, acc);
         tmem_ld_wait();
-        mean1 = sStat[row * 2]; rstd1 = sStat[row * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) du[j] += acc[j];  // grad wrt x1 = residual path + FFN path
       }
-      float m1 = 0.f, m2 = 0.f;
       float w[32];
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float4 t = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c) : make_float4(0, 0, 0, 0);
-        xh[c] = (t.x - mean1) * rstd1; xh[c + 1] = (t.y - mean1) * rstd1; xh[c + 2] = (t.z - mean1) * rstd1; xh[c + 3] = (t.w - mean1) * rstd1;
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = (u1v[j] - mean1) * rstd1;
+        w[j] = du[j] * xh[j];
+        w[8 + j] = du[j];
+        const float g = du[j] * p_g1[c0 + j];
+        m.x += g; m.y = fmaf(g, xh[j], m.y);
       }
+      m = xsum(m);
+      const float m1 = m.x * (1.f / D), m2 = m.y * (1.f / D);
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        du[c] += acc[c];                              // grad wrt x1 = residual path + FFN path
-        w[c] = du[c] * xh[c];
-        float g = du[c] * p_g1[c];
-        m1 += g; m2 = fmaf(g, xh[c], m2);
-      }
-      m1 *= (1.f / D); m2 *= (1.f / D);
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_g1[lane], t); }
+      for (int j = 0; j < 8; ++j) du[j] = rstd1 * (du[j] * p_g1[c0 + j] - m1 - xh[j] * m2);
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D + c0);
+      float k0, k1, k2, k3;
+      drop4(a.d1, e0, k0, k1, k2, k3);
+      w[16] = du[0] * k0; w[17] = du[1] * k1; w[18] = du[2] * k2; w[19] = du[3] * k3;       // da1 = grad wrt the out-proj output (+bias)
+      drop4(a.d1, e0 + 4, k0, k1, k2, k3);
+      w[20] = du[4] * k0; w[21] = du[5] * k1; w[22] = du[6] * k2; w[23] = du[7] * k3;
 #pragma unroll
-      for (int c = 0; c < D; ++c) w[c] = du[c];
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_be1[lane], t); }
-      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
-#pragma unroll
-      for (int c = 0; c < D; c += 4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) du[c + j] = rstd1 * (du[c + j] * p_g1[c + j] - m1 - xh[c + j] * m2);
-        float k0, k1, k2, k3;
-        drop4(a.d1, e0 + c, k0, k1, k2, k3);
-        w[c] = du[c] * k0; w[c + 1] = du[c + 1] * k1; w[c + 2] = du[c + 2] * k2; w[c + 3] = du[c + 3] * k3;   // da1 = grad wrt the out-proj output (+bias)
-      }
-#pragma unroll
-      for (int c = 0; c < D; c += 8)
-        *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c, 128)) =
-            make_uint4(pack_bf16(w[c], w[c + 1]), pack_bf16(w[c + 2], w[c + 3]), pack_bf16(w[c + 4], w[c + 5]), pack_bf16(w[c + 6], w[c + 7]));
+      for (int j = 24; j < 32; ++j) w[j] = 0.f;
+      *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c0, 128)) =
+          make_uint4(pack_bf16(w[16], w[17]), pack_bf16(w[18], w[19]), pack_bf16(w[20], w[21]), pack_bf16(w[22], w[23]));
       if (valid) {                                    // park du1 (residual path into dx) in the output buffer
-#pragma unroll
-        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(du[c], du[c + 1], du[c + 2], du[c + 3]);
+        *reinterpret_cast<float4 *>(a.dx + grow * D + c0) = make_float4(du[0], du[1], du[2], du[3]);
+        *reinterpret_cast<float4 *>(a.dx + grow * D + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
       }
-      { float t = warp_colsum32(w, lane); atomicAdd(&g_bo[lane], t); }
+      const float t = warp_colsum32(w, lane);
+      if (lane < 8) atomicAdd(&g_g1[c0 + lane], t);
+      else if (lane < 16) atomicAdd(&g_be1[c0 + lane - 8], t);
+      else if (lane < 24) atomicAdd(&g_bo[c0 + lane - 16], t);
     }
     fence_async_smem();
     fence_before_sync();
@@ -1217,17 +1213,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         }
       }
     }
-    if (part == 0) {
-      float acc[D];
-#pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_sa + lane_off + (uint32_t)cb, acc + cb);
+    {                                                 // dx = du1 (parked by this same thread) + dx_in
+      float acc[8];
+      tmem_ld8(t_sa + lane_off + (uint32_t)c0, acc);
       tmem_ld_wait();
       if (valid) {
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-          float4 t = *reinterpret_cast<const float4 *>(a.dx + grow * D + c);
-          *reinterpret_cast<float4 *>(a.dx + grow * D + c) = make_float4(t.x + acc[c], t.y + acc[c + 1], t.z + acc[c + 2], t.w + acc[c + 3]);
-        }
+        const float4 t0 = *reinterpret_cast<const float4 *>(a.dx + grow * D + c0), t1 = *reinterpret_cast<const float4 *>(a.dx + grow * D + c0 + 4);
+        *reinterpret_cast<float4 *>(a.dx + grow * D + c0) = make_float4(t0.x + acc[0], t0.y + acc[1], t0.z + acc[2], t0.w + acc[3]);
+        *reinterpret_cast<float4 *>(a.dx + grow * D + c0 + 4) = make_float4(t1.x + acc[4], t1.y + acc[5], t1.z + acc[6], t1.w + acc[7]);
       }
     }
     fence_before_sync();
