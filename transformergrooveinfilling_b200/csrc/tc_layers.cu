@@ -769,6 +769,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     const int c0 = part * 8;
     float du[8];                       // gradient w.r.t. the LayerNorm input currently being processed (this thread's 8 columns)
     float mean1 = 0.f, rstd1 = 1.f;    // LayerNorm1 statistics of this row
+    float u1k[8];                      // whole layer: this thread's u1 columns, loaded in B0 and kept for B2 (no second round trip)
     // ---- B0: LN2 backward ; x1 = LN1(u1) ; stage x_in (and the memory tile / the FFN input) ----
     {
       float dyv[8], u2v[8], u1v[8];
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
           rstd1 = rsqrtf(fmaxf(e.w * (1.f / D) - mean1 * mean1, 0.f) + LN_EPS);
           float y[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = (u1v[j] - mean1) * rstd1 * p_g1[c0 + j] + p_be1[c0 + j];
+          for (int j = 0; j < 8; ++j) { u1k[j] = u1v[j]; y[j] = (u1v[j] - mean1) * rstd1 * p_g1[c0 + j] + p_be1[c0 + j]; }
           *reinterpret_cast<uint4 *>(sX1 + kmajor_off(row, c0, 128)) =
               make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
         }
@@ -994,7 +995,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     // ---- B2: LN1 backward (all parts, 8 columns each) ----
     {
       float u1v[8], xh[8];
-      {
+      if constexpr (MODE == TC_MODE_LAYER) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u1v[j] = u1k[j];
+      } else {
         const float4 t0 = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c0) : make_float4(0, 0, 0, 0);
         const float4 t1 = valid ? *reinterpret_cast<const float4 *>(a.u1_in + grow * D + c0 + 4) : make_float4(0, 0, 0, 0);
         u1v[0] = t0.x; u1v[1] = t0.y; u1v[2] = t0.z; u1v[3] = t0.w; u1v[4] = t1.x; u1v[5] = t1.y; u1v[6] = t1.z; u1v[7] = t1.w;
