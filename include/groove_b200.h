@@ -33,9 +33,12 @@ extern "C" {
 
 /* which implementation a configuration runs on (gt_path_kind) */
 #define GT_PATH_FP32_SIMT   0  /* precision fp32: fp32 FMA kernels */
-#define GT_PATH_FUSED_D32   1  /* precision bf16, d_model = 32 encoder-only: fused tcgen05 layer kernels */
+#define GT_PATH_FUSED_D32   1  /* precision bf16, d_model = 32: fused tcgen05 layer kernels — encoder-only models, and encoder-decoder
+                                  models with head_dim 2 / 4 / 8 (every decoder layer = three fused block launches) */
 #define GT_PATH_FUSED_D256  2  /* precision bf16, d_model = 256, head_dim 16 / 32, encoder-only: weight-streaming fused kernels */
-#define GT_PATH_GEMM_TC     3  /* precision bf16, every other shape incl. encoder-decoder: per-op kernels, contractions on gemm_tc */
+#define GT_PATH_GEMM_TC     3  /* precision bf16, every other shape: per-op kernels, contractions on gemm_tc, attention on mma.sync
+                                  (d_model = 32 encoder-decoder models outside the fused head dims still run their encoder
+                                  stack and decoder FFN blocks in the fused kernels) */
 
 /* Mirrors the constructor arguments of GrooveTransformerEncoder / GrooveTransformer
  * (BGT/models/transformer.py:10-11, :87-88) and params["model"] of train.py:115-143. */
