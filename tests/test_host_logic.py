@@ -186,3 +186,27 @@ def test_sample_sweep_and_params_from_config():
     sym = dict(a[0], experiment="InfillingClosedHH_Symbolic", encoder_only=0)
     p = params_from_config(sym)
     assert p["model"]["embedding_size_src"] == 27 and p["model"]["num_decoder_layers"] == sym["num_encoder_decoder_layers"]
+
+
+def test_bench_flop_accounting_matches_survey():
+    """bench.py's algorithmic FLOPs per sequence are the SURVEY.md §8(d) figures (2 FLOP per MAC, backward = 2x forward)."""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved = (os.dup(1), sys.stdout)                     # bench.py points fd 1 at stderr on import; undo that for pytest
+    try:
+        spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        os.dup2(saved[0], 1)
+        sys.stdout = saved[1]
+    want = {"c1": 8.522e6, "c2": 45.091e6, "c3": 624.968e6, "c4": 659.571e6, "c5": 97.229e6}
+    for k, v in want.items():
+        assert abs(bench.train_flops_per_seq(bench.WORKLOADS[k]) - v) / v < 1e-3, k
+    for k, w in bench.WORKLOADS.items():                # hyper-parameters verbatim from the reference yamls (SURVEY.md §8)
+        assert w["d"] % w["H"] == 0 and w["batch"] % 4 == 0
+    x, y = bench.synth_batch(bench.WORKLOADS["c2"], 8, 1)
+    assert x.shape == (8, 32, 16) and y.shape == (8, 32, 27)
+    hits = y[..., :9]
+    assert set(hits.unique().tolist()) <= {0.0, 1.0}
+    assert float((y[..., 9:18] * (1 - hits)).abs().max()) == 0.0 and float(y[..., 18:].abs().max()) <= 0.5
