@@ -182,18 +182,20 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_fwd_kernel(const float *
       const float lg = a0 + a1;
       if (q < ntok && lane < 27) {
         const int64_t o = (tok0 + q) * 27 + lane;
-        const float sg = 1.f / (1.f + expf(-lg));
+        // one sigmoid serves the three roles (no divergent expf / tanhf / log1pf paths): v = sigmoid(x), o = 0.5 tanh(x) =
+        // sigmoid(2 x) - 0.5, and the hit BCE softplus(h) - h y = h (1 - y) + log(1 + exp(-h)) reuses exp(-h)
+        const float e = __expf(role == 2 ? -2.f * lg : -lg);
+        const float sg = __fdividef(1.f, 1.f + e);
         float out;
         if (role == 0) out = thres >= 0.f ? (sg > thres ? 1.f : 0.f) : lg;
         else if (role == 1) out = sg;
-        else out = 0.5f * tanhf(lg);
+        else out = sg - 0.5f;
         hvo[o] = out;
         if (y != nullptr) {
           const float w = (yh[q] == 1.f) ? 1.f : penalty;
           float dl;
           if (role == 0) {
-            const float sp = fmaxf(lg, 0.f) - lg * yh[q] + log1pf(expf(-fabsf(lg)));
-            a_loss = fmaf(sp, w, a_loss);
+            a_loss = fmaf(fmaf(lg, 1.f - yh[q], __logf(1.f + e)), w, a_loss);
             a_ok += ((sg > 0.5f ? 1.f : 0.f) == yh[q]) ? 1.f : 0.f;
             dl = gscale * w * (sg - yh[q]);
           } else {
@@ -246,7 +248,7 @@ int edge32_tail_fwd_loss(const float *x, const float *gamma, const float *beta, 
 
 // ---- tail backward --------------------------------------------------------------------------------------------------
 // d_in: dL/dlogits when hvo == nullptr, else dL/d(h, v, o) (the activation derivative is applied here from hvo)
-__global__ void __launch_bounds__(EG_WARPS * 32) tail32_bwd_kernel(const float *__restrict__ d_in, const float *__restrict__ hvo,
+__global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const float *__restrict__ d_in, const float *__restrict__ hvo,
                                                                    const float *__restrict__ x, const float *__restrict__ mean,
                                                                    const float *__restrict__ rstd, const float *__restrict__ gamma,
                                                                    const float *__restrict__ beta, const float *__restrict__ Wout,
@@ -254,11 +256,10 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_bwd_kernel(const float *
                                                                    int64_t M) {
   __shared__ __align__(16) float sz[EG_WARPS][EG_TOK][32], sd[EG_WARPS][EG_TOK][32];
   __shared__ float sacc[27 * 32 + 32 + 64];
+  __shared__ float sWc[28 * 32];                    // W_out [27][32] (+ a zero row): lane c reads column c, conflict-free
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = lane / 9;
-  float wc[28];
-#pragma unroll
-  for (int j = 0; j < 28; ++j) wc[j] = j < 27 ? Wout[j * 32 + lane] : 0.f;
+  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) sWc[i] = i < 27 * 32 ? Wout[i] : 0.f;
   const float gm = gamma[lane], be = beta[lane];
   float accw[32], accb = 0.f, adg = 0.f, adb = 0.f;
 #pragma unroll
@@ -266,17 +267,18 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_bwd_kernel(const float *
   for (int i = threadIdx.x; i < 27 * 32 + 96; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int64_t n_groups = (M + EG_TOK - 1) / EG_TOK;
-  for (int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * EG_WARPS) {
+  const int64_t gstride = (int64_t)gridDim.x * EG_WARPS;
+  // software pipeline: the rows of the warp's NEXT group are loaded before the current group is processed, so the global
+  // load latency (this kernel runs at 16 warps per SM) overlaps a whole group of arithmetic
+  float nx[EG_TOK], nmu[EG_TOK], nrs[EG_TOK], nd[EG_TOK];
+  auto fetch = [&](int64_t g) {
     const int64_t tok0 = g * EG_TOK;
-    const int ntok = (int)min((int64_t)EG_TOK, M - tok0);
-    float xh[EG_TOK], rs[EG_TOK], dq[EG_TOK];
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
-      const bool ok = q < ntok;
-      const float xv = ok ? __ldg(x + (tok0 + q) * 32 + lane) : 0.f;
-      const float mu = ok ? __ldg(mean + tok0 + q) : 0.f;
-      rs[q] = ok ? __ldg(rstd + tok0 + q) : 0.f;
-      xh[q] = (xv - mu) * rs[q];
+      const bool ok = g < n_groups && tok0 + q < M;
+      nx[q] = ok ? __ldg(x + (tok0 + q) * 32 + lane) : 0.f;
+      nmu[q] = ok ? __ldg(mean + tok0 + q) : 0.f;
+      nrs[q] = ok ? __ldg(rstd + tok0 + q) : 0.f;
       float d = 0.f;
       if (ok && lane < 27) {
         d = __ldg(d_in + (tok0 + q) * 27 + lane);
@@ -285,11 +287,25 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_bwd_kernel(const float *
           d *= role == 1 ? a * (1.f - a) : (0.5f - 2.f * a * a);
         }
       }
-      dq[q] = d;
-      sz[warp][q][lane] = ok ? xh[q] * gm + be : 0.f;
-      sd[warp][q][lane] = d;
-      accb += d;
+      nd[q] = d;
     }
+  };
+  int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp;
+  fetch(g);
+  for (; g < n_groups; g += gstride) {
+    const int64_t tok0 = g * EG_TOK;
+    const int ntok = (int)min((int64_t)EG_TOK, M - tok0);
+    float xh[EG_TOK], rs[EG_TOK], dq[EG_TOK];
+#pragma unroll
+    for (int q = 0; q < EG_TOK; ++q) {
+      rs[q] = nrs[q];
+      xh[q] = (nx[q] - nmu[q]) * rs[q];
+      dq[q] = nd[q];
+      sz[warp][q][lane] = q < ntok ? xh[q] * gm + be : 0.f;
+      sd[warp][q][lane] = dq[q];
+      accb += dq[q];
+    }
+    fetch(g + gstride);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
@@ -304,7 +320,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_bwd_kernel(const float *
 #pragma unroll
       for (int j = 0; j < 28; j += 4) {
         const float4 dd = *reinterpret_cast<const float4 *>(&sd[warp][q][j]);
-        dz0 = fmaf(dd.x, wc[j], dz0); dz1 = fmaf(dd.y, wc[j + 1], dz1); dz0 = fmaf(dd.z, wc[j + 2], dz0); dz1 = fmaf(dd.w, wc[j + 3], dz1);
+        dz0 = fmaf(dd.x, sWc[j * 32 + lane], dz0); dz1 = fmaf(dd.y, sWc[(j + 1) * 32 + lane], dz1);
+        dz0 = fmaf(dd.z, sWc[(j + 2) * 32 + lane], dz0); dz1 = fmaf(dd.w, sWc[(j + 3) * 32 + lane], dz1);
       }
       const float dz = dz0 + dz1, gd = dz * gm;
       const float s1 = eg_warp_sum(gd) * (1.f / 32), s2 = eg_warp_sum(gd * xh[q]) * (1.f / 32);
