@@ -356,10 +356,136 @@ __global__ void ln_fwd_kernel(const float *__restrict__ a, const float *__restri
   if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
 }
 
+// ---- d_model a multiple of 128: float4 per lane (NV vectors of 4 consecutive columns), one dropout hash per vector ----------
+__device__ __forceinline__ float4 ln_drop4(const Drop &drop, float4 v, uint64_t e) {   // e: element index of v.x (multiple of 4)
+  const uint64_t w = e >> 2;
+  uint32_t lo, hi;
+  hash_quad((uint32_t)w ^ ((uint32_t)(w >> 32) * 0x85EBCA6Bu), drop.key, lo, hi);
+  v.x = ((lo & 0xFFFFu) >= drop.thr) ? v.x * drop.scale : 0.f;
+  v.y = ((lo >> 16) >= drop.thr) ? v.y * drop.scale : 0.f;
+  v.z = ((hi & 0xFFFFu) >= drop.thr) ? v.z * drop.scale : 0.f;
+  v.w = ((hi >> 16) >= drop.thr) ? v.w * drop.scale : 0.f;
+  return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_vec4_kernel(const float *__restrict__ a, const float *__restrict__ res,
+                                                          const float *__restrict__ gamma, const float *__restrict__ beta, float *u_out,
+                                                          float *y, float *mean, float *rstd, int64_t M, Drop drop, int64_t row0) {
+  constexpr int d = NV * 128;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
+  if (row >= M) return;
+  float4 u[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4 *>(a + row * d + c));
+    if (drop.thr) v = ln_drop4(drop, v, (uint64_t)((row0 + row) * d + c));
+    if (res) {
+      const float4 r = __ldg(reinterpret_cast<const float4 *>(res + row * d + c));
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    u[i] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mu = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float t0 = u[i].x - mu, t1 = u[i].y - mu, t2 = u[i].z - mu, t3 = u[i].w - mu;
+    q = fmaf(t0, t0, q); q = fmaf(t1, t1, q); q = fmaf(t2, t2, q); q = fmaf(t3, t3, q);
+  }
+  const float rs = rsqrtf(warp_sum(q) / d + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (u_out) *reinterpret_cast<float4 *>(u_out + row * d + c) = u[i];
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c)), b = __ldg(reinterpret_cast<const float4 *>(beta + c));
+    *reinterpret_cast<float4 *>(y + row * d + c) =
+        make_float4((u[i].x - mu) * rs * g.x + b.x, (u[i].y - mu) * rs * g.y + b.y, (u[i].z - mu) * rs * g.z + b.z, (u[i].w - mu) * rs * g.w + b.w);
+  }
+  if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec4_kernel(const float *__restrict__ dy, const float *__restrict__ u, const float *__restrict__ mean,
+                                                          const float *__restrict__ rstd, const float *__restrict__ gamma, float *du, float *da,
+                                                          float *dgamma, float *dbeta, int64_t M, Drop drop, int64_t row0, int rows_per_warp) {
+  constexpr int d = NV * 128;
+  __shared__ float sm[2 * d];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float4 dg[NV], db[NV], gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dg[i] = make_float4(0, 0, 0, 0); db[i] = dg[i];
+    gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma + (lane + 32 * i) * 4));
+  }
+  const int64_t r_begin = ((int64_t)blockIdx.x * wpb + warp) * rows_per_warp;
+  for (int64_t row = r_begin; row < min(M, r_begin + rows_per_warp); ++row) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 dv = __ldg(reinterpret_cast<const float4 *>(dy + row * d + c)), uv = __ldg(reinterpret_cast<const float4 *>(u + row * d + c));
+      xh[i] = make_float4((uv.x - mu) * rs, (uv.y - mu) * rs, (uv.z - mu) * rs, (uv.w - mu) * rs);
+      g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 = fmaf(g[i].x, xh[i].x, s2); s2 = fmaf(g[i].y, xh[i].y, s2); s2 = fmaf(g[i].z, xh[i].z, s2); s2 = fmaf(g[i].w, xh[i].w, s2);
+      dg[i].x = fmaf(dv.x, xh[i].x, dg[i].x); dg[i].y = fmaf(dv.y, xh[i].y, dg[i].y); dg[i].z = fmaf(dv.z, xh[i].z, dg[i].z); dg[i].w = fmaf(dv.w, xh[i].w, dg[i].w);
+      db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 v = make_float4((g[i].x - s1 - xh[i].x * s2) * rs, (g[i].y - s1 - xh[i].y * s2) * rs, (g[i].z - s1 - xh[i].z * s2) * rs,
+                             (g[i].w - s1 - xh[i].w * s2) * rs);
+      *reinterpret_cast<float4 *>(du + row * d + c) = v;
+      if (da) {
+        if (drop.thr) v = ln_drop4(drop, v, (uint64_t)((row0 + row) * d + c));
+        *reinterpret_cast<float4 *>(da + row * d + c) = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    atomicAdd(&sm[c], dg[i].x); atomicAdd(&sm[c + 1], dg[i].y); atomicAdd(&sm[c + 2], dg[i].z); atomicAdd(&sm[c + 3], dg[i].w);
+    atomicAdd(&sm[d + c], db[i].x); atomicAdd(&sm[d + c + 1], db[i].y); atomicAdd(&sm[d + c + 2], db[i].z); atomicAdd(&sm[d + c + 3], db[i].w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(dgamma + c, sm[c]);
+    atomicAdd(dbeta + c, sm[d + c]);
+  }
+}
+
+static bool ln_vec4_ok(const void *a, const void *b, const void *c, const void *e, const void *f, int d) {
+  auto al = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  return (d == 128 || d == 256 || d == 512) && al(a) && al(b) && al(c) && al(e) && al(f);
+}
+
 int ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, float *u, float *y, float *mean,
            float *rstd, int64_t M, int d, const Drop &drop, int64_t row0, cudaStream_t st) {
   if (M == 0) return 0;
   GT_CHECK(d <= 512, "d_model > 512 not supported");
+  if (ln_vec4_ok(a, res, gamma, u, y, d) && ((uintptr_t)beta & 15) == 0) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+    { LaunchScope _ls(KC_LN, st);
+      if (d == 128) ln_fwd_vec4_kernel<1><<<grid, wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, drop, row0);
+      else if (d == 256) ln_fwd_vec4_kernel<2><<<grid, wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, drop, row0);
+      else ln_fwd_vec4_kernel<4><<<grid, wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, drop, row0); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int wpb = 8;
   { LaunchScope _ls(KC_LN, st);
   ln_fwd_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, st>>>(a, res, gamma, beta, u, y, mean, rstd, M, d, drop, row0); }
@@ -431,6 +557,14 @@ int ln_bwd(const float *dy, const float *u, const float *mean, const float *rstd
   GT_CHECK(d <= 512, "d_model > 512 not supported");
   const int wpb = 8, rpw = 16;
   int64_t blocks = (M + wpb * rpw - 1) / (wpb * rpw);
+  if (ln_vec4_ok(dy, u, gamma, du, da, d)) {
+    { LaunchScope _ls(KC_LN, st);
+      if (d == 128) ln_bwd_vec4_kernel<1><<<(unsigned)blocks, wpb * 32, 0, st>>>(dy, u, mean, rstd, gamma, du, da, dgamma, dbeta, M, drop, row0, rpw);
+      else if (d == 256) ln_bwd_vec4_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(dy, u, mean, rstd, gamma, du, da, dgamma, dbeta, M, drop, row0, rpw);
+      else ln_bwd_vec4_kernel<4><<<(unsigned)blocks, wpb * 32, 0, st>>>(dy, u, mean, rstd, gamma, du, da, dgamma, dbeta, M, drop, row0, rpw); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
+  }
   { LaunchScope _ls(KC_LN, st);
   ln_bwd_kernel<<<(unsigned)blocks, wpb * 32, 2 * d * sizeof(float), st>>>(dy, u, mean, rstd, gamma, du, da, dgamma, dbeta,
                                                                            M, d, drop, row0, rpw); }
