@@ -235,7 +235,7 @@ int decode_feedback(const float *hvo_step, float *tok, float *out, int64_t n_seq
 // one decoder layer of the KV-cached decode for one token per sequence, d_model = 32 (decode32.cu)
 bool dec32_supported(const gt_config &c);
 int dec32_layer_step(const gt_config &c, const LayerP &p, const float *P, const float *y_in, float *y_out, float *kv_self,
-                     const float *kv_cross, int64_t n, int step, cudaStream_t st);
+                     const float *kv_cross, int64_t n, int step, bool do_ffn, cudaStream_t st);
 int predict_feedback(const float *hvo, float *tgt, float *out, int64_t n_seq, int e, int step_i, float thres, cudaStream_t st);
 
 }  // namespace gt

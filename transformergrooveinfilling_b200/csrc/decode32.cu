@@ -24,6 +24,7 @@ struct Dec32Args {
   const float *wqkv, *bqkv, *wo, *bo, *wcq, *bcq, *wco, *bco, *w1, *b1, *w2, *b2, *g1, *be1, *g2, *be2, *g3, *be3;
   int64_t n;
   int step, H, F;
+  int do_ffn;              // 0: stop after the cross-attention block (y_out = x2); the FFN block then runs on the tensor cores
 };
 
 __device__ __forceinline__ float dc_warp_sum(float v) {
@@ -92,8 +93,10 @@ __global__ void __launch_bounds__(DC_WARPS * 32, 1) dec32_layer_step_kernel(cons
     sWcq[(i & 31) * ld32 + (i >> 5)] = a.wcq[i];
     sWco[(i & 31) * ld32 + (i >> 5)] = a.wco[i];
   }
-  for (int i = tid; i < F * 32; i += DC_WARPS * 32) sW1[(i & 31) * ldf + (i >> 5)] = a.w1[i];          // W1 [F][32] -> [c][j]
-  for (int i = tid; i < 32 * F; i += DC_WARPS * 32) sW2[(i % F) * ld32 + i / F] = a.w2[i];              // W2 [32][F] -> [j][c]
+  if (a.do_ffn) {
+    for (int i = tid; i < F * 32; i += DC_WARPS * 32) sW1[(i & 31) * ldf + (i >> 5)] = a.w1[i];        // W1 [F][32] -> [c][j]
+    for (int i = tid; i < 32 * F; i += DC_WARPS * 32) sW2[(i % F) * ld32 + i / F] = a.w2[i];            // W2 [32][F] -> [j][c]
+  }
   for (int i = tid; i < 96; i += DC_WARPS * 32) sB[i] = a.bqkv[i];
   if (tid < 32) {
     sB[96 + tid] = a.bo[tid]; sB[128 + tid] = a.bcq[tid]; sB[160 + tid] = a.bco[tid]; sB[192 + tid] = a.b2[tid];
@@ -132,6 +135,11 @@ __global__ void __launch_bounds__(DC_WARPS * 32, 1) dec32_layer_step_kernel(cons
     __syncwarp();
     const float x2 = dc_layernorm(x1 + dc_matvec32(sWco, ld32, xs, sB[160 + lane], lane), sB[288 + lane], sB[320 + lane]);
     __syncwarp();
+    if (!a.do_ffn) {                                  // bf16 mode: the FFN block of these tokens runs in tc_layer_fwd (TC_MODE_FFN)
+      a.y_out[s * 32 + lane] = x2;
+      __syncwarp();
+      continue;
+    }
     // ---- feed-forward ----
     xs[lane] = x2;
     __syncwarp();
@@ -154,7 +162,7 @@ bool dec32_supported(const gt_config &c) {
 }
 
 int dec32_layer_step(const gt_config &c, const LayerP &p, const float *P, const float *y_in, float *y_out, float *kv_self,
-                     const float *kv_cross, int64_t n, int step, cudaStream_t st) {
+                     const float *kv_cross, int64_t n, int step, bool do_ffn, cudaStream_t st) {
   GT_CHECK(dec32_supported(c), "dec32_layer_step: configuration not supported");
   Dec32Args a;
   a.y_in = y_in; a.y_out = y_out; a.kv_self = kv_self; a.kv_cross = kv_cross;
@@ -162,7 +170,7 @@ int dec32_layer_step(const gt_config &c, const LayerP &p, const float *P, const 
   a.wcq = P + p.ca.w_in; a.bcq = P + p.ca.b_in; a.wco = P + p.ca.w_out; a.bco = P + p.ca.b_out;
   a.w1 = P + p.w1; a.b1 = P + p.b1; a.w2 = P + p.w2; a.b2 = P + p.b2;
   a.g1 = P + p.g1; a.be1 = P + p.be1; a.g2 = P + p.g2; a.be2 = P + p.be2; a.g3 = P + p.g3; a.be3 = P + p.be3;
-  a.n = n; a.step = step; a.H = c.nhead; a.F = c.dim_ff;
+  a.n = n; a.step = step; a.H = c.nhead; a.F = c.dim_ff; a.do_ffn = do_ffn ? 1 : 0;
   const int F = c.dim_ff;
   const size_t smem = (size_t)(32 * 97 + 3 * 32 * 33 + 32 * (F + 1) + F * 33 + 416 + F + DC_WARPS * (32 + F)) * sizeof(float);
   static int sms = 0;

@@ -192,7 +192,7 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
   P.mf_e = train ? take(M) : nullptr; P.rf_e = train ? take(M) : nullptr; P.mem = take(M * d);
   if (hybrid) {
     P.enc_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * c.n_enc + 3) / 4));
-    if (!decode) P.dec_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * 2 * c.n_dec + 3) / 4));
+    P.dec_img = reinterpret_cast<uint8_t *>(take(((int64_t)tc_enc_img_stride(c) * 2 * c.n_dec + 3) / 4));   // decode: FFN blocks only
   }
   if (decode) {
     const int64_t n = n_seq;
@@ -607,6 +607,7 @@ static int predict_decode(const Ctx &x, const Plan &pl, float thres, float *hvo_
     GT_TRY(linear(x, pl.mem, d, x.P + p.ca.w_in + (int64_t)d * d, pl.kv_cross[l], 2 * d, e));
   }
   GT_CUDA(cudaMemsetAsync(pl.s_tok, 0, (size_t)n * E * sizeof(float), x.st));
+  if (pl.dec_img != nullptr && dec32_supported(x.c)) GT_TRY(tc_dec_prep(x.c, x.L, x.P, pl.dec_img, x.st));
   for (int i = 0; i < T; ++i) {
     GemmEpi ein; ein.bias = x.P + x.L.in_dec_b; ein.relu = 1;
     GT_TRY(linear_rows(x, pl.s_tok, E, x.P + x.L.in_dec_w, pl.s_ya, d, d, n, ein));
@@ -614,8 +615,10 @@ static int predict_decode(const Ctx &x, const Plan &pl, float thres, float *hvo_
     float *cur = pl.s_ya, *nxt = pl.s_yb;
     for (int l = 0; l < x.c.n_dec; ++l) {
       const LayerP &p = x.L.dec[l];
-      if (dec32_supported(x.c)) {               // d_model = 32: the whole layer for this token in one kernel (decode32.cu)
-        GT_TRY(dec32_layer_step(x.c, p, x.P, cur, nxt, pl.kv_self[l], pl.kv_cross[l], n, i, x.st));
+      if (dec32_supported(x.c)) {               // d_model = 32: the whole layer for this token in one kernel (decode32.cu) ...
+        const bool tc_ffn = pl.dec_img != nullptr;   // ... bf16 mode: its FFN block on the tensor cores (TC_MODE_FFN over the n token rows)
+        GT_TRY(dec32_layer_step(x.c, p, x.P, cur, tc_ffn ? pl.s_x2 : nxt, pl.kv_self[l], pl.kv_cross[l], n, i, !tc_ffn, x.st));
+        if (tc_ffn) GT_TRY(tc_dec_ffn_rows(x.c, x.L, x.P, pl.dec_img, l, pl.s_x2, nxt, n, x.st));
         std::swap(cur, nxt);
         continue;
       }

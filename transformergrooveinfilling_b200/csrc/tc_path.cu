@@ -443,6 +443,16 @@ int tc_dec_ffn_fwd(const gt_config &c, const Layout &L, const float *params, uin
   a.x_in = x_in; a.x_out = x_out; a.u2 = u;
   return tc_layer_fwd(c.d_model, a, st);
 }
+// the same block over an arbitrary set of token rows (KV-cached decode: one token per sequence), eval mode
+int tc_dec_ffn_rows(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, const float *x_in, float *x_out,
+                    int64_t n_rows, cudaStream_t st) {
+  TcCtx x;
+  tc_ctx(x, c, L, params, nullptr, nullptr, 1, false, 0, 0, 0, st);
+  TcLayerArgs a = tc_dec_ffn_args(x, dec_img, l);
+  a.M = n_rows; a.n_tiles = (int)((n_rows + TC_TILE - 1) / TC_TILE);
+  a.x_in = x_in; a.x_out = x_out; a.u2 = nullptr;
+  return tc_layer_fwd(c.d_model, a, st);
+}
 int tc_dec_ffn_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *dec_img, int l, const float *x_in,
                    const float *u, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step, int64_t seq0,
                    cudaStream_t st) {

@@ -37,6 +37,8 @@ int tc_dec_attn_bwd(const gt_config &c, const Layout &L, const float *params, fl
 int tc_dec_prep(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, cudaStream_t st);
 int tc_dec_ffn_fwd(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, const float *x_in, float *x_out,
                    float *u, int64_t n_seq, bool train, uint64_t seed, uint64_t step, int64_t seq0, cudaStream_t st);
+int tc_dec_ffn_rows(const gt_config &c, const Layout &L, const float *params, uint8_t *dec_img, int l, const float *x_in, float *x_out,
+                    int64_t n_rows, cudaStream_t st);
 int tc_dec_ffn_bwd(const gt_config &c, const Layout &L, const float *params, float *grads, uint8_t *dec_img, int l, const float *x_in,
                    const float *u, const float *dy, float *dx, int64_t n_seq, uint64_t seed, uint64_t step, int64_t seq0,
                    cudaStream_t st);
