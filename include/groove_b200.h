@@ -137,6 +137,18 @@ int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale,
 int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Several consecutive training steps in ONE call over a dataset that is resident on the device (the body of
+ * BGT/models/train.py:118-141 for `n_steps` batches of one epoch): step s gathers rows perm[start + s*batch .. + batch) of
+ * data_x [S,32,e_src] / data_y [S,32,27] into xbuf / ybuf, runs gt_train_step on them with dropout step counter step0 + s,
+ * and applies the optimizer (optimizer 0: SGD, 1: Adam with torch defaults and 1-based counter adam_t0 + s + 1; m, v may be
+ * NULL for SGD).  metrics_out[s*6 .. s*6+6) receives the six calculate_loss values of step s.  Everything is enqueued on
+ * `stream`; the caller's host thread is busy only for the launches, which is what lets several sweep members be driven
+ * from several host threads at once (transformergrooveinfilling_b200/sweep.py).  perm holds int64 row indices on the device. */
+int gt_train_steps(const gt_config *cfg, float *params, const float *pe, const float *data_x, const float *data_y,
+                   const int64_t *perm, int64_t start, int64_t batch, int n_steps, float hit_loss_penalty, float *grads,
+                   float *metrics_out, float *hvo, float *xbuf, float *ybuf, void *ws, int64_t ws_bytes, int optimizer,
+                   float lr, float *m, float *v, int64_t adam_t0, uint64_t seed, uint64_t step0, void *stream);
+
 /* Data-parallel overlap (BASELINE.json north_star: "bucketed NCCL gradient allreduce ... overlapped with backward").
  * The reference has no distributed code; the flat gradient of gt_backward / gt_train_step is partitioned into
  * contiguous buckets listed in the order backward FINISHES them (output head first, one bucket per decoder / encoder

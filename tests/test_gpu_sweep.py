@@ -63,3 +63,27 @@ def test_members_learn_and_are_isolated():
         assert float(hist[-5:, 0].mean()) < float(hist[:5, 0].mean())
     # distinct parameter buffers (no aliasing between members)
     assert pk.members[0].model.flat_parameters().data_ptr() != pk.members[1].model.flat_parameters().data_ptr()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_multi_step_call_equals_python_loop(precision):
+    """gt_train_steps (device-side row gather + train step + optimizer for a whole run of batches in one library call) takes the
+    same steps as the per-step Python loop: same permutations, ragged last batch, dropout counters, SGD and Adam updates."""
+    x, y = _dataset(100)                        # 100 sequences: batch 16 -> 6 full batches + a ragged batch of 4 per epoch
+    steps = 17                                  # two full epochs of the batch-16 member and the start of a third
+
+    def run(fused):
+        torch.manual_seed(0)
+        pk = SweepPacker(CONFIGS[:3], x, y, "cuda", precision=precision, seed=9)
+        pk.run(steps, concurrent=False, fused=fused)
+        return [h.numpy() for h in pk.history()], pk
+
+    a, pka = run(True)
+    b, pkb = run(False)
+    for ha, hb, ma, mb in zip(a, b, pka.members, pkb.members):
+        assert ha.shape == (steps, 6)
+        np.testing.assert_allclose(ha[0], hb[0], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(ha, hb, rtol=2e-4 if precision == "fp32" else 3e-2, atol=1e-6)
+        assert ma.sequences == mb.sequences and ma.model._step == mb.model._step
+        pa, pb = ma.model.flat_parameters().detach(), mb.model.flat_parameters().detach()
+        assert float((pa - pb).abs().max()) / float(pb.abs().max()) < (1e-4 if precision == "fp32" else 2e-2)

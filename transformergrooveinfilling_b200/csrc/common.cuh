@@ -224,6 +224,7 @@ int edge32_tail_bwd(const float *d_in, const float *hvo, const float *x, const f
 int64_t eval_scratch_floats(int64_t n_seq, int n_voices);
 int eval_metrics(const float *pred, const float *gt, int64_t n_seq, int n_voices, float *out, float *partials, cudaStream_t st);
 int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st);
+int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st);
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st);
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,
               int64_t step, float gs, cudaStream_t st);

@@ -802,6 +802,25 @@ __global__ void shift_right_kernel(const float *__restrict__ y, float *out, int6
   int64_t row = i / e;
   out[i] = (row % T == 0) ? 0.f : y[i - e];
 }
+// out[i, :] = data[perm[start + i], :]   (rows of `row` floats, row % 4 == 0)
+__global__ void gather_rows_kernel(const float *__restrict__ data, const int64_t *__restrict__ perm, int64_t start, float *out,
+                                   int64_t n_rows, int row4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * row4) return;
+  const int64_t r = i / row4;
+  const int c = (int)(i % row4);
+  reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(data) + perm[start + r] * row4 + c);
+}
+int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st) {
+  if (n_rows == 0) return 0;
+  GT_CHECK(row_floats % 4 == 0, "gather_rows: row length must be a multiple of 4 floats");
+  const int64_t n = n_rows * (row_floats / 4);
+  { LaunchScope _ls(KC_ELEMWISE, st);
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(data, perm, start, out, n_rows, (int)(row_floats / 4)); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st) {
   int64_t n = n_seq * T * e;
   if (n == 0) return 0;

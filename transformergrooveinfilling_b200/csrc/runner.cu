@@ -798,6 +798,28 @@ int gt_train_step(const gt_config *cfg, const float *params, const float *pe, co
   return backward_all(x, pl, src, tgt_in, hvo, pl.d_hvo);
 }
 
+int gt_train_steps(const gt_config *cfg, float *params, const float *pe, const float *data_x, const float *data_y,
+                   const int64_t *perm, int64_t start, int64_t batch, int n_steps, float hit_loss_penalty, float *grads,
+                   float *metrics_out, float *hvo, float *xbuf, float *ybuf, void *ws, int64_t ws_bytes, int optimizer,
+                   float lr, float *m, float *v, int64_t adam_t0, uint64_t seed, uint64_t step0, void *stream) {
+  GT_TRY(validate_config(cfg));
+  GT_CHECK(data_x && data_y && perm && xbuf && ybuf && metrics_out && params && grads, "gt_train_steps: null pointer");
+  GT_CHECK(batch >= 1 && n_steps >= 0 && start >= 0, "gt_train_steps: bad batch / n_steps / start");
+  GT_CHECK(optimizer == 0 || (optimizer == 1 && m && v), "gt_train_steps: optimizer must be 0 (SGD) or 1 (Adam, with m and v)");
+  static thread_local Layout L;
+  GT_TRY(build_layout(*cfg, L));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < n_steps; ++s) {
+    GT_TRY(gather_rows(data_x, perm, start + (int64_t)s * batch, xbuf, batch, (int64_t)T * cfg->e_src, st));
+    GT_TRY(gather_rows(data_y, perm, start + (int64_t)s * batch, ybuf, batch, (int64_t)T * cfg->e_tgt, st));
+    GT_TRY(gt_train_step(cfg, params, pe, xbuf, ybuf, batch, hit_loss_penalty, grads, metrics_out + (int64_t)s * 6, hvo, ws, ws_bytes, seed,
+                         step0 + (uint64_t)s, 0, stream));
+    if (optimizer == 0) GT_TRY(sgd_step(params, grads, L.total, lr, 1.f, st));
+    else GT_TRY(adam_step(params, grads, m, v, L.total, lr, 0.9f, 0.999f, 1e-8f, adam_t0 + s + 1, 1.f, st));
+  }
+  return 0;
+}
+
 int gt_predict(const gt_config *cfg, const float *params, const float *pe, const float *src, int64_t n_seq, float thres,
                float *hvo_out, void *ws, int64_t ws_bytes, void *stream) {
   return gt_predict_variant(cfg, params, pe, src, n_seq, thres, hvo_out, ws, ws_bytes, 0, stream);

@@ -116,6 +116,64 @@ class SweepMember:
                     self.epoch += 1
             self.steps += n_steps
 
+    def run_steps_fused(self, n_steps: int) -> None:
+        """Same steps as ``run_steps`` (same permutations, batches, dropout counters, optimizer updates), but every run of
+        equal-sized batches of an epoch is ONE library call (``gt_train_steps``: device-side row gather + train step +
+        optimizer per step), so the host thread holds the GIL only between epochs — what lets more than a handful of members
+        make progress at once."""
+        import ctypes as C
+        from . import _lib
+        from .training import FusedAdam, FusedSGD
+        if not self.encoder_only:
+            raise NotImplementedError("SweepPacker drives encoder-only members (every shipped sweep sets encoder_only: 1)")
+        opt, model, ld = self.optimizer, self.model, self.loader
+        if not isinstance(opt, (FusedSGD, FusedAdam)):
+            return self.run_steps(n_steps)
+        lib = _lib.load()
+        adam = isinstance(opt, FusedAdam)
+        dev = ld.device
+        with torch.cuda.stream(self.stream):
+            done = 0
+            S, B = ld.x.shape[0], ld.batch_size
+            while done < n_steps:
+                order = torch.randperm(S, device=dev, generator=ld.gen) if ld.shuffle else torch.arange(S, device=dev)
+                runs = [(0, B, S // B)]                                    # (first row, batch, number of batches)
+                if S % B and not ld.drop_last:
+                    runs.append((S - S % B, S % B, 1))
+                for start, bsz, count in runs:
+                    k = min(count, n_steps - done)
+                    if k <= 0:
+                        break
+                    key = (bsz, model.precision)
+                    if model._train_ws is None or model._train_ws[0] != key:
+                        model._train_ws = (key, model._workspace(bsz, 1, dev), torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev))
+                    _, ws, hvo = model._train_ws
+                    xbuf = torch.empty((bsz,) + tuple(ld.x.shape[1:]), device=dev)
+                    ybuf = torch.empty((bsz,) + tuple(ld.y.shape[1:]), device=dev)
+                    met = torch.empty(k, 6, dtype=torch.float32, device=dev)
+                    g = model.flat_grad()
+                    cfg = model._cfg()
+                    if adam:
+                        b1, b2 = opt.param_groups[0]["betas"]
+                        assert (b1, b2, opt.param_groups[0]["eps"]) == (0.9, 0.999, 1e-8), "gt_train_steps applies torch's Adam defaults"
+                    _lib.check(lib.gt_train_steps(
+                        C.byref(cfg), _lib.ptr(model._flat), _lib.ptr(model._pe_flat()), _lib.ptr(ld.x), _lib.ptr(ld.y), _lib.ptr(order),
+                        start, bsz, k, self.penalty, _lib.ptr(g), _lib.ptr(met), _lib.ptr(hvo), _lib.ptr(xbuf), _lib.ptr(ybuf), _lib.ptr(ws),
+                        ws.numel(), 1 if adam else 0, opt._lr(), _lib.ptr(opt._m) if adam else None, _lib.ptr(opt._v) if adam else None,
+                        opt._t if adam else 0, model._seed, model._step, _lib.stream_ptr(dev)), "gt_train_steps")
+                    model._step += k
+                    if adam:
+                        opt._t += k
+                    self.metrics.extend(met.unbind(0))
+                    self.sequences += bsz * k
+                    done += k
+                    self._keep = (order, xbuf, ybuf)                      # alive until the stream has consumed them
+                    if done == n_steps:
+                        break
+                else:
+                    self.epoch += 1
+            self.steps += n_steps
+
     def history(self) -> torch.Tensor:
         """[steps, 6] host tensor of the per-step metrics (synchronises this member's stream)."""
         self.stream.synchronize()
@@ -144,12 +202,14 @@ class SweepPacker:
             self.members.append(SweepMember(params, x, y, self.device, seed + i))
         torch.cuda.synchronize(self.device)          # dataset copy and parameter initialisation ran on the default stream
 
-    def run(self, n_steps: int, concurrent: bool = True, on_error: Optional[Callable] = None) -> None:
+    def run(self, n_steps: int, concurrent: bool = True, on_error: Optional[Callable] = None, fused: bool = True) -> None:
         """Every member takes ``n_steps`` optimizer steps.  Returns once all steps are ENQUEUED; ``synchronize()`` or
-        ``history()`` waits for the device."""
+        ``history()`` waits for the device.  ``fused=True`` drives each member through ``gt_train_steps`` (one library call per
+        run of equal batches of an epoch), ``fused=False`` through the per-step Python loop; both take identical steps."""
+        step_fn = (lambda m: m.run_steps_fused(n_steps)) if fused else (lambda m: m.run_steps(n_steps))
         if not concurrent:
             for m in self.members:
-                m.run_steps(n_steps)
+                step_fn(m)
                 m.stream.synchronize()           # one member at a time on the device, not just on the host
             return
         errors: List[BaseException] = []
@@ -157,7 +217,7 @@ class SweepPacker:
         def work(m: SweepMember):
             try:
                 torch.cuda.set_device(self.device)
-                m.run_steps(n_steps)
+                step_fn(m)
             except BaseException as e:      # surfaced on the caller's thread below
                 errors.append(e)
 
