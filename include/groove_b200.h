@@ -149,6 +149,28 @@ int gt_train_steps(const gt_config *cfg, float *params, const float *pe, const f
                    float *metrics_out, float *hvo, float *xbuf, float *ybuf, void *ws, int64_t ws_bytes, int optimizer,
                    float lr, float *m, float *v, int64_t adam_t0, uint64_t seed, uint64_t step0, void *stream);
 
+/* One training step captured into a CUDA graph: [row gather of the batch] + gt_train_step + optimizer + bookkeeping.  The
+ * latency-bound regimes (the reference's batch sizes of 16..512, BGT/models/train.py:118-141 once per batch, and several sweep
+ * members per GPU) pay ONE graph launch per step instead of ~47 kernel launches.  xbuf / ybuf / metrics6 / hvo / ws / grads are
+ * the fixed buffers the graph reads and writes.  `counters` points to four device uint64 the graph reads AND advances:
+ *   [0] dropout step counter — the kernels derive their dropout keys from it with site_key's arithmetic, so the masks are those
+ *       of gt_train_step(step = counters[0]);           [1] Adam steps taken so far (bias corrections use [1] + 1);
+ *   [2] row offset into `perm` of this step's batch (+= n_seq per replay);   [3] metrics slot (+= 1 per replay).
+ * data_x / data_y / perm (all three or none): the device-resident dataset and the epoch's permutation (a fixed buffer the caller
+ * refills per epoch, DataLoader(shuffle=True) of train.py:153-158); when given, each replay first gathers rows
+ * perm[counters[2] .. +n_seq) into xbuf / ybuf, otherwise the caller fills xbuf / ybuf before each launch.  metrics_ring
+ * (optional, ring_slots x 6 floats): replay k stores its six calculate_loss values at slot counters[3] % ring_slots.
+ * Available for the fused d_model = 32 encoder-only path (GT_PATH_FUSED_D32, n_dec = 0).  optimizer: 0 SGD, 1 Adam (torch
+ * defaults).  Per-kernel profiling (gt_profile_enable) and bucket events (gt_grad_events_enable) must be off. */
+int gt_graph_train_create(const gt_config *cfg, float *params, const float *pe, float *xbuf, float *ybuf, int64_t n_seq,
+                          float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,
+                          int optimizer, float lr, float *m, float *v, uint64_t seed, unsigned long long *counters,
+                          const float *data_x, const float *data_y, const int64_t *perm, float *metrics_ring,
+                          int64_t ring_slots, void *stream, void **graph_out);
+/* n_replays consecutive steps (each replay advances the counters, so replay k trains on the k-th next batch of the permutation) */
+int gt_graph_launch(void *graph, int n_replays, void *stream);
+int gt_graph_destroy(void *graph);
+
 /* Data-parallel overlap (BASELINE.json north_star: "bucketed NCCL gradient allreduce ... overlapped with backward").
  * The reference has no distributed code; the flat gradient of gt_backward / gt_train_step is partitioned into
  * contiguous buckets listed in the order backward FINISHES them (output head first, one bucket per decoder / encoder

@@ -88,3 +88,69 @@ def test_fused_multi_step_call_equals_python_loop(precision):
         pa, pb = ma.model.flat_parameters().detach(), mb.model.flat_parameters().detach()
         # 17 optimizer steps apart, the two runs differ by the order of their fp32 gradient atomics only (1.4e-4 measured)
         assert float((pa - pb).abs().max()) / float(pb.abs().max()) < (1e-3 if precision == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("optimizer", ["sgd", "adam"])
+def test_graph_replay_equals_fused_call(optimizer):
+    """gt_graph_train_create / gt_graph_launch: the captured step (row gather + train step + optimizer, with the dropout step,
+    the Adam step count, the row offset and the metrics slot read from device counters) takes the same steps as gt_train_steps:
+    same dropout masks (keys derived on the device from the counter), same Adam bias corrections, ragged last batch, epochs."""
+    x, y = _dataset(100)                        # batch 16 -> 6 graph replays + one ragged batch of 4 per epoch
+    steps = 17
+    cfgs = [dict(CONFIGS[0], optimizer_algorithm=optimizer, learning_rate=0.05 if optimizer == "sgd" else 1e-3),
+            dict(CONFIGS[1], optimizer_algorithm=optimizer, learning_rate=0.05 if optimizer == "sgd" else 1e-3, batch_size=32)]
+
+    def run(graph):
+        torch.manual_seed(0)
+        pk = SweepPacker(cfgs, x, y, "cuda", precision="bf16", seed=9)
+        assert all(m.graph_capable() for m in pk.members)
+        pk.run(steps, concurrent=False, graph=graph)
+        return [h.numpy() for h in pk.history()], pk
+
+    a, pka = run(True)
+    b, pkb = run(False)
+    for ha, hb, ma, mb in zip(a, b, pka.members, pkb.members):
+        assert ha.shape == (steps, 6) and np.isfinite(ha).all()
+        np.testing.assert_allclose(ha[0], hb[0], rtol=1e-5, atol=1e-7)        # first step: no history, identical masks
+        np.testing.assert_allclose(ha, hb, rtol=3e-2, atol=1e-6)              # bf16 trajectory tolerance of the tests above
+        assert ma.sequences == mb.sequences and ma.model._step == mb.model._step and ma.epoch == mb.epoch
+        assert getattr(ma.optimizer, "_t", 0) == getattr(mb.optimizer, "_t", 0)
+        pa, pb = ma.model.flat_parameters().detach(), mb.model.flat_parameters().detach()
+        assert float((pa - pb).abs().max()) / float(pb.abs().max()) < 2e-2
+        assert ma._graph is not None and getattr(mb, "_graph", None) is None
+
+
+def test_graph_replay_dropout_masks_follow_the_device_counter():
+    """With learning rate 0 the parameters never move, so step k of a replayed run must reproduce step k of the eager run
+    EXACTLY up to fp32 summation order — any mismatch of a dropout key (derived on the device from counters[0]) would change the
+    loss by far more than that."""
+    x, y = _dataset(96)
+    cfg = dict(CONFIGS[1], optimizer_algorithm="sgd", learning_rate=0.0, batch_size=16, dropout=0.3)
+
+    def run(graph):
+        torch.manual_seed(0)
+        pk = SweepPacker([cfg], x, y, "cuda", precision="bf16", seed=4)
+        pk.run(12, concurrent=False, graph=graph)
+        return pk.history()[0].numpy()
+
+    a, b = run(True), run(False)
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+    assert len({round(float(v), 6) for v in a[:, 0]}) > 6      # different batches and masks per step: the losses differ
+
+
+def test_graph_members_packed_concurrently():
+    x, y = _dataset(96)
+    cfgs = [dict(CONFIGS[1], batch_size=16), CONFIGS[0], CONFIGS[3]]      # the d_model = 256 member falls back to gt_train_steps
+
+    def run(concurrent):
+        torch.manual_seed(0)
+        pk = SweepPacker(cfgs, x, y, "cuda", precision="bf16", seed=5)
+        pk.run(9, concurrent=concurrent, graph=True)
+        return [h.numpy() for h in pk.history()], pk
+
+    packed, pk = run(True)
+    solo, _ = run(False)
+    assert [m.graph_capable() for m in pk.members] == [True, True, False]
+    for a, b in zip(packed, solo):
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(a, b, rtol=3e-2, atol=1e-6)

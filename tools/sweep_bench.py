@@ -1,7 +1,7 @@
 """Sweep packing measurement: aggregate training sequences/s of K sweep members on ONE B200, packed
 (one stream + host thread per member) against the same members run one after the other, at the reference's batch sizes.
 
-    python tools/sweep_bench.py [--members 1,4,8,16] [--steps 60] [--batch 32] [--spec closedhh|c2]
+    python tools/sweep_bench.py [--members 1,4,8,16] [--steps 60] [--batch 32] [--spec closedhh|c2] [--drive loop|fused|graph]
 
 --spec c2      : every member is InfillingClosedHH_training.yaml (C2) at --batch
 --spec closedhh: members drawn from the parameter ranges of configs/InfillingClosedHH_sweep.yaml (restated below)
@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--spec", default="c2", choices=["c2", "closedhh"])
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--drive", default="fused", choices=["loop", "fused", "graph"],
+                    help="per-step Python loop / gt_train_steps per run of batches / one CUDA-graph launch per step")
     args = ap.parse_args()
     w = WORKLOADS["c2"]
     x, y = synth_batch(w, 4096, 1234)
@@ -50,11 +52,12 @@ def main():
         for mode in ("sequential", "packed"):
             torch.manual_seed(0)
             pk = SweepPacker(cfgs, x, y, "cuda", precision=args.precision, seed=3)
-            pk.run(5, concurrent=(mode == "packed"))          # warm-up: workspaces, lazy module loads
+            drive = dict(fused=args.drive != "loop", graph=args.drive == "graph")
+            pk.run(5, concurrent=(mode == "packed"), **drive)          # warm-up: workspaces, lazy module loads, graph capture
             pk.synchronize()
             seq0 = sum(m.sequences for m in pk.members)
             t0 = time.perf_counter()
-            pk.run(args.steps, concurrent=(mode == "packed"))
+            pk.run(args.steps, concurrent=(mode == "packed"), **drive)
             pk.synchronize()
             dt = time.perf_counter() - t0
             res[mode] = (sum(m.sequences for m in pk.members) - seq0) / dt
@@ -63,7 +66,7 @@ def main():
             del pk
             torch.cuda.empty_cache()
         emit(({"metric": "sweep_train_seq_per_s", "members": k, "spec": args.spec, "batch": args.batch if args.spec == "c2" else "sampled",
-                          "steps_per_member": args.steps, "precision": args.precision, "sequential": res["sequential"], "packed": res["packed"],
+                          "steps_per_member": args.steps, "precision": args.precision, "drive": args.drive, "sequential": res["sequential"], "packed": res["packed"],
                           "speedup": res["packed"] / res["sequential"], "ms_per_step_sequential": res["sequential_ms_per_member_step"],
                           "ms_per_round_packed": res["packed_ms_per_member_step"], "final_losses": res["final_losses"],
                           "host_threads": k, "host_cpus": os.cpu_count()}))

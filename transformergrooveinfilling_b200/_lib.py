@@ -48,6 +48,10 @@ SIGNATURES = {
     "gt_predict_variant": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, C.c_int, _p]),
     "gt_sgd_step": (C.c_int, [_p, _p, _i64, _f, _f, _p]),
     "gt_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
+    "gt_graph_train_create": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, C.c_int, _f, _p, _p, _u64, _p,
+                                        _p, _p, _p, _p, _i64, _p, C.POINTER(C.c_void_p)]),
+    "gt_graph_launch": (C.c_int, [_p, C.c_int, _p]),
+    "gt_graph_destroy": (C.c_int, [_p]),
     "gt_train_steps": (C.c_int, [_cfgp, _p, _p, _p, _p, _p, _i64, _i64, C.c_int, _f, _p, _p, _p, _p, _p, _p, _i64, C.c_int, _f, _p, _p,
                                  _i64, _u64, _u64, _p]),
     "gt_grad_buckets": (C.c_int, [_cfgp, C.POINTER(_i64), C.POINTER(_i64), C.c_int]),

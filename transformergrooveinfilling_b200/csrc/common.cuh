@@ -55,9 +55,12 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return x;
 }
-inline uint32_t site_key(uint64_t seed, uint64_t step, int32_t site) {
+inline uint32_t site_key_seed(uint64_t seed) {                      // the seed-only prefix of site_key
   uint32_t k = mix32((uint32_t)seed ^ 0x9E3779B9u);
-  k = mix32(k ^ (uint32_t)(seed >> 32));
+  return mix32(k ^ (uint32_t)(seed >> 32));
+}
+inline uint32_t site_key(uint64_t seed, uint64_t step, int32_t site) {
+  uint32_t k = site_key_seed(seed);
   k = mix32(k + (uint32_t)step * 0x85EBCA6Bu);
   k = mix32(k ^ ((uint32_t)site * 0xC2B2AE35u));
   return k;
@@ -74,7 +77,23 @@ inline float drop_scale(uint32_t thr) { return thr == 0 ? 1.0f : (float)(65536.0
 struct Drop {           // one dropout site; thr == 0 means "inactive"
   uint32_t key = 0, thr = 0;
   float scale = 1.f;
+  // CUDA-graph replay (gt_graph_train_create): the dropout step counter lives in device memory, so the key is derived ON THE
+  // DEVICE from (k0 = seed part of site_key, *step_ptr, site) with exactly site_key's arithmetic — same masks as a normal call
+  uint32_t k0 = 0, site = 0;
+  const unsigned long long *step_ptr = nullptr;
 };
+__device__ __forceinline__ void drop_resolve(Drop &d);
+__device__ __forceinline__ void drop_resolve(Drop &d) {
+  if (d.step_ptr != nullptr) {
+    const uint32_t k = mix32(d.k0 + (uint32_t)(*d.step_ptr) * 0x85EBCA6Bu);
+    d.key = mix32(k ^ (d.site * 0xC2B2AE35u));
+  }
+}
+// when non-null, the pass drivers build Drops that read the step from this device counter (set around graph capture only)
+extern thread_local const unsigned long long *g_drop_step_ptr;
+inline void drop_fill_devstep(Drop &d, uint64_t seed, int site) {
+  if (g_drop_step_ptr != nullptr) { d.k0 = site_key_seed(seed); d.site = (uint32_t)site; d.step_ptr = g_drop_step_ptr; }
+}
 // 64 random bits = four 16-bit dropout decisions for the QUAD of elements 4w .. 4w+3 of one site.  v = (uint32)w ^
 // ((uint32)(w >> 32) * 0x85EBCA6B).  One xorshift-multiply round, then two 32x32 -> 64 multiplies (IMAD.WIDE) whose
 // halves are cross-mixed: 12 instructions per four decisions.
@@ -224,10 +243,13 @@ int edge32_tail_bwd(const float *d_in, const float *hvo, const float *x, const f
 int64_t eval_scratch_floats(int64_t n_seq, int n_voices);
 int eval_metrics(const float *pred, const float *gt, int64_t n_seq, int n_voices, float *out, float *partials, cudaStream_t st);
 int shift_right(const float *y, float *out, int64_t n_seq, int e, cudaStream_t st);
-int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st);
+int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st,
+                const unsigned long long *start_ptr = nullptr);      // start_ptr: row offset += *start_ptr (graph replay)
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st);
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,
-              int64_t step, float gs, cudaStream_t st);
+              int64_t step, float gs, cudaStream_t st, const unsigned long long *t_ptr = nullptr);   // t_ptr: 1-based step = *t_ptr + 1 (graph replay)
+int counter_advance(unsigned long long *counters, int64_t batch, const float *metrics6, float *ring, int64_t ring_slots, cudaStream_t st);
+int optimizer_kernels_warm();
 int debug_dropout_mask(uint32_t key, uint32_t thr, int64_t idx0, int64_t n, uint8_t *keep, cudaStream_t st);
 int attention_decode(const float *q, int64_t ldq, const float *k, const float *v, int64_t ld_key, int64_t ld_seq, int nkeys,
                      float *o, int64_t ldo, int64_t n_seq, int H, int dh, cudaStream_t st);

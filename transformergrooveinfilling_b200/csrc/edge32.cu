@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(EG_WARPS * 32) stem32_kernel(const float *__re
                                                                float *__restrict__ x0, const float *__restrict__ dx0,
                                                                float *gW, float *gb, int64_t M, Drop drop, int64_t e0) {
   constexpr int EP = StemSmem<E>::EP;
+  drop_resolve(drop);                                // graph replay: key from the device step counter
   __shared__ __align__(16) float sx[EG_WARPS][EG_TOK][EP];
   __shared__ float sacc[BWD ? 32 * E + 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

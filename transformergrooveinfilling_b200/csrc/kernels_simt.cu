@@ -804,19 +804,21 @@ __global__ void shift_right_kernel(const float *__restrict__ y, float *out, int6
 }
 // out[i, :] = data[perm[start + i], :]   (rows of `row` floats, row % 4 == 0)
 __global__ void gather_rows_kernel(const float *__restrict__ data, const int64_t *__restrict__ perm, int64_t start, float *out,
-                                   int64_t n_rows, int row4) {
+                                   int64_t n_rows, int row4, const unsigned long long *start_ptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * row4) return;
+  if (start_ptr != nullptr) start += (int64_t)*start_ptr;          // graph replay: the row offset lives in device memory
   const int64_t r = i / row4;
   const int c = (int)(i % row4);
   reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(data) + perm[start + r] * row4 + c);
 }
-int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st) {
+int gather_rows(const float *data, const int64_t *perm, int64_t start, float *out, int64_t n_rows, int64_t row_floats, cudaStream_t st,
+                const unsigned long long *start_ptr) {
   if (n_rows == 0) return 0;
   GT_CHECK(row_floats % 4 == 0, "gather_rows: row length must be a multiple of 4 floats");
   const int64_t n = n_rows * (row_floats / 4);
   { LaunchScope _ls(KC_ELEMWISE, st);
-    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(data, perm, start, out, n_rows, (int)(row_floats / 4)); }
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(data, perm, start, out, n_rows, (int)(row_floats / 4), start_ptr); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -941,9 +943,14 @@ int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream
   return 0;
 }
 __global__ void adam_kernel(float *p, const float *__restrict__ g, float *m, float *v, int64_t n, float lr, float b1, float b2,
-                            float eps, float bc1, float bc2_sqrt, float gs) {
+                            float eps, float bc1, float bc2_sqrt, float gs, const unsigned long long *t_ptr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (t_ptr != nullptr) {                              // graph replay: bias corrections from the device-resident step counter
+    const float t = (float)(*t_ptr + 1ull);
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   // torch/optim/adam.py _single_tensor_adam: exp_avg.lerp_(grad, 1-b1); exp_avg_sq = b2*v + (1-b2) g^2;
   // denom = sqrt(v)/sqrt(bias_correction2) + eps ; p -= (lr / bias_correction1) * m / denom
   float gi = g[i] * gs;
@@ -954,12 +961,38 @@ __global__ void adam_kernel(float *p, const float *__restrict__ g, float *m, flo
   p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps, int64_t step,
-              float gs, cudaStream_t st) {
+              float gs, cudaStream_t st, const unsigned long long *t_ptr) {
   if (n == 0) return 0;
-  GT_CHECK(step >= 1, "Adam step is 1-based");
+  GT_CHECK(step >= 1 || t_ptr != nullptr, "Adam step is 1-based");
+  if (step < 1) step = 1;
   double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
   { LaunchScope _ls(KC_OPT, st);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs); }
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs, t_ptr); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// end of one replayed step: the step's six metrics go to slot counters[3] % ring_slots of the ring (if there is one), then
+// counters[0] (dropout step) += 1, [1] (Adam steps taken) += 1, [2] (row offset into the permutation) += batch, [3] (slot) += 1
+__global__ void counter_advance_kernel(unsigned long long *c, unsigned long long batch, const float *metrics6, float *ring,
+                                       unsigned long long ring_slots) {
+  const unsigned long long slot = c[3];
+  if (ring != nullptr && threadIdx.x < 6) ring[(slot % ring_slots) * 6 + threadIdx.x] = metrics6[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) { c[0] += 1ull; c[1] += 1ull; c[2] += batch; c[3] = slot + 1ull; }
+}
+// forces the (lazily loaded) optimizer kernels into the context: a first launch must not happen inside a stream capture
+int optimizer_kernels_warm() {
+  cudaFuncAttributes fa;
+  GT_CUDA(cudaFuncGetAttributes(&fa, sgd_kernel));
+  GT_CUDA(cudaFuncGetAttributes(&fa, adam_kernel));
+  GT_CUDA(cudaFuncGetAttributes(&fa, counter_advance_kernel));
+  GT_CUDA(cudaFuncGetAttributes(&fa, gather_rows_kernel));
+  return 0;
+}
+int counter_advance(unsigned long long *counters, int64_t batch, const float *metrics6, float *ring, int64_t ring_slots, cudaStream_t st) {
+  { LaunchScope _ls(KC_OPT, st);
+    counter_advance_kernel<<<1, 32, 0, st>>>(counters, (unsigned long long)batch, metrics6, ring, (unsigned long long)(ring_slots > 0 ? ring_slots : 1)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }

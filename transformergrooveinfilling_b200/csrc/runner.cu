@@ -13,6 +13,7 @@
 namespace gt {
 
 static thread_local std::string g_err;
+thread_local const unsigned long long *g_drop_step_ptr = nullptr;
 void set_error(const std::string &msg) { g_err = msg; }
 
 // ---- launch accounting ------------------------------------------------------------------------
@@ -817,6 +818,68 @@ int gt_train_steps(const gt_config *cfg, float *params, const float *pe, const f
     if (optimizer == 0) GT_TRY(sgd_step(params, grads, L.total, lr, 1.f, st));
     else GT_TRY(adam_step(params, grads, m, v, L.total, lr, 0.9f, 0.999f, 1e-8f, adam_t0 + s + 1, 1.f, st));
   }
+  return 0;
+}
+
+struct GtGraph { cudaGraph_t graph; cudaGraphExec_t exec; };
+
+int gt_graph_train_create(const gt_config *cfg, float *params, const float *pe, float *xbuf, float *ybuf, int64_t n_seq,
+                          float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,
+                          int optimizer, float lr, float *m, float *v, uint64_t seed, unsigned long long *counters,
+                          const float *data_x, const float *data_y, const int64_t *perm, float *metrics_ring,
+                          int64_t ring_slots, void *stream, void **graph_out) {
+  GT_TRY(validate_config(cfg));
+  GT_CHECK(graph_out && counters && xbuf && ybuf && params && grads && metrics6 && hvo, "gt_graph_train_create: null pointer");
+  GT_CHECK(fused_layers(*cfg) && cfg->d_model == 32 && cfg->n_dec == 0 && (cfg->e_src == 16 || cfg->e_src == 27) && cfg->e_tgt == 27,
+           "gt_graph_train_create: available for the fused d_model = 32 encoder-only path (precision bf16)");
+  GT_CHECK(optimizer == 0 || (optimizer == 1 && m && v), "gt_graph_train_create: optimizer must be 0 (SGD) or 1 (Adam, with m and v)");
+  GT_CHECK((data_x == nullptr) == (data_y == nullptr) && (data_x == nullptr) == (perm == nullptr),
+           "gt_graph_train_create: data_x, data_y and perm come together (or all null)");
+  GT_CHECK(metrics_ring == nullptr || ring_slots >= 1, "gt_graph_train_create: a metrics ring needs ring_slots >= 1");
+  GT_CHECK(g_prof_class == KC_NONE && !g_bucket_events_on,
+           "gt_graph_train_create: per-kernel profiling and gradient-bucket events must be off while the step is captured");
+  static thread_local Layout L;
+  GT_TRY(build_layout(*cfg, L));
+  cudaStream_t st = (cudaStream_t)stream;
+  // eager warm-up: loads every kernel of the step and sets its attributes outside the capture (it only writes grads / metrics / hvo /
+  // the workspace, which the first replay overwrites; xbuf / ybuf are read as they are)
+  GT_TRY(gt_train_step(cfg, params, pe, xbuf, ybuf, n_seq, hit_loss_penalty, grads, metrics6, hvo, ws, ws_bytes, seed, 0, 0, stream));
+  GT_TRY(optimizer_kernels_warm());
+  GT_CUDA(cudaStreamSynchronize(st));
+  GT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  if (data_x != nullptr) {
+    rc = gather_rows(data_x, perm, 0, xbuf, n_seq, (int64_t)T * cfg->e_src, st, counters + 2);
+    if (rc == 0) rc = gather_rows(data_y, perm, 0, ybuf, n_seq, (int64_t)T * cfg->e_tgt, st, counters + 2);
+  }
+  g_drop_step_ptr = counters;
+  if (rc == 0) rc = gt_train_step(cfg, params, pe, xbuf, ybuf, n_seq, hit_loss_penalty, grads, metrics6, hvo, ws, ws_bytes, seed, 0, 0, stream);
+  g_drop_step_ptr = nullptr;
+  if (rc == 0) rc = optimizer == 0 ? sgd_step(params, grads, L.total, lr, 1.f, st)
+                                   : adam_step(params, grads, m, v, L.total, lr, 0.9f, 0.999f, 1e-8f, 1, 1.f, st, counters + 1);
+  if (rc == 0) rc = counter_advance(counters, n_seq, metrics6, metrics_ring, ring_slots, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+  GT_CHECK(ce == cudaSuccess && graph != nullptr, std::string("gt_graph_train_create: capture failed: ") + cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  if (ie != cudaSuccess) { cudaGraphDestroy(graph); GT_FAIL(std::string("gt_graph_train_create: instantiate failed: ") + cudaGetErrorString(ie)); }
+  GtGraph *h = new GtGraph{graph, exec};
+  *graph_out = h;
+  return 0;
+}
+int gt_graph_launch(void *graph, int n_replays, void *stream) {
+  GT_CHECK(graph != nullptr && n_replays >= 0, "gt_graph_launch: null graph or negative replay count");
+  for (int i = 0; i < n_replays; ++i) GT_CUDA(cudaGraphLaunch(static_cast<GtGraph *>(graph)->exec, (cudaStream_t)stream));
+  return 0;
+}
+int gt_graph_destroy(void *graph) {
+  if (graph == nullptr) return 0;
+  GtGraph *h = static_cast<GtGraph *>(graph);
+  cudaGraphExecDestroy(h->exec);
+  cudaGraphDestroy(h->graph);
+  delete h;
   return 0;
 }
 

@@ -237,8 +237,10 @@ constexpr int FWD_THREADS = 512;
 // MODE 0: whole encoder layer.  MODE 1 (TC_MODE_FFN): the feed-forward block alone — x_out = LN(x_in + drop(FFN(x_in))) with
 // the block's LayerNorm in g2 / be2 — used for the third block of a decoder layer (torch/nn/modules/transformer.py:1143-1153).
 template <int D, int DH, int MODE>
-__global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLayerArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLayerArgs a_in) {
   static_assert(D == 32, "q|k|v epilogue assigns one 32-column projection per thread part");
+  TcLayerArgs a = a_in;
+  drop_resolve(a.d_attn); drop_resolve(a.d1); drop_resolve(a.d_ffn); drop_resolve(a.d2);     // graph replay: keys from the device step counter
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
@@ -680,8 +682,10 @@ constexpr int BWD_THREADS = 512;
 constexpr int BWD_PARTS = BWD_THREADS / 128;
 
 template <int D, int DH, int MODE>
-__global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLayerArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLayerArgs a_in) {
   static_assert(D == 32, "the register-tile column sums assume d_model == 32");
+  TcLayerArgs a = a_in;
+  drop_resolve(a.d_attn); drop_resolve(a.d1); drop_resolve(a.d_ffn); drop_resolve(a.d2);     // graph replay: keys from the device step counter
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_h;
   __shared__ uint32_t tmem_slot;

@@ -116,21 +116,51 @@ class SweepMember:
                     self.epoch += 1
             self.steps += n_steps
 
+    def _fused_run(self, order: torch.Tensor, start: int, bsz: int, k: int) -> None:
+        """``k`` consecutive batches of ``bsz`` rows starting at row ``start`` of the permutation, in one ``gt_train_steps`` call
+        on the current stream."""
+        import ctypes as C
+        from . import _lib
+        from .training import FusedAdam
+        opt, model, ld = self.optimizer, self.model, self.loader
+        lib = _lib.load()
+        adam = isinstance(opt, FusedAdam)
+        dev = ld.device
+        key = (bsz, model.precision)
+        if model._train_ws is None or model._train_ws[0] != key:
+            model._train_ws = (key, model._workspace(bsz, 1, dev), torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev))
+        _, ws, hvo = model._train_ws
+        xbuf = torch.empty((bsz,) + tuple(ld.x.shape[1:]), device=dev)
+        ybuf = torch.empty((bsz,) + tuple(ld.y.shape[1:]), device=dev)
+        met = torch.empty(k, 6, dtype=torch.float32, device=dev)
+        g = model.flat_grad()
+        cfg = model._cfg()
+        if adam:
+            b1, b2 = opt.param_groups[0]["betas"]
+            assert (b1, b2, opt.param_groups[0]["eps"]) == (0.9, 0.999, 1e-8), "gt_train_steps applies torch's Adam defaults"
+        _lib.check(lib.gt_train_steps(
+            C.byref(cfg), _lib.ptr(model._flat), _lib.ptr(model._pe_flat()), _lib.ptr(ld.x), _lib.ptr(ld.y), _lib.ptr(order),
+            start, bsz, k, self.penalty, _lib.ptr(g), _lib.ptr(met), _lib.ptr(hvo), _lib.ptr(xbuf), _lib.ptr(ybuf), _lib.ptr(ws),
+            ws.numel(), 1 if adam else 0, opt._lr(), _lib.ptr(opt._m) if adam else None, _lib.ptr(opt._v) if adam else None,
+            opt._t if adam else 0, model._seed, model._step, _lib.stream_ptr(dev)), "gt_train_steps")
+        model._step += k
+        if adam:
+            opt._t += k
+        self.metrics.extend(met.unbind(0))
+        self.sequences += bsz * k
+        self._keep = (order, xbuf, ybuf)                      # alive until the stream has consumed them
+
     def run_steps_fused(self, n_steps: int) -> None:
         """Same steps as ``run_steps`` (same permutations, batches, dropout counters, optimizer updates), but every run of
         equal-sized batches of an epoch is ONE library call (``gt_train_steps``: device-side row gather + train step +
         optimizer per step), so the host thread holds the GIL only between epochs — what lets more than a handful of members
         make progress at once."""
-        import ctypes as C
-        from . import _lib
         from .training import FusedAdam, FusedSGD
         if not self.encoder_only:
             raise NotImplementedError("SweepPacker drives encoder-only members (every shipped sweep sets encoder_only: 1)")
-        opt, model, ld = self.optimizer, self.model, self.loader
-        if not isinstance(opt, (FusedSGD, FusedAdam)):
+        ld = self.loader
+        if not isinstance(self.optimizer, (FusedSGD, FusedAdam)):
             return self.run_steps(n_steps)
-        lib = _lib.load()
-        adam = isinstance(opt, FusedAdam)
         dev = ld.device
         with torch.cuda.stream(self.stream):
             done = 0
@@ -142,35 +172,107 @@ class SweepMember:
                     runs.append((S - S % B, S % B, 1))
                 for start, bsz, count in runs:
                     k = min(count, n_steps - done)
-                    if k <= 0:
-                        break
-                    key = (bsz, model.precision)
-                    if model._train_ws is None or model._train_ws[0] != key:
-                        model._train_ws = (key, model._workspace(bsz, 1, dev), torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev))
-                    _, ws, hvo = model._train_ws
-                    xbuf = torch.empty((bsz,) + tuple(ld.x.shape[1:]), device=dev)
-                    ybuf = torch.empty((bsz,) + tuple(ld.y.shape[1:]), device=dev)
-                    met = torch.empty(k, 6, dtype=torch.float32, device=dev)
-                    g = model.flat_grad()
-                    cfg = model._cfg()
-                    if adam:
-                        b1, b2 = opt.param_groups[0]["betas"]
-                        assert (b1, b2, opt.param_groups[0]["eps"]) == (0.9, 0.999, 1e-8), "gt_train_steps applies torch's Adam defaults"
-                    _lib.check(lib.gt_train_steps(
-                        C.byref(cfg), _lib.ptr(model._flat), _lib.ptr(model._pe_flat()), _lib.ptr(ld.x), _lib.ptr(ld.y), _lib.ptr(order),
-                        start, bsz, k, self.penalty, _lib.ptr(g), _lib.ptr(met), _lib.ptr(hvo), _lib.ptr(xbuf), _lib.ptr(ybuf), _lib.ptr(ws),
-                        ws.numel(), 1 if adam else 0, opt._lr(), _lib.ptr(opt._m) if adam else None, _lib.ptr(opt._v) if adam else None,
-                        opt._t if adam else 0, model._seed, model._step, _lib.stream_ptr(dev)), "gt_train_steps")
-                    model._step += k
-                    if adam:
-                        opt._t += k
-                    self.metrics.extend(met.unbind(0))
-                    self.sequences += bsz * k
-                    done += k
-                    self._keep = (order, xbuf, ybuf)                      # alive until the stream has consumed them
-                    if done == n_steps:
-                        break
-                else:
+                    if k > 0:
+                        self._fused_run(order, start, bsz, k)
+                        done += k
+                if done < n_steps:
+                    self.epoch += 1
+            self.steps += n_steps
+
+    # ---- CUDA-graph replay: one graph launch per optimizer step --------------------------------------------------------
+    def graph_capable(self) -> bool:
+        """True when this member's step can be replayed as a CUDA graph (``gt_graph_train_create``): the fused d_model = 32
+        encoder-only path in bf16 mode with a fused optimizer."""
+        from . import _lib
+        from .training import FusedAdam, FusedSGD
+        import ctypes as C
+        m = self.model
+        if not self.encoder_only or not isinstance(self.optimizer, (FusedSGD, FusedAdam)):
+            return False
+        cfg = m._cfg()
+        return (_lib.load().gt_path_kind(C.byref(cfg)) == 1 and m.embedding_size_src in (16, 27)
+                and getattr(m, "num_decoder_layers", 0) == 0)
+
+    def _graph_for(self, bsz: int):
+        """The captured step for full batches of ``bsz`` rows (built once; rebuilt if lr / precision change)."""
+        import ctypes as C
+        from . import _lib
+        from .training import FusedAdam
+        opt, model, ld = self.optimizer, self.model, self.loader
+        adam = isinstance(opt, FusedAdam)
+        key = (bsz, model.precision, opt._lr(), self.penalty)
+        g = getattr(self, "_graph", None)
+        if g is not None and g["key"] == key:
+            return g
+        if g is not None:
+            self.stream.synchronize()
+            _lib.check(_lib.load().gt_graph_destroy(g["handle"]), "gt_graph_destroy")
+            self._graph = None
+        dev = ld.device
+        if adam:
+            b1, b2 = opt.param_groups[0]["betas"]
+            assert (b1, b2, opt.param_groups[0]["eps"]) == (0.9, 0.999, 1e-8), "the captured step applies torch's Adam defaults"
+        ring_slots = 1024
+        g = dict(key=key, ring_slots=ring_slots,
+                 ws=model._workspace(bsz, 1, dev), hvo=torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev),
+                 xbuf=torch.zeros((bsz,) + tuple(ld.x.shape[1:]), device=dev), ybuf=torch.zeros((bsz,) + tuple(ld.y.shape[1:]), device=dev),
+                 met6=torch.zeros(6, dtype=torch.float32, device=dev), ring=torch.zeros(ring_slots, 6, dtype=torch.float32, device=dev),
+                 counters=torch.zeros(4, dtype=torch.int64, device=dev), perm=torch.zeros(ld.x.shape[0], dtype=torch.int64, device=dev))
+        handle = C.c_void_p()
+        cfg = model._cfg()
+        self.stream.synchronize()
+        _lib.check(_lib.load().gt_graph_train_create(
+            C.byref(cfg), _lib.ptr(model._flat), _lib.ptr(model._pe_flat()), _lib.ptr(g["xbuf"]), _lib.ptr(g["ybuf"]), bsz, self.penalty,
+            _lib.ptr(model.flat_grad()), _lib.ptr(g["met6"]), _lib.ptr(g["hvo"]), _lib.ptr(g["ws"]), g["ws"].numel(), 1 if adam else 0,
+            opt._lr(), _lib.ptr(opt._m) if adam else None, _lib.ptr(opt._v) if adam else None, model._seed, _lib.ptr(g["counters"]),
+            _lib.ptr(ld.x), _lib.ptr(ld.y), _lib.ptr(g["perm"]), _lib.ptr(g["ring"]), ring_slots, _lib.stream_ptr(dev),
+            C.byref(handle)), "gt_graph_train_create")
+        g["handle"] = handle
+        self._graph = g
+        return g
+
+    def run_steps_graph(self, n_steps: int) -> None:
+        """Same steps as ``run_steps`` / ``run_steps_fused`` (same permutations, batches, dropout counters, optimizer updates),
+        but every full batch is ONE ``cudaGraphLaunch`` (row gather + train step + optimizer + bookkeeping captured once by
+        ``gt_graph_train_create``); the step counters, the row offset into the permutation and the metrics slot live in device
+        memory and the graph advances them itself.  The ragged last batch of an epoch goes through ``gt_train_steps``.
+        Members that are not on the fused d_model = 32 path fall back to ``run_steps_fused``."""
+        import ctypes as C
+        from . import _lib
+        from .training import FusedAdam
+        if not self.graph_capable():
+            return self.run_steps_fused(n_steps)
+        opt, model, ld = self.optimizer, self.model, self.loader
+        lib = _lib.load()
+        adam = isinstance(opt, FusedAdam)
+        dev = ld.device
+        with torch.cuda.stream(self.stream):
+            done = 0
+            S, B = ld.x.shape[0], ld.batch_size
+            while done < n_steps:
+                order = torch.randperm(S, device=dev, generator=ld.gen) if ld.shuffle else torch.arange(S, device=dev)
+                self._keep_order = order
+                full = min(S // B, n_steps - done)
+                if full > 0:
+                    g = self._graph_for(B)
+                    g["perm"].copy_(order)
+                    sp = _lib.stream_ptr(dev)
+                    at = 0
+                    while at < full:
+                        k = min(full - at, g["ring_slots"])
+                        g["counters"].copy_(torch.tensor([model._step, opt._t if adam else 0, at * B, 0], dtype=torch.int64))
+                        _lib.check(lib.gt_graph_launch(g["handle"], k, sp), "gt_graph_launch")
+                        self.metrics.extend(g["ring"][:k].clone().unbind(0))
+                        model._step += k
+                        if adam:
+                            opt._t += k
+                        at += k
+                    self.sequences += B * full
+                    done += full
+                if done < n_steps and S % B and not ld.drop_last:
+                    self._fused_run(order, S - S % B, S % B, 1)
+                    done += 1
+                if done < n_steps:
                     self.epoch += 1
             self.steps += n_steps
 
@@ -202,11 +304,15 @@ class SweepPacker:
             self.members.append(SweepMember(params, x, y, self.device, seed + i))
         torch.cuda.synchronize(self.device)          # dataset copy and parameter initialisation ran on the default stream
 
-    def run(self, n_steps: int, concurrent: bool = True, on_error: Optional[Callable] = None, fused: bool = True) -> None:
+    def run(self, n_steps: int, concurrent: bool = True, on_error: Optional[Callable] = None, fused: bool = True,
+            graph: bool = False) -> None:
         """Every member takes ``n_steps`` optimizer steps.  Returns once all steps are ENQUEUED; ``synchronize()`` or
         ``history()`` waits for the device.  ``fused=True`` drives each member through ``gt_train_steps`` (one library call per
-        run of equal batches of an epoch), ``fused=False`` through the per-step Python loop; both take identical steps."""
-        step_fn = (lambda m: m.run_steps_fused(n_steps)) if fused else (lambda m: m.run_steps(n_steps))
+        run of equal batches of an epoch), ``fused=False`` through the per-step Python loop, ``graph=True`` replays each
+        member's step as a CUDA graph (one ``cudaGraphLaunch`` per step; members off the fused d_model = 32 path use the fused
+        call); all three take identical steps."""
+        step_fn = ((lambda m: m.run_steps_graph(n_steps)) if graph else
+                   (lambda m: m.run_steps_fused(n_steps)) if fused else (lambda m: m.run_steps(n_steps)))
         if not concurrent:
             for m in self.members:
                 step_fn(m)
