@@ -8,7 +8,7 @@ import torch
 import groove_oracle as G
 from _util import build_model
 from transformergrooveinfilling_b200 import FusedSGD, calculate_loss, train_loop
-from transformergrooveinfilling_b200.pipeline import DeviceResidentLoader, HostBatchPrefetcher
+from transformergrooveinfilling_b200.pipeline import DeviceResidentLoader, HostBatchPrefetcher, HostPredictor
 
 pytestmark = pytest.mark.gpu
 
@@ -67,3 +67,27 @@ def test_host_prefetcher_hands_out_submitted_batches_in_order():
     for i, (sx, sy) in enumerate(sums):
         assert float(sx) == float(i) and float(sy) == float(-i)
     assert f.h2d_bytes == 5 * n * 32 * (16 + 27) * 4
+
+
+@pytest.mark.parametrize("n_dec,precision", [(0, "fp32"), (0, "bf16"), (2, "bf16")])
+def test_host_predictor_equals_predict_on_the_whole_array(n_dec, precision):
+    """HostPredictor: chunked, copy-overlapped predict() over a host array returns the [N, 32, 27] array the evaluator builds
+    from model.predict (evaluator.py:171-175): hits as 0 / 1, velocities, offsets — ragged last chunk, pinned or pageable input,
+    caller-provided output, repeated calls on the same slots."""
+    cfg = G.GrooveCfg(32, 4, 64, 2, n_dec, 16, 27, dropout=0.1)
+    m, _ = build_model(cfg, precision=precision)
+    x, _y = G.det_batch(cfg, 1000)
+    x = torch.as_tensor(x, dtype=torch.float32)
+    h, v, o = m.predict(x.cuda())
+    want = torch.cat((h.float(), v, o), 2).cpu()
+    hp = HostPredictor(m, chunk=384)                       # 1000 = 2 x 384 + 232: both slots reused, ragged tail
+    got = hp.predict(x.pin_memory())
+    assert got.shape == (1000, 32, 27) and got.is_pinned() and not m.training
+    assert torch.equal(got, want)                          # same kernels on the same rows: sequences are independent
+    out = torch.empty(1000, 32, 27).pin_memory()
+    assert hp.predict(x, out=out) is out and torch.equal(out, want)        # pageable input, second call
+    assert hp.h2d_bytes == 2 * x.numel() * 4 and hp.d2h_bytes == 2 * want.numel() * 4
+    with pytest.raises(ValueError):
+        hp.predict(x.cuda())
+    with pytest.raises(ValueError):
+        hp.predict(x[:, :, :8])

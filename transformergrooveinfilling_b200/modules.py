@@ -324,14 +324,18 @@ class _GrooveBase(nn.Module):
                                      ws.numel(), self._seed, step, self._seq0, _lib.stream_ptr(x.device)), "gt_train_step")
         return metrics, hvo
 
-    def _predict_hvo(self, src, thres, literal: bool = False):
+    def _predict_hvo(self, src, thres, literal: bool = False, out=None):
         """gt_predict; ``literal=True`` runs the reference's 32 full decoder passes instead of the KV-cached decode
-        (encoder-decoder models; used by the tests to cross-check the two)."""
+        (encoder-decoder models; used by the tests to cross-check the two).  ``out``: a contiguous [n, 32, 27] fp32 device
+        tensor to write into (pipeline.HostPredictor's slots)."""
         lib = _lib.load()
         src = self._check_input(src, self.embedding_size_src, "src")
         n = src.shape[0]
         ws = self._workspace(n, 0 if literal else 2, src.device)
-        out = torch.empty(n, T_STEPS, 27, dtype=torch.float32, device=src.device)
+        if out is None:
+            out = torch.empty(n, T_STEPS, 27, dtype=torch.float32, device=src.device)
+        elif tuple(out.shape) != (n, T_STEPS, 27) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != src.device:
+            raise ValueError("out must be a contiguous float32 [n, 32, 27] tensor on the source's device")
         cfg = self._cfg()
         _lib.check(lib.gt_predict_variant(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._pe_flat()), _lib.ptr(src), n,
                                           float(thres), _lib.ptr(out), _lib.ptr(ws), ws.numel(), 1 if literal else 0,

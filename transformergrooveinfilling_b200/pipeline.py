@@ -14,6 +14,10 @@ are offered:
   ``(x, y, idx)`` like the reference's dataset (`dataset.py:352-356`) and exposes ``.dataset`` with a
   length, so it can be passed to ``train_loop`` as the ``dataloader`` argument unchanged.
 
+* ``HostPredictor`` — the inference side: the evaluator hands ``model.predict`` a HOST array of every test groove and
+  immediately brings the three outputs back to the host (`evaluator.py:171-175`).  The predictor cuts the array into
+  chunks and runs H2D of chunk i+1, ``gt_predict`` of chunk i and D2H of chunk i-1 on three streams.
+
 PyTorch is used for memory, streams and events only; no arithmetic happens here.
 """
 from __future__ import annotations
@@ -120,3 +124,79 @@ class DeviceResidentLoader:
             torch.index_select(self.x, 0, idx, out=bx[:k])
             torch.index_select(self.y, 0, idx, out=by[:k])
             yield bx[:k], by[:k], idx
+
+
+class HostPredictor:
+    """``predict()`` over a HOST array, result back on the host, copies overlapped with compute.
+
+    The reference evaluator calls ``model.predict(processed_inputs, use_thres=True, thres=0.5)`` and then ``.cpu()`` +
+    ``np.concatenate(axis=2)`` on the three outputs (`evaluator.py:171-175`), i.e. what it consumes is one host array
+    ``[N, 32, 27]`` = thresholded hits (as 0.0 / 1.0) | velocities | offsets.  ``predict(xh)`` produces exactly that array:
+    the input is cut into ``chunk``-sequence pieces; piece i+1 is copied host->device on a copy-in stream while piece i runs
+    through ``gt_predict`` on the caller's stream and the hvo of piece i-1 is copied device->host on a copy-out stream (two
+    device slot pairs, events in both directions).  Pinned host arrays make the copies asynchronous; pageable ones work but
+    serialise.  The values are those of ``model.predict`` on the whole array (sequences are independent; tested)."""
+
+    def __init__(self, model, chunk: Optional[int] = None):
+        # default chunk: 4096 sequences for encoder-only models (a chunk is ~7 waves of 148 four-sequence tiles, copies of
+        # 8 MB / 14 MB); 16384 for encoder-decoder models, whose 32-step KV-cached decode is a chain of small kernels per chunk
+        # (measured on C5: 324 K seq/s at 4096 per call, 717 K at 16384) while its copies are < 6 % of the compute time
+        if chunk is None:
+            chunk = 16384 if getattr(model, "num_decoder_layers", 0) > 0 else 4096
+        self.model = model
+        self.device = model.flat_parameters().device
+        if self.device.type != "cuda":
+            raise RuntimeError("HostPredictor needs the model on a CUDA device — the groove_b200 path has no CPU fallback")
+        self.chunk = int(chunk)
+        if self.chunk < 1:
+            raise ValueError("chunk must be >= 1")
+        e = model.embedding_size_src
+        self.s_in, self.s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.xs = [torch.empty(self.chunk, 32, e, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.os = [torch.empty(self.chunk, 32, 27, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def predict(self, xh: torch.Tensor, out: Optional[torch.Tensor] = None, thres: float = 0.5) -> torch.Tensor:
+        xh = torch.as_tensor(xh, dtype=torch.float32)
+        if xh.is_cuda:
+            raise ValueError("HostPredictor.predict takes a host array; call model.predict for device tensors")
+        if xh.dim() != 3 or tuple(xh.shape[1:]) != tuple(self.xs[0].shape[1:]):
+            raise ValueError(f"src must be [N, 32, {self.xs[0].shape[2]}], got {tuple(xh.shape)}")
+        xh = xh.contiguous()
+        n = xh.shape[0]
+        if out is None:
+            out = torch.empty(n, 32, 27, dtype=torch.float32).pin_memory()
+        elif tuple(out.shape) != (n, 32, 27) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 host tensor [N, 32, 27]")
+        self.model.eval()                                         # predict()'s side effect (BGT/models/transformer.py:118)
+        cur = torch.cuda.current_stream(self.device)
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+        computed = [None, None]                                   # gt_predict finished with slot s (recorded on cur)
+        drained = [None, None]                                    # D2H finished reading os[s] (recorded on s_out)
+        with torch.no_grad():
+            for i, lo in enumerate(range(0, n, self.chunk)):
+                k, s = min(self.chunk, n - lo), i & 1
+                with torch.cuda.stream(self.s_in):
+                    if computed[s] is not None:
+                        self.s_in.wait_event(computed[s])
+                    self.xs[s][:k].copy_(xh[lo:lo + k], non_blocking=True)
+                    arrived = torch.cuda.Event()
+                    arrived.record(self.s_in)
+                cur.wait_event(arrived)
+                if drained[s] is not None:
+                    cur.wait_event(drained[s])
+                self.model._predict_hvo(self.xs[s][:k], thres, out=self.os[s][:k])
+                computed[s] = torch.cuda.Event()
+                computed[s].record(cur)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(computed[s])
+                    out[lo:lo + k].copy_(self.os[s][:k], non_blocking=True)
+                    drained[s] = torch.cuda.Event()
+                    drained[s].record(self.s_out)
+        cur.wait_stream(self.s_in)
+        self.s_out.synchronize()                                  # the host array is complete when predict() returns
+        self.h2d_bytes += xh.numel() * 4
+        self.d2h_bytes += out.numel() * 4
+        return out
