@@ -86,6 +86,46 @@ __device__ __forceinline__ void tile_store(const float4 (&v)[ITEMS][2], uint8_t 
 
 __device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }
 
+// Fast path of tile_load / tile_store for a tile that lies wholly inside its operand, with 16-byte loads legal and every K block
+// full.  Item it of thread tid sits at image row r0 + it * (256 >> lch), chunk c = (tid >> 3) & (CH - 1) (32 is a multiple of
+// CH <= 32, so the chunk does not depend on it): the global pointer and the image offset advance by constants per item, and the
+// pointer by a constant per K block — no per-item index arithmetic or bounds checks in the main loop.
+struct FastOp {
+  const float *p;          // this thread's first item of the current K block
+  int64_t istep;           // floats between consecutive items
+  int64_t kadv;            // floats between consecutive K blocks
+  uint32_t soff, sstep;    // image byte offset of the first item, bytes between items
+};
+__device__ __forceinline__ FastOp fast_op(const float *src, int64_t ld, int rows, int lch, int64_t row0, int64_t col0, bool k_is_row, int tid) {
+  FastOp f;
+  const int c = (tid >> 3) & ((1 << lch) - 1);
+  const int r0 = (tid & 7) | (((tid >> 3) >> lch) << 3);
+  const int rstep = GTHREADS >> lch;
+  f.p = src + (row0 + r0) * ld + col0 + (int64_t)c * 8;
+  f.istep = (int64_t)rstep * ld;
+  f.kadv = k_is_row ? (int64_t)GBK * ld : (int64_t)GBK;
+  f.soff = kmajor_off(r0, c * 8, rows);
+  f.sstep = (uint32_t)(rstep >> 3) * 128u;
+  return f;
+}
+template <int ITEMS>
+__device__ __forceinline__ void fast_load(float4 (&v)[ITEMS][2], const FastOp &f) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const float4 *q = reinterpret_cast<const float4 *>(f.p + it * f.istep);
+    v[it][0] = __ldg(q);
+    v[it][1] = __ldg(q + 1);
+  }
+}
+template <int ITEMS>
+__device__ __forceinline__ void fast_store(const float4 (&v)[ITEMS][2], uint8_t *img, const FastOp &f) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it)
+    *reinterpret_cast<uint4 *>(img + f.soff + it * f.sstep) =
+        make_uint4(pack_bf16(v[it][0].x, v[it][0].y), pack_bf16(v[it][0].z, v[it][0].w), pack_bf16(v[it][1].x, v[it][1].y),
+                   pack_bf16(v[it][1].z, v[it][1].w));
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g) {
   constexpr uint32_t A_BYTES = GBM * GBK * 2, B_BYTES = BN * GBK * 2, STG = A_BYTES + B_BYTES;
@@ -123,18 +163,26 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   const uint32_t a_kstep = a_mn ? 256u : 2u * (GBM / 8) * 128u, b_kstep = b_mn ? 256u : 2u * (BN / 8) * 128u;   // bytes per k16
 
   const int nkb = (int)((k_end - k_begin + GBK - 1) / GBK);
+  // interior tiles (the common case: every dimension of the reference's models is a multiple of the tile) take the fast path
+  const bool k_full = ((k_end - k_begin) % GBK) == 0;
+  const bool a_fast = g.a_vec != 0 && k_full && m0 + GBM <= g.M;
+  const bool b_fast = g.b_vec != 0 && k_full && nrem == BN && (BN * GBK / 8) % GTHREADS == 0;
+  FastOp fa = a_mn ? fast_op(g.A, a_ld, a_rows, a_lch, k_begin, m0, true, tid) : fast_op(g.A, a_ld, a_rows, a_lch, m0, k_begin, false, tid);
+  FastOp fb = b_mn ? fast_op(g.B, b_ld, b_rows, b_lch, k_begin, n0, true, tid) : fast_op(g.B, b_ld, b_rows, b_lch, n0, k_begin, false, tid);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % GSTG;
     const int64_t k0 = k_begin + (int64_t)kb * GBK;
     float4 ra[AI][2], rb[BI][2];
-    if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, k_end, m0, g.M, g.a_vec != 0, tid);
+    if (a_fast) { fast_load<AI>(ra, fa); fa.p += fa.kadv; }
+    else if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, k_end, m0, g.M, g.a_vec != 0, tid);
     else tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, m0, g.M, k0, k_end, g.a_vec != 0, tid);
-    if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, k_end, n0, g.N, g.b_vec != 0, tid);
+    if (b_fast) { fast_load<BI>(rb, fb); fb.p += fb.kadv; }
+    else if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, k_end, n0, g.N, g.b_vec != 0, tid);
     else tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, n0, g.N, k0, k_end, g.b_vec != 0, tid);
     if (kb >= GSTG) mbar_wait(&bar_free[s], (uint32_t)((kb / GSTG) - 1) & 1u);    // the MMAs that read this stage have retired
     uint8_t *sA = smem + (uint32_t)s * STG, *sB = sA + A_BYTES;
-    tile_store<AI>(ra, sA, a_rows, a_lch, tid);
-    tile_store<BI>(rb, sB, b_rows, b_lch, tid);
+    if (a_fast) fast_store<AI>(ra, sA, fa); else tile_store<AI>(ra, sA, a_rows, a_lch, tid);
+    if (b_fast) fast_store<BI>(rb, sB, fb); else tile_store<BI>(rb, sB, b_rows, b_lch, tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -162,7 +210,13 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   const int q = warp & 3;
   const int64_t mw0 = m0 + q * 32;                        // first row of this warp
   const bool first_split = blockIdx.y == 0;
-  float *buf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
+  // vector form of phase 2 (every case but the positional-encoding epilogue of the input layer, given 16-byte alignment): lane
+  // = (row i & 3, column quad): one 16-byte access per operand per lane, four whole 128-byte row segments per warp instruction
+  auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec_epi = !e.pe && (g.N & 3) == 0 && (g.ldc & 3) == 0 && al16(g.C) && (!e.bias || al16(e.bias)) &&
+                       (!e.residual || ((e.ld_res & 3) == 0 && al16(e.residual))) && (!e.mask_pos || ((e.ld_mask & 3) == 0 && al16(e.mask_pos)));
+  constexpr int BS = 36;                                  // floats per buffer row: 16-byte aligned rows, conflict-free float4 access
+  float *buf = reinterpret_cast<float *>(smem) + warp * (32 * BS);
   for (int cb = (warp >> 2) * 32; cb < nn; cb += 64) {
     float v[32];
     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
@@ -171,8 +225,17 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
     {
       const int64_t m = mw0 + lane;
       if (e.bias && first_split) {
+        if (vec_epi) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (nb + j < g.N) v[j] += __ldg(e.bias + nb + j);
+          for (int j = 0; j < 32; j += 4)
+            if (nb + j < g.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + nb + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < g.N) v[j] += __ldg(e.bias + nb + j);
+        }
       }
       if (e.relu) {
 #pragma unroll
@@ -200,14 +263,40 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
     }
     __syncwarp();                                           // the previous chunk's phase 2 has finished reading buf
 #pragma unroll
-    for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(&buf[lane * BS + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     __syncwarp();
+    const int rows = (int)min((int64_t)32, g.M - mw0);
+    if (vec_epi) {
+      const int cq = (lane & 7) * 4;
+      const int64_t n = nb + cq;
+      if (n < g.N) {                                        // N % 4 == 0: the quad is in range as a whole
+        for (int i = lane >> 3; i < rows; i += 4) {
+          const int64_t m = mw0 + i;
+          float4 w = *reinterpret_cast<const float4 *>(&buf[i * BS + cq]);
+          if (e.mask_pos) {
+            const float4 k4 = __ldg(reinterpret_cast<const float4 *>(e.mask_pos + m * e.ld_mask + n));
+            w.x = k4.x > 0.f ? w.x * e.mask_scale : 0.f; w.y = k4.y > 0.f ? w.y * e.mask_scale : 0.f;
+            w.z = k4.z > 0.f ? w.z * e.mask_scale : 0.f; w.w = k4.w > 0.f ? w.w * e.mask_scale : 0.f;
+          }
+          if (e.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4 *>(e.residual + m * e.ld_res + n));
+            w.x += r4.x; w.y += r4.y; w.z += r4.z; w.w += r4.w;
+          }
+          float *c = g.C + m * g.ldc + n;
+          if (e.atomic) { atomicAdd(c, w.x); atomicAdd(c + 1, w.y); atomicAdd(c + 2, w.z); atomicAdd(c + 3, w.w); }
+          else if (e.accumulate) {
+            const float4 o = *reinterpret_cast<const float4 *>(c);
+            *reinterpret_cast<float4 *>(c) = make_float4(o.x + w.x, o.y + w.y, o.z + w.z, o.w + w.w);
+          } else *reinterpret_cast<float4 *>(c) = w;
+        }
+      }
+      continue;
+    }
     const int64_t n = nb + lane;
     if (n < g.N) {
-      const int rows = (int)min((int64_t)32, g.M - mw0);
       for (int i = 0; i < rows; ++i) {
         const int64_t m = mw0 + i;
-        float w = buf[i * 33 + lane];
+        float w = buf[i * BS + lane];
         if (e.pe) {
           w += __ldg(e.pe + (m % T) * g.N + n);
           if (e.drop.thr) w = drop_keep(e.drop.key, e.drop.thr, (uint64_t)((e.drop_row0 + m) * g.N + n)) ? w * e.drop.scale : 0.f;
