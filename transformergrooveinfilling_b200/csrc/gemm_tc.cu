@@ -347,10 +347,39 @@ int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sb
   GemmTcArgs g;
   g.A = A; g.B = B; g.C = C; g.sam = sam; g.sak = sak; g.sbn = sbn; g.sbk = sbk; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.e = epi;
+  // tile width: the narrowest of {32, 64, 128, 256} that covers N, 256-wide tiles beyond that (a 384 / 768-wide output uses 128 / 256)
+  // (measured on C3, batch 8192: capping the tile at 128 / 64 columns costs 23 % / 69 % of the GEMM time — every extra n-tile
+  //  re-stages and re-converts the 128-row A block, which is what bounds this kernel)
+  int bn;
+  if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else if (N <= 256) bn = 256;
+  else bn = (N % 256 == 0 || N % 256 > 128) ? 256 : ((N % 128 == 0 || N % 128 > 64) ? 128 : 256);
+  g.n_tiles = (int)((N + bn - 1) / bn);
+  const int64_t m_tiles = (M + GBM - 1) / GBM;
   int64_t splits = 1;
   if (split_k_chunk > 0 && K > split_k_chunk) {
     split_k_chunk = (split_k_chunk + GBK - 1) / GBK * GBK;
     splits = (K + split_k_chunk - 1) / split_k_chunk;
+    // Weight gradients have a handful of output tiles and a very long contraction: the requested chunk only bounds the split from
+    // above.  Shrink it so that tiles x splits fills whole waves of the 2 x 148 resident CTAs (C3 dW1: 4 tiles x 128 splits =
+    // 1.73 waves of 2048-token chunks -> 4 x 147 = 1.99 waves of 1792-token chunks).
+    static int slots = 0;
+    if (slots == 0) {
+      int dev = 0, sms = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      slots = 2 * sms;
+    }
+    const int64_t tiles = m_tiles * g.n_tiles;
+    if (splits >= 8 && tiles < slots) {
+      const int64_t waves = (tiles * splits + slots - 1) / slots;
+      const int64_t want = waves * slots / tiles;
+      if (want > splits) {
+        const int64_t chunk = ((K + want - 1) / want + GBK - 1) / GBK * GBK;
+        if (chunk >= 4 * GBK) { split_k_chunk = chunk; splits = (K + chunk - 1) / chunk; }
+      }
+    }
     while (splits > 65535) { split_k_chunk *= 2; splits = (K + split_k_chunk - 1) / split_k_chunk; }
     g.kchunk = split_k_chunk;
     GT_CHECK(epi.atomic, "split-K GEMM needs an atomic epilogue");
@@ -362,16 +391,7 @@ int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sb
   g.b_vec = aligned16(B) && (b_ld % 4 == 0);
   // a K-major source starts its chunks at k0 (multiple of 64) and an MN-major one at m0 / n0 (multiples of 128 / BN): always 16-byte
   // aligned relative to the base; K-split offsets are multiples of 64 as well.
-  const int64_t m_tiles = (M + GBM - 1) / GBM;
   GT_CHECK(m_tiles * ((N + 31) / 32) < (int64_t)1 << 31, "gemm_tc: too many tiles");
-  // tile width: the narrowest of {32, 64, 128, 256} that covers N, 256-wide tiles beyond that (a 384 / 768-wide output uses 128 / 256)
-  int bn;
-  if (N <= 32) bn = 32;
-  else if (N <= 64) bn = 64;
-  else if (N <= 128) bn = 128;
-  else if (N <= 256) bn = 256;
-  else bn = (N % 256 == 0 || N % 256 > 128) ? 256 : ((N % 128 == 0 || N % 128 > 64) ? 128 : 256);
-  g.n_tiles = (int)((N + bn - 1) / bn);
   switch (bn) {
     case 32: return launch<32>(g, m_tiles, splits, st);
     case 64: return launch<64>(g, m_tiles, splits, st);
