@@ -35,7 +35,9 @@ def _gemm(tc, a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, flags=0, bias=None, res
 
 # (M, N, K): token-rows x out-features x in-features of the model's Linear layers, plus ragged cases
 LINEAR_SHAPES = [(128, 32, 32), (256, 96, 32), (4 * 32, 768, 256), (7 * 32, 512, 256), (13 * 32, 256, 512), (5 * 32, 64, 64),
-                 (9 * 32, 192, 64), (1000, 100, 72), (33, 40, 33), (640, 384, 128)]
+                 (9 * 32, 192, 64), (1000, 100, 72), (33, 40, 33), (640, 384, 128),
+                 # 16 or more M tiles: the weight operand is pre-built as bf16 images once per GEMM and fetched by bulk TMA
+                 (2048, 768, 256), (4099, 100, 72), (2048 + 33, 512, 512), (3000, 40, 33), (64 * 32, 32, 32), (2500, 1024, 192)]
 
 
 @pytest.mark.parametrize("m,n,k", LINEAR_SHAPES)

@@ -17,6 +17,8 @@
 // and consumed as an MN-major operand — no transposition in registers or shared memory.
 #include "common.cuh"
 #include "umma.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace gt {
 using namespace umma;
@@ -31,6 +33,8 @@ struct GemmTcArgs {
   int64_t sam, sak, sbn, sbk, ldc, M, N, K, kchunk;
   int n_tiles;
   int a_vec, b_vec;                 // 16-byte loads are legal on A / B
+  const uint8_t *b_img;             // pre-built bf16 images of B, one per (n-tile, K block) in that order (gemm_tc_bimg_kernel), or null
+  int nkb_img;                      // K blocks per n-tile in b_img
   GemmEpi e;
 };
 
@@ -126,13 +130,32 @@ __device__ __forceinline__ void fast_store(const float4 (&v)[ITEMS][2], uint8_t 
                    pack_bf16(v[it][1].z, v[it][1].w));
 }
 
+// B as the weight operand of a forward / data-gradient GEMM is tiny and shared by every one of the thousands of M tiles, yet it
+// was two thirds of each CTA's staging work (256 of the 384 rows converted per K block).  This pre-pass converts it ONCE per
+// GEMM into the exact shared-memory images (zero-padded at the edges), one contiguous BN x 64 block per (n-tile, K block); the
+// main kernel then fetches a block with a single bulk-TMA copy — no registers, no conversion, no bounds logic for B.
+template <int BN>
+__global__ void __launch_bounds__(GTHREADS) gemm_tc_bimg_kernel(const GemmTcArgs g, uint8_t *img) {
+  constexpr int BI = (BN * GBK / 8 + GTHREADS - 1) / GTHREADS;
+  constexpr uint32_t B_BYTES = BN * GBK * 2;
+  const int tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * BN, k0 = (int64_t)blockIdx.y * GBK;
+  const bool b_mn = g.sbk != 1;
+  const int b_rows = b_mn ? GBK : BN, b_lch = b_mn ? ilog2(BN / 8) : 3;
+  const int64_t b_ld = b_mn ? g.sbk : g.sbn;
+  float4 rb[BI][2];
+  if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, g.K, n0, g.N, g.b_vec != 0, tid);
+  else tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, n0, g.N, k0, g.K, g.b_vec != 0, tid);
+  tile_store<BI>(rb, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * B_BYTES, b_rows, b_lch, tid);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g) {
   constexpr uint32_t A_BYTES = GBM * GBK * 2, B_BYTES = BN * GBK * 2, STG = A_BYTES + B_BYTES;
   constexpr int AI = GBM * GBK / 8 / GTHREADS, BI = (BN * GBK / 8 + GTHREADS - 1) / GTHREADS;
   constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_free[GSTG], bar_done;
+  __shared__ __align__(8) uint64_t bar_free[GSTG], bar_b[GSTG], bar_done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)(blockIdx.x / g.n_tiles) * GBM;
@@ -145,7 +168,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
 
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   if (tid == 0) {
-    for (int i = 0; i < GSTG; ++i) mbar_init(&bar_free[i], 1);
+    for (int i = 0; i < GSTG; ++i) { mbar_init(&bar_free[i], 1); mbar_init(&bar_b[i], 1); }
     mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
@@ -167,27 +190,38 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   const bool k_full = ((k_end - k_begin) % GBK) == 0;
   const bool a_fast = g.a_vec != 0 && k_full && m0 + GBM <= g.M;
   const bool b_fast = g.b_vec != 0 && k_full && nrem == BN && (BN * GBK / 8) % GTHREADS == 0;
+  const bool b_pre = g.b_img != nullptr;                  // B blocks come ready-made by bulk TMA (never with split-K: k_begin = 0)
+  const uint8_t *b_src = b_pre ? g.b_img + (size_t)(blockIdx.x % g.n_tiles) * g.nkb_img * B_BYTES : nullptr;
   FastOp fa = a_mn ? fast_op(g.A, a_ld, a_rows, a_lch, k_begin, m0, true, tid) : fast_op(g.A, a_ld, a_rows, a_lch, m0, k_begin, false, tid);
   FastOp fb = b_mn ? fast_op(g.B, b_ld, b_rows, b_lch, k_begin, n0, true, tid) : fast_op(g.B, b_ld, b_rows, b_lch, n0, k_begin, false, tid);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % GSTG;
     const int64_t k0 = k_begin + (int64_t)kb * GBK;
     float4 ra[AI][2], rb[BI][2];
+    if (b_pre && tid == 0) {                                // first thing in the block: the copy lands while A is fetched and converted
+      if (kb >= GSTG) mbar_wait(&bar_free[s], (uint32_t)((kb / GSTG) - 1) & 1u);
+      mbar_expect_tx(&bar_b[s], B_BYTES);
+      tma_load_1d(smem + (uint32_t)s * STG + A_BYTES, b_src + (size_t)kb * B_BYTES, B_BYTES, &bar_b[s]);
+    }
     if (a_fast) { fast_load<AI>(ra, fa); fa.p += fa.kadv; }
     else if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, k_end, m0, g.M, g.a_vec != 0, tid);
     else tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, m0, g.M, k0, k_end, g.a_vec != 0, tid);
-    if (b_fast) { fast_load<BI>(rb, fb); fb.p += fb.kadv; }
+    if (b_pre) {}
+    else if (b_fast) { fast_load<BI>(rb, fb); fb.p += fb.kadv; }
     else if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, k_end, n0, g.N, g.b_vec != 0, tid);
     else tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, n0, g.N, k0, k_end, g.b_vec != 0, tid);
     if (kb >= GSTG) mbar_wait(&bar_free[s], (uint32_t)((kb / GSTG) - 1) & 1u);    // the MMAs that read this stage have retired
     uint8_t *sA = smem + (uint32_t)s * STG, *sB = sA + A_BYTES;
     if (a_fast) fast_store<AI>(ra, sA, fa); else tile_store<AI>(ra, sA, a_rows, a_lch, tid);
-    if (b_fast) fast_store<BI>(rb, sB, fb); else tile_store<BI>(rb, sB, b_rows, b_lch, tid);
+    if (b_pre) {}
+    else if (b_fast) fast_store<BI>(rb, sB, fb);
+    else tile_store<BI>(rb, sB, b_rows, b_lch, tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
+      if (b_pre) mbar_wait(&bar_b[s], (uint32_t)(kb / GSTG) & 1u);
       const int64_t krem = k_end - k0;
       const int nk16 = krem >= GBK ? GBK / 16 : (int)((krem + 15) / 16);
       const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
@@ -317,13 +351,46 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// scratch for the B images: one buffer per (device, stream), kept for the life of the process — GEMMs of one stream run in order,
+// so the next pre-pass cannot overwrite images a previous main kernel still reads; different streams (sweep members, each on its
+// own host thread) never share a buffer
+constexpr size_t BIMG_BYTES = 4u << 20;
+uint8_t *bimg_scratch(cudaStream_t st) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, uint8_t *> pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(st) * 64u + (uint64_t)dev;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = pool.find(key);
+  if (it != pool.end()) return it->second;
+  void *p = nullptr;
+  if (cudaMalloc(&p, BIMG_BYTES) != cudaSuccess) { cudaGetLastError(); p = nullptr; }    // no scratch: the GEMM stages B itself
+  pool[key] = static_cast<uint8_t *>(p);
+  return static_cast<uint8_t *>(p);
+}
+
 template <int BN>
-int launch(const GemmTcArgs &g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
+int launch(GemmTcArgs g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
   constexpr size_t smem = (size_t)GSTG * (GBM * GBK * 2 + BN * GBK * 2);
   static bool attr_done = false;
   if (!attr_done) {
     GT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
+  }
+  g.b_img = nullptr; g.nkb_img = 0;
+  const int64_t nkb = (g.K + GBK - 1) / GBK;
+  const size_t need = (size_t)g.n_tiles * nkb * BN * GBK * 2;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (splits == 1 && m_tiles >= 16 && need <= BIMG_BYTES && cap == cudaStreamCaptureStatusNone) {
+    uint8_t *img = bimg_scratch(st);
+    if (img != nullptr) {
+      { LaunchScope _ls(KC_GEMM_TC, st);
+        gemm_tc_bimg_kernel<BN><<<dim3((unsigned)g.n_tiles, (unsigned)nkb), GTHREADS, 0, st>>>(g, img); }
+      GT_CUDA(cudaGetLastError());
+      g.b_img = img; g.nkb_img = (int)nkb;
+    }
   }
   dim3 grid((unsigned)(m_tiles * g.n_tiles), (unsigned)splits);
   { LaunchScope _ls(KC_GEMM_TC, st);
