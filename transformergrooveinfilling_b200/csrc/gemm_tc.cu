@@ -34,7 +34,8 @@ struct GemmTcArgs {
   int n_tiles;
   int a_vec, b_vec;                 // 16-byte loads are legal on A / B
   const uint8_t *b_img;             // pre-built bf16 images of B, one per (n-tile, K block) in that order (gemm_tc_bimg_kernel), or null
-  int nkb_img;                      // K blocks per n-tile in b_img
+  const uint8_t *a_img;             // same for A, one per (m-tile, K block) (gemm_tc_aimg_kernel); only together with b_img
+  int nkb_img;                      // K blocks of the whole contraction (per n-tile / m-tile in the images)
   GemmEpi e;
 };
 
@@ -149,6 +150,23 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tc_bimg_kernel(const GemmTcArgs
   tile_store<BI>(rb, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * B_BYTES, b_rows, b_lch, tid);
 }
 
+// The same for A (activations): one streaming pass fp32 -> bf16 images, after which the main kernel's K loop is two bulk-TMA
+// copies and four UMMAs per block issued by one thread — the conversion runs at full occupancy here instead of latency-bound
+// inside a 2-CTA-per-SM GEMM, and an A block shared by several n-tiles is converted once.
+__global__ void __launch_bounds__(GTHREADS) gemm_tc_aimg_kernel(const GemmTcArgs g, uint8_t *img) {
+  constexpr int AI = GBM * GBK / 8 / GTHREADS;
+  constexpr uint32_t A_BYTES = GBM * GBK * 2;
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * GBM, k0 = (int64_t)blockIdx.y * GBK;
+  const bool a_mn = g.sak != 1;
+  const int a_rows = a_mn ? GBK : GBM, a_lch = a_mn ? 4 : 3;
+  const int64_t a_ld = a_mn ? g.sak : g.sam;
+  float4 ra[AI][2];
+  if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, g.K, m0, g.M, g.a_vec != 0, tid);
+  else tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, m0, g.M, k0, g.K, g.a_vec != 0, tid);
+  tile_store<AI>(ra, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * A_BYTES, a_rows, a_lch, tid);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g) {
   constexpr uint32_t A_BYTES = GBM * GBK * 2, B_BYTES = BN * GBK * 2, STG = A_BYTES + B_BYTES;
@@ -186,6 +204,44 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   const uint32_t a_kstep = a_mn ? 256u : 2u * (GBM / 8) * 128u, b_kstep = b_mn ? 256u : 2u * (BN / 8) * 128u;   // bytes per k16
 
   const int nkb = (int)((k_end - k_begin + GBK - 1) / GBK);
+  if (g.a_img != nullptr) {
+    // both operands pre-imaged: thread 0 alone runs the K loop (copies of block kb + 2 are issued as soon as the MMAs of block
+    // kb have retired), the other warps go straight to the epilogue's wait; its own warp parks at the __syncwarp instead of
+    // spinning on the barrier next to it
+    if (warp == 0) {
+    if (lane == 0) {
+      const int64_t kb0 = k_begin / GBK;
+      const uint8_t *a_src = g.a_img + ((size_t)(blockIdx.x / g.n_tiles) * g.nkb_img + kb0) * A_BYTES;
+      const uint8_t *b_src = g.b_img + ((size_t)(blockIdx.x % g.n_tiles) * g.nkb_img + kb0) * B_BYTES;
+      auto issue = [&](int kb) {
+        const int s = kb % GSTG;
+        uint8_t *sA = smem + (uint32_t)s * STG;
+        mbar_expect_tx(&bar_b[s], STG);
+        tma_load_1d(sA, a_src + (size_t)kb * A_BYTES, A_BYTES, &bar_b[s]);
+        tma_load_1d(sA + A_BYTES, b_src + (size_t)kb * B_BYTES, B_BYTES, &bar_b[s]);
+      };
+      for (int kb = 0; kb < nkb && kb < GSTG; ++kb) issue(kb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GSTG;
+        mbar_wait(&bar_b[s], (uint32_t)(kb / GSTG) & 1u);
+        fence_after_sync();
+        const int64_t krem = k_end - (k_begin + (int64_t)kb * GBK);
+        const int nk16 = krem >= GBK ? GBK / 16 : (int)((krem + 15) / 16);
+        const uint32_t aA = smem_u32(smem + (uint32_t)s * STG), aB = aA + A_BYTES;
+        for (int k = 0; k < nk16; ++k)
+          mma_bf16_ss(tmem, make_desc(aA + (uint32_t)k * a_kstep, a_lbo, a_sbo), make_desc(aB + (uint32_t)k * b_kstep, b_lbo, b_sbo), idesc,
+                      (kb | k) > 0 ? 1u : 0u);
+        mma_commit(&bar_free[s]);
+        if (kb + 1 == nkb) mma_commit(&bar_done);
+        if (kb + GSTG < nkb) {
+          mbar_wait(&bar_free[s], (uint32_t)(kb / GSTG) & 1u);
+          issue(kb + GSTG);
+        }
+      }
+    }
+    __syncwarp();
+    }
+  } else {
   // interior tiles (the common case: every dimension of the reference's models is a multiple of the tile) take the fast path
   const bool k_full = ((k_end - k_begin) % GBK) == 0;
   const bool a_fast = g.a_vec != 0 && k_full && m0 + GBM <= g.M;
@@ -231,6 +287,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
       mma_commit(&bar_free[s]);
       if (kb + 1 == nkb) mma_commit(&bar_done);
     }
+  }
   }
   mbar_wait(&bar_done, 0);
   fence_after_sync();
@@ -351,23 +408,34 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// scratch for the B images: one buffer per (device, stream), kept for the life of the process — GEMMs of one stream run in order,
-// so the next pre-pass cannot overwrite images a previous main kernel still reads; different streams (sweep members, each on its
-// own host thread) never share a buffer
-constexpr size_t BIMG_BYTES = 4u << 20;
-uint8_t *bimg_scratch(cudaStream_t st) {
+// scratch for the operand images: one buffer per (device, stream), grown on demand and kept for the life of the process — GEMMs
+// of one stream run in order, so the next pre-pass cannot overwrite images a previous main kernel still reads; different
+// streams (sweep members, each on its own host thread) never share a buffer.  Growing frees the old buffer (cudaFree waits for
+// the device), which happens during the first step only.
+constexpr size_t IMG_MAX_BYTES = (size_t)1 << 30;
+struct ImgScratch { uint8_t *p = nullptr; size_t bytes = 0; };
+uint8_t *img_scratch(cudaStream_t st, size_t need) {
   static std::mutex mu;
-  static std::unordered_map<uint64_t, uint8_t *> pool;
+  static std::unordered_map<uint64_t, ImgScratch> pool;
   int dev = 0;
   cudaGetDevice(&dev);
   const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(st) * 64u + (uint64_t)dev;
   std::lock_guard<std::mutex> lock(mu);
-  auto it = pool.find(key);
-  if (it != pool.end()) return it->second;
+  ImgScratch &sc = pool[key];
+  if (sc.bytes >= need) return sc.p;
+  if (sc.p != nullptr) { cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
+  const size_t want = (need + ((size_t)4 << 20) - 1) / ((size_t)4 << 20) * ((size_t)4 << 20);
   void *p = nullptr;
-  if (cudaMalloc(&p, BIMG_BYTES) != cudaSuccess) { cudaGetLastError(); p = nullptr; }    // no scratch: the GEMM stages B itself
-  pool[key] = static_cast<uint8_t *>(p);
-  return static_cast<uint8_t *>(p);
+  if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }      // no scratch: the GEMM stages its operands itself
+  sc.p = static_cast<uint8_t *>(p); sc.bytes = want;
+  return sc.p;
+}
+
+// 0: operands staged by the GEMM's own threads; 1: weight operand pre-imaged (GEMMs without split-K); 2 (default): both operands
+// pre-imaged whenever the scratch fits, weight-only otherwise
+int pre_mode() {
+  static const int m = getenv("GT_GEMM_PRE") ? atoi(getenv("GT_GEMM_PRE")) : 2;
+  return m;
 }
 
 template <int BN>
@@ -378,18 +446,28 @@ int launch(GemmTcArgs g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
     GT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  g.b_img = nullptr; g.nkb_img = 0;
+  g.b_img = nullptr; g.a_img = nullptr; g.nkb_img = 0;
   const int64_t nkb = (g.K + GBK - 1) / GBK;
-  const size_t need = (size_t)g.n_tiles * nkb * BN * GBK * 2;
+  const size_t need_b = (size_t)g.n_tiles * nkb * BN * GBK * 2, need_a = (size_t)m_tiles * nkb * GBM * GBK * 2;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
-  if (splits == 1 && m_tiles >= 16 && need <= BIMG_BYTES && cap == cudaStreamCaptureStatusNone) {
-    uint8_t *img = bimg_scratch(st);
+  const int mode = cap == cudaStreamCaptureStatusNone ? pre_mode() : 0;
+  const bool big = m_tiles * g.n_tiles * splits >= 32;            // small problems are launch-latency bound: no extra kernels
+  const bool all = mode >= 2 && big && nkb <= 65535 && need_a + need_b <= IMG_MAX_BYTES;
+  const bool only_b = !all && mode >= 1 && splits == 1 && m_tiles >= 16 && need_b <= ((size_t)4 << 20);
+  if (all || only_b) {
+    uint8_t *img = img_scratch(st, all ? need_a + need_b : need_b);
     if (img != nullptr) {
       { LaunchScope _ls(KC_GEMM_TC, st);
         gemm_tc_bimg_kernel<BN><<<dim3((unsigned)g.n_tiles, (unsigned)nkb), GTHREADS, 0, st>>>(g, img); }
       GT_CUDA(cudaGetLastError());
       g.b_img = img; g.nkb_img = (int)nkb;
+      if (all) {
+        { LaunchScope _ls(KC_GEMM_TC, st);
+          gemm_tc_aimg_kernel<<<dim3((unsigned)m_tiles, (unsigned)nkb), GTHREADS, 0, st>>>(g, img + need_b); }
+        GT_CUDA(cudaGetLastError());
+        g.a_img = img + need_b;
+      }
     }
   }
   dim3 grid((unsigned)(m_tiles * g.n_tiles), (unsigned)splits);
