@@ -21,3 +21,4 @@ for f in sorted(glob.glob("gpurun_out/final_*.json")):
     except Exception as e:
         print(f, "ERR", e)
 PY
+CUDA_DEVICE_MAX_CONNECTIONS=32 timeout 200 python tools/sweep_bench.py --members 1,8,32 --steps 120 --drive graph > gpurun_out/final_sweep_graph.jsonl 2> gpurun_out/final_sweep_graph.err; echo "sweep graph rc=$?"; cut -c1-330 gpurun_out/final_sweep_graph.jsonl
