@@ -276,6 +276,22 @@ class SweepMember:
                     self.epoch += 1
             self.steps += n_steps
 
+    def close(self) -> None:
+        """Releases the captured step (``gt_graph_destroy``) once the stream has drained; the member stays usable (the graph is
+        rebuilt on the next ``run_steps_graph``)."""
+        g = getattr(self, "_graph", None)
+        if g is not None:
+            from . import _lib
+            self._graph = None
+            self.stream.synchronize()
+            _lib.load().gt_graph_destroy(g["handle"])
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the driver reclaims the graph with the context
+            pass
+
     def history(self) -> torch.Tensor:
         """[steps, 6] host tensor of the per-step metrics (synchronises this member's stream)."""
         self.stream.synchronize()
