@@ -156,6 +156,25 @@ def test_grad_buckets_partition_the_flat_vector_in_backward_order():
     assert lib.gt_grad_bucket_wait(0, None) != 0 and b"not enabled" in lib.gt_last_error()
 
 
+def test_graph_entry_points_validate_their_arguments_before_any_launch():
+    """gt_graph_train_create / gt_graph_launch / gt_graph_destroy (include/groove_b200.h): argument errors come back as a
+    status + message, never as a launch — checked here without a GPU."""
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    assert lib.gt_graph_launch(None, 1, None) != 0 and b"gt_graph_launch" in lib.gt_last_error()
+    assert lib.gt_graph_destroy(None) == 0
+    handle = C.c_void_p()
+    fp32 = _lib.GtConfig(32, 4, 16, 1, 0, 16, 27, _lib.PREC_FP32, 0.1, 0)
+    # null buffers are refused first; a configuration off the fused d_model = 32 encoder-only path is refused by name
+    assert lib.gt_graph_train_create(C.byref(fp32), None, None, None, None, 4, 0.5, None, None, None, None, 0, 0, 0.1, None, None, 1,
+                                     None, None, None, None, None, 0, None, C.byref(handle)) != 0
+    assert b"null pointer" in lib.gt_last_error() and not handle.value
+    one = C.c_void_p(16)        # any non-null address: validation stops at the path check, nothing is dereferenced
+    assert lib.gt_graph_train_create(C.byref(fp32), one, one, one, one, 4, 0.5, one, one, one, one, 1 << 20, 0, 0.1, None, None, 1,
+                                     one, None, None, None, None, 0, None, C.byref(handle)) != 0
+    assert b"fused d_model = 32 encoder-only path" in lib.gt_last_error() and not handle.value
+
+
 def test_input_pipelines_refuse_a_cpu_device():
     from transformergrooveinfilling_b200.pipeline import DeviceResidentLoader, HostBatchPrefetcher
     with pytest.raises(RuntimeError):
