@@ -8,13 +8,19 @@
 // operands are rounded to bf16 on their way into shared memory and contracted by UMMA with an fp32 accumulator
 // in TMEM, i.e. exactly the arithmetic of the fused bf16 layer kernels.
 //
-// One CTA = one 128 x BN tile of C and one K range.  Per 64-deep K block all 256 threads load fp32 from global
-// (32-byte chunks, 8 rows x 4 chunks per warp so that the 16-byte st.shared of the packed chunk is conflict-free),
-// convert, and write the canonical no-swizzle core-matrix image; one thread issues the 4 UMMAs of the block and
-// commits them to the stage's mbarrier; two stages, so the loads of block i+1 overlap the MMAs of block i, and two
-// CTAs per SM overlap one CTA's epilogue with the other's main loop.  An operand whose contraction index is NOT the
-// contiguous one in memory (the data-gradient and weight-gradient forms) is staged as the image of its transpose
-// and consumed as an MN-major operand — no transposition in registers or shared memory.
+// One CTA = one 128 x BN tile of C and one K range; two CTAs per SM overlap one CTA's epilogue with the other's main loop.  Three
+// ways of getting the operands into the canonical no-swizzle core-matrix images UMMA reads (launch<BN>() picks; GT_GEMM_PRE):
+//   * both operands pre-imaged (default whenever the problem has >= 32 CTAs and the scratch fits): gemm_tc_aimg_kernel /
+//     gemm_tc_bimg_kernel convert A and B once per GEMM, at full occupancy and HBM speed, into contiguous 64-deep tile images;
+//     the main kernel's K loop is then two bulk-TMA copies and four UMMAs per block, issued by one thread, two stages deep;
+//   * weight operand pre-imaged only (scratch too small for A): B by bulk TMA, A staged by the CTA's threads as below;
+//   * in-kernel staging (small problems, stream capture): per 64-deep K block all 256 threads load fp32 from global (32-byte
+//     chunks, 8 rows x 4 chunks per warp so that the 16-byte st.shared of the packed chunk is conflict-free), convert and write
+//     the image; one thread issues the 4 UMMAs of the block and commits them to the stage's mbarrier.
+// An operand whose contraction index is NOT the contiguous one in memory (the data-gradient and weight-gradient forms) is
+// imaged as its transpose and consumed as an MN-major operand — no transposition in registers or shared memory.  The epilogue
+// drains TMEM per warp (lane = row), applies bias / ReLU / dropout, turns the chunk through shared memory and writes float4
+// row segments with the mask / residual / accumulate / atomic options applied per quad.
 #include "common.cuh"
 #include "umma.cuh"
 #include <mutex>
