@@ -140,7 +140,7 @@ def test_graph_replay_dropout_masks_follow_the_device_counter():
 
 def test_graph_members_packed_concurrently():
     x, y = _dataset(96)
-    cfgs = [dict(CONFIGS[1], batch_size=16), CONFIGS[0], CONFIGS[3]]      # the d_model = 256 member falls back to gt_train_steps
+    cfgs = [dict(CONFIGS[1], batch_size=16), CONFIGS[2], CONFIGS[3]]      # fused d_model = 32 | per-op d_model = 64 | d_model = 256 falls back to gt_train_steps
 
     def run(concurrent):
         torch.manual_seed(0)
@@ -154,3 +154,22 @@ def test_graph_members_packed_concurrently():
     for a, b in zip(packed, solo):
         np.testing.assert_allclose(a[0], b[0], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(a, b, rtol=3e-2, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_on_the_per_op_paths(precision):
+    """The per-op kernels (fp32 SIMT path; bf16 path with the contractions on the generic tcgen05 GEMM and mma.sync attention)
+    also derive their dropout keys from the device counter: with learning rate 0 a replayed run reproduces the eager losses."""
+    x, y = _dataset(96)
+    cfg = dict(CONFIGS[2], optimizer_algorithm="sgd", learning_rate=0.0, batch_size=16, dropout=0.3)      # d_model = 64, 2 heads of 32
+
+    def run(graph):
+        torch.manual_seed(0)
+        pk = SweepPacker([cfg], x, y, "cuda", precision=precision, seed=4)
+        assert pk.members[0].graph_capable()
+        pk.run(12, concurrent=False, graph=graph)
+        return pk.history()[0].numpy()
+
+    a, b = run(True), run(False)
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+    assert len({round(float(v), 6) for v in a[:, 0]}) > 6

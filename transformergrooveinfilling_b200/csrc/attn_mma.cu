@@ -102,6 +102,8 @@ constexpr int AM_WARPS = 4;
 
 template <int DH>
 __global__ void __launch_bounds__(AM_WARPS * 32) attn_mma_fwd_kernel(const AttnArgs a) {
+  Drop adrop = a.drop;
+  drop_resolve(adrop);                               // graph replay: key from the device step counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t pair = (int64_t)blockIdx.x * AM_WARPS + warp;
   if (pair >= a.n_seq * a.H) return;
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_mma_fwd_kernel(const AttnA
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     am_softmax(p[u], a.causal != 0, u, g, t);
-    const uint32_t keep = am_keep_bits(a.drop, w_pair, u, g, t);
-    const float ks = a.drop.scale;
+    const uint32_t keep = am_keep_bits(adrop, w_pair, u, g, t);
+    const float ks = adrop.scale;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_mma_fwd_kernel(const AttnA
 
 template <int DH>
 __global__ void __launch_bounds__(AM_WARPS * 32) attn_mma_bwd_kernel(const AttnArgs a) {
+  Drop adrop = a.drop;
+  drop_resolve(adrop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t pair = (int64_t)blockIdx.x * AM_WARPS + warp;
   if (pair >= a.n_seq * a.H) return;
@@ -176,11 +180,11 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_mma_bwd_kernel(const AttnA
     am_scores<DH>(Q, a.ldq, K, a.ldk, inv_sqrt_dh * 1.4426950408889634f, g, t, p);
     am_scores<DH>(dO, a.ld_do, V, a.ldv, 1.f, g, t, dp);
     const uint64_t w_pair = (uint64_t)((((a.seq0 + seq) * a.H + head) * T) * 8);
-    const float ks = a.drop.scale;
+    const float ks = adrop.scale;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       am_softmax(p[u], a.causal != 0, u, g, t);
-      const uint32_t keep = am_keep_bits(a.drop, w_pair, u, g, t);
+      const uint32_t keep = am_keep_bits(adrop, w_pair, u, g, t);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {

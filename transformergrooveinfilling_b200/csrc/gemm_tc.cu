@@ -304,6 +304,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
   // buffer (the operand stages are free: every MMA has retired) so that phase 2 runs with lane = column: every access to
   // C, the residual and the ReLU mask is a 128-byte row segment per warp instruction instead of 32 scattered 16-byte ones.
   const GemmEpi &e = g.e;
+  Drop edrop = g.e.drop;
+  drop_resolve(edrop);                                    // graph replay: key from the device step counter
   const int q = warp & 3;
   const int64_t mw0 = m0 + q * 32;                        // first row of this warp
   const bool first_split = blockIdx.y == 0;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (e.drop.thr && !e.pe && m < g.M) {
+      if (edrop.thr && !e.pe && m < g.M) {
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const int64_t n = nb + j4;
@@ -347,13 +349,13 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
           if (n + 4 <= g.N && (idx & 3) == 0) {             // the four elements are one quad of the site: one hash
             const uint64_t wq = idx >> 2;
             uint32_t lo, hi;
-            hash_quad((uint32_t)wq ^ ((uint32_t)(wq >> 32) * 0x85EBCA6Bu), e.drop.key, lo, hi);
+            hash_quad((uint32_t)wq ^ ((uint32_t)(wq >> 32) * 0x85EBCA6Bu), edrop.key, lo, hi);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j4 + j] = quad_keep(lo, hi, j, e.drop.thr) ? v[j4 + j] * e.drop.scale : 0.f;
+            for (int j = 0; j < 4; ++j) v[j4 + j] = quad_keep(lo, hi, j, edrop.thr) ? v[j4 + j] * edrop.scale : 0.f;
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (n + j < g.N) v[j4 + j] = drop_keep(e.drop.key, e.drop.thr, idx + j) ? v[j4 + j] * e.drop.scale : 0.f;
+              if (n + j < g.N) v[j4 + j] = drop_keep(edrop.key, edrop.thr, idx + j) ? v[j4 + j] * edrop.scale : 0.f;
           }
         }
       }
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
         float w = buf[i * BS + lane];
         if (e.pe) {
           w += __ldg(e.pe + (m % T) * g.N + n);
-          if (e.drop.thr) w = drop_keep(e.drop.key, e.drop.thr, (uint64_t)((e.drop_row0 + m) * g.N + n)) ? w * e.drop.scale : 0.f;
+          if (edrop.thr) w = drop_keep(edrop.key, edrop.thr, (uint64_t)((e.drop_row0 + m) * g.N + n)) ? w * edrop.scale : 0.f;
         }
         if (e.mask_pos) w = __ldg(e.mask_pos + m * e.ld_mask + n) > 0.f ? w * e.mask_scale : 0.f;
         if (e.residual) w += __ldg(e.residual + m * e.ld_res + n);

@@ -21,6 +21,7 @@ struct GemmArgs {
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
+  drop_resolve(g.e.drop);                            // graph replay: key from the device step counter
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -143,6 +144,7 @@ int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStr
 // Attention: one warp per (sequence, head); lane = query row (forward) / key row (dK,dV)
 // =============================================================================================
 __global__ void attention_fwd_kernel(AttnArgs a, int warps) {
+  drop_resolve(a.drop);
   extern __shared__ float sm[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t pair = (int64_t)blockIdx.x * warps + warp;
@@ -201,6 +203,7 @@ __global__ void attention_fwd_kernel(AttnArgs a, int warps) {
 }
 
 __global__ void attention_bwd_kernel(AttnArgs a, int warps) {
+  drop_resolve(a.drop);
   extern __shared__ float sm[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t pair = (int64_t)blockIdx.x * warps + warp;
@@ -319,6 +322,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void ln_fwd_kernel(const float *__restrict__ a, const float *__restrict__ res, const float *__restrict__ gamma,
                               const float *__restrict__ beta, float *u_out, float *y, float *mean, float *rstd,
                               int64_t M, int d, Drop drop, int64_t row0) {
+  drop_resolve(drop);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
   if (row >= M) return;
@@ -372,6 +376,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_vec4_kernel(const float *__restrict__ a, const float *__restrict__ res,
                                                           const float *__restrict__ gamma, const float *__restrict__ beta, float *u_out,
                                                           float *y, float *mean, float *rstd, int64_t M, Drop drop, int64_t row0) {
+  drop_resolve(drop);
   constexpr int d = NV * 128;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
@@ -413,6 +418,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_vec4_kernel(const float *__restrict__ dy, const float *__restrict__ u, const float *__restrict__ mean,
                                                           const float *__restrict__ rstd, const float *__restrict__ gamma, float *du, float *da,
                                                           float *dgamma, float *dbeta, int64_t M, Drop drop, int64_t row0, int rows_per_warp) {
+  drop_resolve(drop);
   constexpr int d = NV * 128;
   __shared__ float sm[2 * d];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
@@ -497,6 +503,7 @@ int ln_fwd(const float *a, const float *res, const float *gamma, const float *be
 __global__ void ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ u, const float *__restrict__ mean,
                               const float *__restrict__ rstd, const float *__restrict__ gamma, float *du, float *da,
                               float *dgamma, float *dbeta, int64_t M, int d, Drop drop, int64_t row0, int rows_per_warp) {
+  drop_resolve(drop);
   extern __shared__ float sm[];          // [2][d] block partials
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
@@ -577,6 +584,7 @@ int ln_bwd(const float *dy, const float *u, const float *mean, const float *rstd
 // =============================================================================================
 __global__ void pe_dropout_fwd_kernel(const float *__restrict__ r, const float *__restrict__ pe, float *x0, int64_t n,
                                       int d, Drop drop, int64_t e0) {
+  drop_resolve(drop);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = r[i] + pe[i % ((int64_t)T * d)];
@@ -593,6 +601,7 @@ int pe_dropout_fwd(const float *r, const float *pe, float *x0, int64_t M, int d,
 }
 __global__ void pe_dropout_bwd_kernel(const float *__restrict__ dx0, const float *__restrict__ r, float *g, int64_t n,
                                       Drop drop, int64_t e0) {
+  drop_resolve(drop);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = dx0[i];

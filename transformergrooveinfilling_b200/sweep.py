@@ -181,8 +181,9 @@ class SweepMember:
 
     # ---- CUDA-graph replay: one graph launch per optimizer step --------------------------------------------------------
     def graph_capable(self) -> bool:
-        """True when this member's step can be replayed as a CUDA graph (``gt_graph_train_create``): the fused d_model = 32
-        encoder-only path in bf16 mode with a fused optimizer."""
+        """True when this member's step can be replayed as a CUDA graph (``gt_graph_train_create``): an encoder-only model with
+        a fused optimizer on the fused d_model = 32 path, the per-op tcgen05 path or the fp32 path (the d_model = 256 fused
+        kernels do not read the device-resident dropout step yet)."""
         from . import _lib
         from .training import FusedAdam, FusedSGD
         import ctypes as C
@@ -190,8 +191,12 @@ class SweepMember:
         if not self.encoder_only or not isinstance(self.optimizer, (FusedSGD, FusedAdam)):
             return False
         cfg = m._cfg()
-        return (_lib.load().gt_path_kind(C.byref(cfg)) == 1 and m.embedding_size_src in (16, 27)
-                and getattr(m, "num_decoder_layers", 0) == 0)
+        if getattr(m, "num_decoder_layers", 0) != 0:
+            return False
+        kind = _lib.load().gt_path_kind(C.byref(cfg))
+        if kind == _lib.PATH_FUSED_D32:
+            return m.embedding_size_src in (16, 27)
+        return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC)
 
     def _graph_for(self, bsz: int):
         """The captured step for full batches of ``bsz`` rows (built once; rebuilt if lr / precision change)."""
@@ -236,7 +241,7 @@ class SweepMember:
         but every full batch is ONE ``cudaGraphLaunch`` (row gather + train step + optimizer + bookkeeping captured once by
         ``gt_graph_train_create``); the step counters, the row offset into the permutation and the metrics slot live in device
         memory and the graph advances them itself.  The ragged last batch of an epoch goes through ``gt_train_steps``.
-        Members that are not on the fused d_model = 32 path fall back to ``run_steps_fused``."""
+        Members whose path cannot be captured (``graph_capable``) fall back to ``run_steps_fused``."""
         import ctypes as C
         from . import _lib
         from .training import FusedAdam
