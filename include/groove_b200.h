@@ -219,6 +219,11 @@ int gt_debug_gemm(int tc, const float *a, int64_t sam, int64_t sak, const float 
                   float drop_p, uint64_t seed, uint64_t step, int32_t site, int64_t row0, int64_t split_k_chunk,
                   void *stream);
 
+/* Binds a caller-owned device buffer as the operand-image scratch of this thread's following gt_debug_gemm(tc != 0) calls
+ * (the model passes carve the same scratch out of their workspace: the library allocates no device memory).  NULL / 0 unbinds:
+ * the GEMM then stages its operands inside the main kernel. */
+int gt_debug_gemm_scratch(void *scratch, int64_t bytes);
+
 /* Micro-benchmark of the tensor pipe: n_mma back-to-back 128 x n x 16 bf16 UMMAs per SM from shared-memory
  * operands; out[0] (device float) = clocks per UMMA.  Used by tools/umma_rate.py. */
 int gt_debug_umma_rate(int n, int n_mma, int ksteps, float *out, void *stream);

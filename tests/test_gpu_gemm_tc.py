@@ -20,6 +20,9 @@ pytestmark = pytest.mark.gpu
 LOSS_RTOL = 2e-3
 
 
+_SCRATCH = None
+
+
 def _bf16r(t):
     return t.bfloat16().float()
 
@@ -28,6 +31,13 @@ def _gemm(tc, a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, flags=0, bias=None, res
           mask_scale=1.0, drop_p=0.0, row0=0, split=0):
     lib = _lib.load()
     p = lambda t: 0 if t is None else t.data_ptr()
+    if tc:
+        # the operand-image scratch is caller-owned (the model passes carve it out of their workspace); 256 MB covers every
+        # unit-test problem, so the pre-imaged bulk-TMA variants of the kernel are the ones exercised here
+        global _SCRATCH
+        if _SCRATCH is None:
+            _SCRATCH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.gt_debug_gemm_scratch(_SCRATCH.data_ptr(), _SCRATCH.numel()), "gt_debug_gemm_scratch")
     _lib.check(lib.gt_debug_gemm(tc, p(a), sam, sak, p(b), sbn, sbk, p(c), ldc, m, n, k, flags, p(bias), p(residual), ld_res,
                                  p(mask), ld_mask, mask_scale, drop_p, 5, 2, 77, row0, split, 0), "gt_debug_gemm")
     torch.cuda.synchronize()

@@ -232,3 +232,43 @@ def test_bench_flop_accounting_matches_survey():
     hits = y[..., :9]
     assert set(hits.unique().tolist()) <= {0.0, 1.0}
     assert float((y[..., 9:18] * (1 - hits)).abs().max()) == 0.0 and float(y[..., 18:].abs().max()) <= 0.5
+
+
+def test_deepcopy_and_pickle_keep_parameters_bound_to_the_flat_vector():
+    """copy.deepcopy (best-model snapshots, EMA) and pickling must give a model whose nn.Parameters are still views of the ONE
+    flat vector the kernels read (the default deepcopy detached them silently)."""
+    import copy
+    import pickle
+    from transformergrooveinfilling_b200 import GrooveTransformerEncoder
+    m = GrooveTransformerEncoder(32, 16, 27, 4, 16, 0.18, 2, 32, "cpu")
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert torch.equal(clone.flat_parameters().detach(), m.flat_parameters().detach())
+        assert clone.flat_parameters().data_ptr() != m.flat_parameters().data_ptr()
+        with torch.no_grad():
+            clone.OutputLayer.Linear.bias.fill_(2.0)                 # write through a parameter ...
+        assert float(clone.flat_parameters().detach()[-28:-1].sum()) == 54.0     # ... lands in the clone's flat vector
+        assert float(m.flat_parameters().detach()[-28:-1].abs().sum()) == 0.0      # ... and not in the original's
+        sd = m.state_dict()
+        sd["Encoder.Encoder.norm.weight"] = torch.full((32,), 0.5)
+        clone.load_state_dict(sd)
+        o, s = clone._offsets[[n for n, _ in clone._spec_list].index("Encoder.Encoder.norm.weight")]
+        assert torch.equal(clone.flat_parameters().detach()[o:o + s], torch.full((32,), 0.5))
+        assert [n for n, _ in clone.named_parameters()] == [n for n, _ in m.named_parameters()]
+
+
+def test_dropout_seed_follows_torch_seed():
+    from transformergrooveinfilling_b200 import GrooveTransformerEncoder
+    torch.manual_seed(123)
+    a = GrooveTransformerEncoder(32, 16, 27, 4, 16, 0.18, 1, 32, "cpu")
+    torch.manual_seed(124)
+    b = GrooveTransformerEncoder(32, 16, 27, 4, 16, 0.18, 1, 32, "cpu")
+    assert a._seed == 123 and b._seed == 124 and a._step == 0
+
+
+def test_calculate_loss_rejects_other_loss_functions():
+    from transformergrooveinfilling_b200 import calculate_loss
+    z = torch.zeros(2, 32, 9)
+    with pytest.raises(ValueError, match="BCEWithLogitsLoss"):
+        calculate_loss((z, z, z), torch.zeros(2, 32, 27), torch.nn.BCEWithLogitsLoss(), torch.nn.MSELoss(reduction="none"), 1.0)
+    with pytest.raises(ValueError, match="MSELoss"):
+        calculate_loss((z, z, z), torch.zeros(2, 32, 27), None, torch.nn.L1Loss(reduction="none"), 1.0)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gt_debug_dropout_mask": (C.c_int, [_u64, _u64, C.c_int32, _f, _i64, _i64, _p, _p]),
     "gt_debug_gemm": (C.c_int, [C.c_int, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _i64, _p, _i64,
                                 _f, _f, _u64, _u64, C.c_int32, _i64, _i64, _p]),
+    "gt_debug_gemm_scratch": (C.c_int, [_p, _i64]),
     "gt_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, _p]),
     "gt_debug_tc_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
 }

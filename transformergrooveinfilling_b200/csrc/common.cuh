@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/groove_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -49,6 +51,17 @@ struct LaunchScope {     // RAII: counts the launch; records start/stop events w
   LaunchScope(int cls, cudaStream_t st);
   ~LaunchScope();
 };
+
+// ---- NVTX ranges per phase (forward / loss / backward / optimizer ...): visible in nsys / ncu --nvtx timelines; a push / pop
+// without an attached tool is a null function-pointer check (SURVEY.md §5 "tracing").  GT_NVTX=0 disables them.
+bool nvtx_enabled();
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char *name) : on(nvtx_enabled()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+};
+#define GT_NVTX(name) gt::NvtxRange _gt_nvtx_##__LINE__(name)
 
 // ---- counter-based dropout generator (restated bit-exactly in oracle/groove_oracle.py) -----
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -185,6 +198,9 @@ bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64
 int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk,
             float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &epi,
             int64_t split_k_chunk, cudaStream_t st);
+// operand-image scratch of gemm_tc: caller-owned (a workspace region), bound to the calling thread for the duration of a pass
+void gemm_tc_bind_scratch(void *p, int64_t bytes);
+int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F);
 // out[n] += sum_m X[m*ld + n]
 int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStream_t st);
 

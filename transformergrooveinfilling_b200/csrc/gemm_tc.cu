@@ -23,8 +23,7 @@
 // row segments with the mask / residual / accumulate / atomic options applied per quad.
 #include "common.cuh"
 #include "umma.cuh"
-#include <mutex>
-#include <unordered_map>
+#include <algorithm>
 
 namespace gt {
 using namespace umma;
@@ -416,28 +415,15 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// scratch for the operand images: one buffer per (device, stream), grown on demand and kept for the life of the process — GEMMs
-// of one stream run in order, so the next pre-pass cannot overwrite images a previous main kernel still reads; different
-// streams (sweep members, each on its own host thread) never share a buffer.  Growing frees the old buffer (cudaFree waits for
-// the device), which happens during the first step only.
-constexpr size_t IMG_MAX_BYTES = (size_t)1 << 30;
-struct ImgScratch { uint8_t *p = nullptr; size_t bytes = 0; };
-uint8_t *img_scratch(cudaStream_t st, size_t need) {
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, ImgScratch> pool;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(st) * 64u + (uint64_t)dev;
-  std::lock_guard<std::mutex> lock(mu);
-  ImgScratch &sc = pool[key];
-  if (sc.bytes >= need) return sc.p;
-  if (sc.p != nullptr) { cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
-  const size_t want = (need + ((size_t)4 << 20) - 1) / ((size_t)4 << 20) * ((size_t)4 << 20);
-  void *p = nullptr;
-  if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }      // no scratch: the GEMM stages its operands itself
-  sc.p = static_cast<uint8_t *>(p); sc.bytes = want;
-  return sc.p;
-}
+// scratch for the operand images: CALLER-OWNED (include/groove_b200.h: the library keeps no device memory).  The pass drivers
+// carve it out of the workspace (runner.cu: Plan::gemm_img, sized by gemm_tc_scratch_bytes) and bind it to the calling thread
+// for the duration of the pass; GEMMs of one pass run in stream order, so the next pre-pass cannot overwrite images a previous
+// main kernel still reads, and two models never share a buffer (each has its own workspace).  Without a bound scratch — or when
+// a problem's images do not fit — the GEMM stages its operands itself.
+constexpr size_t IMG_MAX_BYTES = (size_t)4 << 30;
+thread_local uint8_t *g_img_scratch = nullptr;
+thread_local size_t g_img_scratch_bytes = 0;
+uint8_t *img_scratch(size_t need) { return (g_img_scratch != nullptr && need <= g_img_scratch_bytes) ? g_img_scratch : nullptr; }
 
 // 0: operands staged by the GEMM's own threads; 1: weight operand pre-imaged (GEMMs without split-K); 2 (default): both operands
 // pre-imaged whenever the scratch fits, weight-only otherwise
@@ -457,14 +443,12 @@ int launch(GemmTcArgs g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
   g.b_img = nullptr; g.a_img = nullptr; g.nkb_img = 0;
   const int64_t nkb = (g.K + GBK - 1) / GBK;
   const size_t need_b = (size_t)g.n_tiles * nkb * BN * GBK * 2, need_a = (size_t)m_tiles * nkb * GBM * GBK * 2;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cap);
-  const int mode = cap == cudaStreamCaptureStatusNone ? pre_mode() : 0;
+  const int mode = pre_mode();                                    // the scratch is a fixed workspace region: valid under stream capture too
   const bool big = m_tiles * g.n_tiles * splits >= 32;            // small problems are launch-latency bound: no extra kernels
-  const bool all = mode >= 2 && big && nkb <= 65535 && need_a + need_b <= IMG_MAX_BYTES;
+  const bool all = mode >= 2 && big && nkb <= 65535 && need_a + need_b <= IMG_MAX_BYTES && need_a + need_b <= g_img_scratch_bytes;
   const bool only_b = !all && mode >= 1 && splits == 1 && m_tiles >= 16 && need_b <= ((size_t)4 << 20);
   if (all || only_b) {
-    uint8_t *img = img_scratch(st, all ? need_a + need_b : need_b);
+    uint8_t *img = img_scratch(all ? need_a + need_b : need_b);
     if (img != nullptr) {
       { LaunchScope _ls(KC_GEMM_TC, st);
         gemm_tc_bimg_kernel<BN><<<dim3((unsigned)g.n_tiles, (unsigned)nkb), GTHREADS, 0, st>>>(g, img); }
@@ -486,6 +470,20 @@ int launch(GemmTcArgs g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
 }
 
 }  // namespace
+
+void gemm_tc_bind_scratch(void *p, int64_t bytes) {
+  g_img_scratch = static_cast<uint8_t *>(p);
+  g_img_scratch_bytes = p != nullptr && bytes > 0 ? (size_t)bytes : 0;
+}
+
+// upper bound of the operand images of any Linear forward / dgrad / wgrad GEMM of a model with these widths over `tokens` rows:
+// forward / dgrad: A = [tokens x K], B = [N x K]; wgrad: A = [N_w x tokens], B = [K_w x tokens] (both <= the widest layer dims)
+int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F) {
+  auto pad = [](int64_t v, int64_t m) { return (v + m - 1) / m * m; };
+  const int64_t wide = pad(std::max<int64_t>(3 * d, F), 256), narrow = pad(std::max<int64_t>(d, F), 256);
+  const int64_t need = 2 * pad(tokens, 128) * (wide + narrow) + ((int64_t)1 << 20);
+  return std::min<int64_t>(need, (int64_t)IMG_MAX_BYTES);
+}
 
 bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t M, int64_t N, int64_t K) {
   // one of the two indices of each operand must be contiguous; tiny contractions / outputs stay on the SIMT kernel

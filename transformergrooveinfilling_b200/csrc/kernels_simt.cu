@@ -731,6 +731,7 @@ int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metri
 }
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
                  float grad_scale, float *partials, cudaStream_t st) {
+  GT_NVTX("groove.loss");
   int64_t M = n_seq * T;
   GT_CHECK(M > 0, "empty batch");
   int64_t blocks = (M + LOSS_ROWS_PER_BLOCK - 1) / LOSS_ROWS_PER_BLOCK;
@@ -945,6 +946,7 @@ __global__ void sgd_kernel(float *p, const float *__restrict__ g, int64_t n, flo
   if (i < n) p[i] = p[i] - lr * (g[i] * gs);
 }
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st) {
+  GT_NVTX("groove.optimizer");
   if (n == 0) return 0;
   { LaunchScope _ls(KC_OPT, st);
   sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, lr, gs); }
@@ -971,6 +973,7 @@ __global__ void adam_kernel(float *p, const float *__restrict__ g, float *m, flo
 }
 int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps, int64_t step,
               float gs, cudaStream_t st, const unsigned long long *t_ptr) {
+  GT_NVTX("groove.optimizer");
   if (n == 0) return 0;
   GT_CHECK(step >= 1 || t_ptr != nullptr, "Adam step is 1-based");
   if (step < 1) step = 1;

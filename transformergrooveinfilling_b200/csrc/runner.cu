@@ -2,6 +2,7 @@
 // C ABI (include/groove_b200.h).  One C call = one whole pass (all layers), so Python pays one
 // ctypes call per forward / backward / fused train step.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -15,13 +16,19 @@ namespace gt {
 static thread_local std::string g_err;
 thread_local const unsigned long long *g_drop_step_ptr = nullptr;
 void set_error(const std::string &msg) { g_err = msg; }
+bool nvtx_enabled() {
+  static const bool on = !(getenv("GT_NVTX") && atoi(getenv("GT_NVTX")) == 0);
+  return on;
+}
 
 // ---- launch accounting ------------------------------------------------------------------------
 static int64_t g_launches[KC_MAX] = {0};
-static int g_prof_class = KC_NONE;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
-static std::vector<int> g_prof_cls;
-static size_t g_prof_used = 0;
+// Profiling brackets and gradient-bucket events belong to the host thread that enabled them: sweep members drive the library
+// from many host threads at once (sweep.py), and one thread's bench / data-parallel bookkeeping must not see another's launches.
+static thread_local int g_prof_class = KC_NONE;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static thread_local std::vector<int> g_prof_cls;
+static thread_local size_t g_prof_used = 0;
 
 LaunchScope::LaunchScope(int c, cudaStream_t s) : cls(c), st(s), slot(-1) {
   __atomic_fetch_add(&g_launches[c], 1, __ATOMIC_RELAXED);     // members of a sweep launch from several host threads
@@ -36,8 +43,8 @@ LaunchScope::~LaunchScope() {
 }
 
 // ---- gradient buckets ---------------------------------------------------------------------------
-static std::vector<cudaEvent_t> g_bucket_events;
-static bool g_bucket_events_on = false;
+static thread_local std::vector<cudaEvent_t> g_bucket_events;
+static thread_local bool g_bucket_events_on = false;
 
 int grad_bucket_count(const gt_config &c) { return c.n_dec > 0 ? c.n_enc + c.n_dec + 3 : c.n_enc + 2; }
 
@@ -148,6 +155,8 @@ struct Plan {
   uint8_t *enc_img;                  // hybrid encoder (fused d_model = 32 layer kernels inside an encoder-decoder model): weight images
   uint8_t *dec_img;                  // hybrid decoder: W1 / W2 images of the fused feed-forward blocks
   float *s_tok, *s_ya, *s_yb, *s_x1, *s_x2, *s_q, *s_ctx, *s_a, *s_hd, *s_z, *s_hvo;
+  uint8_t *gemm_img;                 // bf16 mode: operand images of the generic tcgen05 GEMM (gemm_tc.cu), caller-owned like everything else
+  int64_t gemm_img_bytes;
   int64_t bytes;
 };
 
@@ -221,6 +230,10 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     P.dh = take(M * F); P.dqkv = take(M * 3 * d); P.dctx = take(M * d); P.dlog = take(M * c.e_tgt);
     P.g0 = take(M * d);
     if (c.n_dec > 0) { P.dmem = take(M * d); P.dqc = take(M * d); P.dkvc = take(M * 2 * d); }
+  }
+  if (c.precision == GT_PREC_BF16 && !(hybrid && tc_dec_attn_supported(c))) {      // (every block fused: no generic GEMM of width >= 32 left)
+    P.gemm_img_bytes = gemm_tc_scratch_bytes(M, d, F);
+    P.gemm_img = reinterpret_cast<uint8_t *>(take((P.gemm_img_bytes + 3) / 4));
   }
   P.bytes = off;
 }
@@ -412,6 +425,7 @@ static int head_fwd(const Ctx &x, const float *z, float *hvo, float thres) {
 // y != nullptr (hybrid decoder with fused ends only): the tail also evaluates calculate_loss and leaves dL/dlogits in pl.dlog
 static int forward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, float *hvo, const float *y = nullptr,
                        float penalty = 0.f, float *metrics6 = nullptr) {
+  GT_NVTX("groove.forward");
   GT_TRY(encoder_fwd(x, pl, src));
   if (x.c.n_dec > 0) {
     GT_CHECK(tgt_in != nullptr, "encoder-decoder forward needs the shifted target");
@@ -522,6 +536,7 @@ static int input_layer_bwd(const Ctx &x, const Plan &pl, const float *dx0, const
 
 static int backward_all(const Ctx &x, const Plan &pl, const float *src, const float *tgt_in, const float *hvo,
                         const float *d_hvo) {
+  GT_NVTX("groove.backward");
   const int d = x.c.d_model, E = x.c.e_tgt;
   Drop none;
   const bool fused_dec_ends = x.c.n_dec > 0 && dec_fused_edges(x, pl);
@@ -678,6 +693,7 @@ static int check_ws(const gt_config *cfg, int64_t n_seq, int mode, void *ws, int
   GT_CHECK(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
   make_plan(*cfg, n_seq, mode, (char *)ws, pl);
   GT_CHECK(ws_bytes >= pl.bytes, "workspace too small: need " + std::to_string(pl.bytes) + " bytes, got " + std::to_string(ws_bytes));
+  gemm_tc_bind_scratch(pl.gemm_img, pl.gemm_img_bytes);      // this thread's GEMMs of the pass image their operands here
   return 0;
 }
 
@@ -730,6 +746,7 @@ int64_t gt_workspace_bytes(const gt_config *cfg, int64_t n_seq, int mode) {
 int gt_forward(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *tgt_in,
                int64_t n_seq, float *hvo, void *ws, int64_t ws_bytes, int train, uint64_t seed, uint64_t step,
                int64_t seq0, void *stream) {
+  GT_NVTX("gt_forward");
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, train != 0, seed, step, seq0, stream));
   GT_CHECK(src != nullptr && hvo != nullptr, "null src / hvo");
@@ -743,6 +760,7 @@ int gt_forward(const gt_config *cfg, const float *params, const float *pe, const
 int gt_backward(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *tgt_in,
                 int64_t n_seq, const float *hvo, const float *d_hvo, float *grads, void *ws, int64_t ws_bytes, uint64_t seed,
                 uint64_t step, int64_t seq0, void *stream) {
+  GT_NVTX("gt_backward");
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
   GT_CHECK(src != nullptr && hvo != nullptr && d_hvo != nullptr && grads != nullptr, "null src / hvo / d_hvo / grads");
@@ -777,6 +795,7 @@ int gt_eval_metrics(const float *pred_hvo, const float *gt_hvo, int64_t n_seq, i
 int gt_train_step(const gt_config *cfg, const float *params, const float *pe, const float *src, const float *y,
                   int64_t n_seq, float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws,
                   int64_t ws_bytes, uint64_t seed, uint64_t step, int64_t seq0, void *stream) {
+  GT_NVTX("gt_train_step");
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, grads, pe, n_seq, true, seed, step, seq0, stream));
   GT_CHECK(src && y && grads && metrics6 && hvo, "gt_train_step: null pointer");
@@ -893,6 +912,7 @@ int gt_predict(const gt_config *cfg, const float *params, const float *pe, const
 
 int gt_predict_variant(const gt_config *cfg, const float *params, const float *pe, const float *src, int64_t n_seq, float thres,
                        float *hvo_out, void *ws, int64_t ws_bytes, int variant, void *stream) {
+  GT_NVTX("gt_predict_variant");
   static thread_local Ctx x;
   GT_TRY(make_ctx(x, cfg, params, nullptr, pe, n_seq, false, 0, 0, 0, stream));
   GT_CHECK(src && hvo_out, "gt_predict: null pointer");
@@ -1019,6 +1039,11 @@ int gt_debug_gemm(int tc, const float *a, int64_t sam, int64_t sak, const float 
   if (thr) { e.drop.thr = thr; e.drop.key = site_key(seed, step, site); e.drop.scale = drop_scale(thr); e.drop_row0 = row0; }
   if (tc) return gemm_tc(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
   return gemm_f32(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
+}
+
+int gt_debug_gemm_scratch(void *scratch, int64_t bytes) {
+  gemm_tc_bind_scratch(scratch, bytes);
+  return 0;
 }
 
 int gt_debug_umma_rate(int n, int n_mma, int ksteps, float *out, void *stream) {

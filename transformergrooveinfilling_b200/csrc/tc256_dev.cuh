@@ -31,7 +31,14 @@ __device__ __forceinline__ float t256_colsum32(float (&v)[32], int lane) {
 
 #define T256_STAMP() do { if (dbg_on && ndbg < 60) a.dbg[ndbg++] = clock64(); } while (0)
 
-// optional clock64 timeline of CTA 0 (GT_T256_DBG=<number of launches to trace>)
+// optional clock64 timeline of CTA 0 (GT_T256_DBG=<number of launches to trace>).  Developer builds only (-DGT_T256_TIMELINE):
+// it allocates its own 4 KB device buffer, which the release library must not do (the caller owns all device memory).
+#ifndef GT_T256_TIMELINE
+struct T256Dbg {
+  bool arm(T256Args &, cudaStream_t) { return false; }
+  void report(const char *, cudaStream_t) {}
+};
+#else
 struct T256Dbg {
   unsigned long long *buf = nullptr;
   int left = getenv("GT_T256_DBG") ? atoi(getenv("GT_T256_DBG")) : 0;
@@ -56,6 +63,7 @@ struct T256Dbg {
     fprintf(stderr, "\n");
   }
 };
+#endif
 int t256_num_sms();
 
 }  // namespace gt

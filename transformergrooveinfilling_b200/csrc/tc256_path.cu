@@ -164,6 +164,7 @@ static int t256_prep(const T256Ctx &x, const T256Plan &pl) {
 // y != nullptr: the tail also evaluates calculate_loss (metrics6) and leaves dL/dlogits in pl.dlog (fused edges only)
 static int t256_forward_all(const T256Ctx &x, const T256Plan &pl, const float *src, float *hvo, bool save, float thres,
                             const float *y = nullptr, float penalty = 0.f, float *metrics6 = nullptr) {
+  GT_NVTX("groove.forward");
   const int d = x.c.d_model, L = x.c.n_enc;
   const bool fused = t256_fused_edges(x.c);
   GT_TRY(t256_prep(x, pl));
@@ -201,6 +202,7 @@ static int t256_wgrad_f32(const T256Ctx &x, const float *dY, int64_t N, const fl
 }
 
 static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *src, const float *hvo, const float *d_hvo) {
+  GT_NVTX("groove.backward");
   const int d = x.c.d_model, E = x.c.e_tgt, L = x.c.n_enc;
   const bool fused = t256_fused_edges(x.c);
   Drop none;

@@ -242,6 +242,7 @@ static int tc_prep(const TcCtx &x, const TcPlan &pl) {
 // y != nullptr: the tail also evaluates calculate_loss (metrics6) and leaves dL/dlogits in pl.dlog (fused edges only)
 static int tc_forward_all(const TcCtx &x, const TcPlan &pl, const float *src, float *hvo, bool save, float thres,
                           const float *y = nullptr, float penalty = 0.f, float *metrics6 = nullptr) {
+  GT_NVTX("groove.forward");
   const int d = x.c.d_model;
   const bool fused = tc_fused_edges(x.c);
   GT_TRY(tc_prep(x, pl));
@@ -282,6 +283,7 @@ static int tc_wgrad(const TcCtx &x, const float *dY, int64_t N, const float *X, 
 
 // hvo == nullptr: d_hvo already holds dL/dlogits (left by the fused tail + loss forward)
 static int tc_backward_all(const TcCtx &x, const TcPlan &pl, const float *src, const float *hvo, const float *d_hvo) {
+  GT_NVTX("groove.backward");
   const int d = x.c.d_model, E = x.c.e_tgt;
   const bool fused = tc_fused_edges(x.c);
   Drop none;

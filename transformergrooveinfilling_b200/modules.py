@@ -77,7 +77,11 @@ class _GrooveFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, src, tgt_in, flat):
-        hvo, ws, step = model._run_forward(src, tgt_in, train=model.training, save=True)
+        # eval() with grad enabled (fine-tuning a frozen-dropout model, saliency maps): the reference's nn.Dropout is the
+        # identity and autograd still works.  The library saves activations only in its training plan, so that case runs the
+        # training plan with p = 0 — the same arithmetic as the inference plan — and backward is told the same p.
+        ctx.train = bool(model.training)
+        hvo, ws, step = model._run_forward(src, tgt_in, train=ctx.train, save=True)
         ctx.model, ctx.ws, ctx.step = model, ws, step
         ctx.save_for_backward(src, tgt_in if tgt_in is not None else src.new_empty(0), hvo)
         ctx.has_tgt = tgt_in is not None
@@ -90,7 +94,7 @@ class _GrooveFn(torch.autograd.Function):
         g = torch.zeros_like(model._flat)
         lib = _lib.load()
         d_hvo = d_hvo.contiguous()
-        cfg = model._cfg(train=True)
+        cfg = model._cfg(dropout=None if ctx.train else 0.0)
         _lib.check(lib.gt_backward(C.byref(cfg), _lib.ptr(model._flat), _lib.ptr(model._pe_flat()), _lib.ptr(src),
                                    _lib.ptr(tgt_in) if ctx.has_tgt else 0, src.shape[0], _lib.ptr(hvo), _lib.ptr(d_hvo),
                                    _lib.ptr(g), _lib.ptr(ctx.ws), ctx.ws.numel(), model._seed, ctx.step, model._seq0,
@@ -111,7 +115,9 @@ class _GrooveBase(nn.Module):
             raise ValueError("embedding_size_tgt must be 27 (9 voices x hit/velocity/offset)")
         self._spec_list = _spec(d_model, dim_ff, e_src, e_tgt, n_enc, n_dec)
         self.precision = "fp32"
-        self._seed, self._step, self._seq0 = 0x5EED, 0, 0
+        # dropout stream: tied to torch's seed like the reference's nn.Dropout (torch.manual_seed before construction gives a
+        # reproducible run; independent processes draw independent masks); set_seed() overrides it
+        self._seed, self._step, self._seq0 = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF, 0, 0
         self._train_ws = None
 
         lib = _lib.load()
@@ -154,6 +160,7 @@ class _GrooveBase(nn.Module):
             self.InputLayerDecoder.PositionalEncoding.register_buffer("pe", pe.clone())
         object.__setattr__(self, "_flat", flat.requires_grad_(True))
         self._flat.register_post_accumulate_grad_hook(self._bind_grads)
+        self._train_ws = None
         self.reset_parameters()
         if device is not None and str(device) != "cpu":
             self.to(device)
@@ -196,26 +203,53 @@ class _GrooveBase(nn.Module):
         for p, (o, s) in zip(self._views, self._offsets):
             p.grad = g[o:o + s].view(p.shape)
 
-    def _apply(self, fn, recurse=True):
-        new = fn(self._flat.detach())
-        if new.dtype != torch.float32:
-            raise TypeError("groove_b200 keeps fp32 master parameters; precision is selected with set_precision()")
-        had_grad = self._flat.grad
-        flat = new.detach().requires_grad_(True)
+    def _rebind_views(self, flat_data: torch.Tensor, grad: torch.Tensor | None = None):
+        """Make ``flat_data`` THE flat vector: every nn.Parameter becomes a view of it again (after .to(), deepcopy, unpickling)."""
+        flat = flat_data.detach().requires_grad_(True)
         object.__setattr__(self, "_flat", flat)
         flat.register_post_accumulate_grad_hook(self._bind_grads)
         for p, (o, s) in zip(self._views, self._offsets):
             p.data = flat.detach()[o:o + s].view(p.shape)
             p.grad = None
-        if had_grad is not None:
-            flat.grad = fn(had_grad)
+        if grad is not None:
+            flat.grad = grad
             self._bind_grads(flat)
+        self._train_ws = None
+
+    def _apply(self, fn, recurse=True):
+        new = fn(self._flat.detach())
+        if new.dtype != torch.float32:
+            raise TypeError("groove_b200 keeps fp32 master parameters; precision is selected with set_precision()")
+        had_grad = self._flat.grad
+        self._rebind_views(new, fn(had_grad) if had_grad is not None else None)
         for m in self.modules():
             for k, b in m._buffers.items():
                 if b is not None:
                     m._buffers[k] = fn(b)
-        self._train_ws = None
         return self
+
+    # copy.deepcopy (best-model snapshots, EMA copies) and pickling: the default implementations would clone the flat vector and
+    # every Parameter separately, leaving the copy's parameters detached from the vector the kernels read.
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in ("_flat", "_train_ws"):
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        g = self._flat.grad
+        new._rebind_views(self._flat.detach().clone(), g.detach().clone() if g is not None else None)
+        return new
+
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items() if k not in ("_flat", "_train_ws")}
+        state["_flat_data"] = self._flat.detach()
+        return state
+
+    def __setstate__(self, state):
+        flat = state.pop("_flat_data")
+        self.__dict__.update(state)
+        self._rebind_views(flat)
 
     def flat_parameters(self) -> torch.Tensor:  # noqa: D401
         """The single fp32 vector every parameter is a view of (C layout: gt_param_layout)."""
@@ -243,12 +277,12 @@ class _GrooveBase(nn.Module):
         self._seed, self._step, self._seq0 = int(seed), int(step), int(seq0)
         return self
 
-    def _cfg(self, train=None):
+    def _cfg(self, dropout=None):
         n_dec = getattr(self, "num_decoder_layers", 0)
         return _lib.GtConfig(self.d_model, self.nhead, self.dim_feedforward, self.num_encoder_layers, n_dec,
                              self.embedding_size_src, self.embedding_size_tgt,
                              _lib.PREC_BF16 if getattr(self, "precision", "fp32") == "bf16" else _lib.PREC_FP32,
-                             float(self.dropout), 0)
+                             float(self.dropout if dropout is None else dropout), 0)
 
     def _check_input(self, x, e, what):
         if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != T_STEPS or x.shape[2] != e:
@@ -275,12 +309,13 @@ class _GrooveBase(nn.Module):
         n = src.shape[0]
         ws = self._workspace(n, 1 if (save or train) else 0, src.device)     # gt_forward(train=1) saves activations
         hvo = torch.empty(n, T_STEPS, self.embedding_size_tgt, dtype=torch.float32, device=src.device)
-        cfg = self._cfg()
+        # save without train (eval-mode autograd): the training plan (activations saved) with dropout switched off
+        cfg = self._cfg(dropout=0.0 if (save and not train) else None)
         step = self._step
         if train:
             self._step += 1
         _lib.check(lib.gt_forward(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._pe_flat()), _lib.ptr(src),
-                                  _lib.ptr(tgt_in), n, _lib.ptr(hvo), _lib.ptr(ws), ws.numel(), 1 if train else 0,
+                                  _lib.ptr(tgt_in), n, _lib.ptr(hvo), _lib.ptr(ws), ws.numel(), 1 if (train or save) else 0,
                                   self._seed, step, self._seq0, _lib.stream_ptr(src.device)), "gt_forward")
         return hvo, ws, step
 

@@ -57,7 +57,14 @@ def calculate_loss(prediction, y, bce_fn=None, mse_fn=None, hit_loss_penalty=1.0
     ``(total_loss 0-dim tensor with grad_fn, hit_accuracy, hit_perplexity, bce_hits, mse_velocities,
     mse_offsets)`` with the last five as Python floats.  ``bce_fn`` / ``mse_fn`` are accepted for
     signature compatibility (train.py:176-179 passes BCEWithLogitsLoss / MSELoss with reduction
-    'none'); the fused kernel implements exactly those two losses."""
+    'none'); the fused kernel implements exactly those two losses and any other callable is rejected."""
+    for fn, cls, what in ((bce_fn, torch.nn.BCEWithLogitsLoss, "bce_fn"), (mse_fn, torch.nn.MSELoss, "mse_fn")):
+        # the kernel IS BCEWithLogitsLoss / MSELoss with reduction 'none' and no weights; anything else would be silently
+        # replaced by them, so it is rejected (use the model's autograd path with your own loss function instead)
+        if fn is not None and not (isinstance(fn, cls) and fn.reduction == "none" and getattr(fn, "weight", None) is None
+                                   and getattr(fn, "pos_weight", None) is None):
+            raise ValueError(f"groove_b200 calculate_loss implements {cls.__name__}(reduction='none') for {what} "
+                             f"(train.py:176-179); got {fn!r}")
     hvo = _packed(prediction)
     if not hvo.is_cuda:
         raise RuntimeError("groove_b200 calculate_loss runs on CUDA only — there is no CPU fallback")
@@ -178,6 +185,9 @@ class FusedAdam(_FusedOptimizer):
                 self._t = int(float(e["step"]))
 
 
+DROPOUT_STATE_KEY = "groove_b200_dropout_state"
+
+
 # ----------------------------------------------------------------------------------------------
 # initialize_model  (BGT/models/train.py:43-108)
 # ----------------------------------------------------------------------------------------------
@@ -235,6 +245,9 @@ def initialize_model(params):
         model.load_state_dict(checkpoint["model_state_dict"])
         optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
         epoch = checkpoint["epoch"]
+        ds = checkpoint.get(DROPOUT_STATE_KEY)          # absent in reference checkpoints: a fresh stream, like the reference
+        if ds is not None:
+            model.set_seed(ds["seed"], ds["step"], model._seq0)
     return model, optimizer, epoch
 
 
@@ -307,8 +320,11 @@ def train_loop(dataloader, groove_transformer, loss_fn, bce_fn, mse_fn, opt, epo
         run_dir = wandb.run.dir if _wandb_active() else os.environ.get("GROOVE_CKPT_DIR", ".")
         run_id = wandb.run.id if _wandb_active() else "local"
         fn = os.path.join(run_dir, "transformer_run_{}_Epoch_{}.Model".format(run_id, epoch))
-        torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt.state_dict(),
-                    "loss": loss_value}, fn)
+        ckpt = {"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "loss": loss_value}
+        if isinstance(model, _GrooveBase):             # extra key the reference's loader ignores: resume continues the mask stream
+            ckpt[DROPOUT_STATE_KEY] = {"seed": model._seed, "step": model._step}
+        torch.save(ckpt, fn)
         if _wandb_active():
             wandb.save(fn, base_path=wandb.run.dir)
 
