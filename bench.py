@@ -34,14 +34,14 @@ def emit(line: dict) -> None:
 
 import torch  # noqa: E402
 
-# hyper-parameters verbatim from the reference yamls (C1..C5); `batch` is the per-GPU
-# synthetic batch used for throughput
+# hyper-parameters verbatim from the reference yamls (C1..C5); `batch` is the per-GPU synthetic batch used for
+# throughput, the sizes of SURVEY.md §8(d): 262 144 (C1), 65 536 (C2 / C5), 16 384 (C3 / C4)
 WORKLOADS = {
-    "c1": dict(yaml="InfillingClosedHH_testing_training.yaml", d=32, H=4, F=16, L=6, Ld=0, E=16, p=0.18, lr=0.094, pen=0.47, batch=65536),
-    "c2": dict(yaml="InfillingClosedHH_training.yaml", d=32, H=16, F=512, L=6, Ld=0, E=16, p=0.24, lr=0.07, pen=0.38, batch=32768),
-    "c3": dict(yaml="InfillingKicksAndSnares_training.yaml", d=256, H=2, F=512, L=6, Ld=0, E=16, p=0.30, lr=0.089, pen=0.73, batch=8192),
-    "c4": dict(yaml="InfillingRandom_test_large.yaml", d=256, H=16, F=64, L=11, Ld=0, E=16, p=0.15, lr=0.04, pen=1.0, batch=8192),
-    "c5": dict(yaml="InfillingClosedHH_Symbolic_training.yaml(encoder_only=0)", d=32, H=16, F=512, L=6, Ld=6, E=27, p=0.24, lr=0.07, pen=0.38, batch=16384),
+    "c1": dict(yaml="InfillingClosedHH_testing_training.yaml", d=32, H=4, F=16, L=6, Ld=0, E=16, p=0.18, lr=0.094, pen=0.47, batch=262144),
+    "c2": dict(yaml="InfillingClosedHH_training.yaml", d=32, H=16, F=512, L=6, Ld=0, E=16, p=0.24, lr=0.07, pen=0.38, batch=65536),
+    "c3": dict(yaml="InfillingKicksAndSnares_training.yaml", d=256, H=2, F=512, L=6, Ld=0, E=16, p=0.30, lr=0.089, pen=0.73, batch=16384),
+    "c4": dict(yaml="InfillingRandom_test_large.yaml", d=256, H=16, F=64, L=11, Ld=0, E=16, p=0.15, lr=0.04, pen=1.0, batch=16384),
+    "c5": dict(yaml="InfillingClosedHH_Symbolic_training.yaml(encoder_only=0)", d=32, H=16, F=512, L=6, Ld=6, E=27, p=0.24, lr=0.07, pen=0.38, batch=65536),
 }
 
 
@@ -113,41 +113,109 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_baseline(w, steps, warmup, batch, dropout):
-    """The oracle port (oracle/groove_oracle.py: the reference's arithmetic as plain torch-CPU tensor
-    ops + autograd, torch-native dropout like the reference's nn.Dropout) timed on this box's host
-    cores: forward + calculate_loss + backward + SGD update per step."""
+def reference_stepper(w, batch, dropout, optimizer, device):
+    """One training step of the reference, as a closure: the body of BGT/models/train.py:118-141 without wandb
+    (zero_grad -> forward -> calculate_loss -> backward -> opt.step()).
+
+    kind "reference": the UNMODIFIED reference modules from oracle/_ref (oracle/build_ref.py copies them there, git-ignored,
+    at build() time): GrooveTransformerEncoder / GrooveTransformer + calculate_loss + torch.optim.SGD / Adam exactly as
+    initialize_model builds them (BGT/models/train.py:43-66), nn.Dropout at the given p.
+    kind "port": oracle/groove_oracle.py (fused ATen ops, torch-native dropout) — only when oracle/_ref is absent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    ref, _why = ref_loader.load_reference()
+    x, y = synth_batch(w, batch, 1234)
+    x, y = x.to(device), y.to(device)
+    if ref is not None:
+        import importlib
+        tr = importlib.import_module(ref_loader.NAME + ".models.transformer")
+        torch.manual_seed(0)
+        if w["Ld"]:
+            model = tr.GrooveTransformer(w["d"], w["E"], 27, w["H"], w["F"], dropout, w["L"], w["Ld"], 32, device)
+        else:
+            model = tr.GrooveTransformerEncoder(w["d"], w["E"], 27, w["H"], w["F"], dropout, w["L"], 32, device)
+        model.to(device)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3) if optimizer == "adam" else torch.optim.SGD(model.parameters(), lr=w["lr"])
+        bce, mse = torch.nn.BCEWithLogitsLoss(reduction="none"), torch.nn.MSELoss(reduction="none")
+        y_s = torch.cat((torch.zeros_like(y[:, :1]), y[:, :-1]), dim=1) if w["Ld"] else None       # train.py:130-131
+
+        def step():
+            opt.zero_grad()
+            pred = model(x, y_s) if w["Ld"] else model(x)
+            loss = ref.calculate_loss(pred, y, bce, mse, w["pen"])[0]
+            loss.backward()
+            opt.step()
+            return loss
+        return step, "reference"
     import groove_oracle as G
-    torch.set_num_threads(os.cpu_count())
     G.FAST_BASELINE = True
     cfg = G.GrooveCfg(w["d"], w["H"], w["F"], w["L"], w["Ld"], w["E"], 27, dropout)
-    P = G.det_params(cfg)
-    x, y = synth_batch(w, batch, 1234)
+    state = {"P": {k: v.to(device) for k, v in G.det_params(cfg).items()}, "t": 0}
+    state["m"] = {k: torch.zeros_like(v) for k, v in state["P"].items()}
+    state["v"] = {k: torch.zeros_like(v) for k, v in state["P"].items()}
+
+    def step():
+        P = state["P"]
+        _, grads, _ = G.train_step_oracle(P, cfg, x, y, w["pen"], G.DropCtx(dropout, train=True, native=True))
+        if optimizer == "adam":
+            state["t"] += 1
+            for k in P:
+                P[k], state["m"][k], state["v"][k] = G.adam_step(P[k], grads[k], state["m"][k], state["v"][k], state["t"], 1e-3)
+        else:
+            state["P"] = {k: G.sgd_step(v, grads[k], w["lr"]) for k, v in P.items()}
+    return step, "port"
+
+
+def cpu_baseline(w, steps, warmup, batch, dropout, optimizer):
+    """The reference's own CPU implementation of the step, timed on this box's host cores (all of them)."""
+    torch.set_num_threads(os.cpu_count())
+    step, kind = reference_stepper(w, batch, dropout, optimizer, "cpu")
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, grads, _ = G.train_step_oracle(P, cfg, x, y, w["pen"], G.DropCtx(dropout, train=True, native=True))
-        P = {k: G.sgd_step(v, grads[k], w["lr"]) for k, v in P.items()}
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     tot = sum(times)
-    return batch * len(times) / tot, tot / len(times)
+    return batch * len(times) / tot, tot / len(times), kind
+
+
+def cuda_eager_baseline(w, steps, warmup, batch, dropout, optimizer, dev):
+    """SURVEY.md §2 / §8(d) "second baseline": the same reference code with device="cuda" (train.py:133) — PyTorch eager on this
+    B200, fp32 (TF32 off, torch defaults), timed with CUDA events.  calculate_loss's five .item() calls sync every step, as
+    they do in the reference."""
+    step, kind = reference_stepper(w, batch, dropout, optimizer, dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return batch * steps / (ms / 1e3), ms / steps, kind
 
 
 def run_reference(args, w):
+    """--impl reference: the reference's own CPU path on this box's host cores, same workload (model, dropout, optimizer);
+    each step is a bounded sample (batch 512 of the per-GPU batch the GPU arm runs) so that K + W steps end within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = 512 if args.steps + args.warmup <= 30 else 256
-    v, sec = cpu_baseline(w, args.steps, args.warmup, batch, w["p"])
+    v, sec, kind = cpu_baseline(w, args.steps, args.warmup, batch, w["p"], args.optimizer)
+    what = "unmodified reference from oracle/_ref (BGT/models/train.py:118-141 body)" if kind == "reference" else "oracle port (oracle/_ref absent)"
     line = {
         "impl": "reference", "metric": "train_seq_per_s", "value": v, "unit": "seq/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(w, args, batch, 1, "f32-cpu"),
-        "cpu_baseline": {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps of batch {batch} ({w['yaml']}, dropout {w['p']}, SGD), oracle port on host CPU"},
+        "cpu_baseline": {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{args.steps} steps of batch {batch} ({w['yaml']}, dropout {w['p']}, {args.optimizer}); {what}",
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": v, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,6 +303,72 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
         dist.destroy_process_group()
 
 
+def quick_infer(args, w, model, x, xh, n, timed):
+    """predict() on the headline workload: resident value + e2e through pipeline.HostPredictor (pinned host array in, pinned
+    [N, 32, 27] host array out, copies inside the timed region) — BGT/models/transformer.py:117-125, evaluator.py:171-175."""
+    from transformergrooveinfilling_b200 import HostPredictor
+    steps = max(3, min(args.steps, 10))
+    model.eval()
+    out_h = torch.empty(n, 32, 27, dtype=torch.float32).pin_memory()
+    hp = HostPredictor(model)
+
+    def resident():
+        with torch.no_grad():
+            model._predict_hvo(x, 0.5)
+
+    def e2e():
+        hp.predict(xh, out=out_h)
+
+    for _ in range(3):
+        resident()
+    ms = timed(resident, steps)
+    for _ in range(2):
+        e2e()
+    ms_e = timed(e2e, steps)
+    return {"metric": "infer_seq_per_s", "value": n * steps / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms / steps, "steps": steps,
+            "per_gpu_batch": n, "step_tflops": train_flops_per_seq(w) / 3 * n * steps / (ms / 1e3) / 1e12,
+            "e2e": {"value": n * steps / (ms_e / 1e3), "unit": "seq/s", "h2d_bytes_per_step": xh.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e / steps,
+                    "api": "HostPredictor.predict (H2D / gt_predict / D2H of neighbouring chunks on three streams)"}}
+
+
+def quick_train(args, name, dev, lib):
+    """Train value (resident inputs) of another BASELINE config on this GPU, in the same record: 3 warm-up + 6 timed steps."""
+    import ctypes as C
+    from transformergrooveinfilling_b200 import FusedAdam, FusedSGD, GrooveTransformer, GrooveTransformerEncoder, _lib
+    w = WORKLOADS[name]
+    n = w["batch"]
+    torch.manual_seed(0)
+    if w["Ld"]:
+        m = GrooveTransformer(w["d"], w["E"], 27, w["H"], w["F"], w["p"], w["L"], w["Ld"], 32, dev)
+    else:
+        m = GrooveTransformerEncoder(w["d"], w["E"], 27, w["H"], w["F"], w["p"], w["L"], 32, dev)
+    m.set_precision("bf16").set_seed(1234).train()
+    opt = FusedAdam(m, 1e-3) if args.optimizer == "adam" else FusedSGD(m, w["lr"])
+    xh, yh = synth_batch(w, n, 1234)
+    x, y = xh.to(dev), yh.to(dev)
+
+    def step():
+        m.train_step(x, y, w["pen"])
+        opt.step()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(6):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 6
+    kind = lib.gt_path_kind(C.byref(m._cfg()))
+    v = n / (ms / 1e3)
+    return {"metric": "train_seq_per_s", "workload": w["yaml"], "value": v, "unit": "seq/s", "ms_per_step": ms, "steps": 6,
+            "per_gpu_batch": n, "optimizer": args.optimizer, "precision": "bf16", "step_tflops": train_flops_per_seq(w) * v / 1e12,
+            "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[kind]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,6 +381,8 @@ def main():
     ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train step (headline) or predict()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-this-GPU run of the reference modules")
+    ap.add_argument("--no-extras", action="store_true", help="skip the infer / other-workload keys of the N = 1 line")
     ap.add_argument("--infer-chunk", type=int, default=0, help="--mode infer: sequences per chunk of the host-array predict pipeline (e2e); 0 = HostPredictor's default")
     ap.add_argument("--dp-bucket-mb", type=float, default=4.0, help="gradient bucket size of the overlapped all-reduce (N > 1)")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of per-bucket overlap")
@@ -422,7 +558,7 @@ def main():
         avg_ms = tot_ms.value / cnt.value
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = fl_launch / (avg_ms / 1e3) / 1e12
-        traffic, traffic_note = None, None
+        traffic, traffic_note, tr = None, None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
             if tr and precision == "bf16":
@@ -438,6 +574,13 @@ def main():
                 "avg_launch_ms": avg_ms, "launches_timed": cnt.value,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
                 "kernel_share_of_step": tot_ms.value / ms}
+        # what actually limits the kernel (ncu `--set full` capture summarised under profiles/; the contract's `bound` stays
+        # the roof `achieved` / `peak` are quoted on): neither roof binds the d_model = 32 kernels — CUDA-core issue does
+        if tr and precision == "bf16" and "limiter" in tr:
+            roof["limiter"] = tr["limiter"]
+            for k in ("issue_active", "tensor_pipe_active", "warp_insts_per_seq_layer", "source"):
+                if k in tr:
+                    roof["ncu_" + k if k != "source" else "ncu_source"] = tr[k]
     # ---- per-kernel-class breakdown: 3 extra steps with every class bracketed by events (outside the timed regions) ----
     kernels = {}
     names = {1: "gemm_f32", 2: "attention_fwd_f32", 3: "attention_bwd_f32", 4: "layernorm", 5: "elementwise", 6: "loss", 7: "optimizer",
@@ -478,12 +621,40 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss, "kernels": kernels,
         "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[path_kind],
     }
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the other halves of BASELINE.json's metric, in the same driver-run record: predict() throughput on this
+        # workload (resident + through HostPredictor with host buffers) and the train value of the other configs ----
+        del dp, opt, feeder
+        model._train_ws = None
+        torch.cuda.empty_cache()
+        line["infer"] = quick_infer(args, w, model, x, xh, n, timed)
+        del model, x, y
+        torch.cuda.empty_cache()
+        line["other_workloads"] = {}
+        for name in ("c3", "c4"):
+            if name != args.workload:
+                try:
+                    line["other_workloads"][name] = quick_train(args, name, dev, lib)
+                except Exception as e:  # noqa: BLE001 — an extra must never cost the headline line
+                    line["other_workloads"][name] = {"error": repr(e)[:200]}
+                torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            eb = min(n, 8192)
+            v, ms_e, kind = cuda_eager_baseline(w, 5, 3, eb, w["p"], args.optimizer, dev)
+            line["cuda_eager_baseline"] = {"value": v, "unit": "seq/s", "ms_per_step": ms_e, "kind": kind, "dtype": "f32",
+                                           "sample": f"5 steps of batch {eb}, same workload (dropout {w['p']}, {args.optimizer}); "
+                                                     "reference modules with device='cuda' (train.py:133), PyTorch eager on this GPU"}
+        except Exception as e:  # noqa: BLE001
+            line["cuda_eager_baseline"] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = 512
-        v, sec = cpu_baseline(w, 4, 1, cb, w["p"])
-        v0, _ = cpu_baseline(w, 6, 1, cb, 0.0)
-        line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"4 steps of batch {cb}, same workload (dropout {w['p']}, torch-native masks), SGD; oracle port on host CPU",
+        v, sec, kind = cpu_baseline(w, 4, 1, cb, w["p"], args.optimizer)
+        v0, _, _ = cpu_baseline(w, 6, 1, cb, 0.0, args.optimizer)
+        what = "unmodified reference from oracle/_ref (BGT/models/train.py:118-141 body)" if kind == "reference" else "oracle port (oracle/_ref absent)"
+        line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"4 steps of batch {cb}, same workload (dropout {w['p']}, {args.optimizer}); {what}",
                                 "value_dropout0": v0, "host_cpus": os.cpu_count()}
     if rank == 0:
         emit(line)

@@ -202,6 +202,12 @@ __global__ void attention_fwd_kernel(AttnArgs a, int warps) {
   }
 }
 
+// Backward.  The head's feature columns are processed in chunks of ATTN_BWD_CH (shared memory per warp is bounded by the
+// chunk, not by head_dim: d_model = 512 with one head — inside the reference's sweep ranges, configs/*_sweep.yaml — needs
+// 271 KB unchunked).  Pass 1 accumulates the scores and dP over the chunks in column order (the same order as the unchunked
+// loop, so results are bit-identical for head dims that fit one chunk); pass 2 re-stages each chunk of q | k | dO and emits
+// that chunk's columns of dq | dk | dv.
+constexpr int ATTN_BWD_CH = 128;
 __global__ void attention_bwd_kernel(AttnArgs a, int warps) {
   drop_resolve(a.drop);
   extern __shared__ float sm[];
@@ -210,28 +216,35 @@ __global__ void attention_bwd_kernel(AttnArgs a, int warps) {
   if (pair >= a.n_seq * a.H) return;
   const int64_t seq = pair / a.H;
   const int head = (int)(pair % a.H);
-  const int dh = a.dh, ls = dh + 1;
+  const int dh = a.dh, ch = dh < ATTN_BWD_CH ? dh : ATTN_BWD_CH, ls = ch + 1;
   const size_t per_warp = (size_t)4 * T * ls + 2 * T * (T + 1);
   float *Qs = sm + warp * per_warp, *Ks = Qs + T * ls, *Vs = Ks + T * ls, *Gs = Vs + T * ls;
   float *dSs = Gs + T * ls, *Ps = dSs + T * (T + 1);
-  for (int e = lane; e < T * dh; e += 32) {
-    int r = e / dh, c = e % dh;
-    int64_t row = seq * T + r;
-    Qs[r * ls + c] = a.q[row * a.ldq + head * dh + c];
-    Ks[r * ls + c] = a.k[row * a.ldk + head * dh + c];
-    Vs[r * ls + c] = a.v[row * a.ldv + head * dh + c];
-    Gs[r * ls + c] = a.d_o[row * a.ld_do + head * dh + c];
-  }
-  __syncwarp();
+  auto stage = [&](int c0, int cw, bool with_v) {
+    __syncwarp();
+    for (int e = lane; e < T * cw; e += 32) {
+      int r = e / cw, c = e % cw;
+      int64_t row = seq * T + r;
+      Qs[r * ls + c] = a.q[row * a.ldq + head * dh + c0 + c];
+      Ks[r * ls + c] = a.k[row * a.ldk + head * dh + c0 + c];
+      if (with_v) Vs[r * ls + c] = a.v[row * a.ldv + head * dh + c0 + c];
+      Gs[r * ls + c] = a.d_o[row * a.ld_do + head * dh + c0 + c];
+    }
+    __syncwarp();
+  };
   float s[T], dp[T];
 #pragma unroll
   for (int j = 0; j < T; ++j) { s[j] = 0.f; dp[j] = 0.f; }
-  for (int c = 0; c < dh; ++c) {
-    float qc = Qs[lane * ls + c], gc = Gs[lane * ls + c];
+  for (int c0 = 0; c0 < dh; c0 += ch) {
+    const int cw = dh - c0 < ch ? dh - c0 : ch;
+    stage(c0, cw, true);
+    for (int c = 0; c < cw; ++c) {
+      float qc = Qs[lane * ls + c], gc = Gs[lane * ls + c];
 #pragma unroll
-    for (int j = 0; j < T; ++j) {
-      s[j] = fmaf(qc, Ks[j * ls + c], s[j]);
-      dp[j] = fmaf(gc, Vs[j * ls + c], dp[j]);
+      for (int j = 0; j < T; ++j) {
+        s[j] = fmaf(qc, Ks[j * ls + c], s[j]);
+        dp[j] = fmaf(gc, Vs[j * ls + c], dp[j]);
+      }
     }
   }
   const float scale = rsqrtf((float)dh);
@@ -264,31 +277,35 @@ __global__ void attention_bwd_kernel(AttnArgs a, int warps) {
     dSs[lane * (T + 1) + j] = ds;
     dp[j] = ds;
   }
-  // dQ[i,c] = sum_j dS[i,j] K[j,c]
-  for (int c = 0; c < dh; ++c) {
-    float acc = 0.f;
+  for (int c0 = 0; c0 < dh; c0 += ch) {
+    const int cw = dh - c0 < ch ? dh - c0 : ch;
+    if (dh > ch) stage(c0, cw, false);     // single chunk: q | k | dO are still staged
+    // dQ[i,c] = sum_j dS[i,j] K[j,c]
+    for (int c = 0; c < cw; ++c) {
+      float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < T; ++j) acc = fmaf(dp[j], Ks[j * ls + c], acc);
-    a.dq[(seq * T + lane) * a.ld_dq + head * dh + c] = acc;
-  }
-  __syncwarp();
-  // lane = key row j: dK[j,c] = sum_i dS[i,j] Q[i,c] ; dV[j,c] = sum_i Pd[i,j] dO[i,c]
-  for (int c = 0; c < dh; ++c) {
-    float dk = 0.f, dv = 0.f;
-#pragma unroll
-    for (int i = 0; i < T; ++i) {
-      dk = fmaf(dSs[i * (T + 1) + lane], Qs[i * ls + c], dk);
-      dv = fmaf(Ps[i * (T + 1) + lane], Gs[i * ls + c], dv);
+      for (int j = 0; j < T; ++j) acc = fmaf(dp[j], Ks[j * ls + c], acc);
+      a.dq[(seq * T + lane) * a.ld_dq + head * dh + c0 + c] = acc;
     }
-    a.dk[(seq * T + lane) * a.ld_dk + head * dh + c] = dk;
-    a.dv[(seq * T + lane) * a.ld_dv + head * dh + c] = dv;
+    __syncwarp();
+    // lane = key row j: dK[j,c] = sum_i dS[i,j] Q[i,c] ; dV[j,c] = sum_i Pd[i,j] dO[i,c]
+    for (int c = 0; c < cw; ++c) {
+      float dk = 0.f, dv = 0.f;
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        dk = fmaf(dSs[i * (T + 1) + lane], Qs[i * ls + c], dk);
+        dv = fmaf(Ps[i * (T + 1) + lane], Gs[i * ls + c], dv);
+      }
+      a.dk[(seq * T + lane) * a.ld_dk + head * dh + c0 + c] = dk;
+      a.dv[(seq * T + lane) * a.ld_dv + head * dh + c0 + c] = dv;
+    }
   }
 }
 
 static int attn_launch(const AttnArgs &a, bool bwd, cudaStream_t st) {
   if (a.n_seq == 0) return 0;
-  const int ls = a.dh + 1;
-  size_t per_warp = bwd ? ((size_t)4 * T * ls + 2 * T * (T + 1)) * sizeof(float) : (size_t)3 * T * ls * sizeof(float);
+  const int ls = a.dh + 1, ls_b = (a.dh < ATTN_BWD_CH ? a.dh : ATTN_BWD_CH) + 1;
+  size_t per_warp = bwd ? ((size_t)4 * T * ls_b + 2 * T * (T + 1)) * sizeof(float) : (size_t)3 * T * ls * sizeof(float);
   int warps = 8;
   while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
   size_t smem = per_warp * warps;
