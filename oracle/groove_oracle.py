@@ -66,21 +66,25 @@ def site_key(seed: int, step: int, site: int) -> int:
     return k
 
 
+DROP_FIELD_ONE = 1 << 14      # csrc/common.cuh: a dropout decision is a 14-bit field compared with a 14-bit threshold
+
+
 def dropout_threshold(p: float) -> int:
-    """16-bit drop threshold: an element is KEPT iff its 16 random bits >= threshold."""
-    return int(min(65535, max(0, round(p * 65536.0))))
+    """14-bit drop threshold: an element is KEPT iff its 14-bit random field >= threshold."""
+    return int(min(DROP_FIELD_ONE - 1, max(0, round(p * float(DROP_FIELD_ONE)))))
 
 
 def hash_quad(v, key):
-    """64 random bits (lo, hi uint32 pairs held in uint64 arrays) per quad value ``v`` — csrc/common.cuh:hash_quad."""
+    """Four 14-bit fields (the low 14 bits of each 16-bit half of lo, hi; uint32 values held in uint64 arrays) per quad
+    value ``v`` — csrc/common.cuh:hash_quad."""
     x = _u32(_u32(v) * np.uint64(0x9E3779B1)) ^ np.uint64(key)
     x ^= x >> np.uint64(16)
     p = x * np.uint64(0x7FEB352D)
     plo, phi = _u32(p), p >> np.uint64(32)
     y = plo ^ phi
     q = y * np.uint64(0x846CA68B)
-    lo = _u32(q) ^ phi
-    hi = (q >> np.uint64(32)) ^ _u32((y << np.uint64(16)) | (y >> np.uint64(16)))
+    lo = (_u32(q) ^ phi) & np.uint64(0x3FFF3FFF)
+    hi = ((q >> np.uint64(32)) ^ _u32((y << np.uint64(16)) | (y >> np.uint64(16)))) & np.uint64(0x3FFF3FFF)
     return lo, hi
 
 
@@ -105,9 +109,9 @@ def key_perm(k):
 
 
 def dropout_scale(p: float) -> float:
-    """1/(1-p_eff) with p_eff the 16-bit quantised probability actually applied."""
+    """1/(1-p_eff) with p_eff the 14-bit quantised probability actually applied."""
     thr = dropout_threshold(p)
-    return 1.0 if thr == 0 else float(np.float32(65536.0 / (65536.0 - thr)))
+    return 1.0 if thr == 0 else float(np.float32(float(DROP_FIELD_ONE) / (float(DROP_FIELD_ONE) - thr)))
 
 
 def det_uniform(tag: int, n: int, lo: float, hi: float) -> np.ndarray:

@@ -18,7 +18,14 @@ comparisons tighten to fp32 re-ordering noise.  The rounding points were read of
   (tc_attn32.cuh, tc256.cu/_bwd.cu,      backward: dO -> bf16, dS/sqrt(dh) -> bf16 (dq), dS*ln2 -> bf16 against the
    attn_mma.cu)                          scaled q (fused kernels) or dS/sqrt(dh) against bf16(q) (per-op kernel)
   d_model = 32 fused path                residual stream, LayerNorm, input layer and head in fp32 (edge32.cu);
-                                         head dims outside {2, 4, 8}: attention in fp32 (SIMT)
+  (tc_layers.cu, tc_attn32.cuh)          head dims outside {2, 4, 8}: attention in fp32 (SIMT).  mma attention: the P V
+                                         contraction takes E = bf16(exp2(s - max)) with dropped keys zeroed, the row factor
+                                         1 / (rowsum (1 - p)) lands on the context; backward: c * dropped-P and c * dS as bf16
+                                         (c = 1/sqrt(dh)), dk from (c dS)^T against the scaled q.  FFN: b1 rides in the
+                                         contraction as bf16; H = bf16(relu(.)) with dropped units zeroed and NO 1 / (1 - p),
+                                         which multiplies the FFN2 accumulator instead (backward: the da2 image); dH is
+                                         rounded, then masked by H != 0; the linear1 / in-projection bias gradients are
+                                         column sums of the ROUNDED dH / dq | dk | dv images (taken on the tensor cores)
   d_model = 256 fused path               residual stream between layers and the saved pre-LayerNorm sums are bf16
                                          images: LayerNorm backward takes its statistics / x-hat from bf16(u);
                                          stem: dW_in | db_in = bf16(g)^T [bf16(src) | 1]; tail: dW_out, dgamma from
@@ -97,6 +104,86 @@ class _LinB(torch.autograd.Function):
 
 def lin_b(x, w, b):
     return _LinB.apply(x, w, b)
+
+
+class _LinBr(torch.autograd.Function):
+    """_LinB whose bias gradient is the column sum of the ROUNDED gradient image (fused d_model = 32 kernels: in-projection)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xb, wb = bf16(x), bf16(w)
+        ctx.save_for_backward(xb, wb)
+        return xb @ wb.T + b
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, wb = ctx.saved_tensors
+        gb = bf16(g)
+        g2 = gb.reshape(-1, gb.shape[-1])
+        return gb @ wb, g2.T @ xb.reshape(-1, xb.shape[-1]), g2.sum(0)
+
+
+class _FFN32(torch.autograd.Function):
+    """Feed-forward block of the fused d_model = 32 kernels (tc_layers.cu): see the module header."""
+
+    @staticmethod
+    def forward(ctx, x1, w1, b1, w2, b2, keep, fs):
+        x1b, w1b, w2b = bf16(x1), bf16(w1), bf16(w2)
+        h = bf16(torch.relu(x1b @ w1b.T + bf16(b1)))
+        if keep is not None:
+            h = h * keep
+        ctx.save_for_backward(x1b, w1b, w2b, h)
+        ctx.fs = fs
+        return (h @ w2b.T) * fs + b2
+
+    @staticmethod
+    def backward(ctx, g):
+        x1b, w1b, w2b, h = ctx.saved_tensors
+        d, f = w1b.shape[1], w1b.shape[0]
+        ga = bf16(g * ctx.fs)
+        dh = bf16(ga @ w2b) * (h != 0).to(g.dtype)
+        dh2, ga2 = dh.reshape(-1, f), ga.reshape(-1, d)
+        return (dh @ w1b, dh2.T @ x1b.reshape(-1, d), dh2.sum(0), ga2.T @ h.reshape(-1, f), g.reshape(-1, d).sum(0), None, None)
+
+
+class _AttnCore32(torch.autograd.Function):
+    """mma.sync attention of the fused d_model = 32 kernels (tc_attn32.cuh), heads laid out [N, H, T, dh]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, keep, scale, causal):
+        dh = q.shape[-1]
+        c = np.float32(1.0 / math.sqrt(dh)) * np.float32(LOG2E)
+        qs, kb, vb = bf16(q * float(c)), bf16(k), bf16(v)
+        s2 = qs @ kb.transpose(-1, -2)
+        if causal:
+            t = s2.shape[-1]
+            s2 = s2.masked_fill(torch.triu(torch.ones(t, t, dtype=torch.bool), diagonal=1), -1e30)
+        e = torch.exp2(s2 - s2.max(-1, keepdim=True).values)
+        inv = 1.0 / e.sum(-1, keepdim=True)
+        eb = bf16(e) if keep is None else bf16(e) * keep.to(e.dtype)
+        ctx.save_for_backward(qs, kb, vb, e, inv, keep if keep is not None else torch.empty(0))
+        ctx.scale, ctx.has_keep = scale, keep is not None
+        return bf16((eb @ vb) * (inv * scale))
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qs, kb, vb, e, inv, keep = ctx.saved_tensors
+        dh = qs.shape[-1]
+        c1, rc1 = float(np.float32(1.0 / math.sqrt(dh))), float(np.float32(math.sqrt(dh)))
+        dob = bf16(dctx)
+        dp = dob @ vb.transpose(-1, -2)
+        i = inv * c1
+        pd = e * (i * ctx.scale)
+        if ctx.has_keep:
+            pd = pd * keep.to(pd.dtype)
+        t = pd * dp
+        delta = t.sum(-1, keepdim=True)
+        dsq = bf16(t - e * (delta * rc1 * i))
+        pdb = bf16(pd)
+        dq = dsq @ kb
+        dk = (dsq.transpose(-1, -2) @ qs) * (LN2 * rc1)
+        dv = (pdb.transpose(-1, -2) @ dob) * rc1
+        return dq, dk, dv, None, None, None
 
 
 class _AttnCore(torch.autograd.Function):
@@ -236,7 +323,7 @@ def _keep_probs(drop: G.DropCtx, n, h, site):
 
 def _attn_variant(path, dh, causal_or_cross_block=False):
     if path == PATH_FUSED_D32:
-        return "f" if dh in (2, 4, 8) else "fp32"
+        return "g" if dh in (2, 4, 8) else "fp32"
     if path == PATH_FUSED_D256:
         return "f"
     return "p" if dh in (16, 32, 64, 128) else "fp32"
@@ -246,19 +333,23 @@ def mha_b(P, pre, xq, xkv, nhead, drop, site, path, causal=False):
     n, t, d = xq.shape
     dh = d // nhead
     w, b = P[pre + ".in_proj_weight"], P[pre + ".in_proj_bias"]
+    variant = _attn_variant(path, dh)
+    lin_in = _LinBr.apply if variant == "g" else lin_b
     if xq is xkv:
-        q, k, v = lin_b(xq, w, b).split(d, dim=-1)
+        q, k, v = lin_in(xq, w, b).split(d, dim=-1)
     else:
-        q = lin_b(xq, w[:d], b[:d])
-        k, v = lin_b(xkv, w[d:], b[d:]).split(d, dim=-1)
+        q = lin_in(xq, w[:d], b[:d])
+        k, v = lin_in(xkv, w[d:], b[d:]).split(d, dim=-1)
     split = lambda z: z.reshape(n, -1, nhead, dh).permute(0, 2, 1, 3)
     q, k, v = split(q), split(k), split(v)
-    variant = _attn_variant(path, dh)
     if variant == "fp32":
         s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
         if causal:
             s = s + torch.triu(torch.full((t, t), float("-inf"), dtype=s.dtype), diagonal=1)
         ctx = drop.probs(torch.softmax(s, dim=-1), site) @ v
+    elif variant == "g":
+        keep = _keep_probs(drop, n, nhead, site)
+        ctx = _AttnCore32.apply(q, k, v, keep, G.dropout_scale(drop.p) if drop.active() else 1.0, causal)
     else:
         keep = _keep_probs(drop, n, nhead, site)
         ctx = _AttnCore.apply(q, k, v, keep, G.dropout_scale(drop.p) if drop.active() else 1.0, causal, variant)
@@ -270,11 +361,23 @@ def _ln(path, u, g, b):
     return _LNq.apply(u, g, b) if path == PATH_FUSED_D256 else G.layer_norm(u, g, b)
 
 
+def _ffn(P, pre, x1, drop, site, path):
+    w1, b1, w2, b2 = P[pre + ".linear1.weight"], P[pre + ".linear1.bias"], P[pre + ".linear2.weight"], P[pre + ".linear2.bias"]
+    if path == PATH_FUSED_D32:
+        keep = None
+        if drop.active():
+            n, t, _ = x1.shape
+            idx = np.arange(n * t * w1.shape[0], dtype=np.uint64) + np.uint64(drop.seq0 * t * w1.shape[0])
+            keep = torch.from_numpy(G.dropout_keep(drop.seed, drop.step, site, idx, drop.p).reshape(n, t, w1.shape[0])).to(x1.dtype)
+        return _FFN32.apply(x1, w1, b1, w2, b2, keep, G.dropout_scale(drop.p) if drop.active() else 1.0)
+    h = drop.rows(torch.relu(lin_b(x1, w1, b1)), site)
+    return lin_b(h, w2, b2)
+
+
 def encoder_layer_b(P, pre, x, nhead, drop, li, path):
     a = mha_b(P, pre + ".self_attn", x, x, nhead, drop, G.site_id(0, li, 0), path)
     x1 = _ln(path, x + drop.rows(a, G.site_id(0, li, 1)), P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
-    h = drop.rows(torch.relu(lin_b(x1, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"])), G.site_id(0, li, 2))
-    f = lin_b(h, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"])
+    f = _ffn(P, pre, x1, drop, G.site_id(0, li, 2), path)
     out = _ln(path, x1 + drop.rows(f, G.site_id(0, li, 3)), P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
     return rb(out) if path == PATH_FUSED_D256 else out
 
@@ -284,8 +387,7 @@ def decoder_layer_b(P, pre, y, mem, nhead, drop, li, path):
     y = G.layer_norm(y + drop.rows(a, G.site_id(1, li, 1)), P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
     c = mha_b(P, pre + ".multihead_attn", y, mem, nhead, drop, G.site_id(1, li, 4), path)
     y = G.layer_norm(y + drop.rows(c, G.site_id(1, li, 5)), P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
-    h = drop.rows(torch.relu(lin_b(y, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"])), G.site_id(1, li, 2))
-    f = lin_b(h, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"])
+    f = _ffn(P, pre, y, drop, G.site_id(1, li, 2), path)
     return G.layer_norm(y + drop.rows(f, G.site_id(1, li, 3)), P[pre + ".norm3.weight"], P[pre + ".norm3.bias"])
 
 

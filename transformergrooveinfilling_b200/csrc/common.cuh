@@ -78,14 +78,19 @@ inline uint32_t site_key(uint64_t seed, uint64_t step, int32_t site) {
   k = mix32(k ^ ((uint32_t)site * 0xC2B2AE35u));
   return k;
 }
+// A dropout decision is a 14-BIT field compared with a 14-bit threshold: keep <=> field >= thr, thr = round(p * 16384)
+// (p quantised to 1 / 16384).  14 bits because two such fields sitting in the halves of a 32-bit word are then two
+// non-negative, finite fp16 bit patterns whose fp16 order is their integer order: the hot kernels decide both with ONE packed
+// half-precision compare (HSET2 -> 0xFFFF / 0 per half) and apply the result to a packed bf16 pair with one LOP3.
+constexpr uint32_t DROP_FIELD_BITS = 14, DROP_FIELD_ONE = 1u << DROP_FIELD_BITS, DROP_FIELD_MASK2 = 0x3FFF3FFFu;
 inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 65536.0;
+  double t = (double)p * (double)DROP_FIELD_ONE;
   long r = lrint(t);            // round-half-even like Python's round()
   if (r < 0) r = 0;
-  if (r > 65535) r = 65535;
+  if (r > (long)DROP_FIELD_ONE - 1) r = (long)DROP_FIELD_ONE - 1;
   return (uint32_t)r;
 }
-inline float drop_scale(uint32_t thr) { return thr == 0 ? 1.0f : (float)(65536.0 / (65536.0 - (double)thr)); }
+inline float drop_scale(uint32_t thr) { return thr == 0 ? 1.0f : (float)((double)DROP_FIELD_ONE / ((double)DROP_FIELD_ONE - (double)thr)); }
 
 struct Drop {           // one dropout site; thr == 0 means "inactive"
   uint32_t key = 0, thr = 0;
@@ -107,9 +112,10 @@ extern thread_local const unsigned long long *g_drop_step_ptr;
 inline void drop_fill_devstep(Drop &d, uint64_t seed, int site) {
   if (g_drop_step_ptr != nullptr) { d.k0 = site_key_seed(seed); d.site = (uint32_t)site; d.step_ptr = g_drop_step_ptr; }
 }
-// 64 random bits = four 16-bit dropout decisions for the QUAD of elements 4w .. 4w+3 of one site.  v = (uint32)w ^
-// ((uint32)(w >> 32) * 0x85EBCA6B).  One xorshift-multiply round, then two 32x32 -> 64 multiplies (IMAD.WIDE) whose
-// halves are cross-mixed: 12 instructions per four decisions.
+// Four 14-bit dropout fields (the low 14 bits of each 16-bit half of lo / hi) for the QUAD of elements 4w .. 4w+3 of one site.
+// v = (uint32)w ^ ((uint32)(w >> 32) * 0x85EBCA6B).  One xorshift-multiply round, then two 32x32 -> 64 multiplies (IMAD.WIDE)
+// whose halves are cross-mixed, then the field mask: 14 instructions per four decisions.  (Cheaper two-multiply variants were
+// measured and rejected: adjacent quads of a sequential index correlate at 0.2 - 0.6; this one stays below 0.003.)
 __host__ __device__ __forceinline__ void hash_quad(uint32_t v, uint32_t key, uint32_t &lo, uint32_t &hi) {
   uint32_t x = (v * 0x9E3779B1u) ^ key;
   x ^= x >> 16;
@@ -117,10 +123,10 @@ __host__ __device__ __forceinline__ void hash_quad(uint32_t v, uint32_t key, uin
   const uint32_t plo = (uint32_t)p, phi = (uint32_t)(p >> 32);
   const uint32_t y = plo ^ phi;
   const uint64_t q = (uint64_t)y * 0x846CA68Bu;
-  lo = (uint32_t)q ^ phi;
-  hi = (uint32_t)(q >> 32) ^ ((y << 16) | (y >> 16));
+  lo = ((uint32_t)q ^ phi) & DROP_FIELD_MASK2;
+  hi = ((uint32_t)(q >> 32) ^ ((y << 16) | (y >> 16))) & DROP_FIELD_MASK2;
 }
-// decision k (0..3) of a quad: 16-bit field k of (lo, hi) >= thr  <=> keep
+// decision k (0..3) of a quad: field k of (lo, hi) >= thr  <=> keep
 __host__ __device__ __forceinline__ bool quad_keep(uint32_t lo, uint32_t hi, int k, uint32_t thr) {
   const uint32_t word = (k & 2) ? hi : lo;
   return ((k & 1) ? (word >> 16) : (word & 0xFFFFu)) >= thr;

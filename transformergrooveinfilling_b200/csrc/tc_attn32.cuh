@@ -82,12 +82,15 @@ __device__ __forceinline__ void a32_softmax(float (&sacc)[2][4][4], float (&inv)
       sm[u][1] += __shfl_xor_sync(0xffffffffu, sm[u][1], o);
     }
 #pragma unroll
-  for (int u = 0; u < 2; ++u) { inv[u][0] = 1.f / sm[u][0]; inv[u][1] = 1.f / sm[u][1]; }
+  for (int u = 0; u < 2; ++u) { inv[u][0] = rcp_approx(sm[u][0]); inv[u][1] = rcp_approx(sm[u][1]); }
 }
 
 // ---- forward: ctx rows of one (sequence s, head h) pair -> bf16 K-major A image sCtx --------------------------
 // w_pair = quad index (element index >> 2) of (query row 0, position 0) of this pair at the attention dropout site
 // CAUSAL: key j of query i is masked for j > i (BGT/models/utils.py:53-56 get_tgt_mask; decoder self-attention)
+// The probabilities enter the P V contraction UNNORMALISED: E = bf16(exp2(s - max)) with the dropped keys zeroed by a packed
+// mask (umma.cuh: keep2), and the row factor 1 / (rowsum (1 - p)) is applied to the DH context values instead of the 32
+// probabilities:  ctx = bf16( (E_kept V) / (rowsum (1 - p)) ).
 template <int DH, bool CAUSAL = false>
 __device__ __forceinline__ void a32_attn_fwd(const uint8_t *sQ, const uint8_t *sK, const uint8_t *sV, uint8_t *sCtx, int s, int h, int lane,
                                              const Drop &dr, uint64_t w_pair) {
@@ -117,62 +120,59 @@ __device__ __forceinline__ void a32_attn_fwd(const uint8_t *sQ, const uint8_t *s
   }
   float inv[2][2];
   a32_softmax(sacc, inv);
+  const uint32_t thr2 = dr.thr | (dr.thr << 16);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const float i0 = inv[u][0] * dr.scale, i1 = inv[u][1] * dr.scale;
+    uint32_t pa[4][2];                                  // [key n-tile][row g / g + 8]: packed pairs (keys 8 nt + 2t, + 1)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      pa[nt][0] = pack_bf16(sacc[u][nt][0], sacc[u][nt][1]);
+      pa[nt][1] = pack_bf16(sacc[u][nt][2], sacc[u][nt][3]);
+    }
     if (dr.thr) {
       const int q0 = 16 * u + g;
       const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;            // rows q0 and q0 + 8
       const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
       const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
+      for (int np = 0; np < 2; ++np) {                  // quad 4 np + t of a row = this lane's keys of n-tiles 2 np, 2 np + 1 (common.cuh: key_perm)
         uint32_t la, ha, lb, hb;
         hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
         hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
-        sacc[u][2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np][0] * i0 : 0.f;
-        sacc[u][2 * np][1] = ((la >> 16) >= dr.thr) ? sacc[u][2 * np][1] * i0 : 0.f;
-        sacc[u][2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np + 1][0] * i0 : 0.f;
-        sacc[u][2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? sacc[u][2 * np + 1][1] * i0 : 0.f;
-        sacc[u][2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np][2] * i1 : 0.f;
-        sacc[u][2 * np][3] = ((lb >> 16) >= dr.thr) ? sacc[u][2 * np][3] * i1 : 0.f;
-        sacc[u][2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? sacc[u][2 * np + 1][2] * i1 : 0.f;
-        sacc[u][2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? sacc[u][2 * np + 1][3] * i1 : 0.f;
+        pa[2 * np][0] &= keep2(la, thr2); pa[2 * np + 1][0] &= keep2(ha, thr2);
+        pa[2 * np][1] &= keep2(lb, thr2); pa[2 * np + 1][1] &= keep2(hb, thr2);
       }
-    } else {
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) { sacc[u][nt][0] *= i0; sacc[u][nt][1] *= i0; sacc[u][nt][2] *= i1; sacc[u][nt][3] *= i1; }
     }
-  }
-  // O = P V : keys 16 kt .. 16 kt + 15 per k-step
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
+    // O = E V : keys 16 kt .. 16 kt + 15 per k-step
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int kt = 0; kt < 2; ++kt)
-      mma16816(o, pack_bf16(sacc[u][2 * kt][0], sacc[u][2 * kt][1]), pack_bf16(sacc[u][2 * kt][2], sacc[u][2 * kt][3]),
-               pack_bf16(sacc[u][2 * kt + 1][0], sacc[u][2 * kt + 1][1]), pack_bf16(sacc[u][2 * kt + 1][2], sacc[u][2 * kt + 1][3]),
-               bv[2 * kt], bv[2 * kt + 1]);
+    for (int kt = 0; kt < 2; ++kt) mma16816(o, pa[2 * kt][0], pa[2 * kt][1], pa[2 * kt + 1][0], pa[2 * kt + 1][1], bv[2 * kt], bv[2 * kt + 1]);
     if (own) {
+      const float i0 = inv[u][0] * dr.scale, i1 = inv[u][1] * dr.scale;
       const int r0 = s * 32 + 16 * u + g, col = blk * 8 + 2 * t;
-      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0, col, 128)) = pack_bf16(o[0], o[1]);
-      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0 + 8, col, 128)) = pack_bf16(o[2], o[3]);
+      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0, col, 128)) = pack_bf16(o[0] * i0, o[1] * i0);
+      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0 + 8, col, 128)) = pack_bf16(o[2] * i1, o[3] * i1);
     }
   }
 }
 
 // ---- backward of one (sequence s, head h) pair -------------------------------------------------------------------
 // sDO: dL/dctx rows.  Writes the recomputed ctx rows to sCtx (for dWo) and dq | dk | dv to the K-major image sDQ
-// [128 x 96] (columns [0,32) dq wrt the UNscaled q, [32,64) dk, [64,96) dv); adds the in-projection bias gradient
-// (column sums over the pair's 32 rows) to g_b[0..96).
+// [128 x 96] (columns [0,32) dq wrt the UNscaled q, [32,64) dk, [64,96) dv).  The in-projection bias gradient is the
+// column sum of that image, taken on the tensor cores by the caller (tc_layers.cu: colsum_image).
+// Arithmetic per probability (c = 1/sqrt(dh), ks = 1/(1-p), P = E / rowsum):
+//   p1 = P c ;  pd = keep ? p1 ks : 0  (= c x the dropped probability) ;  delta = sum_j pd dP / c  (= sum_j P dP_dropped)
+//   dS c = pd dP - p1 delta            -> bf16 -> dq = (dS c) K ,  dk = (dS c)^T Qs ln2 / c  (Qs = q log2(e) c, as staged)
+//   ctx  = (pd V) / c ,  dv = (pd^T dO) / c                        (the 1 / c lands on the DH-wide results, not on 32 probabilities)
 template <int DH, bool CAUSAL = false>
 __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *sK, const uint8_t *sV, const uint8_t *sDO, uint8_t *sCtx, uint8_t *sDQ,
-                                             int s, int h, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
+                                             int s, int h, int lane, const Drop &dr, uint64_t w_pair) {
   static_assert(DH == 2 || DH == 4 || DH == 8, "mma attention path: head dim 2, 4 or 8");
   const int g = lane >> 2, t = lane & 3;
   const int blk = (h * DH) >> 3, cin = (h * DH) & 7;
   const bool own = (unsigned)(2 * t - cin) < (unsigned)DH;
-  const float inv_sqrt_dh = rsqrtf((float)DH), ln2 = 0.6931471805599453f, ks = dr.scale;
+  const float c1 = rsqrtf((float)DH), rc1 = sqrtf((float)DH), ks = dr.scale;
+  const float dk_scale = 0.6931471805599453f * rc1;
   const uint32_t lrow = (uint32_t)(s * 32 + (lane & 7) + 8 * (lane >> 3)) * A32_ROWB + (uint32_t)blk * 16u;
   uint32_t bk[4], bv[4], bkt[4], bvt[4], bqt[4], bot[4];
   ldmatrix_x4(bk, sK + lrow);
@@ -181,7 +181,7 @@ __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *s
   ldmatrix_x4_trans(bvt, sV + lrow);
   ldmatrix_x4_trans(bqt, sQ + lrow);
   ldmatrix_x4_trans(bot, sDO + lrow);
-  float dk[2][4], dv[2][4], sq[2] = {0.f, 0.f};
+  float dk[2][4], dv[2][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -221,10 +221,10 @@ __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *s
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float i0 = 1.f / s0, i1 = 1.f / s1;
-    uint32_t keep = 0xFFFFu;                           // bit (4 nt + c)
+    const float i0 = rcp_approx(s0) * c1, i1 = rcp_approx(s1) * c1;
+    // pd = keep ? p1 ks : 0 in place of dp's partner: pdm[nt][c]
+    float pdm[4][4];
     if (dr.thr) {
-      keep = 0;
       const int q0 = 16 * mt + g;
       const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;
       const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
@@ -234,41 +234,36 @@ __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *s
         uint32_t la, ha, lb, hb;
         hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
         hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
-        keep |= ((la & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np);
-        keep |= ((la >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 1);
-        keep |= ((lb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 2);
-        keep |= ((lb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 3);
-        keep |= ((ha & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 4);
-        keep |= ((ha >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 5);
-        keep |= ((hb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 6);
-        keep |= ((hb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 7);
+        const float k0 = i0 * ks, k1 = i1 * ks;
+        pdm[2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? p[2 * np][0] * k0 : 0.f;
+        pdm[2 * np][1] = ((la >> 16) >= dr.thr) ? p[2 * np][1] * k0 : 0.f;
+        pdm[2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][0] * k0 : 0.f;
+        pdm[2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? p[2 * np + 1][1] * k0 : 0.f;
+        pdm[2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? p[2 * np][2] * k1 : 0.f;
+        pdm[2 * np][3] = ((lb >> 16) >= dr.thr) ? p[2 * np][3] * k1 : 0.f;
+        pdm[2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][2] * k1 : 0.f;
+        pdm[2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? p[2 * np + 1][3] * k1 : 0.f;
       }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { pdm[nt][0] = p[nt][0] * i0; pdm[nt][1] = p[nt][1] * i0; pdm[nt][2] = p[nt][2] * i1; pdm[nt][3] = p[nt][3] * i1; }
     }
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        p[nt][c] *= (c < 2 ? i0 : i1);
-        dp[nt][c] = ((keep >> (4 * nt + c)) & 1u) ? dp[nt][c] * ks : 0.f;
-      }
-      d0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
-      d1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+      dp[nt][0] *= pdm[nt][0]; dp[nt][1] *= pdm[nt][1]; dp[nt][2] *= pdm[nt][2]; dp[nt][3] *= pdm[nt][3];      // pd dP
+      d0 += dp[nt][0] + dp[nt][1];
+      d1 += dp[nt][2] + dp[nt][3];
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    uint32_t pdp[4][2], dsq[4][2], dsk[4][2];          // dropped P ; dS / sqrt(dh) (dq) ; dS * ln2 (dk: q is stored scaled by log2e / sqrt(dh))
+    const float e0 = -(d0 * rc1) * i0, e1 = -(d1 * rc1) * i1;          // - delta x (p1 / E)
+    uint32_t pdp[4][2], dsq[4][2];                      // c x dropped P ; c x dS
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      float ds[4], pd[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        ds[c] = p[nt][c] * (dp[nt][c] - (c < 2 ? d0 : d1));
-        pd[c] = ((keep >> (4 * nt + c)) & 1u) ? p[nt][c] * ks : 0.f;
-      }
-      pdp[nt][0] = pack_bf16(pd[0], pd[1]); pdp[nt][1] = pack_bf16(pd[2], pd[3]);
-      dsq[nt][0] = pack_bf16(ds[0] * inv_sqrt_dh, ds[1] * inv_sqrt_dh); dsq[nt][1] = pack_bf16(ds[2] * inv_sqrt_dh, ds[3] * inv_sqrt_dh);
-      dsk[nt][0] = pack_bf16(ds[0] * ln2, ds[1] * ln2); dsk[nt][1] = pack_bf16(ds[2] * ln2, ds[3] * ln2);
+      pdp[nt][0] = pack_bf16(pdm[nt][0], pdm[nt][1]); pdp[nt][1] = pack_bf16(pdm[nt][2], pdm[nt][3]);
+      dsq[nt][0] = pack_bf16(fmaf(p[nt][0], e0, dp[nt][0]), fmaf(p[nt][1], e0, dp[nt][1]));
+      dsq[nt][1] = pack_bf16(fmaf(p[nt][2], e1, dp[nt][2]), fmaf(p[nt][3], e1, dp[nt][3]));
     }
     float o[4] = {0.f, 0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -278,44 +273,29 @@ __device__ __forceinline__ void a32_attn_bwd(const uint8_t *sQ, const uint8_t *s
     }
 #pragma unroll
     for (int kmt = 0; kmt < 2; ++kmt) {                // dk / dv rows = keys 16 kmt .. ; contraction over this m-tile's 16 queries
-      const uint32_t s0t = movmatrix_trans(dsk[2 * kmt][0]), s1t = movmatrix_trans(dsk[2 * kmt + 1][0]);
-      const uint32_t s2t = movmatrix_trans(dsk[2 * kmt][1]), s3t = movmatrix_trans(dsk[2 * kmt + 1][1]);
+      const uint32_t s0t = movmatrix_trans(dsq[2 * kmt][0]), s1t = movmatrix_trans(dsq[2 * kmt + 1][0]);
+      const uint32_t s2t = movmatrix_trans(dsq[2 * kmt][1]), s3t = movmatrix_trans(dsq[2 * kmt + 1][1]);
       mma16816(dk[kmt], s0t, s1t, s2t, s3t, bqt[2 * mt], bqt[2 * mt + 1]);
       const uint32_t p0t = movmatrix_trans(pdp[2 * kmt][0]), p1t = movmatrix_trans(pdp[2 * kmt + 1][0]);
       const uint32_t p2t = movmatrix_trans(pdp[2 * kmt][1]), p3t = movmatrix_trans(pdp[2 * kmt + 1][1]);
       mma16816(dv[kmt], p0t, p1t, p2t, p3t, bot[2 * mt], bot[2 * mt + 1]);
     }
     if (own) {
-      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0, col, 128)) = pack_bf16(o[0], o[1]);
-      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0 + 8, col, 128)) = pack_bf16(o[2], o[3]);
+      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0, col, 128)) = pack_bf16(o[0] * rc1, o[1] * rc1);
+      *reinterpret_cast<uint32_t *>(sCtx + kmajor_off(r0 + 8, col, 128)) = pack_bf16(o[2] * rc1, o[3] * rc1);
       *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(r0, col, 128)) = pack_bf16(dq[0], dq[1]);
       *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(r0 + 8, col, 128)) = pack_bf16(dq[2], dq[3]);
     }
-    sq[0] += dq[0] + dq[2]; sq[1] += dq[1] + dq[3];
   }
   if (own) {
 #pragma unroll
     for (int kmt = 0; kmt < 2; ++kmt) {
       const int kr = s * 32 + 16 * kmt + g;
-      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr, 32 + col, 128)) = pack_bf16(dk[kmt][0], dk[kmt][1]);
-      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr + 8, 32 + col, 128)) = pack_bf16(dk[kmt][2], dk[kmt][3]);
-      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr, 64 + col, 128)) = pack_bf16(dv[kmt][0], dv[kmt][1]);
-      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr + 8, 64 + col, 128)) = pack_bf16(dv[kmt][2], dv[kmt][3]);
+      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr, 32 + col, 128)) = pack_bf16(dk[kmt][0] * dk_scale, dk[kmt][1] * dk_scale);
+      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr + 8, 32 + col, 128)) = pack_bf16(dk[kmt][2] * dk_scale, dk[kmt][3] * dk_scale);
+      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr, 64 + col, 128)) = pack_bf16(dv[kmt][0] * rc1, dv[kmt][1] * rc1);
+      *reinterpret_cast<uint32_t *>(sDQ + kmajor_off(kr + 8, 64 + col, 128)) = pack_bf16(dv[kmt][2] * rc1, dv[kmt][3] * rc1);
     }
-  }
-  // in-projection bias gradient: column sums over the pair's 32 rows (lanes with equal t hold the same columns)
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    float a = sq[j];
-    float b = dk[0][j] + dk[0][j + 2] + dk[1][j] + dk[1][j + 2];
-    float c = dv[0][j] + dv[0][j + 2] + dv[1][j] + dv[1][j + 2];
-#pragma unroll
-    for (int o = 4; o <= 16; o <<= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if (g == 0 && own) { atomicAdd(g_b + col + j, a); atomicAdd(g_b + 32 + col + j, b); atomicAdd(g_b + 64 + col + j, c); }
   }
 }
 

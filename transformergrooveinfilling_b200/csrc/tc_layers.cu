@@ -34,8 +34,9 @@ __global__ void tc_prep_kernel(TcPrepArgs a) {
   const TcImg o = tc_img(D, F);
   uint8_t *img = a.img + (size_t)l * a.img_stride;
   const int kb_d = D / 8, kb_f = F / 8;
-  const int n_qkv = 3 * D * kb_d, n_wo = D * kb_d, n_w1 = F * kb_d, n_w2 = D * kb_f;
-  const int total = n_qkv + n_wo + n_w1 + n_w2;
+  const int n_qkv = 3 * D * kb_d, n_wo = D * kb_d, n_w1 = F * kb_d, n_w2 = D * kb_f, n_b1 = F * (TC_KAUG / 8);
+  const int total = n_qkv + n_wo + n_w1 + n_w2 + n_b1;
+  const uint32_t w1_chunk = tc_w1_chunk_bytes(D, FC);
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
     int i = id;
     if (i < n_qkv) {
@@ -52,11 +53,18 @@ __global__ void tc_prep_kernel(TcPrepArgs a) {
     i -= n_wo;
     if (i < n_w1) {                     // W1 [F, D]: chunk c = rows c*FC.. -> image [FC x D]
       int gr = i / kb_d, kb = i % kb_d, c = gr / FC, r = gr % FC;
-      *reinterpret_cast<uint4 *>(img + o.w1 + (size_t)c * FC * D * 2 + kmajor_off(r, kb * 8, FC)) =
+      *reinterpret_cast<uint4 *>(img + o.w1 + (size_t)c * w1_chunk + kmajor_off(r, kb * 8, FC)) =
           pack8(a.params + a.w1[l] + (int64_t)gr * D + kb * 8);
       continue;
     }
     i -= n_w1;
+    if (i < n_b1) {                     // the TC_KAUG bias columns of every W1 chunk image: column D = bf16(b1), the rest 0
+      int gr = i / (TC_KAUG / 8), sl = i % (TC_KAUG / 8), c = gr / FC, r = gr % FC;
+      const uint32_t w0 = sl == 0 ? pack_bf16(a.params[a.b1[l] + gr], 0.f) : 0u;
+      *reinterpret_cast<uint4 *>(img + o.w1 + (size_t)c * w1_chunk + kmajor_off(r, D + sl * 8, FC)) = make_uint4(w0, 0u, 0u, 0u);
+      continue;
+    }
+    i -= n_b1;
     {                                   // W2 [D, F]: chunk c = columns c*FC.. -> image [D x FC]
       int j = i / kb_f, gk = (i % kb_f) * 8, c = gk / FC, kk = gk % FC;
       *reinterpret_cast<uint4 *>(img + o.w2 + (size_t)c * D * FC * 2 + kmajor_off(j, kk, D)) =
@@ -110,7 +118,7 @@ __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC, bool mma) {
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
   s.xa = al128(s.par + (uint32_t)(9 * D + F) * 4u);
-  s.q = al128(s.xa + 128u * D * 2u);                 // fp32 q rows, stride D+4 (16-byte aligned, conflict-free)
+  s.q = al128(s.xa + 128u * (D + TC_KAUG) * 2u);     // (xa: x image + the TC_KAUG ones / zero columns) ; q: fp32 rows, stride D+4
   if (mma) {
     s.k = s.q + A32_IMG;
     s.v = s.k + A32_IMG;
@@ -226,6 +234,56 @@ __device__ __forceinline__ void store_kv_row(float *dst, const float (&v)[D], in
   (void)H;
 }
 
+// The K columns [D, D + TC_KAUG) of an FFN-input A image: column D = 1.0 (multiplies the bias row of the W1 chunk images), rest 0.
+// Written once per kernel: the tile loop only rewrites columns [0, D).
+__device__ __forceinline__ void write_kaug_columns(uint8_t *img, int tid, int D) {
+  if (tid < 128 * (TC_KAUG / 8)) {
+    const int r = tid & 127, sl = tid >> 7;
+    *reinterpret_cast<uint4 *>(img + kmajor_off(r, D + sl * 8, 128)) = make_uint4(sl == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+  }
+}
+// FFN hidden epilogue of one 16-column block: the accumulator already holds x1 W1^T + b1 (TC_KAUG); ReLU is fused into the bf16
+// pack, the dropout decisions are packed compares ANDed onto the pairs.  The 1 / (1 - p) factor is NOT applied here: it is one
+// multiply per OUTPUT column of linear2 (forward: on the FFN2 accumulator; backward: folded into the da2 image).
+__device__ __forceinline__ void ffn_hidden_block(uint32_t taddr, uint8_t *dst_row /* image + kmajor_off(row, cb, 128) */, const Drop &d,
+                                                 uint32_t wlo, uint32_t xhi) {
+  float v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16_relu(v[2 * j], v[2 * j + 1]);
+  if (d.thr) {
+    const uint32_t thr2 = d.thr | (d.thr << 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t lo, hi;
+      hash_quad((wlo + (uint32_t)q) ^ xhi, d.key, lo, hi);
+      pk[2 * q] &= keep2(lo, thr2);
+      pk[2 * q + 1] &= keep2(hi, thr2);
+    }
+  }
+  *reinterpret_cast<uint4 *>(dst_row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4 *>(dst_row + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);      // next 8-column slab of a 128-row image
+}
+// Column sums over the 128 token rows of `nslab` 8-column slabs of a K-major [128 x 8 nslab] bf16 image, on the tensor cores:
+// warp w takes slabs w, w + 16, ...; per slab 8 x mma.m16n8k16 with an all-ones A operand (the B fragments come straight
+// from ldmatrix.trans), fp32 sums land in lanes 0..3 and are added to dst[8 slab + ...] (shared-memory partials).
+__device__ __forceinline__ void colsum_image(const uint8_t *img, int nslab, float *dst, int warp, int lane, int nwarps) {
+  const uint32_t ones = 0x3F803F80u;
+  for (int sl = warp; sl < nslab; sl += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, img + (uint32_t)sl * 2048u + (uint32_t)(32 * kq + (lane & 7) + 8 * (lane >> 3)) * 16u);
+      mma16816(acc, ones, ones, ones, ones, b[0], b[1]);
+      mma16816(acc, ones, ones, ones, ones, b[2], b[3]);
+    }
+    if (lane < 4) { atomicAdd(dst + sl * 8 + 2 * lane, acc[0]); atomicAdd(dst + sl * 8 + 2 * lane + 1, acc[1]); }
+  }
+}
+
 // =============================================================================================
 // forward: x_in -> QKV (UMMA) -> attention (SIMT) -> out-proj (UMMA) -> +res, LN1 -> FFN1 (UMMA,
 // chunked) -> relu/dropout -> FFN2 (UMMA, accumulating in TMEM) -> +res, LN2 -> x_out
@@ -265,7 +323,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
-  const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
+  const int F = a.F, FC = a.FC, H = DH > 0 ? D / DH : a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   constexpr bool MMA = attn_mma(DH);
   constexpr bool ATTN_ONLY = MODE >= TC_MODE_ATTN_CAUSAL, CAUSAL = MODE == TC_MODE_ATTN_CAUSAL, CROSS = MODE == TC_MODE_ATTN_CROSS;
   static_assert(!ATTN_ONLY || MMA, "attention-only blocks use the mma.sync attention path");
@@ -287,8 +345,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
   if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
-  if constexpr (!ATTN_ONLY)
-    for (int i = tid; i < F; i += FWD_THREADS) p_b1[i] = a.b1[i];
+  if constexpr (!ATTN_ONLY) write_kaug_columns(sXa, tid, D);      // linear1's bias rides in the contraction (tc_layers.cuh: TC_KAUG)
+  (void)p_b1;
   if (tid < D) {
     if constexpr (MODE != TC_MODE_FFN) { p_bo[tid] = a.bo[tid]; p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
     if constexpr (!ATTN_ONLY) { p_b2[tid] = a.b2[tid]; p_g2[tid] = a.g2[tid]; p_be2[tid] = a.be2[tid]; }
@@ -487,10 +545,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     if constexpr (ATTN_ONLY) continue;
     // ---- P6: FFN, hidden dimension in chunks of FC; FFN2 accumulates in TMEM across chunks ----
     const uint32_t idesc1 = make_idesc_bf16(128, FC), idesc2 = make_idesc_bf16(128, D);
+    const uint32_t w1_chunk = tc_w1_chunk_bytes(D, FC);
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1, FC, k), idesc1, k > 0);
+      for (int k = 0; k < (D + TC_KAUG) / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1, FC, k), idesc1, k > 0);
       mma_commit(&bar_mma);
     }
     const int nblk = FC / 16;                          // 16-column blocks of the chunk, dealt round-robin to the 4 parts
@@ -501,29 +560,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
         const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 2;        // multiple of 4 (F, FC multiples of 16)
         for (int b = part; b < nblk; b += 4) {
           const int cb = b * 16;
-          const uint64_t wb = w0 + (uint64_t)(cb >> 2);                                 // + (0..3) below never carries
-          const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
-          float v[16];
-          tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
-            float h2 = fmaxf(v[j + 2] + p_b1[c * FC + cb + j + 2], 0.f), h3 = fmaxf(v[j + 3] + p_b1[c * FC + cb + j + 3], 0.f);
-            if (a.d_ffn.thr) {
-              uint32_t lo, hi;
-              hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
-              h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-              h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
-              h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
-              h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
-            }
-            pk[j >> 1] = pack_bf16(h0, h1);
-            pk[(j >> 1) + 1] = pack_bf16(h2, h3);
-          }
-          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4 *>(sH + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          const uint64_t wb = w0 + (uint64_t)(cb >> 2);                                 // + (0..3) never carries
+          ffn_hidden_block(t_big + lane_off + (uint32_t)cb, sH + kmajor_off(row, cb, 128), a.d_ffn, (uint32_t)wb,
+                           (uint32_t)(wb >> 32) * 0x85EBCA6Bu);
         }
       }
       fence_async_smem();
@@ -535,8 +574,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
           mma_bf16_ss(t_small, desc_a128(aH, k), desc_b(aW + io.w2 + (uint32_t)c * D * FC * 2u, D, k), idesc2, (c | k) > 0);
         if (c + 1 < nchunk) {
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)
-            mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), idesc1, k > 0);
+          for (int k = 0; k < (D + TC_KAUG) / 16; ++k)
+            mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * w1_chunk, FC, k), idesc1, k > 0);
         }
         mma_commit(&bar_mma);
       }
@@ -550,15 +589,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, f + cb);
       tmem_ld_wait();
       const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      const float fs = a.d_ffn.scale;                  // 1 / (1 - p) of the hidden dropout: applied here, once per output column
       float s1 = 0.f;
 #pragma unroll
       for (int c = 0; c < D; c += 4) {
         float m0, m1, m2, m3;
         drop4(a.d2, e0 + c, m0, m1, m2, m3);
-        f[c] = x1[c] + (f[c] + p_b2[c]) * m0;
-        f[c + 1] = x1[c + 1] + (f[c + 1] + p_b2[c + 1]) * m1;
-        f[c + 2] = x1[c + 2] + (f[c + 2] + p_b2[c + 2]) * m2;
-        f[c + 3] = x1[c + 3] + (f[c + 3] + p_b2[c + 3]) * m3;
+        f[c] = x1[c] + fmaf(f[c], fs, p_b2[c]) * m0;
+        f[c + 1] = x1[c + 1] + fmaf(f[c + 1], fs, p_b2[c + 1]) * m1;
+        f[c + 2] = x1[c + 2] + fmaf(f[c + 2], fs, p_b2[c + 2]) * m2;
+        f[c + 3] = x1[c + 3] + fmaf(f[c + 3], fs, p_b2[c + 3]) * m3;
         s1 += (f[c] + f[c + 1]) + (f[c + 2] + f[c + 3]);
       }
       if (a.u2 && valid) {
@@ -657,10 +697,9 @@ __host__ __device__ inline BwdSmem bwd_smem(int D, int F, bool mma) {
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
   s.gpar = al128(s.par + (uint32_t)(9 * D + F) * 4u);
-  s.stat = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);   // per-row (mean1, rstd1)
-  s.xin = al128(s.stat + 2u * 128u * 4u * 16u);         // two ping-pong buffers of [128 rows][4 parts] float4
+  s.xin = al128(s.gpar + (uint32_t)(9 * D + F) * 4u);
   s.x1 = s.xin + 128u * D * 2u;
-  s.da = s.x1 + 128u * D * 2u;
+  s.da = s.x1 + 128u * (D + TC_KAUG) * 2u;            // (x1 image + the TC_KAUG ones / zero columns of the H recompute)
   s.ctx = s.da + 128u * D * 2u;
   s.dq = s.ctx + 128u * D * 2u;                       // dqkv image [128 x 3D]; M-padded reads run into the union below
   uint32_t u = al128(s.dq + 128u * 3u * D * 2u);
@@ -680,6 +719,10 @@ __host__ __device__ inline BwdSmem bwd_smem(int D, int F, bool mma) {
   s.h = u;                                            // FFN phase (aliases the attention scratch): H and dH images
   s.dh = s.h + 128u * 128u * 2u;
   uint32_t end_ffn = s.dh + 128u * 128u * 2u;
+  // row-statistics exchange of the two LayerNorm-backward phases (two ping-pong buffers of [128 rows][4 parts] float4 = 16 KB):
+  // aliases the dH image, which is dead in both (B0: start of a tile ; B2: every FFN MMA of the tile has retired, the attention
+  // images that share this range are written after B2's closing barrier)
+  s.stat = s.dh;
   s.total = end_attn > end_ffn ? end_attn : end_ffn;
   return s;
 }
@@ -721,7 +764,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
-  const int F = a.F, FC = a.FC, H = a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
+  const int F = a.F, FC = a.FC, H = DH > 0 ? D / DH : a.H, dh = DH > 0 ? DH : a.dh, nchunk = F / FC;
   constexpr bool MMA = attn_mma(DH);
   constexpr bool ATTN_ONLY = MODE >= TC_MODE_ATTN_CAUSAL, CAUSAL = MODE == TC_MODE_ATTN_CAUSAL, CROSS = MODE == TC_MODE_ATTN_CROSS;
   static_assert(!ATTN_ONLY || MMA, "attention-only blocks use the mma.sync attention path");
@@ -758,8 +801,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   for (int i = tid; i < 9 * D + F; i += BWD_THREADS) sG[i] = 0.f;
   if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += BWD_THREADS) p_bqkv[i] = a.bqkv[i];
-  if constexpr (!ATTN_ONLY)
-    for (int i = tid; i < F; i += BWD_THREADS) p_b1[i] = a.b1[i];
+  if constexpr (!ATTN_ONLY) write_kaug_columns(sX1, tid, D);      // linear1's bias rides in the H recompute (tc_layers.cuh: TC_KAUG)
+  (void)p_b1;
   if (tid < D) {
     if constexpr (MODE != TC_MODE_FFN) { p_g1[tid] = a.g1[tid]; p_be1[tid] = a.be1[tid]; }
     if constexpr (!ATTN_ONLY) p_g2[tid] = a.g2[tid];
@@ -880,8 +923,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         w[20] = du[4] * k0; w[21] = du[5] * k1; w[22] = du[6] * k2; w[23] = du[7] * k3;
 #pragma unroll
         for (int j = 24; j < 32; ++j) w[j] = 0.f;
+        // the image carries the hidden dropout's 1 / (1 - p) (forward: f = fs (H_kept W2^T) + b2): both its consumers need it
+        // — dH = (fs da2) W2 and dW2 = (fs da2)^T H_kept — while the bias gradient below sums the unscaled da2
+        const float fs = a.d_ffn.scale;
         *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c0, 128)) =
-            make_uint4(pack_bf16(w[16], w[17]), pack_bf16(w[18], w[19]), pack_bf16(w[20], w[21]), pack_bf16(w[22], w[23]));
+            make_uint4(pack_bf16(w[16] * fs, w[17] * fs), pack_bf16(w[18] * fs, w[19] * fs), pack_bf16(w[20] * fs, w[21] * fs),
+                       pack_bf16(w[22] * fs, w[23] * fs));
         const float t = warp_colsum32(w, lane);
         if (lane < 8) atomicAdd(&g_g2[c0 + lane], t);
         else if (lane < 16) atomicAdd(&g_be2[c0 + lane - 8], t);
@@ -893,10 +940,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     __syncthreads();
     if constexpr (!ATTN_ONLY) {
     // ---- B1: FFN backward, chunk by chunk ----
+    const uint32_t w1_chunk = tc_w1_chunk_bytes(D, FC);
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1, FC, k), id_kk_fc, k > 0);
+      for (int k = 0; k < (D + TC_KAUG) / 16; ++k) mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1, FC, k), id_kk_fc, k > 0);
       mma_commit(&bar_h);
     }
     // The H recompute of chunk c + 1 is issued BEFORE the dx1 / dW1 / dW2 MMAs of chunk c and signals its own barrier, so the
@@ -908,41 +956,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       const uint32_t aHc = (c & 1) ? aCtx : aH;
       mbar_wait(&bar_h, phh); phh ^= 1;               // H(c) accumulator ready
       fence_after_sync();
-      uint32_t mask = 0;                              // (kept && h > 0) bits of this thread's (<= 2) 16-column blocks
       {
         const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 2;
-        int t = 0;
-        for (int b = part; b < nblk; b += BWD_PARTS, ++t) {
+        for (int b = part; b < nblk; b += BWD_PARTS) {
           const int cb = b * 16;
           const uint64_t wb = w0 + (uint64_t)(cb >> 2);
-          const uint32_t xhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu, wlo = (uint32_t)wb;
-          float v[16];
-          tmem_ld16(t_big + lane_off + (uint32_t)cb, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
-          uint32_t bits = 0;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float h0 = fmaxf(v[j] + p_b1[c * FC + cb + j], 0.f), h1 = fmaxf(v[j + 1] + p_b1[c * FC + cb + j + 1], 0.f);
-            float h2 = fmaxf(v[j + 2] + p_b1[c * FC + cb + j + 2], 0.f), h3 = fmaxf(v[j + 3] + p_b1[c * FC + cb + j + 3], 0.f);
-            if (a.d_ffn.thr) {
-              uint32_t lo, hi;
-              hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
-              h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-              h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
-              h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
-              h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
-            }
-            bits |= (h0 > 0.f ? 1u : 0u) << j;
-            bits |= (h1 > 0.f ? 1u : 0u) << (j + 1);
-            bits |= (h2 > 0.f ? 1u : 0u) << (j + 2);
-            bits |= (h3 > 0.f ? 1u : 0u) << (j + 3);
-            pk[j >> 1] = pack_bf16(h0, h1);
-            pk[(j >> 1) + 1] = pack_bf16(h2, h3);
-          }
-          *reinterpret_cast<uint4 *>(sHc + kmajor_off(row, cb, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4 *>(sHc + kmajor_off(row, cb + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          mask |= bits << (16 * t);
+          ffn_hidden_block(t_big + lane_off + (uint32_t)cb, sHc + kmajor_off(row, cb, 128), a.d_ffn, (uint32_t)wb,
+                           (uint32_t)(wb >> 32) * 0x85EBCA6Bu);
         }
       }
       fence_async_smem();
@@ -957,47 +977,35 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       }
       mbar_wait(&bar_mma, ph); ph ^= 1;
       fence_after_sync();
-      if (part < nblk) {                              // this thread owns blocks b0 = part and (if present) b1 = part + PARTS
-        const float sc = a.d_ffn.scale;
-        const int b0 = part, b1 = part + BWD_PARTS;
-        const bool two = b1 < nblk;
-        float w[32];
-        tmem_ld16(t_big + lane_off + (uint32_t)(b0 * 16), w);
-        if (two) {
-          tmem_ld16(t_big + lane_off + (uint32_t)(b1 * 16), w + 16);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[16 + j] = 0.f;
-        }
+      // dH = dH_acc where the hidden unit was kept and positive, i.e. where this thread's own H pair (still in the image it
+      // wrote above) is non-zero: pack, one packed compare and one AND per pair; the 1 / (1 - p) came in with the da2 image
+      for (int b = part; b < nblk; b += BWD_PARTS) {
+        const int cb = b * 16;
+        float w[16];
+        tmem_ld16(t_big + lane_off + (uint32_t)cb, w);
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(sHc + kmajor_off(row, cb, 128));
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(sHc + kmajor_off(row, cb, 128) + 2048);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) w[j] = ((mask >> j) & 1u) ? w[j] * sc : 0.f;
-        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b0 * 16, 128)) =
-            make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b0 * 16 + 8, 128)) =
-            make_uint4(pack_bf16(w[8], w[9]), pack_bf16(w[10], w[11]), pack_bf16(w[12], w[13]), pack_bf16(w[14], w[15]));
-        if (two) {
-          *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b1 * 16, 128)) =
-              make_uint4(pack_bf16(w[16], w[17]), pack_bf16(w[18], w[19]), pack_bf16(w[20], w[21]), pack_bf16(w[22], w[23]));
-          *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, b1 * 16 + 8, 128)) =
-              make_uint4(pack_bf16(w[24], w[25]), pack_bf16(w[26], w[27]), pack_bf16(w[28], w[29]), pack_bf16(w[30], w[31]));
-        }
-        const float t = warp_colsum32(w, lane);       // bias gradient of linear1: lane l <-> column (l<16 ? b0 : b1)*16 + l%16
-        if (lane < 16) atomicAdd(&g_b1[c * FC + b0 * 16 + lane], t);
-        else if (two) atomicAdd(&g_b1[c * FC + b1 * 16 + lane - 16], t);
+        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb, 128)) =
+            make_uint4(pack_bf16(w[0], w[1]) & nonzero2(h0.x), pack_bf16(w[2], w[3]) & nonzero2(h0.y),
+                       pack_bf16(w[4], w[5]) & nonzero2(h0.z), pack_bf16(w[6], w[7]) & nonzero2(h0.w));
+        *reinterpret_cast<uint4 *>(sDH + kmajor_off(row, cb, 128) + 2048) =
+            make_uint4(pack_bf16(w[8], w[9]) & nonzero2(h1.x), pack_bf16(w[10], w[11]) & nonzero2(h1.y),
+                       pack_bf16(w[12], w[13]) & nonzero2(h1.z), pack_bf16(w[14], w[15]) & nonzero2(h1.w));
       }
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
+      colsum_image(sDH, FC >> 3, g_b1 + c * FC, warp, lane, BWD_THREADS / 32);      // linear1 bias gradient: column sums of the dH image
       if (tid == 0) {
         fence_after_sync();
         if (c + 1 < nchunk) {                         // H(c + 1) first, with its own barrier (t_big: the dH(c) accumulator is drained)
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)
-            mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * FC * D * 2u, FC, k), id_kk_fc, k > 0);
+          for (int k = 0; k < (D + TC_KAUG) / 16; ++k)
+            mma_bf16_ss(t_big, desc_a128(aX1, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * w1_chunk, FC, k), id_kk_fc, k > 0);
           mma_commit(&bar_h);
         }
-        const uint32_t w1c = aW + io.w1 + (uint32_t)c * FC * D * 2u;
+        const uint32_t w1c = aW + io.w1 + (uint32_t)c * w1_chunk;
         for (int k = 0; k < FC / 16; ++k)             // dx1 += dH . W1[chunk, :]     (B: MN-major view of the W1 chunk image [FC x D])
           mma_bf16_ss(t_sa, desc_a128(aDH, k), desc_mn(w1c, FC, k), id_kmn_d, (c | k) > 0);
 #pragma unroll
@@ -1136,7 +1144,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {
         const int s = p / H, h = p - s * H;
         const uint64_t w_pair = (uint64_t)((((a.seq0 + (int64_t)tile * 4 + s) * H + h) * 32) * 8);
-        a32_attn_bwd<DH, CAUSAL>(smem + sp.q, smem + sp.k, smem + sp.v, smem + sp.dctx, sCtx, sDQ, s, h, lane, a.d_attn, w_pair, g_bqkv);
+        a32_attn_bwd<DH, CAUSAL>(smem + sp.q, smem + sp.k, smem + sp.v, smem + sp.dctx, sCtx, sDQ, s, h, lane, a.d_attn, w_pair);
       }
     } else
     for (int p = warp; p < 4 * H; p += BWD_THREADS / 32) {      // lane = query row; dK/dV via warp transposed sums
@@ -1212,6 +1220,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    if constexpr (MMA) colsum_image(sDQ, 3 * D / 8, g_bqkv, warp, lane, BWD_THREADS / 32);      // in-projection bias gradient: column sums of the dq | dk | dv image
     // ---- B6: dx_in = dqkv . Wqkv ; dWqkv += dqkv^T x_in ; dWo += da1^T ctx ----
     if (tid == 0) {
       fence_after_sync();

@@ -15,15 +15,20 @@ constexpr int TC_MAX_LAYERS = 16;
 // self-attention or cross-attention over an encoder-memory tile: the three blocks of a decoder layer
 constexpr int TC_MODE_LAYER = 0, TC_MODE_FFN = 1, TC_MODE_ATTN_CAUSAL = 2, TC_MODE_ATTN_CROSS = 3;
 
+// linear1's bias rides in the contraction: the A image of the FFN input carries TC_KAUG extra K columns (column D = 1.0, the
+// rest 0) and every W1 chunk image the matching columns (column D = bf16(b1), the rest 0), so the accumulator the epilogue
+// drains already holds x1 W1^T + b1 and the epilogue is pack-with-ReLU + dropout mask only.
+constexpr int TC_KAUG = 16;
 struct TcImg {               // byte offsets of the bf16 operand images of one layer
   uint32_t wqkv, wo, w1, w2, total;
 };
+__host__ __device__ inline uint32_t tc_w1_chunk_bytes(int D, int FC) { return (uint32_t)(FC * (D + TC_KAUG) * 2); }
 __host__ __device__ inline TcImg tc_img(int D, int F) {
   TcImg o;
   o.wqkv = 0;
   o.wo = (uint32_t)(3 * D * D * 2);
   o.w1 = o.wo + (uint32_t)(D * D * 2);
-  o.w2 = o.w1 + (uint32_t)(F * D * 2);
+  o.w2 = o.w1 + (uint32_t)(F * (D + TC_KAUG) * 2);
   o.total = o.w2 + (uint32_t)(D * F * 2);
   return o;
 }
@@ -37,7 +42,7 @@ inline int tc_ffn_chunk(int F) {
 struct TcPrepArgs {
   const float *params;
   uint8_t *img;                        // n_layers * img_stride bytes
-  int64_t w_in[TC_MAX_LAYERS], w_out[TC_MAX_LAYERS], w1[TC_MAX_LAYERS], w2[TC_MAX_LAYERS];
+  int64_t w_in[TC_MAX_LAYERS], w_out[TC_MAX_LAYERS], w1[TC_MAX_LAYERS], w2[TC_MAX_LAYERS], b1[TC_MAX_LAYERS];
   uint32_t img_stride;
   int n_layers, D, F, FC;
 };

@@ -235,6 +235,7 @@ static int tc_prep(const TcCtx &x, const TcPlan &pl) {
   a.D = x.c.d_model; a.F = x.c.dim_ff; a.FC = tc_ffn_chunk(x.c.dim_ff);
   for (int l = 0; l < x.c.n_enc; ++l) {
     a.w_in[l] = x.L->enc[l].sa.w_in; a.w_out[l] = x.L->enc[l].sa.w_out; a.w1[l] = x.L->enc[l].w1; a.w2[l] = x.L->enc[l].w2;
+    a.b1[l] = x.L->enc[l].b1;
   }
   return tc_prep_weights(a, x.st);
 }
@@ -378,6 +379,7 @@ int tc_dec_prep(const gt_config &c, const Layout &L, const float *params, uint8_
     for (int l = 0; l < c.n_dec; ++l) {
       const AttnP &ap = pass == 0 ? L.dec[l].sa : L.dec[l].ca;
       a.w_in[l] = ap.w_in; a.w_out[l] = ap.w_out; a.w1[l] = L.dec[l].w1; a.w2[l] = L.dec[l].w2;
+      a.b1[l] = L.dec[l].b1;
     }
     GT_TRY(tc_prep_weights(a, st));
   }

@@ -3,6 +3,7 @@
 // sm_100a only.  Bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace gt {
@@ -189,6 +190,29 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gmem, uint32_t byte
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// two fp32 -> packed bf16 pair with ReLU fused into the conversion (low half = lo)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// Two dropout decisions at once.  `fields` holds two 14-bit fields in its 16-bit halves (common.cuh: hash_quad), `thr2` the
+// 14-bit threshold in both halves: as fp16 bit patterns both are non-negative and finite, where fp16 order = integer order,
+// so ONE packed half-precision compare yields 0xFFFF (keep) / 0x0000 (drop) per half — AND it onto a packed bf16 pair.
+__device__ __forceinline__ uint32_t keep2(uint32_t fields, uint32_t thr2) {
+  return __hge2_mask(*reinterpret_cast<const __half2 *>(&fields), *reinterpret_cast<const __half2 *>(&thr2));
+}
+// 0xFFFF per half where the packed bf16 (or fp16) value is non-zero (inputs are >= +0: ReLU outputs)
+__device__ __forceinline__ uint32_t nonzero2(uint32_t v) {
+  const uint32_t z = 0u;
+  return __hne2_mask(*reinterpret_cast<const __half2 *>(&v), *reinterpret_cast<const __half2 *>(&z));
+}
+__device__ __forceinline__ float rcp_approx(float x) {      // 1 / x, one MUFU (x is a softmax denominator in [1, 32])
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace umma
