@@ -35,7 +35,7 @@ CASES = {
     "c2_l1_n3": (G.GrooveCfg(32, 16, 512, 1, 0, 16, 27), 0.38, 0.24, 3, GRAD_TOL),       # ragged last tile
     "c5enc_l1": (G.GrooveCfg(32, 16, 512, 1, 0, 27, 27), 0.38, 0.24, 9, GRAD_TOL),       # symbolic input
     "f96_h1": (G.GrooveCfg(32, 1, 96, 2, 0, 16, 27), 0.5, 0.1, 6, GRAD_TOL),             # fused d32 with fp32 (SIMT) attention
-    "c5_encdec_l1": (G.GrooveCfg(32, 16, 512, 1, 1, 27, 27), 0.38, 0.24, 16, GRAD_TOL),  # decoder blocks: causal / cross / FFN
+    "c5_encdec_l1": (G.GrooveCfg(32, 16, 512, 1, 1, 27, 27), 0.38, 0.24, 64, GRAD_TOL),  # decoder blocks: causal / cross / FFN (4 blocks deep)
     "c5_dec_h4_l1": (G.GrooveCfg(32, 4, 64, 1, 1, 27, 27), 0.38, 0.1, 16, GRAD_TOL),
     "c4_l1": (G.GrooveCfg(256, 16, 64, 1, 0, 16, 27), 1.0, 0.15, 16, GRAD_TOL),          # fused d256, head dim 16
     "h8_l1": (G.GrooveCfg(256, 8, 128, 1, 0, 16, 27), 0.5, 0.1, 16, GRAD_TOL),           # fused d256, head dim 32, two FFN chunks

@@ -108,7 +108,7 @@ __device__ __forceinline__ void drop4(const Drop &d, uint64_t idx4, float &m0, f
 }
 
 struct SmemPlan {
-  uint32_t w, par, xa, q, k, v, ctx, h, total;
+  uint32_t w, par, stat, xa, q, k, v, ctx, h, h2, total;
 };
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 // mma = attention on mma.sync (tc_attn32.cuh): q | k | v are bf16 row-major token images instead of fp32 rows / compact heads
@@ -117,7 +117,8 @@ __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC, bool mma) {
   SmemPlan s;
   s.w = 0;
   s.par = al128(tc_img(D, F).total);
-  s.xa = al128(s.par + (uint32_t)(9 * D + F) * 4u);
+  s.stat = al128(s.par + (uint32_t)(9 * D + F) * 4u);      // LayerNorm row statistics exchanged between the 4 column parts: [128 rows][4] float2
+  s.xa = al128(s.stat + 128u * 4u * 8u);
   s.q = al128(s.xa + 128u * (D + TC_KAUG) * 2u);     // (xa: x image + the TC_KAUG ones / zero columns) ; q: fp32 rows, stride D+4
   if (mma) {
     s.k = s.q + A32_IMG;
@@ -129,7 +130,8 @@ __host__ __device__ inline SmemPlan fwd_smem(int D, int F, int FC, bool mma) {
     s.ctx = al128(s.v + 128u * D * 4u);
   }
   s.h = al128(s.ctx + 128u * D * 2u);
-  s.total = al128(s.h + 128u * (uint32_t)(FC < 32 ? 32 : FC) * 2u);     // >= 8 KB: the cross-attention memory tile is staged here
+  s.h2 = al128(s.h + 128u * (uint32_t)(FC < 32 ? 32 : FC) * 2u);        // >= 8 KB: the cross-attention memory tile is staged in h
+  s.total = al128(s.h2 + 128u * (uint32_t)(FC < 32 ? 32 : FC) * 2u);    // h | h2: the hidden image is double buffered across FFN chunks
   return s;
 }
 
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   const ArgsView<DEVSTEP> view(a_in);
   const TcLayerArgs &a = view.a;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_h;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
@@ -339,10 +341,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   float *sV = reinterpret_cast<float *>(smem + sp.v);
   uint8_t *sCtx = smem + sp.ctx;
   uint8_t *sH = smem + sp.h;
+  float2 *sStat = reinterpret_cast<float2 *>(smem + sp.stat);
   constexpr int LQ = D + 4;
+  const int c0 = part * 8;                             // this thread's 8 columns of its token row in the LayerNorm phases
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); mbar_init(&bar_h, 1); fence_mbar_init(); }
   if constexpr (MODE != TC_MODE_FFN)
     for (int i = tid; i < 3 * D; i += FWD_THREADS) p_bqkv[i] = a.bqkv[i];
   if constexpr (!ATTN_ONLY) write_kaug_columns(sXa, tid, D);      // linear1's bias rides in the contraction (tc_layers.cuh: TC_KAUG)
@@ -362,48 +366,53 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     }
   }
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_big = tmem, t_small = tmem + 128;
+  const uint32_t t_big = tmem, t_small = tmem + 128, t_big2 = tmem + 256;      // t_big | t_big2: FFN1 accumulators of even / odd chunks
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t aXa = smem_u32(sXa), aCtx = smem_u32(sCtx), aH = smem_u32(sH), aW = smem_u32(sW);
   mbar_wait(&bar_w, 0);
-  uint32_t ph = 0;
+  uint32_t ph = 0, phh = 0;
+  // Row statistics of a LayerNorm: every thread holds 8 of its row's 32 columns; the 4 warps that share 32 token rows (warp & 3
+  // equal: they also share the TMEM lanes) exchange (sum, sum of squares) through shared memory behind a 128-thread named
+  // barrier — all 16 warps work in the LayerNorm phases and no block-wide barrier is added.
+  auto row_stats = [&](float s1, float s2, float &mean, float &rstd) {
+    sStat[row * 4 + part] = make_float2(s1, s2);
+    named_bar_sync(1 + (warp & 3), 128);
+    const float4 p01 = *reinterpret_cast<const float4 *>(sStat + row * 4), p23 = *reinterpret_cast<const float4 *>(sStat + row * 4 + 2);
+    mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.f / D);
+    rstd = rsqrtf(fmaxf(((p01.y + p01.w) + (p23.y + p23.w)) * (1.f / D) - mean * mean, 0.f) + LN_EPS);
+    named_bar_sync(1 + (warp & 3), 128);               // the four slots may be rewritten (next LayerNorm phase)
+  };
   const float attn_scale = rsqrtf((float)dh) * 1.4426950408889634f;   // 1/sqrt(dh) * log2(e), folded into q
   const float keep_scale = a.d_attn.scale;
 
   // this thread's 8-column chunk of the NEXT tile's input row (and memory row), fetched a whole tile time ahead: the tile
   // would otherwise start with a load of rows nobody has touched yet
-  uint4 xnext = make_uint4(0, 0, 0, 0), mnext = make_uint4(0, 0, 0, 0);
+  float4 xn0 = make_float4(0, 0, 0, 0), xn1 = xn0;
+  uint4 mnext = make_uint4(0, 0, 0, 0);
   auto fetch_tile = [&](int t) {
     const int64_t r = (int64_t)t * TC_TILE + row;
-    xnext = make_uint4(0, 0, 0, 0); mnext = make_uint4(0, 0, 0, 0);
+    xn0 = make_float4(0, 0, 0, 0); xn1 = xn0; mnext = make_uint4(0, 0, 0, 0);
     if (t < a.n_tiles && r < a.M) {
-      xnext = pack8(a.x_in + r * D + part * 8);
-      if constexpr (CROSS) mnext = pack8(a.mem + r * D + part * 8);
+      xn0 = *reinterpret_cast<const float4 *>(a.x_in + r * D + c0);
+      xn1 = *reinterpret_cast<const float4 *>(a.x_in + r * D + c0 + 4);
+      if constexpr (CROSS) mnext = pack8(a.mem + r * D + c0);
     }
   };
   fetch_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t grow = (int64_t)tile * TC_TILE + row;
     const bool valid = grow < a.M;
-    // ---- P0: x_in tile -> bf16 A operand (8 columns per thread) ----
+    // ---- P0: x_in tile -> bf16 A operand (8 columns per thread); the fp32 chunk stays in registers: it is this thread's residual ----
+    float x1[8] = {xn0.x, xn0.y, xn0.z, xn0.w, xn1.x, xn1.y, xn1.z, xn1.w};     // x_in chunk now; LayerNorm1 output (FFN input / residual) after P5
     {
-      *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, part * 8, 128)) = xnext;
-      if constexpr (CROSS) *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 8, 128)) = mnext;   // keys / values come from the encoder memory tile
+      *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c0, 128)) =
+          make_uint4(pack_bf16(x1[0], x1[1]), pack_bf16(x1[2], x1[3]), pack_bf16(x1[4], x1[5]), pack_bf16(x1[6], x1[7]));
+      if constexpr (CROSS) *reinterpret_cast<uint4 *>(sH + kmajor_off(row, c0, 128)) = mnext;   // keys / values come from the encoder memory tile
       fetch_tile(tile + (int)gridDim.x);
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    float x1[D];                                       // part 0: the FFN block's input row (= its residual)
-    if constexpr (MODE != 0) {
-      if (part == 0) {
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-          const float4 t = valid ? *reinterpret_cast<const float4 *>(a.x_in + grow * D + c) : make_float4(0, 0, 0, 0);
-          x1[c] = t.x; x1[c + 1] = t.y; x1[c + 2] = t.z; x1[c + 3] = t.w;
-        }
-      }
-    }
     if constexpr (MODE != TC_MODE_FFN) {
     // ---- P1: QKV = x Wqkv^T  (cross: q = x Wq^T, k | v = mem Wkv^T: rows [D, 3D) of the packed in-projection) ----
     if (tid == 0) {
@@ -499,43 +508,37 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;
     fence_after_sync();
-    // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = row, part 0) ----
-    if (part == 0) {
-#pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, x1 + cb);
+    // ---- P5: + bias, dropout, + residual, LayerNorm1 (thread = (row, 8 columns)) ----
+    {
+      float u[8];
+      tmem_ld8(t_small + lane_off + (uint32_t)c0, u);
       tmem_ld_wait();
-      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
-      float s1 = 0.f;
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D + c0);
+      float m[8];
+      drop4(a.d1, e0, m[0], m[1], m[2], m[3]);
+      drop4(a.d1, e0 + 4, m[4], m[5], m[6], m[7]);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float4 xr = valid ? *reinterpret_cast<const float4 *>(a.x_in + grow * D + c) : make_float4(0, 0, 0, 0);
-        float m0, m1, m2, m3;
-        drop4(a.d1, e0 + c, m0, m1, m2, m3);
-        x1[c] = xr.x + (x1[c] + p_bo[c]) * m0;
-        x1[c + 1] = xr.y + (x1[c + 1] + p_bo[c + 1]) * m1;
-        x1[c + 2] = xr.z + (x1[c + 2] + p_bo[c + 2]) * m2;
-        x1[c + 3] = xr.w + (x1[c + 3] + p_bo[c + 3]) * m3;
-        s1 += (x1[c] + x1[c + 1]) + (x1[c + 2] + x1[c + 3]);
-        if (a.u1 && valid) *reinterpret_cast<float4 *>(a.u1 + grow * D + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
+      for (int j = 0; j < 8; ++j) {
+        u[j] = x1[j] + (u[j] + p_bo[c0 + j]) * m[j];
+        s1 += u[j]; s2 = fmaf(u[j], u[j], s2);
       }
-      const float mu = s1 * (1.f / D);
-      float q = 0.f;
+      if (a.u1 && valid) {
+        *reinterpret_cast<float4 *>(a.u1 + grow * D + c0) = make_float4(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<float4 *>(a.u1 + grow * D + c0 + 4) = make_float4(u[4], u[5], u[6], u[7]);
+      }
+      float mu, rs;
+      row_stats(s1, s2, mu, rs);
 #pragma unroll
-      for (int c = 0; c < D; ++c) { float t = x1[c] - mu; q = fmaf(t, t, q); }
-      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
-#pragma unroll
-      for (int c = 0; c < D; ++c) x1[c] = (x1[c] - mu) * rs * p_g1[c] + p_be1[c];
+      for (int j = 0; j < 8; ++j) x1[j] = (u[j] - mu) * rs * p_g1[c0 + j] + p_be1[c0 + j];
       if constexpr (ATTN_ONLY) {                       // attention block alone: its LayerNorm output is the block output
         if (valid) {
-#pragma unroll
-          for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.x_out + grow * D + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
+          *reinterpret_cast<float4 *>(a.x_out + grow * D + c0) = make_float4(x1[0], x1[1], x1[2], x1[3]);
+          *reinterpret_cast<float4 *>(a.x_out + grow * D + c0 + 4) = make_float4(x1[4], x1[5], x1[6], x1[7]);
         }
       } else {
-#pragma unroll
-        for (int c = 0; c < D; c += 8)
-          *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c, 128)) =
-              make_uint4(pack_bf16(x1[c], x1[c + 1]), pack_bf16(x1[c + 2], x1[c + 3]), pack_bf16(x1[c + 4], x1[c + 5]),
-                         pack_bf16(x1[c + 6], x1[c + 7]));
+        *reinterpret_cast<uint4 *>(sXa + kmajor_off(row, c0, 128)) =
+            make_uint4(pack_bf16(x1[0], x1[1]), pack_bf16(x1[2], x1[3]), pack_bf16(x1[4], x1[5]), pack_bf16(x1[6], x1[7]));
       }
     }
     fence_async_smem();
@@ -544,24 +547,36 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
     }  // MODE != TC_MODE_FFN
     if constexpr (ATTN_ONLY) continue;
     // ---- P6: FFN, hidden dimension in chunks of FC; FFN2 accumulates in TMEM across chunks ----
+    // FFN1 accumulators and hidden images are double buffered: FFN1(c + 1) is issued BEFORE the epilogue of chunk c starts, so
+    // the tensor pipe works under the epilogue and no MMA round trip is exposed inside the loop.  One commit covers everything
+    // issued before it: the wait for FFN1(c) also proves FFN2(c - 2) retired, i.e. hidden image (c & 1) may be rewritten.
     const uint32_t idesc1 = make_idesc_bf16(128, FC), idesc2 = make_idesc_bf16(128, D);
     const uint32_t w1_chunk = tc_w1_chunk_bytes(D, FC);
+    const uint32_t h_bytes = sp.h2 - sp.h;
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
       for (int k = 0; k < (D + TC_KAUG) / 16; ++k) mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1, FC, k), idesc1, k > 0);
-      mma_commit(&bar_mma);
+      mma_commit(&bar_h);
     }
     const int nblk = FC / 16;                          // 16-column blocks of the chunk, dealt round-robin to the 4 parts
     for (int c = 0; c < nchunk; ++c) {
-      mbar_wait(&bar_mma, ph); ph ^= 1;               // FFN1(c) (and FFN2(c-1)) complete
+      const uint32_t tb = (c & 1) ? t_big2 : t_big;
+      mbar_wait(&bar_h, phh); phh ^= 1;               // FFN1(c) complete
       fence_after_sync();
+      if (tid == 0 && c + 1 < nchunk) {
+#pragma unroll
+        for (int k = 0; k < (D + TC_KAUG) / 16; ++k)
+          mma_bf16_ss((c & 1) ? t_big : t_big2, desc_a128(aXa, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * w1_chunk, FC, k), idesc1, k > 0);
+        mma_commit(&bar_h);
+      }
       {
+        uint8_t *sHc = sH + (c & 1) * h_bytes;
         const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * FC) >> 2;        // multiple of 4 (F, FC multiples of 16)
         for (int b = part; b < nblk; b += 4) {
           const int cb = b * 16;
           const uint64_t wb = w0 + (uint64_t)(cb >> 2);                                 // + (0..3) never carries
-          ffn_hidden_block(t_big + lane_off + (uint32_t)cb, sH + kmajor_off(row, cb, 128), a.d_ffn, (uint32_t)wb,
+          ffn_hidden_block(tb + lane_off + (uint32_t)cb, sHc + kmajor_off(row, cb, 128), a.d_ffn, (uint32_t)wb,
                            (uint32_t)(wb >> 32) * 0x85EBCA6Bu);
         }
       }
@@ -570,52 +585,41 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
+        const uint32_t aHc = aH + (uint32_t)(c & 1) * h_bytes;
         for (int k = 0; k < FC / 16; ++k)
-          mma_bf16_ss(t_small, desc_a128(aH, k), desc_b(aW + io.w2 + (uint32_t)c * D * FC * 2u, D, k), idesc2, (c | k) > 0);
-        if (c + 1 < nchunk) {
-#pragma unroll
-          for (int k = 0; k < (D + TC_KAUG) / 16; ++k)
-            mma_bf16_ss(t_big, desc_a128(aXa, k), desc_b(aW + io.w1 + (uint32_t)(c + 1) * w1_chunk, FC, k), idesc1, k > 0);
-        }
-        mma_commit(&bar_mma);
+          mma_bf16_ss(t_small, desc_a128(aHc, k), desc_b(aW + io.w2 + (uint32_t)c * D * FC * 2u, D, k), idesc2, (c | k) > 0);
+        if (c + 1 == nchunk) mma_commit(&bar_mma);
       }
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // last FFN2 complete
     fence_after_sync();
-    // ---- P8: + bias, dropout, + residual, LayerNorm2 -> x_out ----
-    if (part == 0) {
-      float f[D];
-#pragma unroll
-      for (int cb = 0; cb < D; cb += 16) tmem_ld16(t_small + lane_off + (uint32_t)cb, f + cb);
+    // ---- P8: + bias, dropout, + residual, LayerNorm2 -> x_out (thread = (row, 8 columns)) ----
+    {
+      float f[8];
+      tmem_ld8(t_small + lane_off + (uint32_t)c0, f);
       tmem_ld_wait();
-      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D);
+      const uint64_t e0 = (uint64_t)((a.seq0 * 32 + grow) * D + c0);
       const float fs = a.d_ffn.scale;                  // 1 / (1 - p) of the hidden dropout: applied here, once per output column
-      float s1 = 0.f;
+      float m[8];
+      drop4(a.d2, e0, m[0], m[1], m[2], m[3]);
+      drop4(a.d2, e0 + 4, m[4], m[5], m[6], m[7]);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; c += 4) {
-        float m0, m1, m2, m3;
-        drop4(a.d2, e0 + c, m0, m1, m2, m3);
-        f[c] = x1[c] + fmaf(f[c], fs, p_b2[c]) * m0;
-        f[c + 1] = x1[c + 1] + fmaf(f[c + 1], fs, p_b2[c + 1]) * m1;
-        f[c + 2] = x1[c + 2] + fmaf(f[c + 2], fs, p_b2[c + 2]) * m2;
-        f[c + 3] = x1[c + 3] + fmaf(f[c + 3], fs, p_b2[c + 3]) * m3;
-        s1 += (f[c] + f[c + 1]) + (f[c + 2] + f[c + 3]);
+      for (int j = 0; j < 8; ++j) {
+        f[j] = x1[j] + fmaf(f[j], fs, p_b2[c0 + j]) * m[j];
+        s1 += f[j]; s2 = fmaf(f[j], f[j], s2);
       }
       if (a.u2 && valid) {
-#pragma unroll
-        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(a.u2 + grow * D + c) = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
+        *reinterpret_cast<float4 *>(a.u2 + grow * D + c0) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4 *>(a.u2 + grow * D + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
       }
-      const float mu = s1 * (1.f / D);
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; ++c) { float t = f[c] - mu; q = fmaf(t, t, q); }
-      const float rs = rsqrtf(q * (1.f / D) + LN_EPS);
+      float mu, rs;
+      row_stats(s1, s2, mu, rs);
       if (valid) {
 #pragma unroll
-        for (int c = 0; c < D; c += 4)
-          *reinterpret_cast<float4 *>(a.x_out + grow * D + c) =
-              make_float4((f[c] - mu) * rs * p_g2[c] + p_be2[c], (f[c + 1] - mu) * rs * p_g2[c + 1] + p_be2[c + 1],
-                          (f[c + 2] - mu) * rs * p_g2[c + 2] + p_be2[c + 2], (f[c + 3] - mu) * rs * p_g2[c + 3] + p_be2[c + 3]);
+        for (int j = 0; j < 8; ++j) f[j] = (f[j] - mu) * rs * p_g2[c0 + j] + p_be2[c0 + j];
+        *reinterpret_cast<float4 *>(a.x_out + grow * D + c0) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4 *>(a.x_out + grow * D + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
       }
     }
     fence_before_sync();
@@ -623,7 +627,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 static int num_sms() {
@@ -720,9 +724,12 @@ __host__ __device__ inline BwdSmem bwd_smem(int D, int F, bool mma) {
   s.dh = s.h + 128u * 128u * 2u;
   uint32_t end_ffn = s.dh + 128u * 128u * 2u;
   // row-statistics exchange of the two LayerNorm-backward phases (two ping-pong buffers of [128 rows][4 parts] float4 = 16 KB):
-  // aliases the dH image, which is dead in both (B0: start of a tile ; B2: every FFN MMA of the tile has retired, the attention
-  // images that share this range are written after B2's closing barrier)
-  s.stat = s.dh;
+  // aliases the first half of the EVEN hidden image, which is dead in both phases — B0: start of a tile; B2: every FFN MMA of
+  // the tile has retired, the last generic reads of that image (the dH epilogue of an even chunk) lie before a block-wide
+  // barrier, and the attention images that share this range are written after B2's closing barrier.  (It must NOT alias the
+  // dH image: the tensor-core column sum of the last chunk's dH still reads it when the first warps enter B2 — found by
+  // compute-sanitizer racecheck, profiles/r02/r02_sanitizer_racecheck_bf16_before_fix.txt.)
+  s.stat = s.h;
   s.total = end_attn > end_ffn ? end_attn : end_ffn;
   return s;
 }
