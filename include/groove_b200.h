@@ -160,8 +160,8 @@ int gt_train_steps(const gt_config *cfg, float *params, const float *pe, const f
  * refills per epoch, DataLoader(shuffle=True) of train.py:153-158); when given, each replay first gathers rows
  * perm[counters[2] .. +n_seq) into xbuf / ybuf, otherwise the caller fills xbuf / ybuf before each launch.  metrics_ring
  * (optional, ring_slots x 6 floats): replay k stores its six calculate_loss values at slot counters[3] % ring_slots.
- * Available for encoder-only models (n_dec = 0) on GT_PATH_FUSED_D32, GT_PATH_GEMM_TC and GT_PATH_FP32_SIMT (the fused
- * d_model = 256 kernels and the decoder blocks do not read the device-resident step yet).  optimizer: 0 SGD, 1 Adam (torch
+ * Available on every path (GT_PATH_*), for encoder-only and encoder-decoder models (for n_dec > 0 the shifted target is built
+ * from ybuf inside the graph, BGT/models/train.py:130-131).  optimizer: 0 SGD, 1 Adam (torch
  * defaults).  Per-kernel profiling (gt_profile_enable) and bucket events (gt_grad_events_enable) must be off. */
 int gt_graph_train_create(const gt_config *cfg, float *params, const float *pe, float *xbuf, float *ybuf, int64_t n_seq,
                           float hit_loss_penalty, float *grads, float *metrics6, float *hvo, void *ws, int64_t ws_bytes,

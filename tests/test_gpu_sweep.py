@@ -140,7 +140,7 @@ def test_graph_replay_dropout_masks_follow_the_device_counter():
 
 def test_graph_members_packed_concurrently():
     x, y = _dataset(96)
-    cfgs = [dict(CONFIGS[1], batch_size=16), CONFIGS[2], CONFIGS[3]]      # fused d_model = 32 | per-op d_model = 64 | d_model = 256 falls back to gt_train_steps
+    cfgs = [dict(CONFIGS[1], batch_size=16), CONFIGS[2], CONFIGS[3]]      # fused d_model = 32 | per-op d_model = 64 | fused d_model = 256
 
     def run(concurrent):
         torch.manual_seed(0)
@@ -150,7 +150,7 @@ def test_graph_members_packed_concurrently():
 
     packed, pk = run(True)
     solo, _ = run(False)
-    assert [m.graph_capable() for m in pk.members] == [True, True, False]
+    assert [m.graph_capable() for m in pk.members] == [True, True, True]
     for a, b in zip(packed, solo):
         np.testing.assert_allclose(a[0], b[0], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(a, b, rtol=3e-2, atol=1e-6)
@@ -173,3 +173,65 @@ def test_graph_replay_on_the_per_op_paths(precision):
     a, b = run(True), run(False)
     np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
     assert len({round(float(v), 6) for v in a[:, 0]}) > 6
+
+
+def test_graph_replay_on_the_fused_d256_path():
+    """The weight-streaming d_model = 256 kernels (tc256*.cu, edge256.cu) derive their dropout keys from the device counter too
+    (common.cuh: DropArgsView): with learning rate 0 a replayed run reproduces the eager losses."""
+    x, y = _dataset(96)
+    cfg = dict(CONFIGS[3], optimizer_algorithm="sgd", learning_rate=0.0, batch_size=16, dropout=0.3)
+
+    def run(graph):
+        torch.manual_seed(0)
+        pk = SweepPacker([cfg], x, y, "cuda", precision="bf16", seed=4)
+        assert pk.members[0].graph_capable()
+        pk.run(12, concurrent=False, graph=graph)
+        return pk.history()[0].numpy()
+
+    a, b = run(True), run(False)
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+    assert len({round(float(v), 6) for v in a[:, 0]}) > 6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_encoder_decoder(precision):
+    """gt_graph_train_create on a GrooveTransformer (encoder-decoder, BGT/models/transformer.py:9-46): the decoder blocks of the
+    fused kernels (causal / cross attention, FFN block modes) and the per-op kernels read the device-resident dropout step, and
+    the shifted target (train.py:130-131) is built inside the graph.  Replays with lr = 0 must reproduce eager gt_train_step."""
+    import ctypes as C
+    import groove_oracle as G
+    from _util import build_model
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    cfg = G.GrooveCfg(32, 16, 64, 1, 2, 27, 27)
+    model, _ = build_model(cfg, dropout=0.25, precision=precision)
+    model.set_seed(21, 0, 0).train()
+    n, steps = 12, 5
+    xs, ys = zip(*[G.det_batch(cfg, n, tag=40 + i) for i in range(steps)])
+    eager = []
+    for i in range(steps):
+        m, _ = model.train_step(xs[i].cuda(), ys[i].cuda(), 0.5)
+        eager.append(m.cpu().numpy().copy())
+    dev = torch.device("cuda")
+    xbuf, ybuf = torch.zeros(n, 32, 27, device=dev), torch.zeros(n, 32, 27, device=dev)
+    grads = torch.zeros_like(model.flat_parameters().detach())
+    metrics, hvo = torch.zeros(6, device=dev), torch.empty(n, 32, 27, device=dev)
+    ws = model._workspace(n, 1, dev)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    ring = torch.zeros(steps, 6, device=dev)
+    handle = C.c_void_p()
+    c = model._cfg()
+    side = torch.cuda.Stream()                  # stream capture is not allowed on the legacy default stream
+    sp = side.cuda_stream
+    torch.cuda.synchronize()
+    _lib.check(lib.gt_graph_train_create(C.byref(c), _lib.ptr(model.flat_parameters()), _lib.ptr(model._pe_flat()), _lib.ptr(xbuf), _lib.ptr(ybuf),
+                                         n, 0.5, _lib.ptr(grads), _lib.ptr(metrics), _lib.ptr(hvo), _lib.ptr(ws), ws.numel(), 0, 0.0, None, None, 21,
+                                         _lib.ptr(counters), None, None, None, _lib.ptr(ring), steps, sp, C.byref(handle)), "gt_graph_train_create")
+    for i in range(steps):
+        with torch.cuda.stream(side):
+            xbuf.copy_(xs[i].cuda()); ybuf.copy_(ys[i].cuda())
+            _lib.check(lib.gt_graph_launch(handle, 1, sp), "gt_graph_launch")
+    torch.cuda.synchronize()
+    _lib.check(lib.gt_graph_destroy(handle), "gt_graph_destroy")
+    np.testing.assert_allclose(ring.cpu().numpy(), np.stack(eager), rtol=2e-5, atol=1e-7)
+    assert int(counters[0]) == steps and len({round(float(v), 6) for v in ring[:, 0]}) == steps

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(E256_THREADS, 1) stem256_kernel(const float *_
                                                                   uint8_t *__restrict__ x_img, const float *__restrict__ dx_tiled,
                                                                   uint8_t *__restrict__ g_img, uint8_t *__restrict__ src_img, int64_t M,
                                                                   int n_tiles, Drop drop, int64_t row0) {
+  drop_resolve(drop);                                // graph replay: key from the device step counter
   constexpr int EP = StemCfg<E>::EP;
   extern __shared__ __align__(16) float esm[];
   float *sWT = esm, *sB = sWT + E * 256, *sPe = sB + 256, *sx = sPe + (BWD ? 0 : 256 * 32);

@@ -850,10 +850,11 @@ int gt_graph_train_create(const gt_config *cfg, float *params, const float *pe, 
                           int64_t ring_slots, void *stream, void **graph_out) {
   GT_TRY(validate_config(cfg));
   GT_CHECK(graph_out && counters && xbuf && ybuf && params && grads && metrics6 && hvo, "gt_graph_train_create: null pointer");
-  // every kernel of these paths derives its dropout keys from the device counter when asked to (drop_resolve); the d_model = 256
-  // fused kernels and the decoder blocks do not yet
-  GT_CHECK(cfg->n_dec == 0 && (!fused_layers(*cfg) || (cfg->d_model == 32 && (cfg->e_src == 16 || cfg->e_src == 27) && cfg->e_tgt == 27)),
-           "gt_graph_train_create: available for encoder-only models on the fused d_model = 32 path, the per-op tcgen05 path and the fp32 path");
+  // every dropout-carrying kernel of every path derives its dropout keys from the device counter when asked to (drop_resolve /
+  // DropArgsView): encoder-only and encoder-decoder models, fp32 and bf16, fused or per-op.  The fused d_model = 32 ends
+  // (edge32.cu) are instantiated for the reference's two input widths.
+  GT_CHECK(!fused_layers(*cfg) || cfg->d_model != 32 || ((cfg->e_src == 16 || cfg->e_src == 27) && cfg->e_tgt == 27),
+           "gt_graph_train_create: the fused d_model = 32 path needs embedding_size_src 16 or 27");
   GT_CHECK(optimizer == 0 || (optimizer == 1 && m && v), "gt_graph_train_create: optimizer must be 0 (SGD) or 1 (Adam, with m and v)");
   GT_CHECK((data_x == nullptr) == (data_y == nullptr) && (data_x == nullptr) == (perm == nullptr),
            "gt_graph_train_create: data_x, data_y and perm come together (or all null)");

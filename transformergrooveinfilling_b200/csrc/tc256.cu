@@ -296,8 +296,10 @@ __device__ __forceinline__ void t256_attn_fwd(const uint8_t *sQKV, uint8_t *sCtx
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int DH>
-__global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T256Args a) {
+template <int DH, bool DEVSTEP = false>
+__global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T256Args a_in) {
+  const DropArgsView<T256Args, DEVSTEP> view(a_in);
+  const T256Args &a = view.a;
   constexpr int G = T256_G, GH = 64 / DH, NS = T256_NS, NHP = (8 * GH) / 16;
   using S = T256FwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -791,6 +793,13 @@ static int t256_launch_fwd(const T256Args &a_in, int grid, cudaStream_t st) {
   static T256Dbg dbg;
   T256Args a = a_in;
   const bool d = dbg.arm(a, st);
+  if (drop_args_devstep(a)) {                // graph replay: dropout keys derived on the device from the step counter
+    GT_CUDA(cudaFuncSetAttribute(t256_layer_fwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256FwdSmem::total));
+    { LaunchScope _ls(KC_TC_LAYER_FWD, st);
+      t256_layer_fwd_kernel<DH, true><<<grid, T256_THREADS, T256FwdSmem::total, st>>>(a); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
+  }
   GT_CUDA(cudaFuncSetAttribute(t256_layer_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256FwdSmem::total));
   { LaunchScope _ls(KC_TC_LAYER_FWD, st);
     t256_layer_fwd_kernel<DH><<<grid, T256_THREADS, T256FwdSmem::total, st>>>(a); }

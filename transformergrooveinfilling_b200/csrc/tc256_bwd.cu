@@ -315,8 +315,10 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
 // =============================================================================================
 // data-gradient kernel
 // =============================================================================================
-template <int DH>
-__global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T256Args a) {
+template <int DH, bool DEVSTEP = false>
+__global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T256Args a_in) {
+  const DropArgsView<T256Args, DEVSTEP> view(a_in);
+  const T256Args &a = view.a;
   constexpr int G = T256_G, GH = 64 / DH, NS = T256_NS;
   using S = T256BwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -702,6 +704,13 @@ static int t256_launch_bwd(const T256Args &a_in, int grid, cudaStream_t st) {
   static T256Dbg dbg;
   T256Args a = a_in;
   const bool d = dbg.arm(a, st);
+  if (drop_args_devstep(a)) {
+    GT_CUDA(cudaFuncSetAttribute(t256_layer_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256BwdSmem::total));
+    { LaunchScope _ls(KC_TC_LAYER_BWD, st);
+      t256_layer_bwd_kernel<DH, true><<<grid, T256_THREADS, T256BwdSmem::total, st>>>(a); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
+  }
   GT_CUDA(cudaFuncSetAttribute(t256_layer_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256BwdSmem::total));
   { LaunchScope _ls(KC_TC_LAYER_BWD, st);
     t256_layer_bwd_kernel<DH><<<grid, T256_THREADS, T256BwdSmem::total, st>>>(a); }

@@ -106,6 +106,7 @@ struct T256Ctx {
     uint32_t thr = drop_threshold(c.dropout);
     if (!train || thr == 0) return d;
     d.thr = thr; d.key = site_key(seed, step, site); d.scale = drop_scale(thr);
+    drop_fill_devstep(d, seed, site);
     return d;
   }
 };

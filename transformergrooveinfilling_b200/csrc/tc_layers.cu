@@ -643,16 +643,12 @@ static int num_sms() {
 
 template <int DH, int MODE = 0>
 static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
-  if (args_devstep(a)) {
-    if constexpr (MODE == 0) {
-      GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      { LaunchScope _ls(KC_TC_LAYER_FWD, st);
-        tc_layer_fwd_kernel<32, DH, 0, true><<<grid, FWD_THREADS, smem, st>>>(a); }
-      GT_CUDA(cudaGetLastError());
-      return 0;
-    } else {
-      GT_FAIL("device-resident dropout step (graph replay) is available for whole encoder layers only");
-    }
+  if (args_devstep(a)) {                     // graph replay: dropout keys derived on the device from the step counter
+    GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LaunchScope _ls(KC_TC_LAYER_FWD, st);
+      tc_layer_fwd_kernel<32, DH, MODE, true><<<grid, FWD_THREADS, smem, st>>>(a); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
   }
   GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_FWD, st);
@@ -786,12 +782,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *g_g2 = g_be1 + D, *g_be2 = g_g2 + D;
   float4 *sEx = reinterpret_cast<float4 *>(smem + sp.stat);     // [2][128 rows][4 parts]: row-statistics exchange (ping-pong)
   int xphase = 0;
-  // sum of a float4 over the four column parts of this token row
+  // sum of a float4 over the four column parts of this token row: only the 4 warps that share these 32 rows (warp & 3 equal)
+  // exchange, behind a 128-thread named barrier instead of a block-wide one (the ping-pong buffers make a second barrier unnecessary)
   auto xsum = [&](const float4 v) -> float4 {
     float4 *buf = sEx + xphase * 512;
     xphase ^= 1;
     buf[row * 4 + part] = v;
-    __syncthreads();
+    named_bar_sync(1 + (warp & 3), 128);
     const float4 p0 = buf[row * 4], p1 = buf[row * 4 + 1], p2 = buf[row * 4 + 2], p3 = buf[row * 4 + 3];
     return make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w));
   };
@@ -1337,15 +1334,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
 template <int DH, int MODE = 0>
 static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_t st) {
   if (args_devstep(a)) {
-    if constexpr (MODE == 0) {
-      GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      { LaunchScope _ls(KC_TC_LAYER_BWD, st);
-        tc_layer_bwd_kernel<32, DH, 0, true><<<grid, BWD_THREADS, smem, st>>>(a); }
-      GT_CUDA(cudaGetLastError());
-      return 0;
-    } else {
-      GT_FAIL("device-resident dropout step (graph replay) is available for whole encoder layers only");
-    }
+    GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LaunchScope _ls(KC_TC_LAYER_BWD, st);
+      tc_layer_bwd_kernel<32, DH, MODE, true><<<grid, BWD_THREADS, smem, st>>>(a); }
+    GT_CUDA(cudaGetLastError());
+    return 0;
   }
   GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_BWD, st);

@@ -181,9 +181,8 @@ class SweepMember:
 
     # ---- CUDA-graph replay: one graph launch per optimizer step --------------------------------------------------------
     def graph_capable(self) -> bool:
-        """True when this member's step can be replayed as a CUDA graph (``gt_graph_train_create``): an encoder-only model with
-        a fused optimizer on the fused d_model = 32 path, the per-op tcgen05 path or the fp32 path (the d_model = 256 fused
-        kernels do not read the device-resident dropout step yet)."""
+        """True when this member's step can be replayed as a CUDA graph (``gt_graph_train_create``): a fused optimizer on any
+        path (fp32, fused d_model = 32 / 256, per-op tcgen05); sweep members are encoder-only like every shipped yaml."""
         from . import _lib
         from .training import FusedAdam, FusedSGD
         import ctypes as C
@@ -196,7 +195,7 @@ class SweepMember:
         kind = _lib.load().gt_path_kind(C.byref(cfg))
         if kind == _lib.PATH_FUSED_D32:
             return m.embedding_size_src in (16, 27)
-        return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC)
+        return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC, _lib.PATH_FUSED_D256)
 
     def _graph_for(self, bsz: int):
         """The captured step for full batches of ``bsz`` rows (built once; rebuilt if lr / precision change)."""
