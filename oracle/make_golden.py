@@ -24,7 +24,7 @@ sys.path.insert(0, "/root/reference")          # the UNMODIFIED reference; must 
 warnings.filterwarnings("ignore")
 
 import groove_oracle as G  # noqa: E402
-from golden_cases import CASES, digest  # noqa: E402
+from golden_cases import CASES, N_TRAJ, digest  # noqa: E402
 from BaseGrooveTransformers.models.transformer import GrooveTransformerEncoder, GrooveTransformer  # noqa: E402
 from BaseGrooveTransformers.models.train import calculate_loss  # noqa: E402
 import BaseGrooveTransformers as _ref  # noqa: E402
@@ -73,13 +73,13 @@ def run_case(name, cfg, n, penalty, lr):
         for k in names:
             out["grad/" + k] = params[k].grad.numpy().copy()
 
-    # loss trajectories: 6 SGD steps and 6 Adam steps from the same start
+    # loss trajectories: N_TRAJ (20) SGD steps and N_TRAJ Adam steps from the same start
     for opt_name in ("sgd", "adam"):
         m2, _ = build_ref(cfg)
         m2.train()
         opt = torch.optim.SGD(m2.parameters(), lr=lr) if opt_name == "sgd" else torch.optim.Adam(m2.parameters(), lr=1e-3)
         traj = []
-        for _ in range(6):
+        for _ in range(N_TRAJ):
             opt.zero_grad()
             r = calculate_loss(fwd(m2), y, bce, mse, penalty)
             r[0].backward()

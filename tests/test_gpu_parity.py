@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import groove_oracle as G
-from golden_cases import CASES, digest
+from golden_cases import CASES, N_TRAJ, digest
 from _util import build_model, grads_by_name, params_by_name, rel_err
 from transformergrooveinfilling_b200 import FusedAdam, FusedSGD, calculate_loss
 
@@ -127,7 +127,7 @@ def test_loss_trajectory_matches_reference(name, opt):
     x, y = [t.cuda() for t in G.det_batch(cfg, n)]
     model.train()
     traj = []
-    for _ in range(6):
+    for _ in range(N_TRAJ):
         o.zero_grad()
         metrics, _ = model.train_step(x, y, pen)
         o.step()
