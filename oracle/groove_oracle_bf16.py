@@ -58,7 +58,7 @@ def path_for(cfg: G.GrooveCfg) -> str:
     if cfg.d_model == 32 and cfg.dim_ff % 16 == 0 and cfg.dim_ff <= 512 and (dh == 1 or dh % 2 == 0):
         if cfg.n_dec == 0 or dh in (2, 4, 8):
             return PATH_FUSED_D32
-    if cfg.d_model == 256 and cfg.n_dec == 0 and dh in (16, 32) and cfg.dim_ff % 64 == 0 and 64 <= cfg.dim_ff <= 512:
+    if cfg.d_model == 256 and cfg.n_dec == 0 and dh in (16, 32, 128) and cfg.dim_ff % 64 == 0 and 64 <= cfg.dim_ff <= 512:
         return PATH_FUSED_D256
     return PATH_PER_OP
 
@@ -188,7 +188,8 @@ class _AttnCore32(torch.autograd.Function):
 
 class _AttnCore(torch.autograd.Function):
     """softmax(q k^T / sqrt(dh)) (dropout) v for heads laid out [N, H, T, dh], with the mma.sync kernels' rounding points.
-    variant 'f': fused kernels (tc_attn32.cuh, tc256.cu / tc256_bwd.cu); 'p': per-op kernel (attn_mma.cu)."""
+    variant 'f': fused kernels (tc_attn32.cuh, tc256.cu / tc256_bwd.cu); 'h': the head_dim 128 units of tc256*.cu (forward as
+    'f'); 'p': per-op kernel (attn_mma.cu)."""
 
     @staticmethod
     def forward(ctx, q, k, v, keep, scale, causal, variant):
@@ -219,6 +220,16 @@ class _AttnCore(torch.autograd.Function):
         ds = p * (dp - delta)
         dsq = bf16(ds * inv_sqrt)
         dq = dsq @ kb
+        if ctx.variant == "h":
+            # head_dim 128 of the fused d_model = 256 kernels (tc256_bwd.cu:t256_attn_bwd128): the backward arithmetic of
+            # tc_attn32.cuh — c * dropped-P and c * dS as bf16 (c = 1/sqrt(dh)), ONE dS fragment feeds dq and dk
+            rc1 = float(np.float32(math.sqrt(dh)))
+            dsq = bf16(ds * inv_sqrt)
+            pdc = p * (ctx.scale * inv_sqrt) if not ctx.has_keep else p * keep.to(p.dtype) * (ctx.scale * inv_sqrt)
+            dq = dsq @ kb
+            dk = (dsq.transpose(-1, -2) @ qs) * (LN2 * rc1)
+            dv = (bf16(pdc).transpose(-1, -2) @ dob) * rc1
+            return dq, dk, dv, None, None, None, None
         if ctx.variant == "f":
             dk = bf16(ds * LN2).transpose(-1, -2) @ qs
         else:
@@ -325,7 +336,7 @@ def _attn_variant(path, dh, causal_or_cross_block=False):
     if path == PATH_FUSED_D32:
         return "g" if dh in (2, 4, 8) else "fp32"
     if path == PATH_FUSED_D256:
-        return "f"
+        return "h" if dh == 128 else "f"
     return "p" if dh in (16, 32, 64, 128) else "fp32"
 
 

@@ -14,6 +14,9 @@ SHAPES = {
     "c4_l2": (G.GrooveCfg(256, 16, 64, 2, 0, 16, 27), 1.0, 0.15),       # InfillingRandom_test_large.yaml, 2 of its 11 layers
     "h8_f128": (G.GrooveCfg(256, 8, 128, 1, 0, 16, 27), 0.5, 0.1),      # head_dim 32, two FFN chunks
     "h16_f192_sym": (G.GrooveCfg(256, 16, 192, 1, 0, 27, 27), 0.7, 0.3),
+    # InfillingKicksAndSnares_training.yaml (C3): 2 heads of 128 — a head spans two 64-column groups (t256_attn128_*, t256_attn_bwd128)
+    "c3_l2": (G.GrooveCfg(256, 2, 512, 2, 0, 16, 27), 0.73, 0.30),
+    "h2_f64": (G.GrooveCfg(256, 2, 64, 1, 0, 16, 27), 0.5, 0.2),
 }
 
 
@@ -45,9 +48,10 @@ def test_train_forward_with_dropout(name):
     assert np.abs(v.cpu().numpy() - rv.numpy()).max() < 2e-2
 
 
-def test_many_tiles_persistent_loop():
+@pytest.mark.parametrize("name", ["c4_l2", "c3_l2"])
+def test_many_tiles_persistent_loop(name):
     """more tiles than SMs: every CTA walks several tiles, exercising every mbarrier phase flip"""
-    cfg, pen, p = SHAPES["c4_l2"]
+    cfg, pen, p = SHAPES[name]
     model, P = build_model(cfg, dropout=0.0, precision="bf16")
     model.eval()
     x, y = G.det_batch(cfg, 4 * 148 * 3 + 2)
@@ -70,7 +74,8 @@ def _worst_grad_err(model, grads):
     return worst
 
 
-@pytest.mark.parametrize("name,n", [("c4_l2", 4), ("c4_l2", 64), ("h8_f128", 5), ("h8_f128", 64), ("h16_f192_sym", 7)])
+@pytest.mark.parametrize("name,n", [("c4_l2", 4), ("c4_l2", 64), ("h8_f128", 5), ("h8_f128", 64), ("h16_f192_sym", 7),
+                                    ("c3_l2", 4), ("c3_l2", 64), ("h2_f64", 7), ("c3_l2", 4 * 148 * 2 + 5)])
 def test_train_step_matches_oracle(name, n):
     cfg, pen, p = SHAPES[name]
     model, P = build_model(cfg, dropout=p, precision="bf16")
@@ -123,7 +128,7 @@ def test_loss_trajectory_bf16_vs_fp32():
     assert traj["fp32"][-1] < traj["fp32"][0]
 
 
-@pytest.mark.parametrize("name,n", [("c4_l2", 6), ("h16_f192_sym", 9)])
+@pytest.mark.parametrize("name,n", [("c4_l2", 6), ("h16_f192_sym", 9), ("c3_l2", 6)])
 def test_autograd_path_equals_fused_step(name, n):
     """model(x) -> calculate_loss -> loss.backward() against the single-call fused step: same layer kernels, different tail
     kernels (edge256.cu: the fused step folds calculate_loss into the tail forward and hands dL/dlogits to the tail backward,

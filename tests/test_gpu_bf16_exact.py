@@ -39,7 +39,10 @@ CASES = {
     "c5_dec_h4_l1": (G.GrooveCfg(32, 4, 64, 1, 1, 27, 27), 0.38, 0.1, 16, GRAD_TOL),
     "c4_l1": (G.GrooveCfg(256, 16, 64, 1, 0, 16, 27), 1.0, 0.15, 16, GRAD_TOL),          # fused d256, head dim 16
     "h8_l1": (G.GrooveCfg(256, 8, 128, 1, 0, 16, 27), 0.5, 0.1, 16, GRAD_TOL),           # fused d256, head dim 32, two FFN chunks
-    "c3_l1": (G.GrooveCfg(256, 2, 512, 1, 0, 16, 27), 0.73, 0.3, 16, GRAD_TOL),          # C3 shape (head dim 128)
+    # C3 shape (fused d256, head dim 128: a head spans two 64-column groups).  512 hidden units x 2048 tokens = 1 M ReLU inputs: a handful
+    # lie within fp32 summation-order noise of 0 and get the other side's mask (tools/diag_c3b.py: the whole error sits in 3 - 5 hidden
+    # units, with or without dropout, at head dim 16 as well); one such flip is 1 / n of that unit's gradient: 5.5e-3 at n = 16, 1.3e-3 here
+    "c3_l1": (G.GrooveCfg(256, 2, 512, 1, 0, 16, 27), 0.73, 0.3, 64, GRAD_TOL),
     "d64_per_op": (G.GrooveCfg(64, 4, 64, 1, 0, 16, 27), 1.0, 0.1, 8, GRAD_TOL),         # per-op path: gemm_tc + attn_mma
     # ---- full depth at batch >= 128: GRAD_TOL
     "c1_n256": (G.GrooveCfg(32, 4, 16, 6, 0, 16, 27), 0.47, 0.18, 256, GRAD_TOL),

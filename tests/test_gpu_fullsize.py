@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 # (config, hit_loss_penalty, dropout, full per-GPU batch of bench.py)
 FULL = {
     "c2": (G.GrooveCfg(32, 16, 512, 6, 0, 16, 27), 0.38, 0.24, 32768),      # InfillingClosedHH_training.yaml (headline)
+    "c3": (G.GrooveCfg(256, 2, 512, 6, 0, 16, 27), 0.73, 0.3, 8192),        # InfillingKicksAndSnares_training.yaml (head dim 128)
     "c4": (G.GrooveCfg(256, 16, 64, 11, 0, 16, 27), 1.0, 0.15, 8192),       # InfillingRandom_test_large.yaml
     "c5_encdec": (G.GrooveCfg(32, 16, 512, 6, 6, 27, 27), 0.38, 0.24, 16384),  # InfillingClosedHH_Symbolic (encoder_only = 0)
 }

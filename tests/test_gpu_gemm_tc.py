@@ -121,8 +121,10 @@ def test_epilogues_match_simt_kernel(m, n, k):
 
 
 SHAPES = {
-    # InfillingKicksAndSnares_training.yaml (C3): d_model 256, 2 heads of 128, FFN 512 — 2 of its 6 layers
+    # InfillingKicksAndSnares_training.yaml (C3): d_model 256, 2 heads of 128, FFN 512 — 2 of its 6 layers.  Round 2: the fused
+    # d_model = 256 kernels cover head dim 128, so C3 left the per-op path; the same shape with 4 heads of 64 still runs per-op
     "c3_l2": (G.GrooveCfg(256, 2, 512, 2, 0, 16, 27), 0.73, 0.30),
+    "d256_h4_l2": (G.GrooveCfg(256, 4, 512, 2, 0, 16, 27), 0.73, 0.30),
     "d64_h4": (G.GrooveCfg(64, 4, 128, 2, 0, 16, 27), 0.5, 0.1),
     "d128_h8_sym": (G.GrooveCfg(128, 8, 96, 1, 0, 27, 27), 0.7, 0.2),
     # InfillingClosedHH_Symbolic_training.yaml with encoder_only = 0 (C5 encoder-decoder), 2 + 2 of its 6 + 6 layers
@@ -147,6 +149,7 @@ def test_path_kind():
     # runner.cu: fused encoder stack + three fused blocks per decoder layer); the other shapes run per-op on gemm_tc
     for k in FUSED_ENCDEC:
         assert kinds.pop(k) == _lib.PATH_FUSED_D32
+    assert kinds.pop("c3_l2") == _lib.PATH_FUSED_D256
     assert set(kinds.values()) == {_lib.PATH_GEMM_TC}, kinds
     m32, _ = build_model(G.GrooveCfg(32, 4, 16, 1, 0, 16, 27), precision="bf16")
     assert lib.gt_path_kind(C.byref(m32._cfg())) == _lib.PATH_FUSED_D32
@@ -192,7 +195,7 @@ def _worst_grad_err(model, grads):
     return worst
 
 
-@pytest.mark.parametrize("name,n", [("c3_l2", 4), ("c3_l2", 64), ("d64_h4", 5), ("d64_h4", 67), ("d128_h8_sym", 64),
+@pytest.mark.parametrize("name,n", [("c3_l2", 4), ("c3_l2", 64), ("d256_h4_l2", 4), ("d256_h4_l2", 64), ("d64_h4", 5), ("d64_h4", 67), ("d128_h8_sym", 64),
                                     ("c5_encdec_l2", 6), ("c5_encdec_l2", 64), ("d64_encdec", 64), ("d32_h8_f16_encdec", 64),
                                     ("d32_h8_f16_encdec", 7), ("d32_h4_f96_encdec", 64), ("d32_h2_encdec", 64),
                                     ("c5_encdec_l2", 4 * 148 + 3)])
@@ -211,7 +214,7 @@ def test_train_step_matches_oracle(name, n):
 
 
 def test_bf16_vs_fp32_same_masks_large_batch():
-    """C3 hyper-parameters (2 layers), 512 sequences, dropout on: the bf16 (gemm_tc) and fp32 (SIMT) paths draw identical masks."""
+    """C3 hyper-parameters (2 layers), 512 sequences, dropout on: the bf16 (fused d_model = 256 kernels, head dim 128) and fp32 (SIMT) paths draw identical masks."""
     cfg, pen, p = SHAPES["c3_l2"]
     x, y = [t.cuda() for t in G.det_batch(cfg, 512)]
     out = {}

@@ -14,7 +14,8 @@ CASES = {
     "h1_simt_attention": (G.GrooveCfg(32, 1, 96, 2, 0, 16, 27), 5, 0.1),
     "c5_encdec_l1": (G.GrooveCfg(32, 16, 64, 1, 1, 27, 27), 5, 0.1),
     "c4_l2_fused_d256": (G.GrooveCfg(256, 16, 64, 2, 0, 16, 27), 4, 0.15),
-    "c3_l1_per_op": (G.GrooveCfg(256, 2, 128, 1, 0, 16, 27), 4, 0.3),
+    "c3_l1_fused_d256_h128": (G.GrooveCfg(256, 2, 128, 1, 0, 16, 27), 4, 0.3),   # head dim 128: attention variant 'h'
+    "d256_h4_per_op": (G.GrooveCfg(256, 4, 128, 1, 0, 16, 27), 4, 0.3),          # head dim 64 has no fused kernel
     "d64_per_op": (G.GrooveCfg(64, 4, 64, 1, 0, 16, 27), 4, 0.1),
 }
 

@@ -11,7 +11,7 @@ bool t256_shape_supported(const gt_config &c, std::string *why) {
   if (c.d_model != 256) return no("t256 kernels are instantiated for d_model=256");
   if (c.n_enc > TC_MAX_LAYERS) return no("more than 16 layers");
   const int dh = c.d_model / c.nhead;
-  if (dh != 16 && dh != 32) return no("d_model=256 tensor-core kernels need head_dim 16 or 32 (nhead 16 or 8)");
+  if (dh != 16 && dh != 32 && dh != 128) return no("d_model=256 tensor-core kernels need head_dim 16, 32 or 128 (nhead 16, 8 or 2)");
   if (c.dim_ff % 64 != 0 || c.dim_ff < 64 || c.dim_ff > 512) return no("d_model=256 tensor-core kernels need dim_feedforward in {64,128,...,512}");
   return true;
 }
@@ -29,10 +29,10 @@ __global__ void t256_prep_kernel(TcPrepArgs a) {
   const int l = blockIdx.y;
   const int F = a.F;
   uint8_t *img = a.img + (size_t)l * a.img_stride + (size_t)blockIdx.z * (a.img_stride / T256_REP);
-  const int nf = t256_fwd_stages(F), nst = nf + t256_bwd_stages(F);
+  const int nf = t256_fwd_stages(F), nst = nf + t256_bwd_stages(F, a.dh);
   const float *Wqkv = a.params + a.w_in[l], *Wo = a.params + a.w_out[l], *W1 = a.params + a.w1[l], *W2 = a.params + a.w2[l];
   for (int st = blockIdx.x; st < nst; st += gridDim.x) {
-    const T256Stage s = st < nf ? t256_fwd_stage(st) : t256_bwd_stage(st - nf, F);
+    const T256Stage s = st < nf ? t256_fwd_stage(st) : t256_bwd_stage(st - nf, F, a.dh);
     uint8_t *dst = img + (size_t)st * T256_STAGE;
     const int kbn = s.K / 8, total = s.N * kbn;
     for (int id = threadIdx.x; id < total; id += blockDim.x) {
@@ -293,6 +293,97 @@ __device__ __forceinline__ void t256_attn_fwd(const uint8_t *sQKV, uint8_t *sCtx
     }
 }
 
+// ---- head_dim 128 (InfillingKicksAndSnares: 2 heads of 128): a head spans TWO 64-column groups ---------------------------
+// One warp owns one unit = 16 query rows (m-tile `half`) of (sequence s, the head the group pair belongs to).  The scores
+// contract over all 128 features, i.e. over both groups: the EVEN group adds its 64-feature partial into the warp's
+// accumulators (kept in registers until the odd group arrives), the ODD group completes them.
+__device__ __forceinline__ void t256_attn128_scores(const uint8_t *sQKV, int s, int half, int lane, float (&sacc)[4][4]) {
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = s * 32 + half * 16 + g;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    const int qc = 16 * kt + 2 * t, kc = 64 + qc;
+    const uint32_t a0 = lds32(sQKV + kmajor_off(r0, qc, 128));
+    const uint32_t a1 = lds32(sQKV + kmajor_off(r0 + 8, qc, 128));
+    const uint32_t a2 = lds32(sQKV + kmajor_off(r0, qc + 8, 128));
+    const uint32_t a3 = lds32(sQKV + kmajor_off(r0 + 8, qc + 8, 128));
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int key = s * 32 + 8 * nt + g;
+      mma16816(sacc[nt], a0, a1, a2, a3, lds32(sQKV + kmajor_off(key, kc, 128)), lds32(sQKV + kmajor_off(key, kc + 8, 128)));
+    }
+  }
+}
+// softmax + dropout of the completed scores -> packed bf16 probability fragments pa[key n-tile][row g / g + 8]
+__device__ __forceinline__ void t256_attn128_probs(float (&sacc)[4][4], uint32_t (&pa)[4][2], int half, int lane, const Drop &dr, uint64_t w_pair) {
+  const int g = lane >> 2, t = lane & 3;
+  float m0 = sacc[0][0], m1 = sacc[0][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { m0 = fmaxf(m0, fmaxf(sacc[nt][0], sacc[nt][1])); m1 = fmaxf(m1, fmaxf(sacc[nt][2], sacc[nt][3])); }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    sacc[nt][0] = ex2_ftz(sacc[nt][0] - m0); sacc[nt][1] = ex2_ftz(sacc[nt][1] - m0);
+    sacc[nt][2] = ex2_ftz(sacc[nt][2] - m1); sacc[nt][3] = ex2_ftz(sacc[nt][3] - m1);
+    s0 += sacc[nt][0] + sacc[nt][1]; s1 += sacc[nt][2] + sacc[nt][3];
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float i0 = dr.scale / s0, i1 = dr.scale / s1;
+  if (dr.thr) {
+    const int q0 = half * 16 + g;
+    const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;            // rows q0 and q0 + 8
+    const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
+    const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t la, ha, lb, hb;
+      hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
+      hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
+      sacc[2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? sacc[2 * np][0] * i0 : 0.f;
+      sacc[2 * np][1] = ((la >> 16) >= dr.thr) ? sacc[2 * np][1] * i0 : 0.f;
+      sacc[2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? sacc[2 * np + 1][0] * i0 : 0.f;
+      sacc[2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? sacc[2 * np + 1][1] * i0 : 0.f;
+      sacc[2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? sacc[2 * np][2] * i1 : 0.f;
+      sacc[2 * np][3] = ((lb >> 16) >= dr.thr) ? sacc[2 * np][3] * i1 : 0.f;
+      sacc[2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? sacc[2 * np + 1][2] * i1 : 0.f;
+      sacc[2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? sacc[2 * np + 1][3] * i1 : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { sacc[nt][0] *= i0; sacc[nt][1] *= i0; sacc[nt][2] *= i1; sacc[nt][3] *= i1; }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { pa[nt][0] = pack_bf16(sacc[nt][0], sacc[nt][1]); pa[nt][1] = pack_bf16(sacc[nt][2], sacc[nt][3]); }
+}
+// O[16 x 64] = P V for 64 value columns: V rows (keys) of sequence s start at column vcol0 of the K-major image `vimg` (R = 128)
+__device__ __forceinline__ void t256_attn128_pv(const uint32_t (&pa)[4][2], const uint8_t *vimg, int vcol0, int s, int lane, float (&oacc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { oacc[i][0] = 0.f; oacc[i][1] = 0.f; oacc[i][2] = 0.f; oacc[i][3] = 0.f; }
+  const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int kt = 0; kt < 2; ++kt) {                  // keys 16 kt .. 16 kt + 15
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {                // value columns 16 np .. 16 np + 15
+      const int key = s * 32 + 16 * kt + (mi & 1) * 8 + rr;
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, vimg + kmajor_off(key, vcol0 + 16 * np + (mi >> 1) * 8, 128));
+      mma16816(oacc[2 * np], pa[2 * kt][0], pa[2 * kt][1], pa[2 * kt + 1][0], pa[2 * kt + 1][1], b[0], b[1]);
+      mma16816(oacc[2 * np + 1], pa[2 * kt][0], pa[2 * kt][1], pa[2 * kt + 1][0], pa[2 * kt + 1][1], b[2], b[3]);
+    }
+  }
+}
+__device__ __forceinline__ void t256_attn128_store_ctx(uint8_t *ctx_buf, const float (&oacc)[8][4], int s, int half, int lane) {
+  const int g = lane >> 2, t = lane & 3, r0 = s * 32 + half * 16 + g;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t *>(ctx_buf + kmajor_off(r0, 8 * nt + 2 * t, 128)) = pack_bf16(oacc[nt][0], oacc[nt][1]);
+    *reinterpret_cast<uint32_t *>(ctx_buf + kmajor_off(r0 + 8, 8 * nt + 2 * t, 128)) = pack_bf16(oacc[nt][2], oacc[nt][3]);
+  }
+}
+
 // =============================================================================================
 // forward
 // =============================================================================================
@@ -300,7 +391,7 @@ template <int DH, bool DEVSTEP = false>
 __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T256Args a_in) {
   const DropArgsView<T256Args, DEVSTEP> view(a_in);
   const T256Args &a = view.a;
-  constexpr int G = T256_G, GH = 64 / DH, NS = T256_NS, NHP = (8 * GH) / 16;
+  constexpr int G = T256_G, GH = DH >= 64 ? 1 : 64 / DH, NS = T256_NS, NHP = DH >= 64 ? 1 : (8 * GH) / 16;
   using S = T256FwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_xready, bar_xfree, bar_qkvfull, bar_qkvfree, bar_ctxready[2],
@@ -475,6 +566,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
       T256_STAMP();
       const int64_t grow = (int64_t)tile * TC_TILE + row;
       // ---- P1: head groups ----
+      float s128[4][4];                                 // head_dim 128: partial scores of the even group (warps 0..7)
       for (int g = 0; g < G; ++g) {
         const uint32_t nq = it * G + (uint32_t)g;
         mbar_wait(&bar_qkvfull, nq & 1u);
@@ -498,7 +590,8 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
           }
         }
         fence_before_sync();
-        if (tid == 0) tma_store_wait_read();                    // bulk stores that were still reading sCtx / sH have drained
+        if (tid == 0) tma_store_wait_read();                    // bulk stores that were still reading sCtx / sH / sQKV have drained
+        if constexpr (DH == 128) fence_async_smem();            // the q | k | v image is bulk-stored below
         named_bar_sync(1, T256_CTHREADS);
         if (tid == 0) mbar_arrive(&bar_qkvfree);
         T256_STAMP();
@@ -506,6 +599,56 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         {
           const uint32_t nb = it * (G / 2) + (uint32_t)(g >> 1);
           mbar_wait(&bar_ctxfree[b], (nb & 1u) ^ 1u);          // the out-projection that read this ctx buffer two groups ago retired
+        }
+        if constexpr (DH == 128) {
+          // ---- a head of 128 = groups (2h, 2h + 1).  Train: the group's q | k | v image is saved for the backward (no recompute there)
+          if (tid == 0 && a.qkv_img) {
+            tma_store_1d(a.qkv_img + ((size_t)tile * G + g) * T256_QKV_GROUP_IMG, sQKV, (uint32_t)T256_QKV_GROUP_IMG);
+            tma_store_commit();
+          }
+          const int us = warp >> 1, uhalf = warp & 1;            // unit of warps 0..7: 16 query rows of sequence us
+          if ((g & 1) == 0) {
+            if (warp < 8) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { s128[i][0] = 0.f; s128[i][1] = 0.f; s128[i][2] = 0.f; s128[i][3] = 0.f; }
+              t256_attn128_scores(sQKV, us, uhalf, lane, s128);
+            }
+            // park the even group's 64 value columns in ctx buffer 0 (free until this head's context is written): the q | k | v
+            // image is overwritten by the odd group before the probabilities exist
+            *reinterpret_cast<uint4 *>(sCtx + kmajor_off(row, part * 16, 128)) = *reinterpret_cast<const uint4 *>(sQKV + kmajor_off(row, 128 + part * 16, 128));
+            *reinterpret_cast<uint4 *>(sCtx + kmajor_off(row, part * 16 + 8, 128)) = *reinterpret_cast<const uint4 *>(sQKV + kmajor_off(row, 128 + part * 16 + 8, 128));
+            if (tid == 0) tma_store_wait_read();                 // the bulk store of this group's q | k | v image has read sQKV: the odd group may overwrite it
+            named_bar_sync(1, T256_CTHREADS);
+            T256_STAMP();
+            continue;                                            // no context yet: both ctxready barriers are raised after the odd group
+          }
+          if (warp < 8) {
+            t256_attn128_scores(sQKV, us, uhalf, lane, s128);
+            const int64_t seq = a.seq0 + (int64_t)tile * 4 + us;
+            const uint64_t w_pair = (uint64_t)((seq * H + (g >> 1)) * 32) * 8u;
+            uint32_t pa[4][2];
+            t256_attn128_probs(s128, pa, uhalf, lane, a.d_attn, w_pair);
+            float oacc[8][4];
+            t256_attn128_pv(pa, sQKV, 128, us, lane, oacc);                 // odd group's value columns: still in the q | k | v image
+            t256_attn128_store_ctx(sCtx + 16384, oacc, us, uhalf, lane);
+            t256_attn128_pv(pa, sCtx, 0, us, lane, oacc);                   // even group's value columns: parked in ctx buffer 0 ...
+            named_bar_sync(2, 256);                                          // ... which every unit has now finished reading
+            t256_attn128_store_ctx(sCtx, oacc, us, uhalf, lane);
+          }
+          if (tid == 0) tma_store_wait_read();                   // (as above: sQKV is rewritten by the next group / the FFN's hidden image)
+          fence_async_smem();
+          named_bar_sync(1, T256_CTHREADS);
+          if (tid == 0) {
+            mbar_arrive(&bar_ctxready[0]);
+            mbar_arrive(&bar_ctxready[1]);
+            if (a.ctx_img) {
+              tma_store_1d(a.ctx_img + (size_t)tile * T256_TILE_IMG + (size_t)(g - 1) * 16384, sCtx, 16384u);
+              tma_store_1d(a.ctx_img + (size_t)tile * T256_TILE_IMG + (size_t)g * 16384, sCtx + 16384, 16384u);
+              tma_store_commit();
+            }
+          }
+          T256_STAMP();
+          continue;
         }
         if (warp < 8 * GH / NHP) {
           int s[NHP], hl[NHP], half[NHP];
@@ -517,7 +660,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
             const int64_t seq = a.seq0 + (int64_t)tile * 4 + s[u];
             w_pair[u] = (uint64_t)((seq * H + (g * GH + hl[u])) * 32) * 8u;      // quad index of (row 0, position 0) of this (sequence, head)
           }
-          t256_attn_fwd<DH, NHP>(sQKV, sCtx + b * 16384, s, hl, half, lane, a.d_attn, w_pair);
+          if constexpr (DH != 128) t256_attn_fwd<DH, NHP>(sQKV, sCtx + b * 16384, s, hl, half, lane, a.d_attn, w_pair);
         }
         fence_async_smem();
         named_bar_sync(1, T256_CTHREADS);
@@ -814,6 +957,7 @@ int t256_layer_fwd(const T256Args &a, cudaStream_t st) {
   switch (a.dh) {
     case 16: return t256_launch_fwd<16>(a, grid, st);
     case 32: return t256_launch_fwd<32>(a, grid, st);
+    case 128: return t256_launch_fwd<128>(a, grid, st);
     default: GT_FAIL("t256_layer_fwd: head dim not instantiated");
   }
 }

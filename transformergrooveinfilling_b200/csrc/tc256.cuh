@@ -79,12 +79,20 @@ __host__ __device__ inline T256Stage t256_fwd_stage(int st) {
   t256_stage_dims(s);
   return s;
 }
-__host__ __device__ inline int t256_bwd_stages(int F) { return 4 * (F / 64) + 8 + 14 * T256_G; }
-__host__ __device__ inline T256Stage t256_bwd_stage(int st, int F) {
+// head_dim 128 (C3: a head spans two 64-column groups): the backward does not recompute q | k | v — the forward saves their bf16
+// group images — so its stream has no type-0 stages: per FFN chunk W2^T x2, W1^T x2 ; Wo^T x8 ; WqkvT(g) x6 for g = 0..G-1
+__host__ __device__ inline int t256_bwd_stages(int F, int dh = 16) { return 4 * (F / 64) + 8 + (dh == 128 ? 6 : 14) * T256_G; }
+__host__ __device__ inline T256Stage t256_bwd_stage(int st, int F, int dh = 16) {
   // per FFN chunk: W2^T x2, W1^T x2 ; Wo^T x8 ; then QKV(0) x8, for g = 1..G-1: QKV(g) x8, WqkvT(g-1) x6 ; WqkvT(G-1) x6
   T256Stage s;
   const int nf = 4 * (F / 64);
   s.b = 0;
+  if (dh == 128 && st >= nf + 8) {
+    const int r0 = st - nf - 8;
+    s.type = 7; s.a = r0 / 6; s.b = r0 % 6;
+    t256_stage_dims(s);
+    return s;
+  }
   if (st < nf) {
     const int c = st / 4, k = st % 4;
     s.a = c;
@@ -103,7 +111,8 @@ __host__ __device__ inline T256Stage t256_bwd_stage(int st, int F) {
   t256_stage_dims(s);
   return s;
 }
-__host__ __device__ inline uint32_t t256_img_bytes(int F) { return (uint32_t)(t256_fwd_stages(F) + t256_bwd_stages(F)) * T256_STAGE; }
+__host__ __device__ inline uint32_t t256_img_bytes(int F, int dh = 16) { return (uint32_t)(t256_fwd_stages(F) + t256_bwd_stages(F, dh)) * T256_STAGE; }
+constexpr int64_t T256_QKV_GROUP_IMG = 128 * 192 * 2;    // bytes of one saved q | k | v group image [128 x 192] (head_dim 128 only)
 
 struct T256Args {
   // activations: the residual stream between layers lives in HBM as bf16 images (tile-padded); gradients as tiled fp32
@@ -111,6 +120,8 @@ struct T256Args {
   uint8_t *x_img_out;                    // forward: layer output
   uint8_t *u1_img, *u2_img;              // pre-LayerNorm sums (written by forward in train mode, read by backward)
   uint8_t *x1_img, *ctx_img, *h_img;     // forward (train): images saved for backward / the weight-gradient kernel
+  uint8_t *qkv_img;                      // head_dim 128 only: the four [128 x 192] q | k | v group images of every tile (q pre-scaled), saved
+                                         // by the forward (train) and read by the backward instead of recomputing them
   // backward
   const float *dy;
   float *dx;

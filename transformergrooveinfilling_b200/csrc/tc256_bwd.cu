@@ -213,6 +213,176 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
   }
 }
 
+// ---- attention backward for one (sequence s, head) pair at head_dim 128; one warp ------------------------------------------
+// The head's 128 features live in TWO scratch images (the even / odd 64-column group): img[half] = [128 x 256] with cols
+// [0,64) q (scaled by log2e/sqrt(dh)), [64,128) k, [128,192) v, [192,256) dO of that group.  Phase A contracts the scores and
+// dP = dO V^T over all 128 features and turns them into the bf16 fragments of c dS and c dropped-P (c = 1/sqrt(dh), the
+// arithmetic of tc_attn32.cuh); phase B walks the features in blocks of 16 columns: dq | dk | dv overwrite q | k | v in place
+// (this warp is the only reader of those rows x columns).  g_b: bias-gradient partials of the two groups, [2][3][64].
+__device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, int s, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
+  constexpr int DH = 128;
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, rr = lane & 7;
+  const float c1 = rsqrtf((float)DH), rc1 = sqrtf((float)DH), ks = dr.scale;
+  const float dk_scale = 0.6931471805599453f * rc1;
+  uint32_t pdp[2][4][2], dsq[2][4][2];                 // [query m-tile][key n-tile][rows g / g + 8]
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = s * 32 + 16 * mt + g;
+    float p[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { p[i][c] = 0.f; dp[i][c] = 0.f; }
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      const uint8_t *im = hf ? imgO : imgE;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const int c0 = 16 * kt + 2 * t;
+        const uint32_t a0 = lds32(im + kmajor_off(r0, c0, 128)), a1 = lds32(im + kmajor_off(r0 + 8, c0, 128));
+        const uint32_t a2 = lds32(im + kmajor_off(r0, c0 + 8, 128)), a3 = lds32(im + kmajor_off(r0 + 8, c0 + 8, 128));
+        const uint32_t o0 = lds32(im + kmajor_off(r0, 192 + c0, 128)), o1 = lds32(im + kmajor_off(r0 + 8, 192 + c0, 128));
+        const uint32_t o2 = lds32(im + kmajor_off(r0, 192 + c0 + 8, 128)), o3 = lds32(im + kmajor_off(r0 + 8, 192 + c0 + 8, 128));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int key = s * 32 + 8 * nt + g;
+          mma16816(p[nt], a0, a1, a2, a3, lds32(im + kmajor_off(key, 64 + c0, 128)), lds32(im + kmajor_off(key, 64 + c0 + 8, 128)));
+          mma16816(dp[nt], o0, o1, o2, o3, lds32(im + kmajor_off(key, 128 + c0, 128)), lds32(im + kmajor_off(key, 128 + c0 + 8, 128)));
+        }
+      }
+    }
+    float m0 = p[0][0], m1 = p[0][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { m0 = fmaxf(m0, fmaxf(p[nt][0], p[nt][1])); m1 = fmaxf(m1, fmaxf(p[nt][2], p[nt][3])); }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      p[nt][0] = ex2_ftz(p[nt][0] - m0); p[nt][1] = ex2_ftz(p[nt][1] - m0);
+      p[nt][2] = ex2_ftz(p[nt][2] - m1); p[nt][3] = ex2_ftz(p[nt][3] - m1);
+      s0 += p[nt][0] + p[nt][1]; s1 += p[nt][2] + p[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = c1 / s0, i1 = c1 / s1;
+    // pd = keep ? E (c ks / rowsum) : 0   (= c x the dropped probability)
+    float pdm[4][4];
+    if (dr.thr) {
+      const int q0 = 16 * mt + g;
+      const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;
+      const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
+      const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
+      const float k0 = i0 * ks, k1 = i1 * ks;
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t la, ha, lb, hb;
+        hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
+        hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
+        pdm[2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? p[2 * np][0] * k0 : 0.f;
+        pdm[2 * np][1] = ((la >> 16) >= dr.thr) ? p[2 * np][1] * k0 : 0.f;
+        pdm[2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][0] * k0 : 0.f;
+        pdm[2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? p[2 * np + 1][1] * k0 : 0.f;
+        pdm[2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? p[2 * np][2] * k1 : 0.f;
+        pdm[2 * np][3] = ((lb >> 16) >= dr.thr) ? p[2 * np][3] * k1 : 0.f;
+        pdm[2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][2] * k1 : 0.f;
+        pdm[2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? p[2 * np + 1][3] * k1 : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { pdm[nt][0] = p[nt][0] * i0; pdm[nt][1] = p[nt][1] * i0; pdm[nt][2] = p[nt][2] * i1; pdm[nt][3] = p[nt][3] * i1; }
+    }
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      dp[nt][0] *= pdm[nt][0]; dp[nt][1] *= pdm[nt][1]; dp[nt][2] *= pdm[nt][2]; dp[nt][3] *= pdm[nt][3];
+      d0 += dp[nt][0] + dp[nt][1];
+      d1 += dp[nt][2] + dp[nt][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    const float e0 = -(d0 * rc1) * i0, e1 = -(d1 * rc1) * i1;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      pdp[mt][nt][0] = pack_bf16(pdm[nt][0], pdm[nt][1]); pdp[mt][nt][1] = pack_bf16(pdm[nt][2], pdm[nt][3]);
+      dsq[mt][nt][0] = pack_bf16(fmaf(p[nt][0], e0, dp[nt][0]), fmaf(p[nt][1], e0, dp[nt][1]));
+      dsq[mt][nt][1] = pack_bf16(fmaf(p[nt][2], e1, dp[nt][2]), fmaf(p[nt][3], e1, dp[nt][3]));
+    }
+  }
+  __syncwarp();                                         // every lane has finished phase A: the images may be overwritten block by block
+  // ---- phase B: 16 feature columns at a time ----
+#pragma unroll 1
+  for (int blk = 0; blk < 8; ++blk) {
+    uint8_t *im = blk >= 4 ? imgO : imgE;
+    const int cq = (blk & 3) * 16;                      // column of the block inside its group: q at cq, k at 64 + cq, v at 128 + cq, dO at 192 + cq
+    float dq[2][2][4], dk[2][2][4], dv[2][2][4];        // [m-tile][n-tile of the block][4]
+#pragma unroll
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { dq[a2][b2][c] = 0.f; dk[a2][b2][c] = 0.f; dv[a2][b2][c] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {                    // contraction index 16 kt .. 16 kt + 15: keys for dq, queries for dk / dv
+      const int rowk = s * 32 + 16 * kt + (mi & 1) * 8 + rr;
+      uint32_t bk[4], bq[4], bo[4];
+      ldmatrix_x4_trans(bk, im + kmajor_off(rowk, 64 + cq + (mi >> 1) * 8, 128));
+      ldmatrix_x4_trans(bq, im + kmajor_off(rowk, cq + (mi >> 1) * 8, 128));
+      ldmatrix_x4_trans(bo, im + kmajor_off(rowk, 192 + cq + (mi >> 1) * 8, 128));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {                  // dq rows = queries of m-tile mt, contraction over keys 16 kt ..
+        mma16816(dq[mt][0], dsq[mt][2 * kt][0], dsq[mt][2 * kt][1], dsq[mt][2 * kt + 1][0], dsq[mt][2 * kt + 1][1], bk[0], bk[1]);
+        mma16816(dq[mt][1], dsq[mt][2 * kt][0], dsq[mt][2 * kt][1], dsq[mt][2 * kt + 1][0], dsq[mt][2 * kt + 1][1], bk[2], bk[3]);
+      }
+#pragma unroll
+      for (int kmt = 0; kmt < 2; ++kmt) {               // dk / dv rows = keys of m-tile kmt, contraction over the queries of m-tile kt
+        const uint32_t s0t = movmatrix_trans(dsq[kt][2 * kmt][0]), s1t = movmatrix_trans(dsq[kt][2 * kmt + 1][0]);
+        const uint32_t s2t = movmatrix_trans(dsq[kt][2 * kmt][1]), s3t = movmatrix_trans(dsq[kt][2 * kmt + 1][1]);
+        mma16816(dk[kmt][0], s0t, s1t, s2t, s3t, bq[0], bq[1]);
+        mma16816(dk[kmt][1], s0t, s1t, s2t, s3t, bq[2], bq[3]);
+        const uint32_t p0t = movmatrix_trans(pdp[kt][2 * kmt][0]), p1t = movmatrix_trans(pdp[kt][2 * kmt + 1][0]);
+        const uint32_t p2t = movmatrix_trans(pdp[kt][2 * kmt][1]), p3t = movmatrix_trans(pdp[kt][2 * kmt + 1][1]);
+        mma16816(dv[kmt][0], p0t, p1t, p2t, p3t, bo[0], bo[1]);
+        mma16816(dv[kmt][1], p0t, p1t, p2t, p3t, bo[2], bo[3]);
+      }
+    }
+    __syncwarp();                                       // all lanes have read this block's q / k / dO columns
+    float *gb = g_b + (blk >= 4 ? 192 : 0);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      float sq0 = 0.f, sq1 = 0.f, sk0 = 0.f, sk1 = 0.f, sv0 = 0.f, sv1 = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = s * 32 + 16 * mt + g, col = cq + 8 * nt + 2 * t;
+        const float k0 = dk[mt][nt][0] * dk_scale, k1 = dk[mt][nt][1] * dk_scale, k2 = dk[mt][nt][2] * dk_scale, k3 = dk[mt][nt][3] * dk_scale;
+        const float v0 = dv[mt][nt][0] * rc1, v1 = dv[mt][nt][1] * rc1, v2 = dv[mt][nt][2] * rc1, v3 = dv[mt][nt][3] * rc1;
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0, col, 128)) = pack_bf16(dq[mt][nt][0], dq[mt][nt][1]);
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0 + 8, col, 128)) = pack_bf16(dq[mt][nt][2], dq[mt][nt][3]);
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0, 64 + col, 128)) = pack_bf16(k0, k1);
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0 + 8, 64 + col, 128)) = pack_bf16(k2, k3);
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0, 128 + col, 128)) = pack_bf16(v0, v1);
+        *reinterpret_cast<uint32_t *>(im + kmajor_off(r0 + 8, 128 + col, 128)) = pack_bf16(v2, v3);
+        sq0 += dq[mt][nt][0] + dq[mt][nt][2]; sq1 += dq[mt][nt][1] + dq[mt][nt][3];
+        sk0 += k0 + k2; sk1 += k1 + k3; sv0 += v0 + v2; sv1 += v1 + v3;
+      }
+      // in-projection bias gradient: column sums over the pair's 32 rows (lanes with equal t hold the same columns)
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        sq0 += __shfl_xor_sync(0xffffffffu, sq0, o); sq1 += __shfl_xor_sync(0xffffffffu, sq1, o);
+        sk0 += __shfl_xor_sync(0xffffffffu, sk0, o); sk1 += __shfl_xor_sync(0xffffffffu, sk1, o);
+        sv0 += __shfl_xor_sync(0xffffffffu, sv0, o); sv1 += __shfl_xor_sync(0xffffffffu, sv1, o);
+      }
+      if (g == 0) {
+        const int col = cq + 8 * nt + 2 * t;
+        atomicAdd(gb + col, sq0); atomicAdd(gb + col + 1, sq1);
+        atomicAdd(gb + 64 + col, sk0); atomicAdd(gb + 64 + col + 1, sk1);
+        atomicAdd(gb + 128 + col, sv0); atomicAdd(gb + 128 + col + 1, sv1);
+      }
+    }
+  }
+}
+
 // ---- LayerNorm backward over a [128 x 256] tile; thread = (row, 64-column part) ----------------------------------
 // dyv(cb, out16): loads 16 values of the incoming gradient for columns part*64 + cb..  (re-readable)
 // Writes du (tiled fp32 -> park) and da = du * dropmask (bf16 -> sImg and gImg); accumulates dgamma / dbeta / dbias partials.
@@ -319,7 +489,8 @@ template <int DH, bool DEVSTEP = false>
 __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T256Args a_in) {
   const DropArgsView<T256Args, DEVSTEP> view(a_in);
   const T256Args &a = view.a;
-  constexpr int G = T256_G, GH = 64 / DH, NS = T256_NS;
+  constexpr int G = T256_G, GH = DH >= 64 ? 1 : 64 / DH, NS = T256_NS;
+  constexpr bool H128 = DH == 128;                   // a head spans two groups: q | k | v come from the forward's saved images, no recompute
   using S = T256BwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_da2ready, bar_hready, bar_hfree, bar_dhfull, bar_dhimgready, bar_r2a,
@@ -353,7 +524,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
   const uint32_t t_dx = tmem, t_b = tmem + 256;
   const uint32_t aR1 = smem_u32(sR1), aR2 = smem_u32(sR2), aRing = smem_u32(sRing);
   const int nfs = 4 * NCH;                          // FFN stages per tile
-  const uint32_t uses_per_tile = (uint32_t)(16 + NCH);   // (64 + 4 NCH) / NS
+  const uint32_t uses_per_tile = H128 ? (uint32_t)(8 + NCH) : (uint32_t)(16 + NCH);   // stages per tile / NS: (64 + 4 NCH) / 4, head_dim 128: (32 + 4 NCH) / 4
   const uint8_t *wimg = a.img + (size_t)(blockIdx.x % T256_REP) * a.img_rep_stride + (size_t)t256_fwd_stages(F) * T256_STAGE;
 
   if (warp == 16) {
@@ -376,6 +547,12 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           tma_load_1d(sR2, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) stage(4 * c + j, 16384u);
+        }
+        if constexpr (H128) {
+          // no x image and no q | k | v recompute stages: Wo^T x8, then WqkvT(g) x6 for the four groups
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) stage(nfs + j, 16384u);
+          continue;
         }
         mbar_wait(&bar_r2a, it & 1u);                          // dx1 of the last FFN chunk retired: r2 is free for the x image
         mbar_expect_tx(&bar_xready, 65536u);
@@ -449,6 +626,30 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           mma_commit(&bar_empty[st % NS]);
         }
         mma_commit(&bar_dctxfull);
+        if constexpr (H128) {
+          // ---- attention backward, per HEAD: the dq | dk | dv images of its two groups sit in r1 (even) and r2 (odd) ----
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&bar_dqkvready, (it * 2u + (uint32_t)h) & 1u);
+            fence_after_sync();
+            for (int e = 0; e < 2; ++e) {
+              const int gg = 2 * h + e;
+              const uint64_t dA = e ? dR2 : dR1;
+#pragma unroll 2
+              for (int b = 0; b < 6; ++b) {
+                const int st = nfs + 8 + gg * 6 + b;
+                full_wait(st);
+                const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  mma_bf16_ss(t_dx, desc_adv(dA, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (gg | b | k) > 0);
+                mma_commit(&bar_empty[st % NS]);
+              }
+            }
+            mma_commit(&bar_dqkvfree);
+          }
+          mma_commit(&bar_dxinfull);                      // (bar_r2b is raised by the compute warps: the bulk stores of dq | dk | dv read r2 too)
+          continue;
+        }
         // ---- attention backward, per head group ----
         mbar_wait(&bar_xready, it & 1u);
         fence_after_sync();
@@ -604,8 +805,50 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       __threadfence_block();
       fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
-      if (tid == 0) mbar_arrive(&bar_qkvfree);
+      if (tid == 0 && !H128) mbar_arrive(&bar_qkvfree);
       T256_STAMP();
+      if constexpr (H128) {
+        // ---- B6 (head_dim 128): per head, stage q | k | v (saved by the forward) and dO (from this CTA's dctx scratch) of its two
+        // groups into r1 (even group) and r2 (odd group), attention backward in place, hand both dq | dk | dv images to the issuer ----
+        for (int h = 0; h < 2; ++h) {
+          if (h >= 1) mbar_wait(&bar_dqkvfree, (it * 2u) & 1u);   // dx_in of head 0 no longer reads r1 / r2
+          if (tid == 0) tma_store_wait_read();                     // ... nor do the bulk stores of its dq | dk | dv slices
+          named_bar_sync(1, T256_CTHREADS);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int gg = 2 * h + e;
+            uint8_t *dst = e ? sR2 : sR1;
+            const uint8_t *qg = a.qkv_img + ((size_t)tile * G + gg) * T256_QKV_GROUP_IMG;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+              *reinterpret_cast<uint4 *>(dst + (size_t)(i * T256_CTHREADS + tid) * 16) = __ldg(reinterpret_cast<const uint4 *>(qg + (size_t)(i * T256_CTHREADS + tid) * 16));
+            *reinterpret_cast<uint4 *>(dst + 49152 + (size_t)tid * 16) = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)gg * 16384 + (size_t)tid * 16));
+            *reinterpret_cast<uint4 *>(dst + 49152 + 8192 + (size_t)tid * 16) = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)gg * 16384 + 8192 + (size_t)tid * 16));
+          }
+          named_bar_sync(1, T256_CTHREADS);
+          T256_STAMP();
+          if (warp < 4) {
+            const int64_t seq = a.seq0 + (int64_t)tile * 4 + warp;
+            const uint64_t w_pair = (uint64_t)((seq * H + h) * 32) * 8u;
+            t256_attn_bwd128(sR1, sR2, warp, lane, a.d_attn, w_pair, g_bqkv + (2 * h) * 192);
+          }
+          fence_async_smem();
+          named_bar_sync(1, T256_CTHREADS);
+          if (tid == 0) {
+            mbar_arrive(&bar_dqkvready);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const uint8_t *src = e ? sR2 : sR1;
+              uint8_t *dq_g = a.dqkv_img + (size_t)tile * (3 * T256_TILE_IMG) + (size_t)(2 * h + e) * 16384;
+              tma_store_1d(dq_g, src, 16384u);
+              tma_store_1d(dq_g + T256_TILE_IMG, src + 16384, 16384u);
+              tma_store_1d(dq_g + 2 * T256_TILE_IMG, src + 32768, 16384u);
+            }
+            tma_store_commit();
+          }
+          T256_STAMP();
+        }
+      } else
       // ---- B6: head groups ----
       for (int g = 0; g < G; ++g) {
         const uint32_t n = it * G + (uint32_t)g;
@@ -642,7 +885,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           const int s = warp / GH, hl = warp % GH;
           const int64_t seq = a.seq0 + (int64_t)tile * 4 + s;
           const uint64_t w_pair = (uint64_t)((seq * H + (g * GH + hl)) * 32) * 8u;     // quad index of (row 0, position 0)
-          t256_attn_bwd<DH>(sR1, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
+          if constexpr (!H128) t256_attn_bwd<DH>(sR1, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
         }
         fence_async_smem();
         named_bar_sync(1, T256_CTHREADS);
@@ -673,7 +916,10 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           *reinterpret_cast<float4 *>(dx_t + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4) =
               make_float4(pv[j].x + f[4 * j], pv[j].y + f[4 * j + 1], pv[j].z + f[4 * j + 2], pv[j].w + f[4 * j + 3]);
       }
-      if (tid == 0) tma_store_wait_read();
+      if (tid == 0) {
+        tma_store_wait_read();
+        if constexpr (H128) mbar_arrive(&bar_r2b);      // dx_in has retired (bar_dxinfull) and the dq | dk | dv bulk stores no longer read r2
+      }
       fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
       T256_STAMP();
@@ -726,6 +972,9 @@ int t256_layer_bwd(const T256Args &a, cudaStream_t st) {
   switch (a.dh) {
     case 16: return t256_launch_bwd<16>(a, grid, st);
     case 32: return t256_launch_bwd<32>(a, grid, st);
+    case 128:
+      GT_CHECK(a.qkv_img != nullptr, "t256_layer_bwd: head_dim 128 needs the q | k | v images saved by the forward");
+      return t256_launch_bwd<128>(a, grid, st);
     default: GT_FAIL("t256_layer_bwd: head dim not instantiated");
   }
 }

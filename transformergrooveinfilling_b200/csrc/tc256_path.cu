@@ -16,6 +16,7 @@ struct T256Plan {
   uint8_t *ximg[TC_MAX_LAYERS + 1];               // bf16 images of the residual stream
   uint8_t *u1img[TC_MAX_LAYERS], *u2img[TC_MAX_LAYERS];
   uint8_t *x1img[TC_MAX_LAYERS], *ctximg[TC_MAX_LAYERS], *himg[TC_MAX_LAYERS];
+  uint8_t *qkvimg[TC_MAX_LAYERS];                 // head_dim 128: saved q | k | v group images
   float *d_hvo, *loss_partials, *dlog, *dxrm, *dxrm2, *g0, *dxa, *dxb;
   uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch, *wg_jobs;
   float *park_scratch;
@@ -41,7 +42,8 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
     return base ? base + o : nullptr;
   };
   P.n_tiles = n_tiles;
-  P.img_stride = ((t256_img_bytes(c.dim_ff) + 255u) & ~255u) * T256_REP;
+  const int dh = c.d_model / c.nhead;
+  P.img_stride = ((t256_img_bytes(c.dim_ff, dh) + 255u) & ~255u) * T256_REP;
   P.img = reinterpret_cast<uint8_t *>(take((int64_t)P.img_stride * c.n_enc));
   const bool train = mode == 1;
   const bool fused = t256_fused_edges(c);
@@ -61,6 +63,7 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
       P.x1img[l] = reinterpret_cast<uint8_t *>(take(ti));
       P.ctximg[l] = reinterpret_cast<uint8_t *>(take(ti));
       P.himg[l] = reinterpret_cast<uint8_t *>(take(th));
+      if (dh == 128) P.qkvimg[l] = reinterpret_cast<uint8_t *>(take((int64_t)n_tiles * T256_G * T256_QKV_GROUP_IMG));
     }
     if (!fused) P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
     P.loss_partials = reinterpret_cast<float *>(take((loss_scratch_floats(n_seq) + edge256_loss_partials()) * 4));
@@ -155,7 +158,7 @@ static int t256_prep(const T256Ctx &x, const T256Plan &pl) {
   TcPrepArgs a;
   memset(&a, 0, sizeof(a));
   a.params = x.P; a.img = pl.img; a.img_stride = pl.img_stride; a.n_layers = x.c.n_enc;
-  a.D = x.c.d_model; a.F = x.c.dim_ff; a.FC = 64;
+  a.D = x.c.d_model; a.F = x.c.dim_ff; a.FC = 64; a.dh = x.c.d_model / x.c.nhead;
   for (int l = 0; l < x.c.n_enc; ++l) {
     a.w_in[l] = x.L->enc[l].sa.w_in; a.w_out[l] = x.L->enc[l].sa.w_out; a.w1[l] = x.L->enc[l].w1; a.w2[l] = x.L->enc[l].w2;
   }
@@ -181,7 +184,7 @@ static int t256_forward_all(const T256Ctx &x, const T256Plan &pl, const float *s
   for (int l = 0; l < L; ++l) {
     T256Args a = t256_layer_args(x, pl, l);
     a.x_img_in = pl.ximg[l]; a.x_img_out = pl.ximg[l + 1];
-    if (save) { a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; }
+    if (save) { a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; a.qkv_img = pl.qkvimg[l]; }
     GT_TRY(t256_layer_fwd(a, x.st));
   }
   if (fused)
@@ -228,7 +231,7 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
     const LayerP &p = x.L->enc[l];
     T256Args a = t256_layer_args(x, pl, l);
     a.x_img_in = pl.ximg[l]; a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.dy = cur; a.dx = oth;
-    a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l];
+    a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; a.qkv_img = pl.qkvimg[l];
     a.da2_img = pl.da2img; a.da1_img = pl.da1img; a.dh_img = pl.dhimg; a.dqkv_img = pl.dqkvimg; a.dctx_scratch = pl.dctx_scratch; a.park_scratch = pl.park_scratch;
     GT_TRY(t256_layer_bwd(a, x.st));
     T256WgradArgs w;

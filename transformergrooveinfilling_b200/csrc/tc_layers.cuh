@@ -45,6 +45,7 @@ struct TcPrepArgs {
   int64_t w_in[TC_MAX_LAYERS], w_out[TC_MAX_LAYERS], w1[TC_MAX_LAYERS], w2[TC_MAX_LAYERS], b1[TC_MAX_LAYERS];
   uint32_t img_stride;
   int n_layers, D, F, FC;
+  int dh;                              // d_model = 256 streams only: head dim (128 selects the backward stream without q | k | v recompute)
 };
 
 struct TcLayerArgs {
