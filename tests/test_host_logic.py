@@ -165,17 +165,21 @@ def test_graph_entry_points_validate_their_arguments_before_any_launch():
     assert lib.gt_graph_destroy(None) == 0
     handle = C.c_void_p()
     fp32 = _lib.GtConfig(32, 4, 16, 1, 0, 16, 27, _lib.PREC_FP32, 0.1, 0)
-    # null buffers are refused first; a configuration off the fused d_model = 32 encoder-only path is refused by name
+    # null buffers are refused first; every path is capturable, so what stops the other calls is the workspace check of their own path
     assert lib.gt_graph_train_create(C.byref(fp32), None, None, None, None, 4, 0.5, None, None, None, None, 0, 0, 0.1, None, None, 1,
                                      None, None, None, None, None, 0, None, C.byref(handle)) != 0
     assert b"null pointer" in lib.gt_last_error() and not handle.value
-    one = C.c_void_p(16)        # any non-null address: validation stops at the path check, nothing is dereferenced
-    d256 = _lib.GtConfig(256, 16, 64, 1, 0, 16, 27, _lib.PREC_BF16, 0.1, 0)        # fused d_model = 256 path: not capturable yet
-    encdec = _lib.GtConfig(32, 4, 16, 1, 1, 16, 27, _lib.PREC_BF16, 0.1, 0)
-    for cfg in (d256, encdec):
+    one = C.c_void_p(16)        # any non-null address: validation stops at the (misaligned) workspace, nothing is dereferenced
+    d256 = _lib.GtConfig(256, 16, 64, 1, 0, 16, 27, _lib.PREC_BF16, 0.1, 0)        # fused d_model = 256 path
+    encdec = _lib.GtConfig(32, 4, 16, 1, 1, 16, 27, _lib.PREC_BF16, 0.1, 0)        # encoder-decoder on the fused d_model = 32 path
+    for cfg in (d256, encdec, fp32):
         assert lib.gt_graph_train_create(C.byref(cfg), one, one, one, one, 4, 0.5, one, one, one, one, 1 << 20, 0, 0.1, None, None, 1,
                                          one, None, None, None, None, 0, None, C.byref(handle)) != 0
-        assert b"available for encoder-only models" in lib.gt_last_error() and not handle.value
+        assert b"256-byte aligned" in lib.gt_last_error() and not handle.value
+    # Adam without its moment vectors is refused by name
+    assert lib.gt_graph_train_create(C.byref(d256), one, one, one, one, 4, 0.5, one, one, one, one, 1 << 20, 1, 0.1, None, None, 1,
+                                     one, None, None, None, None, 0, None, C.byref(handle)) != 0
+    assert b"optimizer must be" in lib.gt_last_error() and not handle.value
 
 
 def test_input_pipelines_refuse_a_cpu_device():

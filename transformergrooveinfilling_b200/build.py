@@ -18,6 +18,14 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
 
+# Developer builds (e.g. GROOVE_B200_DEV_FLAGS="-DGT_T256_TIMELINE" for the clock64 phase time line of tc256*.cu) go to their own
+# library / object directory, so the release library is never replaced by one that allocates its own debug buffers.
+_DEV = os.environ.get("GROOVE_B200_DEV_FLAGS", "").split()
+if _DEV:
+    LIB = os.path.join(HERE, "libgroove_b200_dev.so")
+    STAMP = LIB + ".stamp"
+    NVCC_FLAGS = NVCC_FLAGS + _DEV
+
 
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
@@ -43,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     objs = []
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, "build_dev" if _DEV else "build")
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for s in SOURCES:
