@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
   using S = T256FwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_xready, bar_xfree, bar_qkvfull, bar_qkvfree, bar_ctxready[2],
-      bar_ctxfree[2], bar_outfull, bar_x1ready, bar_hfull, bar_hready, bar_out2full;
+      bar_ctxfree[2], bar_outfull, bar_x1ready, bar_hfull[2], bar_hready[2], bar_out2full;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = a.F, NCH = F / 64, H = a.H;
@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
     for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
     mbar_init(&bar_xready, 1); mbar_init(&bar_xfree, 1); mbar_init(&bar_qkvfull, 1); mbar_init(&bar_qkvfree, 1);
     mbar_init(&bar_ctxready[0], 1); mbar_init(&bar_ctxready[1], 1); mbar_init(&bar_ctxfree[0], 1); mbar_init(&bar_ctxfree[1], 1);
-    mbar_init(&bar_outfull, 1); mbar_init(&bar_x1ready, 1); mbar_init(&bar_hfull, 1); mbar_init(&bar_hready, 1); mbar_init(&bar_out2full, 1);
+    mbar_init(&bar_outfull, 1); mbar_init(&bar_x1ready, 1); mbar_init(&bar_hfull[0], 1); mbar_init(&bar_hfull[1], 1);
+    mbar_init(&bar_hready[0], 1); mbar_init(&bar_hready[1], 1); mbar_init(&bar_out2full, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < 768; i += T256_THREADS) p_bqkv[i] = a.bqkv[i];
@@ -422,7 +423,10 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_out = tmem, t_qkv = tmem + 256, t_h = tmem + 448;
+  // FFN chunks alternate between two (hidden accumulator, H image) slots: chunk n = it * NCH + c uses slot n & 1 — accumulator columns
+  // 448.. / 256.. (the q | k | v accumulator is idle during the FFN), image at sH + slot * 16384 (sH aliases the 48 KB q | k | v image)
+  const uint32_t t_out = tmem, t_qkv = tmem + 256;
+  auto t_h_slot = [&](uint32_t fs) { return fs ? tmem + 256u : tmem + 448u; };
   const uint32_t aX = smem_u32(sX), aRing = smem_u32(sRing), aH = smem_u32(sH), aCtx = smem_u32(sCtx);
 
   if (warp == 16) {
@@ -466,7 +470,8 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
     // ======================= MMA issuer: one elected lane runs the whole program =======================
     if (elect_one()) {
       const uint32_t id_qkv = make_idesc_bf16(128, 192), id_256 = make_idesc_bf16(128, 256), id_64 = make_idesc_bf16(128, 64);
-      const uint64_t dX = descA128(aX), dH = descA128(aH);
+      const uint64_t dX = descA128(aX);
+      const uint64_t dH = descA128(aH);
       const uint64_t dC[2] = {descA128(aCtx), descA128(aCtx + 16384u)};
       const uint64_t dR192 = descB(aRing, 192), dR256 = descB(aRing, 256), dR64 = descB(aRing, 64);   // slot 0; slot j adds j * STAGE
       uint32_t it = 0, nstamp = 0;
@@ -522,22 +527,26 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         mbar_wait(&bar_x1ready, it & 1u);
         fence_after_sync();
         auto ffn1 = [&](int c) {
+          const uint32_t fs = (it * (uint32_t)NCH + (uint32_t)c) & 1u;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             full_wait(hf, use0 + 10u + (uint32_t)c);
             const uint64_t db = desc_adv(dR64, (uint32_t)hf * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              mma_bf16_ss(t_h, desc_adv(dX, (uint32_t)(hf * 8 + k) * 4096u), desc_adv(db, (uint32_t)k * 2048u), id_64, (hf | k) > 0);
+              mma_bf16_ss(t_h_slot(fs), desc_adv(dX, (uint32_t)(hf * 8 + k) * 4096u), desc_adv(db, (uint32_t)k * 2048u), id_64, (hf | k) > 0);
             mma_commit(&bar_empty[hf]);
           }
-          mma_commit(&bar_hfull);
+          mma_commit(&bar_hfull[fs]);
           if (c + 1 == NCH) mma_commit(&bar_xfree);        // sX may be refilled with the next tile's x image
         };
+        // FFN1 of chunk c + 1 is issued BEFORE the issuer waits for the H image of chunk c (other accumulator / image slot), so the
+        // hidden-activation epilogue overlaps the tensor work of its neighbours; ring slots 0, 1 (W1) run one use ahead of 2, 3 (W2)
         ffn1(0);
         for (int c = 0; c < NCH; ++c) {
-          const uint32_t nh = it * (uint32_t)NCH + (uint32_t)c;
-          mbar_wait(&bar_hready, nh & 1u);
+          const uint32_t nh = it * (uint32_t)NCH + (uint32_t)c, fs = nh & 1u;
+          if (c + 1 < NCH) ffn1(c + 1);
+          mbar_wait(&bar_hready[fs], (nh >> 1) & 1u);
           fence_after_sync();
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -545,10 +554,9 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
             const uint64_t db = desc_adv(dR256, (uint32_t)(2 + hf) * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              mma_bf16_ss(t_out, desc_adv(dH, (uint32_t)(hf * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (c | hf | k) > 0);
+              mma_bf16_ss(t_out, desc_adv(dH, fs * 16384u + (uint32_t)(hf * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (c | hf | k) > 0);
             mma_commit(&bar_empty[2 + hf]);
           }
-          if (c + 1 < NCH) ffn1(c + 1);
         }
         mma_commit(&bar_out2full);
       }
@@ -730,6 +738,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         named_bar_sync(1, T256_CTHREADS);
         const float4 sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
         const float rs = rsqrtf(((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256) + LN_EPS);
+        if (part == 0 && a.ln1_stat) a.ln1_stat[grow] = make_float2(mu, rs);      // the backward takes the row statistics from here
         const float *g1 = p_g1 + part * 64, *be1 = p_be1 + part * 64;
         uint8_t *x1g = a.x1_img ? a.x1_img + (size_t)tile * T256_TILE_IMG : nullptr;
 #pragma unroll
@@ -749,45 +758,46 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
       T256_STAMP();
       // ---- P3: FFN hidden chunks: + bias, ReLU, dropout -> bf16 H image ----
       for (int c = 0; c < NCH; ++c) {
-        const uint32_t nh = it * (uint32_t)NCH + (uint32_t)c;
-        mbar_wait(&bar_hfull, nh & 1u);
+        const uint32_t nh = it * (uint32_t)NCH + (uint32_t)c, fs = nh & 1u;
+        uint8_t *sHs = sH + fs * 16384u;
+        mbar_wait(&bar_hfull[fs], (nh >> 1) & 1u);
         fence_after_sync();
         T256_STAMP();
         float v[16];
-        tmem_ld16(t_h + lane_off + (uint32_t)(part * 16), v);
+        tmem_ld16(t_h_slot(fs) + lane_off + (uint32_t)(part * 16), v);
         tmem_ld_wait();
         const uint64_t w0 = (uint64_t)((a.seq0 * 32 + grow) * F + c * 64 + part * 16) >> 2;
         const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
         const float *b1 = p_b1 + c * 64 + part * 16;
+        // ReLU fused into the bf16 conversion, two dropout decisions per packed half-precision compare (umma.cuh: keep2);
+        // relu((v + b) s) = relu(v + b) s for s > 0, one rounding either way
+        const float hs = a.d_ffn.thr ? a.d_ffn.scale : 1.f;
+        const uint32_t thr2 = a.d_ffn.thr | (a.d_ffn.thr << 16);
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          float h0 = fmaxf(v[j] + b1[j], 0.f), h1 = fmaxf(v[j + 1] + b1[j + 1], 0.f);
-          float h2 = fmaxf(v[j + 2] + b1[j + 2], 0.f), h3 = fmaxf(v[j + 3] + b1[j + 3], 0.f);
+          const float4 bb = *reinterpret_cast<const float4 *>(b1 + j);
+          pk[j >> 1] = pack_bf16_relu((v[j] + bb.x) * hs, (v[j + 1] + bb.y) * hs);
+          pk[(j >> 1) + 1] = pack_bf16_relu((v[j + 2] + bb.z) * hs, (v[j + 3] + bb.w) * hs);
           if (a.d_ffn.thr) {
             uint32_t lo, hi;
             hash_quad((wlo + (uint32_t)(j >> 2)) ^ xhi, a.d_ffn.key, lo, hi);
-            h0 = ((lo & 0xFFFFu) >= a.d_ffn.thr) ? h0 * a.d_ffn.scale : 0.f;
-            h1 = ((lo >> 16) >= a.d_ffn.thr) ? h1 * a.d_ffn.scale : 0.f;
-            h2 = ((hi & 0xFFFFu) >= a.d_ffn.thr) ? h2 * a.d_ffn.scale : 0.f;
-            h3 = ((hi >> 16) >= a.d_ffn.thr) ? h3 * a.d_ffn.scale : 0.f;
+            pk[j >> 1] &= keep2(lo, thr2);
+            pk[(j >> 1) + 1] &= keep2(hi, thr2);
           }
-          pk[j >> 1] = pack_bf16(h0, h1);
-          pk[(j >> 1) + 1] = pack_bf16(h2, h3);
         }
-        if (c > 0) {                                   // the bulk store of the previous chunk's H image must have finished reading sH
-          if (tid == 0) tma_store_wait_read();
-          named_bar_sync(1, T256_CTHREADS);
-        }
-        *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 16, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4 *>(sH + kmajor_off(row, part * 16 + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        // this slot's previous H image (chunk n - 2) is no longer read: its out-projection UMMAs retired before bar_hfull of this
+        // chunk was committed, and its bulk store finished reading before the closing barrier of chunk n - 1 (below)
+        *reinterpret_cast<uint4 *>(sHs + kmajor_off(row, part * 16, 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4 *>(sHs + kmajor_off(row, part * 16 + 8, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         fence_async_smem();
         fence_before_sync();
+        if (tid == 0) tma_store_wait_read();           // the bulk store of the PREVIOUS chunk's image (other slot) has drained: chunk n + 1 may overwrite it
         named_bar_sync(1, T256_CTHREADS);
         if (tid == 0) {
-          mbar_arrive(&bar_hready);
+          mbar_arrive(&bar_hready[fs]);
           if (a.h_img) {
-            tma_store_1d(a.h_img + ((size_t)tile * NCH + c) * 16384, sH, 16384u);
+            tma_store_1d(a.h_img + ((size_t)tile * NCH + c) * 16384, sHs, 16384u);
             tma_store_commit();
           }
         }
@@ -844,6 +854,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
         T256_STAMP();
         const float4 sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
         const float rs = rsqrtf(((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256) + LN_EPS);
+        if (part == 0 && a.ln2_stat) a.ln2_stat[grow] = make_float2(mu, rs);
         const float *g2 = p_g2 + part * 64, *be2 = p_be2 + part * 64;
         uint8_t *xog = a.x_img_out + (size_t)tile * T256_TILE_IMG;
 #pragma unroll

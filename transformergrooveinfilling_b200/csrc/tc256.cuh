@@ -120,6 +120,7 @@ struct T256Args {
   uint8_t *x_img_out;                    // forward: layer output
   uint8_t *u1_img, *u2_img;              // pre-LayerNorm sums (written by forward in train mode, read by backward)
   uint8_t *x1_img, *ctx_img, *h_img;     // forward (train): images saved for backward / the weight-gradient kernel
+  float2 *ln1_stat, *ln2_stat;           // forward (train) writes, backward reads: (mean, rstd) of LayerNorm1 / LayerNorm2 per token row (tile-padded)
   uint8_t *qkv_img;                      // head_dim 128 only: the four [128 x 192] q | k | v group images of every tile (q pre-scaled), saved
                                          // by the forward (train) and read by the backward instead of recomputing them
   // backward
@@ -127,7 +128,6 @@ struct T256Args {
   float *dx;
   uint8_t *da2_img, *da1_img, *dh_img, *dqkv_img;   // bf16 images written for the weight-gradient kernel
   uint8_t *dctx_scratch;                 // per-CTA 64 KB scratch (L2 resident)
-  float *park_scratch;                   // per-CTA fp32 tile (128 KB, L2 resident): LayerNorm-input gradients du2 / du1
   const uint8_t *img;                    // this layer's stage streams (forward, then backward), T256_REP replicas
   uint32_t img_rep_stride;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;

@@ -3,14 +3,14 @@
 // weight-gradient kernel that contracts the saved bf16 operand images over all tokens.
 //
 // data-gradient kernel, per tile of 128 tokens (torch/nn/modules/transformer.py:951-956 backwards):
-//   B0  LayerNorm2 backward (dy, u2)            -> du2 (parked, per-CTA scratch), da2 = du2 * mask2 (bf16 image)
+//   B0  LayerNorm2 backward (dy, u2)            -> du2 (tcgen05.st into the dx accumulator), da2 = du2 * mask2 (bf16 image)
 //   B1  dH(c)  = da2 W2[:, chunk c]             UMMA 128x64x256      B2  relu/dropout mask from the saved H image
-//   B3  dx1   += dH(c) W1[chunk c, :]           UMMA 128x256x64
-//   B4  LayerNorm1 backward (du2 + dx1, u1)     -> du1 (parked), da1 = du1 * mask1 (bf16 image)
+//   B3  dx1   += dH(c) W1[chunk c, :]           UMMA 128x256x64, accumulating onto du2
+//   B4  LayerNorm1 backward (du2 + dx1, u1)     -> du1 (stored back into the accumulator), da1 = du1 * mask1 (bf16 image)
 //   B5  dctx   = da1 Wo                         UMMA 128x256x256  -> bf16 -> per-CTA scratch (L2)
 //   B6  per head group: recompute q|k|v (UMMA 128x192x256), attention backward on mma.sync fragments,
 //       dx_in += dqkv_g Wqkv[group rows, :]     UMMA 128x256x192
-//   B7  dx = du1 + dx_in
+//   B7  dx = du1 + dx_in  (what the accumulator holds: the dx_in UMMAs accumulate onto du1)
 // Every bf16 image a weight gradient needs (da2, dH, da1, dqkv here; x, x1, ctx, H from the forward) is
 // left in HBM in the canonical UMMA layout, so the weight-gradient kernel stages them with plain bulk
 // copies and feeds them to the tensor core as MN-major operands (contraction over the token rows).
@@ -22,9 +22,9 @@ namespace gt {
 
 struct T256BwdSmem {
   // r1: da2 image -> da1 image -> attention scratch [128 x 256] = q | k | v | dO(group)
-  // r2: FFN phase: H chunk image (+0) and dH chunk image (+16384) ; attention phase: x image
+  // r2: FFN phase: two slots of (H chunk image +0, dH chunk image +16384), 32 KB each, used alternately ; attention phase: x image
   static constexpr uint32_t r1 = 0, r2 = 65536, ring = 131072, par = 196608, gpar = par + 1280 * 4, stat = gpar + 2816 * 4,
-                            total = stat + 4096;
+                            total = stat + 16384;          // stat: LayerNorm row statistics (4 KB) ; head_dim 128: fragment exchange (16 KB)
 };
 static_assert(T256BwdSmem::total <= 227 * 1024 - 1024, "backward shared memory budget");
 
@@ -219,37 +219,49 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
 // dP = dO V^T over all 128 features and turns them into the bf16 fragments of c dS and c dropped-P (c = 1/sqrt(dh), the
 // arithmetic of tc_attn32.cuh); phase B walks the features in blocks of 16 columns: dq | dk | dv overwrite q | k | v in place
 // (this warp is the only reader of those rows x columns).  g_b: bias-gradient partials of the two groups, [2][3][64].
-__device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, int s, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
+// FOUR warps share a pair (wq = 0..3).  Phase A is split by query m-tile: warps wq = 0, 1 turn the 16 queries of m-tile wq into
+// the fragments and leave them in the exchange buffer xch ([m-tile][16 registers][32 lanes] words of this sequence); after one
+// block-wide barrier (phase B overwrites what phase A reads) every warp loads both m-tiles' fragments and takes the feature
+// blocks wq and wq + 4 of phase B.  Operand fragments come from ldmatrix (a core matrix of the image = 8 rows x 16 bytes).
+__device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, uint32_t *xch, int s, int wq, int lane, const Drop &dr, uint64_t w_pair,
+                                                 float *g_b) {
   constexpr int DH = 128;
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, rr = lane & 7;
   const float c1 = rsqrtf((float)DH), rc1 = sqrtf((float)DH), ks = dr.scale;
   const float dk_scale = 0.6931471805599453f * rc1;
-  uint32_t pdp[2][4][2], dsq[2][4][2];                 // [query m-tile][key n-tile][rows g / g + 8]
-#pragma unroll 1
-  for (int mt = 0; mt < 2; ++mt) {
-    const int r0 = s * 32 + 16 * mt + g;
+  if (wq < 2) {
+    const int mt = wq;
     float p[4][4], dp[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { p[i][c] = 0.f; dp[i][c] = 0.f; }
+    // lane addresses: A-operand tiles (queries x 16 features): matrix (l >> 3) = rows 8 (mi & 1).., features 8 (mi >> 1)..
+    //                 B-operand tiles (keys x 16 features):    matrix (l >> 3) = keys 8 (mi >> 1).., features 8 (mi & 1)..
+    const uint32_t offA = kmajor_off(s * 32 + 16 * mt + (mi & 1) * 8 + rr, (mi >> 1) * 8, 128);
+    const uint32_t offB = kmajor_off(s * 32 + (mi >> 1) * 8 + rr, (mi & 1) * 8, 128);
 #pragma unroll 1
     for (int hf = 0; hf < 2; ++hf) {
       const uint8_t *im = hf ? imgO : imgE;
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
-        const int c0 = 16 * kt + 2 * t;
-        const uint32_t a0 = lds32(im + kmajor_off(r0, c0, 128)), a1 = lds32(im + kmajor_off(r0 + 8, c0, 128));
-        const uint32_t a2 = lds32(im + kmajor_off(r0, c0 + 8, 128)), a3 = lds32(im + kmajor_off(r0 + 8, c0 + 8, 128));
-        const uint32_t o0 = lds32(im + kmajor_off(r0, 192 + c0, 128)), o1 = lds32(im + kmajor_off(r0 + 8, 192 + c0, 128));
-        const uint32_t o2 = lds32(im + kmajor_off(r0, 192 + c0 + 8, 128)), o3 = lds32(im + kmajor_off(r0 + 8, 192 + c0 + 8, 128));
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int key = s * 32 + 8 * nt + g;
-          mma16816(p[nt], a0, a1, a2, a3, lds32(im + kmajor_off(key, 64 + c0, 128)), lds32(im + kmajor_off(key, 64 + c0 + 8, 128)));
-          mma16816(dp[nt], o0, o1, o2, o3, lds32(im + kmajor_off(key, 128 + c0, 128)), lds32(im + kmajor_off(key, 128 + c0 + 8, 128)));
-        }
+        const uint32_t cstep = (uint32_t)kt * 4096u;    // 16 feature columns = two 8-column slabs of 2048 B
+        uint32_t aq[4], ao[4], bk0[4], bk1[4], bv0[4], bv1[4];
+        ldmatrix_x4(aq, im + offA + cstep);
+        ldmatrix_x4(ao, im + offA + 192u * 256u + cstep);
+        ldmatrix_x4(bk0, im + offB + 64u * 256u + cstep);
+        ldmatrix_x4(bk1, im + offB + 64u * 256u + 256u + cstep);
+        ldmatrix_x4(bv0, im + offB + 128u * 256u + cstep);
+        ldmatrix_x4(bv1, im + offB + 128u * 256u + 256u + cstep);
+        mma16816(p[0], aq[0], aq[1], aq[2], aq[3], bk0[0], bk0[1]);
+        mma16816(p[1], aq[0], aq[1], aq[2], aq[3], bk0[2], bk0[3]);
+        mma16816(p[2], aq[0], aq[1], aq[2], aq[3], bk1[0], bk1[1]);
+        mma16816(p[3], aq[0], aq[1], aq[2], aq[3], bk1[2], bk1[3]);
+        mma16816(dp[0], ao[0], ao[1], ao[2], ao[3], bv0[0], bv0[1]);
+        mma16816(dp[1], ao[0], ao[1], ao[2], ao[3], bv0[2], bv0[3]);
+        mma16816(dp[2], ao[0], ao[1], ao[2], ao[3], bv1[0], bv1[1]);
+        mma16816(dp[3], ao[0], ao[1], ao[2], ao[3], bv1[2], bv1[3]);
       }
     }
     float m0 = p[0][0], m1 = p[0][2];
@@ -303,17 +315,30 @@ __device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, i
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     const float e0 = -(d0 * rc1) * i0, e1 = -(d1 * rc1) * i1;
+    // exchange layout: word ((mt * 4 + nt) * 4 + j) * 32 + lane, j = 0, 1: dropped-P rows g / g + 8 ; j = 2, 3: dS rows g / g + 8
+    uint4 *xo = reinterpret_cast<uint4 *>(xch) + (mt * 4) * 32 + lane;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      pdp[mt][nt][0] = pack_bf16(pdm[nt][0], pdm[nt][1]); pdp[mt][nt][1] = pack_bf16(pdm[nt][2], pdm[nt][3]);
-      dsq[mt][nt][0] = pack_bf16(fmaf(p[nt][0], e0, dp[nt][0]), fmaf(p[nt][1], e0, dp[nt][1]));
-      dsq[mt][nt][1] = pack_bf16(fmaf(p[nt][2], e1, dp[nt][2]), fmaf(p[nt][3], e1, dp[nt][3]));
-    }
+    for (int nt = 0; nt < 4; ++nt)
+      xo[nt * 32] = make_uint4(pack_bf16(pdm[nt][0], pdm[nt][1]), pack_bf16(pdm[nt][2], pdm[nt][3]),
+                               pack_bf16(fmaf(p[nt][0], e0, dp[nt][0]), fmaf(p[nt][1], e0, dp[nt][1])),
+                               pack_bf16(fmaf(p[nt][2], e1, dp[nt][2]), fmaf(p[nt][3], e1, dp[nt][3])));
   }
-  __syncwarp();                                         // every lane has finished phase A: the images may be overwritten block by block
+  named_bar_sync(1, T256_CTHREADS);                     // every warp has finished phase A: the images may be overwritten block by block
+  uint32_t pdp[2][4][2], dsq[2][4][2];                  // [query m-tile][key n-tile][rows g / g + 8]
+  {
+    const uint4 *xi = reinterpret_cast<const uint4 *>(xch) + lane;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint4 v = xi[(mt * 4 + nt) * 32];
+        pdp[mt][nt][0] = v.x; pdp[mt][nt][1] = v.y; dsq[mt][nt][0] = v.z; dsq[mt][nt][1] = v.w;
+      }
+  }
   // ---- phase B: 16 feature columns at a time ----
 #pragma unroll 1
-  for (int blk = 0; blk < 8; ++blk) {
+  for (int bi = 0; bi < 2; ++bi) {
+    const int blk = wq + 4 * bi;
     uint8_t *im = blk >= 4 ? imgO : imgE;
     const int cq = (blk & 3) * 16;                      // column of the block inside its group: q at cq, k at 64 + cq, v at 128 + cq, dO at 192 + cq
     float dq[2][2][4], dk[2][2][4], dv[2][2][4];        // [m-tile][n-tile of the block][4]
@@ -385,52 +410,67 @@ __device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, i
 
 // ---- LayerNorm backward over a [128 x 256] tile; thread = (row, 64-column part) ----------------------------------
 // dyv(cb, out16): loads 16 values of the incoming gradient for columns part*64 + cb..  (re-readable)
-// Writes du (tiled fp32 -> park) and da = du * dropmask (bf16 -> sImg and gImg); accumulates dgamma / dbeta / dbias partials.
+// Writes du (fp32 -> TMEM accumulator t_du) and da = du * dropmask (bf16 -> sImg and gImg); accumulates dgamma / dbeta / dbias partials.
+// The row's mean / rstd come from the forward (`stat`: float2 per token row), so there is no statistics pass over u; both passes
+// walk the thread's 64 columns in chunks of 16 with the NEXT chunk's loads issued before the current chunk's arithmetic (the phase
+// is bound by the latency of its global loads — 4 warps per scheduler, every warp in the same phase — not by their bytes).
 template <class DyLoad>
-__device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*global tile image*/, const float *gamma, float *park /*tiled fp32 tile*/,
+__device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*global tile image*/, const float2 *stat /*this row's (mean, rstd)*/,
+                                            const float *gamma, uint32_t t_du /*TMEM: this thread's row, column 0*/,
                                             uint8_t *sImg, uint8_t *gImg, const Drop &dr, uint64_t e_row /* element index of (row, col 0) */,
-                                            float *g_gamma, float *g_beta, float *g_bias, float *sStatA, float *sStatB, int row, int part, int lane) {
-  // pass A: statistics of u
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 64; c += 8) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + c, 128));
-    const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
-  }
-  sStatA[row * 4 + part] = s1; sStatB[row * 4 + part] = s2;
-  named_bar_sync(1, T256_CTHREADS);
-  float mu, rs;
-  {
-    const float4 sa = *reinterpret_cast<const float4 *>(sStatA + row * 4), sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
-    mu = ((sa.x + sa.y) + (sa.z + sa.w)) * (1.f / 256);
-    const float var = fmaxf(((sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256) - mu * mu, 0.f);
-    rs = rsqrtf(var + LN_EPS);
-  }
-  named_bar_sync(1, T256_CTHREADS);                  // everyone has read the statistics before they are overwritten below
+                                            float *g_gamma, float *g_beta, float *g_bias, float *sStatA, float *sStatB, int row, int part, int lane,
+                                            unsigned long long *dbg, int &ndbg) {
+#define LN_STAMP() do { if (dbg != nullptr && ndbg < 60) dbg[ndbg++] = clock64(); } while (0)
+  const float2 mr = __ldg(stat);
+  const float rs = mr.y, nmr = -mr.x * mr.y;
+  const uint8_t *u_row = u_img + kmajor_off(row, part * 64, 128);      // 8 columns further = + 2048 bytes
   // pass B: m1 = mean(dy g), m2 = mean(dy g xhat) ; dgamma / dbeta column sums
   float m1 = 0.f, m2 = 0.f;
+  const ColsumSel csel = colsum_sel(lane);
+  const int cs_col = (lane >> 2) + 8 * (lane & 1);    // lanes with (lane & 3) < 2 flush column g (t = 0) / g + 8 (t = 1) of a 16-column sum
+  const bool cs_on = (lane & 3) < 2;
+  float dyn[16];
+  uint4 un0, un1;
+  dyv(0, dyn);
+  un0 = *reinterpret_cast<const uint4 *>(u_row); un1 = *reinterpret_cast<const uint4 *>(u_row + 2048);
 #pragma unroll 1
   for (int cb = 0; cb < 64; cb += 16) {
-    float dy[16], w[32];
-    dyv(cb, dy);
-    const uint4 v0 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb, 128));
-    const uint4 v1 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 8, 128));
+    float dy[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dy[j] = dyn[j];
+    const uint4 v0 = un0, v1 = un1;
+    if (cb + 16 < 64) {
+      dyv(cb + 16, dyn);
+      un0 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256); un1 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256 + 2048);
+    }
     const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
                           bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
+    uint32_t pg[8], pb[8];                            // bf16 pairs of dy * xhat (-> dgamma) and dy (-> dbeta)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float xh = (uu[j] - mu) * rs, gd = dy[j] * gamma[part * 64 + cb + j];
-      m1 += gd; m2 = fmaf(gd, xh, m2);
-      w[j] = dy[j] * xh; w[16 + j] = dy[j];
+    for (int j = 0; j < 16; j += 2) {
+      const float4 gm = *reinterpret_cast<const float4 *>(gamma + part * 64 + cb + (j & ~3));
+      const float ga = (j & 2) ? gm.z : gm.x, gb = (j & 2) ? gm.w : gm.y;
+      const float xa = fmaf(uu[j], rs, nmr), xb = fmaf(uu[j + 1], rs, nmr);
+      const float gda = dy[j] * ga, gdb = dy[j + 1] * gb;
+      m1 += gda + gdb; m2 = fmaf(gda, xa, m2); m2 = fmaf(gdb, xb, m2);
+      pg[j >> 1] = pack_bf16(dy[j] * xa, dy[j + 1] * xb);
+      pb[j >> 1] = pack_bf16(dy[j], dy[j + 1]);
     }
-    const float tsum = t256_colsum32(w, lane);
-    if (lane < 16) atomicAdd(g_gamma + part * 64 + cb + lane, tsum);
-    else atomicAdd(g_beta + part * 64 + cb + lane - 16, tsum);
+    float sg0, sg1, sb0, sb1;
+    warp_colsum16_packed(pg, csel, sg0, sg1);
+    warp_colsum16_packed(pb, csel, sb0, sb1);
+    if (cs_on) {
+      atomicAdd(g_gamma + part * 64 + cb + cs_col, (lane & 1) ? sg1 : sg0);
+      atomicAdd(g_beta + part * 64 + cb + cs_col, (lane & 1) ? sb1 : sb0);
+    }
   }
+  LN_STAMP();
   sStatA[row * 4 + part] = m1; sStatB[row * 4 + part] = m2;
+  // first chunk of pass C: issued before the barrier, so its latency overlaps the exchange of the row sums
+  dyv(0, dyn);
+  un0 = *reinterpret_cast<const uint4 *>(u_row); un1 = *reinterpret_cast<const uint4 *>(u_row + 2048);
   named_bar_sync(1, T256_CTHREADS);
+  LN_STAMP();
   {
     const float4 sa = *reinterpret_cast<const float4 *>(sStatA + row * 4), sb = *reinterpret_cast<const float4 *>(sStatB + row * 4);
     m1 = ((sa.x + sa.y) + (sa.z + sa.w)) * (1.f / 256);
@@ -439,46 +479,59 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
   // pass C: du = rstd (dy g - m1 - xhat m2) ; da = du * dropmask
   const uint64_t w0 = (e_row + (uint64_t)(part * 64)) >> 2;
   const uint32_t wlo = (uint32_t)w0, xhi = (uint32_t)(w0 >> 32) * 0x85EBCA6Bu;
+  const float ks = dr.thr ? dr.scale : 1.f;
+  const uint32_t thr2 = dr.thr | (dr.thr << 16);
 #pragma unroll 1
-  for (int cb = 0; cb < 64; cb += 32) {
-    float w[32];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+  for (int cb = 0; cb < 64; cb += 16) {
+    float w[16];
+    {
       float dy[16];
-      dyv(cb + 16 * h, dy);
-      const uint4 v0 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 16 * h, 128));
-      const uint4 v1 = *reinterpret_cast<const uint4 *>(u_img + kmajor_off(row, part * 64 + cb + 16 * h + 8, 128));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dy[j] = dyn[j];
+      const uint4 v0 = un0, v1 = un1;
+      if (cb + 16 < 64) {
+        dyv(cb + 16, dyn);
+        un0 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256); un1 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256 + 2048);
+      }
       const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
                             bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float xh = (uu[j] - mu) * rs;
-        w[16 * h + j] = rs * (dy[j] * gamma[part * 64 + cb + 16 * h + j] - m1 - xh * m2);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 gm = *reinterpret_cast<const float4 *>(gamma + part * 64 + cb + j);
+        const float gj[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xh = fmaf(uu[j + e], rs, nmr);
+          w[j + e] = rs * (dy[j + e] * gj[e] - m1 - xh * m2);
+        }
       }
     }
+    // du (the gradient that by-passes the sub-layer through the residual) goes straight into the TMEM accumulator the next UMMAs
+    // add their dx onto — no fp32 tile parked in L2 and re-read (it was 640 KB of the ~3 MB a tile moved between SM and L2)
+    tmem_st16(t_du + (uint32_t)(part * 64 + cb), w);
+    // da = dropout(du): scale in fp32, round to bf16 pairs, AND the packed keep masks (two decisions per half-precision compare)
+    uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4 *>(park + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+    for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16(w[j] * ks, w[j + 1] * ks);
     if (dr.thr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 16; j += 4) {
         uint32_t lo, hi;
         hash_quad((wlo + (uint32_t)((cb + j) >> 2)) ^ xhi, dr.key, lo, hi);
-        w[j] = ((lo & 0xFFFFu) >= dr.thr) ? w[j] * dr.scale : 0.f;
-        w[j + 1] = ((lo >> 16) >= dr.thr) ? w[j + 1] * dr.scale : 0.f;
-        w[j + 2] = ((hi & 0xFFFFu) >= dr.thr) ? w[j + 2] * dr.scale : 0.f;
-        w[j + 3] = ((hi >> 16) >= dr.thr) ? w[j + 3] * dr.scale : 0.f;
+        pk[j >> 1] &= keep2(lo, thr2);
+        pk[(j >> 1) + 1] &= keep2(hi, thr2);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 pk = make_uint4(pack_bf16(w[j], w[j + 1]), pack_bf16(w[j + 2], w[j + 3]), pack_bf16(w[j + 4], w[j + 5]), pack_bf16(w[j + 6], w[j + 7]));
+    for (int j = 0; j < 16; j += 8) {
+      const uint4 pv = make_uint4(pk[j >> 1], pk[(j >> 1) + 1], pk[(j >> 1) + 2], pk[(j >> 1) + 3]);
       const uint32_t off = kmajor_off(row, part * 64 + cb + j, 128);
-      *reinterpret_cast<uint4 *>(sImg + off) = pk;
-      *reinterpret_cast<uint4 *>(gImg + off) = pk;
+      *reinterpret_cast<uint4 *>(sImg + off) = pv;
+      *reinterpret_cast<uint4 *>(gImg + off) = pv;
     }
-    const float tsum = t256_colsum32(w, lane);
-    atomicAdd(g_bias + part * 64 + cb + lane, tsum);
+    float s0, s1;
+    warp_colsum16_packed(pk, csel, s0, s1);
+    if (cs_on) atomicAdd(g_bias + part * 64 + cb + cs_col, (lane & 1) ? s1 : s0);
   }
 }
 
@@ -493,7 +546,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
   constexpr bool H128 = DH == 128;                   // a head spans two groups: q | k | v come from the forward's saved images, no recompute
   using S = T256BwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_da2ready, bar_hready, bar_hfree, bar_dhfull, bar_dhimgready, bar_r2a,
+  __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_da2ready, bar_hready[2], bar_hfree[2], bar_dhfull[2], bar_dhimgready[2], bar_r2a,
       bar_r2b, bar_dx1full, bar_da1ready, bar_dctxfull, bar_xready, bar_qkvfree, bar_qkvfull, bar_dqkvready, bar_dqkvfree, bar_dxinfull;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -509,7 +562,8 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    uint64_t *bars[] = {&bar_da2ready, &bar_hready, &bar_hfree, &bar_dhfull, &bar_dhimgready, &bar_r2a, &bar_r2b, &bar_dx1full, &bar_da1ready,
+    uint64_t *bars[] = {&bar_da2ready, &bar_hready[0], &bar_hready[1], &bar_hfree[0], &bar_hfree[1], &bar_dhfull[0], &bar_dhfull[1],
+                        &bar_dhimgready[0], &bar_dhimgready[1], &bar_r2a, &bar_r2b, &bar_dx1full, &bar_da1ready,
                         &bar_dctxfull, &bar_xready, &bar_qkvfree, &bar_qkvfull, &bar_dqkvready, &bar_dqkvfree, &bar_dxinfull};
     for (uint64_t *b : bars) mbar_init(b, 1);
     fence_mbar_init();
@@ -541,10 +595,11 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         };
         mbar_wait(&bar_r2b, (it & 1u) ^ 1u);                   // the previous tile's q|k|v recompute no longer reads the x image in r2
         for (int c = 0; c < NCH; ++c) {
-          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
-          mbar_wait(&bar_hfree, (n & 1u) ^ 1u);
-          mbar_expect_tx(&bar_hready, 16384u);
-          tma_load_1d(sR2, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready);
+          // FFN chunks alternate between two (H chunk, dH image) slots of r2: chunk n uses slot n & 1 for the (n >> 1)-th time
+          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c, fs = n & 1u, fu = (n >> 1) & 1u;
+          mbar_wait(&bar_hfree[fs], fu ^ 1u);
+          mbar_expect_tx(&bar_hready[fs], 16384u);
+          tma_load_1d(sR2 + fs * 32768u, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready[fs]);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) stage(4 * c + j, 16384u);
         }
@@ -572,7 +627,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
     // ======================= MMA issuer =======================
     if (elect_one()) {
       const uint32_t id_192 = make_idesc_bf16(128, 192), id_256 = make_idesc_bf16(128, 256), id_64 = make_idesc_bf16(128, 64);
-      const uint64_t dR1 = descA128(aR1), dR2 = descA128(aR2), dDH = descA128(aR2 + 16384u);
+      const uint64_t dR1 = descA128(aR1), dR2 = descA128(aR2);
       const uint64_t dB192 = descB(aRing, 192), dB256 = descB(aRing, 256), dB64 = descB(aRing, 64);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -584,21 +639,30 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         // ---- FFN backward ----
         mbar_wait(&bar_da2ready, it & 1u);
         fence_after_sync();
-        for (int c = 0; c < NCH; ++c) {
-          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
+        // dH(c + 1) is issued BEFORE the issuer waits for the dH image of chunk c, into the other accumulator / image slot, so the
+        // hidden-gradient epilogue of chunk c overlaps the tensor work of its neighbours.  The ring is consumed out of stream
+        // order (stages 4c+4, 4c+5 before 4c+2, 4c+3) but every slot still sees its stages in order, and four slots = one chunk.
+        auto issue_dh = [&](int c) {                    // dH(c) = da2 W2[:, chunk]
+          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c, fs = n & 1u;
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {              // dH(c) = da2 W2[:, chunk]
+          for (int hf = 0; hf < 2; ++hf) {
             const int st = 4 * c + hf;
             full_wait(st);
             const uint64_t db = desc_adv(dB64, (uint32_t)(st % NS) * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              mma_bf16_ss(t_b, desc_adv(dR1, (uint32_t)(hf * 8 + k) * 4096u), desc_adv(db, (uint32_t)k * 2048u), id_64, (hf | k) > 0);
+              mma_bf16_ss(t_b + fs * 64u, desc_adv(dR1, (uint32_t)(hf * 8 + k) * 4096u), desc_adv(db, (uint32_t)k * 2048u), id_64, (hf | k) > 0);
             mma_commit(&bar_empty[st % NS]);
           }
-          mma_commit(&bar_dhfull);
-          mbar_wait(&bar_dhimgready, n & 1u);
+          mma_commit(&bar_dhfull[fs]);
+        };
+        issue_dh(0);
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t n = it * (uint32_t)NCH + (uint32_t)c, fs = n & 1u, fu = (n >> 1) & 1u;
+          if (c + 1 < NCH) issue_dh(c + 1);
+          mbar_wait(&bar_dhimgready[fs], fu);
           fence_after_sync();
+          const uint64_t dDH = descA128(aR2 + fs * 32768u + 16384u);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {              // dx1 += dH(c) W1[chunk, :]
             const int st = 4 * c + 2 + hf;
@@ -606,7 +670,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              mma_bf16_ss(t_dx, desc_adv(dDH, (uint32_t)(hf * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (c | hf | k) > 0);
+              mma_bf16_ss(t_dx, desc_adv(dDH, (uint32_t)(hf * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du2
             mma_commit(&bar_empty[st % NS]);
           }
         }
@@ -641,7 +705,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
                 const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  mma_bf16_ss(t_dx, desc_adv(dA, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (gg | b | k) > 0);
+                  mma_bf16_ss(t_dx, desc_adv(dA, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du1
                 mma_commit(&bar_empty[st % NS]);
               }
             }
@@ -665,7 +729,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              mma_bf16_ss(t_dx, desc_adv(dR1, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, (gg | b | k) > 0);
+              mma_bf16_ss(t_dx, desc_adv(dR1, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du1
             mma_commit(&bar_empty[st % NS]);
           }
           mma_commit(&bar_dqkvfree);
@@ -700,10 +764,10 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float attn_scale = rsqrtf((float)DH) * 1.4426950408889634f;
+    const ColsumSel csel = colsum_sel(lane);
     uint8_t *scratch = a.dctx_scratch + (size_t)blockIdx.x * T256_TILE_IMG;
-    // du2 / du1 are parked in a per-CTA fp32 tile that is rewritten every tile, so it stays L2-resident and its lines are
-    // (mostly) never written back to HBM; parking them in the tile's own dx rows cost two extra HBM round trips per tile
-    float *park = a.park_scratch + (size_t)blockIdx.x * T256_TILE_F32;
+    // du2 / du1 (LayerNorm-input gradients, the residual by-pass) are written into the dx accumulator t_dx with tcgen05.st and the
+    // following UMMAs accumulate onto them; earlier versions parked them in a per-CTA fp32 tile in L2 and re-added them
     uint32_t it = 0;
     int ndbg = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -722,24 +786,27 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
           }
         };
-        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, p_g2, park, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
-                    g_g2, g_be2, g_b2, sStatA, sStatB, row, part, lane);
+        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, a.ln2_stat + grow, p_g2, t_dx + lane_off, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
+                    g_g2, g_be2, g_b2, sStatA, sStatB, row, part, lane, dbg_on ? a.dbg : nullptr, ndbg);
       }
+      tmem_st_wait();                                 // du2 sits in t_dx: dx1 accumulates onto it
       fence_async_smem();
+      fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
       if (tid == 0) mbar_arrive(&bar_da2ready);
       T256_STAMP();
       // ---- B2: hidden-activation gradient per FFN chunk ----
       for (int c = 0; c < NCH; ++c) {
-        const uint32_t n = it * (uint32_t)NCH + (uint32_t)c;
-        mbar_wait(&bar_hready, n & 1u);
-        mbar_wait(&bar_dhfull, n & 1u);
+        const uint32_t n = it * (uint32_t)NCH + (uint32_t)c, fs = n & 1u, fu = (n >> 1) & 1u;
+        uint8_t *sH = sR2 + fs * 32768u;                // this chunk's slot: H image at +0, dH image at +16384
+        mbar_wait(&bar_hready[fs], fu);
+        mbar_wait(&bar_dhfull[fs], fu);
         fence_after_sync();
-        float w[32];
-        tmem_ld16(t_b + lane_off + (uint32_t)(part * 16), w);
+        float w[16];
+        tmem_ld16(t_b + fs * 64u + lane_off + (uint32_t)(part * 16), w);
         tmem_ld_wait();
-        const uint4 h0 = *reinterpret_cast<const uint4 *>(sR2 + kmajor_off(row, part * 16, 128));
-        const uint4 h1 = *reinterpret_cast<const uint4 *>(sR2 + kmajor_off(row, part * 16 + 8, 128));
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(sH + kmajor_off(row, part * 16, 128));
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(sH + kmajor_off(row, part * 16 + 8, 128));
         const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const float sc = a.d_ffn.scale;
 #pragma unroll
@@ -747,42 +814,37 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           w[2 * j] = (hh[j] & 0x7FFFu) != 0u && !(hh[j] & 0x8000u) ? w[2 * j] * sc : 0.f;                  // H > 0  (bf16 low half)
           w[2 * j + 1] = (hh[j] & 0x7FFF0000u) != 0u && !(hh[j] & 0x80000000u) ? w[2 * j + 1] * sc : 0.f;  // bf16 high half
         }
-#pragma unroll
-        for (int j = 16; j < 32; ++j) w[j] = 0.f;
         const uint4 pk0 = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
         const uint4 pk1 = make_uint4(pack_bf16(w[8], w[9]), pack_bf16(w[10], w[11]), pack_bf16(w[12], w[13]), pack_bf16(w[14], w[15]));
         uint8_t *dhg = a.dh_img + ((size_t)tile * NCH + c) * 16384;
         const uint32_t o0 = kmajor_off(row, part * 16, 128), o1 = kmajor_off(row, part * 16 + 8, 128);
-        *reinterpret_cast<uint4 *>(sR2 + 16384 + o0) = pk0; *reinterpret_cast<uint4 *>(sR2 + 16384 + o1) = pk1;
+        *reinterpret_cast<uint4 *>(sH + 16384 + o0) = pk0; *reinterpret_cast<uint4 *>(sH + 16384 + o1) = pk1;
         *reinterpret_cast<uint4 *>(dhg + o0) = pk0; *reinterpret_cast<uint4 *>(dhg + o1) = pk1;
-        const float tsum = t256_colsum32(w, lane);
-        if (lane < 16) atomicAdd(g_b1 + c * 64 + part * 16 + lane, tsum);
+        {
+          const uint32_t ph[8] = {pk0.x, pk0.y, pk0.z, pk0.w, pk1.x, pk1.y, pk1.z, pk1.w};
+          float s0, s1;
+          warp_colsum16_packed(ph, csel, s0, s1);       // linear1 bias gradient: column sums of the dH image rows of this warp
+          if ((lane & 3) < 2) atomicAdd(g_b1 + c * 64 + part * 16 + (lane >> 2) + 8 * (lane & 1), (lane & 1) ? s1 : s0);
+        }
         fence_async_smem();
         fence_before_sync();
         named_bar_sync(1, T256_CTHREADS);
-        if (tid == 0) { mbar_arrive(&bar_dhimgready); mbar_arrive(&bar_hfree); }
+        if (tid == 0) { mbar_arrive(&bar_dhimgready[fs]); mbar_arrive(&bar_hfree[fs]); }
       }
       T256_STAMP();
-      // ---- B4: LayerNorm1 backward on du2 (parked) + dx1 (TMEM) ----
+      // ---- B4: LayerNorm1 backward on du2 + dx1 (TMEM accumulator) ----
       mbar_wait(&bar_dx1full, it & 1u);
       fence_after_sync();
       T256_STAMP();
       {
-        auto dyload = [&](int cb, float (&o)[16]) {
-          float f[16];
-          tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(park + ((size_t)((part * 64 + cb + j) >> 2) * 128 + row) * 4));
-            o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
-          }
+        auto dyload = [&](int cb, float (&o)[16]) {     // du2 + dx1: the accumulator was seeded with du2
+          tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), o);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += f[j];
         };
-        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, p_g1, park, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
-                    g_g1, g_be1, g_bo, sStatA, sStatB, row, part, lane);
+        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, a.ln1_stat + grow, p_g1, t_dx + lane_off, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
+                    g_g1, g_be1, g_bo, sStatA, sStatB, row, part, lane, dbg_on ? a.dbg : nullptr, ndbg);
       }
+      tmem_st_wait();                                 // du1 sits in t_dx: dx_in accumulates onto it
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
@@ -827,10 +889,12 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           }
           named_bar_sync(1, T256_CTHREADS);
           T256_STAMP();
-          if (warp < 4) {
-            const int64_t seq = a.seq0 + (int64_t)tile * 4 + warp;
+          {
+            const int s = warp & 3;
+            const int64_t seq = a.seq0 + (int64_t)tile * 4 + s;
             const uint64_t w_pair = (uint64_t)((seq * H + h) * 32) * 8u;
-            t256_attn_bwd128(sR1, sR2, warp, lane, a.d_attn, w_pair, g_bqkv + (2 * h) * 192);
+            t256_attn_bwd128(sR1, sR2, reinterpret_cast<uint32_t *>(smem + S::stat) + s * 1024, s, warp >> 2, lane, a.d_attn, w_pair,
+                             g_bqkv + (2 * h) * 192);
           }
           fence_async_smem();
           named_bar_sync(1, T256_CTHREADS);
@@ -899,7 +963,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         }
         T256_STAMP();
       }
-      // ---- B7: dx = du1 (parked) + dx_in ----
+      // ---- B7: dx = du1 + dx_in (one accumulator) ----
       mbar_wait(&bar_dxinfull, it & 1u);
       fence_after_sync();
       T256_STAMP();
@@ -907,14 +971,11 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       for (int cb = 0; cb < 64; cb += 16) {
         float f[16];
         tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), f);
-        float4 pv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pv[j] = __ldcg(reinterpret_cast<const float4 *>(park + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4));
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<float4 *>(dx_t + ((size_t)((part * 64 + cb + 4 * j) >> 2) * 128 + row) * 4) =
-              make_float4(pv[j].x + f[4 * j], pv[j].y + f[4 * j + 1], pv[j].z + f[4 * j + 2], pv[j].w + f[4 * j + 3]);
+              make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
       }
       if (tid == 0) {
         tma_store_wait_read();

@@ -17,9 +17,9 @@ struct T256Plan {
   uint8_t *u1img[TC_MAX_LAYERS], *u2img[TC_MAX_LAYERS];
   uint8_t *x1img[TC_MAX_LAYERS], *ctximg[TC_MAX_LAYERS], *himg[TC_MAX_LAYERS];
   uint8_t *qkvimg[TC_MAX_LAYERS];                 // head_dim 128: saved q | k | v group images
+  float2 *ln1stat[TC_MAX_LAYERS], *ln2stat[TC_MAX_LAYERS];   // (mean, rstd) per token row of the two LayerNorms, saved by the forward
   float *d_hvo, *loss_partials, *dlog, *dxrm, *dxrm2, *g0, *dxa, *dxb;
   uint8_t *da2img, *da1img, *dhimg, *dqkvimg, *dctx_scratch, *wg_jobs;
-  float *park_scratch;
   uint8_t *dlimg, *srcimg;                        // fused edges: [128 x 32] bf16 images per tile
   float *edge_scratch;                            // fused edges: T [256][32] + sums [64] (tail), Tin [256][32] (stem)
   int64_t bytes;
@@ -63,6 +63,8 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
       P.x1img[l] = reinterpret_cast<uint8_t *>(take(ti));
       P.ctximg[l] = reinterpret_cast<uint8_t *>(take(ti));
       P.himg[l] = reinterpret_cast<uint8_t *>(take(th));
+      P.ln1stat[l] = reinterpret_cast<float2 *>(take((int64_t)n_tiles * 128 * 8));
+      P.ln2stat[l] = reinterpret_cast<float2 *>(take((int64_t)n_tiles * 128 * 8));
       if (dh == 128) P.qkvimg[l] = reinterpret_cast<uint8_t *>(take((int64_t)n_tiles * T256_G * T256_QKV_GROUP_IMG));
     }
     if (!fused) P.d_hvo = reinterpret_cast<float *>(take(M * c.e_tgt * 4));
@@ -84,7 +86,6 @@ static void t256_make_plan(const gt_config &c, int64_t n_seq, int mode, char *ba
     P.dhimg = reinterpret_cast<uint8_t *>(take(th));
     P.dqkvimg = reinterpret_cast<uint8_t *>(take(3 * ti));
     P.dctx_scratch = reinterpret_cast<uint8_t *>(take((int64_t)160 * T256_TILE_IMG));
-    P.park_scratch = reinterpret_cast<float *>(take((int64_t)160 * T256_TILE_F32 * 4));
     P.wg_jobs = reinterpret_cast<uint8_t *>(take(T256_WG_JOBBUF));
   } else {
     uint8_t *ia = reinterpret_cast<uint8_t *>(take(ti)), *ib = reinterpret_cast<uint8_t *>(take(ti));
@@ -184,7 +185,7 @@ static int t256_forward_all(const T256Ctx &x, const T256Plan &pl, const float *s
   for (int l = 0; l < L; ++l) {
     T256Args a = t256_layer_args(x, pl, l);
     a.x_img_in = pl.ximg[l]; a.x_img_out = pl.ximg[l + 1];
-    if (save) { a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; a.qkv_img = pl.qkvimg[l]; }
+    if (save) { a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; a.qkv_img = pl.qkvimg[l]; a.ln1_stat = pl.ln1stat[l]; a.ln2_stat = pl.ln2stat[l]; }
     GT_TRY(t256_layer_fwd(a, x.st));
   }
   if (fused)
@@ -230,9 +231,9 @@ static int t256_backward_all(const T256Ctx &x, const T256Plan &pl, const float *
   for (int l = L - 1; l >= 0; --l) {
     const LayerP &p = x.L->enc[l];
     T256Args a = t256_layer_args(x, pl, l);
-    a.x_img_in = pl.ximg[l]; a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.dy = cur; a.dx = oth;
+    a.x_img_in = pl.ximg[l]; a.u1_img = pl.u1img[l]; a.u2_img = pl.u2img[l]; a.ln1_stat = pl.ln1stat[l]; a.ln2_stat = pl.ln2stat[l]; a.dy = cur; a.dx = oth;
     a.x1_img = pl.x1img[l]; a.ctx_img = pl.ctximg[l]; a.h_img = pl.himg[l]; a.qkv_img = pl.qkvimg[l];
-    a.da2_img = pl.da2img; a.da1_img = pl.da1img; a.dh_img = pl.dhimg; a.dqkv_img = pl.dqkvimg; a.dctx_scratch = pl.dctx_scratch; a.park_scratch = pl.park_scratch;
+    a.da2_img = pl.da2img; a.da1_img = pl.da1img; a.dh_img = pl.dhimg; a.dqkv_img = pl.dqkvimg; a.dctx_scratch = pl.dctx_scratch;
     GT_TRY(t256_layer_bwd(a, x.st));
     T256WgradArgs w;
     memset(&w, 0, sizeof(w));

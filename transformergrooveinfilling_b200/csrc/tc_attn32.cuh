@@ -28,12 +28,7 @@ __device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1,
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0));
 }
-// four 8x8 b16 matrices, not transposed: thread (g, t) receives word t of row g of each matrix
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem_row) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(smem_row)));
-}
+// (ldmatrix_x4 — four 8x8 b16 matrices, not transposed: thread (g, t) receives word t of row g of each matrix — lives in umma.cuh)
 
 // write 32 fp32 values of one token row as bf16 into an attention image
 __device__ __forceinline__ void a32_store_row(uint8_t *img, int row, const float (&v)[32], float scale) {

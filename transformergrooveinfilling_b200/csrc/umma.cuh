@@ -106,6 +106,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: lane (32 w % 4 + l) of the warp's lane quadrant, 16 consecutive 32-bit columns (the mirror of tmem_ld16).
+// A later tcgen05.mma that ACCUMULATES onto these columns sees them after tmem_st_wait + fence_before_sync + a thread sync.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
+  const uint32_t *r = reinterpret_cast<const uint32_t *>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -168,11 +181,60 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(smem_row)));
 }
+// four 8x8 b16 matrices as they lie (row = 16 contiguous bytes); lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
 // transpose one 8x8 b16 matrix held as a mma fragment (lane holds row lane/4, columns 2*(lane%4), +1)
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
   uint32_t d;
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
   return d;
+}
+
+// D(16x8, f32) += A(16x8 tf32, row) * B(8x8 tf32, col)
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// ---- column sums over the 32 lanes of a warp on the tensor cores (lane = token row, registers = feature columns) ----------
+// The butterfly (31 shuffles + 62 selects + 31 adds per 32 values) was 15 % of the instructions of the d_model = 256 backward.
+// Here the lane's 16 values go in as the B operand of four mma.m16n8k16: B[k][n] of lane (g = lane / 4, t = lane % 4) is
+// "row-group g, slot (t, register, half)", and a 0/1 SELECTOR A operand routes slot (register r, half h) of group q's mma to
+// output row 4 q + 2 r + h — so D1[column c][n] = sum of column c over the four lanes of row-group n.  One tf32 mma with an
+// all-ones B then sums D1 over its 8 row-groups (the D1 accumulator fragment IS the A fragment layout of m16n8k8, up to the
+// order of k, which a sum does not see).  Result: every lane (g, t) holds column g in s0 and column g + 8 in s1.
+// Inputs are rounded to bf16 (like every other tensor-core column sum of this library), the partial sums to tf32.
+struct ColsumSel {
+  uint32_t l0, h0, l1, h1;
+};
+__device__ __forceinline__ ColsumSel colsum_sel(int lane) {
+  const int g = lane >> 2, gi = g & 3;
+  const uint32_t lo = gi == 0 ? 0x00003F80u : (gi == 1 ? 0x3F800000u : 0u);     // k < 8: even k (low half) / odd k (high half)
+  const uint32_t hi = gi == 2 ? 0x00003F80u : (gi == 3 ? 0x3F800000u : 0u);     // k >= 8
+  ColsumSel s;
+  s.l0 = g < 4 ? lo : 0u; s.h0 = g < 4 ? hi : 0u; s.l1 = g < 4 ? 0u : lo; s.h1 = g < 4 ? 0u : hi;
+  return s;
+}
+// pk[j] = packed bf16 pair (column 2 j, column 2 j + 1) of this lane's row, j = 0..7
+__device__ __forceinline__ void warp_colsum16_packed(const uint32_t (&pk)[8], const ColsumSel &s, float &s0, float &s1) {
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  mma16816(d, s.l0, 0u, s.h0, 0u, pk[0], pk[1]);      // columns 0..3   -> rows 0..3
+  mma16816(d, s.l1, 0u, s.h1, 0u, pk[2], pk[3]);      // columns 4..7   -> rows 4..7
+  mma16816(d, 0u, s.l0, 0u, s.h0, pk[4], pk[5]);      // columns 8..11  -> rows 8..11
+  mma16816(d, 0u, s.l1, 0u, s.h1, pk[6], pk[7]);      // columns 12..15 -> rows 12..15
+  float e[4] = {0.f, 0.f, 0.f, 0.f};
+  mma1688_tf32(e, f32_to_tf32(d[0]), f32_to_tf32(d[2]), f32_to_tf32(d[1]), f32_to_tf32(d[3]), 0x3F800000u, 0x3F800000u);
+  s0 = e[0]; s1 = e[2];
 }
 
 // ---- bulk TMA (1-D): global -> shared, completion counted in bytes on an mbarrier -------------
