@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
     // stream has a multiple of NS stages per tile, so every stage's ring slot is a compile-time constant.
     if (elect_one()) {
       const uint8_t *wimg = a.img + (size_t)(blockIdx.x % T256_REP) * a.img_rep_stride;
+      const uint64_t pol_w = l2_policy_evict_last();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bar_xfree, (it & 1u) ^ 1u);                 // FFN1 of the previous tile no longer reads sX
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
           mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
           if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[192 + st] = clock64();
           mbar_expect_tx(&bar_full[slot], bytes);
-          tma_load_1d(sRing + slot * T256_STAGE, wimg + (size_t)st * T256_STAGE, bytes, &bar_full[slot]);
+          tma_load_1d_hint(sRing + slot * T256_STAGE, wimg + (size_t)st * T256_STAGE, bytes, &bar_full[slot], pol_w);
         }
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
             const uint32_t use = use0 + 10u + (uint32_t)c;
             mbar_wait(&bar_empty[j], (use & 1u) ^ 1u);
             mbar_expect_tx(&bar_full[j], 16384u);
-            tma_load_1d(sRing + j * T256_STAGE, wimg + (size_t)(40 + c * 4 + j) * T256_STAGE, 16384u, &bar_full[j]);
+            tma_load_1d_hint(sRing + j * T256_STAGE, wimg + (size_t)(40 + c * 4 + j) * T256_STAGE, 16384u, &bar_full[j], pol_w);
           }
         }
       }

@@ -585,13 +585,14 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
     // ======================= TMA producer =======================
     if (elect_one()) {
       uint32_t it = 0;
+      const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t use0 = it * uses_per_tile;
         auto stage = [&](int st, uint32_t bytes) {
           const int slot = st % NS;
           mbar_wait(&bar_empty[slot], ((use0 + (uint32_t)(st / NS)) & 1u) ^ 1u);
           mbar_expect_tx(&bar_full[slot], bytes);
-          tma_load_1d(sRing + slot * T256_STAGE, wimg + (size_t)st * T256_STAGE, bytes, &bar_full[slot]);
+          tma_load_1d_hint(sRing + slot * T256_STAGE, wimg + (size_t)st * T256_STAGE, bytes, &bar_full[slot], pol_w);
         };
         mbar_wait(&bar_r2b, (it & 1u) ^ 1u);                   // the previous tile's q|k|v recompute no longer reads the x image in r2
         for (int c = 0; c < NCH; ++c) {
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           const uint32_t n = it * (uint32_t)NCH + (uint32_t)c, fs = n & 1u, fu = (n >> 1) & 1u;
           mbar_wait(&bar_hfree[fs], fu ^ 1u);
           mbar_expect_tx(&bar_hready[fs], 16384u);
-          tma_load_1d(sR2 + fs * 32768u, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready[fs]);
+          tma_load_1d_hint(sR2 + fs * 32768u, a.h_img + ((size_t)tile * NCH + c) * 16384, 16384u, &bar_hready[fs], pol_a);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) stage(4 * c + j, 16384u);
         }
@@ -611,8 +612,8 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         }
         mbar_wait(&bar_r2a, it & 1u);                          // dx1 of the last FFN chunk retired: r2 is free for the x image
         mbar_expect_tx(&bar_xready, 65536u);
-        tma_load_1d(sR2, a.x_img_in + (size_t)tile * T256_TILE_IMG, 32768u, &bar_xready);
-        tma_load_1d(sR2 + 32768, a.x_img_in + (size_t)tile * T256_TILE_IMG + 32768, 32768u, &bar_xready);
+        tma_load_1d_hint(sR2, a.x_img_in + (size_t)tile * T256_TILE_IMG, 32768u, &bar_xready, pol_a);
+        tma_load_1d_hint(sR2 + 32768, a.x_img_in + (size_t)tile * T256_TILE_IMG + 32768, 32768u, &bar_xready, pol_a);
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) stage(nfs + j, 16384u);
 #pragma unroll 1
@@ -1042,17 +1043,20 @@ int t256_layer_bwd(const T256Args &a, cudaStream_t st) {
 
 // =============================================================================================
 // weight-gradient kernel: dW = sum over tiles of  A_tile^T B_tile  with both operands taken as MN-major views
-// of the saved [128 tokens x C] images.  CTA = (job, split): job = one [128 x N] block of one weight gradient,
-// split = a contiguous range of tiles.  Two 96 KB stages (A block 32 KB + B up to 64 KB) double-buffer the
-// bulk-TMA loads against the 8 UMMAs of a tile; the accumulator lives in TMEM for the whole CTA and is added
-// to the fp32 gradient with vector atomics at the end.
+// of the saved [128 tokens x C] images.  CTA = (job, split): job = TWO adjacent [128 x N] blocks of one weight gradient
+// (256 output rows), split = a contiguous range of tiles.  The kernel is bound by the bytes it pulls from L2 (~43 B / clock /
+// SM with every SM streaming), so the B image of a tile (up to 64 KB) is fetched once for both 128-row blocks: 128 KB per
+// 8.4 M MACs instead of 96 KB per 4.2 M.  Six 32 KB slots form a ring of sub-stages (see the kernel); the accumulators
+// (2 blocks x [128 x N] fp32) live in TMEM for the CTA's whole tile range and are added to the fp32 gradient with vector
+// atomics at the end.
 // =============================================================================================
 struct T256WJob {
   const uint8_t *a_img, *b_img;       // per-tile images
-  uint32_t a_tile_stride, a_off;      // bytes: tile stride of the A image, offset of this job's 128-column block
+  uint32_t a_tile_stride, a_off;      // bytes: tile stride of the A image, offset of this job's first 128-column block
   uint32_t b_tile_stride, b_bytes;    // B: whole image of the tile ([128 x N])
-  int N;                              // 64..256
-  float *out;                         // out[(m) * ld_m + n * ld_n]
+  int N;                              // 16..256
+  int na;                             // 128-column blocks of A taken by this job: always 2 (adjacent)
+  float *out;                         // out[(m) * ld_m + n * ld_n], m = 0 .. 255
   int ld_m, ld_n;
   int tile0, tile1;
 };
@@ -1060,21 +1064,29 @@ constexpr int T256_WG_MAXJOBS = 160;
 struct T256WgradLaunch {
   T256WJob jobs[T256_WG_MAXJOBS];
 };
+static_assert(sizeof(T256WJob) * T256_WG_MAXJOBS <= T256_WG_JOBBUF, "weight-gradient job list exceeds its device buffer");
 
 __device__ __forceinline__ uint64_t t256_desc_mn(uint32_t base, uint32_t bytes) {      // image [128 rows (k) x cols (mn)]; k16 step = 256 B
   return make_desc(base + bytes, 128u, 2048u);
 }
 
+constexpr uint32_t T256_WG_SLOT = 32768;
+constexpr int T256_WG_SLOTS = 6;
+
+// Sub-stages of a tile, 32 KB each, in ring order: A0 (first 128-column block of A), B0 (first <= 128 columns of B), A1, B1 (the
+// rest of B when N > 128).  Four groups of 8 UMMAs [128 x N/nbh x 16] contract them pairwise — (A0,B0) (A1,B0) (A0,B1) (A1,B1) —
+// and each sub-stage is handed back to the producer right after the last group that reads it has been issued, so 64 - 96 KB of
+// loads are in flight all the time (the kernel is bound by L2 -> SM bytes: bytes in flight / latency is its throughput).
 __global__ void __launch_bounds__(192, 1) t256_wgrad_kernel(const T256WJob *__restrict__ jobs) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+  __shared__ __align__(8) uint64_t bar_full[T256_WG_SLOTS], bar_empty[T256_WG_SLOTS], bar_done;
   __shared__ uint32_t tmem_slot;
   const T256WJob job = jobs[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t STG = 98304;
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1); mbar_init(&bar_done, 1);
+    for (int i = 0; i < T256_WG_SLOTS; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -1082,32 +1094,61 @@ __global__ void __launch_bounds__(192, 1) t256_wgrad_kernel(const T256WJob *__re
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const int ntl = job.tile1 - job.tile0;
+  const int nbh = job.b_bytes > 32768u ? 2 : 1;              // halves of B
+  const int nh = job.N / nbh;                                // columns per half
+  const uint32_t bh_bytes = job.b_bytes / (uint32_t)nbh;
+  const uint32_t ns = 2u + (uint32_t)nbh;                    // sub-stages per tile (job.na == 2)
   if (warp == 4) {
     if (elect_one()) {
+      const uint64_t pol = l2_policy_evict_first();        // every image byte is read once per job: do not let it displace the other kernels' weights
       for (int i = 0; i < ntl; ++i) {
-        const int slot = i & 1;
-        mbar_wait(&bar_empty[slot], (((uint32_t)i >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&bar_full[slot], 32768u + job.b_bytes);
         const size_t tile = (size_t)(job.tile0 + i);
-        tma_load_1d(smem + slot * STG, job.a_img + tile * job.a_tile_stride + job.a_off, 32768u, &bar_full[slot]);
-        for (uint32_t off = 0; off < job.b_bytes; off += 32768u) {
-          const uint32_t nb = job.b_bytes - off < 32768u ? job.b_bytes - off : 32768u;
-          tma_load_1d(smem + slot * STG + 32768 + off, job.b_img + tile * job.b_tile_stride + off, nb, &bar_full[slot]);
+        const uint8_t *ag = job.a_img + tile * job.a_tile_stride + job.a_off, *bg = job.b_img + tile * job.b_tile_stride;
+        for (uint32_t j = 0; j < ns; ++j) {                  // A0, B0, A1, B1
+          const uint32_t q = (uint32_t)i * ns + j, slot = q % T256_WG_SLOTS, use = q / T256_WG_SLOTS;
+          const bool is_a = (j & 1u) == 0u;
+          const uint8_t *src = is_a ? ag + (j >> 1) * 32768u : bg + (j >> 1) * bh_bytes;
+          const uint32_t bytes = is_a ? 32768u : bh_bytes;
+          mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
+          mbar_expect_tx(&bar_full[slot], bytes);
+          tma_load_1d_hint(smem + slot * T256_WG_SLOT, src, bytes, &bar_full[slot], pol);
         }
       }
     }
   } else if (warp == 5) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, job.N, 1, 1);
+      const uint32_t idesc = make_idesc_bf16(128, nh, 1, 1);
+      const uint32_t base = smem_u32(smem);
       for (int i = 0; i < ntl; ++i) {
-        const int slot = i & 1;
-        mbar_wait(&bar_full[slot], ((uint32_t)i >> 1) & 1u);
-        fence_after_sync();
-        const uint32_t base = smem_u32(smem) + slot * STG;
+        uint32_t sl[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_bf16_ss(tmem, t256_desc_mn(base, (uint32_t)k * 256u), t256_desc_mn(base + 32768u, (uint32_t)k * 256u), idesc, (i | k) > 0);
-        mma_commit(&bar_empty[slot]);
+        for (uint32_t j = 0; j < 4; ++j) sl[j] = ((uint32_t)i * ns + j) % T256_WG_SLOTS;
+        auto wait_full = [&](uint32_t j) {
+          mbar_wait(&bar_full[sl[j]], ((((uint32_t)i * ns + j) / T256_WG_SLOTS) & 1u));
+          fence_after_sync();
+        };
+        auto group = [&](uint32_t ja, uint32_t jb, uint32_t acc) {
+          const uint32_t pa = base + sl[ja] * T256_WG_SLOT, pb = base + sl[jb] * T256_WG_SLOT;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_bf16_ss(tmem + acc, t256_desc_mn(pa, (uint32_t)k * 256u), t256_desc_mn(pb, (uint32_t)k * 256u), idesc, (i | k) > 0);
+        };
+        wait_full(0); wait_full(1);
+        group(0, 1, 0u);                                     // A0 x B0
+        wait_full(2);
+        group(2, 1, 256u);                                   // A1 x B0
+        mma_commit(&bar_empty[sl[1]]);
+        if (nbh == 2) {
+          wait_full(3);
+          group(0, 3, 128u);                                 // A0 x B1
+          mma_commit(&bar_empty[sl[0]]);
+          group(2, 3, 256u + 128u);                          // A1 x B1
+          mma_commit(&bar_empty[sl[2]]);
+          mma_commit(&bar_empty[sl[3]]);
+        } else {
+          mma_commit(&bar_empty[sl[0]]);
+          mma_commit(&bar_empty[sl[2]]);
+        }
       }
       mma_commit(&bar_done);
     }
@@ -1116,77 +1157,81 @@ __global__ void __launch_bounds__(192, 1) t256_wgrad_kernel(const T256WJob *__re
     if (ntl > 0) {
       mbar_wait(&bar_done, 0);
       fence_after_sync();
-      const int m = warp * 32 + lane;
       const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-      for (int cb = 0; cb < job.N; cb += 16) {
-        float f[16];
-        tmem_ld16(tmem + lane_off + (uint32_t)cb, f);
-        tmem_ld_wait();
-        if (job.ld_n == 1) {
-          float *o = job.out + (size_t)m * job.ld_m + cb;
+      for (int ab = 0; ab < 2; ++ab) {
+        const int m = ab * 128 + warp * 32 + lane;
+        for (int cb = 0; cb < job.N; cb += 16) {
+          float f[16];
+          // accumulator of (block ab, half h) at column 256 ab + 128 h; inside a half the columns are consecutive
+          tmem_ld16(tmem + (uint32_t)ab * 256u + (uint32_t)(cb / nh) * 128u + (uint32_t)(cb % nh) + lane_off, f);
+          tmem_ld_wait();
+          if (job.ld_n == 1) {
+            float *o = job.out + (size_t)m * job.ld_m + cb;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4 *>(o + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
-        } else {
+            for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4 *>(o + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(job.out + (size_t)m * job.ld_m + (size_t)(cb + j) * job.ld_n, f[j]);
+            for (int j = 0; j < 16; ++j) atomicAdd(job.out + (size_t)m * job.ld_m + (size_t)(cb + j) * job.ld_n, f[j]);
+          }
         }
       }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int t256_wgrad_launch(T256WgradLaunch &L, int nj, void *job_buf, cudaStream_t st) {
+  GT_CUDA(cudaMemcpyAsync(job_buf, L.jobs, sizeof(T256WJob) * nj, cudaMemcpyHostToDevice, st));
+  GT_CUDA(cudaFuncSetAttribute(t256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T256_WG_SLOTS * T256_WG_SLOT)));
+  { LaunchScope _ls(KC_TC_WGRAD, st);
+    t256_wgrad_kernel<<<nj, 192, T256_WG_SLOTS * T256_WG_SLOT, st>>>(reinterpret_cast<const T256WJob *>(job_buf)); }
+  GT_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st) {
-  // job list: dWqkv 6 blocks (A = dqkv cols, B = x), dWo 2 (A = da1, B = ctx), dW1^T 2 (A = x1, B = dH), dW2 2 (A = da2, B = H)
+  // job list (each job = 256 output rows = two 128-column blocks of the A image): dWqkv 3 (A = dqkv, B = x), dWo 1 (A = da1, B = ctx),
+  // per block of <= 256 hidden units: dW1^T 1 (A = x1, B = dH), dW2 1 (A = da2, B = H)
   static thread_local T256WgradLaunch L;
   const int F = a.F, nt = a.n_tiles;
   const uint32_t hbytes = (uint32_t)(128 * F * 2);
-  struct Base { const uint8_t *ai; uint32_t as, ao; const uint8_t *bi; uint32_t bs, bb; int N; float *out; int ldm, ldn; int weight; };
+  struct Base { const uint8_t *ai; uint32_t as, ao; const uint8_t *bi; uint32_t bs, bb; int N; float *out; int ldm, ldn; };
   Base base[16];
   int nb = 0;
-  for (int mb = 0; mb < 6; ++mb)
-    base[nb++] = {a.dqkv_img, (uint32_t)(3 * T256_TILE_IMG), (uint32_t)mb * 32768u, a.x_img, (uint32_t)T256_TILE_IMG, 65536u, 256,
-                  a.gwqkv + (size_t)mb * 128 * 256, 256, 1, 4};
-  for (int mb = 0; mb < 2; ++mb)
-    base[nb++] = {a.da1_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.ctx_img, (uint32_t)T256_TILE_IMG, 65536u, 256,
-                  a.gwo + (size_t)mb * 128 * 256, 256, 1, 4};
+  for (int p = 0; p < 3; ++p)
+    base[nb++] = {a.dqkv_img, (uint32_t)(3 * T256_TILE_IMG), (uint32_t)p * 65536u, a.x_img, (uint32_t)T256_TILE_IMG, 65536u, 256,
+                  a.gwqkv + (size_t)p * 256 * 256, 256, 1};
+  base[nb++] = {a.da1_img, (uint32_t)T256_TILE_IMG, 0u, a.ctx_img, (uint32_t)T256_TILE_IMG, 65536u, 256, a.gwo, 256, 1};
   const int nfb = (F + 255) / 256;                   // N blocks of at most 256 hidden units
   for (int fb = 0; fb < nfb; ++fb) {
     const int Nf = F - fb * 256 < 256 ? F - fb * 256 : 256;
-    const int wgt = Nf > 128 ? 4 : (Nf > 64 ? 2 : 1);
-    for (int mb = 0; mb < 2; ++mb) {
-      // dW1[f][j] = sum_t dH[t][f] x1[t][j]  computed transposed: acc[m = j][n = f]
-      base[nb++] = {a.x1_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.dh_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
-                    a.gw1 + (size_t)fb * 256 * 256 + (size_t)mb * 128, 1, 256, wgt};
-      // dW2[j][f] = sum_t da2[t][j] H[t][f]
-      base[nb++] = {a.da2_img, (uint32_t)T256_TILE_IMG, (uint32_t)mb * 32768u, a.h_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
-                    a.gw2 + (size_t)mb * 128 * F + (size_t)fb * 256, F, 1, wgt};
-    }
+    // dW1[f][j] = sum_t dH[t][f] x1[t][j]  computed transposed: acc[m = j][n = f]
+    base[nb++] = {a.x1_img, (uint32_t)T256_TILE_IMG, 0u, a.dh_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
+                  a.gw1 + (size_t)fb * 256 * 256, 1, 256};
+    // dW2[j][f] = sum_t da2[t][j] H[t][f]
+    base[nb++] = {a.da2_img, (uint32_t)T256_TILE_IMG, 0u, a.h_img + (size_t)fb * 65536, hbytes, (uint32_t)(Nf * 256), Nf,
+                  a.gw2 + (size_t)fb * 256, F, 1};
   }
-  int wsum = 0;
-  for (int i = 0; i < nb; ++i) wsum += base[i].weight;
+  // CTAs per job in proportion to the bytes a tile of the job pulls from L2 (that is what bounds the kernel)
+  int64_t wsum = 0;
+  for (int i = 0; i < nb; ++i) wsum += 65536 + base[i].bb;
   const int sms = t256_num_sms();
   int nj = 0;
   for (int i = 0; i < nb; ++i) {
-    int splits = (int)((int64_t)sms * base[i].weight / wsum);
+    int splits = (int)((int64_t)sms * (65536 + base[i].bb) / wsum);
     if (splits < 1) splits = 1;
     if (splits > nt) splits = nt;
     for (int s = 0; s < splits && nj < T256_WG_MAXJOBS; ++s) {
       T256WJob &j = L.jobs[nj++];
       j.a_img = base[i].ai; j.a_tile_stride = base[i].as; j.a_off = base[i].ao;
-      j.b_img = base[i].bi; j.b_tile_stride = base[i].bs; j.b_bytes = base[i].bb; j.N = base[i].N;
+      j.b_img = base[i].bi; j.b_tile_stride = base[i].bs; j.b_bytes = base[i].bb; j.N = base[i].N; j.na = 2;
       j.out = base[i].out; j.ld_m = base[i].ldm; j.ld_n = base[i].ldn;
       j.tile0 = (int)((int64_t)nt * s / splits); j.tile1 = (int)((int64_t)nt * (s + 1) / splits);
     }
   }
-  GT_CUDA(cudaMemcpyAsync(job_buf, L.jobs, sizeof(T256WJob) * nj, cudaMemcpyHostToDevice, st));
-  GT_CUDA(cudaFuncSetAttribute(t256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 98304));
-  { LaunchScope _ls(KC_TC_WGRAD, st);
-    t256_wgrad_kernel<<<nj, 192, 2 * 98304, st>>>(reinterpret_cast<const T256WJob *>(job_buf)); }
-  GT_CUDA(cudaGetLastError());
-  return 0;
+  return t256_wgrad_launch(L, nj, job_buf, st);
 }
 
 // out[256][N] (row stride N) += sum over tiles of A_tile^T B_tile: A = [128 x 256] images (tile stride 64 KB), B = [128 x N] images
@@ -1195,25 +1240,19 @@ int t256_wgrad(const T256WgradArgs &a, void *job_buf, cudaStream_t st) {
 int t256_wgrad_pair(const uint8_t *a_img, const uint8_t *b_img, int N, float *out, int n_tiles, void *job_buf, cudaStream_t st) {
   static thread_local T256WgradLaunch L;
   GT_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "t256_wgrad_pair: N must be a multiple of 16 in [16, 256]");
-  const int sms = t256_num_sms();
-  int splits = sms / 2;
+  int splits = t256_num_sms();
+  if (splits > T256_WG_MAXJOBS) splits = T256_WG_MAXJOBS;
   if (splits > n_tiles) splits = n_tiles;
   if (splits < 1) splits = 1;
   int nj = 0;
-  for (int mb = 0; mb < 2; ++mb)
-    for (int s = 0; s < splits; ++s) {
-      T256WJob &j = L.jobs[nj++];
-      j.a_img = a_img; j.a_tile_stride = (uint32_t)T256_TILE_IMG; j.a_off = (uint32_t)mb * 32768u;
-      j.b_img = b_img; j.b_tile_stride = (uint32_t)(128 * N * 2); j.b_bytes = (uint32_t)(128 * N * 2); j.N = N;
-      j.out = out + (size_t)mb * 128 * N; j.ld_m = N; j.ld_n = 1;
-      j.tile0 = (int)((int64_t)n_tiles * s / splits); j.tile1 = (int)((int64_t)n_tiles * (s + 1) / splits);
-    }
-  GT_CUDA(cudaMemcpyAsync(job_buf, L.jobs, sizeof(T256WJob) * nj, cudaMemcpyHostToDevice, st));
-  GT_CUDA(cudaFuncSetAttribute(t256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 98304));
-  { LaunchScope _ls(KC_TC_WGRAD, st);
-    t256_wgrad_kernel<<<nj, 192, 2 * 98304, st>>>(reinterpret_cast<const T256WJob *>(job_buf)); }
-  GT_CUDA(cudaGetLastError());
-  return 0;
+  for (int s = 0; s < splits; ++s) {
+    T256WJob &j = L.jobs[nj++];
+    j.a_img = a_img; j.a_tile_stride = (uint32_t)T256_TILE_IMG; j.a_off = 0u;
+    j.b_img = b_img; j.b_tile_stride = (uint32_t)(128 * N * 2); j.b_bytes = (uint32_t)(128 * N * 2); j.N = N; j.na = 2;
+    j.out = out; j.ld_m = N; j.ld_n = 1;
+    j.tile0 = (int)((int64_t)n_tiles * s / splits); j.tile1 = (int)((int64_t)n_tiles * (s + 1) / splits);
+  }
+  return t256_wgrad_launch(L, nj, job_buf, st);
 }
 
 }  // namespace gt

@@ -244,6 +244,24 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                : "memory");
 }
 
+// the same copy with an L2 eviction-priority hint (createpolicy): the weight stage streams are re-read by every CTA for every tile
+// (evict_last) while ~3 MB of activations per tile stream through L2 once (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // asynchronous L2 prefetch of a contiguous global range (bytes: multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
