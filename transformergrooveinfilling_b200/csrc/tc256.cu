@@ -428,6 +428,10 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_fwd_kernel(const T
   const uint32_t t_out = tmem, t_qkv = tmem + 256;
   auto t_h_slot = [&](uint32_t fs) { return fs ? tmem + 256u : tmem + 448u; };
   const uint32_t aX = smem_u32(sX), aRing = smem_u32(sRing), aH = smem_u32(sH), aCtx = smem_u32(sCtx);
+  if (a.stagger) {                                    // see t256_launch_bwd
+    const long long until = clock64() + (long long)(blockIdx.x & 3) * (long long)a.stagger;
+    while (clock64() < until) __nanosleep(200);
+  }
 
   if (warp == 16) {
     // ======================= TMA producer: x image of the tile, then its weight stage stream =======================
@@ -946,7 +950,9 @@ int t256_num_sms() {
 template <int DH>
 static int t256_launch_fwd(const T256Args &a_in, int grid, cudaStream_t st) {
   static T256Dbg dbg;
+  static const uint32_t stagger = getenv("GT_T256_STAGGER_FWD") ? (uint32_t)atoi(getenv("GT_T256_STAGGER_FWD")) : 0u;
   T256Args a = a_in;
+  a.stagger = a.n_tiles >= 16 * grid ? stagger : 0u;
   const bool d = dbg.arm(a, st);
   if (drop_args_devstep(a)) {                // graph replay: dropout keys derived on the device from the step counter
     GT_CUDA(cudaFuncSetAttribute(t256_layer_fwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256FwdSmem::total));

@@ -136,6 +136,7 @@ struct T256Args {
   int n_tiles, F, H, dh;
   Drop d_attn, d1, d_ffn, d2;
   int64_t seq0;
+  uint32_t stagger;                      // backward: CTA b starts (b % 4) * stagger clocks late, so that the HBM-heavy phases of the persistent CTAs do not coincide
   unsigned long long *dbg;               // optional clock64 timeline of CTA 0 (GT_T256_DBG=n)
 };
 

@@ -32,12 +32,19 @@ static_assert(T256BwdSmem::total <= 227 * 1024 - 1024, "backward shared memory b
 // sS: scratch image [128 x 256]: cols [0,64) q (scaled by log2e/sqrt(dh)), [64,128) k, [128,192) v, [192,256) dO.
 // dq / dk / dv overwrite q / k / v in place (this warp is the only reader of those rows x columns).
 // g_b: shared-memory partial sums of the in-projection bias gradient for this group: [3][64].
+// Arithmetic of tc_attn32.cuh: with c = 1/sqrt(dh), E = exp2(s - max) and r = rowsum(E), the two bf16 fragments are
+// c Pd = keep ? E (c ks / r) : 0 and c dS = (c Pd) dO.V - E (c / r) rowsum((c Pd) dO.V) sqrt(dh) — one multiply and one FMA per
+// probability after the exponential; dq = (c dS) K needs no scale, dk and dv take theirs (ln2 sqrt(dh), sqrt(dh)) when stored.
+// Operand fragments of the score contractions come from ldmatrix (a core matrix of the image = 8 rows x 16 bytes).
 template <int DH>
 __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int lane, const Drop &dr, uint64_t w_pair, float *g_b) {
   const int g = lane >> 2, t = lane & 3;
   const int qc = hl * DH, kc = 64 + hl * DH, vc = 128 + hl * DH, oc = 192 + hl * DH;
-  const float inv_sqrt_dh = rsqrtf((float)DH), ln2 = 0.6931471805599453f, ks = dr.scale;
+  const float c1 = rsqrtf((float)DH), rc1 = sqrtf((float)DH), ks = dr.scale;
+  const float dk_scale = 0.6931471805599453f * rc1;
   const int mi = lane >> 3, rr = lane & 7;
+  // lane address of the B-operand tiles (keys x 16 features): matrix (l >> 3) = keys 8 (mi >> 1).., features 8 (mi & 1)..
+  const uint32_t offB = kmajor_off(s * 32 + (mi >> 1) * 8 + rr, kc + (mi & 1) * 8, 128);
   float dk[2][DH / 8][4], dv[2][DH / 8][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -52,6 +59,8 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
 #pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int r0 = s * 32 + 16 * mt + g;             // query rows r0, r0 + 8
+    // A-operand tiles (queries x 16 features): matrix (l >> 3) = rows 8 (mi & 1).., features 8 (mi >> 1)..
+    const uint32_t offA = kmajor_off(s * 32 + 16 * mt + (mi & 1) * 8 + rr, qc + (mi >> 1) * 8, 128);
     float p[4][4], dp[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -59,17 +68,22 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
       for (int c = 0; c < 4; ++c) { p[i][c] = 0.f; dp[i][c] = 0.f; }
 #pragma unroll
     for (int kt = 0; kt < DH / 16; ++kt) {
-      const int c0 = 16 * kt + 2 * t;
-      const uint32_t a0 = lds32(sS + kmajor_off(r0, qc + c0, 128)), a1 = lds32(sS + kmajor_off(r0 + 8, qc + c0, 128));
-      const uint32_t a2 = lds32(sS + kmajor_off(r0, qc + c0 + 8, 128)), a3 = lds32(sS + kmajor_off(r0 + 8, qc + c0 + 8, 128));
-      const uint32_t o0 = lds32(sS + kmajor_off(r0, oc + c0, 128)), o1 = lds32(sS + kmajor_off(r0 + 8, oc + c0, 128));
-      const uint32_t o2 = lds32(sS + kmajor_off(r0, oc + c0 + 8, 128)), o3 = lds32(sS + kmajor_off(r0 + 8, oc + c0 + 8, 128));
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int key = s * 32 + 8 * nt + g;
-        mma16816(p[nt], a0, a1, a2, a3, lds32(sS + kmajor_off(key, kc + c0, 128)), lds32(sS + kmajor_off(key, kc + c0 + 8, 128)));
-        mma16816(dp[nt], o0, o1, o2, o3, lds32(sS + kmajor_off(key, vc + c0, 128)), lds32(sS + kmajor_off(key, vc + c0 + 8, 128)));
-      }
+      const uint32_t cstep = (uint32_t)kt * 4096u;    // 16 feature columns = two 8-column slabs of 2048 B
+      uint32_t aq[4], ao[4], bk0[4], bk1[4], bv0[4], bv1[4];
+      ldmatrix_x4(aq, sS + offA + cstep);
+      ldmatrix_x4(ao, sS + offA + 192u * 256u + cstep);
+      ldmatrix_x4(bk0, sS + offB + cstep);
+      ldmatrix_x4(bk1, sS + offB + 256u + cstep);
+      ldmatrix_x4(bv0, sS + offB + 64u * 256u + cstep);
+      ldmatrix_x4(bv1, sS + offB + 64u * 256u + 256u + cstep);
+      mma16816(p[0], aq[0], aq[1], aq[2], aq[3], bk0[0], bk0[1]);
+      mma16816(p[1], aq[0], aq[1], aq[2], aq[3], bk0[2], bk0[3]);
+      mma16816(p[2], aq[0], aq[1], aq[2], aq[3], bk1[0], bk1[1]);
+      mma16816(p[3], aq[0], aq[1], aq[2], aq[3], bk1[2], bk1[3]);
+      mma16816(dp[0], ao[0], ao[1], ao[2], ao[3], bv0[0], bv0[1]);
+      mma16816(dp[1], ao[0], ao[1], ao[2], ao[3], bv0[2], bv0[3]);
+      mma16816(dp[2], ao[0], ao[1], ao[2], ao[3], bv1[0], bv1[1]);
+      mma16816(dp[3], ao[0], ao[1], ao[2], ao[3], bv1[2], bv1[3]);
     }
     // softmax (rows r0: c0,c1 ; r0+8: c2,c3)
     float m0 = p[0][0], m1 = p[0][2];
@@ -86,59 +100,51 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float i0 = 1.f / s0, i1 = 1.f / s1;
-    // dropout keep bits of this lane's 16 probabilities: bit (4 nt + c)
-    uint32_t keep = 0xFFFFu;
+    const float i0 = c1 / s0, i1 = c1 / s1;
+    // pd = keep ? E (c ks / rowsum) : 0   (= c x the dropped probability)
+    float pdm[4][4];
     if (dr.thr) {
-      keep = 0;
       const int q0 = 16 * mt + g;
       const uint64_t wa = w_pair + (uint64_t)q0 * 8u, wb = wa + 64u;      // quad index of position 0 of rows q0 and q0 + 8
       const uint32_t alo = (uint32_t)wa, ahi = (uint32_t)(wa >> 32) * 0x85EBCA6Bu;
       const uint32_t blo = (uint32_t)wb, bhi = (uint32_t)(wb >> 32) * 0x85EBCA6Bu;
+      const float k0 = i0 * ks, k1 = i1 * ks;
 #pragma unroll
       for (int np = 0; np < 2; ++np) {            // quad 4 np + t = this lane's keys of nt = 2 np, 2 np + 1 (common.cuh: key_perm)
         uint32_t la, ha, lb, hb;
         hash_quad((alo + (uint32_t)(4 * np + t)) ^ ahi, dr.key, la, ha);
         hash_quad((blo + (uint32_t)(4 * np + t)) ^ bhi, dr.key, lb, hb);
-        keep |= ((la & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np);
-        keep |= ((la >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 1);
-        keep |= ((lb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 2);
-        keep |= ((lb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 3);
-        keep |= ((ha & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 4);
-        keep |= ((ha >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 5);
-        keep |= ((hb & 0xFFFFu) >= dr.thr ? 1u : 0u) << (8 * np + 6);
-        keep |= ((hb >> 16) >= dr.thr ? 1u : 0u) << (8 * np + 7);
+        pdm[2 * np][0] = ((la & 0xFFFFu) >= dr.thr) ? p[2 * np][0] * k0 : 0.f;
+        pdm[2 * np][1] = ((la >> 16) >= dr.thr) ? p[2 * np][1] * k0 : 0.f;
+        pdm[2 * np + 1][0] = ((ha & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][0] * k0 : 0.f;
+        pdm[2 * np + 1][1] = ((ha >> 16) >= dr.thr) ? p[2 * np + 1][1] * k0 : 0.f;
+        pdm[2 * np][2] = ((lb & 0xFFFFu) >= dr.thr) ? p[2 * np][2] * k1 : 0.f;
+        pdm[2 * np][3] = ((lb >> 16) >= dr.thr) ? p[2 * np][3] * k1 : 0.f;
+        pdm[2 * np + 1][2] = ((hb & 0xFFFFu) >= dr.thr) ? p[2 * np + 1][2] * k1 : 0.f;
+        pdm[2 * np + 1][3] = ((hb >> 16) >= dr.thr) ? p[2 * np + 1][3] * k1 : 0.f;
       }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { pdm[nt][0] = p[nt][0] * i0; pdm[nt][1] = p[nt][1] * i0; pdm[nt][2] = p[nt][2] * i1; pdm[nt][3] = p[nt][3] * i1; }
     }
-    // P, dropped P (pd), dL/dP through the dropout, delta = rowsum(dPd * P), dS = P (dPd - delta)
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        p[nt][c] *= (c < 2 ? i0 : i1);
-        dp[nt][c] = ((keep >> (4 * nt + c)) & 1u) ? dp[nt][c] * ks : 0.f;
-      }
-      d0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
-      d1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+      dp[nt][0] *= pdm[nt][0]; dp[nt][1] *= pdm[nt][1]; dp[nt][2] *= pdm[nt][2]; dp[nt][3] *= pdm[nt][3];
+      d0 += dp[nt][0] + dp[nt][1];
+      d1 += dp[nt][2] + dp[nt][3];
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    // packed bf16 fragments: pdp = dropped probabilities, dsq = dS / sqrt(dh) (for dq), dsk = dS * ln2 (for dk; q is stored scaled)
-    uint32_t pdp[4][2], dsq[4][2], dsk[4][2];
+    const float e0 = -(d0 * rc1) * i0, e1 = -(d1 * rc1) * i1;
+    uint32_t pdp[4][2], dsq[4][2];                  // c x dropped probabilities, c x dS
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      float ds[4], pd[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        ds[c] = p[nt][c] * (dp[nt][c] - (c < 2 ? d0 : d1));
-        pd[c] = ((keep >> (4 * nt + c)) & 1u) ? p[nt][c] * ks : 0.f;
-      }
-      pdp[nt][0] = pack_bf16(pd[0], pd[1]); pdp[nt][1] = pack_bf16(pd[2], pd[3]);
-      dsq[nt][0] = pack_bf16(ds[0] * inv_sqrt_dh, ds[1] * inv_sqrt_dh); dsq[nt][1] = pack_bf16(ds[2] * inv_sqrt_dh, ds[3] * inv_sqrt_dh);
-      dsk[nt][0] = pack_bf16(ds[0] * ln2, ds[1] * ln2); dsk[nt][1] = pack_bf16(ds[2] * ln2, ds[3] * ln2);
+      pdp[nt][0] = pack_bf16(pdm[nt][0], pdm[nt][1]); pdp[nt][1] = pack_bf16(pdm[nt][2], pdm[nt][3]);
+      dsq[nt][0] = pack_bf16(fmaf(p[nt][0], e0, dp[nt][0]), fmaf(p[nt][1], e0, dp[nt][1]));
+      dsq[nt][1] = pack_bf16(fmaf(p[nt][2], e1, dp[nt][2]), fmaf(p[nt][3], e1, dp[nt][3]));
     }
-    // dk += dS^T Q ; dv += Pd^T dO   (contraction over this m-tile's 16 queries; A = transposed fragments)
+    // dk += (c dS)^T Q ; dv += (c Pd)^T dO   (contraction over this m-tile's 16 queries; A = transposed fragments)
 #pragma unroll
     for (int np = 0; np < DH / 16; ++np) {
       const int qrow = s * 32 + 16 * mt + (mi & 1) * 8 + rr;
@@ -147,8 +153,8 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
       ldmatrix_x4_trans(bo, sS + kmajor_off(qrow, oc + 16 * np + (mi >> 1) * 8, 128));
 #pragma unroll
       for (int kmt = 0; kmt < 2; ++kmt) {
-        const uint32_t s0t = movmatrix_trans(dsk[2 * kmt][0]), s1t = movmatrix_trans(dsk[2 * kmt + 1][0]);
-        const uint32_t s2t = movmatrix_trans(dsk[2 * kmt][1]), s3t = movmatrix_trans(dsk[2 * kmt + 1][1]);
+        const uint32_t s0t = movmatrix_trans(dsq[2 * kmt][0]), s1t = movmatrix_trans(dsq[2 * kmt + 1][0]);
+        const uint32_t s2t = movmatrix_trans(dsq[2 * kmt][1]), s3t = movmatrix_trans(dsq[2 * kmt + 1][1]);
         mma16816(dk[kmt][2 * np], s0t, s1t, s2t, s3t, bq[0], bq[1]);
         mma16816(dk[kmt][2 * np + 1], s0t, s1t, s2t, s3t, bq[2], bq[3]);
         const uint32_t p0t = movmatrix_trans(pdp[2 * kmt][0]), p1t = movmatrix_trans(pdp[2 * kmt + 1][0]);
@@ -157,7 +163,7 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
         mma16816(dv[kmt][2 * np + 1], p0t, p1t, p2t, p3t, bo[2], bo[3]);
       }
     }
-    // dq = (dS / sqrt(dh)) K
+    // dq = (c dS) K
     float dq[DH / 8][4];
 #pragma unroll
     for (int b = 0; b < DH / 8; ++b) { dq[b][0] = 0.f; dq[b][1] = 0.f; dq[b][2] = 0.f; dq[b][3] = 0.f; }
@@ -185,6 +191,8 @@ __device__ __forceinline__ void t256_attn_bwd(uint8_t *sS, int s, int hl, int la
   for (int kmt = 0; kmt < 2; ++kmt)
 #pragma unroll
     for (int nt = 0; nt < DH / 8; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { dk[kmt][nt][c] *= dk_scale; dv[kmt][nt][c] *= rc1; }
       const int kr = s * 32 + 16 * kmt + g;
       *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr, kc + 8 * nt + 2 * t, 128)) = pack_bf16(dk[kmt][nt][0], dk[kmt][nt][1]);
       *reinterpret_cast<uint32_t *>(sS + kmajor_off(kr + 8, kc + 8 * nt + 2 * t, 128)) = pack_bf16(dk[kmt][nt][2], dk[kmt][nt][3]);
@@ -417,6 +425,8 @@ __device__ __forceinline__ void t256_attn_bwd128(uint8_t *imgE, uint8_t *imgO, u
 template <class DyLoad>
 __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*global tile image*/, const float2 *stat /*this row's (mean, rstd)*/,
                                             const float *gamma, uint32_t t_du /*TMEM: this thread's row, column 0*/,
+                                            uint32_t t_dy /*TMEM stash for dy (256 columns), or 0xFFFFFFFF: dyv is cheap to call again*/,
+                                            uint32_t t_u /*TMEM stash for the packed u words: 8 columns at the head of every 16-column chunk*/,
                                             uint8_t *sImg, uint8_t *gImg, const Drop &dr, uint64_t e_row /* element index of (row, col 0) */,
                                             float *g_gamma, float *g_beta, float *g_bias, float *sStatA, float *sStatB, int row, int part, int lane,
                                             unsigned long long *dbg, int &ndbg) {
@@ -443,6 +453,13 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
       dyv(cb + 16, dyn);
       un0 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256); un1 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256 + 2048);
     }
+    {
+      // pass C takes this chunk's dy and u back from tensor memory instead of from L2 (both phases are bound by global-load
+      // latency and SM <-> L2 bytes; a TMEM round trip costs neither)
+      const uint32_t uw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      tmem_st8(t_u + (uint32_t)(part * 64 + cb), uw);
+      if (t_dy != 0xFFFFFFFFu) tmem_st16(t_dy + (uint32_t)(part * 64 + cb), dy);
+    }
     const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
                           bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
     uint32_t pg[8], pb[8];                            // bf16 pairs of dy * xhat (-> dgamma) and dy (-> dbeta)
@@ -466,9 +483,7 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
   }
   LN_STAMP();
   sStatA[row * 4 + part] = m1; sStatB[row * 4 + part] = m2;
-  // first chunk of pass C: issued before the barrier, so its latency overlaps the exchange of the row sums
-  dyv(0, dyn);
-  un0 = *reinterpret_cast<const uint4 *>(u_row); un1 = *reinterpret_cast<const uint4 *>(u_row + 2048);
+  tmem_st_wait();                                    // the stashes of pass B are in tensor memory
   named_bar_sync(1, T256_CTHREADS);
   LN_STAMP();
   {
@@ -486,15 +501,12 @@ __device__ __forceinline__ void t256_ln_bwd(DyLoad dyv, const uint8_t *u_img /*g
     float w[16];
     {
       float dy[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dy[j] = dyn[j];
-      const uint4 v0 = un0, v1 = un1;
-      if (cb + 16 < 64) {
-        dyv(cb + 16, dyn);
-        un0 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256); un1 = *reinterpret_cast<const uint4 *>(u_row + (cb + 16) * 256 + 2048);
-      }
-      const float uu[16] = {bf16lo(v0.x), bf16hi(v0.x), bf16lo(v0.y), bf16hi(v0.y), bf16lo(v0.z), bf16hi(v0.z), bf16lo(v0.w), bf16hi(v0.w),
-                            bf16lo(v1.x), bf16hi(v1.x), bf16lo(v1.y), bf16hi(v1.y), bf16lo(v1.z), bf16hi(v1.z), bf16lo(v1.w), bf16hi(v1.w)};
+      uint32_t uw[8];
+      tmem_ld8(t_u + (uint32_t)(part * 64 + cb), reinterpret_cast<float *>(uw));
+      if (t_dy != 0xFFFFFFFFu) { tmem_ld16(t_dy + (uint32_t)(part * 64 + cb), dy); tmem_ld_wait(); }
+      else dyv(cb, dy);                               // (waits for its own TMEM load, which also completes the one above)
+      const float uu[16] = {bf16lo(uw[0]), bf16hi(uw[0]), bf16lo(uw[1]), bf16hi(uw[1]), bf16lo(uw[2]), bf16hi(uw[2]), bf16lo(uw[3]), bf16hi(uw[3]),
+                            bf16lo(uw[4]), bf16hi(uw[4]), bf16lo(uw[5]), bf16hi(uw[5]), bf16lo(uw[6]), bf16hi(uw[6]), bf16lo(uw[7]), bf16hi(uw[7])};
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const float4 gm = *reinterpret_cast<const float4 *>(gamma + part * 64 + cb + j);
@@ -577,6 +589,10 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
   const uint32_t tmem = tmem_slot;
   const uint32_t t_dx = tmem, t_b = tmem + 256;
   const uint32_t aR1 = smem_u32(sR1), aR2 = smem_u32(sR2), aRing = smem_u32(sRing);
+  if (a.stagger) {
+    const long long until = clock64() + (long long)(blockIdx.x & 3) * (long long)a.stagger;
+    while (clock64() < until) __nanosleep(200);
+  }
   const int nfs = 4 * NCH;                          // FFN stages per tile
   const uint32_t uses_per_tile = H128 ? (uint32_t)(8 + NCH) : (uint32_t)(16 + NCH);   // stages per tile / NS: (64 + 4 NCH) / 4, head_dim 128: (32 + 4 NCH) / 4
   const uint8_t *wimg = a.img + (size_t)(blockIdx.x % T256_REP) * a.img_rep_stride + (size_t)t256_fwd_stages(F) * T256_STAGE;
@@ -787,7 +803,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             o[j] = v.x; o[j + 1] = v.y; o[j + 2] = v.z; o[j + 3] = v.w;
           }
         };
-        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, a.ln2_stat + grow, p_g2, t_dx + lane_off, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
+        t256_ln_bwd(dyload, a.u2_img + (size_t)tile * T256_TILE_IMG, a.ln2_stat + grow, p_g2, t_dx + lane_off, t_b + lane_off, t_dx + lane_off, sR1, a.da2_img + (size_t)tile * T256_TILE_IMG, a.d2, e_row,
                     g_g2, g_be2, g_b2, sStatA, sStatB, row, part, lane, dbg_on ? a.dbg : nullptr, ndbg);
       }
       tmem_st_wait();                                 // du2 sits in t_dx: dx1 accumulates onto it
@@ -842,7 +858,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), o);
           tmem_ld_wait();
         };
-        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, a.ln1_stat + grow, p_g1, t_dx + lane_off, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
+        t256_ln_bwd(dyload, a.u1_img + (size_t)tile * T256_TILE_IMG, a.ln1_stat + grow, p_g1, t_dx + lane_off, 0xFFFFFFFFu, t_b + lane_off, sR1, a.da1_img + (size_t)tile * T256_TILE_IMG, a.d1, e_row,
                     g_g1, g_be1, g_bo, sStatA, sStatB, row, part, lane, dbg_on ? a.dbg : nullptr, ndbg);
       }
       tmem_st_wait();                                 // du1 sits in t_dx: dx_in accumulates onto it
@@ -1010,7 +1026,13 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
 template <int DH>
 static int t256_launch_bwd(const T256Args &a_in, int grid, cudaStream_t st) {
   static T256Dbg dbg;
+  // Persistent CTAs with equal work run in lockstep, so their HBM-heavy phases (LayerNorm2 backward pulls dy + u2 while the dx
+  // rows of the previous tile drain: ~90 % of the HBM peak with every SM in that phase) coincide and the HBM idles during the
+  // attention phases.  Starting CTA b (b % 4) * 20 K clocks late spreads them out: C4 backward 20.3 -> 19.7 ms per step.
+  // Only for launches long enough (>= 16 tiles per CTA) that the late start is < 3 % of the kernel.
+  static const uint32_t stagger = getenv("GT_T256_STAGGER") ? (uint32_t)atoi(getenv("GT_T256_STAGGER")) : 20000u;
   T256Args a = a_in;
+  a.stagger = a.n_tiles >= 16 * grid ? stagger : 0u;
   const bool d = dbg.arm(a, st);
   if (drop_args_devstep(a)) {
     GT_CUDA(cudaFuncSetAttribute(t256_layer_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T256BwdSmem::total));
