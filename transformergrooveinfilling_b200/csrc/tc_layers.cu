@@ -744,6 +744,24 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   }
   return v[0];
 }
+// LayerNorm-backward column sums of one warp (lane = token row): w[0..7] -> dgamma, w[8..15] -> dbeta, w[16..23] -> bias of the
+// sub-layer, each for the thread's 8 feature columns.  On the tensor cores (umma.cuh: warp_colsum16_packed; inputs rounded to
+// bf16 like every other column sum here): 12 conversions + 7 mma.sync instead of the 31-shuffle butterfly of warp_colsum32.
+__device__ __forceinline__ void ln_bwd_colsums(const float (&w)[32], int lane, float *gg, float *gbe, float *gb) {
+  const ColsumSel sel = colsum_sel(lane);
+  uint32_t pa[8], pb[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pa[j] = pack_bf16(w[2 * j], w[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pb[j] = pack_bf16(w[16 + 2 * j], w[16 + 2 * j + 1]);
+  float s0, s1;
+  warp_colsum16_packed(pa, sel, s0, s1);
+  const float s2 = warp_colsum8_packed(pb, sel);
+  const int g = lane >> 2, t = lane & 3;
+  if (t == 0) atomicAdd(gg + g, s0);
+  else if (t == 1) atomicAdd(gbe + g, s1);
+  else if (t == 2) atomicAdd(gb + g, s2);
+}
 __device__ __forceinline__ float warp_sum_all(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -933,10 +951,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<uint4 *>(sDA + kmajor_off(row, c0, 128)) =
             make_uint4(pack_bf16(w[16] * fs, w[17] * fs), pack_bf16(w[18] * fs, w[19] * fs), pack_bf16(w[20] * fs, w[21] * fs),
                        pack_bf16(w[22] * fs, w[23] * fs));
-        const float t = warp_colsum32(w, lane);
-        if (lane < 8) atomicAdd(&g_g2[c0 + lane], t);
-        else if (lane < 16) atomicAdd(&g_be2[c0 + lane - 8], t);
-        else if (lane < 24) atomicAdd(&g_b2[c0 + lane - 16], t);
+        ln_bwd_colsums(w, lane, g_g2 + c0, g_be2 + c0, g_b2 + c0);
       }
     }
     fence_async_smem();
@@ -1000,7 +1015,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      colsum_image(sDH, FC >> 3, g_b1 + c * FC, warp, lane, BWD_THREADS / 32);      // linear1 bias gradient: column sums of the dH image
       if (tid == 0) {
         fence_after_sync();
         if (c + 1 < nchunk) {                         // H(c + 1) first, with its own barrier (t_big: the dH(c) accumulator is drained)
@@ -1019,6 +1033,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         }
         if (c + 1 == nchunk) mma_commit(&bar_mma);    // earlier chunks: covered by the dH commit of the next chunk
       }
+      // linear1 bias gradient: column sums of the dH image — AFTER the issue, so that it overlaps the round trip of H(c + 1) instead
+      // of delaying it (the image is rewritten only behind the __syncthreads that follows the next chunk's H epilogue)
+      colsum_image(sDH, FC >> 3, g_b1 + c * FC, warp, lane, BWD_THREADS / 32);
     }
     mbar_wait(&bar_mma, ph); ph ^= 1;                 // dx1 complete, all weight-gradient MMAs of this tile retired
     fence_after_sync();
@@ -1091,10 +1108,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
         *reinterpret_cast<float4 *>(a.dx + grow * D + c0) = make_float4(du[0], du[1], du[2], du[3]);
         *reinterpret_cast<float4 *>(a.dx + grow * D + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
       }
-      const float t = warp_colsum32(w, lane);
-      if (lane < 8) atomicAdd(&g_g1[c0 + lane], t);
-      else if (lane < 16) atomicAdd(&g_be1[c0 + lane - 8], t);
-      else if (lane < 24) atomicAdd(&g_bo[c0 + lane - 16], t);
+      ln_bwd_colsums(w, lane, g_g1 + c0, g_be1 + c0, g_bo + c0);
     }
     fence_async_smem();
     fence_before_sync();

@@ -243,6 +243,16 @@ __device__ __forceinline__ void warp_colsum16_packed(const uint32_t (&pk)[8], co
   s0 = e[0]; s1 = e[2];
 }
 
+// 8 columns only (pk[j] = columns 2 j, 2 j + 1): every lane (g, t) receives the sum of column g
+__device__ __forceinline__ float warp_colsum8_packed(const uint32_t (&pk)[4], const ColsumSel &s) {
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  mma16816(d, s.l0, 0u, s.h0, 0u, pk[0], pk[1]);      // columns 0..3 -> rows 0..3
+  mma16816(d, s.l1, 0u, s.h1, 0u, pk[2], pk[3]);      // columns 4..7 -> rows 4..7
+  float e[4] = {0.f, 0.f, 0.f, 0.f};
+  mma1688_tf32(e, f32_to_tf32(d[0]), 0u, f32_to_tf32(d[1]), 0u, 0x3F800000u, 0x3F800000u);
+  return e[0];
+}
+
 // ---- bulk TMA (1-D): global -> shared, completion counted in bytes on an mbarrier -------------
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
