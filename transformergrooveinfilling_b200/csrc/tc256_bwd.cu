@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
   using S = T256BwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_da2ready, bar_hready[2], bar_hfree[2], bar_dhfull[2], bar_dhimgready[2], bar_r2a,
-      bar_r2b, bar_dx1full, bar_da1ready, bar_dctxfull, bar_xready, bar_qkvfree, bar_qkvfull, bar_dqkvready, bar_dqkvfree, bar_dxinfull;
+      bar_r2b, bar_dx1full, bar_da1ready, bar_dctxfull, bar_xready, bar_qkvfree, bar_qkvfull, bar_dqkvready, bar_dqkvfree, bar_dxinfull, bar_qkvstaged;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = a.F, NCH = F / 64, H = a.H;
@@ -578,6 +578,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
                         &bar_dhimgready[0], &bar_dhimgready[1], &bar_r2a, &bar_r2b, &bar_dx1full, &bar_da1ready,
                         &bar_dctxfull, &bar_xready, &bar_qkvfree, &bar_qkvfull, &bar_dqkvready, &bar_dqkvfree, &bar_dxinfull};
     for (uint64_t *b : bars) mbar_init(b, 1);
+    mbar_init(&bar_qkvstaged, 2);                     // head_dim 128: one arrive.expect_tx per saved q | k | v group image of a head
     fence_mbar_init();
   }
   for (int i = tid; i < 768; i += T256_THREADS) p_bqkv[i] = a.bqkv[i];
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             }
             mma_commit(&bar_dqkvfree);
           }
-          mma_commit(&bar_dxinfull);                      // (bar_r2b is raised by the compute warps: the bulk stores of dq | dk | dv read r2 too)
+          mma_commit(&bar_dxinfull);                      // (bar_r2b is raised by the compute warps at the end of the tile: the bulk stores of dq | dk | dv read r2 too)
           continue;
         }
         // ---- attention backward, per head group ----
@@ -736,6 +737,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         fence_after_sync();
         const int A0 = nfs + 8;
         auto dxin = [&](int gg, int st0) {              // dx_in += dqkv[:, group gg] Wqkv[group gg rows, :]   (K = 192: six stages)
+          const uint64_t dA = gg == G - 1 ? dR2 : dR1;   // the last group's dq | dk | dv image sits in r2
           const uint32_t n = it * G + (uint32_t)gg;
           mbar_wait(&bar_dqkvready, n & 1u);
           fence_after_sync();
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             const uint64_t db = desc_adv(dB256, (uint32_t)(st % NS) * T256_STAGE);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              mma_bf16_ss(t_dx, desc_adv(dR1, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du1
+              mma_bf16_ss(t_dx, desc_adv(dA, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du1
             mma_commit(&bar_empty[st % NS]);
           }
           mma_commit(&bar_dqkvfree);
@@ -768,7 +770,6 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
             mma_commit(&bar_empty[st % NS]);
           }
           mma_commit(&bar_qkvfull);
-          if (g == G - 1) mma_commit(&bar_r2b);
           if (g >= 1) dxin(g - 1, st0 + 8);
         }
         dxin(G - 1, A0 + 50);
@@ -782,6 +783,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float attn_scale = rsqrtf((float)DH) * 1.4426950408889634f;
     const ColsumSel csel = colsum_sel(lane);
+    const uint64_t pol_stage = l2_policy_evict_first();
     uint8_t *scratch = a.dctx_scratch + (size_t)blockIdx.x * T256_TILE_IMG;
     // du2 / du1 (LayerNorm-input gradients, the residual by-pass) are written into the dx accumulator t_dx with tcgen05.st and the
     // following UMMAs accumulate onto them; earlier versions parked them in a per-CTA fp32 tile in L2 and re-added them
@@ -853,6 +855,15 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       mbar_wait(&bar_dx1full, it & 1u);
       fence_after_sync();
       T256_STAMP();
+      // head_dim 128: the saved q | k | v group images (48 KB each) are staged by bulk TMA, one thread issuing, as early as their
+      // target is free: head 0's odd group -> r2 here (the FFN is done with r2), its even group -> r1 once dctx has read the da1 image
+      auto stage_qkv = [&](int gg, uint8_t *dst) {
+        const uint8_t *qg = a.qkv_img + ((size_t)tile * G + gg) * T256_QKV_GROUP_IMG;
+        mbar_expect_tx(&bar_qkvstaged, (uint32_t)T256_QKV_GROUP_IMG);
+        tma_load_1d_hint(dst, qg, 32768u, &bar_qkvstaged, pol_stage);
+        tma_load_1d_hint(dst + 32768, qg + 32768, 16384u, &bar_qkvstaged, pol_stage);
+      };
+      if constexpr (H128) { if (tid == 0) stage_qkv(1, sR2); }
       {
         auto dyload = [&](int cb, float (&o)[16]) {     // du2 + dx1: the accumulator was seeded with du2
           tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), o);
@@ -871,6 +882,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       mbar_wait(&bar_dctxfull, it & 1u);
       fence_after_sync();
       T256_STAMP();
+      if constexpr (H128) { if (tid == 0) stage_qkv(0, sR1); }
 #pragma unroll
       for (int cb = 0; cb < 64; cb += 16) {
         float f[16];
@@ -890,20 +902,20 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         // ---- B6 (head_dim 128): per head, stage q | k | v (saved by the forward) and dO (from this CTA's dctx scratch) of its two
         // groups into r1 (even group) and r2 (odd group), attention backward in place, hand both dq | dk | dv images to the issuer ----
         for (int h = 0; h < 2; ++h) {
-          if (h >= 1) mbar_wait(&bar_dqkvfree, (it * 2u) & 1u);   // dx_in of head 0 no longer reads r1 / r2
-          if (tid == 0) tma_store_wait_read();                     // ... nor do the bulk stores of its dq | dk | dv slices
-          named_bar_sync(1, T256_CTHREADS);
+          if (h >= 1) {
+            mbar_wait(&bar_dqkvfree, (it * 2u) & 1u);             // dx_in of head 0 no longer reads r1 / r2
+            if (tid == 0) tma_store_wait_read();                   // ... nor do the bulk stores of its dq | dk | dv slices
+            named_bar_sync(1, T256_CTHREADS);
+            if (tid == 0) { stage_qkv(2, sR1); stage_qkv(3, sR2); }
+          }
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+          for (int e = 0; e < 2; ++e) {                            // dO of the head's two groups: from this CTA's dctx scratch (generic copies)
             const int gg = 2 * h + e;
             uint8_t *dst = e ? sR2 : sR1;
-            const uint8_t *qg = a.qkv_img + ((size_t)tile * G + gg) * T256_QKV_GROUP_IMG;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-              *reinterpret_cast<uint4 *>(dst + (size_t)(i * T256_CTHREADS + tid) * 16) = __ldg(reinterpret_cast<const uint4 *>(qg + (size_t)(i * T256_CTHREADS + tid) * 16));
             *reinterpret_cast<uint4 *>(dst + 49152 + (size_t)tid * 16) = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)gg * 16384 + (size_t)tid * 16));
             *reinterpret_cast<uint4 *>(dst + 49152 + 8192 + (size_t)tid * 16) = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)gg * 16384 + 8192 + (size_t)tid * 16));
           }
+          mbar_wait(&bar_qkvstaged, (it * 2u + (uint32_t)h) & 1u);  // both q | k | v images of the head have landed
           named_bar_sync(1, T256_CTHREADS);
           T256_STAMP();
           {
@@ -942,8 +954,11 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         const uint4 dc0 = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)g * 16384 + (size_t)tid * 16));
         const uint4 dc1 = __ldcg(reinterpret_cast<const uint4 *>(scratch + (size_t)g * 16384 + 8192 + (size_t)tid * 16));
         tmem_ld_wait();
-        if (g >= 1) mbar_wait(&bar_dqkvfree, (n - 1u) & 1u);     // dx_in of the previous group no longer reads the dqkv image in r1
-        if (tid == 0) tma_store_wait_read();                       // ... nor do the bulk stores of its dq | dk | dv slices
+        // The LAST group takes r2 as its scratch image: the x image there is dead once its q|k|v recompute has retired (bar_qkvfull
+        // above), so its staging does not wait for dx_in of group G - 2 to release r1 (4 K clocks of a 121 K tile at C4).
+        uint8_t *sS = g == G - 1 ? sR2 : sR1;
+        if (g >= 1 && g < G - 1) mbar_wait(&bar_dqkvfree, (n - 1u) & 1u);     // dx_in of the previous group no longer reads the dqkv image in r1
+        if (tid == 0 && g < G - 1) tma_store_wait_read();                       // ... nor do the bulk stores of its dq | dk | dv slices
         fence_before_sync();
         named_bar_sync(1, T256_CTHREADS);
         if (tid == 0 && g + 1 < G) mbar_arrive(&bar_qkvfree);     // the TMEM chunk is drained: the next group's q|k|v may overwrite it
@@ -955,27 +970,27 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           float w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) w[j] = (v[i * 8 + j] + bias[j]) * sc;
-          *reinterpret_cast<uint4 *>(sR1 + kmajor_off(row, n0, 128)) =
+          *reinterpret_cast<uint4 *>(sS + kmajor_off(row, n0, 128)) =
               make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
         }
-        *reinterpret_cast<uint4 *>(sR1 + 49152 + (size_t)tid * 16) = dc0;
-        *reinterpret_cast<uint4 *>(sR1 + 49152 + 8192 + (size_t)tid * 16) = dc1;
+        *reinterpret_cast<uint4 *>(sS + 49152 + (size_t)tid * 16) = dc0;
+        *reinterpret_cast<uint4 *>(sS + 49152 + 8192 + (size_t)tid * 16) = dc1;
         named_bar_sync(1, T256_CTHREADS);
         T256_STAMP();
         if (warp < 4 * GH) {
           const int s = warp / GH, hl = warp % GH;
           const int64_t seq = a.seq0 + (int64_t)tile * 4 + s;
           const uint64_t w_pair = (uint64_t)((seq * H + (g * GH + hl)) * 32) * 8u;     // quad index of (row 0, position 0)
-          if constexpr (!H128) t256_attn_bwd<DH>(sR1, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
+          if constexpr (!H128) t256_attn_bwd<DH>(sS, s, hl, lane, a.d_attn, w_pair, g_bqkv + g * 192);
         }
         fence_async_smem();
         named_bar_sync(1, T256_CTHREADS);
         if (tid == 0) {
           mbar_arrive(&bar_dqkvready);
           uint8_t *dq_g = a.dqkv_img + (size_t)tile * (3 * T256_TILE_IMG) + (size_t)g * 16384;
-          tma_store_1d(dq_g, sR1, 16384u);
-          tma_store_1d(dq_g + T256_TILE_IMG, sR1 + 16384, 16384u);
-          tma_store_1d(dq_g + 2 * T256_TILE_IMG, sR1 + 32768, 16384u);
+          tma_store_1d(dq_g, sS, 16384u);
+          tma_store_1d(dq_g + T256_TILE_IMG, sS + 16384, 16384u);
+          tma_store_1d(dq_g + 2 * T256_TILE_IMG, sS + 32768, 16384u);
           tma_store_commit();
         }
         T256_STAMP();
@@ -996,7 +1011,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       }
       if (tid == 0) {
         tma_store_wait_read();
-        if constexpr (H128) mbar_arrive(&bar_r2b);      // dx_in has retired (bar_dxinfull) and the dq | dk | dv bulk stores no longer read r2
+        mbar_arrive(&bar_r2b);                          // dx_in has retired (bar_dxinfull) and the dq | dk | dv bulk stores no longer read r2
       }
       fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
