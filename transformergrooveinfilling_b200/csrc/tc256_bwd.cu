@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
                 mma_commit(&bar_empty[st % NS]);
               }
             }
-            mma_commit(&bar_dqkvfree);
+            if (h == 0) mma_commit(&bar_dqkvfree);        // (head 1's images are released by bar_dxinfull: a commit nobody waits for is a synccheck finding)
           }
           mma_commit(&bar_dxinfull);                      // (bar_r2b is raised by the compute warps at the end of the tile: the bulk stores of dq | dk | dv read r2 too)
           continue;
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
               mma_bf16_ss(t_dx, desc_adv(dA, (uint32_t)(b * 2 + k) * 4096u), desc_adv(db, (uint32_t)k * 8192u), id_256, 1);     // onto du1
             mma_commit(&bar_empty[st % NS]);
           }
-          mma_commit(&bar_dqkvfree);
+          if (gg < G - 2) mma_commit(&bar_dqkvfree);      // groups G - 2 and G - 1 release their images through bar_dxinfull (nobody waits on this barrier for them)
         };
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
@@ -812,7 +812,12 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(1, T256_CTHREADS);
-      if (tid == 0) mbar_arrive(&bar_da2ready);
+      if (tid == 0) {
+        mbar_arrive(&bar_da2ready);
+        // u1 of this tile is first touched by LayerNorm1 backward, one FFN phase from now: pull it into L2 while the HBM is quiet
+        prefetch_l2_bulk(a.u1_img + (size_t)tile * T256_TILE_IMG, 32768u);
+        prefetch_l2_bulk(a.u1_img + (size_t)tile * T256_TILE_IMG + 32768, 32768u);
+      }
       T256_STAMP();
       // ---- B2: hidden-activation gradient per FFN chunk ----
       for (int c = 0; c < NCH; ++c) {
@@ -903,7 +908,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         // groups into r1 (even group) and r2 (odd group), attention backward in place, hand both dq | dk | dv images to the issuer ----
         for (int h = 0; h < 2; ++h) {
           if (h >= 1) {
-            mbar_wait(&bar_dqkvfree, (it * 2u) & 1u);             // dx_in of head 0 no longer reads r1 / r2
+            mbar_wait(&bar_dqkvfree, it & 1u);                    // dx_in of head 0 no longer reads r1 / r2
             if (tid == 0) tma_store_wait_read();                   // ... nor do the bulk stores of its dq | dk | dv slices
             named_bar_sync(1, T256_CTHREADS);
             if (tid == 0) { stage_qkv(2, sR1); stage_qkv(3, sR2); }
@@ -957,7 +962,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         // The LAST group takes r2 as its scratch image: the x image there is dead once its q|k|v recompute has retired (bar_qkvfull
         // above), so its staging does not wait for dx_in of group G - 2 to release r1 (4 K clocks of a 121 K tile at C4).
         uint8_t *sS = g == G - 1 ? sR2 : sR1;
-        if (g >= 1 && g < G - 1) mbar_wait(&bar_dqkvfree, (n - 1u) & 1u);     // dx_in of the previous group no longer reads the dqkv image in r1
+        if (g >= 1 && g < G - 1) mbar_wait(&bar_dqkvfree, (it * (uint32_t)(G - 2) + (uint32_t)(g - 1)) & 1u);     // dx_in of the previous group no longer reads the dqkv image in r1
         if (tid == 0 && g < G - 1) tma_store_wait_read();                       // ... nor do the bulk stores of its dq | dk | dv slices
         fence_before_sync();
         named_bar_sync(1, T256_CTHREADS);
