@@ -869,6 +869,18 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         tma_load_1d_hint(dst + 32768, qg + 32768, 16384u, &bar_qkvstaged, pol_stage);
       };
       if constexpr (H128) { if (tid == 0) stage_qkv(1, sR2); }
+      // dy / u2 of this CTA's NEXT tile (first touched by its LayerNorm2 backward) are pulled into L2 during the LAST attention unit of
+      // this tile, when the weight stream has nothing but the final dx_in stages left (at the start of the attention phases the same
+      // prefetch competes with the stream and loses: profiles/r02b)
+      auto prefetch_next = [&]() {
+        const int nt = tile + (int)gridDim.x;
+        if (nt >= a.n_tiles) return;
+        const uint8_t *dyp = reinterpret_cast<const uint8_t *>(a.dy + (size_t)nt * T256_TILE_F32);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) prefetch_l2_bulk(dyp + q * 32768, 32768u);
+        prefetch_l2_bulk(a.u2_img + (size_t)nt * T256_TILE_IMG, 32768u);
+        prefetch_l2_bulk(a.u2_img + (size_t)nt * T256_TILE_IMG + 32768, 32768u);
+      };
       {
         auto dyload = [&](int cb, float (&o)[16]) {     // du2 + dx1: the accumulator was seeded with du2
           tmem_ld16(t_dx + lane_off + (uint32_t)(part * 64 + cb), o);
@@ -922,6 +934,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
           }
           mbar_wait(&bar_qkvstaged, (it * 2u + (uint32_t)h) & 1u);  // both q | k | v images of the head have landed
           named_bar_sync(1, T256_CTHREADS);
+          if (h == 1 && tid == 0) prefetch_next();
           T256_STAMP();
           {
             const int s = warp & 3;
@@ -981,6 +994,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1) t256_layer_bwd_kernel(const T
         *reinterpret_cast<uint4 *>(sS + 49152 + (size_t)tid * 16) = dc0;
         *reinterpret_cast<uint4 *>(sS + 49152 + 8192 + (size_t)tid * 16) = dc1;
         named_bar_sync(1, T256_CTHREADS);
+        if (g == G - 1 && tid == 0) prefetch_next();
         T256_STAMP();
         if (warp < 4 * GH) {
           const int s = warp / GH, hl = warp % GH;
@@ -1047,10 +1061,10 @@ template <int DH>
 static int t256_launch_bwd(const T256Args &a_in, int grid, cudaStream_t st) {
   static T256Dbg dbg;
   // Persistent CTAs with equal work run in lockstep, so their HBM-heavy phases (LayerNorm2 backward pulls dy + u2 while the dx
-  // rows of the previous tile drain: ~90 % of the HBM peak with every SM in that phase) coincide and the HBM idles during the
-  // attention phases.  Starting CTA b (b % 4) * 20 K clocks late spreads them out: C4 backward 20.3 -> 19.7 ms per step.
-  // Only for launches long enough (>= 16 tiles per CTA) that the late start is < 3 % of the kernel.
-  static const uint32_t stagger = getenv("GT_T256_STAGGER") ? (uint32_t)atoi(getenv("GT_T256_STAGGER")) : 20000u;
+  // rows of the previous tile drain) coincide and the HBM idles during the attention phases.  Starting CTA b (b % 4) * S clocks late
+  // spreads them out (GT_T256_STAGGER=S: C4 backward 20.3 -> 19.7 ms at S = 20000 before the next-tile L2 prefetch existed);
+  // with that prefetch (issued during the last attention unit) the two are equivalent (18.9 ms either way), so the default is off.
+  static const uint32_t stagger = getenv("GT_T256_STAGGER") ? (uint32_t)atoi(getenv("GT_T256_STAGGER")) : 0u;
   T256Args a = a_in;
   a.stagger = a.n_tiles >= 16 * grid ? stagger : 0u;
   const bool d = dbg.arm(a, st);
