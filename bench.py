@@ -255,7 +255,7 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
     from transformergrooveinfilling_b200 import _lib
     path_kind = lib.gt_path_kind(C.byref(model._cfg()))
     fused = path_kind in (_lib.PATH_FUSED_D32, _lib.PATH_FUSED_D256)
-    lib.gt_profile_enable({0: 1, 1: 17, 2: 17, 3: 22}[path_kind], 16384)
+    lib.gt_profile_enable({0: 1, 1: 17, 2: 17, 3: 22, 4: 22}[path_kind], 16384)
     l0 = lib.gt_launch_count(-1)
     sampler = ClockSampler(dev.index)
     sampler.start()
@@ -292,9 +292,9 @@ def run_infer(args, w, model, lib, x, xh, n, world, rank, dev, barrier, timed, p
                     "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps, "chunk": hp.chunk,
                     "api": "HostPredictor.predict (H2D / gt_predict / D2H of neighbouring chunks on three streams)"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[path_kind]}
+            "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc", 4: "per_op_gemm_tc_split_fp32"}[path_kind]}
     if cnt.value and not fused:
-        line["dominant_gemm"] = {"class": "gemm_tc" if path_kind == 3 else "gemm_f32", "launches_timed": cnt.value,
+        line["dominant_gemm"] = {"class": "gemm_tc" if path_kind in (3, 4) else "gemm_f32", "launches_timed": cnt.value,
                                  "share_of_step": tot_ms.value / ms}
     if rank == 0:
         emit(line)
@@ -377,7 +377,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: workload table)")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp32_tc"],
+                    help="fp32_tc: the 1e-4 parity mode with every Linear contraction on tcgen05 (three-term bf16 split operands)")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train step (headline) or predict()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -431,7 +432,8 @@ def main():
             model = None
     if model is None:
         torch.manual_seed(0)
-        model, precision = make("fp32"), "fp32"
+        precision = "fp32_tc" if args.precision == "fp32_tc" else "fp32"
+        model = make(precision)
     if world > 1:                                   # identical replicas
         dist.broadcast(model.flat_parameters().detach(), 0)
     opt = FusedAdam(model, 1e-3) if args.optimizer == "adam" else FusedSGD(model, w["lr"])
@@ -500,7 +502,7 @@ def main():
     # ---- timed region: kernel-resident throughput, dominant kernel class bracketed by CUDA events ----
     # fp32 SIMT GEMM / fused layer backward kernel / generic tcgen05 GEMM (shapes without fused layer kernels)
     path_kind = lib.gt_path_kind(C.byref(model._cfg()))
-    dom = {_lib.PATH_FP32_SIMT: 1, _lib.PATH_FUSED_D32: 18, _lib.PATH_FUSED_D256: 18, _lib.PATH_GEMM_TC: 22}[path_kind]
+    dom = {_lib.PATH_FP32_SIMT: 1, _lib.PATH_FUSED_D32: 18, _lib.PATH_FUSED_D256: 18, _lib.PATH_GEMM_TC: 22, _lib.PATH_GEMM_TC_SPLIT: 22}[path_kind]
     lib.gt_profile_enable(dom, 4096)
     l0 = lib.gt_launch_count(-1)
     sampler = ClockSampler(local)
@@ -530,7 +532,7 @@ def main():
     roof = None
     if cnt.value > 0:
         # the dominant kernel class and the share of the step's algorithmic FLOPs its launches carry
-        if path_kind == _lib.PATH_GEMM_TC:
+        if path_kind in (_lib.PATH_GEMM_TC, _lib.PATH_GEMM_TC_SPLIT):
             # every Linear contraction of the step (forward, data gradient, weight gradient) except the K = 16 / 27 input
             # layers and the 27-wide head runs in gemm_tc; attention runs in the SIMT attention kernels
             d, F, L, Ld = w["d"], w["F"], w["L"], w["Ld"]
@@ -619,7 +621,7 @@ def main():
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4, "d2h_bytes_per_step": 24,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss, "kernels": kernels,
-        "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc"}[path_kind],
+        "path": {0: "fp32_simt", 1: "fused_tcgen05_d32", 2: "fused_tcgen05_d256", 3: "per_op_gemm_tc", 4: "per_op_gemm_tc_split_fp32"}[path_kind],
     }
     if rank == 0 and world == 1 and not args.no_extras:
         # ---- the other halves of BASELINE.json's metric, in the same driver-run record: predict() throughput on this

@@ -30,6 +30,11 @@ extern "C" {
 /* precision modes */
 #define GT_PREC_FP32 0         /* fp32 SIMT arithmetic everywhere (the 1e-4 "fp32/TF32" parity mode) */
 #define GT_PREC_BF16 1         /* bf16 operands / fp32 accumulate on tcgen05 tensor cores (2e-3 mode) */
+#define GT_PREC_FP32_TC 2      /* the 1e-4 parity mode ON the tensor cores: every Linear contraction runs on tcgen05 with its fp32
+                                  operands split exactly into three bf16 terms (x0 + x1 + x2) and the six products down to 2^-18
+                                  contracted with fp32 accumulation ("3 x bf16", the bf16 form of 3xTF32: measured gradient
+                                  error 1 - 2e-6 against 5e-7 of the FFMA kernels and 3e-3 of bf16 operands); attention,
+                                  LayerNorm, loss and optimizers are the fp32 kernels of GT_PREC_FP32 */
 
 /* which implementation a configuration runs on (gt_path_kind) */
 #define GT_PATH_FP32_SIMT   0  /* precision fp32: fp32 FMA kernels */
@@ -39,6 +44,8 @@ extern "C" {
 #define GT_PATH_GEMM_TC     3  /* precision bf16, every other shape: per-op kernels, contractions on gemm_tc, attention on mma.sync
                                   (d_model = 32 encoder-decoder models outside the fused head dims still run their encoder
                                   stack and decoder FFN blocks in the fused kernels) */
+#define GT_PATH_GEMM_TC_SPLIT 4 /* precision fp32_tc, every shape: the per-op kernels of GT_PATH_FP32_SIMT with the contractions on
+                                  gemm_tc in split form */
 
 /* Mirrors the constructor arguments of GrooveTransformerEncoder / GrooveTransformer
  * (BGT/models/transformer.py:10-11, :87-88) and params["model"] of train.py:115-143. */
@@ -209,7 +216,9 @@ int gt_debug_tc_gemm(const uint16_t *a, const uint16_t *b, float *d, int m, int 
                      int variant, void *stream);
 
 /* Test hook for the generic GEMMs: C[m,n] = epi(sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]) on fp32 device buffers.
- * tc != 0 runs the tcgen05 kernel (operands rounded to bf16, fp32 accumulate), tc == 0 the fp32 SIMT kernel.
+ * tc == 1 runs the tcgen05 kernel (operands rounded to bf16, fp32 accumulate), tc == 2 the same kernel in split form
+ * (GT_PREC_FP32_TC: three-term bf16 split operands, fp32 results; needs a bound scratch, falls back to the SIMT
+ * kernel without one), tc == 0 the fp32 SIMT kernel.
  * flags: bit0 relu, bit1 accumulate (C += v), bit2 atomic (required when split_k_chunk splits K).  bias[N], residual
  * (ld_res) and mask_pos (ld_mask, mask_scale) may be NULL; drop_p > 0 applies the counter-based dropout of site
  * `site` at (seed, step) to element (row0 + m) * N + n. */

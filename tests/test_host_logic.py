@@ -51,6 +51,27 @@ def test_invalid_configs_are_rejected_with_messages():
     assert lib.gt_sgd_step(None, None, 4, 0.1, 1.0, None) != 0        # null pointers are refused before any launch
 
 
+def test_precision_modes_select_their_paths():
+    """gt_path_kind is host logic: fp32 -> FFMA kernels, fp32_tc -> the per-op kernels with split-operand tcgen05 contractions for
+    every shape (its workspace carries the three-image operand scratch), bf16 -> fused kernels where they exist; anything else is
+    refused."""
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    cfg = lambda prec, d=32, h=16, f=512, ld=0: _lib.GtConfig(d, h, f, 6, ld, 16, 27, prec, 0.1, 0)
+    assert lib.gt_path_kind(C.byref(cfg(_lib.PREC_FP32))) == _lib.PATH_FP32_SIMT
+    assert lib.gt_path_kind(C.byref(cfg(_lib.PREC_BF16))) == _lib.PATH_FUSED_D32
+    for shape in (dict(), dict(d=256, h=2), dict(d=256, h=16, f=64), dict(ld=6), dict(d=64, h=4, f=128)):
+        assert lib.gt_path_kind(C.byref(cfg(_lib.PREC_FP32_TC, **shape))) == _lib.PATH_GEMM_TC_SPLIT
+    w32, wtc = (lib.gt_workspace_bytes(C.byref(cfg(p, d=256, h=2)), 64, 1) for p in (_lib.PREC_FP32, _lib.PREC_FP32_TC))
+    assert wtc > w32 > 0
+    assert lib.gt_path_kind(C.byref(cfg(3))) < 0 and b"precision" in lib.gt_last_error()
+    from transformergrooveinfilling_b200 import GrooveTransformerEncoder
+    m = GrooveTransformerEncoder(32, 16, 27, 4, 64, 0.1, 2, 32, "cpu")
+    assert m.set_precision("fp32_tc")._cfg().precision == _lib.PREC_FP32_TC
+    with pytest.raises(ValueError):
+        m.set_precision("tf32")
+
+
 def test_state_dict_keys_match_reference_demo_checkpoint():
     from BaseGrooveTransformers.models.transformer import GrooveTransformerEncoder
     want = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "demo_checkpoint_keys.txt")) if not l.startswith("#")]

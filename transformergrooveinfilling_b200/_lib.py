@@ -10,8 +10,8 @@ import threading
 
 from . import build as _build
 
-PREC_FP32, PREC_BF16 = 0, 1
-PATH_FP32_SIMT, PATH_FUSED_D32, PATH_FUSED_D256, PATH_GEMM_TC = 0, 1, 2, 3
+PREC_FP32, PREC_BF16, PREC_FP32_TC = 0, 1, 2
+PATH_FP32_SIMT, PATH_FUSED_D32, PATH_FUSED_D256, PATH_GEMM_TC, PATH_GEMM_TC_SPLIT = 0, 1, 2, 3, 4
 T_STEPS = 32
 
 

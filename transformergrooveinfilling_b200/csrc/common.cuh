@@ -221,10 +221,12 @@ int gemm_f32(const float *A, int64_t sam, int64_t sak, const float *B, int64_t s
 bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t M, int64_t N, int64_t K);
 int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk,
             float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &epi,
-            int64_t split_k_chunk, cudaStream_t st);
+            int64_t split_k_chunk, cudaStream_t st, int split = 0);
+// split = 1 (GT_PREC_FP32_TC): every operand is imaged as a bf16 triple x0 + x1 + x2 (exact) and contracted in six passes — fp32
+// results on the tensor cores; without a bound scratch the problem runs on gemm_f32.
 // operand-image scratch of gemm_tc: caller-owned (a workspace region), bound to the calling thread for the duration of a pass
 void gemm_tc_bind_scratch(void *p, int64_t bytes);
-int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F);
+int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F, int split = 0);
 // out[n] += sum_m X[m*ld + n]
 int colsum_f32(const float *X, int64_t ld, int64_t M, int N, float *out, cudaStream_t st);
 

@@ -41,6 +41,7 @@ struct GemmTcArgs {
   const uint8_t *b_img;             // pre-built bf16 images of B, one per (n-tile, K block) in that order (gemm_tc_bimg_kernel), or null
   const uint8_t *a_img;             // same for A, one per (m-tile, K block) (gemm_tc_aimg_kernel); only together with b_img
   int nkb_img;                      // K blocks of the whole contraction (per n-tile / m-tile in the images)
+  int split;                        // 1: fp32 results on the tensor cores — every image block is a bf16 [x0 | x1 | x2] triple (see split_pair)
   GemmEpi e;
 };
 
@@ -91,6 +92,38 @@ __device__ __forceinline__ void tile_store(const float4 (&v)[ITEMS][2], uint8_t 
     *reinterpret_cast<uint4 *>(img + kmajor_off(r, c * 8, rows)) =
         make_uint4(pack_bf16(v[it][0].x, v[it][0].y), pack_bf16(v[it][0].z, v[it][0].w), pack_bf16(v[it][1].x, v[it][1].y),
                    pack_bf16(v[it][1].z, v[it][1].w));
+  }
+}
+
+// Split form (GT_PREC_FP32_TC): x = x0 + x1 + x2 exactly, x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1) (8 + 8 + 8
+// significand bits; the subtractions are exact in fp32).  The main kernel contracts the six products of weight >= 2^-18 —
+// x0.y0, x0.y1, x1.y0, x1.y1, x0.y2, x2.y0 — into the same fp32 accumulator: what is dropped is <= 2^-26 of a product, below the
+// accumulator's own rounding, i.e. fp32 results (the 1e-4 parity mode) at a sixth of the bf16 tensor rate instead of the FFMA rate.
+// (Two-term splits — three products, 2^-16 — were measured first: 1e-5 gradient errors, not enough for 20-step trajectories.)
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t &p0, uint32_t &p1, uint32_t &p2) {
+  p0 = pack_bf16(x, y);
+  x -= __uint_as_float(p0 << 16); y -= __uint_as_float(p0 & 0xFFFF0000u);
+  p1 = pack_bf16(x, y);
+  x -= __uint_as_float(p1 << 16); y -= __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = pack_bf16(x, y);
+}
+template <int ITEMS>
+__device__ __forceinline__ void tile_store_split(const float4 (&v)[ITEMS][2], uint8_t *img, uint32_t img_bytes, int rows, int lch, int tid) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int i = tid + it * GTHREADS;
+    if (i >= (rows << lch)) continue;
+    int r, c;
+    item_rc(i, lch, r, c);
+    uint4 h, m, l;
+    split_pair(v[it][0].x, v[it][0].y, h.x, m.x, l.x);
+    split_pair(v[it][0].z, v[it][0].w, h.y, m.y, l.y);
+    split_pair(v[it][1].x, v[it][1].y, h.z, m.z, l.z);
+    split_pair(v[it][1].z, v[it][1].w, h.w, m.w, l.w);
+    uint8_t *dst = img + kmajor_off(r, c * 8, rows);
+    *reinterpret_cast<uint4 *>(dst) = h;
+    *reinterpret_cast<uint4 *>(dst + img_bytes) = m;
+    *reinterpret_cast<uint4 *>(dst + 2u * img_bytes) = l;
   }
 }
 
@@ -152,7 +185,8 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tc_bimg_kernel(const GemmTcArgs
   float4 rb[BI][2];
   if (b_mn) tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, k0, g.K, n0, g.N, g.b_vec != 0, tid);
   else tile_load<BI>(rb, g.B, b_ld, b_rows, b_lch, n0, g.N, k0, g.K, g.b_vec != 0, tid);
-  tile_store<BI>(rb, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * B_BYTES, b_rows, b_lch, tid);
+  if (g.split) tile_store_split<BI>(rb, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 3u * B_BYTES, B_BYTES, b_rows, b_lch, tid);
+  else tile_store<BI>(rb, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * B_BYTES, b_rows, b_lch, tid);
 }
 
 // The same for A (activations): one streaming pass fp32 -> bf16 images, after which the main kernel's K loop is two bulk-TMA
@@ -169,14 +203,16 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tc_aimg_kernel(const GemmTcArgs
   float4 ra[AI][2];
   if (a_mn) tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, k0, g.K, m0, g.M, g.a_vec != 0, tid);
   else tile_load<AI>(ra, g.A, a_ld, a_rows, a_lch, m0, g.M, k0, g.K, g.a_vec != 0, tid);
-  tile_store<AI>(ra, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * A_BYTES, a_rows, a_lch, tid);
+  if (g.split) tile_store_split<AI>(ra, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 3u * A_BYTES, A_BYTES, a_rows, a_lch, tid);
+  else tile_store<AI>(ra, img + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * A_BYTES, a_rows, a_lch, tid);
 }
 
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g) {
   constexpr uint32_t A_BYTES = GBM * GBK * 2, B_BYTES = BN * GBK * 2, STG = A_BYTES + B_BYTES;
   constexpr int AI = GBM * GBK / 8 / GTHREADS, BI = (BN * GBK / 8 + GTHREADS - 1) / GTHREADS;
-  constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+  // split mode (BN <= 128) keeps a second accumulator for the five correction products: columns [BN, 2 BN)
+  constexpr uint32_t TCOLS = BN <= 128 ? (2 * BN < 32 ? 32 : 2 * BN) : BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_free[GSTG], bar_b[GSTG], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -216,14 +252,20 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
     if (warp == 0) {
     if (lane == 0) {
       const int64_t kb0 = k_begin / GBK;
-      const uint8_t *a_src = g.a_img + ((size_t)(blockIdx.x / g.n_tiles) * g.nkb_img + kb0) * A_BYTES;
-      const uint8_t *b_src = g.b_img + ((size_t)(blockIdx.x % g.n_tiles) * g.nkb_img + kb0) * B_BYTES;
+      // split mode: block kb of an operand is a triple of images [x0 | x1 | x2]; a stage holds both triples (1 CTA per SM, BN <= 128)
+      // and is contracted in six passes, smallest products first
+      const int im = g.split ? 3 : 1, npass = g.split ? 6 : 1;
+      const uint32_t stg = (uint32_t)im * STG;
+      const uint8_t *a_src = g.a_img + ((size_t)(blockIdx.x / g.n_tiles) * g.nkb_img + kb0) * im * A_BYTES;
+      const uint8_t *b_src = g.b_img + ((size_t)(blockIdx.x % g.n_tiles) * g.nkb_img + kb0) * im * B_BYTES;
       auto issue = [&](int kb) {
         const int s = kb % GSTG;
-        uint8_t *sA = smem + (uint32_t)s * STG;
-        mbar_expect_tx(&bar_b[s], STG);
-        tma_load_1d(sA, a_src + (size_t)kb * A_BYTES, A_BYTES, &bar_b[s]);
-        tma_load_1d(sA + A_BYTES, b_src + (size_t)kb * B_BYTES, B_BYTES, &bar_b[s]);
+        uint8_t *sA = smem + (uint32_t)s * stg;
+        mbar_expect_tx(&bar_b[s], stg);
+        for (int i = 0; i < im; ++i) {
+          tma_load_1d(sA + (uint32_t)i * A_BYTES, a_src + ((size_t)kb * im + i) * A_BYTES, A_BYTES, &bar_b[s]);
+          tma_load_1d(sA + (uint32_t)im * A_BYTES + (uint32_t)i * B_BYTES, b_src + ((size_t)kb * im + i) * B_BYTES, B_BYTES, &bar_b[s]);
+        }
       };
       for (int kb = 0; kb < nkb && kb < GSTG; ++kb) issue(kb);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -232,10 +274,20 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
         fence_after_sync();
         const int64_t krem = k_end - (k_begin + (int64_t)kb * GBK);
         const int nk16 = krem >= GBK ? GBK / 16 : (int)((krem + 15) / 16);
-        const uint32_t aA = smem_u32(smem + (uint32_t)s * STG), aB = aA + A_BYTES;
-        for (int k = 0; k < nk16; ++k)
-          mma_bf16_ss(tmem, make_desc(aA + (uint32_t)k * a_kstep, a_lbo, a_sbo), make_desc(aB + (uint32_t)k * b_kstep, b_lbo, b_sbo), idesc,
-                      (kb | k) > 0 ? 1u : 0u);
+        const uint32_t aA = smem_u32(smem + (uint32_t)s * stg), aB = aA + (uint32_t)im * A_BYTES;
+        for (int p = 0; p < npass; ++p) {
+          // (A image, B image) of pass p: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0); plain mode: (0,0)
+          const uint32_t ia = g.split ? ((0x001102u >> (4 * p)) & 3u) : 0u, ib = g.split ? ((0x010120u >> (4 * p)) & 3u) : 0u;
+          // The tensor core TRUNCATES when it adds into the fp32 accumulator: every UMMA costs up to one ulp of the accumulator,
+          // always towards zero (measured: 96 accumulations of a K = 256 contraction left 1e-5).  The x0.y0 products therefore have
+          // the main accumulator to themselves and the five corrections (2^-9 of it and less) add up in a second one, whose
+          // truncation is invisible; the epilogue adds the two in fp32.
+          const bool corr = g.split && p < 5;
+          for (int k = 0; k < nk16; ++k)
+            mma_bf16_ss(tmem + (corr ? (uint32_t)BN : 0u), make_desc(aA + ia * A_BYTES + (uint32_t)k * a_kstep, a_lbo, a_sbo),
+                        make_desc(aB + ib * B_BYTES + (uint32_t)k * b_kstep, b_lbo, b_sbo), idesc,
+                        (corr ? (kb | p | k) : (kb | k)) > 0 ? 1u : 0u);
+        }
         mma_commit(&bar_free[s]);
         if (kb + 1 == nkb) mma_commit(&bar_done);
         if (kb + GSTG < nkb) {
@@ -319,6 +371,13 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tc_kernel(const GemmTcArgs g
     float v[32];
     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
     tmem_ld_wait();
+    if (g.split) {                                        // + the correction accumulator
+      float c2[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cb), c2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += c2[j];
+    }
     const int64_t nb = n0 + cb;
     {
       const int64_t m = mw0 + lane;
@@ -420,7 +479,8 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 // for the duration of the pass; GEMMs of one pass run in stream order, so the next pre-pass cannot overwrite images a previous
 // main kernel still reads, and two models never share a buffer (each has its own workspace).  Without a bound scratch — or when
 // a problem's images do not fit — the GEMM stages its operands itself.
-constexpr size_t IMG_MAX_BYTES = (size_t)4 << 30;
+constexpr size_t IMG_MAX_BYTES = (size_t)8 << 30;
+constexpr int GEMM_TC_NO_SPLIT = -77;      // launch(): a split-mode problem whose operands cannot both be pre-imaged (gemm_tc falls back to FFMA)
 thread_local uint8_t *g_img_scratch = nullptr;
 thread_local size_t g_img_scratch_bytes = 0;
 uint8_t *img_scratch(size_t need) { return (g_img_scratch != nullptr && need <= g_img_scratch_bytes) ? g_img_scratch : nullptr; }
@@ -434,19 +494,24 @@ int pre_mode() {
 
 template <int BN>
 int launch(GemmTcArgs g, int64_t m_tiles, int64_t splits, cudaStream_t st) {
-  constexpr size_t smem = (size_t)GSTG * (GBM * GBK * 2 + BN * GBK * 2);
+  constexpr size_t smem1 = (size_t)GSTG * (GBM * GBK * 2 + BN * GBK * 2);
+  // split mode: a stage holds three images per operand (BN <= 128: 192 KB, one CTA per SM)
+  const size_t smem = g.split ? 3 * smem1 : smem1;
+  if (g.split && BN > 128) return GEMM_TC_NO_SPLIT;
   static bool attr_done = false;
   if (!attr_done) {
-    GT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BN <= 128 ? 3 * smem1 : smem1)));
     attr_done = true;
   }
   g.b_img = nullptr; g.a_img = nullptr; g.nkb_img = 0;
   const int64_t nkb = (g.K + GBK - 1) / GBK;
-  const size_t need_b = (size_t)g.n_tiles * nkb * BN * GBK * 2, need_a = (size_t)m_tiles * nkb * GBM * GBK * 2;
+  const size_t im = g.split ? 3 : 1;
+  const size_t need_b = (size_t)g.n_tiles * nkb * BN * GBK * 2 * im, need_a = (size_t)m_tiles * nkb * GBM * GBK * 2 * im;
   const int mode = pre_mode();                                    // the scratch is a fixed workspace region: valid under stream capture too
   const bool big = m_tiles * g.n_tiles * splits >= 32;            // small problems are launch-latency bound: no extra kernels
-  const bool all = mode >= 2 && big && nkb <= 65535 && need_a + need_b <= IMG_MAX_BYTES && need_a + need_b <= g_img_scratch_bytes;
+  const bool all = mode >= 2 && (big || g.split) && nkb <= 65535 && need_a + need_b <= IMG_MAX_BYTES && need_a + need_b <= g_img_scratch_bytes;
   const bool only_b = !all && mode >= 1 && splits == 1 && m_tiles >= 16 && need_b <= ((size_t)4 << 20);
+  if (g.split && !(all && img_scratch(need_a + need_b) != nullptr)) return GEMM_TC_NO_SPLIT;     // small problem / no scratch
   if (all || only_b) {
     uint8_t *img = img_scratch(all ? need_a + need_b : need_b);
     if (img != nullptr) {
@@ -478,10 +543,10 @@ void gemm_tc_bind_scratch(void *p, int64_t bytes) {
 
 // upper bound of the operand images of any Linear forward / dgrad / wgrad GEMM of a model with these widths over `tokens` rows:
 // forward / dgrad: A = [tokens x K], B = [N x K]; wgrad: A = [N_w x tokens], B = [K_w x tokens] (both <= the widest layer dims)
-int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F) {
+int64_t gemm_tc_scratch_bytes(int64_t tokens, int64_t d, int64_t F, int split) {
   auto pad = [](int64_t v, int64_t m) { return (v + m - 1) / m * m; };
   const int64_t wide = pad(std::max<int64_t>(3 * d, F), 256), narrow = pad(std::max<int64_t>(d, F), 256);
-  const int64_t need = 2 * pad(tokens, 128) * (wide + narrow) + ((int64_t)1 << 20);
+  const int64_t need = (split ? 6 : 2) * pad(tokens, 128) * (wide + narrow) + ((int64_t)1 << 20);
   return std::min<int64_t>(need, (int64_t)IMG_MAX_BYTES);
 }
 
@@ -492,12 +557,13 @@ bool gemm_tc_supported(int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64
 }
 
 int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk, float *C, int64_t ldc, int64_t M,
-            int64_t N, int64_t K, const GemmEpi &epi, int64_t split_k_chunk, cudaStream_t st) {
+            int64_t N, int64_t K, const GemmEpi &epi, int64_t split_k_chunk, cudaStream_t st, int split) {
   if (M == 0 || N == 0) return 0;
+  const int64_t split_k_chunk_in = split_k_chunk;
   GT_CHECK(gemm_tc_supported(sam, sak, sbn, sbk, M, N, K), "gemm_tc: unsupported operand layout / shape");
   GemmTcArgs g;
   g.A = A; g.B = B; g.C = C; g.sam = sam; g.sak = sak; g.sbn = sbn; g.sbk = sbk; g.ldc = ldc;
-  g.M = M; g.N = N; g.K = K; g.e = epi;
+  g.M = M; g.N = N; g.K = K; g.e = epi; g.split = split ? 1 : 0;
   // tile width: the narrowest of {32, 64, 128, 256} that covers N, 256-wide tiles beyond that (a 384 / 768-wide output uses 128 / 256)
   // (measured on C3, batch 8192: capping the tile at 128 / 64 columns costs 23 % / 69 % of the GEMM time — every extra n-tile
   //  re-stages and re-converts the 128-row A block, which is what bounds this kernel)
@@ -507,6 +573,7 @@ int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sb
   else if (N <= 128) bn = 128;
   else if (N <= 256) bn = 256;
   else bn = (N % 256 == 0 || N % 256 > 128) ? 256 : ((N % 128 == 0 || N % 128 > 64) ? 128 : 256);
+  if (split && bn > 128) bn = 128;                        // a split-mode stage (three images per operand) fits for BN <= 128
   g.n_tiles = (int)((N + bn - 1) / bn);
   const int64_t m_tiles = (M + GBM - 1) / GBM;
   int64_t splits = 1;
@@ -543,12 +610,17 @@ int gemm_tc(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sb
   // a K-major source starts its chunks at k0 (multiple of 64) and an MN-major one at m0 / n0 (multiples of 128 / BN): always 16-byte
   // aligned relative to the base; K-split offsets are multiples of 64 as well.
   GT_CHECK(m_tiles * ((N + 31) / 32) < (int64_t)1 << 31, "gemm_tc: too many tiles");
+  int rc;
   switch (bn) {
-    case 32: return launch<32>(g, m_tiles, splits, st);
-    case 64: return launch<64>(g, m_tiles, splits, st);
-    case 128: return launch<128>(g, m_tiles, splits, st);
-    default: return launch<256>(g, m_tiles, splits, st);
+    case 32: rc = launch<32>(g, m_tiles, splits, st); break;
+    case 64: rc = launch<64>(g, m_tiles, splits, st); break;
+    case 128: rc = launch<128>(g, m_tiles, splits, st); break;
+    default: rc = launch<256>(g, m_tiles, splits, st); break;
   }
+  // split mode promises fp32-class results: a problem that cannot be pre-imaged (a handful of tiles, no scratch bound) runs on the
+  // exact FFMA kernel instead of the in-kernel bf16 staging
+  if (rc == GEMM_TC_NO_SPLIT) return gemm_f32(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, epi, split_k_chunk_in, st);
+  return rc;
 }
 
 }  // namespace gt

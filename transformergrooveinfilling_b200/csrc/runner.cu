@@ -92,7 +92,7 @@ int validate_config(const gt_config *c) {
   GT_CHECK(c->e_src >= 1 && c->e_src <= 512, "embedding_size_src out of range");
   GT_CHECK(c->e_tgt == 27, "embedding_size_tgt must be 27 (9 voices x hit/velocity/offset)");
   GT_CHECK(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
-  GT_CHECK(c->precision == GT_PREC_FP32 || c->precision == GT_PREC_BF16, "unknown precision mode");
+  GT_CHECK(c->precision == GT_PREC_FP32 || c->precision == GT_PREC_BF16 || c->precision == GT_PREC_FP32_TC, "unknown precision mode");
   return 0;
 }
 
@@ -231,8 +231,8 @@ static void make_plan(const gt_config &c, int64_t n_seq, int mode, char *base, P
     P.g0 = take(M * d);
     if (c.n_dec > 0) { P.dmem = take(M * d); P.dqc = take(M * d); P.dkvc = take(M * 2 * d); }
   }
-  if (c.precision == GT_PREC_BF16 && !(hybrid && tc_dec_attn_supported(c))) {      // (every block fused: no generic GEMM of width >= 32 left)
-    P.gemm_img_bytes = gemm_tc_scratch_bytes(M, d, F);
+  if (c.precision == GT_PREC_FP32_TC || (c.precision == GT_PREC_BF16 && !(hybrid && tc_dec_attn_supported(c)))) {      // (every block fused: no generic GEMM of width >= 32 left)
+    P.gemm_img_bytes = gemm_tc_scratch_bytes(M, d, F, c.precision == GT_PREC_FP32_TC);
     P.gemm_img = reinterpret_cast<uint8_t *>(take((P.gemm_img_bytes + 3) / 4));
   }
   P.bytes = off;
@@ -250,6 +250,7 @@ struct Ctx {
   int64_t n_seq, M;
   bool train;
   bool tc;                    // precision = bf16 on a shape without fused layer kernels: contractions run on gemm_tc
+  bool split;                 // precision = fp32_tc: contractions on gemm_tc in split form (three bf16 terms per fp32 operand), everything else fp32
   uint64_t seed, step;
   int64_t seq0;
   cudaStream_t st;
@@ -270,7 +271,8 @@ static const int64_t WGRAD_CHUNK = 2048;
 // qualifies (gemm_tc_supported), the fp32 SIMT GEMM otherwise (fp32 mode; K = 16 / 27 input layers and the 27-wide head)
 static int gemm(const Ctx &x, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbn, int64_t sbk, float *C,
                 int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpi &e, int64_t split_k_chunk) {
-  if (x.tc && gemm_tc_supported(sam, sak, sbn, sbk, M, N, K)) return gemm_tc(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, e, split_k_chunk, x.st);
+  if ((x.tc || x.split) && gemm_tc_supported(sam, sak, sbn, sbk, M, N, K))
+    return gemm_tc(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, e, split_k_chunk, x.st, x.split ? 1 : 0);
   return gemm_f32(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, e, split_k_chunk, x.st);
 }
 
@@ -286,7 +288,8 @@ static int linear_dgrad(const Ctx &x, const float *dY, int64_t N, const float *W
 static int linear_wgrad(const Ctx &x, const float *dY, int64_t ldy, int64_t N, const float *X, int64_t ldx, int64_t K,
                         float *dW, float *db) {
   GemmEpi e; e.atomic = 1;
-  GT_TRY(gemm(x, dY, 1, ldy, X, 1, ldx, dW, K, N, K, x.M, e, WGRAD_CHUNK));
+  // (fp32_tc: 512-token chunks — the tensor core's accumulator truncation grows with the UMMAs per accumulator, gemm_tc.cu)
+  GT_TRY(gemm(x, dY, 1, ldy, X, 1, ldx, dW, K, N, K, x.M, e, x.split ? 512 : WGRAD_CHUNK));
   if (db) GT_TRY(colsum_f32(dY, ldy, x.M, (int)N, db, x.st));
   return 0;
 }
@@ -681,6 +684,7 @@ static int make_ctx(Ctx &x, const gt_config *cfg, const float *params, float *gr
   x.P = params; x.G = grads; x.pe = pe; x.n_seq = n_seq; x.M = n_seq * T; x.train = train;
   x.seed = seed; x.step = step; x.seq0 = seq0; x.st = (cudaStream_t)stream;
   x.tc = cfg->precision == GT_PREC_BF16;
+  x.split = cfg->precision == GT_PREC_FP32_TC;
   return 0;
 }
 
@@ -711,6 +715,7 @@ const char *gt_last_error(void) { return g_err.c_str(); }
 
 int gt_path_kind(const gt_config *cfg) {
   if (validate_config(cfg)) return -1;
+  if (cfg->precision == GT_PREC_FP32_TC) return GT_PATH_GEMM_TC_SPLIT;
   if (cfg->precision != GT_PREC_BF16) return GT_PATH_FP32_SIMT;
   // encoder-decoder, d_model = 32, head dim 2 / 4 / 8: every block of every layer runs in the fused tcgen05 kernels
   if (cfg->n_dec > 0 && tc_encoder_supported(*cfg) && tc_dec_attn_supported(*cfg) && cfg->e_tgt == 27) return GT_PATH_FUSED_D32;
@@ -1038,7 +1043,7 @@ int gt_debug_gemm(int tc, const float *a, int64_t sam, int64_t sak, const float 
   e.residual = residual; e.ld_res = ld_res; e.mask_pos = mask_pos; e.ld_mask = ld_mask; e.mask_scale = mask_scale;
   const uint32_t thr = drop_threshold(drop_p);
   if (thr) { e.drop.thr = thr; e.drop.key = site_key(seed, step, site); e.drop.scale = drop_scale(thr); e.drop_row0 = row0; }
-  if (tc) return gemm_tc(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
+  if (tc) return gemm_tc(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream, tc == 2 ? 1 : 0);
   return gemm_f32(a, sam, sak, b, sbn, sbk, c, ldc, m, n, k, e, split_k_chunk, (cudaStream_t)stream);
 }
 

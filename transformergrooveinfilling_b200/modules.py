@@ -105,6 +105,9 @@ class _GrooveFn(torch.autograd.Function):
         return None, None, None, g
 
 
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp32_tc": _lib.PREC_FP32_TC}
+
+
 class _GrooveBase(nn.Module):
     def _build(self, d_model, e_src, e_tgt, nhead, dim_ff, dropout, n_enc, n_dec, max_len, device):
         if max_len != T_STEPS:
@@ -265,9 +268,10 @@ class _GrooveBase(nn.Module):
         return self.InputLayerEncoder.PositionalEncoding.pe
 
     def set_precision(self, mode: str):
-        """'fp32' (exact SIMT kernels) or 'bf16' (tcgen05 tensor-core kernels)."""
-        if mode not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        """'fp32' (exact SIMT kernels), 'fp32_tc' (the same 1e-4 parity mode with every Linear contraction on the tcgen05
+        tensor cores: fp32 operands split exactly into three bf16 terms, GT_PREC_FP32_TC) or 'bf16' (fused tcgen05 kernels)."""
+        if mode not in _PRECISIONS:
+            raise ValueError("precision must be 'fp32', 'fp32_tc' or 'bf16'")
         self.precision = mode
         self._train_ws = None
         return self
@@ -281,7 +285,7 @@ class _GrooveBase(nn.Module):
         n_dec = getattr(self, "num_decoder_layers", 0)
         return _lib.GtConfig(self.d_model, self.nhead, self.dim_feedforward, self.num_encoder_layers, n_dec,
                              self.embedding_size_src, self.embedding_size_tgt,
-                             _lib.PREC_BF16 if getattr(self, "precision", "fp32") == "bf16" else _lib.PREC_FP32,
+                             _PRECISIONS[getattr(self, "precision", "fp32")],
                              float(self.dropout if dropout is None else dropout), 0)
 
     def _check_input(self, x, e, what):

@@ -195,7 +195,7 @@ class SweepMember:
         kind = _lib.load().gt_path_kind(C.byref(cfg))
         if kind == _lib.PATH_FUSED_D32:
             return m.embedding_size_src in (16, 27)
-        return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC, _lib.PATH_FUSED_D256)
+        return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC, _lib.PATH_GEMM_TC_SPLIT, _lib.PATH_FUSED_D256)
 
     def _graph_for(self, bsz: int):
         """The captured step for full batches of ``bsz`` rows (built once; rebuilt if lr / precision change)."""
