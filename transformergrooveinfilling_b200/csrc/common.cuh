@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <stdlib.h>
+#include <utility>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -46,6 +48,32 @@ enum KernelClass {
   KC_TC_PREP = 16, KC_TC_LAYER_FWD = 17, KC_TC_LAYER_BWD = 18, KC_TC_HEAD = 19, KC_TC_WGRAD = 20, KC_TC_INPUT = 21, KC_GEMM_TC = 22,
   KC_MAX = 32
 };
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
+// A kernel launched through launch_pdl may become resident while its predecessor in the stream is still running; it must
+// execute griddep_wait() before it touches anything the predecessor writes (a no-op for a plain launch), and lets ITS successor
+// in with griddep_launch().  The fused layer kernels call both right after their prologue (TMEM allocation, barrier init,
+// bulk-TMA load of the layer's weight images — data written at the start of the step, at least two kernels back): with a grid
+// smaller than the GPU (the yaml batch sizes: 8 CTAs) the prologue of layer l + 1 runs on idle SMs while layer l computes.
+// launch_dependents AFTER the wait keeps the chain one deep: when kernel l + 1 starts, kernel l - 1 has completed.  GT_PDL=0 disables.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("GT_PDL") && atoi(getenv("GT_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 struct LaunchScope {     // RAII: counts the launch; records start/stop events when its class is being profiled
   int cls; cudaStream_t st; int slot;
   LaunchScope(int cls, cudaStream_t st);

@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_layer_fwd_kernel(const TcLa
       if constexpr (CROSS) mnext = pack8(a.mem + r * D + c0);
     }
   };
+  // everything above touched only this layer's parameters; the activations below are the previous kernel's output (common.cuh: PDL)
+  griddep_wait();
+  griddep_launch();
   fetch_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t grow = (int64_t)tile * TC_TILE + row;
@@ -646,13 +649,13 @@ static int launch_fwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
   if (args_devstep(a)) {                     // graph replay: dropout keys derived on the device from the step counter
     GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { LaunchScope _ls(KC_TC_LAYER_FWD, st);
-      tc_layer_fwd_kernel<32, DH, MODE, true><<<grid, FWD_THREADS, smem, st>>>(a); }
+      GT_CUDA(launch_pdl(tc_layer_fwd_kernel<32, DH, MODE, true>, dim3(grid), dim3(FWD_THREADS), smem, st, a)); }
     GT_CUDA(cudaGetLastError());
     return 0;
   }
   GT_CUDA(cudaFuncSetAttribute(tc_layer_fwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_FWD, st);
-    tc_layer_fwd_kernel<32, DH, MODE><<<grid, FWD_THREADS, smem, st>>>(a); }
+    GT_CUDA(launch_pdl(tc_layer_fwd_kernel<32, DH, MODE>, dim3(grid), dim3(FWD_THREADS), smem, st, a)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -857,6 +860,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
   const uint32_t id_mnmn_d = make_idesc_bf16(128, D, 1, 1);      // weight gradients A MN-major, B MN-major
   const uint32_t id_kk_3d = make_idesc_bf16(128, 3 * D, 0, 0);   // q|k|v recompute
 
+  // everything above touched only this layer's parameters; dy / the saved activations are earlier kernels' output (common.cuh: PDL)
+  griddep_wait();
+  griddep_launch();
   int iter = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++iter) {
     const int64_t grow = (int64_t)tile * TC_TILE + row;
@@ -1350,13 +1356,13 @@ static int launch_bwd(const TcLayerArgs &a, uint32_t smem, int grid, cudaStream_
   if (args_devstep(a)) {
     GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { LaunchScope _ls(KC_TC_LAYER_BWD, st);
-      tc_layer_bwd_kernel<32, DH, MODE, true><<<grid, BWD_THREADS, smem, st>>>(a); }
+      GT_CUDA(launch_pdl(tc_layer_bwd_kernel<32, DH, MODE, true>, dim3(grid), dim3(BWD_THREADS), smem, st, a)); }
     GT_CUDA(cudaGetLastError());
     return 0;
   }
   GT_CUDA(cudaFuncSetAttribute(tc_layer_bwd_kernel<32, DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { LaunchScope _ls(KC_TC_LAYER_BWD, st);
-    tc_layer_bwd_kernel<32, DH, MODE><<<grid, BWD_THREADS, smem, st>>>(a); }
+    GT_CUDA(launch_pdl(tc_layer_bwd_kernel<32, DH, MODE>, dim3(grid), dim3(BWD_THREADS), smem, st, a)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
