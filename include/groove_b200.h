@@ -13,7 +13,7 @@
  *   - return value 0 = success; non-zero = error, message via gt_last_error() (thread-local);
  *     no C++ exception crosses this boundary; shape / alignment violations are rejected before
  *     any launch;
- *   - all tensors are float32, row-major, batch-first: src [n_seq,32,e_src], y/hvo [n_seq,32,27].
+ *   - all tensors are float32, row-major, batch-first: src [n_seq,32,e_src], y/hvo [n_seq,32,e_tgt] (27 below stands for e_tgt).
  */
 #ifndef GROOVE_B200_H
 #define GROOVE_B200_H
@@ -56,7 +56,9 @@ typedef struct gt_config {
   int32_t n_enc;       /* num_encoder_layers */
   int32_t n_dec;       /* num_decoder_layers; 0 = encoder-only model */
   int32_t e_src;       /* embedding_size_src (16 MSO / 27 symbolic) */
-  int32_t e_tgt;       /* embedding_size_tgt (27 = 9 voices x h,v,o) */
+  int32_t e_tgt;       /* embedding_size_tgt = 3 x n_voices (hits | velocities | offsets thirds, BGT/models/io_layers.py:34-40);
+                          27 in every set of the reference — the fused stem / tail kernels cover 27, other widths take the
+                          generic kernels */
   int32_t precision;   /* GT_PREC_* */
   float   dropout;     /* p of every nn.Dropout on the path */
   int32_t reserved;
@@ -104,6 +106,9 @@ int gt_backward(const gt_config *cfg, const float *params, const float *pe,
 int64_t gt_loss_scratch_floats(int64_t n_seq);
 int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty,
             float *metrics6, float *d_hvo, float grad_scale, float *partials, void *stream);
+/* the same for hvo / y of [n_seq,32,3*n_voices] (train.py:12-13 splits the last axis into thirds); gt_loss = 9 voices */
+int gt_loss_voices(const float *hvo, const float *y, int64_t n_seq, int n_voices, float hit_loss_penalty,
+                   float *metrics6, float *d_hvo, float grad_scale, float *partials, void *stream);
 
 /* Evaluator metrics — the step right after predict() in the reference's per-epoch evaluation
  * (GrooveEvaluator/GrooveEvaluator/evaluator.py:189-251 get_hits_accuracies / get_velocity_errors /

@@ -18,6 +18,10 @@ CASES = {
     # full depth of the two d_model = 256 configurations (outputs, loss, gradient / parameter digests, 20-step trajectories)
     "c3_kicksnares_full":  (G.GrooveCfg(256, 2, 512, 6, 0, 16, 27), 3, 0.73, 0.004),
     "c4_random_large_full": (G.GrooveCfg(256, 16, 64, 11, 0, 16, 27), 3, 1.0, 0.004),
+    # embedding_size_tgt other than 27: the reference splits the head's output and y into thirds whatever the voice count
+    # (BGT/models/io_layers.py:34-40, train.py:12-13) — 4 voices encoder-only, 5 voices encoder-decoder
+    "voices4_enc":         (G.GrooveCfg(32, 4, 64, 2, 0, 16, 12), 4, 0.6, 0.05),
+    "voices5_encdec":      (G.GrooveCfg(32, 8, 48, 1, 2, 16, 15), 3, 0.4, 0.05),
 }
 # The SGD learning rate of the d_model = 256 trajectories is 0.004, not the yamls' 0.089 / 0.04: on a 3-sequence batch the yaml
 # rates make the loss jump 7 -> 15 -> 8 -> 13 ..., and float32 and float64 runs of the SAME arithmetic differ by 2 - 10 % after

@@ -426,13 +426,13 @@ def det_params(cfg: GrooveCfg, tag: int = 7, dtype=torch.float32):
 def det_batch(cfg: GrooveCfg, n: int, tag: int = 11, dtype=torch.float32):
     """Synthetic batch per SURVEY.md §8d: y = cat(hits~B(.15), vel*hits, off*hits); MSO x (E=16) =
     cat(strength*m, timing*m), m~B(.5); symbolic x (E=27) = an independent HVO draw."""
-    def hvo(tg):
-        hits = det_uniform(tg, n * 32 * 9, 0, 1).reshape(n, 32, 9) < 0.15
-        vel = det_uniform(tg + 1, n * 32 * 9, 0, 1).reshape(n, 32, 9) * hits
-        off = (det_uniform(tg + 2, n * 32 * 9, 0, 1).reshape(n, 32, 9) - 0.5) * hits
+    def hvo(tg, nv=9):
+        hits = det_uniform(tg, n * 32 * nv, 0, 1).reshape(n, 32, nv) < 0.15
+        vel = det_uniform(tg + 1, n * 32 * nv, 0, 1).reshape(n, 32, nv) * hits
+        off = (det_uniform(tg + 2, n * 32 * nv, 0, 1).reshape(n, 32, nv) - 0.5) * hits
         return np.concatenate([hits.astype(np.float32), vel, off], axis=2).astype(np.float32)
 
-    y = hvo(tag * 100)
+    y = hvo(tag * 100, cfg.e_tgt // 3)          # embedding_size_tgt = 3 x voices (9 in every set of the reference)
     if cfg.e_src == 27:
         x = hvo(tag * 100 + 10)
     else:

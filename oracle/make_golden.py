@@ -113,6 +113,9 @@ def demo_checkpoint_keys():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]                            # python -B oracle/make_golden.py [case ...]: regenerate only the named cases
     for nm, (cfg, n, pen, lr) in CASES.items():
-        run_case(nm, cfg, n, pen, lr)
-    demo_checkpoint_keys()
+        if not only or nm in only:
+            run_case(nm, cfg, n, pen, lr)
+    if not only:
+        demo_checkpoint_keys()

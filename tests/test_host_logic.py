@@ -44,7 +44,7 @@ def test_invalid_configs_are_rejected_with_messages():
     bad = _lib.GtConfig(30, 4, 16, 1, 0, 16, 27, 0, 0.0, 0)
     assert lib.gt_param_count(C.byref(bad)) < 0 and b"divisible" in lib.gt_last_error()
     bad = _lib.GtConfig(32, 4, 16, 1, 0, 16, 26, 0, 0.0, 0)
-    assert lib.gt_workspace_bytes(C.byref(bad), 4, 1) < 0 and b"27" in lib.gt_last_error()
+    assert lib.gt_workspace_bytes(C.byref(bad), 4, 1) < 0 and b"multiple of 3" in lib.gt_last_error()
     ok = _lib.GtConfig(32, 4, 16, 1, 0, 16, 27, 0, 0.0, 0)
     assert lib.gt_workspace_bytes(C.byref(ok), 0, 1) < 0
     assert lib.gt_workspace_bytes(C.byref(ok), 8, 1) > lib.gt_workspace_bytes(C.byref(ok), 8, 0) > 0

@@ -41,6 +41,7 @@ SIGNATURES = {
     "gt_backward": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),
     "gt_loss_scratch_floats": (_i64, [_i64]),
     "gt_loss": (C.c_int, [_p, _p, _i64, _f, _p, _p, _f, _p, _p]),
+    "gt_loss_voices": (C.c_int, [_p, _p, _i64, C.c_int, _f, _p, _p, _f, _p, _p]),
     "gt_eval_scratch_floats": (_i64, [_i64, C.c_int]),
     "gt_eval_metrics": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gt_train_step": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, _u64, _u64, _i64, _p]),

@@ -291,7 +291,7 @@ int head_activation(float *hvo, int64_t M, int e_tgt, float thres, cudaStream_t 
 // dlogits = d_hvo * activation'(hvo)
 int head_activation_bwd(const float *d_hvo, const float *hvo, float *dlogits, int64_t M, int e_tgt, cudaStream_t st);
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
-                 float grad_scale, float *partials, cudaStream_t st);
+                 float grad_scale, float *partials, cudaStream_t st, int n_voices = 9);
 int64_t loss_scratch_floats(int64_t n_seq);
 int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metrics6, cudaStream_t st);
 // fused ends of the d_model = 32 path (edge32.cu): input layer + positional encoding + dropout ; final LayerNorm + output

@@ -676,18 +676,22 @@ int64_t loss_scratch_floats(int64_t n_seq) {
   int64_t blocks = (n_seq * T + LOSS_ROWS_PER_BLOCK - 1) / LOSS_ROWS_PER_BLOCK;
   return 4 * (blocks > 0 ? blocks : 1);
 }
-__global__ void loss_partial_kernel(const float *__restrict__ hvo, const float *__restrict__ y, int64_t M, float penalty,
+// VT = 9: the reference's nine drum voices, fully unrolled; VT = 0: any voice count V (embedding_size_tgt = 3 V — the reference's
+// calculate_loss splits y into thirds, BGT/models/train.py:12-13)
+template <int VT>
+__global__ void loss_partial_kernel(const float *__restrict__ hvo, const float *__restrict__ y, int64_t M, int Vrt, float penalty,
                                     float *d_hvo, float gscale, float *partials) {
   __shared__ float red[4][LOSS_ROWS_PER_BLOCK / 32];
+  const int V = VT > 0 ? VT : Vrt;
   const int64_t row = (int64_t)blockIdx.x * LOSS_ROWS_PER_BLOCK + threadIdx.x;
   float bce = 0.f, mv = 0.f, mo = 0.f, ok = 0.f;
   if (row < M) {
-    const float *p = hvo + row * 27, *t = y + row * 27;
-    float *g = d_hvo ? d_hvo + row * 27 : nullptr;
+    const float *p = hvo + row * 3 * V, *t = y + row * 3 * V;
+    float *g = d_hvo ? d_hvo + row * 3 * V : nullptr;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      float h = p[k], v = p[9 + k], o = p[18 + k];
-      float yh = t[k], yv = t[9 + k], yo = t[18 + k];
+    for (int k = 0; k < V; ++k) {
+      float h = p[k], v = p[V + k], o = p[2 * V + k];
+      float yh = t[k], yv = t[V + k], yo = t[2 * V + k];
       float w = (yh == 1.f) ? 1.f : penalty;
       float sp = fmaxf(h, 0.f) - h * yh + log1pf(expf(-fabsf(h)));
       bce = fmaf(sp, w, bce);
@@ -699,8 +703,8 @@ __global__ void loss_partial_kernel(const float *__restrict__ hvo, const float *
       ok += (hit == yh) ? 1.f : 0.f;
       if (g) {
         g[k] = gscale * w * (sg - yh);
-        g[9 + k] = gscale * 2.f * w * dv;
-        g[18 + k] = gscale * 2.f * w * dof;
+        g[V + k] = gscale * 2.f * w * dv;
+        g[2 * V + k] = gscale * 2.f * w * dof;
       }
     }
   }
@@ -718,7 +722,7 @@ __global__ void loss_partial_kernel(const float *__restrict__ hvo, const float *
     partials[(int64_t)blockIdx.x * 4 + threadIdx.x] = s;
   }
 }
-__global__ void loss_final_kernel(const float *__restrict__ partials, int64_t blocks, int64_t M, float *metrics6) {
+__global__ void loss_final_kernel(const float *__restrict__ partials, int64_t blocks, int64_t M, int V, float *metrics6) {
   __shared__ double red[4][256];
   double acc[4] = {0, 0, 0, 0};
   for (int64_t b = threadIdx.x; b < blocks; b += blockDim.x)
@@ -733,7 +737,7 @@ __global__ void loss_final_kernel(const float *__restrict__ partials, int64_t bl
   if (threadIdx.x == 0) {
     double bce = red[0][0] / (double)M, mv = red[1][0] / (double)M, mo = red[2][0] / (double)M;
     metrics6[0] = (float)(bce + mv + mo);
-    metrics6[1] = (float)(red[3][0] / ((double)M * 9.0));
+    metrics6[1] = (float)(red[3][0] / ((double)M * (double)V));
     metrics6[2] = (float)exp(bce);
     metrics6[3] = (float)bce;
     metrics6[4] = (float)mv;
@@ -742,21 +746,23 @@ __global__ void loss_final_kernel(const float *__restrict__ partials, int64_t bl
 }
 int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metrics6, cudaStream_t st) {
   { LaunchScope _ls(KC_LOSS, st);
-  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, metrics6); }
+  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, 9, metrics6); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
 int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty, float *metrics6, float *d_hvo,
-                 float grad_scale, float *partials, cudaStream_t st) {
+                 float grad_scale, float *partials, cudaStream_t st, int n_voices) {
   GT_NVTX("groove.loss");
   int64_t M = n_seq * T;
   GT_CHECK(M > 0, "empty batch");
+  GT_CHECK(n_voices >= 1, "loss: embedding_size_tgt must be a positive multiple of 3");
   int64_t blocks = (M + LOSS_ROWS_PER_BLOCK - 1) / LOSS_ROWS_PER_BLOCK;
   { LaunchScope _ls(KC_LOSS, st);
-  loss_partial_kernel<<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, penalty, d_hvo, grad_scale / (float)M, partials); }
+  if (n_voices == 9) loss_partial_kernel<9><<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, 9, penalty, d_hvo, grad_scale / (float)M, partials);
+  else loss_partial_kernel<0><<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, n_voices, penalty, d_hvo, grad_scale / (float)M, partials); }
   GT_CUDA(cudaGetLastError());
   { LaunchScope _ls(KC_LOSS, st);
-  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, metrics6); }
+  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, n_voices, metrics6); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -90,7 +90,9 @@ int validate_config(const gt_config *c) {
   GT_CHECK(c->n_enc >= 1 && c->n_enc <= 64, "num_encoder_layers must be in [1,64]");
   GT_CHECK(c->n_dec >= 0 && c->n_dec <= 64, "num_decoder_layers must be in [0,64]");
   GT_CHECK(c->e_src >= 1 && c->e_src <= 512, "embedding_size_src out of range");
-  GT_CHECK(c->e_tgt == 27, "embedding_size_tgt must be 27 (9 voices x hit/velocity/offset)");
+  // BGT/models/io_layers.py:34-40 / train.py:12-13 split the target embedding into thirds (hits | velocities | offsets)
+  GT_CHECK(c->e_tgt >= 3 && c->e_tgt <= 192 && c->e_tgt % 3 == 0,
+           "embedding_size_tgt must be a multiple of 3 in [3, 192] (n_voices x hit / velocity / offset; the reference's sets use 27)");
   GT_CHECK(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
   GT_CHECK(c->precision == GT_PREC_FP32 || c->precision == GT_PREC_BF16 || c->precision == GT_PREC_FP32_TC, "unknown precision mode");
   return 0;
@@ -778,11 +780,17 @@ int gt_backward(const gt_config *cfg, const float *params, const float *pe, cons
 
 int64_t gt_loss_scratch_floats(int64_t n_seq) { return loss_scratch_floats(n_seq); }
 
-int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty, float *metrics6, float *d_hvo,
-            float grad_scale, float *partials, void *stream) {
+int gt_loss_voices(const float *hvo, const float *y, int64_t n_seq, int n_voices, float hit_loss_penalty, float *metrics6,
+                   float *d_hvo, float grad_scale, float *partials, void *stream) {
   GT_CHECK(hvo && y && metrics6 && partials, "gt_loss: null pointer");
   GT_CHECK(n_seq >= 1, "gt_loss: empty batch");
-  return loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, d_hvo, grad_scale, partials, (cudaStream_t)stream);
+  GT_CHECK(n_voices >= 1 && n_voices <= 64, "gt_loss: n_voices must be in [1, 64]");
+  return loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, d_hvo, grad_scale, partials, (cudaStream_t)stream, n_voices);
+}
+
+int gt_loss(const float *hvo, const float *y, int64_t n_seq, float hit_loss_penalty, float *metrics6, float *d_hvo,
+            float grad_scale, float *partials, void *stream) {
+  return gt_loss_voices(hvo, y, n_seq, 9, hit_loss_penalty, metrics6, d_hvo, grad_scale, partials, stream);
 }
 
 int64_t gt_eval_scratch_floats(int64_t n_seq, int n_voices) {
@@ -820,7 +828,7 @@ int gt_train_step(const gt_config *cfg, const float *params, const float *pe, co
     return backward_all(x, pl, src, tgt_in, nullptr, pl.dlog);
   }
   GT_TRY(forward_all(x, pl, src, tgt_in, hvo));
-  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, x.st));
+  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, hit_loss_penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, x.st, cfg->e_tgt / 3));
   return backward_all(x, pl, src, tgt_in, hvo, pl.d_hvo);
 }
 

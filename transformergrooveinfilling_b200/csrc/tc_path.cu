@@ -506,7 +506,7 @@ int tc_train_step(const gt_config &c, const Layout &L, const float *params, cons
     return tc_backward_all(x, pl, src, nullptr, pl.dlog);
   }
   GT_TRY(tc_forward_all(x, pl, src, hvo, true, -1.f));
-  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, st));
+  GT_TRY(loss_fwd_bwd(hvo, y, n_seq, penalty, metrics6, pl.d_hvo, 1.f, pl.loss_partials, st, c.e_tgt / 3));
   return tc_backward_all(x, pl, src, hvo, pl.d_hvo);
 }
 

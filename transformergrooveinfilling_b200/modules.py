@@ -114,8 +114,10 @@ class _GrooveBase(nn.Module):
             raise ValueError(f"max_len must be {T_STEPS} (the reference requires T == max_len, BGT/models/utils.py:49)")
         if d_model % nhead != 0:
             raise AssertionError("embed_dim must be divisible by num_heads")
-        if e_tgt != 27:
-            raise ValueError("embedding_size_tgt must be 27 (9 voices x hit/velocity/offset)")
+        if e_tgt < 3 or e_tgt % 3 != 0:
+            # BGT/models/io_layers.py:34-40 splits the head's output into thirds (hits | velocities | offsets); every set of the
+            # reference has 9 voices (27), which is what the fused stem / tail kernels cover — other widths run the generic kernels
+            raise ValueError("embedding_size_tgt must be a positive multiple of 3 (n_voices x hit / velocity / offset)")
         self._spec_list = _spec(d_model, dim_ff, e_src, e_tgt, n_enc, n_dec)
         self.precision = "fp32"
         # dropout stream: tied to torch's seed like the reference's nn.Dropout (torch.manual_seed before construction gives a
@@ -332,7 +334,8 @@ class _GrooveBase(nn.Module):
 
     @staticmethod
     def _split(hvo):
-        h, v, o = hvo[..., 0:9], hvo[..., 9:18], hvo[..., 18:27]
+        nv = hvo.shape[-1] // 3
+        h, v, o = hvo[..., 0:nv], hvo[..., nv:2 * nv], hvo[..., 2 * nv:3 * nv]
         for t in (h, v, o):
             t._groove_hvo = hvo       # lets calculate_loss find the packed [N,32,27] tensor without a copy
         return h, v, o
@@ -353,7 +356,7 @@ class _GrooveBase(nn.Module):
         key = (n, self.precision)
         if self._train_ws is None or self._train_ws[0] != key:
             self._train_ws = (key, self._workspace(n, 1, x.device),
-                              torch.empty(n, T_STEPS, 27, dtype=torch.float32, device=x.device))
+                              torch.empty(n, T_STEPS, self.embedding_size_tgt, dtype=torch.float32, device=x.device))
         _, ws, hvo = self._train_ws
         metrics = torch.empty(6, dtype=torch.float32, device=x.device)
         step = self._step
@@ -372,9 +375,9 @@ class _GrooveBase(nn.Module):
         n = src.shape[0]
         ws = self._workspace(n, 0 if literal else 2, src.device)
         if out is None:
-            out = torch.empty(n, T_STEPS, 27, dtype=torch.float32, device=src.device)
-        elif tuple(out.shape) != (n, T_STEPS, 27) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != src.device:
-            raise ValueError("out must be a contiguous float32 [n, 32, 27] tensor on the source's device")
+            out = torch.empty(n, T_STEPS, self.embedding_size_tgt, dtype=torch.float32, device=src.device)
+        elif tuple(out.shape) != (n, T_STEPS, self.embedding_size_tgt) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != src.device:
+            raise ValueError("out must be a contiguous float32 [n, 32, embedding_size_tgt] tensor on the source's device")
         cfg = self._cfg()
         _lib.check(lib.gt_predict_variant(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._pe_flat()), _lib.ptr(src), n,
                                           float(thres), _lib.ptr(out), _lib.ptr(ws), ws.numel(), 1 if literal else 0,
@@ -418,7 +421,8 @@ class GrooveTransformerEncoder(_GrooveBase):
         self.eval()
         with torch.no_grad():
             out = self._predict_hvo(src, thres)
-        return out[..., 0:9].to(torch.int64), out[..., 9:18], out[..., 18:27]
+        nv = self.embedding_size_tgt // 3
+        return out[..., 0:nv].to(torch.int64), out[..., nv:2 * nv], out[..., 2 * nv:]
 
 
 class GrooveTransformer(_GrooveBase):
@@ -454,4 +458,5 @@ class GrooveTransformer(_GrooveBase):
         self.eval()
         with torch.no_grad():
             out = self._predict_hvo(src, thres)
-        return out[..., 0:9], out[..., 9:18], out[..., 18:27]      # all float32, like the reference
+        nv = self.embedding_size_tgt // 3
+        return out[..., 0:nv], out[..., nv:2 * nv], out[..., 2 * nv:]      # all float32, like the reference

@@ -153,7 +153,8 @@ class HostPredictor:
         e = model.embedding_size_src
         self.s_in, self.s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self.xs = [torch.empty(self.chunk, 32, e, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.os = [torch.empty(self.chunk, 32, 27, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.e_tgt = int(model.embedding_size_tgt)
+        self.os = [torch.empty(self.chunk, 32, self.e_tgt, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -166,9 +167,9 @@ class HostPredictor:
         xh = xh.contiguous()
         n = xh.shape[0]
         if out is None:
-            out = torch.empty(n, 32, 27, dtype=torch.float32).pin_memory()
-        elif tuple(out.shape) != (n, 32, 27) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
-            raise ValueError("out must be a contiguous float32 host tensor [N, 32, 27]")
+            out = torch.empty(n, 32, self.e_tgt, dtype=torch.float32).pin_memory()
+        elif tuple(out.shape) != (n, 32, self.e_tgt) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 host tensor [N, 32, embedding_size_tgt]")
         self.model.eval()                                         # predict()'s side effect (BGT/models/transformer.py:118)
         cur = torch.cuda.current_stream(self.device)
         self.s_in.wait_stream(cur)

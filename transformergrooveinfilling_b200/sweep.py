@@ -128,7 +128,7 @@ class SweepMember:
         dev = ld.device
         key = (bsz, model.precision)
         if model._train_ws is None or model._train_ws[0] != key:
-            model._train_ws = (key, model._workspace(bsz, 1, dev), torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev))
+            model._train_ws = (key, model._workspace(bsz, 1, dev), torch.empty(bsz, 32, model.embedding_size_tgt, dtype=torch.float32, device=dev))
         _, ws, hvo = model._train_ws
         xbuf = torch.empty((bsz,) + tuple(ld.x.shape[1:]), device=dev)
         ybuf = torch.empty((bsz,) + tuple(ld.y.shape[1:]), device=dev)
@@ -194,7 +194,7 @@ class SweepMember:
             return False
         kind = _lib.load().gt_path_kind(C.byref(cfg))
         if kind == _lib.PATH_FUSED_D32:
-            return m.embedding_size_src in (16, 27)
+            return m.embedding_size_src in (16, 27) and m.embedding_size_tgt == 27
         return kind in (_lib.PATH_FP32_SIMT, _lib.PATH_GEMM_TC, _lib.PATH_GEMM_TC_SPLIT, _lib.PATH_FUSED_D256)
 
     def _graph_for(self, bsz: int):
@@ -218,7 +218,7 @@ class SweepMember:
             assert (b1, b2, opt.param_groups[0]["eps"]) == (0.9, 0.999, 1e-8), "the captured step applies torch's Adam defaults"
         ring_slots = 1024
         g = dict(key=key, ring_slots=ring_slots,
-                 ws=model._workspace(bsz, 1, dev), hvo=torch.empty(bsz, 32, 27, dtype=torch.float32, device=dev),
+                 ws=model._workspace(bsz, 1, dev), hvo=torch.empty(bsz, 32, model.embedding_size_tgt, dtype=torch.float32, device=dev),
                  xbuf=torch.zeros((bsz,) + tuple(ld.x.shape[1:]), device=dev), ybuf=torch.zeros((bsz,) + tuple(ld.y.shape[1:]), device=dev),
                  met6=torch.zeros(6, dtype=torch.float32, device=dev), ring=torch.zeros(ring_slots, 6, dtype=torch.float32, device=dev),
                  counters=torch.zeros(4, dtype=torch.int64, device=dev), perm=torch.zeros(ld.x.shape[0], dtype=torch.int64, device=dev))

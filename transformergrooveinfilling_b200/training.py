@@ -31,8 +31,8 @@ class _LossFn(torch.autograd.Function):
         metrics = torch.empty(6, dtype=torch.float32, device=hvo.device)
         d_hvo = torch.empty_like(hvo) if ctx.needs_input_grad[0] else None
         partials = torch.empty(lib.gt_loss_scratch_floats(n), dtype=torch.float32, device=hvo.device)
-        _lib.check(lib.gt_loss(_lib.ptr(hvo), _lib.ptr(y), n, float(penalty), _lib.ptr(metrics), _lib.ptr(d_hvo), 1.0,
-                               _lib.ptr(partials), _lib.stream_ptr(hvo.device)), "gt_loss")
+        _lib.check(lib.gt_loss_voices(_lib.ptr(hvo), _lib.ptr(y), n, hvo.shape[2] // 3, float(penalty), _lib.ptr(metrics),
+                                      _lib.ptr(d_hvo), 1.0, _lib.ptr(partials), _lib.stream_ptr(hvo.device)), "gt_loss")
         ctx.d_hvo = d_hvo
         ctx.mark_non_differentiable(metrics)
         return metrics[0].clone(), metrics
@@ -68,8 +68,8 @@ def calculate_loss(prediction, y, bce_fn=None, mse_fn=None, hit_loss_penalty=1.0
     hvo = _packed(prediction)
     if not hvo.is_cuda:
         raise RuntimeError("groove_b200 calculate_loss runs on CUDA only — there is no CPU fallback")
-    if y.shape != hvo.shape or y.shape[1:] != (32, 27):
-        raise ValueError(f"y must have shape {tuple(hvo.shape)}, got {tuple(y.shape)}")
+    if y.shape != hvo.shape or y.shape[1] != 32 or y.shape[2] % 3 != 0:
+        raise ValueError(f"y must have shape {tuple(hvo.shape)} = [N, 32, 3 x voices], got {tuple(y.shape)}")
     y = y.to(hvo.device).contiguous().float()
     loss, metrics = _LossFn.apply(hvo.contiguous(), y, float(hit_loss_penalty))
     m = metrics.tolist()                      # ONE device->host read instead of the reference's five .item()
