@@ -62,16 +62,37 @@ __global__ void __launch_bounds__(EG_WARPS * 32) stem32_kernel(const float *__re
   }
   __syncwarp();
   const int64_t n_groups = (M + EG_TOK - 1) / EG_TOK;
-  for (int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * EG_WARPS) {
+  const int64_t gstride = (int64_t)gridDim.x * EG_WARPS;
+  // software pipeline: the NEXT group's source rows (EG_TOK * E contiguous floats: NS per lane) and gradient rows are requested
+  // before the current group is processed, so their latency overlaps a group of arithmetic instead of opening every group
+  constexpr int NS = (EG_TOK * E + 31) / 32;
+  float ns[NS], ndv[BWD ? EG_TOK : 1];
+  auto fetch = [&](int64_t gn) {
+    const int64_t t0 = gn * EG_TOK;
+    const int nt = gn < n_groups ? (int)min((int64_t)EG_TOK, M - t0) : 0;
+#pragma unroll
+    for (int u = 0; u < NS; ++u) ns[u] = (lane + 32 * u) < nt * E ? __ldg(src + t0 * E + lane + 32 * u) : 0.f;
+    if (BWD) {
+#pragma unroll
+      for (int q = 0; q < EG_TOK; ++q) ndv[q] = q < nt ? __ldg(dx0 + (t0 + q) * 32 + lane) : 0.f;
+    }
+  };
+  fetch((int64_t)blockIdx.x * EG_WARPS + warp);
+  for (int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp; g < n_groups; g += gstride) {
     const int64_t tok0 = g * EG_TOK;
     const int ntok = (int)min((int64_t)EG_TOK, M - tok0);
     // the group's source rows are contiguous in memory: coalesced loads, scattered into padded rows
-    for (int i = lane; i < ntok * E; i += 32) sx[warp][i / E][i % E] = __ldg(src + tok0 * E + i);
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int i = lane + 32 * u;
+      if (i < EG_TOK * E) sx[warp][i / E][i % E] = ns[u];
+    }
     float dv[EG_TOK];
     if (BWD) {
 #pragma unroll
-      for (int q = 0; q < EG_TOK; ++q) dv[q] = q < ntok ? __ldg(dx0 + (tok0 + q) * 32 + lane) : 0.f;
+      for (int q = 0; q < EG_TOK; ++q) dv[q] = ndv[q];
     }
+    fetch(g + gstride);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
@@ -149,19 +170,31 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_fwd_kernel(const float *
   const float bj = lane < 27 ? bout[lane] : 0.f, gm = gamma[lane], be = beta[lane];
   float a_loss = 0.f, a_ok = 0.f;                  // role 0: bce / correct hits ; role 1: velocity mse ; role 2: offset mse
   const int64_t n_groups = (M + EG_TOK - 1) / EG_TOK;
-  for (int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * EG_WARPS) {
+  const int64_t gstride = (int64_t)gridDim.x * EG_WARPS;
+  // software pipeline (as in tail32_bwd_kernel): the rows of the warp's NEXT group are requested before the current group is
+  // processed — at ~16 resident warps per SM (32 weight registers per lane) the load latency was exposed once per group
+  float nx[EG_TOK], nyj[EG_TOK], nyh[EG_TOK];
+  auto fetch = [&](int64_t gn) {
+    const int64_t t0 = gn * EG_TOK;
+#pragma unroll
+    for (int q = 0; q < EG_TOK; ++q) {
+      const bool ok = gn < n_groups && t0 + q < M;
+      nx[q] = ok ? __ldg(x + (t0 + q) * 32 + lane) : 0.f;
+      nyj[q] = 0.f; nyh[q] = 0.f;
+      if (y != nullptr && ok && lane < 27) {
+        nyj[q] = __ldg(y + (t0 + q) * 27 + lane);
+        nyh[q] = __ldg(y + (t0 + q) * 27 + (lane - 9 * role));
+      }
+    }
+  };
+  fetch((int64_t)blockIdx.x * EG_WARPS + warp);
+  for (int64_t g = (int64_t)blockIdx.x * EG_WARPS + warp; g < n_groups; g += gstride) {
     const int64_t tok0 = g * EG_TOK;
     const int ntok = (int)min((int64_t)EG_TOK, M - tok0);
     float xv[EG_TOK], yj[EG_TOK], yh[EG_TOK];
 #pragma unroll
-    for (int q = 0; q < EG_TOK; ++q) {
-      xv[q] = q < ntok ? __ldg(x + (tok0 + q) * 32 + lane) : 0.f;
-      yj[q] = 0.f; yh[q] = 0.f;
-      if (y != nullptr && q < ntok && lane < 27) {
-        yj[q] = __ldg(y + (tok0 + q) * 27 + lane);
-        yh[q] = __ldg(y + (tok0 + q) * 27 + (lane - 9 * role));
-      }
-    }
+    for (int q = 0; q < EG_TOK; ++q) { xv[q] = nx[q]; yj[q] = nyj[q]; yh[q] = nyh[q]; }
+    fetch(g + gstride);
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
       const float mu = eg_warp_sum(xv[q]) * (1.f / 32);
@@ -257,10 +290,13 @@ __global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const floa
                                                                    int64_t M) {
   __shared__ __align__(16) float sz[EG_WARPS][EG_TOK][32], sd[EG_WARPS][EG_TOK][32];
   __shared__ float sacc[27 * 32 + 32 + 64];
-  __shared__ float sWc[28 * 32];                    // W_out [27][32] (+ a zero row): lane c reads column c, conflict-free
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = lane / 9;
-  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) sWc[i] = i < 27 * 32 ? Wout[i] : 0.f;
+  // lane c keeps column c of W_out [27][32] (+ a zero row) in registers: read from shared memory it was 28 of the 45 shared-memory
+  // wavefronts per token, and the kernel ran at the shared-memory pipe's rate (2.6 x its HBM time)
+  float wc[28];
+#pragma unroll
+  for (int j = 0; j < 28; ++j) wc[j] = j < 27 ? __ldg(Wout + j * 32 + lane) : 0.f;
   const float gm = gamma[lane], be = beta[lane];
   float accw[32], accb = 0.f, adg = 0.f, adb = 0.f;
 #pragma unroll
@@ -271,15 +307,17 @@ __global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const floa
   const int64_t gstride = (int64_t)gridDim.x * EG_WARPS;
   // software pipeline: the rows of the warp's NEXT group are loaded before the current group is processed, so the global
   // load latency (this kernel runs at 16 warps per SM) overlaps a whole group of arithmetic
-  float nx[EG_TOK], nmu[EG_TOK], nrs[EG_TOK], nd[EG_TOK];
+  // (row statistics: lane q holds those of token q — one load per lane instead of EG_TOK broadcast loads, handed out by shuffles)
+  float nx[EG_TOK], nd[EG_TOK], nmu = 0.f, nrs = 0.f;
   auto fetch = [&](int64_t g) {
     const int64_t tok0 = g * EG_TOK;
+    const bool okl = g < n_groups && lane < EG_TOK && tok0 + lane < M;
+    nmu = okl ? __ldg(mean + tok0 + lane) : 0.f;
+    nrs = okl ? __ldg(rstd + tok0 + lane) : 0.f;
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
       const bool ok = g < n_groups && tok0 + q < M;
       nx[q] = ok ? __ldg(x + (tok0 + q) * 32 + lane) : 0.f;
-      nmu[q] = ok ? __ldg(mean + tok0 + q) : 0.f;
-      nrs[q] = ok ? __ldg(rstd + tok0 + q) : 0.f;
       float d = 0.f;
       if (ok && lane < 27) {
         d = __ldg(d_in + (tok0 + q) * 27 + lane);
@@ -299,8 +337,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const floa
     float xh[EG_TOK], rs[EG_TOK], dq[EG_TOK];
 #pragma unroll
     for (int q = 0; q < EG_TOK; ++q) {
-      rs[q] = nrs[q];
-      xh[q] = (nx[q] - nmu[q]) * rs[q];
+      rs[q] = __shfl_sync(0xffffffffu, nrs, q);
+      xh[q] = (nx[q] - __shfl_sync(0xffffffffu, nmu, q)) * rs[q];
       dq[q] = nd[q];
       sz[warp][q][lane] = q < ntok ? xh[q] * gm + be : 0.f;
       sd[warp][q][lane] = dq[q];
@@ -321,8 +359,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const floa
 #pragma unroll
       for (int j = 0; j < 28; j += 4) {
         const float4 dd = *reinterpret_cast<const float4 *>(&sd[warp][q][j]);
-        dz0 = fmaf(dd.x, sWc[j * 32 + lane], dz0); dz1 = fmaf(dd.y, sWc[(j + 1) * 32 + lane], dz1);
-        dz0 = fmaf(dd.z, sWc[(j + 2) * 32 + lane], dz0); dz1 = fmaf(dd.w, sWc[(j + 3) * 32 + lane], dz1);
+        dz0 = fmaf(dd.x, wc[j], dz0); dz1 = fmaf(dd.y, wc[j + 1], dz1);
+        dz0 = fmaf(dd.z, wc[j + 2], dz0); dz1 = fmaf(dd.w, wc[j + 3], dz1);
       }
       const float dz = dz0 + dz1, gd = dz * gm;
       const float s1 = eg_warp_sum(gd) * (1.f / 32), s2 = eg_warp_sum(gd * xh[q]) * (1.f / 32);
