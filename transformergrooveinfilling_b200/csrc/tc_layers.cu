@@ -1311,24 +1311,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_layer_bwd_kernel(const TcLa
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) tmem_ld16(t + lane_off + (uint32_t)cb, v + cb);
       tmem_ld_wait();
-      if (job < nchunk) {
-        if (m < FC) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) atomicAdd(a.gw1 + (int64_t)(job * FC + m) * D + i, v[i]);
-        }
-      } else if (job < 2 * nchunk) {
+      if (job >= nchunk && job < 2 * nchunk) {          // dW2^T: lane = hidden unit = the contiguous index of gw2 — coalesced as it is
         if (m < FC) {
 #pragma unroll
           for (int j = 0; j < D; ++j) atomicAdd(a.gw2 + (int64_t)j * F + (job - nchunk) * FC + m, v[j]);
         }
-      } else if (job == 2 * nchunk) {
-        if (m < 3 * D) {
+      } else {
+        // dW1 / dWqkv / dWo: lane = output ROW, the 32 values of a thread are contiguous in memory — as scalar atomics every warp
+        // instruction touched 32 different 128-byte lines.  The warp's 32 x 32 block is turned through (dead) shared memory so
+        // that one instruction adds one whole row: 32 x fewer L2 requests (the flush is 160 KB per CTA onto the same 40 K words).
+        float *gdst;
+        int rows;
+        if (job < nchunk) { gdst = a.gw1 + (int64_t)job * FC * D; rows = FC; }
+        else if (job == 2 * nchunk) { gdst = a.gwqkv; rows = 3 * D; }
+        else { gdst = a.gwo; rows = D; }
+        float *stg = reinterpret_cast<float *>(smem + sp.xin) + warp * (32 * 33);
 #pragma unroll
-          for (int i = 0; i < D; ++i) atomicAdd(a.gwqkv + (int64_t)m * D + i, v[i]);
-        }
-      } else if (m < D) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) atomicAdd(a.gwo + (int64_t)m * D + i, v[i]);
+        for (int i = 0; i < D; ++i) stg[lane * 33 + i] = v[i];
+        __syncwarp();
+        const int m0 = (warp & 3) * 32;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+          if (m0 + r < rows) atomicAdd(gdst + (int64_t)(m0 + r) * D + lane, stg[r * 33 + lane]);
+        __syncwarp();
       }
     }
   }
