@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32) stem32_kernel(const float *__re
                                                                float *__restrict__ x0, const float *__restrict__ dx0,
                                                                float *gW, float *gb, int64_t M, Drop drop, int64_t e0) {
   constexpr int EP = StemSmem<E>::EP;
+  griddep_wait();                                    // launched with launch_pdl (common.cuh): nothing is read before the predecessor is done
+  griddep_launch();
   drop_resolve(drop);                                // graph replay: key from the device step counter
   __shared__ __align__(16) float sx[EG_WARPS][EG_TOK][EP];
   __shared__ float sacc[BWD ? 32 * E + 32 : 1];
@@ -137,8 +139,8 @@ int edge32_stem_fwd(const float *src, int E, const float *W, const float *b, con
   if (M == 0) return 0;
   GT_CHECK(E == 16 || E == 27, "edge32: embedding_size_src must be 16 or 27");
   LaunchScope _ls(KC_TC_INPUT, st);
-  if (E == 16) stem32_kernel<16, false><<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(src, W, b, pe, x0, nullptr, nullptr, nullptr, M, drop, row0 * 32);
-  else stem32_kernel<27, false><<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(src, W, b, pe, x0, nullptr, nullptr, nullptr, M, drop, row0 * 32);
+  if (E == 16) GT_CUDA(launch_pdl(stem32_kernel<16, false>, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, src, W, b, pe, x0, (const float *)nullptr, (float *)nullptr, (float *)nullptr, M, drop, row0 * 32));
+  else GT_CUDA(launch_pdl(stem32_kernel<27, false>, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, src, W, b, pe, x0, (const float *)nullptr, (float *)nullptr, (float *)nullptr, M, drop, row0 * 32));
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -147,8 +149,8 @@ int edge32_stem_bwd(const float *dx0, const float *src, int E, const float *W, c
   if (M == 0) return 0;
   GT_CHECK(E == 16 || E == 27, "edge32: embedding_size_src must be 16 or 27");
   LaunchScope _ls(KC_TC_INPUT, st);
-  if (E == 16) stem32_kernel<16, true><<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(src, W, b, nullptr, nullptr, dx0, gW, gb, M, drop, row0 * 32);
-  else stem32_kernel<27, true><<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(src, W, b, nullptr, nullptr, dx0, gW, gb, M, drop, row0 * 32);
+  if (E == 16) GT_CUDA(launch_pdl(stem32_kernel<16, true>, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, src, W, b, (const float *)nullptr, (float *)nullptr, dx0, gW, gb, M, drop, row0 * 32));
+  else GT_CUDA(launch_pdl(stem32_kernel<27, true>, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, src, W, b, (const float *)nullptr, (float *)nullptr, dx0, gW, gb, M, drop, row0 * 32));
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -162,6 +164,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32) tail32_fwd_kernel(const float *
                                                                    float *__restrict__ dlog, float *partials) {
   __shared__ __align__(16) float sz[EG_WARPS][EG_TOK][32];
   __shared__ float red[4][EG_WARPS];
+  griddep_wait();
+  griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = lane / 9;                       // 0 hits, 1 velocities, 2 offsets, 3 idle lanes (27..31)
   float wr[32];
@@ -262,8 +266,8 @@ int edge32_tail_fwd(const float *x, const float *gamma, const float *beta, const
                     float *mean, float *rstd, int64_t M, float thres, cudaStream_t st) {
   if (M == 0) return 0;
   { LaunchScope _ls(KC_TC_HEAD, st);
-    tail32_fwd_kernel<<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(x, gamma, beta, Wout, bout, hvo, mean, rstd, M, thres, nullptr, 0.f, 0.f,
-                                                             nullptr, nullptr); }
+    GT_CUDA(launch_pdl(tail32_fwd_kernel, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, x, gamma, beta, Wout, bout, hvo, mean, rstd, M, thres,
+                       (const float *)nullptr, 0.f, 0.f, (float *)nullptr, (float *)nullptr)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -274,8 +278,8 @@ int edge32_tail_fwd_loss(const float *x, const float *gamma, const float *beta, 
   GT_CHECK(M > 0, "empty batch");
   const int blocks = eg_blocks(M);
   { LaunchScope _ls(KC_TC_HEAD, st);
-    tail32_fwd_kernel<<<blocks, EG_WARPS * 32, 0, st>>>(x, gamma, beta, Wout, bout, hvo, mean, rstd, M, -1.f, y, penalty, 1.f / (float)M,
-                                                       dlog, partials); }
+    GT_CUDA(launch_pdl(tail32_fwd_kernel, dim3(blocks), dim3(EG_WARPS * 32), 0, st, x, gamma, beta, Wout, bout, hvo, mean, rstd, M, -1.f, y,
+                       penalty, 1.f / (float)M, dlog, partials)); }
   GT_CUDA(cudaGetLastError());
   return loss_finalize(partials, blocks, M, metrics6, st);
 }
@@ -290,6 +294,8 @@ __global__ void __launch_bounds__(EG_WARPS * 32, 2) tail32_bwd_kernel(const floa
                                                                    int64_t M) {
   __shared__ __align__(16) float sz[EG_WARPS][EG_TOK][32], sd[EG_WARPS][EG_TOK][32];
   __shared__ float sacc[27 * 32 + 32 + 64];
+  griddep_wait();
+  griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = lane / 9;
   // lane c keeps column c of W_out [27][32] (+ a zero row) in registers: read from shared memory it was 28 of the 45 shared-memory
@@ -391,7 +397,8 @@ int edge32_tail_bwd(const float *d_in, const float *hvo, const float *x, const f
                     cudaStream_t st) {
   if (M == 0) return 0;
   { LaunchScope _ls(KC_TC_HEAD, st);
-    tail32_bwd_kernel<<<eg_blocks(M), EG_WARPS * 32, 0, st>>>(d_in, hvo, x, mean, rstd, gamma, beta, Wout, dx, gW, gb, gg, gbe, M); }
+    GT_CUDA(launch_pdl(tail32_bwd_kernel, dim3(eg_blocks(M)), dim3(EG_WARPS * 32), 0, st, d_in, hvo, x, mean, rstd, gamma, beta, Wout, dx, gW, gb,
+                       gg, gbe, M)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -724,6 +724,8 @@ __global__ void loss_partial_kernel(const float *__restrict__ hvo, const float *
 }
 __global__ void loss_final_kernel(const float *__restrict__ partials, int64_t blocks, int64_t M, int V, float *metrics6) {
   __shared__ double red[4][256];
+  griddep_wait();                                      // launch_pdl (common.cuh)
+  griddep_launch();
   double acc[4] = {0, 0, 0, 0};
   for (int64_t b = threadIdx.x; b < blocks; b += blockDim.x)
     for (int q = 0; q < 4; ++q) acc[q] += (double)partials[b * 4 + q];
@@ -746,7 +748,7 @@ __global__ void loss_final_kernel(const float *__restrict__ partials, int64_t bl
 }
 int loss_finalize(const float *partials, int64_t blocks, int64_t M, float *metrics6, cudaStream_t st) {
   { LaunchScope _ls(KC_LOSS, st);
-  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, 9, metrics6); }
+  GT_CUDA(launch_pdl(loss_final_kernel, dim3(1), dim3(256), 0, st, partials, blocks, M, 9, metrics6)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -762,7 +764,7 @@ int loss_fwd_bwd(const float *hvo, const float *y, int64_t n_seq, float penalty,
   else loss_partial_kernel<0><<<(unsigned)blocks, LOSS_ROWS_PER_BLOCK, 0, st>>>(hvo, y, M, n_voices, penalty, d_hvo, grad_scale / (float)M, partials); }
   GT_CUDA(cudaGetLastError());
   { LaunchScope _ls(KC_LOSS, st);
-  loss_final_kernel<<<1, 256, 0, st>>>(partials, blocks, M, n_voices, metrics6); }
+  GT_CUDA(launch_pdl(loss_final_kernel, dim3(1), dim3(256), 0, st, partials, blocks, M, n_voices, metrics6)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -965,19 +967,21 @@ int decode_feedback(const float *hvo_step, float *tok, float *out, int64_t n_seq
 
 // ---- optimizers over the flat vectors ---------------------------------------------------------
 __global__ void sgd_kernel(float *p, const float *__restrict__ g, int64_t n, float lr, float gs) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();                                      // launch_pdl (common.cuh); no early launch_dependents: the layer kernels read
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // parameters before their own wait
   if (i < n) p[i] = p[i] - lr * (g[i] * gs);
 }
 int sgd_step(float *p, const float *g, int64_t n, float lr, float gs, cudaStream_t st) {
   GT_NVTX("groove.optimizer");
   if (n == 0) return 0;
   { LaunchScope _ls(KC_OPT, st);
-  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, lr, gs); }
+  GT_CUDA(launch_pdl(sgd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p, g, n, lr, gs)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
 __global__ void adam_kernel(float *p, const float *__restrict__ g, float *m, float *v, int64_t n, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float gs, const unsigned long long *t_ptr) {
+  griddep_wait();                                      // launch_pdl (common.cuh); no early launch_dependents (see sgd_kernel)
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (t_ptr != nullptr) {                              // graph replay: bias corrections from the device-resident step counter
@@ -1002,7 +1006,7 @@ int adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
   if (step < 1) step = 1;
   double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
   { LaunchScope _ls(KC_OPT, st);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs, t_ptr); }
+  GT_CUDA(launch_pdl(adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gs, t_ptr)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,6 +29,9 @@ __device__ __forceinline__ uint4 pack8(const float *s) {
 }
 
 __global__ void tc_prep_kernel(TcPrepArgs a) {
+  // launch_pdl (common.cuh): the parameters are the optimizer kernel's output.  No early launch_dependents here: the layer kernels
+  // read THESE images before their own griddepcontrol.wait, so whatever follows may only start when this kernel's CTAs have exited
+  griddep_wait();
   const int l = blockIdx.y;
   const int D = a.D, F = a.F, FC = a.FC;
   const TcImg o = tc_img(D, F);
@@ -76,7 +79,7 @@ __global__ void tc_prep_kernel(TcPrepArgs a) {
 int tc_prep_weights(const TcPrepArgs &a, cudaStream_t st) {
   dim3 grid(16, a.n_layers);
   { LaunchScope _ls(KC_TC_PREP, st);
-    tc_prep_kernel<<<grid, 256, 0, st>>>(a); }
+    GT_CUDA(launch_pdl(tc_prep_kernel, grid, dim3(256), 0, st, a)); }
   GT_CUDA(cudaGetLastError());
   return 0;
 }
