@@ -387,6 +387,9 @@ def main():
     ap.add_argument("--infer-chunk", type=int, default=0, help="--mode infer: sequences per chunk of the host-array predict pipeline (e2e); 0 = HostPredictor's default")
     ap.add_argument("--dp-bucket-mb", type=float, default=4.0, help="gradient bucket size of the overlapped all-reduce (N > 1)")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of per-bucket overlap")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: gradient exchange + optimizer as one kernel over NVLink peer memory (p2p; auto = when the ranks can "
+                         "map each other's buffers) or bucketed NCCL all-reduce + optimizer kernel (nccl)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -438,7 +441,7 @@ def main():
         dist.broadcast(model.flat_parameters().detach(), 0)
     opt = FusedAdam(model, 1e-3) if args.optimizer == "adam" else FusedSGD(model, w["lr"])
     dp = DataParallelStep(model, opt, w["pen"], overlap=False if args.no_overlap else None,
-                          bucket_bytes=int(args.dp_bucket_mb * (1 << 20)))
+                          bucket_bytes=int(args.dp_bucket_mb * (1 << 20)), exchange=args.exchange)
 
     xh, yh = synth_batch(w, n, 1234 + rank)
     xh, yh = xh.pin_memory(), yh.pin_memory()
@@ -615,7 +618,10 @@ def main():
         "metric": "train_seq_per_s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(w, args, n, world, precision),
+        "config": dict(workload_config(w, args, n, world, precision),
+                       **({"exchange": ("one kernel: rank-ordered gradient sum over NVLink peer memory + optimizer (csrc/peer_opt.cu)"
+                                        if dp.exchange == "p2p" else "bucketed NCCL all-reduce overlapped with backward + optimizer kernel")}
+                          if world > 1 else {})),
         "step_tflops": fl_step * world * args.steps / (ms / 1e3) / 1e12,
         "roofline": roof,
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4, "d2h_bytes_per_step": 24,

@@ -149,6 +149,25 @@ int gt_sgd_step(float *p, const float *g, int64_t n, float lr, float grad_scale,
 int gt_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Data-parallel exchange + optimizer as ONE kernel over NVLink peer memory (one process per GPU of one node; SURVEY.md 8e: the
+ * gradient sum in front of the optimizer is the path's only exchange step).  gt_peer_alloc cudaMallocs an exchange buffer and
+ * returns its 64-byte cudaIpcMemHandle_t (ship it to the peers by any means, e.g. torch.distributed.all_gather_object);
+ * gt_peer_open maps a peer's buffer (cudaIpcMemLazyEnablePeerAccess); gt_peer_publish copies the rank's flat gradient into its
+ * own buffer at offset_floats (double buffered by step parity by the caller); after a barrier every rank enqueued behind its
+ * publish, gt_*_step_peers reads element i of ALL `world` buffers (exchange_bufs[r] = rank r's buffer as mapped in THIS process,
+ * own buffer included), adds them in rank order (bit-identical on every rank) and applies the update of gt_sgd_step / gt_adam_step;
+ * gsum (may be NULL) receives the summed gradient.  The buffers are the caller's to close / free. */
+int gt_peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64);
+int gt_peer_open(const uint8_t *handle64, void **ptr);
+int gt_peer_close(void *ptr);
+int gt_peer_free(void *ptr);
+int gt_peer_publish(void *exchange, int64_t offset_floats, const float *grads, int64_t n, void *stream);
+int gt_sgd_step_peers(float *p, const void *const *exchange_bufs, int world, int64_t offset_floats, float *gsum, int64_t n,
+                      float lr, float grad_scale, void *stream);
+int gt_adam_step_peers(float *p, const void *const *exchange_bufs, int world, int64_t offset_floats, float *m, float *v,
+                       float *gsum, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                       void *stream);
+
 /* Several consecutive training steps in ONE call over a dataset that is resident on the device (the body of
  * BGT/models/train.py:118-141 for `n_steps` batches of one epoch): step s gathers rows perm[start + s*batch .. + batch) of
  * data_x [S,32,e_src] / data_y [S,32,27] into xbuf / ybuf, runs gt_train_step on them with dropout step counter step0 + s,

@@ -49,6 +49,13 @@ SIGNATURES = {
     "gt_predict_variant": (C.c_int, [_cfgp, _p, _p, _p, _i64, _f, _p, _p, _i64, C.c_int, _p]),
     "gt_sgd_step": (C.c_int, [_p, _p, _i64, _f, _f, _p]),
     "gt_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
+    "gt_peer_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "gt_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gt_peer_close": (C.c_int, [_p]),
+    "gt_peer_free": (C.c_int, [_p]),
+    "gt_peer_publish": (C.c_int, [_p, _i64, _p, _i64, _p]),
+    "gt_sgd_step_peers": (C.c_int, [_p, C.POINTER(C.c_void_p), C.c_int, _i64, _p, _i64, _f, _f, _p]),
+    "gt_adam_step_peers": (C.c_int, [_p, C.POINTER(C.c_void_p), C.c_int, _i64, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
     "gt_graph_train_create": (C.c_int, [_cfgp, _p, _p, _p, _p, _i64, _f, _p, _p, _p, _p, _i64, C.c_int, _f, _p, _p, _u64, _p,
                                         _p, _p, _p, _p, _i64, _p, C.POINTER(C.c_void_p)]),
     "gt_graph_launch": (C.c_int, [_p, C.c_int, _p]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgroove_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["kernels_simt.cu", "edge32.cu", "edge256.cu", "decode32.cu", "attn_mma.cu", "gemm_tc.cu", "runner.cu", "tc_path.cu", "tc_layers.cu", "tc256.cu", "tc256_path.cu", "tc256_bwd.cu"]
+SOURCES = ["kernels_simt.cu", "peer_opt.cu", "edge32.cu", "edge256.cu", "decode32.cu", "attn_mma.cu", "gemm_tc.cu", "runner.cu", "tc_path.cu", "tc_layers.cu", "tc256.cu", "tc256_path.cu", "tc256_bwd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

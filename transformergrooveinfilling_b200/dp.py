@@ -61,6 +61,79 @@ def merge_buckets(ranges: Sequence[Tuple[int, int]], min_floats: int) -> List[Tu
     return [tuple(g) for g in groups]
 
 
+class PeerExchange:
+    """Gradient exchange over NVLink peer memory for one process per GPU on ONE node (csrc/peer_opt.cu): every rank owns an
+    exchange buffer (two halves, alternating by step) that all peers map through CUDA IPC; ``step`` = publish the flat gradient
+    -> barrier (a tiny NCCL all-reduce that also carries the step's six metrics) -> ONE kernel that sums element i over all ranks'
+    buffers in rank order and applies the optimizer.  Setup is collective and agrees across ranks: if any rank cannot allocate
+    or map a buffer, ``ok`` is False everywhere and the caller keeps the NCCL all-reduce."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib, self.group = C, _lib.load(), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = int(n_floats)
+        self.half = (self.n + 63) // 64 * 64                    # floats per half (16-byte aligned offsets)
+        self.device = device
+        self.local = C.c_void_p()
+        self.peers = [None] * self.world
+        self.parity = 0
+        self.bar = torch.zeros(8, dtype=torch.float32, device=device)
+        handle = C.create_string_buffer(64)
+        ok, why = True, ""
+        with torch.cuda.device(device):
+            if self._lib.gt_peer_alloc(2 * self.half * 4, C.byref(self.local), handle) != 0:
+                ok, why = False, self._lib.gt_last_error().decode()
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bool(ok), bytes(handle.raw)), group=group)
+            ok = all(h[0] for h in handles)
+            if ok:
+                for r, (_, hb) in enumerate(handles):
+                    if r == self.rank:
+                        self.peers[r] = self.local.value
+                        continue
+                    q = C.c_void_p()
+                    if self._lib.gt_peer_open(hb, C.byref(q)) != 0:
+                        ok, why = False, self._lib.gt_last_error().decode()
+                        break
+                    self.peers[r] = q.value
+            flags = [None] * self.world
+            dist.all_gather_object(flags, (bool(ok), why), group=group)
+        self.ok = all(f[0] for f in flags)
+        self.why = "; ".join(f[1] for f in flags if f[1])
+        if self.ok:
+            self.bufs = (C.c_void_p * self.world)(*self.peers)
+        else:
+            self.close()
+
+    def publish(self, grad: torch.Tensor):
+        from . import _lib
+        _lib.check(self._lib.gt_peer_publish(self.local, self.parity * self.half, _lib.ptr(grad), self.n,
+                                             _lib.stream_ptr(self.device)), "gt_peer_publish")
+
+    def barrier(self, metrics: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Stream-ordered rendezvous: returns the SUM over ranks of ``metrics`` (6 floats) as a by-product."""
+        self.bar.zero_()
+        if metrics is not None:
+            self.bar[:6].copy_(metrics[:6])
+        dist.all_reduce(self.bar, op=dist.ReduceOp.SUM, group=self.group)
+        return self.bar
+
+    def optimizer_step(self, opt):
+        opt.step_peers(self.bufs, self.world, self.parity * self.half)
+        self.parity ^= 1
+
+    def close(self):
+        for r, q in enumerate(self.peers):
+            if q is not None and r != self.rank:
+                self._lib.gt_peer_close(self._C.c_void_p(q))
+        self.peers = [None] * self.world
+        if self.local:
+            self._lib.gt_peer_free(self.local)
+            self.local = self._C.c_void_p()
+
+
 class DataParallelStep:
     """step(x_local, y_local) = local fused fwd+loss+bwd -> all-reduce(SUM) of the flat gradient ->
     optimizer step with grad_scale = 1/world.
@@ -69,13 +142,17 @@ class DataParallelStep:
     backward is still running: the library records one CUDA event per bucket as backward finishes
     it (include/groove_b200.h: gt_grad_buckets / gt_grad_bucket_wait), and each group's NCCL
     all-reduce is issued on a communication stream that waits only for that event.  ``compute`` /
-    ``bucket_ranges`` / ``wait_bucket`` are injection points for the CPU (gloo) tests."""
+    ``bucket_ranges`` / ``wait_bucket`` are injection points for the CPU (gloo) tests.
+
+    ``exchange='p2p'`` (``'auto'``: whenever the ranks can map each other's buffers and the optimizer is fused) replaces the
+    all-reduce + optimizer pair by PeerExchange: publish -> barrier -> one kernel that sums the gradient over NVLink peer memory
+    in rank order and applies the optimizer.  ``self.exchange`` says which form runs."""
 
     def __init__(self, model, optimizer, hit_loss_penalty: float, group=None,
                  compute: Optional[Callable] = None, comm_stream: Optional["torch.cuda.Stream"] = None,
                  overlap: Optional[bool] = None, bucket_bytes: int = 512 * 1024,
                  bucket_ranges: Optional[Sequence[Tuple[int, int]]] = None,
-                 wait_bucket: Optional[Callable[[int], None]] = None):
+                 wait_bucket: Optional[Callable[[int], None]] = None, exchange: str = "nccl"):
         self.model, self.opt, self.penalty, self.group = model, optimizer, hit_loss_penalty, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -85,6 +162,21 @@ class DataParallelStep:
         self.groups: Optional[List[Tuple[int, int, int]]] = None
         if hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = 1.0 / self.world
+        if exchange not in ("nccl", "p2p", "auto"):
+            raise ValueError("exchange must be 'nccl', 'p2p' or 'auto'")
+        self.peer: Optional[PeerExchange] = None
+        self.exchange = "nccl"
+        if exchange != "nccl" and self.world > 1 and compute is None:
+            if not hasattr(optimizer, "step_peers"):
+                if exchange == "p2p":
+                    raise ValueError("exchange='p2p' needs FusedSGD / FusedAdam (the exchange is part of the optimizer kernel)")
+            else:
+                flat = model.flat_parameters()
+                px = PeerExchange(flat.numel(), flat.device, group)
+                if px.ok:
+                    self.peer, self.exchange, overlap = px, "p2p", False
+                elif exchange == "p2p":
+                    raise RuntimeError("exchange='p2p': the ranks cannot map each other's exchange buffers: " + px.why)
         if overlap is None:
             overlap = self.world > 1 and (compute is None or bucket_ranges is not None)
         if overlap and self.world > 1:
@@ -133,6 +225,15 @@ class DataParallelStep:
         else:
             metrics, _ = self.model.train_step(x_local, y_local, self.penalty)
             grad = self.model.flat_grad()
+        if self.peer is not None:
+            self.peer.publish(grad)
+            summed = self.peer.barrier(metrics if reduce_metrics else None)      # every rank's gradient is published
+            self.peer.optimizer_step(self.opt)
+            if reduce_metrics:
+                m = summed[:6] / self.world
+                m[2] = torch.exp(m[3])
+                return m
+            return metrics
         if self.world > 1:
             if self.groups is not None:
                 self._reduce_overlapped(grad)

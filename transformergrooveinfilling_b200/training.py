@@ -129,6 +129,15 @@ class FusedSGD(_FusedOptimizer):
         _lib.check(lib.gt_sgd_step(_lib.ptr(m._flat), _lib.ptr(g), m._flat.numel(), self._lr(), float(self.grad_scale),
                                    _lib.stream_ptr(m._flat.device)), "gt_sgd_step")
 
+    @torch.no_grad()
+    def step_peers(self, bufs, world: int, offset_floats: int):
+        """The same update with the gradient taken as the rank-ordered SUM over the ``world`` exchange buffers (dp.PeerExchange):
+        gradient exchange + optimizer in one kernel over NVLink peer memory.  ``flat_grad()`` receives the sum."""
+        m = self.model
+        lib = _lib.load()
+        _lib.check(lib.gt_sgd_step_peers(_lib.ptr(m._flat), bufs, world, offset_floats, _lib.ptr(m._flat.grad), m._flat.numel(),
+                                         self._lr(), float(self.grad_scale), _lib.stream_ptr(m._flat.device)), "gt_sgd_step_peers")
+
     def state_dict(self):
         return {"state": {}, "param_groups": self._packed_groups()}
 
@@ -164,6 +173,20 @@ class FusedAdam(_FusedOptimizer):
         _lib.check(lib.gt_adam_step(_lib.ptr(m._flat), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), m._flat.numel(),
                                     self._lr(), float(b1), float(b2), float(self.param_groups[0]["eps"]), self._t,
                                     float(self.grad_scale), _lib.stream_ptr(m._flat.device)), "gt_adam_step")
+
+    @torch.no_grad()
+    def step_peers(self, bufs, world: int, offset_floats: int):
+        """See FusedSGD.step_peers."""
+        m = self.model
+        if self._m.device != m._flat.device:
+            self._m, self._v = self._m.to(m._flat.device), self._v.to(m._flat.device)
+        self._t += 1
+        b1, b2 = self.param_groups[0]["betas"]
+        lib = _lib.load()
+        _lib.check(lib.gt_adam_step_peers(_lib.ptr(m._flat), bufs, world, offset_floats, _lib.ptr(self._m), _lib.ptr(self._v),
+                                          _lib.ptr(m._flat.grad), m._flat.numel(), self._lr(), float(b1), float(b2),
+                                          float(self.param_groups[0]["eps"]), self._t, float(self.grad_scale),
+                                          _lib.stream_ptr(m._flat.device)), "gt_adam_step_peers")
 
     def state_dict(self):
         state = {}
