@@ -8,7 +8,8 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
  *   - the caller (PyTorch) owns all buffers; the library borrows them for the duration of the
- *     enqueue and keeps no reference;
+ *     enqueue and keeps no reference (gt_peer_alloc / gt_peer_free are the one explicit allocation pair: an IPC
+ *     handle names a whole cudaMalloc allocation);
  *   - every call enqueues asynchronously on the cudaStream_t passed as `stream` (void* here);
  *   - return value 0 = success; non-zero = error, message via gt_last_error() (thread-local);
  *     no C++ exception crosses this boundary; shape / alignment violations are rejected before

@@ -297,3 +297,18 @@ def test_calculate_loss_rejects_other_loss_functions():
         calculate_loss((z, z, z), torch.zeros(2, 32, 27), torch.nn.BCEWithLogitsLoss(), torch.nn.MSELoss(reduction="none"), 1.0)
     with pytest.raises(ValueError, match="MSELoss"):
         calculate_loss((z, z, z), torch.zeros(2, 32, 27), None, torch.nn.L1Loss(reduction="none"), 1.0)
+
+
+def test_data_parallel_exchange_argument_is_validated():
+    """exchange = 'nccl' | 'p2p' | 'auto': unknown values and p2p with an injected compute are refused before anything is set up; a
+    single process (world 1) never builds a peer exchange."""
+    from transformergrooveinfilling_b200.dp import DataParallelStep
+    from transformergrooveinfilling_b200 import FusedSGD, GrooveTransformerEncoder
+    m = GrooveTransformerEncoder(32, 16, 27, 4, 64, 0.1, 1, 32, "cpu")
+    opt = FusedSGD(m, 0.1)
+    with pytest.raises(ValueError, match="exchange"):
+        DataParallelStep(m, opt, 0.5, exchange="rdma")
+    with pytest.raises(ValueError, match="injected compute"):
+        DataParallelStep(m, opt, 0.5, compute=lambda x, y: (None, None), exchange="p2p")
+    dp = DataParallelStep(m, opt, 0.5, exchange="auto")
+    assert dp.world == 1 and dp.peer is None and dp.exchange == "nccl" and hasattr(opt, "step_peers")

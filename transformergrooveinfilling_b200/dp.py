@@ -166,6 +166,8 @@ class DataParallelStep:
             raise ValueError("exchange must be 'nccl', 'p2p' or 'auto'")
         self.peer: Optional[PeerExchange] = None
         self.exchange = "nccl"
+        if exchange == "p2p" and compute is not None:
+            raise ValueError("exchange='p2p' runs the library's own step (no injected compute)")
         if exchange != "nccl" and self.world > 1 and compute is None:
             if not hasattr(optimizer, "step_peers"):
                 if exchange == "p2p":
