@@ -312,3 +312,13 @@ def test_data_parallel_exchange_argument_is_validated():
         DataParallelStep(m, opt, 0.5, compute=lambda x, y: (None, None), exchange="p2p")
     dp = DataParallelStep(m, opt, 0.5, exchange="auto")
     assert dp.world == 1 and dp.peer is None and dp.exchange == "nccl" and hasattr(opt, "step_peers")
+    # the C entry points refuse null / oversized arguments before any launch
+    from transformergrooveinfilling_b200 import _lib
+    lib = _lib.load()
+    bufs = (C.c_void_p * 2)(None, None)
+    assert lib.gt_sgd_step_peers(None, bufs, 2, 0, None, 4, 0.1, 1.0, None) != 0
+    assert lib.gt_adam_step_peers(C.c_void_p(256), bufs, 2, 0, C.c_void_p(256), C.c_void_p(256), None, 4, 0.1, 0.9, 0.999, 1e-8, 1, 1.0, None) != 0
+    assert b"exchange buffer" in lib.gt_last_error()
+    assert lib.gt_adam_step_peers(C.c_void_p(256), bufs, 17, 0, C.c_void_p(256), C.c_void_p(256), None, 4, 0.1, 0.9, 0.999, 1e-8, 1, 1.0, None) != 0
+    assert b"world size" in lib.gt_last_error()
+    assert lib.gt_peer_publish(None, 0, None, 4, None) != 0 and lib.gt_peer_open(None, None) != 0
