@@ -152,7 +152,7 @@ class DataParallelStep:
                  compute: Optional[Callable] = None, comm_stream: Optional["torch.cuda.Stream"] = None,
                  overlap: Optional[bool] = None, bucket_bytes: int = 512 * 1024,
                  bucket_ranges: Optional[Sequence[Tuple[int, int]]] = None,
-                 wait_bucket: Optional[Callable[[int], None]] = None, exchange: str = "nccl"):
+                 wait_bucket: Optional[Callable[[int], None]] = None, exchange: str = "nccl", peer=None):
         self.model, self.opt, self.penalty, self.group = model, optimizer, hit_loss_penalty, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -166,6 +166,8 @@ class DataParallelStep:
             raise ValueError("exchange must be 'nccl', 'p2p' or 'auto'")
         self.peer: Optional[PeerExchange] = None
         self.exchange = "nccl"
+        if peer is not None:                               # injection point of the CPU (gloo) tests: publish / barrier / optimizer_step
+            self.peer, self.exchange, overlap, exchange = peer, "p2p", False, "nccl"
         if exchange == "p2p" and compute is not None:
             raise ValueError("exchange='p2p' runs the library's own step (no injected compute)")
         if exchange != "nccl" and self.world > 1 and compute is None:
